@@ -1,0 +1,170 @@
+/*
+ * kpeg_cuda.h -- C ABI of the B200 (sm_100a) baseline-JPEG decode hot path.
+ *
+ * libKPEG has no plugin / FFI interface of its own: its hot path is reachable only through the
+ * C++ class kpeg::JPEGDecoder (reference include/Decoder.hpp:26-128) and the `kpeg` CLI
+ * (reference main.cpp:54-79).  This header is the thin boundary the drop-in JPEGDecoder in
+ * libkpeg_b200/host/ calls; every entry point names the reference member(s) whose work it
+ * replaces.  Plain pointers and sizes only, no C++ or torch types.  All file:line citations are
+ * relative to /root/reference.
+ *
+ * There is NO CPU fallback behind this interface: every decode call runs the CUDA kernels in
+ * libkpeg_b200/csrc/ and fails with KPEG_ERR_CUDA when no device is usable.
+ */
+#ifndef KPEG_CUDA_H
+#define KPEG_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return codes ------------------------------------------------------------------------ */
+#define KPEG_OK 0
+#define KPEG_ERR_FORMAT (-1)      /* malformed container      -> JPEGDecoder::ResultCode::ERROR     (Decoder.cpp:126-132) */
+#define KPEG_ERR_UNSUPPORTED (-2) /* SOF1/SOF2/subsampling... -> JPEGDecoder::ResultCode::TERMINATE (Decoder.cpp:65-66,351-356) */
+#define KPEG_ERR_STREAM (-3)      /* corrupt entropy-coded data (the reference hangs / reads out of bounds, Decoder.cpp:706-803) */
+#define KPEG_ERR_NOMEM (-4)
+#define KPEG_ERR_CUDA (-5)        /* no device / CUDA runtime failure (see kpeg_cuda_last_error) */
+#define KPEG_ERR_ARG (-6)
+#define KPEG_ERR_NOT_CONVERGED (-7) /* internal: speculative decode needed more fix-up rounds (retried automatically) */
+
+/* ---- plan flags -------------------------------------------------------------------------- */
+/* Reproduce MCU.cpp:97-104: a block whose DC *difference* is 0 loses its AC coefficients
+ * (SURVEY F1).  ON for bit-exact parity with the reference; OFF for ITU-T T.81 behaviour. */
+#define KPEG_FLAG_REF_PARITY 1u
+
+/* One Huffman table as it appears in a DHT segment (Types.hpp:116, Decoder.cpp:366-459). */
+typedef struct kpeg_huff_spec {
+    uint8_t counts[16];   /* number of codes of length 1..16 */
+    uint8_t symbols[256]; /* symbols in order of increasing code length */
+} kpeg_huff_spec;
+
+/*
+ * Everything the kernels need to know about one image, produced by the host-side container
+ * parse (replaces the state JPEGDecoder accumulates in parseQuantizationTable / parseSOF0Segment /
+ * parseHuffmanTable / parseSOSSegment, Decoder.cpp:230-530).  POD; caller-owned.
+ */
+typedef struct kpeg_plan {
+    uint16_t width, height;     /* SOF0 X, Y (Decoder.cpp:301-364) */
+    uint8_t ncomp;              /* 1 (T.81 extension) or 3; sampling is always 1x1 */
+    uint8_t comp_tq[3];         /* quantisation-table id per component */
+    uint8_t comp_td[3];         /* DC Huffman table id per component   */
+    uint8_t comp_ta[3];         /* AC Huffman table id per component   */
+    uint16_t restart_interval;  /* DRI value in MCUs, 0 = none (T.81 extension) */
+    uint32_t flags;             /* KPEG_FLAG_* */
+    uint8_t qt_present[4];
+    uint8_t ht_present[2][4];
+    uint16_t qt[4][64];         /* zig-zag (file) order, as Decoder.cpp:230-299 keeps them */
+    kpeg_huff_spec ht[2][4];    /* [class 0=DC,1=AC][id] */
+} kpeg_plan;
+
+/* Per-decode statistics.  Stage times are filled only while profiling is enabled
+ * (kpeg_cuda_set_profiling); they are CUDA-event times on the decode stream, in milliseconds. */
+typedef struct kpeg_stats {
+    uint32_t width, height, ncomp;
+    uint64_t scan_bytes;        /* stuffed entropy-coded bytes handed in                  */
+    uint64_t unstuffed_bytes;   /* after FF00 / RSTn removal                              */
+    uint32_t segments;          /* restart intervals found (1 when there is no DRI)       */
+    uint32_t subsequences;      /* speculative decode units                               */
+    uint32_t sync_rounds;       /* fix-up rounds that ran until the relay reached a fixed point */
+    uint32_t exact_samples;     /* IDCT samples re-evaluated on the exact (reference-order) path */
+    float ms_h2d, ms_unstuff, ms_entropy, ms_dc_scan, ms_idct, ms_d2h, ms_total;
+    uint32_t kernel_launches;   /* kernels launched for this decode */
+} kpeg_stats;
+
+typedef struct kpeg_ctx kpeg_ctx;
+
+/* ---- host-side container parse (no CUDA) --------------------------------------------------
+ * Replaces JPEGDecoder::decodeImageFile's marker loop + parseSegmentInfo + the parse* members
+ * (Decoder.cpp:53-75,90-152,164-530,579-619).  T.81-correct superset of what the reference
+ * accepts: unknown APPn/COM are skipped by length, DRI and Nf==1 are honoured.  On success
+ * [*scan_off, *scan_off + *scan_len) is the entropy-coded segment (what scanImageData,
+ * Decoder.cpp:532-577, would read: everything after the SOS header up to the EOI marker). */
+int kpeg_parse_jfif(const uint8_t *file, size_t len, kpeg_plan *plan, size_t *scan_off, size_t *scan_len);
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* One context per (thread, device): owns a CUDA stream, device scratch and pinned staging,
+ * all grown on demand and reused across decodes.  Not thread-safe; use one context per thread. */
+int kpeg_cuda_create(int device, kpeg_ctx **out);
+void kpeg_cuda_destroy(kpeg_ctx *ctx);
+const char *kpeg_cuda_last_error(const kpeg_ctx *ctx); /* never NULL */
+int kpeg_cuda_device_count(void);
+int kpeg_cuda_set_profiling(kpeg_ctx *ctx, int on);
+/* Tuning knobs of the speculative entropy decode (0 = leave unchanged): bits per subsequence
+ * (multiple of 32, 64..65536; default 512 or $KPEG_SUB_BITS) and the number of relay rounds issued
+ * up front (>= 2; default 4 or $KPEG_RELAY_ROUNDS; more are added automatically when needed). */
+int kpeg_cuda_set_tuning(kpeg_ctx *ctx, int sub_bits, int relay_rounds);
+/* The CUDA stream (cudaStream_t) all of this context's work is issued on. */
+void *kpeg_cuda_stream(kpeg_ctx *ctx);
+
+/* Pinned host memory for scan / pixel buffers (plain malloc'd memory also works, slower). */
+void *kpeg_cuda_host_alloc(size_t bytes);
+void kpeg_cuda_host_free(void *p);
+/* Device memory helpers for callers that keep data resident (bench, pipelines). */
+void *kpeg_cuda_device_alloc(kpeg_ctx *ctx, size_t bytes);
+void kpeg_cuda_device_free(kpeg_ctx *ctx, void *p);
+int kpeg_cuda_memcpy_h2d(kpeg_ctx *ctx, void *dst, const void *src, size_t bytes);
+int kpeg_cuda_memcpy_d2h(kpeg_ctx *ctx, void *dst, const void *src, size_t bytes);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+/*
+ * Decode one entropy-coded segment to pixels.  Replaces JPEGDecoder::byteStuffScanData,
+ * decodeScanData (Decoder.cpp:621-855), MCU::constructMCU / computeIDCT / performLevelShift /
+ * convertYCbCrToRGB (MCU.cpp:64-279) and Image::createImageFromMCUs (Image.cpp:20-86).
+ *
+ *  scan, scan_len : HOST pointer to the stuffed entropy-coded bytes (may contain RSTn markers).
+ *  pixels_out     : HOST buffer of width*height*ncomp bytes; interleaved R,G,B rows top-down for
+ *                   ncomp==3 (the payload Image::dumpRawData writes, Image.cpp:129-135), one gray
+ *                   byte per pixel for ncomp==1.
+ * Synchronous: returns after the pixels are in pixels_out.
+ */
+int kpeg_cuda_decode(kpeg_ctx *ctx, const kpeg_plan *plan, const uint8_t *scan, size_t scan_len,
+                     uint8_t *pixels_out, kpeg_stats *stats);
+
+/* Same, but `d_scan` and `d_pixels_out` are DEVICE pointers on the context's device; work is
+ * enqueued on the context's stream and the call returns after the stream has drained and the
+ * device-side status word has been checked. */
+int kpeg_cuda_decode_device(kpeg_ctx *ctx, const kpeg_plan *plan, const uint8_t *d_scan, size_t scan_len,
+                            uint8_t *d_pixels_out, kpeg_stats *stats);
+
+/*
+ * Batch of n images that share ONE plan (same dimensions, tables and restart interval -- the
+ * case of BASELINE.json configs 4 and of repeated frames).  The scans are decoded as one
+ * concatenated stream whose image boundaries are treated like restart boundaries, so the whole
+ * batch costs one kernel sequence.  Host-pointer variant copies in/out through pinned staging.
+ */
+int kpeg_cuda_decode_batch(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *const *scans,
+                           const size_t *scan_lens, uint8_t *const *pixels_out, kpeg_stats *stats);
+/* Device-resident batch: d_scans is ONE device buffer holding the n scans back to back,
+ * scan_offsets[n+1] (host array) delimit them; d_pixels_out receives n images back to back. */
+int kpeg_cuda_decode_batch_device(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *d_scans,
+                                  const uint64_t *scan_offsets, uint8_t *d_pixels_out, kpeg_stats *stats);
+/* "Packed" batch stream = the n stuffed scans back to back, each FOLLOWED by one 2-byte RSTn marker
+ * (FF D0+(i&7)).  kpeg_batch_pack builds it on the host; the *_packed_device entry decodes such a
+ * stream that is already resident in device memory (no copies at all inside the call). */
+size_t kpeg_batch_packed_size(int n, const size_t *scan_lens);
+int kpeg_batch_pack(int n, const uint8_t *const *scans, const size_t *scan_lens, uint8_t *dst, size_t cap);
+int kpeg_cuda_decode_batch_packed_device(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *d_packed,
+                                         size_t packed_len, uint8_t *d_pixels_out, kpeg_stats *stats);
+
+/* Whole-file convenience used by the JPEGDecoder drop-in: parse + decode.  pixels_out must hold
+ * width*height*ncomp bytes (query with kpeg_parse_jfif first) -- cap is checked. */
+int kpeg_cuda_decode_file(kpeg_ctx *ctx, const uint8_t *file, size_t len, uint32_t flags, uint8_t *pixels_out,
+                          size_t cap, kpeg_plan *plan_out, kpeg_stats *stats);
+
+/* Parity hook: the quantised coefficients of the LAST decode on this context, as the reference
+ * holds them transiently inside MCU::constructMCU (MCU.cpp:93-108): [block][64] int16, blocks
+ * MCU-interleaved (Y,Cb,Cr per MCU), zig-zag order, DC prediction already integrated.
+ * `cap` is in int16 elements. */
+int kpeg_cuda_read_coefficients(kpeg_ctx *ctx, int16_t *out, size_t cap);
+
+/* Exact bytes of the PPM header Image::dumpRawData writes (Image.cpp:124-127); returns length. */
+int kpeg_ppm_header(int width, int height, char *buf, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,233 @@
+// idct_core.h -- reconstruction arithmetic of the B200 decode path (host + device inline).
+//
+// Replaces MCU::constructMCU's dequantise / de-zigzag, MCU::computeIDCT, performLevelShift and
+// convertYCbCrToRGB (reference src/MCU.cpp:110-120, 172-216, 218-245, 247-279).
+//
+// Parity strategy.  The reference evaluates the 2-D IDCT as a 64-term sum with a
+// *float* accumulator and *double* products, then rounds half away from zero.  About 0.7 % of all
+// samples of a natural image are exact x.5 ties in real arithmetic and the reference resolves them
+// by its own rounding noise, so no "accurate" IDCT reproduces its integers.  We therefore run
+//   (1) a fast separable fp32 IDCT (AAN factorisation, 5 multiplies + 29 adds per 8 points) and
+//       accept its rounding wherever the value is provably further from a tie than the combined
+//       error bound of both evaluations, and
+//   (2) for the few samples inside that band, the reference's own operation sequence
+//       (exact_sample below: same operand types, same order, no FMA contraction),
+// which makes the integer samples -- and hence the RGB bytes -- identical to the reference's.
+// The colour conversion uses the same two-tier scheme (fp32 with a provable margin, the
+// reference's double expression otherwise).
+#ifndef KPEG_IDCT_CORE_H
+#define KPEG_IDCT_CORE_H
+
+#include <math.h>
+
+#include "kpeg_common.h"
+
+namespace kpeg {
+
+// ---- explicitly rounded primitives (never contracted into FMAs) ------------------------------
+KPEG_HD float mul_f32(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+KPEG_HD double mul_f64(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+KPEG_HD double add_f64(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+KPEG_HD double sub_f64(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+
+// zig-zag index -> natural (row*8+col) index; same map as Transform.cpp:5-27
+// (zzOrderToMatIndices), produced by walking the anti-diagonals.  constexpr so that fully
+// unrolled kernels turn it into register renaming.
+KPEG_HD constexpr int zigzag_to_natural(int i)
+{
+    int idx = 0;
+    for (int d = 0; d < 15; ++d) {
+        const int lo = d < 8 ? 0 : d - 7, hi = d < 8 ? d : 7;
+        for (int k = lo; k <= hi; ++k) {
+            const int r = (d & 1) ? k : (hi + lo - k);
+            if (idx == i)
+                return r * 8 + (d - r);
+            ++idx;
+        }
+    }
+    return 63;
+}
+
+struct ZigZagTables {
+    unsigned char zz2nat[64];
+    unsigned char nat2zz[64];
+};
+KPEG_HD constexpr ZigZagTables make_zigzag_tables()
+{
+    ZigZagTables t{};
+    for (int i = 0; i < 64; ++i) {
+        t.zz2nat[i] = (unsigned char)zigzag_to_natural(i);
+    }
+    for (int i = 0; i < 64; ++i)
+        t.nat2zz[t.zz2nat[i]] = (unsigned char)i;
+    return t;
+}
+
+// AAN prescale factors: s[0] = 1, s[k] = sqrt(2) * cos(k*pi/16).
+inline double aan_scale(int k)
+{
+    const double s[8] = {1.0, 1.387039845322148, 1.306562964876377, 1.175875602419359,
+                         1.0, 0.785694958387102, 0.541196100146197, 0.275899379282943};
+    return s[k];
+}
+
+// One 8-point AAN inverse DCT on prescaled inputs, in place.
+KPEG_HD void idct8_aan(float &v0, float &v1, float &v2, float &v3, float &v4, float &v5, float &v6, float &v7)
+{
+    // even part
+    const float t10 = v0 + v4, t11 = v0 - v4;
+    const float t13 = v2 + v6;
+    const float t12 = (v2 - v6) * 1.414213562373095f - t13;
+    const float e0 = t10 + t13, e3 = t10 - t13, e1 = t11 + t12, e2 = t11 - t12;
+    // odd part
+    const float z13 = v5 + v3, z10 = v5 - v3, z11 = v1 + v7, z12 = v1 - v7;
+    const float o7 = z11 + z13;
+    const float t21 = (z11 - z13) * 1.414213562373095f;
+    const float z5 = (z10 + z12) * 1.847759065022573f;
+    const float t20 = z5 - z12 * 1.082392200292394f;
+    const float t22 = z5 - z10 * 2.613125929752753f;
+    const float o6 = t22 - o7;
+    const float o5 = t21 - o6;
+    const float o4 = t20 - o5;
+    v0 = e0 + o7;
+    v7 = e0 - o7;
+    v1 = e1 + o6;
+    v6 = e1 - o6;
+    v2 = e2 + o5;
+    v5 = e2 - o5;
+    v3 = e3 + o4;
+    v4 = e3 - o4;
+}
+
+// Fast 2-D IDCT of one block held as 64 prescaled floats in NATURAL order (f[row*8+col]);
+// result overwrites f: f[row*8+col] = sample before the +128 level shift.
+KPEG_HD void idct8x8_fast(float f[64])
+{
+#pragma unroll
+    for (int c = 0; c < 8; ++c) // columns
+        idct8_aan(f[c], f[8 + c], f[16 + c], f[24 + c], f[32 + c], f[40 + c], f[48 + c], f[56 + c]);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) // rows
+        idct8_aan(f[8 * r], f[8 * r + 1], f[8 * r + 2], f[8 * r + 3], f[8 * r + 4], f[8 * r + 5], f[8 * r + 6],
+                  f[8 * r + 7]);
+}
+
+// |fast - reference| <= TIE_REL * A + TIE_ABS with A = sum |dequantised coefficient| (derivation in
+// DESIGN.md "K3 rounding"; margin checked by tests/test_idct_core.py).  Because the 2-D DCT
+// basis is orthonormal, A <= 8 * sqrt(sum over the 64 outputs of y^2); the kernel uses that
+// energy, which costs one FMA per sample.
+constexpr float TIE_REL = 1.5e-6f;
+constexpr float TIE_ABS = 2.0e-5f;
+
+KPEG_HD float tie_band(float energy) { return TIE_REL * 8.0f * sqrtf(energy) + TIE_ABS; }
+
+// round-half-away-from-zero of a float, as roundl() does on the promoted value (MCU.cpp:228).
+KPEG_HD int round_half_away(float out)
+{
+    const float a = fabsf(out);
+    float r = floorf(a);
+    if (a - r >= 0.5f)
+        r += 1.0f;
+    const int ri = (int)r;
+    return out < 0.0f ? -ri : ri;
+}
+
+// The reference's own evaluation of one output sample (row x, column y) of one block:
+// src/MCU.cpp:178-199 + :228.  coef_at(i) = quantised coefficient at zig-zag index i (DC already
+// integrated), q = quantiser in zig-zag order.  Returns the UNSHIFTED rounded sample
+// (the reference then adds 128).  Terms with a zero coefficient add +-0.0 to the float
+// accumulator, which leaves it unchanged, so they are skipped.
+template <class CoefAt>
+KPEG_HD int exact_sample(const CoefAt &coef_at, const int32_t *q, const double (*cosd)[8], const float (*cc)[8],
+                         const unsigned char *nat2zz, int x, int y)
+{
+    float sum = 0.0f;
+    for (int nat = 0; nat < 64; ++nat) { // u outer, v inner == ascending natural index (MCU.cpp:184-187)
+        const int zi = nat2zz[nat];
+        const int cq = coef_at(zi);
+        if (cq == 0)
+            continue;
+        const int u = nat >> 3, v = nat & 7;
+        const int F = cq * q[zi];                      // MCU.cpp:110-112 (dequantise), :115-120 (de-zigzag)
+        const float t = mul_f32(cc[u][v], (float)F);   // Cu * Cv * block : float
+        const double d = mul_f64(mul_f64((double)t, cosd[x][u]), cosd[y][v]);
+        sum = (float)add_f64((double)sum, d);          // float accumulator, rounded every term
+    }
+    const float out = (float)mul_f64(0.25, (double)sum); // MCU.cpp:198
+    return round_half_away(out);
+}
+
+// ---- colour ------------------------------------------------------------------------------------
+// MCU.cpp:255-265 on UNSHIFTED samples y, cb, cr (reference value = sample + 128):
+//   R = floor(Y + 1.402 (Cr-128)), G = floor(Y - 0.344136 (Cb-128) - 0.714136 (Cr-128)),
+//   B = floor(Y + 1.772 (Cb-128)), all in double, then clamped to [0,255].
+KPEG_HD void ycc_to_rgb_exact(int y, int cb, int cr, int &R, int &G, int &B)
+{
+    const double Y = (double)(y + 128), db = (double)cb, dr = (double)cr;
+    const double r = add_f64(Y, mul_f64(1.402, dr));
+    const double g = sub_f64(sub_f64(Y, mul_f64(0.344136, db)), mul_f64(0.714136, dr));
+    const double b = add_f64(Y, mul_f64(1.772, db));
+    R = (int)floor(r);
+    G = (int)floor(g);
+    B = (int)floor(b);
+    R = R < 0 ? 0 : (R > 255 ? 255 : R);
+    G = G < 0 ? 0 : (G > 255 ? 255 : G);
+    B = B < 0 ? 0 : (B > 255 ? 255 : B);
+}
+
+// fp32 evaluation, valid when |y|,|cb|,|cr| <= COLOUR_FAST_RANGE:
+//  * 1.402 d = 701 d / 500 and 1.772 d = 443 d / 250 are either integers or at least 0.002 away
+//    from one; with the +0.001 bias and < 5e-4 of fp32 error the floor cannot flip, and for the
+//    integer case the double expression of the reference yields that integer too (checked
+//    exhaustively by tests/test_idct_core.py);
+//  * G's fraction is a multiple of 8e-6: if the fp32 value is closer than COLOUR_G_BAND to an
+//    integer the caller must use ycc_to_rgb_exact (returns false).
+constexpr float COLOUR_FAST_RANGE = 2000.0f;
+constexpr float COLOUR_G_BAND = 1.0e-3f;
+
+KPEG_HD bool ycc_to_rgb_fast(float y, float cb, float cr, float &R, float &G, float &B)
+{
+    const float yc = y + 128.001f; // level shift + bias
+    const float r = fmaf(1.402f, cr, yc);
+    const float b = fmaf(1.772f, cb, yc);
+    const float g = fmaf(-0.714136f, cr, fmaf(-0.344136f, cb, y + 128.0f));
+    const float gf = floorf(g);
+    const float gd = g - gf;
+    const float m = fmaxf(fmaxf(fabsf(y), fabsf(cb)), fabsf(cr));
+    const bool ok = (gd > COLOUR_G_BAND) && (gd < 1.0f - COLOUR_G_BAND) && (m <= COLOUR_FAST_RANGE);
+    R = fminf(fmaxf(floorf(r), 0.0f), 255.0f);
+    G = fminf(fmaxf(gf, 0.0f), 255.0f);
+    B = fminf(fmaxf(floorf(b), 0.0f), 255.0f);
+    return ok;
+}
+
+} // namespace kpeg
+#endif

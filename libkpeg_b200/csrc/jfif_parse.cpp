@@ -1,0 +1,201 @@
+// jfif_parse.cpp -- host-side container parse of the drop-in (no CUDA).
+//
+// Produces the POD kpeg_plan the kernels consume.  It replaces the marker loop of
+// JPEGDecoder::decodeImageFile and the parse* members (reference src/Decoder.cpp:53-75, 90-152,
+// 164-530, 579-619) and is a T.81-correct superset of what they accept:
+// segments are skipped by their length field, so APPn / COM / DRI are fine where the reference
+// stops with "[ FATAL ] Invalid JFIF file"; SOF / SOS table selectors are honoured (the reference
+// hard-wires Y -> 0, Cb/Cr -> 1, Decoder.cpp:704, MCU.cpp:110, which is what every file it decodes
+// correctly uses); Nf == 1 is accepted.  Unsupported codings map to KPEG_ERR_UNSUPPORTED
+// (reference: ResultCode::TERMINATE), malformed data to KPEG_ERR_FORMAT (ResultCode::ERROR).
+#include <stdio.h>
+#include <string.h>
+
+#include "kpeg_cuda.h"
+
+namespace {
+
+inline unsigned be16(const uint8_t *p) { return (unsigned)((p[0] << 8) | p[1]); }
+
+// End of the entropy-coded segment that starts at `s`: the first marker that is neither a stuffed
+// FF00, an RSTn nor a fill byte.  scanImageData (Decoder.cpp:532-577) stops at FF D9 only; both
+// agree on well-formed single-scan files.
+size_t find_scan_end(const uint8_t *f, size_t n, size_t s)
+{
+    // Fast path: a baseline single-scan file ends "... <entropy data> FF D9".  The kernels flag any
+    // other marker they meet inside the data (ST_BAD_MARKER), so trusting the tail is safe.
+    if (n >= s + 2 && f[n - 2] == 0xFF && f[n - 1] == 0xD9)
+        return n - 2;
+    size_t e = s;
+    while (e + 1 < n) {
+        const uint8_t *q = (const uint8_t *)memchr(f + e, 0xFF, n - 1 - e);
+        if (!q)
+            return n;
+        e = (size_t)(q - f);
+        const uint8_t b = f[e + 1];
+        if (b == 0x00 || (b >= 0xD0 && b <= 0xD7)) {
+            e += 2;
+            continue;
+        }
+        if (b == 0xFF) {
+            e += 1;
+            continue;
+        }
+        return e;
+    }
+    return n;
+}
+
+} // namespace
+
+extern "C" int kpeg_parse_jfif(const uint8_t *f, size_t n, kpeg_plan *pl, size_t *scan_off, size_t *scan_len)
+{
+    if (!f || !pl || !scan_off || !scan_len)
+        return KPEG_ERR_ARG;
+    memset(pl, 0, sizeof *pl);
+    if (n < 4 || f[0] != 0xFF || f[1] != 0xD8)
+        return KPEG_ERR_FORMAT; // no SOI
+    size_t i = 2;
+    bool have_frame = false;
+    uint8_t comp_id[3] = {0, 0, 0};
+    for (;;) {
+        if (i + 2 > n)
+            return KPEG_ERR_FORMAT;
+        if (f[i] != 0xFF)
+            return KPEG_ERR_FORMAT; // Decoder.cpp:126-132
+        while (i + 1 < n && f[i + 1] == 0xFF)
+            ++i; // fill bytes before a marker (T.81 B.1.1.2)
+        if (i + 2 > n)
+            return KPEG_ERR_FORMAT;
+        const unsigned marker = f[i + 1];
+        i += 2;
+        if (marker == 0xD8 || marker == 0x01 || (marker >= 0xD0 && marker <= 0xD7))
+            continue; // stand-alone markers
+        if (marker == 0xD9)
+            return KPEG_ERR_FORMAT; // EOI before any scan
+        if (i + 2 > n)
+            return KPEG_ERR_FORMAT;
+        const unsigned L = be16(f + i);
+        if (L < 2 || i + L > n)
+            return KPEG_ERR_FORMAT;
+        const uint8_t *p = f + i + 2;
+        const unsigned plen = L - 2;
+        switch (marker) {
+        case 0xC0: { // SOF0 -- parseSOF0Segment, Decoder.cpp:301-364
+            if (plen < 6)
+                return KPEG_ERR_FORMAT;
+            if (p[0] != 8)
+                return KPEG_ERR_UNSUPPORTED;
+            const unsigned H = be16(p + 1), W = be16(p + 3), nf = p[5];
+            if (nf != 1 && nf != 3)
+                return KPEG_ERR_UNSUPPORTED;
+            if (plen < 6 + 3 * nf)
+                return KPEG_ERR_FORMAT;
+            if (W == 0 || H == 0)
+                return KPEG_ERR_UNSUPPORTED; // DNL-defined height is not baseline-decodable here
+            for (unsigned c = 0; c < nf; ++c) {
+                comp_id[c] = p[6 + 3 * c];
+                // "Chroma subsampling not yet supported!" (Decoder.cpp:351-356).  A single-component
+                // frame is always decoded 1x1 whatever H,V it declares (T.81 A.2.2).
+                if (nf == 3 && p[7 + 3 * c] != 0x11)
+                    return KPEG_ERR_UNSUPPORTED;
+                if (p[8 + 3 * c] > 3)
+                    return KPEG_ERR_FORMAT;
+                pl->comp_tq[c] = p[8 + 3 * c];
+            }
+            pl->width = (uint16_t)W;
+            pl->height = (uint16_t)H;
+            pl->ncomp = (uint8_t)nf;
+            have_frame = true;
+            break;
+        }
+        case 0xC1: case 0xC2: case 0xC3: case 0xC5: case 0xC6: case 0xC7:
+        case 0xC9: case 0xCA: case 0xCB: case 0xCD: case 0xCE: case 0xCF:
+            return KPEG_ERR_UNSUPPORTED; // Decoder.cpp:65-66 (SOF1, SOF2) and the other non-baseline frames
+        case 0xDB: { // DQT -- parseQuantizationTable, Decoder.cpp:230-299 (8-bit tables, zig-zag order)
+            unsigned k = 0;
+            while (k < plen) {
+                const unsigned pq = p[k] >> 4, tq = p[k] & 15u;
+                if (tq > 3)
+                    return KPEG_ERR_FORMAT;
+                if (pq != 0)
+                    return KPEG_ERR_UNSUPPORTED; // 16-bit tables are not baseline
+                if (k + 65 > plen)
+                    return KPEG_ERR_FORMAT;
+                for (int q = 0; q < 64; ++q)
+                    pl->qt[tq][q] = p[k + 1 + q];
+                pl->qt_present[tq] = 1;
+                k += 65;
+            }
+            break;
+        }
+        case 0xC4: { // DHT -- parseHuffmanTable, Decoder.cpp:366-459
+            unsigned k = 0;
+            while (k < plen) {
+                if (k + 17 > plen)
+                    return KPEG_ERR_FORMAT;
+                const unsigned tc = p[k] >> 4, th = p[k] & 15u;
+                if (tc > 1 || th > 3)
+                    return KPEG_ERR_FORMAT;
+                kpeg_huff_spec *h = &pl->ht[tc][th];
+                memset(h, 0, sizeof *h); // a redefinition replaces the table (the reference appends)
+                unsigned total = 0;
+                for (int q = 0; q < 16; ++q) {
+                    h->counts[q] = p[k + 1 + q];
+                    total += h->counts[q];
+                }
+                if (total > 256 || k + 17 + total > plen)
+                    return KPEG_ERR_FORMAT;
+                memcpy(h->symbols, p + k + 17, total);
+                pl->ht_present[tc][th] = 1;
+                k += 17 + total;
+            }
+            break;
+        }
+        case 0xDD: // DRI -- no counterpart in the reference; T.81 B.2.4.4
+            if (plen < 2)
+                return KPEG_ERR_FORMAT;
+            pl->restart_interval = (uint16_t)be16(p);
+            break;
+        case 0xDA: { // SOS -- parseSOSSegment, Decoder.cpp:461-530
+            if (!have_frame || plen < 1)
+                return KPEG_ERR_FORMAT;
+            const unsigned ns = p[0];
+            if (ns != pl->ncomp)
+                return KPEG_ERR_UNSUPPORTED; // non-interleaved multi-scan files
+            if (plen < 1 + 2 * ns + 3)
+                return KPEG_ERR_FORMAT;
+            for (unsigned s = 0; s < ns; ++s) {
+                if (p[1 + 2 * s] != comp_id[s])
+                    return KPEG_ERR_UNSUPPORTED; // scan order must be frame order
+                const unsigned td = p[2 + 2 * s] >> 4, ta = p[2 + 2 * s] & 15u;
+                if (td > 3 || ta > 3)
+                    return KPEG_ERR_FORMAT;
+                pl->comp_td[s] = (uint8_t)td;
+                pl->comp_ta[s] = (uint8_t)ta;
+            }
+            for (unsigned c = 0; c < pl->ncomp; ++c) {
+                if (!pl->qt_present[pl->comp_tq[c]] || !pl->ht_present[0][pl->comp_td[c]] ||
+                    !pl->ht_present[1][pl->comp_ta[c]])
+                    return KPEG_ERR_FORMAT;
+            }
+            const size_t s0 = i + L;
+            const size_t e = find_scan_end(f, n, s0);
+            *scan_off = s0;
+            *scan_len = e - s0;
+            return KPEG_OK;
+        }
+        default: // APPn, COM, DNL, ...: skipped by length
+            break;
+        }
+        i += L;
+    }
+}
+
+extern "C" int kpeg_ppm_header(int width, int height, char *buf, size_t cap)
+{
+    // Image::dumpRawData, Image.cpp:124-127
+    return snprintf(buf, cap,
+                    "P6\n# PPM dump created using libKPEG: https://github.com/TheIllusionistMirage/libKPEG\n%d %d\n255\n",
+                    width, height);
+}

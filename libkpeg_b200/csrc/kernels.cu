@@ -1,0 +1,891 @@
+// kernels.cu -- hand-written sm_100a kernels of the baseline-JPEG decode hot path.
+//
+//   K0  unstuff_*      FF00 / RSTn removal + restart-segment table     (Decoder.cpp:532-577, 621-653)
+//   K1  entropy_*      Huffman + run-length decode, parallel over fixed-size subsequences with a
+//                      self-synchronising relay and a segmented offset scan (Decoder.cpp:655-855)
+//   K2  dc_*           DC prediction as a segmented prefix scan           (MCU.cpp:107-108)
+//   K3  idct_kernel    dequantise + de-zigzag + 8x8 IDCT + level shift + YCbCr->RGB + interleaved
+//                      store, one pass over HBM                           (MCU.cpp:110-279, Image.cpp:51-70)
+//
+// All file:line citations are relative to /root/reference.  The arithmetic lives in
+// entropy_core.h / idct_core.h (host+device inline, also exercised on the CPU by tests/emu).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <utility>
+
+#include "entropy_core.h"
+#include "idct_core.h"
+#include "kernels.cuh"
+#include "unstuff_core.h"
+#include "kpeg_common.h"
+
+namespace kpeg {
+
+// =================================================================================================
+// small block-level primitives
+// =================================================================================================
+
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_exclusive_sum(uint32_t v, uint32_t *s_warp /*[THREADS/32 + 1]*/, uint32_t &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+            incl += o;
+    }
+    if (lane == 31)
+        s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < THREADS / 32 ? s_warp[lane] : 0u;
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d)
+                wi += o;
+        }
+        if (lane < THREADS / 32)
+            s_warp[lane] = wi - w; // exclusive warp offsets
+        if (lane == 31)
+            s_warp[THREADS / 32] = wi;
+    }
+    __syncthreads();
+    total = s_warp[THREADS / 32];
+    const uint32_t r = s_warp[warp] + incl - v;
+    __syncthreads();
+    return r;
+}
+
+// =================================================================================================
+// K0: unstuffing and restart-marker scan
+// =================================================================================================
+//
+// Byte classes inside an entropy-coded segment (T.81 B.1.1.5): FF 00 is a data byte FF; FF D0..D7 is
+// a restart marker (segment boundary); FF FF is a fill byte; anything else is flagged.  The
+// reference drops only the 00 (Decoder.cpp:631-650) and cannot handle RSTn.
+
+__global__ void __launch_bounds__(UNSTUFF_THREADS) unstuff_count_kernel(UnstuffArgs a)
+{
+    __shared__ uint32_t s_w[UNSTUFF_THREADS / 32 + 1];
+    const uint32_t base = (blockIdx.x * UNSTUFF_THREADS + threadIdx.x) * UNSTUFF_BYTES_PER_THREAD;
+    uint32_t kept = 0, rst = 0, bad = 0;
+    if (base < a.scan_len) {
+        const ByteClass c = classify16(a.scan, a.scan_len, base);
+        kept = __popc(c.keep);
+        rst = __popc(c.rst);
+        bad = c.bad;
+    }
+    // pack both counts into one reduction: kept <= 4096 per tile, rst <= 2048
+    uint32_t tot;
+    block_exclusive_sum<UNSTUFF_THREADS>(kept | (rst << 16), s_w, tot);
+    if (threadIdx.x == 0) {
+        a.tile_kept[blockIdx.x] = tot & 0xFFFFu;
+        a.tile_rst[blockIdx.x] = tot >> 16;
+    }
+    if (bad)
+        atomicOr(&a.meta->status, ST_BAD_MARKER);
+}
+
+// One block: exclusive scan of the per-tile counts, stream totals, segment-table prefill.
+__global__ void __launch_bounds__(1024) unstuff_scan_kernel(UnstuffArgs a, uint32_t sub_bits)
+{
+    __shared__ uint32_t s_w[1024 / 32 + 1];
+    __shared__ uint32_t s_carry[2];
+    if (threadIdx.x == 0)
+        s_carry[0] = s_carry[1] = 0;
+    __syncthreads();
+    for (uint32_t t0 = 0; t0 < a.ntiles; t0 += 1024) {
+        const uint32_t t = t0 + threadIdx.x;
+        const uint32_t k = t < a.ntiles ? a.tile_kept[t] : 0u;
+        const uint32_t r = t < a.ntiles ? a.tile_rst[t] : 0u;
+        uint32_t tk, tr;
+        const uint32_t ek = block_exclusive_sum<1024>(k, s_w, tk);
+        const uint32_t er = block_exclusive_sum<1024>(r, s_w, tr);
+        if (t < a.ntiles) {
+            a.tile_kept[t] = s_carry[0] + ek;
+            a.tile_rst[t] = s_carry[1] + er;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_carry[0] += tk;
+            s_carry[1] += tr;
+        }
+        __syncthreads();
+    }
+    const uint32_t total_kept = s_carry[0], total_rst = s_carry[1];
+    const uint32_t total_bits = total_kept * 8u;
+    for (uint32_t k = threadIdx.x; k < a.nseg + 2u; k += 1024)
+        a.seg_bit[k] = k == 0u ? 0u : (k <= a.nseg ? total_bits : 0xFFFFFFFFu);
+    if (threadIdx.x == 0) {
+        a.meta->total_kept = total_kept;
+        a.meta->total_rst = total_rst;
+        a.meta->total_bits = total_bits;
+        const uint32_t nsub = (total_bits + sub_bits - 1u) / sub_bits;
+        a.meta->nsub = nsub ? nsub : 1u;
+        if (total_rst != a.nseg - 1u && total_rst != a.nseg)
+            atomicOr(&a.meta->status, ST_SEG_COUNT);
+    }
+}
+
+__global__ void __launch_bounds__(UNSTUFF_THREADS) unstuff_write_kernel(UnstuffArgs a)
+{
+    __shared__ uint32_t s_w[UNSTUFF_THREADS / 32 + 1];
+    const uint32_t base = (blockIdx.x * UNSTUFF_THREADS + threadIdx.x) * UNSTUFF_BYTES_PER_THREAD;
+    ByteClass c;
+    c.keep = c.rst = 0;
+    if (base < a.scan_len)
+        c = classify16(a.scan, a.scan_len, base);
+    uint32_t tot;
+    const uint32_t ex = block_exclusive_sum<UNSTUFF_THREADS>(__popc(c.keep) | (__popc(c.rst) << 16), s_w, tot);
+    uint32_t pos = a.tile_kept[blockIdx.x] + (ex & 0xFFFFu);
+    uint32_t ridx = a.tile_rst[blockIdx.x] + (ex >> 16);
+    if ((c.keep | c.rst) == 0u)
+        return;
+    if (c.keep == 0xFFFFu && (pos & 3u) == 0u) {
+        // common case: 16 surviving bytes landing word-aligned -> four byte-swapped word stores
+        uint32_t *w = reinterpret_cast<uint32_t *>(a.words + pos);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            w[k] = __byte_perm(c.b[k], 0, 0x0123);
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (c.rst & (1u << i)) {
+            ++ridx;
+            if (ridx < a.nseg)
+                a.seg_bit[ridx] = pos * 8u;
+        }
+        if (c.keep & (1u << i)) {
+            a.words[pos ^ 3u] = (uint8_t)(c.b[i >> 2] >> (8 * (i & 3)));
+            ++pos;
+        }
+    }
+}
+
+void launch_unstuff(const UnstuffArgs &a, uint32_t sub_bits, cudaStream_t s, uint32_t *launches)
+{
+    unstuff_count_kernel<<<a.ntiles, UNSTUFF_THREADS, 0, s>>>(a);
+    unstuff_scan_kernel<<<1, 1024, 0, s>>>(a, sub_bits);
+    unstuff_write_kernel<<<a.ntiles, UNSTUFF_THREADS, 0, s>>>(a);
+    *launches += 3;
+}
+
+// =================================================================================================
+// K1: entropy decode
+// =================================================================================================
+
+__device__ __forceinline__ void load_luts_to_smem(HuffLut *s_lut, const DeviceTables *t, uint32_t ncomp)
+{
+    const uint4 *src = reinterpret_cast<const uint4 *>(t->lut);
+    uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+    const uint32_t n = ncomp * 2u * (uint32_t)(sizeof(HuffLut) / 16);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        dst[i] = __ldg(src + i);
+    __syncthreads();
+}
+
+// first segment index whose start bit is >= bit  (seg_bit[0..nseg] ascending, seg_bit[nseg] = total_bits)
+__device__ __forceinline__ uint32_t first_seg_at_or_after(const uint32_t *seg_bit, uint32_t nseg, uint32_t bit)
+{
+    uint32_t lo = 0, hi = nseg; // answer in [lo, hi]
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(seg_bit + mid) >= bit)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(ENTROPY_THREADS) entropy_cold_kernel(EntropyArgs a)
+{
+    __shared__ __align__(16) HuffLut s_lut[MAX_COMP * 2];
+    load_luts_to_smem(s_lut, a.tables, a.g.ncomp);
+    const uint32_t sub = blockIdx.x * ENTROPY_THREADS + threadIdx.x;
+    const uint32_t nsub = a.meta->nsub, total_bits = a.meta->total_bits;
+    if (sub >= nsub)
+        return;
+    StreamView S{a.words, a.seg_bit, total_bits};
+    const uint32_t p0 = sub * a.g.sub_bits;
+    const uint32_t end = min(p0 + a.g.sub_bits, total_bits);
+    const uint32_t hint = a.g.nseg > 1u ? first_seg_at_or_after(a.seg_bit, a.g.nseg, p0) : (sub ? 1u : 0u);
+    a.seg_hint[sub] = hint;
+    const SubState out = decode_span<false>(S, a.g, s_lut, end, p0, 0u, 0u, hint, 0u, nullptr, nullptr, nullptr);
+    a.state[sub] = out;
+    a.used[sub] = make_uint2(p0, 0u);
+}
+
+// One relay round: X[i] = decode(i, X[i-1]) for every i whose input changed since it was last used.
+__global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_kernel(EntropyArgs a, int round)
+{
+    if (round > 1 && a.meta->changed[round - 1] == 0u)
+        return; // already at the fixed point
+    __shared__ __align__(16) HuffLut s_lut[MAX_COMP * 2];
+    load_luts_to_smem(s_lut, a.tables, a.g.ncomp);
+    const uint32_t sub = blockIdx.x * ENTROPY_THREADS + threadIdx.x;
+    const uint32_t nsub = a.meta->nsub, total_bits = a.meta->total_bits;
+    if (sub == 0u || sub >= nsub)
+        return;
+    const uint4 inraw = __ldcg(reinterpret_cast<const uint4 *>(&a.state[sub - 1]));
+    const uint32_t in_p = inraw.x, in_cz = inraw.z;
+    const uint2 u = a.used[sub];
+    if (u.x == in_p && u.y == in_cz)
+        return;
+    StreamView S{a.words, a.seg_bit, total_bits};
+    const uint32_t end = min((sub + 1u) * a.g.sub_bits, total_bits);
+    const SubState out =
+        decode_span<false>(S, a.g, s_lut, end, in_p, in_cz >> 8, in_cz & 0xFFu, a.seg_hint[sub], 0u, nullptr, nullptr, nullptr);
+    a.used[sub] = make_uint2(in_p, in_cz);
+    const SubState old = a.state[sub];
+    if (old.p != out.p || old.cz != out.cz || old.n != out.n || old.seg != out.seg) {
+        uint4 o;
+        o.x = out.p;
+        o.y = out.n;
+        o.z = out.cz;
+        o.w = (uint32_t)out.seg;
+        __stcg(reinterpret_cast<uint4 *>(&a.state[sub]), o);
+        atomicAdd(&a.meta->changed[round], 1u);
+    }
+}
+
+// Segmented exclusive scan of the slot counts: start_slot[i] = absolute coefficient slot at the
+// entry of subsequence i.  An element that crossed a segment boundary carries an absolute value.
+__global__ void __launch_bounds__(1024) entropy_scan_kernel(EntropyArgs a)
+{
+    __shared__ uint32_t s_f[33], s_v[33];
+    __shared__ uint32_t s_cf, s_cv;
+    const uint32_t nsub = a.meta->nsub;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        s_cf = 1u; // virtual element -1: absolute slot 0 (segment 0 starts at bit 0)
+        s_cv = 0u;
+    }
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < nsub; i0 += 1024) {
+        const uint32_t i = i0 + threadIdx.x;
+        uint32_t f = 0, v = 0;
+        if (i < nsub) {
+            const SubState st = a.state[i];
+            f = st.seg >= 0 ? 1u : 0u;
+            v = st.n + (f ? seg_slot_base(a.g, (uint32_t)st.seg) : 0u);
+        }
+        // warp inclusive segmented scan
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t of = __shfl_up_sync(0xffffffffu, f, d);
+            const uint32_t ov = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) {
+                if (!f)
+                    v += ov;
+                f |= of;
+            }
+        }
+        if (lane == 31) {
+            s_f[warp] = f;
+            s_v[warp] = v;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t wf = s_f[lane], wv = s_v[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t of = __shfl_up_sync(0xffffffffu, wf, d);
+                const uint32_t ov = __shfl_up_sync(0xffffffffu, wv, d);
+                if (lane >= d) {
+                    if (!wf)
+                        wv += ov;
+                    wf |= of;
+                }
+            }
+            s_f[lane] = wf; // inclusive over warps
+            s_v[lane] = wv;
+        }
+        __syncthreads();
+        // carry from previous warps of this chunk, then from previous chunks
+        uint32_t cf = s_cf, cv = s_cv;
+        if (warp > 0) {
+            const uint32_t pf = s_f[warp - 1], pv = s_v[warp - 1];
+            if (pf) {
+                cf = 1u;
+                cv = pv;
+            } else {
+                cv += pv;
+            }
+        }
+        if (!f)
+            v += cv;
+        f |= cf;
+        // v is now the inclusive value at i == the entry slot of subsequence i+1
+        if (i + 1u < nsub)
+            a.start_slot[i + 1u] = v;
+        if (i == 0u)
+            a.start_slot[0] = 0u;
+        if (i + 1u == nsub)
+            a.meta->final_slot = v;
+        __syncthreads();
+        if (threadIdx.x == 1023) {
+            s_cf = f;
+            s_cv = v;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(ENTROPY_THREADS) entropy_write_kernel(EntropyArgs a)
+{
+    __shared__ __align__(16) HuffLut s_lut[MAX_COMP * 2];
+    load_luts_to_smem(s_lut, a.tables, a.g.ncomp);
+    const uint32_t sub = blockIdx.x * ENTROPY_THREADS + threadIdx.x;
+    const uint32_t nsub = a.meta->nsub, total_bits = a.meta->total_bits;
+    if (sub >= nsub)
+        return;
+    uint32_t p = 0, c = 0, z = 0;
+    if (sub) {
+        const SubState in = a.state[sub - 1];
+        p = in.p;
+        c = in.cz >> 8;
+        z = in.cz & 0xFFu;
+    }
+    const uint32_t slot = a.start_slot[sub];
+    uint32_t st = 0;
+    if ((slot & 63u) != z || ((slot >> 6) % a.g.ncomp) != c)
+        st |= ST_EXIT_MISMATCH;
+    StreamView S{a.words, a.seg_bit, total_bits};
+    const uint32_t end = min((sub + 1u) * a.g.sub_bits, total_bits);
+    const SubState out = decode_span<true>(S, a.g, s_lut, end, p, c, z, a.seg_hint[sub], slot, a.coef, a.dcdiff, &st);
+    const SubState rec = a.state[sub];
+    if (out.p != rec.p || out.cz != rec.cz)
+        st |= ST_EXIT_MISMATCH;
+    if (sub + 1u == nsub && a.meta->final_slot < a.g.total_blocks * 64u)
+        st |= ST_SEG_MISMATCH; // the stream ended before the last MCU
+    if (st)
+        atomicOr(&a.meta->status, st);
+}
+
+void launch_entropy_cold(const EntropyArgs &a, cudaStream_t s, uint32_t *launches)
+{
+    const uint32_t grid = (a.nsub_max + ENTROPY_THREADS - 1) / ENTROPY_THREADS;
+    entropy_cold_kernel<<<grid, ENTROPY_THREADS, 0, s>>>(a);
+    ++*launches;
+}
+
+void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint32_t *launches)
+{
+    const uint32_t grid = (a.nsub_max + ENTROPY_THREADS - 1) / ENTROPY_THREADS;
+    entropy_relay_kernel<<<grid, ENTROPY_THREADS, 0, s>>>(a, round);
+    ++*launches;
+}
+
+void launch_entropy_scan_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches)
+{
+    const uint32_t grid = (a.nsub_max + ENTROPY_THREADS - 1) / ENTROPY_THREADS;
+    entropy_scan_kernel<<<1, 1024, 0, s>>>(a);
+    entropy_write_kernel<<<grid, ENTROPY_THREADS, 0, s>>>(a);
+    *launches += 2;
+}
+
+// =================================================================================================
+// K2: DC prediction = segmented prefix sum of the DC differences (MCU.cpp:107-108; predictor reset at
+// every restart interval / image start, T.81 F.2.1.3.1 -- the reference never resets)
+// =================================================================================================
+
+__device__ __forceinline__ bool mcu_is_reset(const JobGeom &g, uint32_t m)
+{
+    const uint32_t mi = m % g.mcus_per_image;
+    return g.restart_interval ? (mi % g.restart_interval) == 0u : mi == 0u;
+}
+
+struct Dc3 {
+    int32_t v[3];
+    uint32_t f;
+};
+
+__device__ __forceinline__ Dc3 dc_combine(const Dc3 &a, const Dc3 &b) // a then b
+{
+    Dc3 r;
+    r.f = a.f | b.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        r.v[c] = b.f ? b.v[c] : a.v[c] + b.v[c];
+    return r;
+}
+
+__device__ __forceinline__ Dc3 dc_shfl_up(const Dc3 &x, int d)
+{
+    Dc3 r;
+    r.f = __shfl_up_sync(0xffffffffu, x.f, d);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        r.v[c] = __shfl_up_sync(0xffffffffu, x.v[c], d);
+    return r;
+}
+
+// Inclusive segmented scan across the block of one Dc3 per thread; returns the inclusive value and
+// the block aggregate.
+__device__ __forceinline__ Dc3 dc_block_scan(Dc3 x, Dc3 *s_w /*[DC_THREADS/32]*/, Dc3 &aggregate)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const Dc3 o = dc_shfl_up(x, d);
+        if (lane >= d)
+            x = dc_combine(o, x);
+    }
+    if (lane == 31)
+        s_w[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        Dc3 w;
+        if (lane < DC_THREADS / 32)
+            w = s_w[lane];
+        else {
+            w.f = 0;
+            w.v[0] = w.v[1] = w.v[2] = 0;
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const Dc3 o = dc_shfl_up(w, d);
+            if (lane >= d)
+                w = dc_combine(o, w);
+        }
+        if (lane < DC_THREADS / 32)
+            s_w[lane] = w;
+    }
+    __syncthreads();
+    if (warp > 0)
+        x = dc_combine(s_w[warp - 1], x);
+    aggregate = s_w[DC_THREADS / 32 - 1];
+    return x;
+}
+
+__device__ __forceinline__ Dc3 dc_thread_local(const DcArgs &a, uint32_t m0, uint32_t total_mcus, Dc3 incl[DC_MCUS_PER_THREAD])
+{
+    Dc3 run;
+    run.f = 0;
+    run.v[0] = run.v[1] = run.v[2] = 0;
+#pragma unroll
+    for (int k = 0; k < DC_MCUS_PER_THREAD; ++k) {
+        const uint32_t m = m0 + k;
+        Dc3 e;
+        e.f = 0;
+        e.v[0] = e.v[1] = e.v[2] = 0;
+        if (m < total_mcus) {
+            e.f = mcu_is_reset(a.g, m) ? 1u : 0u;
+            for (uint32_t c = 0; c < a.g.ncomp; ++c)
+                e.v[c] = a.dcdiff[m * a.g.ncomp + c];
+        }
+        run = dc_combine(run, e);
+        incl[k] = run;
+    }
+    return run;
+}
+
+__global__ void __launch_bounds__(DC_THREADS) dc_reduce_kernel(DcArgs a)
+{
+    __shared__ Dc3 s_w[DC_THREADS / 32];
+    const uint32_t total_mcus = a.g.nimages * a.g.mcus_per_image;
+    const uint32_t m0 = (blockIdx.x * DC_THREADS + threadIdx.x) * DC_MCUS_PER_THREAD;
+    Dc3 incl[DC_MCUS_PER_THREAD];
+    const Dc3 mine = dc_thread_local(a, m0, total_mcus, incl);
+    Dc3 agg;
+    dc_block_scan(mine, s_w, agg);
+    if (threadIdx.x == 0) {
+        a.tile_carry[blockIdx.x * 4 + 0] = agg.v[0];
+        a.tile_carry[blockIdx.x * 4 + 1] = agg.v[1];
+        a.tile_carry[blockIdx.x * 4 + 2] = agg.v[2];
+        a.tile_carry[blockIdx.x * 4 + 3] = (int32_t)agg.f;
+    }
+}
+
+// one block: tile_carry[t] <- exclusive segmented scan (value carried INTO tile t)
+__global__ void __launch_bounds__(DC_THREADS) dc_tile_scan_kernel(DcArgs a)
+{
+    __shared__ Dc3 s_w[DC_THREADS / 32];
+    __shared__ Dc3 s_carry;
+    __shared__ Dc3 s_incl[DC_THREADS];
+    if (threadIdx.x == 0) {
+        s_carry.f = 0;
+        s_carry.v[0] = s_carry.v[1] = s_carry.v[2] = 0;
+    }
+    __syncthreads();
+    for (uint32_t t0 = 0; t0 < a.ntiles; t0 += DC_THREADS) {
+        const uint32_t t = t0 + threadIdx.x;
+        Dc3 e;
+        e.f = 0;
+        e.v[0] = e.v[1] = e.v[2] = 0;
+        if (t < a.ntiles) {
+            e.v[0] = a.tile_carry[t * 4 + 0];
+            e.v[1] = a.tile_carry[t * 4 + 1];
+            e.v[2] = a.tile_carry[t * 4 + 2];
+            e.f = (uint32_t)a.tile_carry[t * 4 + 3];
+        }
+        Dc3 agg;
+        const Dc3 incl = dc_block_scan(e, s_w, agg);
+        const Dc3 carry = s_carry;
+        const Dc3 full = dc_combine(carry, incl); // inclusive up to tile t
+        // exclusive value = inclusive of t-1: shuffle through shared memory
+        s_incl[threadIdx.x] = full;
+        __syncthreads();
+        if (t < a.ntiles) {
+            const Dc3 ex = threadIdx.x == 0 ? carry : s_incl[threadIdx.x - 1];
+            a.tile_carry[t * 4 + 0] = ex.v[0];
+            a.tile_carry[t * 4 + 1] = ex.v[1];
+            a.tile_carry[t * 4 + 2] = ex.v[2];
+        }
+        __syncthreads();
+        if (threadIdx.x == DC_THREADS - 1)
+            s_carry = full;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(DC_THREADS) dc_apply_kernel(DcArgs a)
+{
+    __shared__ Dc3 s_w[DC_THREADS / 32];
+    const uint32_t total_mcus = a.g.nimages * a.g.mcus_per_image;
+    const uint32_t m0 = (blockIdx.x * DC_THREADS + threadIdx.x) * DC_MCUS_PER_THREAD;
+    Dc3 incl[DC_MCUS_PER_THREAD];
+    const Dc3 mine = dc_thread_local(a, m0, total_mcus, incl);
+    Dc3 agg;
+    const Dc3 inc = dc_block_scan(mine, s_w, agg);
+    // exclusive prefix of this thread = inclusive of the previous thread (through shared memory)
+    __shared__ Dc3 s_incl[DC_THREADS];
+    s_incl[threadIdx.x] = inc;
+    __syncthreads();
+    Dc3 pre;
+    pre.f = 0;
+    pre.v[0] = a.tile_carry[blockIdx.x * 4 + 0];
+    pre.v[1] = a.tile_carry[blockIdx.x * 4 + 1];
+    pre.v[2] = a.tile_carry[blockIdx.x * 4 + 2];
+    if (threadIdx.x > 0)
+        pre = dc_combine(pre, s_incl[threadIdx.x - 1]);
+#pragma unroll
+    for (int k = 0; k < DC_MCUS_PER_THREAD; ++k) {
+        const uint32_t m = m0 + k;
+        if (m < total_mcus) {
+            const Dc3 r = dc_combine(pre, incl[k]);
+            for (uint32_t c = 0; c < a.g.ncomp; ++c)
+                a.dc[m * a.g.ncomp + c] = (int16_t)r.v[c];
+        }
+    }
+}
+
+void launch_dc_scan(const DcArgs &a, cudaStream_t s, uint32_t *launches)
+{
+    dc_reduce_kernel<<<a.ntiles, DC_THREADS, 0, s>>>(a);
+    dc_tile_scan_kernel<<<1, DC_THREADS, 0, s>>>(a);
+    dc_apply_kernel<<<a.ntiles, DC_THREADS, 0, s>>>(a);
+    *launches += 3;
+}
+
+// =================================================================================================
+// K3: fused dequantise + de-zigzag + IDCT + level shift + colour conversion + interleaved store
+// =================================================================================================
+//
+// One CTA reconstructs a strip of IDCT_MCUS_PER_CTA consecutive MCUs (a contiguous chunk of the
+// coefficient buffer, and -- when the strip does not wrap -- 8 contiguous runs of pixels).
+//   stage 0  coalesced 16-byte loads of the strip's coefficients into shared memory (XOR-swizzled
+//            so that the per-thread 128-byte reads of stage 1 are bank-conflict free)
+//   stage 1  one thread per 8x8 block, all 64 values in registers: dequantise (AAN prescale folded
+//            into the quantiser), de-zigzag by register renaming, separable fp32 IDCT, rounding,
+//            tie-band test; samples inside the band are queued
+//   stage 2  the queued samples are re-evaluated in the reference's own operation order
+//   stage 3  per pixel row: YCbCr -> RGB (fp32 with proven margin, double otherwise), pack, store
+
+__device__ __constant__ ZigZagTables c_zz = make_zigzag_tables();
+
+template <int I>
+struct ZzNat {
+    static constexpr int value = zigzag_to_natural(I);
+};
+
+constexpr int IDCT_QUEUE_CAP = 1024;
+
+template <int NC>
+struct IdctSmem {
+    static constexpr int NM = IDCT_MCUS_PER_CTA;
+    static constexpr int NB = NM * NC;
+    uint4 coef[NB * 8];           // 16-byte chunks, chunk k of block b at b*8 + (k ^ (b & 7))
+    float4 samp[NC * 8 * 2 * NM]; // [comp][row][half][mcu] -> 4 samples (rounded, unshifted)
+    float qscale[NC][64];
+    int32_t qint[NC][64];
+    double cosd[8][8];
+    float cc[8][8];
+    uint16_t queue[IDCT_QUEUE_CAP];
+    uint32_t qcount;
+};
+
+template <int NC>
+__device__ __forceinline__ int smem_coef_at(const IdctSmem<NC> &sm, int bl, int zi)
+{
+    const int16_t *p = reinterpret_cast<const int16_t *>(&sm.coef[bl * 8 + ((zi >> 3) ^ (bl & 7))]);
+    return p[zi & 7];
+}
+
+template <int NC>
+__device__ __forceinline__ void store_sample(IdctSmem<NC> &sm, int comp, int ml, int s, float v)
+{
+    const int row = s >> 3, col = s & 7;
+    float *p = reinterpret_cast<float *>(&sm.samp[((comp * 8 + row) * 2 + (col >> 2)) * IdctSmem<NC>::NM + ml]);
+    p[col & 3] = v;
+}
+
+// coefficient I (zig-zag index) of a block held as eight 16-byte chunks
+template <int I>
+__device__ __forceinline__ float chunk_coef(const uint4 (&ch)[8])
+{
+    constexpr int k = I >> 3, j = (I & 7) >> 1, hi = I & 1;
+    const uint32_t w = j == 0 ? ch[k].x : (j == 1 ? ch[k].y : (j == 2 ? ch[k].z : ch[k].w));
+    return (float)(short)(hi ? (w >> 16) : (w & 0xFFFFu));
+}
+
+template <int... Is>
+__device__ __forceinline__ void dequant_dezigzag(const uint4 (&ch)[8], const float *q, float (&f)[64],
+                                                 std::integer_sequence<int, Is...>)
+{
+    ((f[ZzNat<Is>::value] = chunk_coef<Is>(ch) * q[Is]), ...);
+}
+
+__device__ __forceinline__ uint32_t pack4(float a, float b, float c, float d)
+{
+    // a..d are integer-valued floats in [0,255]; adding 1.5*2^23 leaves the integer in the low byte
+    const float M = 12582912.0f;
+    const uint32_t ua = __float_as_uint(a + M), ub = __float_as_uint(b + M);
+    const uint32_t uc = __float_as_uint(c + M), ud = __float_as_uint(d + M);
+    return __byte_perm(__byte_perm(ua, ub, 0x0040), __byte_perm(uc, ud, 0x0040), 0x5410);
+}
+
+template <int NC>
+__global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA) idct_kernel(IdctArgs a)
+{
+    constexpr int NM = IDCT_MCUS_PER_CTA;
+    constexpr int NB = NM * NC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    IdctSmem<NC> &sm = *reinterpret_cast<IdctSmem<NC> *>(smem_raw);
+
+    const int t = threadIdx.x;
+    const int comp = t / NM; // warp-uniform
+    const int ml = t % NM;
+    const int bl = ml * NC + comp; // block index inside the CTA's strip (MCU-interleaved)
+    const uint32_t total_mcus = a.g.nimages * a.g.mcus_per_image;
+    const uint32_t mcu0 = blockIdx.x * NM;
+    const uint32_t m = mcu0 + ml;
+    const uint32_t blk0 = mcu0 * NC;
+
+    // ---- stage 0: tables + coefficients -> shared memory (coalesced 16-byte loads) -------------
+    for (int i = t; i < NC * 64; i += NB) {
+        (&sm.qscale[0][0])[i] = a.tables->qscale[0][i];
+        (&sm.qint[0][0])[i] = a.tables->qint[0][i];
+    }
+    for (int i = t; i < 64; i += NB) {
+        (&sm.cosd[0][0])[i] = a.tables->cosd[0][i];
+        (&sm.cc[0][0])[i] = a.tables->cc[0][i];
+    }
+    if (t == 0)
+        sm.qcount = 0;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.coef) + (size_t)blk0 * 8;
+        const uint32_t nvalid = (a.g.total_blocks > blk0 ? min(a.g.total_blocks - blk0, (uint32_t)NB) : 0u) * 8u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t ci = (uint32_t)(k * NB + t);
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (ci < nvalid)
+                v = __ldg(src + ci);
+            const uint32_t b = ci >> 3, kk = ci & 7u;
+            sm.coef[b * 8 + (kk ^ (b & 7u))] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 1: one thread = one 8x8 block ------------------------------------------------------
+    if (m < total_mcus) {
+        const uint32_t gb = blk0 + bl;
+        const int dcv = a.dc[gb];
+        const bool drop_ac = (a.g.flags & 1u) && a.dcdiff[gb] == 0; // MCU.cpp:97-104
+        uint4 ch[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            ch[k] = sm.coef[bl * 8 + (k ^ (bl & 7))];
+        if (drop_ac) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                ch[k] = make_uint4(0, 0, 0, 0);
+                sm.coef[bl * 8 + (k ^ (bl & 7))] = ch[k];
+            }
+        }
+        // The entropy stage leaves slot 0 empty; the integrated DC value comes from K2.  Patch it
+        // into the shared copy as well: stage 2 reads coefficients from there.
+        ch[0].x = (ch[0].x & 0xFFFF0000u) | ((uint32_t)dcv & 0xFFFFu);
+        sm.coef[bl * 8 + (bl & 7)] = ch[0];
+
+        float f[64];
+        dequant_dezigzag(ch, sm.qscale[comp], f, std::make_integer_sequence<int, 64>{});
+        idct8x8_fast(f);
+
+        float energy = 0.0f;
+#pragma unroll
+        for (int s = 0; s < 64; ++s)
+            energy = fmaf(f[s], f[s], energy);
+        const float thresh = 0.5f - tie_band(energy);
+        const float MAGIC = 12582912.0f; // 1.5 * 2^23: (x + MAGIC) - MAGIC == rint(x) for |x| < 2^22
+#pragma unroll
+        for (int row = 0; row < 8; ++row) {
+            float r[8];
+#pragma unroll
+            for (int col = 0; col < 8; ++col) {
+                const float x = f[row * 8 + col];
+                r[col] = (x + MAGIC) - MAGIC;
+                if (fabsf(x - r[col]) > thresh) {
+                    const uint32_t slot = atomicAdd(&sm.qcount, 1u);
+                    if (slot < IDCT_QUEUE_CAP) {
+                        sm.queue[slot] = (uint16_t)((bl << 6) | (row * 8 + col));
+                    } else {
+                        // queue full (pathologically flat image): resolve on the spot
+                        auto at = [&](int zi) { return smem_coef_at<NC>(sm, bl, zi); };
+                        r[col] = (float)exact_sample(at, sm.qint[comp], sm.cosd, sm.cc, c_zz.nat2zz, row, col);
+                    }
+                }
+            }
+            sm.samp[((comp * 8 + row) * 2 + 0) * NM + ml] = make_float4(r[0], r[1], r[2], r[3]);
+            sm.samp[((comp * 8 + row) * 2 + 1) * NM + ml] = make_float4(r[4], r[5], r[6], r[7]);
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 2: exact (reference-order) evaluation of the samples inside the tie band -------------
+    {
+        const uint32_t nq_all = sm.qcount;
+        const uint32_t nq = min(nq_all, (uint32_t)IDCT_QUEUE_CAP);
+        for (uint32_t e = t; e < nq; e += NB) {
+            const uint32_t ent = sm.queue[e];
+            const int ebl = ent >> 6, s = ent & 63;
+            const int ecomp = ebl % NC, eml = ebl / NC;
+            auto at = [&](int zi) { return smem_coef_at<NC>(sm, ebl, zi); };
+            const int r = exact_sample(at, sm.qint[ecomp], sm.cosd, sm.cc, c_zz.nat2zz, s >> 3, s & 7);
+            store_sample<NC>(sm, ecomp, eml, s, (float)r);
+        }
+        if (t == 0 && nq_all)
+            atomicAdd(&a.meta->exact_samples, nq_all);
+    }
+    __syncthreads();
+
+    // ---- stage 3: colour conversion + interleaved store -------------------------------------------
+    if (m < total_mcus) {
+        const uint32_t img = m / a.g.mcus_per_image;
+        const uint32_t mi = m - img * a.g.mcus_per_image;
+        const uint32_t by = mi / a.g.mcus_x, bx = mi - by * a.g.mcus_x;
+        const uint32_t W = a.g.width, H = a.g.height;
+        uint8_t *img_base = a.pixels + (size_t)img * W * H * NC;
+        const bool full_w = bx * 8u + 8u <= W;
+        const bool vec_ok = full_w && (W % 8u == 0u) && ((reinterpret_cast<uintptr_t>(a.pixels) & 7u) == 0);
+        uint32_t colour_exact = 0;
+        for (int row = comp; row < 8; row += NC) { // the NC warps of the CTA share the 8 pixel rows
+            const uint32_t y = by * 8u + row;
+            if (y >= H)
+                continue;
+            const float4 y0 = sm.samp[((0 * 8 + row) * 2 + 0) * NM + ml];
+            const float4 y1 = sm.samp[((0 * 8 + row) * 2 + 1) * NM + ml];
+            const float Y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+            uint32_t out[2 * NC];
+            if constexpr (NC == 3) {
+                const float4 b0 = sm.samp[((1 * 8 + row) * 2 + 0) * NM + ml];
+                const float4 b1 = sm.samp[((1 * 8 + row) * 2 + 1) * NM + ml];
+                const float4 c0 = sm.samp[((2 * 8 + row) * 2 + 0) * NM + ml];
+                const float4 c1 = sm.samp[((2 * 8 + row) * 2 + 1) * NM + ml];
+                const float Cb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const float Cr[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                float px[24];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float R, G, B;
+                    if (!ycc_to_rgb_fast(Y[j], Cb[j], Cr[j], R, G, B)) {
+                        int r, g, b;
+                        ycc_to_rgb_exact((int)Y[j], (int)Cb[j], (int)Cr[j], r, g, b);
+                        R = (float)r;
+                        G = (float)g;
+                        B = (float)b;
+                        ++colour_exact;
+                    }
+                    px[j * 3 + 0] = R;
+                    px[j * 3 + 1] = G;
+                    px[j * 3 + 2] = B;
+                }
+#pragma unroll
+                for (int k = 0; k < 6; ++k)
+                    out[k] = pack4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
+            } else {
+                // gray: the reference's colour path with Cb = Cr = 128 gives R = G = B = clamp(Y)
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    v[j] = fminf(fmaxf(Y[j] + 128.0f, 0.0f), 255.0f);
+                out[0] = pack4(v[0], v[1], v[2], v[3]);
+                out[1] = pack4(v[4], v[5], v[6], v[7]);
+            }
+            uint8_t *dst = img_base + ((size_t)y * W + bx * 8u) * NC;
+            if (vec_ok) {
+#pragma unroll
+                for (int k = 0; k < NC; ++k)
+                    reinterpret_cast<uint2 *>(dst)[k] = make_uint2(out[2 * k], out[2 * k + 1]);
+            } else {
+                const uint32_t nbytes = (full_w ? 8u : W - bx * 8u) * NC;
+                for (uint32_t j = 0; j < nbytes; ++j)
+                    dst[j] = (uint8_t)(out[j >> 2] >> (8 * (j & 3)));
+            }
+        }
+        if (colour_exact)
+            atomicAdd(&a.meta->colour_exact, colour_exact);
+    }
+}
+
+void kernels_configure()
+{
+    cudaFuncSetAttribute(idct_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<3>));
+    cudaFuncSetAttribute(idct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<1>));
+}
+
+void launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches)
+{
+    const uint32_t total_mcus = a.g.nimages * a.g.mcus_per_image;
+    const uint32_t grid = (total_mcus + IDCT_MCUS_PER_CTA - 1) / IDCT_MCUS_PER_CTA;
+    if (a.g.ncomp == 3)
+        idct_kernel<3><<<grid, 3 * IDCT_MCUS_PER_CTA, sizeof(IdctSmem<3>), s>>>(a);
+    else
+        idct_kernel<1><<<grid, IDCT_MCUS_PER_CTA, sizeof(IdctSmem<1>), s>>>(a);
+    ++*launches;
+}
+
+// =================================================================================================
+// parity hook: coefficients with the DC value merged in and the F1 rule applied
+// =================================================================================================
+__global__ void merge_dc_kernel(int16_t *out, const int16_t *coef, const int16_t *dc, const int16_t *dcdiff,
+                                uint32_t nblocks, uint32_t flags)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nblocks * 64u)
+        return;
+    const uint32_t b = i >> 6, z = i & 63u;
+    int16_t v;
+    if (z == 0u)
+        v = dc[b];
+    else
+        v = ((flags & 1u) && dcdiff[b] == 0) ? (int16_t)0 : coef[i];
+    out[i] = v;
+}
+
+void launch_merge_dc(int16_t *coef_out, const int16_t *coef, const int16_t *dc, const int16_t *dcdiff, uint32_t nblocks,
+                     uint32_t flags, cudaStream_t s)
+{
+    const uint32_t n = nblocks * 64u;
+    merge_dc_kernel<<<(n + 255) / 256, 256, 0, s>>>(coef_out, coef, dc, dcdiff, nblocks, flags);
+}
+
+} // namespace kpeg

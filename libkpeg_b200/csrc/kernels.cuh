@@ -1,0 +1,91 @@
+// kernels.cuh -- launch-side declarations of the sm_100a kernels (definitions in kernels.cu).
+#ifndef KPEG_KERNELS_CUH
+#define KPEG_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include "kpeg_common.h"
+
+namespace kpeg {
+
+constexpr int MAX_RELAY_ROUNDS = 64; // slots in DevMeta::changed; the host loops if more are needed
+
+// Device-resident bookkeeping of one job; zeroed before every decode, read back once at the end.
+struct DevMeta {
+    uint32_t total_kept;   // unstuffed bytes
+    uint32_t total_rst;    // RSTn markers found
+    uint32_t total_bits;   // 8 * total_kept
+    uint32_t nsub;         // subsequences actually used
+    uint32_t status;       // ST_* bits
+    uint32_t exact_samples;
+    uint32_t colour_exact;
+    uint32_t final_slot;   // absolute slot the last subsequence ended on
+    uint32_t changed[MAX_RELAY_ROUNDS];
+};
+
+struct UnstuffArgs {
+    const uint8_t *scan; // stuffed entropy-coded bytes (device)
+    uint32_t scan_len;
+    uint32_t ntiles;
+    uint32_t *tile_kept, *tile_rst;      // per-tile counts, then (after the scan kernel) exclusive offsets
+    uint8_t *words;                      // unstuffed stream as big-endian 32-bit words (byte address ^ 3)
+    uint32_t *seg_bit;                   // [nseg + 2]
+    uint32_t nseg;                       // expected number of segments
+    DevMeta *meta;
+};
+
+constexpr int UNSTUFF_THREADS = 256;
+constexpr int UNSTUFF_BYTES_PER_THREAD = 16;
+constexpr int UNSTUFF_TILE = UNSTUFF_THREADS * UNSTUFF_BYTES_PER_THREAD;
+
+struct EntropyArgs {
+    const uint32_t *words;
+    const uint32_t *seg_bit;
+    const DeviceTables *tables;
+    DevMeta *meta;
+    SubState *state;      // [nsub_max] relay states X[i]
+    uint2 *used;          // [nsub_max] (p, cz) the state X[i] was computed from
+    uint32_t *seg_hint;   // [nsub_max]
+    uint32_t *start_slot; // [nsub_max] absolute slot at the entry of subsequence i
+    int16_t *coef;        // [total_blocks][64]
+    int16_t *dcdiff;      // [total_blocks]
+    uint32_t nsub_max;
+    JobGeom g;
+};
+
+constexpr int ENTROPY_THREADS = 128;
+
+struct DcArgs {
+    const int16_t *dcdiff;
+    int16_t *dc;
+    int32_t *tile_carry; // [ntiles][4]: per component running value at the end of the tile, [3] = "tile contains a reset"
+    uint32_t ntiles;
+    JobGeom g;
+};
+constexpr int DC_THREADS = 256;
+constexpr int DC_MCUS_PER_THREAD = 4;
+constexpr int DC_TILE = DC_THREADS * DC_MCUS_PER_THREAD;
+
+struct IdctArgs {
+    const int16_t *coef;
+    const int16_t *dc;
+    const int16_t *dcdiff;
+    const DeviceTables *tables;
+    uint8_t *pixels; // [nimages][height][width][ncomp]
+    DevMeta *meta;
+    JobGeom g;
+};
+constexpr int IDCT_MCUS_PER_CTA = 32;
+
+void kernels_configure(); // per-device function attributes (call once after cudaSetDevice)
+void launch_unstuff(const UnstuffArgs &a, uint32_t sub_bits, cudaStream_t s, uint32_t *launches);
+void launch_entropy_cold(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);
+void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint32_t *launches);
+void launch_entropy_scan_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);
+void launch_dc_scan(const DcArgs &a, cudaStream_t s, uint32_t *launches);
+void launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches);
+void launch_merge_dc(int16_t *coef_out, const int16_t *coef, const int16_t *dc, const int16_t *dcdiff, uint32_t nblocks,
+                     uint32_t flags, cudaStream_t s);
+
+} // namespace kpeg
+#endif

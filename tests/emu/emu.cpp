@@ -1,0 +1,319 @@
+// tests/emu/emu.cpp -- TEST INFRASTRUCTURE: single-steps the kernel logic of libkpeg_b200/csrc on
+// the CPU.  It includes the very same host+device inline headers the sm_100a kernels are built
+// from (unstuff_core.h, entropy_core.h, idct_core.h, host_tables.h) and replays, thread by
+// thread, what kernels.cu does with them -- so the speculative-decode / relay / offset-scan logic
+// and the two-tier IDCT + colour arithmetic can be checked against the oracle without a GPU.
+// It is NOT linked into libkpeg_cuda.so and nothing in the product calls it.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "entropy_core.h"
+#include "host_tables.h"
+#include "idct_core.h"
+#include "kpeg_cuda.h"
+#include "unstuff_core.h"
+
+using namespace kpeg;
+
+namespace {
+
+// K0 replay: unstuff_count / unstuff_scan / unstuff_write in one sequential sweep.
+void emu_unstuff(const uint8_t *scan, uint32_t len, uint32_t nseg, std::vector<uint8_t> &words,
+                 std::vector<uint32_t> &seg_bit, uint32_t *total_bits, uint32_t *status)
+{
+    words.assign(((size_t)len + 3) / 4 * 4 + 32, 0);
+    uint32_t pos = 0, ridx = 0, st = 0;
+    std::vector<uint32_t> seg_pos;
+    for (uint32_t base = 0; base < len; base += 16) {
+        const ByteClass c = classify16(scan, len, base);
+        if (c.bad)
+            st |= ST_BAD_MARKER;
+        for (int i = 0; i < 16; ++i) {
+            if (c.rst & (1u << i)) {
+                ++ridx;
+                seg_pos.push_back(pos * 8u);
+            }
+            if (c.keep & (1u << i)) {
+                words[pos ^ 3u] = (uint8_t)(c.b[i >> 2] >> (8 * (i & 3)));
+                ++pos;
+            }
+        }
+    }
+    *total_bits = pos * 8u;
+    seg_bit.assign((size_t)nseg + 2, *total_bits);
+    seg_bit[0] = 0;
+    seg_bit[nseg + 1] = 0xFFFFFFFFu;
+    for (uint32_t r = 1; r <= ridx; ++r)
+        if (r < nseg)
+            seg_bit[r] = seg_pos[r - 1];
+    if (ridx != nseg - 1 && ridx != nseg)
+        st |= ST_SEG_COUNT;
+    *status |= st;
+}
+
+uint32_t first_seg_at_or_after(const std::vector<uint32_t> &seg_bit, uint32_t nseg, uint32_t bit)
+{
+    uint32_t lo = 0, hi = nseg;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (seg_bit[mid] >= bit)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    return lo;
+}
+
+} // namespace
+
+extern "C" {
+
+// info[0]=status, [1]=nsub, [2]=relay rounds until the fixed point, [3]=exact IDCT samples,
+// [4]=exact colour pixels, [5]=total_bits, [6]=final_slot
+int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint32_t nimages, uint32_t sub_bits,
+               int16_t *coef_out, uint8_t *pixels_out, uint32_t *info)
+{
+    JobGeom g;
+    const char *why = nullptr;
+    int rc = make_job_geom(plan, nimages, sub_bits, &g, &why);
+    if (rc != KPEG_OK)
+        return rc;
+    DeviceTables *T = new DeviceTables;
+    rc = build_device_tables(plan, T, &why);
+    if (rc != KPEG_OK) {
+        delete T;
+        return rc;
+    }
+    uint32_t status = 0, total_bits = 0;
+    std::vector<uint8_t> words;
+    std::vector<uint32_t> seg_bit;
+    emu_unstuff(scan, (uint32_t)scan_len, g.nseg, words, seg_bit, &total_bits, &status);
+    uint32_t nsub = (total_bits + sub_bits - 1) / sub_bits;
+    if (!nsub)
+        nsub = 1;
+    StreamView S{(const uint32_t *)words.data(), seg_bit.data(), total_bits};
+
+    // K1 cold
+    std::vector<SubState> X(nsub);
+    std::vector<uint32_t> hint(nsub), used_p(nsub), used_cz(nsub);
+    for (uint32_t sub = 0; sub < nsub; ++sub) {
+        const uint32_t p0 = sub * sub_bits;
+        const uint32_t end = std::min(p0 + sub_bits, total_bits);
+        hint[sub] = g.nseg > 1 ? first_seg_at_or_after(seg_bit, g.nseg, p0) : (sub ? 1u : 0u);
+        X[sub] = decode_span<false>(S, g, T->lut, end, p0, 0, 0, hint[sub], 0, nullptr, nullptr, nullptr);
+        used_p[sub] = p0;
+        used_cz[sub] = 0;
+    }
+    // K1 relay (Jacobi-style rounds on a snapshot, like independent thread blocks would see it)
+    uint32_t rounds = 0;
+    for (;;) {
+        uint32_t changed = 0;
+        const std::vector<SubState> prev = X;
+        for (uint32_t sub = 1; sub < nsub; ++sub) {
+            const SubState in = prev[sub - 1];
+            if (used_p[sub] == in.p && used_cz[sub] == in.cz)
+                continue;
+            const uint32_t end = std::min((sub + 1) * sub_bits, total_bits);
+            const SubState out =
+                decode_span<false>(S, g, T->lut, end, in.p, in.cz >> 8, in.cz & 0xFF, hint[sub], 0, nullptr, nullptr, nullptr);
+            used_p[sub] = in.p;
+            used_cz[sub] = in.cz;
+            if (out.p != X[sub].p || out.cz != X[sub].cz || out.n != X[sub].n || out.seg != X[sub].seg) {
+                X[sub] = out;
+                ++changed;
+            }
+        }
+        if (!changed)
+            break;
+        ++rounds;
+        if (rounds > nsub + 2) {
+            delete T;
+            return KPEG_ERR_NOT_CONVERGED;
+        }
+    }
+    // K1 scan
+    std::vector<uint32_t> start(nsub);
+    uint32_t f = 1, v = 0;
+    for (uint32_t i = 0; i < nsub; ++i) {
+        start[i] = v;
+        const SubState st = X[i];
+        if (st.seg >= 0) {
+            f = 1;
+            v = st.n + seg_slot_base(g, (uint32_t)st.seg);
+        } else {
+            v += st.n;
+        }
+    }
+    (void)f;
+    const uint32_t final_slot = v;
+    // K1 write
+    std::vector<int16_t> coef((size_t)g.total_blocks * 64, 0), dcdiff(g.total_blocks, 0), dc(g.total_blocks, 0);
+    for (uint32_t sub = 0; sub < nsub; ++sub) {
+        uint32_t p = 0, c = 0, z = 0;
+        if (sub) {
+            p = X[sub - 1].p;
+            c = X[sub - 1].cz >> 8;
+            z = X[sub - 1].cz & 0xFF;
+        }
+        const uint32_t slot = start[sub];
+        uint32_t st = 0;
+        if ((slot & 63u) != z || ((slot >> 6) % g.ncomp) != c)
+            st |= ST_EXIT_MISMATCH;
+        const uint32_t end = std::min((sub + 1) * sub_bits, total_bits);
+        const SubState out = decode_span<true>(S, g, T->lut, end, p, c, z, hint[sub], slot, coef.data(), dcdiff.data(), &st);
+        if (out.p != X[sub].p || out.cz != X[sub].cz)
+            st |= ST_EXIT_MISMATCH;
+        status |= st;
+    }
+    if (final_slot < g.total_blocks * 64u)
+        status |= ST_SEG_MISMATCH;
+    // K2
+    {
+        int32_t pred[3] = {0, 0, 0};
+        const uint32_t total_mcus = g.nimages * g.mcus_per_image;
+        for (uint32_t m = 0; m < total_mcus; ++m) {
+            const uint32_t mi = m % g.mcus_per_image;
+            const bool reset = g.restart_interval ? (mi % g.restart_interval) == 0 : mi == 0;
+            if (reset)
+                pred[0] = pred[1] = pred[2] = 0;
+            for (uint32_t c = 0; c < g.ncomp; ++c) {
+                pred[c] += dcdiff[m * g.ncomp + c];
+                dc[m * g.ncomp + c] = (int16_t)pred[c];
+            }
+        }
+    }
+    // merged coefficients (what kpeg_cuda_read_coefficients returns)
+    std::vector<int16_t> merged((size_t)g.total_blocks * 64);
+    for (uint32_t b = 0; b < g.total_blocks; ++b) {
+        const bool drop = (g.flags & 1u) && dcdiff[b] == 0;
+        merged[(size_t)b * 64] = dc[b];
+        for (int i = 1; i < 64; ++i)
+            merged[(size_t)b * 64 + i] = drop ? (int16_t)0 : coef[(size_t)b * 64 + i];
+    }
+    if (coef_out)
+        memcpy(coef_out, merged.data(), merged.size() * 2);
+
+    // K3 replay, block by block
+    uint32_t exact = 0, colour_exact = 0;
+    if (pixels_out) {
+        static const ZigZagTables zz = make_zigzag_tables();
+        const uint32_t nc = g.ncomp;
+        const uint32_t total_mcus = g.nimages * g.mcus_per_image;
+        for (uint32_t m = 0; m < total_mcus; ++m) {
+            float samp[3][64];
+            for (uint32_t c = 0; c < nc; ++c) {
+                const int16_t *cz = &merged[((size_t)m * nc + c) * 64];
+                float fb[64];
+                for (int i = 0; i < 64; ++i)
+                    fb[zz.zz2nat[i]] = (float)cz[i] * T->qscale[c][i];
+                idct8x8_fast(fb);
+                float energy = 0.0f;
+                for (int s = 0; s < 64; ++s)
+                    energy = fmaf(fb[s], fb[s], energy);
+                const float thresh = 0.5f - tie_band(energy);
+                const float MAGIC = 12582912.0f;
+                for (int s = 0; s < 64; ++s) {
+                    volatile float t = fb[s] + MAGIC;
+                    float r = t - MAGIC;
+                    if (fabsf(fb[s] - r) > thresh) {
+                        auto at = [&](int zi) { return (int)cz[zi]; };
+                        r = (float)exact_sample(at, T->qint[c], T->cosd, T->cc, zz.nat2zz, s >> 3, s & 7);
+                        ++exact;
+                    }
+                    samp[c][s] = r;
+                }
+            }
+            const uint32_t img = m / g.mcus_per_image, mi = m % g.mcus_per_image;
+            const uint32_t by = mi / g.mcus_x, bx = mi % g.mcus_x;
+            uint8_t *base = pixels_out + (size_t)img * g.width * g.height * nc;
+            for (int s = 0; s < 64; ++s) {
+                const uint32_t y = by * 8 + (s >> 3), x = bx * 8 + (s & 7);
+                if (y >= g.height || x >= g.width)
+                    continue;
+                uint8_t *o = base + ((size_t)y * g.width + x) * nc;
+                if (nc == 3) {
+                    float R, G, B;
+                    if (!ycc_to_rgb_fast(samp[0][s], samp[1][s], samp[2][s], R, G, B)) {
+                        int r, gg, b;
+                        ycc_to_rgb_exact((int)samp[0][s], (int)samp[1][s], (int)samp[2][s], r, gg, b);
+                        R = (float)r;
+                        G = (float)gg;
+                        B = (float)b;
+                        ++colour_exact;
+                    }
+                    o[0] = (uint8_t)(int)R;
+                    o[1] = (uint8_t)(int)G;
+                    o[2] = (uint8_t)(int)B;
+                } else {
+                    const float vv = fminf(fmaxf(samp[0][s] + 128.0f, 0.0f), 255.0f);
+                    o[0] = (uint8_t)(int)vv;
+                }
+            }
+        }
+    }
+    if (info) {
+        info[0] = status;
+        info[1] = nsub;
+        info[2] = rounds;
+        info[3] = exact;
+        info[4] = colour_exact;
+        info[5] = total_bits;
+        info[6] = final_slot;
+    }
+    delete T;
+    return KPEG_OK;
+}
+
+// Two-tier colour conversion of one pixel (unshifted samples).  Returns 1 if the exact path ran.
+int emu_colour(int y, int cb, int cr, int rgb[3])
+{
+    float R, G, B;
+    if (ycc_to_rgb_fast((float)y, (float)cb, (float)cr, R, G, B)) {
+        rgb[0] = (int)R;
+        rgb[1] = (int)G;
+        rgb[2] = (int)B;
+        return 0;
+    }
+    ycc_to_rgb_exact(y, cb, cr, rgb[0], rgb[1], rgb[2]);
+    return 1;
+}
+
+// Fast-path IDCT of one block, no tie handling: out[64] floats (unshifted), returns the tie band.
+float emu_idct_fast(const int16_t zzc[64], const uint16_t qt[64], float out[64])
+{
+    static const ZigZagTables zz = make_zigzag_tables();
+    float fb[64];
+    for (int i = 0; i < 64; ++i) {
+        const int nat = zz.zz2nat[i];
+        const float qs = (float)((double)qt[i] * aan_scale(nat >> 3) * aan_scale(nat & 7) / 8.0);
+        fb[nat] = (float)zzc[i] * qs;
+    }
+    idct8x8_fast(fb);
+    float energy = 0.0f;
+    for (int s = 0; s < 64; ++s) {
+        out[s] = fb[s];
+        energy = fmaf(fb[s], fb[s], energy);
+    }
+    return tie_band(energy);
+}
+
+// Huffman LUT lookup of a left-aligned 32-bit window: returns the packed entry.
+uint32_t emu_huff_lookup(const uint8_t counts[16], const uint8_t *symbols, int is_ac, uint32_t win)
+{
+    HuffLut *L = new HuffLut;
+    uint32_t e = 0xFFFFFFFFu;
+    if (build_huff_lut(counts, symbols, is_ac != 0, L) == 0) {
+        e = L->fast[win >> (32 - LUT_BITS)];
+        if (!e)
+            e = huff_slow_lookup(*L, win);
+    }
+    delete L;
+    return e;
+}
+
+int emu_zigzag(int i) { return zigzag_to_natural(i); }
+
+} // extern "C"
