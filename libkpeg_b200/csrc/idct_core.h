@@ -222,7 +222,9 @@ KPEG_HD bool ycc_to_rgb_fast(float y, float cb, float cr, float &R, float &G, fl
     const float gf = floorf(g);
     const float gd = g - gf;
     const float m = fmaxf(fmaxf(fabsf(y), fabsf(cb)), fabsf(cr));
-    const bool ok = (gd > COLOUR_G_BAND) && (gd < 1.0f - COLOUR_G_BAND) && (m <= COLOUR_FAST_RANGE);
+    // cb == cr == 0 (flat chroma, gray-as-YCbCr files): every channel is exactly y + 128
+    const bool flat = (cb == 0.0f) && (cr == 0.0f);
+    const bool ok = (((gd > COLOUR_G_BAND) && (gd < 1.0f - COLOUR_G_BAND)) || flat) && (m <= COLOUR_FAST_RANGE);
     R = fminf(fmaxf(floorf(r), 0.0f), 255.0f);
     G = fminf(fmaxf(gf, 0.0f), 255.0f);
     B = fminf(fmaxf(floorf(b), 0.0f), 255.0f);
