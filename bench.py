@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- decode throughput of the B200 baseline-JPEG hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU decoder
+
+Workload (config.workload): BASELINE.json configs[2], the configuration the metric is quoted on --
+synthetic 3840x2160 RGB 4:4:4 baseline JPEGs, q=95, NO restart markers (one entropy segment per
+image, which forces the self-synchronising speculative Huffman decode).  One "step" decodes one
+batch of `--batch` such images per GPU (distinct seeds; 8 by default: 51 MB of bit stream, 398 MB of
+coefficients, 199 MB of pixels per step -- all far larger than the 126 MB L2, so no flush is needed
+between iterations).  Images come from the committed deterministic encoder (libkpeg_b200/host/
+synth_encoder.cpp); the reference's own encoder is non-functional.
+
+  value  : whole-job Mpixel/s with the packed bit streams already resident in HBM and the pixels left
+           in HBM (CUDA events on the decode stream, max over ranks).
+  e2e    : the same metric through the host-pointer C-ABI call (kpeg_cuda_decode_batch) with pinned
+           HOST buffers: packing, H2D of the bit streams and D2H of the pixels inside the timed region.
+  roofline / kernels : per-kernel CUDA-event times from the timed region, algorithmic bytes per launch
+           (DESIGN.md "Algorithmic bytes") and the fraction of the measured HBM peak.
+  cpu_baseline : the compiled, unmodified reference (oracle/_ref/kpeg_ref_quiet) on the box's host
+           cores, one process per core, on a bounded sample (512x512 images of the same generator).
+
+With torchrun (N > 1) every rank drives its own GPU on its own images (weak scaling, no collective in
+the data path; torch.distributed is used only for the barrier and the max-over-ranks of the time).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "decode_mpixel_per_s"
+UNIT = "Mpixel/s"
+W4K, H4K, Q4K = 3840, 2160, 95
+WORKLOAD = "synthetic 3840x2160 RGB 4:4:4 baseline q=95, no restart markers (BASELINE.json configs[2])"
+SEED0 = 0x6B706567
+REF_SAMPLE_WH = 512
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---- clocks sampling -------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        # NVML in-process (5 ms period); falls back to polling nvidia-smi if pynvml is unavailable
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            R = pynvml
+            while not self._stop.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                flags = ["Active" if rs & getattr(R, n, 0) else "Not Active" for n in (
+                    "nvmlClocksThrottleReasonHwSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown",
+                    "nvmlClocksThrottleReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwPowerCap")]
+                self.samples.append([str(sm), str(mx), str(pw), *flags])
+                self._stop.wait(0.005)
+            return
+        except Exception:
+            pass
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- reference arm / cpu baseline ---------------------------------------------------------------------
+def _ref_binary():
+    p = ROOT / "oracle" / "_ref" / "kpeg_ref_quiet"
+    return p if p.exists() and os.access(p, os.X_OK) else None
+
+
+def _ref_decode_one(binary, jpg_bytes, workdir):
+    d = tempfile.mkdtemp(dir=workdir)
+    p = Path(d) / "img.jpg"
+    p.write_bytes(jpg_bytes)
+    subprocess.run([str(binary), str(p)], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+    ok = (Path(d) / "img.ppm").exists()
+    return ok
+
+
+def _oracle_decode_one(jpg_bytes):
+    import helpers as H
+    H.oracle_decode(jpg_bytes, parity=True, want_pixels=True, threads=1)
+    return True
+
+
+def reference_step_runner(cores: int):
+    """Returns (kind, run_step, pixels_per_step, sample_description).  One step = `cores` images of
+    REF_SAMPLE_WH^2, one reference process per core (the reference is single-threaded and keeps
+    decoder state in statics, so one process per image: SURVEY F5)."""
+    from libkpeg_b200.synth import QUIRK_FREE, SynthParams, synth_encode
+    jpgs = [synth_encode(SynthParams(REF_SAMPLE_WH, REF_SAMPLE_WH, quality=Q4K, seed=SEED0 + 1000 + i,
+                                     flags=QUIRK_FREE)).tobytes() for i in range(cores)]
+    binary = _ref_binary()
+    workdir = tempfile.mkdtemp(prefix="kpeg_ref_")
+    pool = ThreadPoolExecutor(max_workers=cores)
+    if binary is not None:
+        kind = "reference"
+
+        def run_step():
+            assert all(pool.map(lambda j: _ref_decode_one(binary, j, workdir), jpgs))
+    else:
+        kind = "port"
+
+        def run_step():
+            assert all(pool.map(_oracle_decode_one, jpgs))
+    sample = (f"{cores} images {REF_SAMPLE_WH}x{REF_SAMPLE_WH} RGB 4:4:4 q={Q4K} no-RST from the same generator per step, "
+              f"one {'unmodified reference process (oracle/_ref/kpeg_ref_quiet: stock sources, log level ERROR)' if kind == 'reference' else 'oracle-port thread'} per core")
+    return kind, run_step, cores * REF_SAMPLE_WH * REF_SAMPLE_WH, sample
+
+
+def run_reference_arm(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    kind, run_step, px, sample = reference_step_runner(cores)
+    for _ in range(max(args.warmup, 0)):
+        run_step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run_step()
+    dt = time.perf_counter() - t0
+    value = px * args.steps / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32/f64 (CPU)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---- CUDA arm -----------------------------------------------------------------------------------------
+def run_cuda_arm(args):
+    import torch
+
+    import libkpeg_b200 as K
+    from libkpeg_b200.api import PinnedArray, pack_batch
+    from libkpeg_b200.synth import QUIRK_FREE, SynthParams, synth_encode
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    device = local if world > 1 else 0
+    torch.cuda.set_device(device)
+
+    NB = args.batch
+    W, Hh = args.width, args.height
+    # ---- inputs: NB distinct images per rank -----------------------------------------------------
+    jpgs = [synth_encode(SynthParams(W, Hh, quality=args.quality, seed=SEED0 + rank * 4096 + i, flags=QUIRK_FREE))
+            for i in range(NB)]
+    parsed = [K.parse_jfif(j) for j in jpgs]
+    plan = parsed[0][0]
+    plan.flags = K.KPEG_FLAG_REF_PARITY
+    scans = [j[o:o + n] for j, (_, o, n) in zip(jpgs, parsed)]
+    scan_bytes = int(sum(s.size for s in scans))
+    npix_img = W * Hh
+    pix_bytes_img = npix_img * 3
+
+    dec = K.Decoder(device=device)  # raises without the CUDA library / a GPU: no fallback
+    if args.sub_bits or args.relay_rounds:
+        dec.set_tuning(args.sub_bits, args.relay_rounds)
+    packed = pack_batch(scans)
+    d_packed = dec.device_alloc(packed.size + 64)
+    d_out = dec.device_alloc(NB * pix_bytes_img + 64)
+    dec.h2d(d_packed, packed)
+
+    stream = torch.cuda.ExternalStream(dec.stream, device=torch.device("cuda", device))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness gate (untimed): image 0 of this rank against the CPU oracle ------------------
+    import helpers as H
+    dec.decode_batch_packed_device(plan, NB, d_packed, packed.size, d_out)
+    got0 = np.empty((Hh, W, 3), dtype=np.uint8)
+    dec.d2h(got0, d_out)
+    nblk = (W // 8) * (Hh // 8) * 3
+    coef = dec.read_coefficients(nblk * NB)[:nblk]
+    ref = H.oracle_decode(jpgs[0], parity=True, want_pixels=(rank == 0 and not args.skip_pixel_check))
+    coef_ok = bool(np.array_equal(coef, ref["coef"]))
+    max_abs_err = None
+    if ref["pixels"] is not None:
+        max_abs_err = int(np.abs(got0.astype(np.int16) - ref["pixels"].astype(np.int16)).max())
+    if not coef_ok or (max_abs_err is not None and max_abs_err > 1):
+        raise SystemExit(f"bench: parity gate failed (coefficients equal: {coef_ok}, pixel max-abs-err: {max_abs_err})")
+
+    # ---- device-resident timing ------------------------------------------------------------------------
+    dec.set_profiling(True)
+    for _ in range(max(args.warmup, 3)):
+        dec.decode_batch_packed_device(plan, NB, d_packed, packed.size, d_out)
+    sampler = ClockSampler(device)
+    stage_ms = {k: 0.0 for k in K.Stats.STAGES}
+    launches = 0
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        dec.decode_batch_packed_device(plan, NB, d_packed, packed.size, d_out)
+        for k, v in dec.last_stats.stage_ms().items():
+            stage_ms[k] += v
+        launches += dec.last_stats.kernel_launches
+    ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    st = dec.last_stats
+    stats_snapshot = dict(subsequences=st.subsequences, sync_rounds=st.sync_rounds, exact_samples=st.exact_samples,
+                          unstuffed_bytes=int(st.unstuffed_bytes), launches_per_step=st.kernel_launches)
+    dec.set_profiling(False)
+
+    # ---- end to end: host pinned buffers in, host pinned buffers out -----------------------------------
+    pin_in = [PinnedArray(s.size) for s in scans]
+    for p, s in zip(pin_in, scans):
+        p.array[:] = s
+    pin_out = [PinnedArray(pix_bytes_img) for _ in range(NB)]
+    in_views = [p.array for p in pin_in]
+    out_views = [p.array.reshape(Hh, W, 3) for p in pin_out]
+    for _ in range(max(min(args.warmup, 3), 1)):
+        dec.decode_batch(plan, in_views, out_views)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dec.decode_batch(plan, in_views, out_views)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_ok = bool(np.array_equal(out_views[0], got0))
+    barrier()
+
+    # ---- max over ranks -----------------------------------------------------------------------------------
+    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=torch.device("cuda", device))
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(times[0]), float(times[1])
+    total_px = world * NB * npix_img * args.steps
+    value = total_px / (dev_ms_max / 1e3) / 1e6
+    e2e_value = total_px / (e2e_ms_max / 1e3) / 1e6
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        per_step = {k: v / args.steps for k, v in stage_ms.items()}
+        unstuffed = stats_snapshot["unstuffed_bytes"]
+        coef_bytes = NB * npix_img * 6
+        alg = {  # algorithmic bytes per launch group (DESIGN.md "Algorithmic bytes")
+            "unstuff": packed.size + unstuffed,
+            "entropy_cold": unstuffed,
+            "entropy_relay": unstuffed,
+            "entropy_write": unstuffed + coef_bytes,
+            "memset": coef_bytes,
+            "idct": NB * npix_img * 9,
+            "dc_scan": NB * (npix_img // 64) * 3 * 4,
+        }
+        kernels = {}
+        for k, ms in per_step.items():
+            if k in ("h2d", "d2h") or ms <= 0:
+                continue
+            e = {"ms_per_step": ms}
+            if k in alg:
+                e["algorithmic_bytes"] = alg[k]
+                e["achieved_gbs"] = alg[k] / (ms * 1e-3) / 1e9
+                e["frac_of_hbm_peak"] = e["achieved_gbs"] / peak
+            kernels[k] = e
+        dom = max((k for k in kernels if k != "memset"), key=lambda k: kernels[k]["ms_per_step"])
+        roof = lambda k: {"kernel": k, "bound": "hbm", "achieved": kernels[k].get("achieved_gbs"), "peak": peak,
+                          "unit": "GB/s", "frac": kernels[k].get("frac_of_hbm_peak"), "traffic": None,
+                          "peak_source": peak_src, "ms_per_launch_group": kernels[k]["ms_per_step"],
+                          "share_of_step": kernels[k]["ms_per_step"] / sum(x["ms_per_step"] for x in kernels.values())}
+        entropy_ms = sum(per_step[k] for k in ("unstuff", "entropy_cold", "entropy_relay", "entropy_scan",
+                                               "entropy_write", "dc_scan"))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/int16 entropy decode, f32 IDCT (f64 on the exact path)", "data": "synthetic",
+            "config": {"workload": WORKLOAD if (W, Hh, args.quality) == (W4K, H4K, Q4K) else f"synthetic {W}x{Hh} q={args.quality}",
+                       "images_per_step_per_gpu": NB, "width": W, "height": Hh, "quality": args.quality,
+                       "restart_interval": 0, "parallelism": f"{world} GPU(s), images sharded, no collective",
+                       "l2_policy": "inputs larger than L2 (no flush): per step %.0f MB bit stream + %.0f MB coefficients + %.0f MB pixels"
+                                    % (packed.size / 1e6, coef_bytes / 1e6, NB * pix_bytes_img / 1e6),
+                       "sub_bits": args.sub_bits or "default", "parity_mode": "reference (F1 quirk on)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(packed.size),
+                    "d2h_bytes_per_step": int(NB * pix_bytes_img), "ms_per_step": e2e_ms_max / args.steps,
+                    "timer": "host wall clock around kpeg_cuda_decode_batch (pinned host buffers in and out)",
+                    "matches_device_path": e2e_ok},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof(dom),
+            "roofline_idct": roof("idct"),
+            "kernels": kernels,
+            "entropy_bitstream_gbs": scan_bytes / (entropy_ms * 1e-3) / 1e9 if entropy_ms > 0 else None,
+            "parity": {"coefficients_bit_exact": coef_ok, "pixel_max_abs_err_vs_oracle": max_abs_err,
+                       "checked": "image 0 of rank 0 against the CPU oracle before timing"},
+            "decode_stats": stats_snapshot,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            kind, run_step, px, sample = reference_step_runner(cores)
+            run_step()
+            t0 = time.perf_counter()
+            reps = 0
+            while reps < 2 or (time.perf_counter() - t0 < 10 and reps < 8):
+                run_step()
+                reps += 1
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": px * reps / dt / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": sample + f"; {reps} timed steps"}
+        print(json.dumps(line), flush=True)
+
+    for p in pin_in + pin_out:
+        p.free()
+    dec.device_free(d_packed)
+    dec.device_free(d_out)
+    dec.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="images per step per GPU")
+    ap.add_argument("--width", type=int, default=W4K)
+    ap.add_argument("--height", type=int, default=H4K)
+    ap.add_argument("--quality", type=int, default=Q4K)
+    ap.add_argument("--sub-bits", type=int, default=0)
+    ap.add_argument("--relay-rounds", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-pixel-check", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_cuda_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -61,6 +61,21 @@ typedef struct kpeg_plan {
     kpeg_huff_spec ht[2][4];    /* [class 0=DC,1=AC][id] */
 } kpeg_plan;
 
+/* Stages timed with CUDA events on the decode stream while profiling is on. */
+enum {
+    KPEG_T_H2D = 0,        /* host -> device copy of the scan (host-pointer entry points only)            */
+    KPEG_T_MEMSET,         /* zero-fill of bookkeeping, bit stream tail and coefficient buffer            */
+    KPEG_T_UNSTUFF,        /* K0: unstuff_count + unstuff_scan + unstuff_write                            */
+    KPEG_T_ENTROPY_COLD,   /* K1: speculative cold decode of every subsequence                            */
+    KPEG_T_ENTROPY_RELAY,  /* K1: relay rounds up to the fixed point                                      */
+    KPEG_T_ENTROPY_SCAN,   /* K1: segmented offset scan                                                   */
+    KPEG_T_ENTROPY_WRITE,  /* K1: final decode writing coefficients                                       */
+    KPEG_T_DC_SCAN,        /* K2                                                                          */
+    KPEG_T_IDCT,           /* K3: fused dequant + IDCT + colour + store                                   */
+    KPEG_T_D2H,            /* device -> host copy of the pixels (host-pointer entry points only)          */
+    KPEG_T_COUNT
+};
+
 /* Per-decode statistics.  Stage times are filled only while profiling is enabled
  * (kpeg_cuda_set_profiling); they are CUDA-event times on the decode stream, in milliseconds. */
 typedef struct kpeg_stats {
@@ -71,7 +86,8 @@ typedef struct kpeg_stats {
     uint32_t subsequences;      /* speculative decode units                               */
     uint32_t sync_rounds;       /* fix-up rounds that ran until the relay reached a fixed point */
     uint32_t exact_samples;     /* IDCT samples re-evaluated on the exact (reference-order) path */
-    float ms_h2d, ms_unstuff, ms_entropy, ms_dc_scan, ms_idct, ms_d2h, ms_total;
+    float ms[KPEG_T_COUNT];     /* per-stage CUDA-event time, indexed by KPEG_T_* */
+    float ms_total;             /* first to last event of the call */
     uint32_t kernel_launches;   /* kernels launched for this decode */
 } kpeg_stats;
 
@@ -95,7 +111,7 @@ int kpeg_cuda_device_count(void);
 int kpeg_cuda_set_profiling(kpeg_ctx *ctx, int on);
 /* Tuning knobs of the speculative entropy decode (0 = leave unchanged): bits per subsequence
  * (multiple of 32, 64..65536; default 512 or $KPEG_SUB_BITS) and the number of relay rounds issued
- * up front (>= 2; default 4 or $KPEG_RELAY_ROUNDS; more are added automatically when needed). */
+ * up front (>= 2; default 8 or $KPEG_RELAY_ROUNDS; more are added automatically when needed). */
 int kpeg_cuda_set_tuning(kpeg_ctx *ctx, int sub_bits, int relay_rounds);
 /* The CUDA stream (cudaStream_t) all of this context's work is issued on. */
 void *kpeg_cuda_stream(kpeg_ctx *ctx);

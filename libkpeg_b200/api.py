@@ -53,13 +53,20 @@ class Stats(C.Structure):
         ("scan_bytes", C.c_uint64), ("unstuffed_bytes", C.c_uint64),
         ("segments", C.c_uint32), ("subsequences", C.c_uint32), ("sync_rounds", C.c_uint32),
         ("exact_samples", C.c_uint32),
-        ("ms_h2d", C.c_float), ("ms_unstuff", C.c_float), ("ms_entropy", C.c_float), ("ms_dc_scan", C.c_float),
-        ("ms_idct", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
+        ("ms", C.c_float * 10), ("ms_total", C.c_float),
         ("kernel_launches", C.c_uint32),
     ]
 
+    STAGES = ("h2d", "memset", "unstuff", "entropy_cold", "entropy_relay", "entropy_scan", "entropy_write", "dc_scan",
+              "idct", "d2h")
+
+    def stage_ms(self) -> dict:
+        return {name: float(self.ms[i]) for i, name in enumerate(self.STAGES)}
+
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "ms"}
+        d["ms"] = self.stage_ms()
+        return d
 
 
 # every symbol include/kpeg_cuda.h declares: (restype, argtypes)

@@ -67,7 +67,7 @@ struct BitWindow {
 };
 
 // Codes longer than LUT_BITS: canonical search.  `win` holds the next 32 stream bits, MSB first.
-KPEG_HD uint32_t huff_slow_lookup(const HuffLut &L, uint32_t win)
+KPEG_HD uint32_t huff_slow_lookup(const HuffCanon &L, uint32_t win)
 {
     const uint32_t w16 = win >> 16;
     for (int len = LUT_BITS + 1; len <= 16; ++len) {
@@ -98,7 +98,7 @@ struct StreamView {
 //                    go to coef[] (zig-zag order, buffer pre-zeroed), DC differences to dcdiff[].
 // `k` is a hint: any segment index whose start bit is <= the first boundary after p.
 template <bool WRITE>
-KPEG_HD SubState decode_span(const StreamView &S, const JobGeom &g, const HuffLut *luts, uint32_t end_bit,
+KPEG_HD SubState decode_span(const StreamView &S, const JobGeom &g, const LutSet &luts, const HuffCanon *canon, uint32_t end_bit,
                              uint32_t p, uint32_t c, uint32_t z, uint32_t k, uint32_t slot, int16_t *coef,
                              int16_t *dcdiff, uint32_t *status_accum)
 {
@@ -115,10 +115,12 @@ KPEG_HD SubState decode_span(const StreamView &S, const JobGeom &g, const HuffLu
     bw.seek(p);
     while (p < end_bit) {
         const uint32_t win = bw.peek(p);
-        const HuffLut &L = luts[c * 2u + (z != 0u ? 1u : 0u)];
-        uint32_t e = L.fast[win >> (32 - LUT_BITS)];
-        if (e == 0u)
-            e = huff_slow_lookup(L, win);
+        const uint32_t ti = c * 2u + (z != 0u ? 1u : 0u);
+        uint32_t e = luts.fast[ti][win >> (32 - LUT_BITS)];
+        if (e == 0u) { // code longer than LUT_BITS (or no code at all)
+            const uint32_t li = (win >> 16) - luts.long_base[ti];
+            e = li < luts.long_n[ti] ? (uint32_t)luts.longlut[ti][li] : huff_slow_lookup(canon[ti], win);
+        }
         const uint32_t len = e & 31u, size = (e >> 5) & 15u, adv = e >> 9;
         const uint32_t T = len + size;
         if (p + T > segend) {

@@ -27,8 +27,8 @@ inline int build_device_tables(const kpeg_plan *pl, DeviceTables *T, const char 
             *why = "plan references a table that was never defined";
             return KPEG_ERR_FORMAT;
         }
-        if (build_huff_lut(pl->ht[0][td].counts, pl->ht[0][td].symbols, false, &T->lut[c * 2 + 0]) ||
-            build_huff_lut(pl->ht[1][ta].counts, pl->ht[1][ta].symbols, true, &T->lut[c * 2 + 1])) {
+        if (build_huff_lut(pl->ht[0][td].counts, pl->ht[0][td].symbols, false, &T->luts, c * 2 + 0, &T->canon[c * 2 + 0]) ||
+            build_huff_lut(pl->ht[1][ta].counts, pl->ht[1][ta].symbols, true, &T->luts, c * 2 + 1, &T->canon[c * 2 + 1])) {
             *why = "over-subscribed Huffman table";
             return KPEG_ERR_FORMAT;
         }

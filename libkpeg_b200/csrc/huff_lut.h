@@ -14,34 +14,56 @@
 
 namespace kpeg {
 
-// Returns 0 on success, -1 if the counts over-subscribe the code space or exceed 256 symbols.
-inline int build_huff_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_ac, HuffLut *out)
+// Fills table `ti` of `set` and its canonical twin.  Returns 0 on success, -1 if the counts
+// over-subscribe the code space or exceed 256 symbols.
+inline int build_huff_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_ac, LutSet *set, int ti, HuffCanon *canon)
 {
-    memset(out, 0, sizeof *out);
-    out->is_ac = is_ac ? 1u : 0u;
+    memset(canon, 0, sizeof *canon);
+    memset(set->fast[ti], 0, sizeof set->fast[ti]);
+    memset(set->longlut[ti], 0, sizeof set->longlut[ti]);
+    canon->is_ac = is_ac ? 1u : 0u;
     uint32_t code = 0, idx = 0;
     for (int L = 1; L <= 16; ++L) {
-        out->first_code[L] = (uint16_t)code;
-        out->first_idx[L] = (uint16_t)idx;
+        canon->first_code[L] = (uint16_t)code;
+        canon->first_idx[L] = (uint16_t)idx;
         for (uint32_t k = 0; k < counts[L - 1]; ++k) {
             if (idx >= 256 || code >= (1u << L))
                 return -1;
-            uint8_t sym = symbols[idx];
-            out->symbols[idx] = sym;
-            if (L <= LUT_BITS) {
-                uint32_t e = pack_entry((uint32_t)L, sym, is_ac);
-                uint32_t lo = code << (LUT_BITS - L), hi = (code + 1) << (LUT_BITS - L);
-                for (uint32_t w = lo; w < hi; ++w)
-                    out->fast[w] = (uint16_t)e;
-            }
+            canon->symbols[idx] = symbols[idx];
             ++code;
             ++idx;
         }
-        out->bound[L] = code << (16 - L); // codes of length <= L cover left-aligned windows [0, bound[L])
+        canon->bound[L] = code << (16 - L); // codes of length <= L cover left-aligned windows [0, bound[L])
         code <<= 1;
     }
-    out->bound[0] = 0;
-    out->bound[17] = 0;
+    // first level: every code of length <= LUT_BITS
+    idx = 0;
+    for (int L = 1; L <= LUT_BITS; ++L) {
+        for (uint32_t k = 0; k < counts[L - 1]; ++k, ++idx) {
+            const uint32_t c = canon->first_code[L] + k;
+            const uint32_t e = pack_entry((uint32_t)L, symbols[idx], is_ac);
+            for (uint32_t w = c << (LUT_BITS - L); w < (c + 1) << (LUT_BITS - L); ++w)
+                set->fast[ti][w] = (uint16_t)e;
+        }
+    }
+    // second level: windows in [bound[LUT_BITS], 65536)
+    const uint32_t base = canon->bound[LUT_BITS];
+    set->long_base[ti] = base;
+    set->long_n[ti] = 0;
+    if (65536u - base <= (uint32_t)LONG_CAP) {
+        set->long_n[ti] = 65536u - base;
+        for (uint32_t w = base; w < 65536u; ++w) {
+            uint32_t e = ENTRY_INVALID;
+            for (int L = LUT_BITS + 1; L <= 16; ++L) {
+                if (w < canon->bound[L]) {
+                    const uint32_t i = canon->first_idx[L] + ((w >> (16 - L)) - canon->first_code[L]);
+                    e = pack_entry((uint32_t)L, canon->symbols[i & 255u], is_ac);
+                    break;
+                }
+            }
+            set->longlut[ti][w - base] = (uint16_t)e;
+        }
+    }
     return 0;
 }
 

@@ -19,6 +19,7 @@
 #define KPEG_IDCT_CORE_H
 
 #include <math.h>
+#include <string.h>
 
 #include "kpeg_common.h"
 
@@ -203,33 +204,52 @@ KPEG_HD void ycc_to_rgb_exact(int y, int cb, int cr, int &R, int &G, int &B)
     B = B < 0 ? 0 : (B > 255 ? 255 : B);
 }
 
-// fp32 evaluation, valid when |y|,|cb|,|cr| <= COLOUR_FAST_RANGE:
+// fp32 evaluation, valid when |y|,|cb|,|cr| <= COLOUR_FAST_RANGE (all integer-valued):
 //  * 1.402 d = 701 d / 500 and 1.772 d = 443 d / 250 are either integers or at least 0.002 away
-//    from one; with the +0.001 bias and < 5e-4 of fp32 error the floor cannot flip, and for the
-//    integer case the double expression of the reference yields that integer too (checked
+//    from one; with a +0.001 bias and < 5e-4 of accumulated fp32 error the floor cannot flip, and
+//    for the integer case the reference's double expression yields that integer too (checked
 //    exhaustively by tests/test_idct_core.py);
 //  * G's fraction is a multiple of 8e-6: if the fp32 value is closer than COLOUR_G_BAND to an
-//    integer the caller must use ycc_to_rgb_exact (returns false).
-constexpr float COLOUR_FAST_RANGE = 2000.0f;
+//    integer the caller must use ycc_to_rgb_exact (returns false);
+//  * floor(v) is taken as rint(v - 0.5) through the 1.5*2^23 magic-number add, which is exact for
+//    any v that is not within the error bound of an integer -- guaranteed by the two points above.
+// Outputs are unclamped integers.
+constexpr float COLOUR_FAST_RANGE = 1023.0f;
 constexpr float COLOUR_G_BAND = 1.0e-3f;
+constexpr float RINT_MAGIC = 12582912.0f; // 1.5 * 2^23 == 0x4B400000
+constexpr int32_t RINT_MAGIC_BITS = 0x4B400000;
 
-KPEG_HD bool ycc_to_rgb_fast(float y, float cb, float cr, float &R, float &G, float &B)
+KPEG_HD int32_t float_bits(float x)
 {
-    const float yc = y + 128.001f; // level shift + bias
-    const float r = fmaf(1.402f, cr, yc);
-    const float b = fmaf(1.772f, cb, yc);
-    const float g = fmaf(-0.714136f, cr, fmaf(-0.344136f, cb, y + 128.0f));
-    const float gf = floorf(g);
-    const float gd = g - gf;
-    const float m = fmaxf(fmaxf(fabsf(y), fabsf(cb)), fabsf(cr));
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(x);
+#else
+    int32_t i;
+    memcpy(&i, &x, 4);
+    return i;
+#endif
+}
+
+KPEG_HD bool ycc_to_rgb_fast(float y, float cb, float cr, int &R, int &G, int &B)
+{
+    const float yr = y + 127.501f; // +128 level shift, +0.001 bias, -0.5 (floor by rint)
+    const float yg = y + 127.5f;
+    const float tr = fmaf(1.402f, cr, yr) + RINT_MAGIC;
+    const float tb = fmaf(1.772f, cb, yr) + RINT_MAGIC;
+    const float g = fmaf(-0.714136f, cr, fmaf(-0.344136f, cb, yg));
+    const float tg = g + RINT_MAGIC;
+    const float dg = g - (tg - RINT_MAGIC); // |dg| close to 0.5 <=> the true G is close to an integer
+    R = float_bits(tr) - RINT_MAGIC_BITS;
+    B = float_bits(tb) - RINT_MAGIC_BITS;
+    G = float_bits(tg) - RINT_MAGIC_BITS;
     // cb == cr == 0 (flat chroma, gray-as-YCbCr files): every channel is exactly y + 128
     const bool flat = (cb == 0.0f) && (cr == 0.0f);
-    const bool ok = (((gd > COLOUR_G_BAND) && (gd < 1.0f - COLOUR_G_BAND)) || flat) && (m <= COLOUR_FAST_RANGE);
-    R = fminf(fmaxf(floorf(r), 0.0f), 255.0f);
-    G = fminf(fmaxf(gf, 0.0f), 255.0f);
-    B = fminf(fmaxf(floorf(b), 0.0f), 255.0f);
-    return ok;
+    G = flat ? R : G;
+    const float m = fmaxf(fmaxf(fabsf(y), fabsf(cb)), fabsf(cr));
+    return ((fabsf(dg) < 0.5f - COLOUR_G_BAND) || flat) && (m <= COLOUR_FAST_RANGE);
 }
+
+KPEG_HD int clamp_u8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 
 } // namespace kpeg
 #endif

@@ -180,13 +180,29 @@ void launch_unstuff(const UnstuffArgs &a, uint32_t sub_bits, cudaStream_t s, uin
 // K1: entropy decode
 // =================================================================================================
 
-__device__ __forceinline__ void load_luts_to_smem(HuffLut *s_lut, const DeviceTables *t, uint32_t ncomp)
+// Copies the tables a CTA needs into shared memory: the first level of every table in use and
+// only the populated part of the second level.
+__device__ __forceinline__ void load_luts_to_smem(LutSet &s_lut, const DeviceTables *t, uint32_t ncomp)
 {
-    const uint4 *src = reinterpret_cast<const uint4 *>(t->lut);
-    uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-    const uint32_t n = ncomp * 2u * (uint32_t)(sizeof(HuffLut) / 16);
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
-        dst[i] = __ldg(src + i);
+    const uint32_t nt = ncomp * 2u;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(&t->luts.fast[0][0]);
+        uint4 *dst = reinterpret_cast<uint4 *>(&s_lut.fast[0][0]);
+        const uint32_t n = nt * (uint32_t)(LUT_SIZE * sizeof(uint16_t) / 16);
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+            dst[i] = __ldg(src + i);
+    }
+    if (threadIdx.x < MAX_LUTS) {
+        s_lut.long_base[threadIdx.x] = t->luts.long_base[threadIdx.x];
+        s_lut.long_n[threadIdx.x] = t->luts.long_n[threadIdx.x];
+    }
+    for (uint32_t ti = 0; ti < nt; ++ti) {
+        const uint32_t n = (t->luts.long_n[ti] * (uint32_t)sizeof(uint16_t) + 15u) / 16u;
+        const uint4 *src = reinterpret_cast<const uint4 *>(&t->luts.longlut[ti][0]);
+        uint4 *dst = reinterpret_cast<uint4 *>(&s_lut.longlut[ti][0]);
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+            dst[i] = __ldg(src + i);
+    }
     __syncthreads();
 }
 
@@ -206,7 +222,7 @@ __device__ __forceinline__ uint32_t first_seg_at_or_after(const uint32_t *seg_bi
 
 __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_cold_kernel(EntropyArgs a)
 {
-    __shared__ __align__(16) HuffLut s_lut[MAX_COMP * 2];
+    __shared__ __align__(16) LutSet s_lut;
     load_luts_to_smem(s_lut, a.tables, a.g.ncomp);
     const uint32_t sub = blockIdx.x * ENTROPY_THREADS + threadIdx.x;
     const uint32_t nsub = a.meta->nsub, total_bits = a.meta->total_bits;
@@ -217,7 +233,7 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_cold_kernel(EntropyAr
     const uint32_t end = min(p0 + a.g.sub_bits, total_bits);
     const uint32_t hint = a.g.nseg > 1u ? first_seg_at_or_after(a.seg_bit, a.g.nseg, p0) : (sub ? 1u : 0u);
     a.seg_hint[sub] = hint;
-    const SubState out = decode_span<false>(S, a.g, s_lut, end, p0, 0u, 0u, hint, 0u, nullptr, nullptr, nullptr);
+    const SubState out = decode_span<false>(S, a.g, s_lut, a.tables->canon, end, p0, 0u, 0u, hint, 0u, nullptr, nullptr, nullptr);
     a.state[sub] = out;
     a.used[sub] = make_uint2(p0, 0u);
 }
@@ -227,7 +243,7 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_kernel(EntropyA
 {
     if (round > 1 && a.meta->changed[round - 1] == 0u)
         return; // already at the fixed point
-    __shared__ __align__(16) HuffLut s_lut[MAX_COMP * 2];
+    __shared__ __align__(16) LutSet s_lut;
     load_luts_to_smem(s_lut, a.tables, a.g.ncomp);
     const uint32_t sub = blockIdx.x * ENTROPY_THREADS + threadIdx.x;
     const uint32_t nsub = a.meta->nsub, total_bits = a.meta->total_bits;
@@ -241,7 +257,7 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_kernel(EntropyA
     StreamView S{a.words, a.seg_bit, total_bits};
     const uint32_t end = min((sub + 1u) * a.g.sub_bits, total_bits);
     const SubState out =
-        decode_span<false>(S, a.g, s_lut, end, in_p, in_cz >> 8, in_cz & 0xFFu, a.seg_hint[sub], 0u, nullptr, nullptr, nullptr);
+        decode_span<false>(S, a.g, s_lut, a.tables->canon, end, in_p, in_cz >> 8, in_cz & 0xFFu, a.seg_hint[sub], 0u, nullptr, nullptr, nullptr);
     a.used[sub] = make_uint2(in_p, in_cz);
     const SubState old = a.state[sub];
     if (old.p != out.p || old.cz != out.cz || old.n != out.n || old.seg != out.seg) {
@@ -256,91 +272,146 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_kernel(EntropyA
 }
 
 // Segmented exclusive scan of the slot counts: start_slot[i] = absolute coefficient slot at the
-// entry of subsequence i.  An element that crossed a segment boundary carries an absolute value.
-__global__ void __launch_bounds__(1024) entropy_scan_kernel(EntropyArgs a)
+// entry of subsequence i.  An element that crossed a segment boundary carries an absolute value
+// (flag f = 1), otherwise a relative count.  Three phases: per-tile aggregate, one-block scan of the
+// aggregates, per-tile scan seeded with the tile's carry.
+struct SegVal {
+    uint32_t f, v;
+};
+
+__device__ __forceinline__ SegVal seg_combine(const SegVal &a, const SegVal &b) // a then b
 {
-    __shared__ uint32_t s_f[33], s_v[33];
-    __shared__ uint32_t s_cf, s_cv;
-    const uint32_t nsub = a.meta->nsub;
+    SegVal r;
+    r.f = a.f | b.f;
+    r.v = b.f ? b.v : a.v + b.v;
+    return r;
+}
+
+constexpr int SCAN_THREADS = 1024;
+
+// inclusive scan across the block; s_w must hold SCAN_THREADS/32 entries
+__device__ __forceinline__ SegVal block_seg_scan(SegVal x, SegVal *s_w, SegVal &aggregate)
+{
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        s_cf = 1u; // virtual element -1: absolute slot 0 (segment 0 starts at bit 0)
-        s_cv = 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        SegVal o;
+        o.f = __shfl_up_sync(0xffffffffu, x.f, d);
+        o.v = __shfl_up_sync(0xffffffffu, x.v, d);
+        if (lane >= d)
+            x = seg_combine(o, x);
     }
+    if (lane == 31)
+        s_w[warp] = x;
     __syncthreads();
-    for (uint32_t i0 = 0; i0 < nsub; i0 += 1024) {
-        const uint32_t i = i0 + threadIdx.x;
-        uint32_t f = 0, v = 0;
-        if (i < nsub) {
-            const SubState st = a.state[i];
-            f = st.seg >= 0 ? 1u : 0u;
-            v = st.n + (f ? seg_slot_base(a.g, (uint32_t)st.seg) : 0u);
-        }
-        // warp inclusive segmented scan
+    if (warp == 0) {
+        SegVal w = s_w[lane];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t of = __shfl_up_sync(0xffffffffu, f, d);
-            const uint32_t ov = __shfl_up_sync(0xffffffffu, v, d);
-            if (lane >= d) {
-                if (!f)
-                    v += ov;
-                f |= of;
-            }
+            SegVal o;
+            o.f = __shfl_up_sync(0xffffffffu, w.f, d);
+            o.v = __shfl_up_sync(0xffffffffu, w.v, d);
+            if (lane >= d)
+                w = seg_combine(o, w);
         }
-        if (lane == 31) {
-            s_f[warp] = f;
-            s_v[warp] = v;
+        s_w[lane] = w;
+    }
+    __syncthreads();
+    if (warp > 0)
+        x = seg_combine(s_w[warp - 1], x);
+    aggregate = s_w[SCAN_THREADS / 32 - 1];
+    return x;
+}
+
+__device__ __forceinline__ SegVal load_seg_val(const EntropyArgs &a, uint32_t i, uint32_t nsub)
+{
+    SegVal e;
+    e.f = 0;
+    e.v = 0;
+    if (i < nsub) {
+        const SubState st = a.state[i];
+        e.f = st.seg >= 0 ? 1u : 0u;
+        e.v = st.n + (e.f ? seg_slot_base(a.g, (uint32_t)st.seg) : 0u);
+    }
+    return e;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) entropy_scan_reduce_kernel(EntropyArgs a)
+{
+    __shared__ SegVal s_w[SCAN_THREADS / 32];
+    const uint32_t nsub = a.meta->nsub;
+    if (blockIdx.x * SCAN_THREADS >= nsub)
+        return;
+    SegVal agg;
+    block_seg_scan(load_seg_val(a, blockIdx.x * SCAN_THREADS + threadIdx.x, nsub), s_w, agg);
+    if (threadIdx.x == 0)
+        a.scan_tiles[blockIdx.x] = make_uint2(agg.f, agg.v);
+}
+
+// one block: scan_tiles[t] <- value carried INTO tile t; also the final slot of the stream
+__global__ void __launch_bounds__(SCAN_THREADS) entropy_scan_tiles_kernel(EntropyArgs a)
+{
+    __shared__ SegVal s_w[SCAN_THREADS / 32];
+    __shared__ SegVal s_carry;
+    __shared__ SegVal s_incl[SCAN_THREADS];
+    const uint32_t nsub = a.meta->nsub;
+    const uint32_t ntiles = (nsub + SCAN_THREADS - 1) / SCAN_THREADS;
+    if (threadIdx.x == 0) {
+        s_carry.f = 1u; // virtual element -1: absolute slot 0 (segment 0 starts at bit 0)
+        s_carry.v = 0u;
+    }
+    __syncthreads();
+    for (uint32_t t0 = 0; t0 < ntiles; t0 += SCAN_THREADS) {
+        const uint32_t t = t0 + threadIdx.x;
+        SegVal e;
+        e.f = 0;
+        e.v = 0;
+        if (t < ntiles) {
+            const uint2 r = a.scan_tiles[t];
+            e.f = r.x;
+            e.v = r.y;
+        }
+        SegVal agg;
+        const SegVal incl = seg_combine(s_carry, block_seg_scan(e, s_w, agg));
+        s_incl[threadIdx.x] = incl;
+        __syncthreads();
+        if (t < ntiles) {
+            const SegVal ex = threadIdx.x == 0 ? s_carry : s_incl[threadIdx.x - 1];
+            a.scan_tiles[t] = make_uint2(ex.f, ex.v);
+            if (t + 1u == ntiles)
+                a.meta->final_slot = incl.v;
         }
         __syncthreads();
-        if (warp == 0) {
-            uint32_t wf = s_f[lane], wv = s_v[lane];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t of = __shfl_up_sync(0xffffffffu, wf, d);
-                const uint32_t ov = __shfl_up_sync(0xffffffffu, wv, d);
-                if (lane >= d) {
-                    if (!wf)
-                        wv += ov;
-                    wf |= of;
-                }
-            }
-            s_f[lane] = wf; // inclusive over warps
-            s_v[lane] = wv;
-        }
-        __syncthreads();
-        // carry from previous warps of this chunk, then from previous chunks
-        uint32_t cf = s_cf, cv = s_cv;
-        if (warp > 0) {
-            const uint32_t pf = s_f[warp - 1], pv = s_v[warp - 1];
-            if (pf) {
-                cf = 1u;
-                cv = pv;
-            } else {
-                cv += pv;
-            }
-        }
-        if (!f)
-            v += cv;
-        f |= cf;
-        // v is now the inclusive value at i == the entry slot of subsequence i+1
-        if (i + 1u < nsub)
-            a.start_slot[i + 1u] = v;
-        if (i == 0u)
-            a.start_slot[0] = 0u;
-        if (i + 1u == nsub)
-            a.meta->final_slot = v;
-        __syncthreads();
-        if (threadIdx.x == 1023) {
-            s_cf = f;
-            s_cv = v;
-        }
+        if (threadIdx.x == SCAN_THREADS - 1)
+            s_carry = incl;
         __syncthreads();
     }
 }
 
+__global__ void __launch_bounds__(SCAN_THREADS) entropy_scan_apply_kernel(EntropyArgs a)
+{
+    __shared__ SegVal s_w[SCAN_THREADS / 32];
+    const uint32_t nsub = a.meta->nsub;
+    if (blockIdx.x * SCAN_THREADS >= nsub)
+        return;
+    const uint32_t i = blockIdx.x * SCAN_THREADS + threadIdx.x;
+    SegVal agg;
+    SegVal incl = block_seg_scan(load_seg_val(a, i, nsub), s_w, agg);
+    const uint2 c = a.scan_tiles[blockIdx.x];
+    SegVal carry;
+    carry.f = c.x;
+    carry.v = c.y;
+    incl = seg_combine(carry, incl);
+    // incl = absolute slot at the END of subsequence i == entry of subsequence i+1
+    if (i + 1u < nsub)
+        a.start_slot[i + 1u] = incl.v;
+    if (i == 0u)
+        a.start_slot[0] = 0u;
+}
+
 __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_write_kernel(EntropyArgs a)
 {
-    __shared__ __align__(16) HuffLut s_lut[MAX_COMP * 2];
+    __shared__ __align__(16) LutSet s_lut;
     load_luts_to_smem(s_lut, a.tables, a.g.ncomp);
     const uint32_t sub = blockIdx.x * ENTROPY_THREADS + threadIdx.x;
     const uint32_t nsub = a.meta->nsub, total_bits = a.meta->total_bits;
@@ -359,7 +430,7 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_write_kernel(EntropyA
         st |= ST_EXIT_MISMATCH;
     StreamView S{a.words, a.seg_bit, total_bits};
     const uint32_t end = min((sub + 1u) * a.g.sub_bits, total_bits);
-    const SubState out = decode_span<true>(S, a.g, s_lut, end, p, c, z, a.seg_hint[sub], slot, a.coef, a.dcdiff, &st);
+    const SubState out = decode_span<true>(S, a.g, s_lut, a.tables->canon, end, p, c, z, a.seg_hint[sub], slot, a.coef, a.dcdiff, &st);
     const SubState rec = a.state[sub];
     if (out.p != rec.p || out.cz != rec.cz)
         st |= ST_EXIT_MISMATCH;
@@ -383,12 +454,20 @@ void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint3
     ++*launches;
 }
 
-void launch_entropy_scan_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches)
+void launch_entropy_scan(const EntropyArgs &a, cudaStream_t s, uint32_t *launches)
+{
+    const uint32_t tiles = (a.nsub_max + SCAN_THREADS - 1) / SCAN_THREADS;
+    entropy_scan_reduce_kernel<<<tiles, SCAN_THREADS, 0, s>>>(a);
+    entropy_scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(a);
+    entropy_scan_apply_kernel<<<tiles, SCAN_THREADS, 0, s>>>(a);
+    *launches += 3;
+}
+
+void launch_entropy_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches)
 {
     const uint32_t grid = (a.nsub_max + ENTROPY_THREADS - 1) / ENTROPY_THREADS;
-    entropy_scan_kernel<<<1, 1024, 0, s>>>(a);
     entropy_write_kernel<<<grid, ENTROPY_THREADS, 0, s>>>(a);
-    *launches += 2;
+    ++*launches;
 }
 
 // =================================================================================================
@@ -653,13 +732,31 @@ __device__ __forceinline__ void dequant_dezigzag(const uint4 (&ch)[8], const flo
     ((f[ZzNat<Is>::value] = chunk_coef<Is>(ch) * q[Is]), ...);
 }
 
-__device__ __forceinline__ uint32_t pack4(float a, float b, float c, float d)
+// Out-of-line on purpose: called from 64 unrolled sites that almost never execute it.
+template <int NC>
+__device__ __noinline__ float resolve_exact(const IdctSmem<NC> *sm, int bl, int comp, int s)
 {
-    // a..d are integer-valued floats in [0,255]; adding 1.5*2^23 leaves the integer in the low byte
-    const float M = 12582912.0f;
-    const uint32_t ua = __float_as_uint(a + M), ub = __float_as_uint(b + M);
-    const uint32_t uc = __float_as_uint(c + M), ud = __float_as_uint(d + M);
-    return __byte_perm(__byte_perm(ua, ub, 0x0040), __byte_perm(uc, ud, 0x0040), 0x5410);
+    auto at = [&](int zi) { return smem_coef_at<NC>(*sm, bl, zi); };
+    return (float)exact_sample(at, sm->qint[comp], sm->cosd, sm->cc, c_zz.nat2zz, s >> 3, s & 7);
+}
+
+// Four ints -> four bytes with unsigned saturation (cvt.pack.sat: two values per instruction).
+__device__ __forceinline__ uint32_t pack4_sat(int a, int b, int c, int d)
+{
+    // cvt.pack.sat.u8.s32.b32 d, x, y, z:  d = (z << 16) | (sat(x) << 8) | sat(y)
+    uint32_t hi, r;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(d), "r"(c));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(a), "r"(hi));
+    return r;
+}
+
+// Rare path (G within 1e-3 of an integer, or samples out of the fp32-safe range): the reference's
+// own double expression.  Out of line: eight unrolled call sites.
+__device__ __noinline__ uint32_t colour_exact_px(float y, float cb, float cr)
+{
+    int R, G, B;
+    ycc_to_rgb_exact((int)y, (int)cb, (int)cr, R, G, B); // clamped to [0,255]
+    return (uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16);
 }
 
 template <int NC>
@@ -735,27 +832,40 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA) idct_kernel(IdctArgs a
         for (int s = 0; s < 64; ++s)
             energy = fmaf(f[s], f[s], energy);
         const float thresh = 0.5f - tie_band(energy);
-        const float MAGIC = 12582912.0f; // 1.5 * 2^23: (x + MAGIC) - MAGIC == rint(x) for |x| < 2^22
+        // (x + 1.5*2^23) - 1.5*2^23 == rint(x) for |x| < 2^22; samples inside the tie band are
+        // collected in a 64-bit mask (predicated ORs, no branches in the unrolled part)
+        uint32_t tie_lo = 0, tie_hi = 0;
 #pragma unroll
         for (int row = 0; row < 8; ++row) {
             float r[8];
 #pragma unroll
             for (int col = 0; col < 8; ++col) {
                 const float x = f[row * 8 + col];
-                r[col] = (x + MAGIC) - MAGIC;
+                r[col] = (x + RINT_MAGIC) - RINT_MAGIC;
                 if (fabsf(x - r[col]) > thresh) {
-                    const uint32_t slot = atomicAdd(&sm.qcount, 1u);
-                    if (slot < IDCT_QUEUE_CAP) {
-                        sm.queue[slot] = (uint16_t)((bl << 6) | (row * 8 + col));
-                    } else {
-                        // queue full (pathologically flat image): resolve on the spot
-                        auto at = [&](int zi) { return smem_coef_at<NC>(sm, bl, zi); };
-                        r[col] = (float)exact_sample(at, sm.qint[comp], sm.cosd, sm.cc, c_zz.nat2zz, row, col);
-                    }
+                    if (row < 4)
+                        tie_lo |= 1u << (row * 8 + col);
+                    else
+                        tie_hi |= 1u << (row * 8 + col - 32);
                 }
             }
             sm.samp[((comp * 8 + row) * 2 + 0) * NM + ml] = make_float4(r[0], r[1], r[2], r[3]);
             sm.samp[((comp * 8 + row) * 2 + 1) * NM + ml] = make_float4(r[4], r[5], r[6], r[7]);
+        }
+        while (tie_lo | tie_hi) {
+            int s;
+            if (tie_lo) {
+                s = __ffs(tie_lo) - 1;
+                tie_lo &= tie_lo - 1;
+            } else {
+                s = 32 + __ffs(tie_hi) - 1;
+                tie_hi &= tie_hi - 1;
+            }
+            const uint32_t slot = atomicAdd(&sm.qcount, 1u);
+            if (slot < IDCT_QUEUE_CAP)
+                sm.queue[slot] = (uint16_t)((bl << 6) | s);
+            else // queue full (pathologically flat image): resolve on the spot
+                store_sample<NC>(sm, comp, ml, s, resolve_exact<NC>(&sm, bl, comp, s));
         }
     }
     __syncthreads();
@@ -802,16 +912,15 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA) idct_kernel(IdctArgs a
                 const float4 c1 = sm.samp[((2 * 8 + row) * 2 + 1) * NM + ml];
                 const float Cb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 const float Cr[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                float px[24];
+                int px[24];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    float R, G, B;
+                    int R, G, B;
                     if (!ycc_to_rgb_fast(Y[j], Cb[j], Cr[j], R, G, B)) {
-                        int r, g, b;
-                        ycc_to_rgb_exact((int)Y[j], (int)Cb[j], (int)Cr[j], r, g, b);
-                        R = (float)r;
-                        G = (float)g;
-                        B = (float)b;
+                        const uint32_t e = colour_exact_px(Y[j], Cb[j], Cr[j]);
+                        R = (int)(e & 0xFFu);
+                        G = (int)((e >> 8) & 0xFFu);
+                        B = (int)(e >> 16);
                         ++colour_exact;
                     }
                     px[j * 3 + 0] = R;
@@ -820,15 +929,15 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA) idct_kernel(IdctArgs a
                 }
 #pragma unroll
                 for (int k = 0; k < 6; ++k)
-                    out[k] = pack4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
+                    out[k] = pack4_sat(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
             } else {
                 // gray: the reference's colour path with Cb = Cr = 128 gives R = G = B = clamp(Y)
-                float v[8];
+                int v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    v[j] = fminf(fmaxf(Y[j] + 128.0f, 0.0f), 255.0f);
-                out[0] = pack4(v[0], v[1], v[2], v[3]);
-                out[1] = pack4(v[4], v[5], v[6], v[7]);
+                    v[j] = float_bits(Y[j] + (RINT_MAGIC + 128.0f)) - RINT_MAGIC_BITS; // integer-valued: exact
+                out[0] = pack4_sat(v[0], v[1], v[2], v[3]);
+                out[1] = pack4_sat(v[4], v[5], v[6], v[7]);
             }
             uint8_t *dst = img_base + ((size_t)y * W + bx * 8u) * NC;
             if (vec_ok) {
@@ -837,8 +946,10 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA) idct_kernel(IdctArgs a
                     reinterpret_cast<uint2 *>(dst)[k] = make_uint2(out[2 * k], out[2 * k + 1]);
             } else {
                 const uint32_t nbytes = (full_w ? 8u : W - bx * 8u) * NC;
-                for (uint32_t j = 0; j < nbytes; ++j)
-                    dst[j] = (uint8_t)(out[j >> 2] >> (8 * (j & 3)));
+#pragma unroll
+                for (int j = 0; j < 8 * NC; ++j) // compile-time indices: `out` stays in registers
+                    if ((uint32_t)j < nbytes)
+                        dst[j] = (uint8_t)(out[j >> 2] >> (8 * (j & 3)));
             }
         }
         if (colour_exact)

@@ -47,6 +47,7 @@ struct EntropyArgs {
     uint2 *used;          // [nsub_max] (p, cz) the state X[i] was computed from
     uint32_t *seg_hint;   // [nsub_max]
     uint32_t *start_slot; // [nsub_max] absolute slot at the entry of subsequence i
+    uint2 *scan_tiles;    // [ceil(nsub_max / 1024)] per-tile aggregates / carries of the offset scan
     int16_t *coef;        // [total_blocks][64]
     int16_t *dcdiff;      // [total_blocks]
     uint32_t nsub_max;
@@ -81,7 +82,8 @@ void kernels_configure(); // per-device function attributes (call once after cud
 void launch_unstuff(const UnstuffArgs &a, uint32_t sub_bits, cudaStream_t s, uint32_t *launches);
 void launch_entropy_cold(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint32_t *launches);
-void launch_entropy_scan_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);
+void launch_entropy_scan(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);
+void launch_entropy_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_dc_scan(const DcArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_merge_dc(int16_t *coef_out, const int16_t *coef, const int16_t *dc, const int16_t *dcdiff, uint32_t nblocks,

@@ -30,10 +30,13 @@ namespace kpeg {
 // AC, 16 for ZRL, 64 for EOB -- the consumer clamps to the end of the block).  0 = not resolved.
 constexpr int LUT_BITS = 10;
 constexpr int LUT_SIZE = 1 << LUT_BITS;
+constexpr int LONG_CAP = 1024; // second-level table: one entry per left-aligned 16-bit window above the short codes
 constexpr uint32_t ENTRY_INVALID = 17u | (0u << 5) | (1u << 9); // "needs more than 16 bits"
+constexpr int MAX_COMP = 3;
+constexpr int MAX_LUTS = MAX_COMP * 2; // [comp*2 + (0=DC,1=AC)]
 
-struct HuffLut {
-    uint16_t fast[LUT_SIZE];
+// Canonical description of one table (rare fallback + host-side construction).
+struct HuffCanon {
     uint32_t bound[18];      // bound[L] = exclusive upper bound of the left-aligned 16-bit windows whose code has length <= L
     uint16_t first_code[18]; // first code value of length L
     uint16_t first_idx[18];  // index of its symbol
@@ -41,7 +44,18 @@ struct HuffLut {
     uint32_t is_ac;
     uint32_t pad_[3];
 };
-static_assert(sizeof(HuffLut) % 16 == 0, "HuffLut is copied to shared memory in 16-byte units");
+
+// What the entropy kernels keep in shared memory.  Canonical codes are assigned in increasing order,
+// so every code longer than LUT_BITS lives in the window range [long_base, 65536): a direct table
+// over that (small: 320 entries for the Annex K AC tables) resolves long codes in one more load.
+struct LutSet {
+    uint16_t fast[MAX_LUTS][LUT_SIZE];
+    uint16_t longlut[MAX_LUTS][LONG_CAP];
+    uint32_t long_base[MAX_LUTS]; // == bound[LUT_BITS]
+    uint32_t long_n[MAX_LUTS];    // entries of longlut in use; 0 if the range does not fit (-> canonical search)
+    uint32_t pad_[4];
+};
+static_assert(sizeof(LutSet) % 16 == 0, "LutSet is copied to shared memory in 16-byte units");
 
 // Symbol -> fast-table entry.  DC symbol: category = sym & 15, one slot.  AC symbol: run = sym >> 4,
 // category = sym & 15; 0x00 (EOB) consumes the rest of the block, 0xF0 (ZRL) 16 slots
@@ -55,12 +69,11 @@ KPEG_HD uint32_t pack_entry(uint32_t len, uint32_t sym, bool is_ac)
     return len | (size << 5) | (adv << 9);
 }
 
-constexpr int MAX_COMP = 3;
-
 // Device-side description of one decode job (one image, or a batch of same-plan images decoded as
 // one concatenated stream).  Lives in global memory; kernels get a pointer.
 struct DeviceTables {
-    HuffLut lut[MAX_COMP * 2]; // [comp*2 + (0=DC,1=AC)]
+    LutSet luts;
+    HuffCanon canon[MAX_LUTS];
     float qscale[MAX_COMP][64]; // zig-zag order: quantiser * AAN prescale (fast IDCT path)
     int32_t qint[MAX_COMP][64]; // zig-zag order: plain quantiser (exact path), MCU.cpp:110-112
     double cosd[8][8];          // cosd[x][u] = cos((2x+1)*u*pi/16) in double, host libm -- the factor of MCU.cpp:193

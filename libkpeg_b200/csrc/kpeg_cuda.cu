@@ -33,7 +33,7 @@ struct PinBuf {
     size_t cap = 0;
 };
 
-enum { EV_START, EV_H2D, EV_UNSTUFF, EV_ENTROPY, EV_DC, EV_IDCT, EV_D2H, EV_COUNT };
+constexpr int MAX_EVENTS = 160;
 
 } // namespace
 
@@ -42,11 +42,13 @@ struct kpeg_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     bool profiling = false;
-    cudaEvent_t ev[EV_COUNT] = {};
+    cudaEvent_t ev[MAX_EVENTS] = {};
+    int ev_stage[MAX_EVENTS] = {}; // stage that ENDS at event i (-1 for the first)
+    int nev = 0;
     uint32_t sub_bits = 512;
-    int relay_rounds = 4;
+    int relay_rounds = 8;
 
-    DevBuf scan, words, seg_bit, tile_kept, tile_rst, state, used, seg_hint, start_slot;
+    DevBuf scan, words, seg_bit, tile_kept, tile_rst, state, used, seg_hint, start_slot, scan_tiles;
     DevBuf coef, dcdiff, dc, tile_carry, pixels, tables, meta, merged;
     PinBuf h_tables, h_meta, h_stage;
 
@@ -154,20 +156,20 @@ int make_geom(kpeg_ctx *ctx, const kpeg_plan *pl, uint32_t nimages, JobGeom *g)
     return rc == KPEG_OK ? rc : fail(ctx, rc, why);
 }
 
-void record(kpeg_ctx *ctx, int which)
+// Profiling: an event after every stage; mark(ctx, -1) opens a call.
+void mark(kpeg_ctx *ctx, int stage)
 {
-    if (ctx->profiling)
-        cudaEventRecord(ctx->ev[which], ctx->stream);
-}
-
-float elapsed(kpeg_ctx *ctx, int a, int b)
-{
-    float ms = 0.0f;
-    if (cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]) != cudaSuccess) {
-        cudaGetLastError();
-        return 0.0f;
-    }
-    return ms;
+    if (!ctx->profiling)
+        return;
+    if (stage < 0)
+        ctx->nev = 0;
+    if (ctx->nev >= MAX_EVENTS)
+        return;
+    if (!ctx->ev[ctx->nev])
+        cudaEventCreate(&ctx->ev[ctx->nev]);
+    cudaEventRecord(ctx->ev[ctx->nev], ctx->stream);
+    ctx->ev_stage[ctx->nev] = stage;
+    ++ctx->nev;
 }
 
 int status_to_rc(kpeg_ctx *ctx, uint32_t st)
@@ -184,7 +186,7 @@ int status_to_rc(kpeg_ctx *ctx, uint32_t st)
 }
 
 // The whole device pipeline for one job whose stuffed bytes are already at d_scan.
-// `from_host_events`: EV_START / EV_H2D were recorded by the caller.
+// The caller has opened the profiling window with mark(ctx, -1).
 int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t scan_len, uint32_t nimages,
             uint8_t *d_pixels, kpeg_stats *stats, uint32_t *launches_out)
 {
@@ -210,6 +212,7 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
     TRY(ensure(ctx, ctx->used, (size_t)nsub_max * sizeof(uint2)));
     TRY(ensure(ctx, ctx->seg_hint, (size_t)nsub_max * 4u));
     TRY(ensure(ctx, ctx->start_slot, (size_t)nsub_max * 4u));
+    TRY(ensure(ctx, ctx->scan_tiles, ((size_t)nsub_max / 1024u + 2u) * sizeof(uint2)));
     TRY(ensure(ctx, ctx->coef, coef_bytes + 256));
     TRY(ensure(ctx, ctx->dcdiff, (size_t)g.total_blocks * 2u + 16));
     TRY(ensure(ctx, ctx->dc, (size_t)g.total_blocks * 2u + 16));
@@ -223,6 +226,7 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
 
     CK(cudaMemsetAsync(d_meta, 0, sizeof(DevMeta), s));
     CK(cudaMemsetAsync(ctx->words.p, 0, words_bytes, s));
+    mark(ctx, KPEG_T_MEMSET);
 
     UnstuffArgs ua;
     ua.scan = d_scan;
@@ -235,7 +239,7 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
     ua.nseg = g.nseg;
     ua.meta = d_meta;
     launch_unstuff(ua, g.sub_bits, s, &launches);
-    record(ctx, EV_UNSTUFF);
+    mark(ctx, KPEG_T_UNSTUFF);
 
     EntropyArgs ea;
     ea.words = (const uint32_t *)ctx->words.p;
@@ -246,6 +250,7 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
     ea.used = (uint2 *)ctx->used.p;
     ea.seg_hint = (uint32_t *)ctx->seg_hint.p;
     ea.start_slot = (uint32_t *)ctx->start_slot.p;
+    ea.scan_tiles = (uint2 *)ctx->scan_tiles.p;
     ea.coef = (int16_t *)ctx->coef.p;
     ea.dcdiff = (int16_t *)ctx->dcdiff.p;
     ea.nsub_max = nsub_max;
@@ -268,9 +273,11 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
     ia.g = g;
 
     launch_entropy_cold(ea, s, &launches);
+    mark(ctx, KPEG_T_ENTROPY_COLD);
     int rounds = ctx->relay_rounds < 2 ? 2 : (ctx->relay_rounds > MAX_RELAY_ROUNDS - 1 ? MAX_RELAY_ROUNDS - 1 : ctx->relay_rounds);
     for (int r = 1; r <= rounds; ++r)
         launch_entropy_relay(ea, r, s, &launches);
+    mark(ctx, KPEG_T_ENTROPY_RELAY);
 
     DevMeta *h_meta = (DevMeta *)ctx->h_meta.p;
     uint32_t extra_iterations = 0;
@@ -278,12 +285,15 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
         // everything downstream of the relay; optimistic: issued before convergence is known
         CK(cudaMemsetAsync(ctx->coef.p, 0, coef_bytes, s));
         CK(cudaMemsetAsync(ctx->dcdiff.p, 0, (size_t)g.total_blocks * 2u, s));
-        launch_entropy_scan_write(ea, s, &launches);
-        record(ctx, EV_ENTROPY);
+        mark(ctx, KPEG_T_MEMSET);
+        launch_entropy_scan(ea, s, &launches);
+        mark(ctx, KPEG_T_ENTROPY_SCAN);
+        launch_entropy_write(ea, s, &launches);
+        mark(ctx, KPEG_T_ENTROPY_WRITE);
         launch_dc_scan(da, s, &launches);
-        record(ctx, EV_DC);
+        mark(ctx, KPEG_T_DC_SCAN);
         launch_idct(ia, s, &launches);
-        record(ctx, EV_IDCT);
+        mark(ctx, KPEG_T_IDCT);
         CK(cudaMemcpyAsync(h_meta, d_meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         CK(cudaGetLastError());
@@ -300,6 +310,7 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
             CK(cudaMemsetAsync(&d_meta->changed[2], 0, 2 * sizeof(uint32_t), s));
             launch_entropy_relay(ea, 2, s, &launches);
             launch_entropy_relay(ea, 3, s, &launches);
+            mark(ctx, KPEG_T_ENTROPY_RELAY);
             CK(cudaMemcpyAsync(h_meta, d_meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
             converged = h_meta->changed[3] == 0u;
@@ -334,20 +345,26 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
     return status_to_rc(ctx, h_meta->status);
 }
 
-void fill_times(kpeg_ctx *ctx, kpeg_stats *stats, bool host_io)
+void fill_times(kpeg_ctx *ctx, kpeg_stats *stats)
 {
     if (!stats)
         return;
-    stats->ms_h2d = stats->ms_unstuff = stats->ms_entropy = stats->ms_dc_scan = stats->ms_idct = stats->ms_d2h = stats->ms_total = 0.0f;
-    if (!ctx->profiling)
+    for (int i = 0; i < KPEG_T_COUNT; ++i)
+        stats->ms[i] = 0.0f;
+    stats->ms_total = 0.0f;
+    if (!ctx->profiling || ctx->nev < 2)
         return;
-    stats->ms_h2d = host_io ? elapsed(ctx, EV_START, EV_H2D) : 0.0f;
-    stats->ms_unstuff = elapsed(ctx, EV_H2D, EV_UNSTUFF);
-    stats->ms_entropy = elapsed(ctx, EV_UNSTUFF, EV_ENTROPY);
-    stats->ms_dc_scan = elapsed(ctx, EV_ENTROPY, EV_DC);
-    stats->ms_idct = elapsed(ctx, EV_DC, EV_IDCT);
-    stats->ms_d2h = host_io ? elapsed(ctx, EV_IDCT, EV_D2H) : 0.0f;
-    stats->ms_total = elapsed(ctx, EV_START, host_io ? EV_D2H : EV_IDCT);
+    for (int i = 1; i < ctx->nev; ++i) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ctx->ev[i - 1], ctx->ev[i]) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        const int st = ctx->ev_stage[i];
+        if (st >= 0 && st < KPEG_T_COUNT)
+            stats->ms[st] += ms;
+        stats->ms_total += ms;
+    }
 }
 
 } // namespace
@@ -387,8 +404,6 @@ extern "C" int kpeg_cuda_create(int device, kpeg_ctx **out)
         delete ctx;
         return KPEG_ERR_CUDA;
     }
-    for (int i = 0; i < EV_COUNT; ++i)
-        cudaEventCreate(&ctx->ev[i]);
     kernels_configure();
     if (const char *sb = getenv("KPEG_SUB_BITS")) {
         const long v = strtol(sb, nullptr, 10);
@@ -416,7 +431,7 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
     if (ctx->stream)
         cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->scan,   &ctx->words,  &ctx->seg_bit,    &ctx->tile_kept, &ctx->tile_rst, &ctx->state,
-                      &ctx->used,   &ctx->seg_hint, &ctx->start_slot, &ctx->coef,    &ctx->dcdiff,   &ctx->dc,
+                      &ctx->used,   &ctx->seg_hint, &ctx->start_slot, &ctx->scan_tiles, &ctx->coef,    &ctx->dcdiff,   &ctx->dc,
                       &ctx->tile_carry, &ctx->pixels, &ctx->tables,  &ctx->meta,     &ctx->merged};
     for (DevBuf *b : bufs)
         if (b->p)
@@ -425,7 +440,7 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
     for (PinBuf *b : pins)
         if (b->p)
             cudaFreeHost(b->p);
-    for (int i = 0; i < EV_COUNT; ++i)
+    for (int i = 0; i < MAX_EVENTS; ++i)
         if (ctx->ev[i])
             cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream)
@@ -528,10 +543,9 @@ extern "C" int kpeg_cuda_decode_device(kpeg_ctx *ctx, const kpeg_plan *plan, con
     CK(cudaSetDevice(ctx->device));
     if (stats)
         memset(stats, 0, sizeof *stats);
-    record(ctx, EV_START);
-    record(ctx, EV_H2D);
+    mark(ctx, -1);
     const int rc = run_job(ctx, plan, d_scan, scan_len, 1, d_pixels_out, stats, nullptr);
-    fill_times(ctx, stats, false);
+    fill_times(ctx, stats);
     return rc;
 }
 
@@ -546,16 +560,16 @@ extern "C" int kpeg_cuda_decode(kpeg_ctx *ctx, const kpeg_plan *plan, const uint
     const size_t npix = (size_t)plan->width * plan->height * plan->ncomp;
     TRY(ensure(ctx, ctx->scan, scan_len + 64));
     TRY(ensure(ctx, ctx->pixels, npix + 64));
-    record(ctx, EV_START);
+    mark(ctx, -1);
     CK(cudaMemcpyAsync(ctx->scan.p, scan, scan_len, cudaMemcpyHostToDevice, ctx->stream));
-    record(ctx, EV_H2D);
+    mark(ctx, KPEG_T_H2D);
     const int rc = run_job(ctx, plan, (const uint8_t *)ctx->scan.p, scan_len, 1, (uint8_t *)ctx->pixels.p, stats, nullptr);
     if (rc != KPEG_OK && rc != KPEG_ERR_STREAM)
         return rc;
     CK(cudaMemcpyAsync(pixels_out, ctx->pixels.p, npix, cudaMemcpyDeviceToHost, ctx->stream));
-    record(ctx, EV_D2H);
+    mark(ctx, KPEG_T_D2H);
     CK(cudaStreamSynchronize(ctx->stream));
-    fill_times(ctx, stats, true);
+    fill_times(ctx, stats);
     return rc;
 }
 
@@ -591,10 +605,9 @@ extern "C" int kpeg_cuda_decode_batch_packed_device(kpeg_ctx *ctx, const kpeg_pl
     CK(cudaSetDevice(ctx->device));
     if (stats)
         memset(stats, 0, sizeof *stats);
-    record(ctx, EV_START);
-    record(ctx, EV_H2D);
+    mark(ctx, -1);
     const int rc = run_job(ctx, plan, d_packed, packed_len, (uint32_t)n, d_pixels_out, stats, nullptr);
-    fill_times(ctx, stats, false);
+    fill_times(ctx, stats);
     return rc;
 }
 
@@ -640,17 +653,17 @@ extern "C" int kpeg_cuda_decode_batch(kpeg_ctx *ctx, const kpeg_plan *plan, int 
     TRY(ensure(ctx, ctx->pixels, npix * (size_t)n + 64));
     CK(cudaStreamSynchronize(ctx->stream));
     TRY(kpeg_batch_pack(n, scans, scan_lens, (uint8_t *)ctx->h_stage.p, ctx->h_stage.cap));
-    record(ctx, EV_START);
+    mark(ctx, -1);
     CK(cudaMemcpyAsync(ctx->scan.p, ctx->h_stage.p, total, cudaMemcpyHostToDevice, ctx->stream));
-    record(ctx, EV_H2D);
+    mark(ctx, KPEG_T_H2D);
     const int rc = run_job(ctx, plan, (const uint8_t *)ctx->scan.p, total, (uint32_t)n, (uint8_t *)ctx->pixels.p, stats, nullptr);
     if (rc != KPEG_OK && rc != KPEG_ERR_STREAM)
         return rc;
     for (int i = 0; i < n; ++i)
         CK(cudaMemcpyAsync(pixels_out[i], (uint8_t *)ctx->pixels.p + npix * (size_t)i, npix, cudaMemcpyDeviceToHost, ctx->stream));
-    record(ctx, EV_D2H);
+    mark(ctx, KPEG_T_D2H);
     CK(cudaStreamSynchronize(ctx->stream));
-    fill_times(ctx, stats, true);
+    fill_times(ctx, stats);
     return rc;
 }
 

@@ -103,7 +103,7 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
         const uint32_t p0 = sub * sub_bits;
         const uint32_t end = std::min(p0 + sub_bits, total_bits);
         hint[sub] = g.nseg > 1 ? first_seg_at_or_after(seg_bit, g.nseg, p0) : (sub ? 1u : 0u);
-        X[sub] = decode_span<false>(S, g, T->lut, end, p0, 0, 0, hint[sub], 0, nullptr, nullptr, nullptr);
+        X[sub] = decode_span<false>(S, g, T->luts, T->canon, end, p0, 0, 0, hint[sub], 0, nullptr, nullptr, nullptr);
         used_p[sub] = p0;
         used_cz[sub] = 0;
     }
@@ -118,7 +118,7 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
                 continue;
             const uint32_t end = std::min((sub + 1) * sub_bits, total_bits);
             const SubState out =
-                decode_span<false>(S, g, T->lut, end, in.p, in.cz >> 8, in.cz & 0xFF, hint[sub], 0, nullptr, nullptr, nullptr);
+                decode_span<false>(S, g, T->luts, T->canon, end, in.p, in.cz >> 8, in.cz & 0xFF, hint[sub], 0, nullptr, nullptr, nullptr);
             used_p[sub] = in.p;
             used_cz[sub] = in.cz;
             if (out.p != X[sub].p || out.cz != X[sub].cz || out.n != X[sub].n || out.seg != X[sub].seg) {
@@ -163,7 +163,7 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
         if ((slot & 63u) != z || ((slot >> 6) % g.ncomp) != c)
             st |= ST_EXIT_MISMATCH;
         const uint32_t end = std::min((sub + 1) * sub_bits, total_bits);
-        const SubState out = decode_span<true>(S, g, T->lut, end, p, c, z, hint[sub], slot, coef.data(), dcdiff.data(), &st);
+        const SubState out = decode_span<true>(S, g, T->luts, T->canon, end, p, c, z, hint[sub], slot, coef.data(), dcdiff.data(), &st);
         if (out.p != X[sub].p || out.cz != X[sub].cz)
             st |= ST_EXIT_MISMATCH;
         status |= st;
@@ -235,18 +235,14 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
                     continue;
                 uint8_t *o = base + ((size_t)y * g.width + x) * nc;
                 if (nc == 3) {
-                    float R, G, B;
+                    int R, G, B;
                     if (!ycc_to_rgb_fast(samp[0][s], samp[1][s], samp[2][s], R, G, B)) {
-                        int r, gg, b;
-                        ycc_to_rgb_exact((int)samp[0][s], (int)samp[1][s], (int)samp[2][s], r, gg, b);
-                        R = (float)r;
-                        G = (float)gg;
-                        B = (float)b;
+                        ycc_to_rgb_exact((int)samp[0][s], (int)samp[1][s], (int)samp[2][s], R, G, B);
                         ++colour_exact;
                     }
-                    o[0] = (uint8_t)(int)R;
-                    o[1] = (uint8_t)(int)G;
-                    o[2] = (uint8_t)(int)B;
+                    o[0] = (uint8_t)clamp_u8(R);
+                    o[1] = (uint8_t)clamp_u8(G);
+                    o[2] = (uint8_t)clamp_u8(B);
                 } else {
                     const float vv = fminf(fmaxf(samp[0][s] + 128.0f, 0.0f), 255.0f);
                     o[0] = (uint8_t)(int)vv;
@@ -270,11 +266,11 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
 // Two-tier colour conversion of one pixel (unshifted samples).  Returns 1 if the exact path ran.
 int emu_colour(int y, int cb, int cr, int rgb[3])
 {
-    float R, G, B;
+    int R, G, B;
     if (ycc_to_rgb_fast((float)y, (float)cb, (float)cr, R, G, B)) {
-        rgb[0] = (int)R;
-        rgb[1] = (int)G;
-        rgb[2] = (int)B;
+        rgb[0] = clamp_u8(R);
+        rgb[1] = clamp_u8(G);
+        rgb[2] = clamp_u8(B);
         return 0;
     }
     ycc_to_rgb_exact(y, cb, cr, rgb[0], rgb[1], rgb[2]);
@@ -301,14 +297,29 @@ float emu_idct_fast(const int16_t zzc[64], const uint16_t qt[64], float out[64])
 }
 
 // Huffman LUT lookup of a left-aligned 32-bit window: returns the packed entry.
-uint32_t emu_huff_lookup(const uint8_t counts[16], const uint8_t *symbols, int is_ac, uint32_t win)
+// mode 0: as the kernels do it (fast / long table / canonical); mode 1: canonical search only.
+uint32_t emu_huff_lookup(const uint8_t counts[16], const uint8_t *symbols, int is_ac, uint32_t win, int mode)
 {
-    HuffLut *L = new HuffLut;
+    LutSet *L = new LutSet;
+    HuffCanon canon;
     uint32_t e = 0xFFFFFFFFu;
-    if (build_huff_lut(counts, symbols, is_ac != 0, L) == 0) {
-        e = L->fast[win >> (32 - LUT_BITS)];
-        if (!e)
-            e = huff_slow_lookup(*L, win);
+    if (build_huff_lut(counts, symbols, is_ac != 0, L, 0, &canon) == 0) {
+        if (mode == 1) {
+            e = ENTRY_INVALID;
+            const uint32_t w16 = win >> 16;
+            for (int len = 1; len <= 16; ++len)
+                if (w16 < canon.bound[len]) {
+                    const uint32_t i = canon.first_idx[len] + ((w16 >> (16 - len)) - canon.first_code[len]);
+                    e = pack_entry((uint32_t)len, canon.symbols[i & 255u], is_ac != 0);
+                    break;
+                }
+        } else {
+            e = L->fast[0][win >> (32 - LUT_BITS)];
+            if (!e) {
+                const uint32_t li = (win >> 16) - L->long_base[0];
+                e = li < L->long_n[0] ? (uint32_t)L->longlut[0][li] : huff_slow_lookup(canon, win);
+            }
+        }
     }
     delete L;
     return e;
