@@ -239,25 +239,33 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_cold_kernel(EntropyAr
 }
 
 // One relay round: X[i] = decode(i, X[i-1]) for every i whose input changed since it was last used.
+// After the first round only a few percent of the subsequences are still moving, so a CTA first
+// votes on whether any of its threads has work and leaves before staging the tables if not.
 __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_kernel(EntropyArgs a, int round)
 {
     if (round > 1 && a.meta->changed[round - 1] == 0u)
         return; // already at the fixed point
     __shared__ __align__(16) LutSet s_lut;
-    load_luts_to_smem(s_lut, a.tables, a.g.ncomp);
     const uint32_t sub = blockIdx.x * ENTROPY_THREADS + threadIdx.x;
     const uint32_t nsub = a.meta->nsub, total_bits = a.meta->total_bits;
-    if (sub == 0u || sub >= nsub)
+    uint32_t in_p = 0, in_cz = 0;
+    bool need = false;
+    if (sub != 0u && sub < nsub) {
+        const uint4 inraw = __ldcg(reinterpret_cast<const uint4 *>(&a.state[sub - 1]));
+        in_p = inraw.x;
+        in_cz = inraw.z;
+        const uint2 u = a.used[sub];
+        need = !(u.x == in_p && u.y == in_cz);
+    }
+    if (!__syncthreads_or(need))
         return;
-    const uint4 inraw = __ldcg(reinterpret_cast<const uint4 *>(&a.state[sub - 1]));
-    const uint32_t in_p = inraw.x, in_cz = inraw.z;
-    const uint2 u = a.used[sub];
-    if (u.x == in_p && u.y == in_cz)
+    load_luts_to_smem(s_lut, a.tables, a.g.ncomp);
+    if (!need)
         return;
     StreamView S{a.words, a.seg_bit, total_bits};
     const uint32_t end = min((sub + 1u) * a.g.sub_bits, total_bits);
-    const SubState out =
-        decode_span<false>(S, a.g, s_lut, a.tables->canon, end, in_p, in_cz >> 8, in_cz & 0xFFu, a.seg_hint[sub], 0u, nullptr, nullptr, nullptr);
+    const SubState out = decode_span<false>(S, a.g, s_lut, a.tables->canon, end, in_p, in_cz >> 8, in_cz & 0xFFu,
+                                            a.seg_hint[sub], 0u, nullptr, nullptr, nullptr);
     a.used[sub] = make_uint2(in_p, in_cz);
     const SubState old = a.state[sub];
     if (old.p != out.p || old.cz != out.cz || old.n != out.n || old.seg != out.seg) {
