@@ -177,6 +177,15 @@ int kpeg_cuda_decode_file(kpeg_ctx *ctx, const uint8_t *file, size_t len, uint32
  * `cap` is in int16 elements. */
 int kpeg_cuda_read_coefficients(kpeg_ctx *ctx, int16_t *out, size_t cap);
 
+/* Host-only: cut one restart-marked scan into `parts` bands of whole MCU rows; band b is the byte
+ * range scan[out_begin[b], out_end[b]) and decodes as an image of the same width and tables whose
+ * MCU rows are [out_row[b], out_row[b+1]).  This is how restart-interval tiles of a very large image
+ * are spread over several GPUs (one context per GPU, no device-to-device traffic; the reference has
+ * no tiling).  Needs a restart interval that is a whole number of MCU rows or divides one.
+ * out_begin / out_end have `parts` entries, out_row has parts + 1. */
+int kpeg_split_restart_bands(const uint8_t *scan, size_t len, const kpeg_plan *plan, int parts, uint64_t *out_begin,
+                             uint64_t *out_end, uint32_t *out_row);
+
 /* Exact bytes of the PPM header Image::dumpRawData writes (Image.cpp:124-127); returns length. */
 int kpeg_ppm_header(int width, int height, char *buf, size_t cap);
 

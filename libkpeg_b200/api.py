@@ -100,6 +100,8 @@ SYMBOLS = {
     "kpeg_cuda_decode_file": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, C.c_size_t, C.POINTER(Plan),
                                        C.POINTER(Stats)]),
     "kpeg_cuda_read_coefficients": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "kpeg_split_restart_bands": (C.c_int, [_vp, C.c_size_t, C.POINTER(Plan), C.c_int, C.POINTER(C.c_uint64),
+                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "kpeg_ppm_header": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
 }
 

@@ -192,6 +192,62 @@ extern "C" int kpeg_parse_jfif(const uint8_t *f, size_t n, kpeg_plan *pl, size_t
     }
 }
 
+// Cuts one restart-marked entropy-coded segment into `parts` bands of whole MCU rows, so that each
+// band is itself a complete image of the same width (multi-GPU tiling of very large images,
+// BASELINE.json configs[4]; the reference has no tiling at all).  Requires a restart interval that
+// is a whole number of MCU rows or divides one (every band then starts right after a marker).
+//   out_begin[parts], out_end[parts] : band b is scan[out_begin[b], out_end[b]) -- the RSTn marker
+//                                      that separates two bands belongs to neither
+//   out_row[parts + 1]               : first MCU row of each band (out_row[parts] = total MCU rows)
+// Surplus parts (more parts than MCU rows) come back as empty bands at the end.
+extern "C" int kpeg_split_restart_bands(const uint8_t *scan, size_t len, const kpeg_plan *plan, int parts,
+                                        uint64_t *out_begin, uint64_t *out_end, uint32_t *out_row)
+{
+    if (!scan || !plan || parts < 1 || !out_begin || !out_end || !out_row)
+        return KPEG_ERR_ARG;
+    const uint32_t mx = (plan->width + 7u) / 8u, my = (plan->height + 7u) / 8u;
+    const uint32_t ri = plan->restart_interval;
+    if (ri == 0 || !((ri % mx) == 0 || (mx % ri) == 0))
+        return KPEG_ERR_UNSUPPORTED; // bands must begin on a restart marker
+    const uint32_t row_step = (ri % mx) == 0 ? ri / mx : 1u; // MCU rows between candidate cut points
+    const uint32_t used = (uint32_t)parts < (my + row_step - 1) / row_step ? (uint32_t)parts : (my + row_step - 1) / row_step;
+    // first MCU row of band k: balanced, rounded down to a cut point
+    for (uint32_t k = 0; k <= used; ++k) {
+        uint32_t r = (uint32_t)(((uint64_t)my * k) / used);
+        out_row[k] = k == used ? my : r - r % row_step;
+    }
+    for (uint32_t k = used + 1; k <= (uint32_t)parts; ++k)
+        out_row[k] = my;
+    for (int k = 0; k < parts; ++k)
+        out_begin[k] = out_end[k] = len;
+    out_begin[0] = 0;
+    // walk the markers: marker number j (1-based) precedes restart interval j
+    uint32_t b = 1;
+    uint64_t markers = 0;
+    const uint8_t *p = scan, *end = scan + len;
+    while (b < used && p + 1 < end) {
+        const uint8_t *q = (const uint8_t *)memchr(p, 0xFF, (size_t)(end - 1 - p));
+        if (!q)
+            break;
+        const uint8_t m = q[1];
+        if (m >= 0xD0 && m <= 0xD7) {
+            ++markers;
+            if (((uint64_t)out_row[b] * mx) / ri == markers) {
+                out_end[b - 1] = (uint64_t)(q - scan);
+                out_begin[b] = (uint64_t)(q + 2 - scan);
+                ++b;
+            }
+            p = q + 2;
+        } else {
+            p = q + (m == 0xFF ? 1 : 2);
+        }
+    }
+    if (b < used)
+        return KPEG_ERR_STREAM; // fewer restart markers than the DRI interval promises
+    out_end[used - 1] = len;
+    return KPEG_OK;
+}
+
 extern "C" int kpeg_ppm_header(int width, int height, char *buf, size_t cap)
 {
     // Image::dumpRawData, Image.cpp:124-127

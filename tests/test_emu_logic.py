@@ -1,0 +1,158 @@
+"""CPU single-stepping of the kernel logic (tests/emu: the same entropy_core.h / idct_core.h /
+unstuff_core.h the sm_100a kernels compile) against the oracle: speculative decode + relay fixed
+point + offset scan, restart / image boundaries, the two-tier IDCT and colour arithmetic."""
+import ctypes as C
+
+import numpy as np
+import pytest
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+import helpers as H
+import libkpeg_b200 as K
+from libkpeg_b200.synth import EMIT_RESTART, GRAY_CONTENT, QUIRK_FREE, SynthParams, synth_encode
+
+
+def agree(jpg, parity=True, **kw):
+    o = H.oracle_decode(jpg, parity=parity)
+    e = H.emu_decode(jpg, flags=1 if parity else 0, **kw)
+    assert e["status"] == 0
+    assert np.array_equal(o["coef"], e["coef"]), "coefficients"
+    assert np.array_equal(o["pixels"], e["pixels"]), "pixels"
+    return o, e
+
+
+@pytest.mark.parametrize("sub_bits", [64, 96, 512, 1024, 8192])
+def test_lena_all_subsequence_sizes(lena_jpg, sub_bits):
+    o, e = agree(lena_jpg, sub_bits=sub_bits)
+    assert e["final_slot"] == 512 * 512 // 64 * 3 * 64
+
+
+def test_lena_t81_mode(lena_jpg):
+    agree(lena_jpg, parity=False)
+
+
+@pytest.mark.parametrize("w,h,q,ri", [(64, 48, 90, 0), (256, 64, 90, 16), (200, 120, 75, 7), (96, 96, 50, 1),
+                                       (320, 240, 95, 40), (64, 64, 100, 3)])
+def test_restart_twins(w, h, q, ri):
+    base = dict(width=w, height=h, quality=q, restart_interval=ri, seed=w * 31 + h, noise_amp=30 if q == 100 else 0)
+    plain = synth_encode(SynthParams(**base, flags=QUIRK_FREE)).tobytes()
+    rst = synth_encode(SynthParams(**base, flags=QUIRK_FREE | EMIT_RESTART)).tobytes()
+    _, a = agree(plain)
+    _, b = agree(rst, sub_bits=128)
+    assert np.array_equal(a["pixels"], b["pixels"])
+    assert np.array_equal(a["coef"], b["coef"])
+
+
+@pytest.mark.parametrize("w,h", [(96, 96), (40, 24)])
+def test_gray_twins(w, h):
+    base = dict(width=w, height=h, quality=90, seed=w + h)
+    g1 = synth_encode(SynthParams(**base, file_components=1, flags=QUIRK_FREE | GRAY_CONTENT)).tobytes()
+    g3 = synth_encode(SynthParams(**base, file_components=3, flags=QUIRK_FREE | GRAY_CONTENT)).tobytes()
+    _, a = agree(g1)
+    _, b = agree(g3)
+    assert np.array_equal(a["pixels"], b["pixels"][..., 1])
+    assert b["colour_exact"] == 0  # flat chroma stays on the fast colour path
+
+
+@pytest.mark.parametrize("w,h", [(60, 45), (17, 9), (8, 8), (1, 1), (1000, 3)])
+def test_ragged(w, h):
+    agree(synth_encode(SynthParams(w, h, quality=85, seed=w * h)).tobytes())
+
+
+def test_batch_as_one_stream():
+    jpgs = [synth_encode(SynthParams(64, 40, quality=92, restart_interval=5, flags=QUIRK_FREE | EMIT_RESTART, seed=7 + i))
+            for i in range(6)]
+    parsed = [K.parse_jfif(j) for j in jpgs]
+    scans = [j[o:o + n] for j, (_, o, n) in zip(jpgs, parsed)]
+    e = H.emu_decode(None, scans=scans, plan=parsed[0][0], sub_bits=256)
+    assert e["status"] == 0
+    for i, j in enumerate(jpgs):
+        o = H.oracle_decode(j.tobytes())
+        assert np.array_equal(o["pixels"], e["pixels"][i])
+
+
+def test_corrupt_stream_flags_an_error(lena_jpg):
+    buf = np.frombuffer(lena_jpg, dtype=np.uint8).copy()
+    plan, off, n = K.parse_jfif(buf)
+    e = H.emu_decode(buf[: off + n // 2].tobytes() + b"\xff\xd9", want_pixels=False)
+    assert e["status"] != 0  # truncated: the stream ends before the last MCU
+    rng = np.random.default_rng(3)
+    bad = buf.copy()
+    idx = rng.integers(off + 100, off + n - 100, size=200)
+    bad[idx] = rng.integers(1, 255, size=200).astype(np.uint8)
+    H.emu_decode(bad, want_pixels=False)  # must terminate; status is content dependent
+
+
+@settings(max_examples=25, deadline=None)
+@given(w=st.integers(1, 96), h=st.integers(1, 64), q=st.integers(5, 100), ri=st.integers(0, 9),
+       nc=st.sampled_from([1, 3]), seed=st.integers(0, 2 ** 31), sb=st.sampled_from([64, 128, 512]))
+def test_property_random_streams(w, h, q, ri, nc, seed, sb):
+    flags = QUIRK_FREE | (EMIT_RESTART if ri else 0) | (GRAY_CONTENT if nc == 1 else 0)
+    jpg = synth_encode(SynthParams(w, h, file_components=nc, quality=q, restart_interval=ri, flags=flags, seed=seed,
+                                   noise_amp=(seed % 60) + 1)).tobytes()
+    agree(jpg, sub_bits=sb)
+
+
+def test_fast_idct_error_bound():
+    """|fast fp32 IDCT - reference evaluation| stays inside the tie band the kernel uses (idct_core.h
+    TIE_REL / TIE_ABS), on random sparse and dense blocks up to the extremes of 8-bit JPEG."""
+    rng = np.random.default_rng(11)
+    emu, orc = H.emu(), H.oracle()
+    qt = np.ones(64, dtype=np.uint16)
+    worst = 0.0
+    for trial in range(3000):
+        dens = rng.choice([1, 3, 8, 20, 64])
+        amp = rng.choice([4, 40, 400, 2000])
+        zz = np.zeros(64, dtype=np.int16)
+        idx = rng.choice(64, size=dens, replace=False)
+        zz[idx] = rng.integers(-amp, amp + 1, size=dens)
+        qt[:] = rng.integers(1, 256)
+        fast = np.zeros(64, dtype=np.float32)
+        band = emu.emu_idct_fast(zz.ctypes.data, qt.ctypes.data, fast.ctypes.data)
+        # reference-order evaluation (float accumulator) before rounding
+        F = np.zeros(64, dtype=np.int32)
+        r, c = C.c_int(), C.c_int()
+        for i in range(64):
+            orc.kpo_zigzag_to_rc(i, C.byref(r), C.byref(c))
+            F[r.value * 8 + c.value] = int(zz[i]) * int(qt[i])
+        ref = np.zeros(64, dtype=np.float32)
+        orc.kpo_idct8x8(F.ctypes.data, ref.ctypes.data)
+        err = float(np.abs(fast.astype(np.float64) - ref.astype(np.float64)).max())
+        assert err <= band, (trial, err, band)
+        worst = max(worst, err / band)
+    assert worst < 0.9  # keep some margin
+
+
+def test_colour_two_tier_exhaustive_slices():
+    """Fast fp32 colour path + double fallback == the reference's double expression, on dense slices of
+    the (Y, Cb, Cr) cube including the lattice points where G is an exact integer."""
+    emu, orc = H.emu(), H.oracle()
+    got, want = (C.c_int * 3)(), (C.c_int * 3)()
+    n_exact = 0
+    for y in (-300, -129, -128, -1, 0, 1, 77, 127, 128, 400):
+        for cb in range(-260, 261, 3):
+            for cr in range(-260, 261, 5):
+                n_exact += emu.emu_colour(y, cb, cr, got)
+                orc.kpo_ycbcr_to_rgb(y + 128, cb + 128, cr + 128, want)
+                assert list(got) == list(want), (y, cb, cr)
+    # G = Y exactly when 43017*cb + 89267*cr == 0 (mod 125000): all such points near the origin
+    for cb in range(-600, 601):
+        for cr in range(-600, 601):
+            if (43017 * cb + 89267 * cr) % 125000 == 0:
+                for y in (-140, -3, 0, 5, 131):
+                    emu.emu_colour(y, cb, cr, got)
+                    orc.kpo_ycbcr_to_rgb(y + 128, cb + 128, cr + 128, want)
+                    assert list(got) == list(want), (y, cb, cr)
+    assert n_exact < 2000  # the fallback is rare
+
+
+def test_colour_rb_integer_points():
+    """1.402 d and 1.772 d are exact integers for d = 500 k / 250 k: the fast path must agree there."""
+    emu, orc = H.emu(), H.oracle()
+    got, want = (C.c_int * 3)(), (C.c_int * 3)()
+    for d in (-1000, -750, -500, -250, 250, 500, 750, 1000):
+        for y in (-128, 0, 100):
+            emu.emu_colour(y, d, d, got)
+            orc.kpo_ycbcr_to_rgb(y + 128, d + 128, d + 128, want)
+            assert list(got) == list(want)
