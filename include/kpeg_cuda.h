@@ -110,7 +110,7 @@ const char *kpeg_cuda_last_error(const kpeg_ctx *ctx); /* never NULL */
 int kpeg_cuda_device_count(void);
 int kpeg_cuda_set_profiling(kpeg_ctx *ctx, int on);
 /* Tuning knobs of the speculative entropy decode (0 = leave unchanged): bits per subsequence
- * (multiple of 32, 64..65536; default 512 or $KPEG_SUB_BITS) and the number of relay rounds issued
+ * (a power of two, 64..1024; default 512 or $KPEG_SUB_BITS) and the number of relay rounds issued
  * up front (>= 2; default 8 or $KPEG_RELAY_ROUNDS; more are added automatically when needed). */
 int kpeg_cuda_set_tuning(kpeg_ctx *ctx, int sub_bits, int relay_rounds);
 /* The CUDA stream (cudaStream_t) all of this context's work is issued on. */

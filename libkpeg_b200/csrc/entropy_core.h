@@ -22,15 +22,6 @@
 
 namespace kpeg {
 
-KPEG_HD uint32_t ld_word(const uint32_t *p)
-{
-#if defined(__CUDA_ARCH__)
-    return __ldg(p);
-#else
-    return *p;
-#endif
-}
-
 KPEG_HD uint32_t funnel_left(uint32_t hi, uint32_t lo, uint32_t s)
 {
 #if defined(__CUDA_ARCH__)
@@ -40,33 +31,8 @@ KPEG_HD uint32_t funnel_left(uint32_t hi, uint32_t lo, uint32_t s)
 #endif
 }
 
-// Three-word sliding window over the big-endian word stream; the third word is fetched one
-// word ahead of use so the load is off the symbol-to-symbol dependency chain.
-struct BitWindow {
-    const uint32_t *words;
-    uint32_t j, w0, w1, w2;
-    KPEG_HD void seek(uint32_t p)
-    {
-        j = p >> 5;
-        w0 = ld_word(words + j);
-        w1 = ld_word(words + j + 1);
-        w2 = ld_word(words + j + 2);
-    }
-    // 32 bits starting at bit p; p may have advanced by at most one word since the last call.
-    KPEG_HD uint32_t peek(uint32_t p)
-    {
-        uint32_t jj = p >> 5;
-        if (jj != j) {
-            w0 = w1;
-            w1 = w2;
-            j = jj;
-            w2 = ld_word(words + j + 2);
-        }
-        return funnel_left(w0, w1, p & 31u);
-    }
-};
-
-// Codes longer than LUT_BITS: canonical search.  `win` holds the next 32 stream bits, MSB first.
+// Codes longer than LUT_BITS that the second-level table does not cover: canonical search.
+// `win` holds the next 32 stream bits, MSB first.
 KPEG_HD uint32_t huff_slow_lookup(const HuffCanon &L, uint32_t win)
 {
     const uint32_t w16 = win >> 16;
@@ -79,6 +45,35 @@ KPEG_HD uint32_t huff_slow_lookup(const HuffCanon &L, uint32_t win)
     return ENTRY_INVALID;
 }
 
+// ---- accessors -------------------------------------------------------------------------------------
+// decode_span is a template over where the stream words and the lookup tables live: the kernels
+// pass shared-memory accessors (kernels.cu), the CPU single-stepper plain arrays (below).
+
+struct PlainWords { // word `gw` of the big-endian stream from a plain array
+    const uint32_t *words;
+    KPEG_HD uint32_t operator()(uint32_t gw) const
+    {
+#if defined(__CUDA_ARCH__)
+        return __ldg(words + gw);
+#else
+        return words[gw];
+#endif
+    }
+};
+
+struct PlainLuts {
+    const LutSet *set;
+    const HuffCanon *canon;
+    // toff = table index * LUT_SIZE
+    KPEG_HD uint32_t fast(uint32_t toff, uint32_t idx) const { return (&set->fast[0][0])[toff + idx]; }
+    KPEG_HD uint32_t slow(uint32_t toff, uint32_t win) const
+    {
+        const uint32_t ti = toff >> LUT_BITS;
+        const uint32_t li = (win >> 16) - set->long_base[ti];
+        return li < set->long_n[ti] ? (uint32_t)set->longlut[ti][li] : huff_slow_lookup(canon[ti], win);
+    }
+};
+
 // T.81 F.2.2.1 EXTEND == bitStringtoValue (src/Image.cpp:285-302): leading 1 -> the value itself,
 // leading 0 -> value - (2^n - 1).
 KPEG_HD int32_t extend_value(uint32_t v, uint32_t n)
@@ -87,49 +82,103 @@ KPEG_HD int32_t extend_value(uint32_t v, uint32_t n)
 }
 
 struct StreamView {
-    const uint32_t *words;   // unstuffed stream, big-endian 32-bit words, >= 3 words of slack after the end
     const uint32_t *seg_bit; // [nseg + 2]: start bit of every restart segment, then total_bits, then 0xFFFFFFFF
     uint32_t total_bits;
 };
 
-// Decode from state (p, c, z) until the first symbol boundary at or after `end_bit`.
-//   WRITE == false : speculative / relay pass, only the exit state and slot count are produced.
-//   WRITE == true  : final pass; `slot` is the absolute coefficient slot at entry, AC coefficients
-//                    go to coef[] (zig-zag order, buffer pre-zeroed), DC differences to dcdiff[].
-// `k` is a hint: any segment index whose start bit is <= the first boundary after p.
-template <bool WRITE>
-KPEG_HD SubState decode_span(const StreamView &S, const JobGeom &g, const LutSet &luts, const HuffCanon *canon, uint32_t end_bit,
-                             uint32_t p, uint32_t c, uint32_t z, uint32_t k, uint32_t slot, int16_t *coef,
-                             int16_t *dcdiff, uint32_t *status_accum)
+// ---- coefficient sinks (final pass) ------------------------------------------------------------------
+struct NullSink {
+    KPEG_HD void ac(uint32_t, int32_t) const {}
+    KPEG_HD void dc(uint32_t, int32_t) const {}
+};
+
+// straight to global memory: coef[] must be zero-filled beforehand
+struct GlobalSink {
+    int16_t *coef;   // [blocks][64]
+    int16_t *dcdiff; // [blocks]
+    KPEG_HD void ac(uint32_t pos, int32_t v) const { coef[pos] = (int16_t)v; }
+    KPEG_HD void dc(uint32_t block, int32_t v) const { dcdiff[block] = (int16_t)v; }
+};
+
+// Resumable decoder state of one subsequence.
+struct DecState {
+    uint32_t p, j, sh, w0, w1; // bit position; word index, shift and the two stream words covering it
+    uint32_t toff, z;          // table offset (2*component + (z != 0)) * LUT_SIZE, zig-zag index
+    uint32_t n;                // slots since entry / since the last boundary crossed
+    int32_t seg;               // last boundary crossed, -1 if none
+    uint32_t k, segend;        // next boundary: segment index and its start bit
+    uint32_t slot;             // absolute slot (final pass only)
+    uint32_t st;               // ST_* bits (final pass only)
+};
+
+template <class Words>
+KPEG_HD void dec_init(DecState &d, const Words &W, const StreamView &S, uint32_t p, uint32_t c, uint32_t z, uint32_t k,
+                      uint32_t slot)
 {
-    const uint32_t total_slots = g.total_blocks * 64u;
-    const uint32_t nc = g.ncomp;
     while (S.seg_bit[k] <= p)
         ++k;
-    uint32_t segend = S.seg_bit[k];
-    uint32_t n = 0;
-    int32_t seg = -1;
-    uint32_t st = 0;
-    BitWindow bw;
-    bw.words = S.words;
-    bw.seek(p);
-    while (p < end_bit) {
-        const uint32_t win = bw.peek(p);
-        const uint32_t ti = c * 2u + (z != 0u ? 1u : 0u);
-        uint32_t e = luts.fast[ti][win >> (32 - LUT_BITS)];
-        if (e == 0u) { // code longer than LUT_BITS (or no code at all)
-            const uint32_t li = (win >> 16) - luts.long_base[ti];
-            e = li < luts.long_n[ti] ? (uint32_t)luts.longlut[ti][li] : huff_slow_lookup(canon[ti], win);
-        }
-        const uint32_t len = e & 31u, size = (e >> 5) & 15u, adv = e >> 9;
-        const uint32_t T = len + size;
+    d.k = k;
+    d.segend = S.seg_bit[k];
+    d.p = p;
+    d.j = p >> 5;
+    d.sh = p & 31u;
+    d.w0 = W(d.j);
+    d.w1 = W(d.j + 1u);
+    d.toff = (c * 2u + (z != 0u ? 1u : 0u)) * (uint32_t)LUT_SIZE;
+    d.z = z;
+    d.n = 0;
+    d.seg = -1;
+    d.slot = slot;
+    d.st = 0;
+}
+
+KPEG_HD SubState dec_exit_state(const DecState &d)
+{
+    SubState out;
+    out.p = d.p;
+    out.n = d.n;
+    out.cz = ((d.toff >> (LUT_BITS + 1)) << 8) | d.z;
+    out.seg = d.seg;
+    return out;
+}
+
+// Decode until the first symbol boundary at or after `end_bit` -- or, in the final pass, until the
+// next symbol would belong to a block at or beyond `slot_limit` (a multiple of 64), so that a CTA can
+// assemble its output in shared-memory windows; call again with a larger limit to resume.
+//   WRITE == false : speculative / relay pass, only the exit state and slot count are produced.
+//   WRITE == true  : final pass; d.slot is the absolute coefficient slot, AC coefficients go to
+//                    sink.ac(absolute slot, value), DC differences to sink.dc(block, value).
+//
+// Loop state: bit position p with the words j, j+1 of the stream in registers, sh = p & 31 (a symbol
+// is at most 27 bits, so two words always cover it); word j+2 is fetched unconditionally at the top
+// of every iteration and rotated in, branch-free, when sh crosses 32 -- lanes of a warp cross word
+// boundaries at different symbols, a conditional refill would be executed (mostly masked) by every
+// warp on almost every iteration.  Table offset toff = (2*component + (z != 0)) * LUT_SIZE: a DC
+// symbol switches to the component's AC table (toff |= LUT_SIZE), the end of a block to the next
+// table in the ring.  z is the zig-zag index.
+template <bool WRITE, class Words, class Luts, class Sink>
+KPEG_HD void decode_run(DecState &d, const Words &W, const Luts &L, const StreamView &S, const JobGeom &g,
+                        uint32_t end_bit, uint32_t slot_limit, const Sink &sink)
+{
+    const uint32_t total_slots = g.total_blocks * 64u;
+    const uint32_t ring = g.ncomp * 2u * (uint32_t)LUT_SIZE;
+    uint32_t p = d.p, j = d.j, sh = d.sh, w0 = d.w0, w1 = d.w1, toff = d.toff, z = d.z, n = d.n;
+    uint32_t k = d.k, segend = d.segend, slot = d.slot, st = d.st;
+    int32_t seg = d.seg;
+    while (p < end_bit && (!WRITE || slot < slot_limit)) {
+        const uint32_t nxt = W(j + 2u); // consumed at the bottom of the iteration, if at all
+        const uint32_t win = funnel_left(w0, w1, sh);
+        uint32_t e = L.fast(toff, win >> (32 - LUT_BITS));
+        if (e == 0u) // code longer than LUT_BITS (or no code at all)
+            e = L.slow(toff, win);
+        const uint32_t T = e & 31u;
         if (p + T > segend) {
             // The symbol would straddle a restart / image boundary: we are in its padding.
             if (WRITE && slot != seg_slot_base(g, k) && (k < g.nseg || slot < total_slots))
                 st |= ST_SEG_MISMATCH;
             p = segend;
-            c = 0;
             z = 0;
+            toff = 0;
             n = 0;
             seg = (int32_t)k;
             if (WRITE)
@@ -138,43 +187,83 @@ KPEG_HD SubState decode_span(const StreamView &S, const JobGeom &g, const LutSet
             segend = S.seg_bit[k];
             if (p >= S.total_bits)
                 break;
-            bw.seek(p);
+            j = p >> 5;
+            sh = p & 31u;
+            w0 = W(j);
+            w1 = W(j + 1u);
             continue;
         }
+        const uint32_t adv = e >> 9;
         if (WRITE) {
-            if (len > 16u)
+            const uint32_t size = (e >> 5) & 15u;
+            if (T - size > 16u)
                 st |= ST_BAD_CODE;
             if (size) {
-                const uint32_t raw = (win << len) >> (32u - size);
+                const uint32_t raw = (win << (T - size)) >> (32u - size);
                 const int32_t val = extend_value(raw, size);
                 if (slot + adv > total_slots || z + adv > 64u)
                     st |= ST_SLOT_OVERFLOW;
                 else if (z == 0u)
-                    dcdiff[slot >> 6] = (int16_t)val;
+                    sink.dc(slot >> 6, val);
                 else
-                    coef[slot + adv - 1u] = (int16_t)val;
+                    sink.ac(slot + adv - 1u, val);
             }
         }
         p += T;
+        sh += T;
+        {
+            const bool cross = sh >= 32u; // selects, not a branch
+            sh = cross ? sh - 32u : sh;
+            j = cross ? j + 1u : j;
+            w0 = cross ? w1 : w0;
+            w1 = cross ? nxt : w1;
+        }
         uint32_t zn = z + adv;
         zn = zn > 64u ? 64u : zn;
         n += zn - z;
         if (WRITE)
             slot += zn - z;
-        z = zn;
-        if (z == 64u) {
+        if (zn == 64u) {
             z = 0;
-            c = (c + 1u == nc) ? 0u : c + 1u;
+            toff += (uint32_t)LUT_SIZE;
+            toff = toff == ring ? 0u : toff;
+        } else {
+            z = zn;
+            toff |= (uint32_t)LUT_SIZE;
         }
     }
-    if (WRITE && st)
-        *status_accum |= st;
-    SubState out;
-    out.p = p;
-    out.n = n;
-    out.cz = (c << 8) | z;
-    out.seg = seg;
-    return out;
+    d.p = p;
+    d.j = j;
+    d.sh = sh;
+    d.w0 = w0;
+    d.w1 = w1;
+    d.toff = toff;
+    d.z = z;
+    d.n = n;
+    d.k = k;
+    d.segend = segend;
+    d.slot = slot;
+    d.st = st;
+    d.seg = seg;
+}
+
+// One-shot convenience: whole subsequence, coefficients straight to global memory.
+template <bool WRITE, class Words, class Luts>
+KPEG_HD SubState decode_span(const Words &W, const Luts &L, const StreamView &S, const JobGeom &g, uint32_t end_bit,
+                             uint32_t p, uint32_t c, uint32_t z, uint32_t k, uint32_t slot, int16_t *coef,
+                             int16_t *dcdiff, uint32_t *status_accum)
+{
+    DecState d;
+    dec_init(d, W, S, p, c, z, k, slot);
+    if (WRITE) {
+        const GlobalSink sink{coef, dcdiff};
+        decode_run<true>(d, W, L, S, g, end_bit, 0xFFFFFFFFu, sink);
+        if (d.st)
+            *status_accum |= d.st;
+    } else {
+        decode_run<false>(d, W, L, S, g, end_bit, 0xFFFFFFFFu, NullSink{});
+    }
+    return dec_exit_state(d);
 }
 
 } // namespace kpeg

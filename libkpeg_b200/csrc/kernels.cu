@@ -10,6 +10,7 @@
 // All file:line citations are relative to /root/reference.  The arithmetic lives in
 // entropy_core.h / idct_core.h (host+device inline, also exercised on the CPU by tests/emu).
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include <utility>
@@ -180,28 +181,95 @@ void launch_unstuff(const UnstuffArgs &a, uint32_t sub_bits, cudaStream_t s, uin
 // K1: entropy decode
 // =================================================================================================
 
-// Copies the tables a CTA needs into shared memory: the first level of every table in use and
-// only the populated part of the second level.
-__device__ __forceinline__ void load_luts_to_smem(LutSet &s_lut, const DeviceTables *t, uint32_t ncomp)
+// Shared-memory image of what one CTA needs: the lookup tables (staged once per CTA) and the slice of
+// the bit stream that belongs to the tile of ENTROPY_THREADS subsequences being decoded.  The slice is
+// stored linearly with one padding word after every 32 (position l + (l >> 5)): lanes reading word k
+// of their own subsequence (stride 8, 16 or 32 words) then hit 32 different banks.  The slice
+// carries four extra words: a symbol may run up to 26 bits past the end of the last subsequence and
+// the bit window looks two words ahead.
+struct K1Smem {
+    uint16_t fast[MAX_LUTS * LUT_SIZE];
+    uint16_t longlut[MAX_LUTS * LONG_CAP];
+    uint32_t long_base[8];
+    uint32_t long_n[8];
+    uint32_t words[1]; // padded(ENTROPY_THREADS * words_per_subsequence + 4), sized at launch
+};
+
+constexpr uint32_t K1_TAIL_WORDS = 4;
+
+__host__ __device__ inline uint32_t k1_pad(uint32_t l) { return l + (l >> 5); }
+
+__host__ __device__ inline size_t k1_smem_bytes(uint32_t sub_bits)
 {
-    const uint32_t nt = ncomp * 2u;
+    return sizeof(K1Smem) + (size_t)(k1_pad(ENTROPY_THREADS * (sub_bits / 32u) + K1_TAIL_WORDS) + 2u) * sizeof(uint32_t);
+}
+
+struct SmemWords {
+    uint32_t addr; // shared byte address of words[0]
+    uint32_t gw0;  // global word index of the tile's first word
+    __device__ __forceinline__ uint32_t operator()(uint32_t gw) const
+    {
+        const uint32_t l = gw - gw0;
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr + 4u * (l + (l >> 5))));
+        return v;
+    }
+};
+
+struct SmemLuts {
+    uint32_t fast_addr; // shared byte address of fast[0]
+    const K1Smem *sm;
+    const HuffCanon *canon; // global
+    __device__ __forceinline__ uint32_t fast(uint32_t toff, uint32_t idx) const
+    {
+        uint16_t v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(fast_addr + 2u * (toff + idx)));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t slow(uint32_t toff, uint32_t win) const
+    {
+        const uint32_t ti = toff >> LUT_BITS;
+        const uint32_t li = (win >> 16) - sm->long_base[ti];
+        return li < sm->long_n[ti] ? (uint32_t)sm->longlut[ti * LONG_CAP + li] : huff_slow_lookup(canon[ti], win);
+    }
+};
+
+// Tables: first level of every table in use, populated part of the second level.  No barrier.
+__device__ __forceinline__ void k1_stage_tables(K1Smem &sm, const EntropyArgs &a)
+{
+    const DeviceTables *t = a.tables;
+    const uint32_t nt = a.g.ncomp * 2u;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(&t->luts.fast[0][0]);
-        uint4 *dst = reinterpret_cast<uint4 *>(&s_lut.fast[0][0]);
+        uint4 *dst = reinterpret_cast<uint4 *>(sm.fast);
         const uint32_t n = nt * (uint32_t)(LUT_SIZE * sizeof(uint16_t) / 16);
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
             dst[i] = __ldg(src + i);
     }
     if (threadIdx.x < MAX_LUTS) {
-        s_lut.long_base[threadIdx.x] = t->luts.long_base[threadIdx.x];
-        s_lut.long_n[threadIdx.x] = t->luts.long_n[threadIdx.x];
+        sm.long_base[threadIdx.x] = t->luts.long_base[threadIdx.x];
+        sm.long_n[threadIdx.x] = t->luts.long_n[threadIdx.x];
     }
     for (uint32_t ti = 0; ti < nt; ++ti) {
         const uint32_t n = (t->luts.long_n[ti] * (uint32_t)sizeof(uint16_t) + 15u) / 16u;
         const uint4 *src = reinterpret_cast<const uint4 *>(&t->luts.longlut[ti][0]);
-        uint4 *dst = reinterpret_cast<uint4 *>(&s_lut.longlut[ti][0]);
+        uint4 *dst = reinterpret_cast<uint4 *>(&sm.longlut[ti * LONG_CAP]);
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
             dst[i] = __ldg(src + i);
+    }
+}
+
+// The tile's stream slice (coalesced loads).  Ends with a __syncthreads().
+template <int TILE = ENTROPY_THREADS>
+__device__ __forceinline__ void k1_stage_stream(K1Smem &sm, const EntropyArgs &a, uint32_t tile, uint32_t total_bits,
+                                                uint32_t wlog)
+{
+    const uint32_t gw0 = (tile * TILE) << wlog;
+    const uint32_t nwords = ((uint32_t)TILE << wlog) + K1_TAIL_WORDS;
+    const uint32_t total_words = ((total_bits + 31u) >> 5) + 4u; // the stream buffer has zeroed slack beyond this
+    for (uint32_t l = threadIdx.x; l < nwords; l += blockDim.x) {
+        const uint32_t gw = gw0 + l;
+        sm.words[k1_pad(l)] = gw < total_words ? __ldg(a.words + gw) : 0u;
     }
     __syncthreads();
 }
@@ -220,53 +288,59 @@ __device__ __forceinline__ uint32_t first_seg_at_or_after(const uint32_t *seg_bi
     return lo;
 }
 
-__global__ void __launch_bounds__(ENTROPY_THREADS) entropy_cold_kernel(EntropyArgs a)
+__device__ __forceinline__ SmemLuts k1_luts(const K1Smem &sm, const EntropyArgs &a)
 {
-    __shared__ __align__(16) LutSet s_lut;
-    load_luts_to_smem(s_lut, a.tables, a.g.ncomp);
-    const uint32_t sub = blockIdx.x * ENTROPY_THREADS + threadIdx.x;
-    const uint32_t nsub = a.meta->nsub, total_bits = a.meta->total_bits;
-    if (sub >= nsub)
-        return;
-    StreamView S{a.words, a.seg_bit, total_bits};
-    const uint32_t p0 = sub * a.g.sub_bits;
-    const uint32_t end = min(p0 + a.g.sub_bits, total_bits);
-    const uint32_t hint = a.g.nseg > 1u ? first_seg_at_or_after(a.seg_bit, a.g.nseg, p0) : (sub ? 1u : 0u);
-    a.seg_hint[sub] = hint;
-    const SubState out = decode_span<false>(S, a.g, s_lut, a.tables->canon, end, p0, 0u, 0u, hint, 0u, nullptr, nullptr, nullptr);
-    a.state[sub] = out;
-    a.used[sub] = make_uint2(p0, 0u);
+    SmemLuts L;
+    L.fast_addr = (uint32_t)__cvta_generic_to_shared(sm.fast);
+    L.sm = &sm;
+    L.canon = a.tables->canon;
+    return L;
 }
 
-// One relay round: X[i] = decode(i, X[i-1]) for every i whose input changed since it was last used.
-// After the first round only a few percent of the subsequences are still moving, so a CTA first
-// votes on whether any of its threads has work and leaves before staging the tables if not.
-__global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_kernel(EntropyArgs a, int round)
+template <int TILE = ENTROPY_THREADS>
+__device__ __forceinline__ SmemWords k1_words(const K1Smem &sm, uint32_t tile, uint32_t wlog)
 {
-    if (round > 1 && a.meta->changed[round - 1] == 0u)
-        return; // already at the fixed point
-    __shared__ __align__(16) LutSet s_lut;
-    const uint32_t sub = blockIdx.x * ENTROPY_THREADS + threadIdx.x;
+    SmemWords W;
+    W.addr = (uint32_t)__cvta_generic_to_shared(sm.words);
+    W.gw0 = (tile * TILE) << wlog;
+    return W;
+}
+
+// Persistent over tiles of ENTROPY_THREADS subsequences: tables are staged once per CTA.
+__global__ void __launch_bounds__(ENTROPY_THREADS) entropy_cold_kernel(EntropyArgs a, uint32_t wlog)
+{
+    extern __shared__ __align__(16) unsigned char k1_raw[];
+    K1Smem &sm = *reinterpret_cast<K1Smem *>(k1_raw);
     const uint32_t nsub = a.meta->nsub, total_bits = a.meta->total_bits;
-    uint32_t in_p = 0, in_cz = 0;
-    bool need = false;
-    if (sub != 0u && sub < nsub) {
-        const uint4 inraw = __ldcg(reinterpret_cast<const uint4 *>(&a.state[sub - 1]));
-        in_p = inraw.x;
-        in_cz = inraw.z;
-        const uint2 u = a.used[sub];
-        need = !(u.x == in_p && u.y == in_cz);
+    const uint32_t ntiles = (nsub + ENTROPY_THREADS - 1) / ENTROPY_THREADS;
+    if (blockIdx.x >= ntiles)
+        return;
+    k1_stage_tables(sm, a);
+    const SmemLuts L = k1_luts(sm, a);
+    StreamView S{a.seg_bit, total_bits};
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        k1_stage_stream(sm, a, tile, total_bits, wlog);
+        const uint32_t sub = tile * ENTROPY_THREADS + threadIdx.x;
+        if (sub < nsub) {
+            const SmemWords W = k1_words(sm, tile, wlog);
+            const uint32_t p0 = sub << (wlog + 5u);
+            const uint32_t end = min(p0 + a.g.sub_bits, total_bits);
+            const uint32_t hint = a.g.nseg > 1u ? first_seg_at_or_after(a.seg_bit, a.g.nseg, p0) : (sub ? 1u : 0u);
+            a.seg_hint[sub] = hint;
+            const SubState out = decode_span<false>(W, L, S, a.g, end, p0, 0u, 0u, hint, 0u, nullptr, nullptr, nullptr);
+            a.state[sub] = out;
+        }
+        __syncthreads(); // the slice is overwritten by the next tile
     }
-    if (!__syncthreads_or(need))
-        return;
-    load_luts_to_smem(s_lut, a.tables, a.g.ncomp);
-    if (!need)
-        return;
-    StreamView S{a.words, a.seg_bit, total_bits};
-    const uint32_t end = min((sub + 1u) * a.g.sub_bits, total_bits);
-    const SubState out = decode_span<false>(S, a.g, s_lut, a.tables->canon, end, in_p, in_cz >> 8, in_cz & 0xFFu,
-                                            a.seg_hint[sub], 0u, nullptr, nullptr, nullptr);
-    a.used[sub] = make_uint2(in_p, in_cz);
+}
+
+// Relay: X[i] = decode(i, X[i-1]).  Round 1 visits every subsequence (tiles, like the cold pass) and
+// appends i+1 to the work list whenever X[i] changed; later rounds visit only the work list of the
+// round before (a few percent of the subsequences, scattered, so they read the stream from global
+// memory) until a round appends nothing: the fixed point.
+__device__ __forceinline__ void relay_publish(const EntropyArgs &a, uint32_t sub, const SubState &out, uint32_t nsub,
+                                              uint32_t *list_out, uint32_t *count_out)
+{
     const SubState old = a.state[sub];
     if (old.p != out.p || old.cz != out.cz || old.n != out.n || old.seg != out.seg) {
         uint4 o;
@@ -275,8 +349,67 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_kernel(EntropyA
         o.z = out.cz;
         o.w = (uint32_t)out.seg;
         __stcg(reinterpret_cast<uint4 *>(&a.state[sub]), o);
-        atomicAdd(&a.meta->changed[round], 1u);
+        // Only a change of the exit STATE (position, component, zig-zag index) matters downstream; the
+        // slot count of a subsequence changes almost always when its entry does, its exit state rarely.
+        if ((old.p != out.p || old.cz != out.cz) && sub + 1u < nsub)
+            list_out[atomicAdd(count_out, 1u)] = sub + 1u;
     }
+}
+
+__global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_full_kernel(EntropyArgs a, uint32_t wlog)
+{
+    extern __shared__ __align__(16) unsigned char k1_raw[];
+    K1Smem &sm = *reinterpret_cast<K1Smem *>(k1_raw);
+    const uint32_t nsub = a.meta->nsub, total_bits = a.meta->total_bits;
+    const uint32_t ntiles = (nsub + ENTROPY_THREADS - 1) / ENTROPY_THREADS;
+    if (blockIdx.x >= ntiles)
+        return;
+    k1_stage_tables(sm, a);
+    const SmemLuts L = k1_luts(sm, a);
+    StreamView S{a.seg_bit, total_bits};
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        k1_stage_stream(sm, a, tile, total_bits, wlog);
+        const uint32_t sub = tile * ENTROPY_THREADS + threadIdx.x;
+        if (sub != 0u && sub < nsub) {
+            const SubState in = a.state[sub - 1]; // cold value or already relayed: either is a valid iterate
+            const uint32_t start = sub << (wlog + 5u);
+            if (!(in.p == start && in.cz == 0u)) { // else the cold decode already started from this state
+                const SmemWords W = k1_words(sm, tile, wlog);
+                const uint32_t end = min((sub + 1u) << (wlog + 5u), total_bits);
+                const SubState out = decode_span<false>(W, L, S, a.g, end, in.p, in.cz >> 8, in.cz & 0xFFu, a.seg_hint[sub],
+                                                        0u, nullptr, nullptr, nullptr);
+                relay_publish(a, sub, out, nsub, a.worklist[1], &a.meta->changed[1]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_sparse_kernel(EntropyArgs a, int round, int slot_prev,
+                                                                               int slot_cur)
+{
+    const uint32_t count = a.meta->changed[slot_prev];
+    if (blockIdx.x * ENTROPY_THREADS >= count)
+        return; // also the whole grid once the fixed point is reached (count == 0)
+    extern __shared__ __align__(16) unsigned char k1_raw[];
+    K1Smem &sm = *reinterpret_cast<K1Smem *>(k1_raw);
+    k1_stage_tables(sm, a);
+    __syncthreads();
+    const uint32_t w = blockIdx.x * ENTROPY_THREADS + threadIdx.x;
+    if (w >= count)
+        return;
+    const uint32_t sub = a.worklist[(round - 1) & 1][w];
+    const uint32_t nsub = a.meta->nsub, total_bits = a.meta->total_bits;
+    if (sub >= nsub)
+        return;
+    const SmemLuts L = k1_luts(sm, a);
+    const PlainWords W{a.words};
+    StreamView S{a.seg_bit, total_bits};
+    const uint4 inraw = __ldcg(reinterpret_cast<const uint4 *>(&a.state[sub - 1]));
+    const uint32_t end = min((sub + 1u) * a.g.sub_bits, total_bits);
+    const SubState out = decode_span<false>(W, L, S, a.g, end, inraw.x, inraw.z >> 8, inraw.z & 0xFFu, a.seg_hint[sub], 0u,
+                                            nullptr, nullptr, nullptr);
+    relay_publish(a, sub, out, nsub, a.worklist[round & 1], &a.meta->changed[slot_cur]);
 }
 
 // Segmented exclusive scan of the slot counts: start_slot[i] = absolute coefficient slot at the
@@ -417,48 +550,206 @@ __global__ void __launch_bounds__(SCAN_THREADS) entropy_scan_apply_kernel(Entrop
         a.start_slot[0] = 0u;
 }
 
-__global__ void __launch_bounds__(ENTROPY_THREADS) entropy_write_kernel(EntropyArgs a)
+// ---- final pass -------------------------------------------------------------------------------------
+// A tile of WRITE_THREADS consecutive subsequences owns a contiguous range of coefficient slots
+// [start_slot[first], start_slot[first of next tile]).  The CTA assembles that range in shared
+// memory, WRITE_WIN_BLOCKS blocks at a time (threads whose next symbol lies beyond the window pause
+// and resume in the next one), and flushes every window with full 128-byte lines -- so the
+// coefficient buffer needs no zero-fill and HBM sees no partial-sector read-modify-write.  Only the
+// first and last block of a tile can be shared with a neighbouring tile; those are written
+// element-wise, each tile touching exactly its own slots.
+constexpr int WRITE_THREADS = 64;
+constexpr int WRITE_WIN_BLOCKS = 256;
+
+struct WriteSmemTail {
+    int16_t obuf[WRITE_WIN_BLOCKS * 64];
+    int16_t dcbuf[WRITE_WIN_BLOCKS];
+};
+
+__host__ __device__ inline size_t k1_write_words_bytes(uint32_t sub_bits)
 {
-    __shared__ __align__(16) LutSet s_lut;
-    load_luts_to_smem(s_lut, a.tables, a.g.ncomp);
-    const uint32_t sub = blockIdx.x * ENTROPY_THREADS + threadIdx.x;
-    const uint32_t nsub = a.meta->nsub, total_bits = a.meta->total_bits;
-    if (sub >= nsub)
-        return;
-    uint32_t p = 0, c = 0, z = 0;
-    if (sub) {
-        const SubState in = a.state[sub - 1];
-        p = in.p;
-        c = in.cz >> 8;
-        z = in.cz & 0xFFu;
+    const size_t w = (size_t)(k1_pad(WRITE_THREADS * (sub_bits / 32u) + K1_TAIL_WORDS) + 2u) * sizeof(uint32_t);
+    return (w + 15u) & ~(size_t)15u;
+}
+
+// byte offset of the window buffers inside the dynamic shared memory block (16-byte aligned)
+__host__ __device__ inline size_t k1_write_tail_offset(uint32_t sub_bits)
+{
+    return (offsetof(K1Smem, words) + k1_write_words_bytes(sub_bits) + 15u) & ~(size_t)15u;
+}
+
+__host__ __device__ inline size_t k1_write_smem_bytes(uint32_t sub_bits)
+{
+    return k1_write_tail_offset(sub_bits) + sizeof(WriteSmemTail);
+}
+
+struct SmemSink {
+    uint32_t obuf_addr, dc_addr; // shared byte addresses
+    uint32_t slot0, block0;      // first slot / block of the window
+    __device__ __forceinline__ void ac(uint32_t pos, int32_t v) const
+    {
+        const uint32_t off = pos - slot0;
+        if (off < (uint32_t)(WRITE_WIN_BLOCKS * 64))
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(obuf_addr + 2u * off), "h"((uint16_t)v));
     }
-    const uint32_t slot = a.start_slot[sub];
+    __device__ __forceinline__ void dc(uint32_t block, int32_t v) const
+    {
+        const uint32_t off = block - block0;
+        if (off < (uint32_t)WRITE_WIN_BLOCKS)
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(dc_addr + 2u * off), "h"((uint16_t)v));
+    }
+};
+
+__global__ void __launch_bounds__(WRITE_THREADS) entropy_write_kernel(EntropyArgs a, uint32_t wlog)
+{
+    extern __shared__ __align__(16) unsigned char k1_raw[];
+    K1Smem &sm = *reinterpret_cast<K1Smem *>(k1_raw);
+    WriteSmemTail &tail = *reinterpret_cast<WriteSmemTail *>(k1_raw + k1_write_tail_offset(a.g.sub_bits));
+    const uint32_t nsub = a.meta->nsub, total_bits = a.meta->total_bits;
+    const uint32_t ntiles = (nsub + WRITE_THREADS - 1) / WRITE_THREADS;
+    if (blockIdx.x >= ntiles)
+        return;
+    k1_stage_tables(sm, a);
+    const SmemLuts L = k1_luts(sm, a);
+    StreamView S{a.seg_bit, total_bits};
+    const uint32_t total_slots = a.g.total_blocks * 64u;
+    const uint32_t t = threadIdx.x;
     uint32_t st = 0;
-    if ((slot & 63u) != z || ((slot >> 6) % a.g.ncomp) != c)
-        st |= ST_EXIT_MISMATCH;
-    StreamView S{a.words, a.seg_bit, total_bits};
-    const uint32_t end = min((sub + 1u) * a.g.sub_bits, total_bits);
-    const SubState out = decode_span<true>(S, a.g, s_lut, a.tables->canon, end, p, c, z, a.seg_hint[sub], slot, a.coef, a.dcdiff, &st);
-    const SubState rec = a.state[sub];
-    if (out.p != rec.p || out.cz != rec.cz)
-        st |= ST_EXIT_MISMATCH;
-    if (sub + 1u == nsub && a.meta->final_slot < a.g.total_blocks * 64u)
-        st |= ST_SEG_MISMATCH; // the stream ended before the last MCU
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        k1_stage_stream<WRITE_THREADS>(sm, a, tile, total_bits, wlog);
+        const SmemWords W = k1_words<WRITE_THREADS>(sm, tile, wlog);
+        const uint32_t sub0 = tile * WRITE_THREADS, sub = sub0 + t;
+        // slot range owned by the tile (uniform)
+        const uint32_t s_begin = a.start_slot[sub0];
+        uint32_t s_end = (sub0 + WRITE_THREADS < nsub) ? a.start_slot[sub0 + WRITE_THREADS] : a.meta->final_slot;
+        s_end = min(s_end, total_slots);
+        const uint32_t b_first = s_begin >> 6;
+        const uint32_t b_end = s_end > s_begin ? (s_end + 63u) >> 6 : b_first; // blocks [b_first, b_end)
+
+        DecState d;
+        bool done = true;
+        uint32_t end = 0;
+        if (sub < nsub) {
+            uint32_t p = 0, c = 0, z = 0;
+            if (sub) {
+                const SubState in = a.state[sub - 1];
+                p = in.p;
+                c = in.cz >> 8;
+                z = in.cz & 0xFFu;
+            }
+            const uint32_t slot = a.start_slot[sub];
+            if ((slot & 63u) != z || ((slot >> 6) % a.g.ncomp) != c)
+                st |= ST_EXIT_MISMATCH;
+            end = min((sub + 1u) << (wlog + 5u), total_bits);
+            dec_init(d, W, S, p, c, z, a.seg_hint[sub], slot);
+            done = false;
+        }
+
+        for (uint32_t wb = b_first;; wb += WRITE_WIN_BLOCKS) {
+            // zero the window
+            {
+                uint4 *o = reinterpret_cast<uint4 *>(&tail);
+                constexpr int N16 = (int)(sizeof(WriteSmemTail) / 16);
+#pragma unroll 4
+                for (int i = t; i < N16; i += WRITE_THREADS)
+                    o[i] = make_uint4(0, 0, 0, 0);
+            }
+            __syncthreads();
+            if (!done) {
+                SmemSink sink;
+                sink.obuf_addr = (uint32_t)__cvta_generic_to_shared(tail.obuf);
+                sink.dc_addr = (uint32_t)__cvta_generic_to_shared(tail.dcbuf);
+                sink.slot0 = wb << 6;
+                sink.block0 = wb;
+                // past the tile's own range (corrupt stream): finish in one go, writes fall outside the window
+                const uint32_t limit = wb < b_end ? (wb + WRITE_WIN_BLOCKS) << 6 : 0xFFFFFFFFu;
+                decode_run<true>(d, W, L, S, a.g, end, limit, sink);
+                done = d.p >= end;
+            }
+            const bool all_done = __syncthreads_and(done);
+            // flush blocks [wb, we)
+            const uint32_t we = min(wb + (uint32_t)WRITE_WIN_BLOCKS, b_end);
+            if (wb < we) {
+                const uint32_t nblk = we - wb;
+                const uint4 *src = reinterpret_cast<const uint4 *>(tail.obuf);
+                uint4 *dst = reinterpret_cast<uint4 *>(a.coef) + (size_t)wb * 8u;
+                for (uint32_t ci = t; ci < nblk * 8u; ci += WRITE_THREADS) {
+                    const uint32_t b = wb + (ci >> 3);
+                    const bool full = (b << 6) >= s_begin && ((b + 1u) << 6) <= s_end;
+                    if (full)
+                        dst[ci] = src[ci];
+                }
+                // the (at most two) blocks shared with a neighbouring tile: own slots only
+                if (wb == b_first && (s_begin & 63u)) {
+                    const uint32_t pos = (b_first << 6) + t; // WRITE_THREADS == 64 == slots per block
+                    if (pos >= s_begin && pos < s_end)
+                        a.coef[pos] = tail.obuf[t];
+                }
+                if (we == b_end && (s_end & 63u) && !((b_end - 1u) == b_first && (s_begin & 63u) && wb == b_first)) {
+                    const uint32_t pos = ((b_end - 1u) << 6) + t;
+                    if (pos >= s_begin && pos < s_end)
+                        a.coef[pos] = tail.obuf[((b_end - 1u - wb) << 6) + t];
+                }
+                // DC differences of the blocks whose first slot this tile owns
+                for (uint32_t i = t; i < nblk; i += WRITE_THREADS) {
+                    const uint32_t b = wb + i;
+                    if ((b << 6) >= s_begin && (b << 6) < s_end)
+                        a.dcdiff[b] = tail.dcbuf[i];
+                }
+            }
+            if (all_done)
+                break;
+            __syncthreads(); // the window is zeroed again
+        }
+        if (sub < nsub) {
+            st |= d.st;
+            const SubState rec = a.state[sub];
+            const SubState out = dec_exit_state(d);
+            if (out.p != rec.p || out.cz != rec.cz)
+                st |= ST_EXIT_MISMATCH;
+            if (sub + 1u == nsub && a.meta->final_slot < total_slots)
+                st |= ST_SEG_MISMATCH; // the stream ended before the last MCU
+        }
+        __syncthreads();
+    }
     if (st)
         atomicOr(&a.meta->status, st);
 }
 
+static uint32_t ilog2(uint32_t v)
+{
+    uint32_t l = 0;
+    while ((1u << l) < v)
+        ++l;
+    return l;
+}
+
+static uint32_t g_k1_grid_cap = 148 * 8;
+static uint32_t g_k1_write_grid_cap = 148 * 4;
+
+static uint32_t k1_grid(const EntropyArgs &a)
+{
+    const uint32_t tiles = (a.nsub_max + ENTROPY_THREADS - 1) / ENTROPY_THREADS;
+    return tiles < g_k1_grid_cap ? tiles : g_k1_grid_cap;
+}
+
 void launch_entropy_cold(const EntropyArgs &a, cudaStream_t s, uint32_t *launches)
 {
-    const uint32_t grid = (a.nsub_max + ENTROPY_THREADS - 1) / ENTROPY_THREADS;
-    entropy_cold_kernel<<<grid, ENTROPY_THREADS, 0, s>>>(a);
+    const uint32_t wlog = ilog2(a.g.sub_bits / 32u);
+    entropy_cold_kernel<<<k1_grid(a), ENTROPY_THREADS, k1_smem_bytes(a.g.sub_bits), s>>>(a, wlog);
     ++*launches;
 }
 
 void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint32_t *launches)
 {
-    const uint32_t grid = (a.nsub_max + ENTROPY_THREADS - 1) / ENTROPY_THREADS;
-    entropy_relay_kernel<<<grid, ENTROPY_THREADS, 0, s>>>(a, round);
+    if (round == 1) {
+        const uint32_t wlog = ilog2(a.g.sub_bits / 32u);
+        entropy_relay_full_kernel<<<k1_grid(a), ENTROPY_THREADS, k1_smem_bytes(a.g.sub_bits), s>>>(a, wlog);
+    } else {
+        const uint32_t grid = (a.nsub_max + ENTROPY_THREADS - 1) / ENTROPY_THREADS;
+        entropy_relay_sparse_kernel<<<grid, ENTROPY_THREADS, sizeof(K1Smem), s>>>(a, round, relay_slot(round - 1),
+                                                                                  relay_slot(round));
+    }
     ++*launches;
 }
 
@@ -473,8 +764,10 @@ void launch_entropy_scan(const EntropyArgs &a, cudaStream_t s, uint32_t *launche
 
 void launch_entropy_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches)
 {
-    const uint32_t grid = (a.nsub_max + ENTROPY_THREADS - 1) / ENTROPY_THREADS;
-    entropy_write_kernel<<<grid, ENTROPY_THREADS, 0, s>>>(a);
+    const uint32_t wlog = ilog2(a.g.sub_bits / 32u);
+    const uint32_t tiles = (a.nsub_max + WRITE_THREADS - 1) / WRITE_THREADS;
+    const uint32_t grid = tiles < g_k1_write_grid_cap ? tiles : g_k1_write_grid_cap;
+    entropy_write_kernel<<<grid, WRITE_THREADS, k1_write_smem_bytes(a.g.sub_bits), s>>>(a, wlog);
     ++*launches;
 }
 
@@ -967,6 +1260,25 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA) idct_kernel(IdctArgs a
 
 void kernels_configure()
 {
+    const int k1max = (int)k1_smem_bytes(1024);
+    cudaFuncSetAttribute(entropy_cold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k1max);
+    cudaFuncSetAttribute(entropy_relay_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k1max);
+    cudaFuncSetAttribute(entropy_relay_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
+    {
+        int dev = 0, sms = 148, per_sm = 8;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(entropy_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)k1_write_smem_bytes(1024));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entropy_cold_kernel, ENTROPY_THREADS,
+                                                          k1_smem_bytes(512)) != cudaSuccess || per_sm < 1)
+            per_sm = 4;
+        g_k1_grid_cap = (uint32_t)(sms * per_sm);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entropy_write_kernel, WRITE_THREADS,
+                                                          k1_write_smem_bytes(512)) != cudaSuccess || per_sm < 1)
+            per_sm = 3;
+        g_k1_write_grid_cap = (uint32_t)(sms * per_sm);
+    }
     cudaFuncSetAttribute(idct_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<3>));
     cudaFuncSetAttribute(idct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<1>));
 }

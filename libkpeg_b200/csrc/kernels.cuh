@@ -8,7 +8,12 @@
 
 namespace kpeg {
 
-constexpr int MAX_RELAY_ROUNDS = 64; // slots in DevMeta::changed; the host loops if more are needed
+constexpr int MAX_RELAY_ROUNDS = 64; // slots in DevMeta::changed
+
+// DevMeta::changed slot of relay round r (r >= 1).  Rounds beyond the array reuse slots 2..63 (the
+// host zeroes a slot before reusing it); 62 is even, so slot parity == round parity, which is what
+// selects the ping-pong work list.
+inline int relay_slot(int r) { return r < MAX_RELAY_ROUNDS ? r : 2 + ((r - 2) % (MAX_RELAY_ROUNDS - 2)); }
 
 // Device-resident bookkeeping of one job; zeroed before every decode, read back once at the end.
 struct DevMeta {
@@ -44,7 +49,7 @@ struct EntropyArgs {
     const DeviceTables *tables;
     DevMeta *meta;
     SubState *state;      // [nsub_max] relay states X[i]
-    uint2 *used;          // [nsub_max] (p, cz) the state X[i] was computed from
+    uint32_t *worklist[2]; // [nsub_max] each: subsequences whose input changed in the previous relay round
     uint32_t *seg_hint;   // [nsub_max]
     uint32_t *start_slot; // [nsub_max] absolute slot at the entry of subsequence i
     uint2 *scan_tiles;    // [ceil(nsub_max / 1024)] per-tile aggregates / carries of the offset scan

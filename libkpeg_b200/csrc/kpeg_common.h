@@ -25,12 +25,13 @@ namespace kpeg {
 // canonical-code search over `bound` (T.81 Annex F.2.2.3 style), which the reference does by walking
 // its tree bit by bit (HuffmanTree.cpp:164-193).
 //
-// fast entry (uint16): bits 0-4 code length (1..16), bits 5-8 magnitude bits ("category"),
-// bits 9-15 slot advance (number of zig-zag positions the symbol consumes: 1 for DC, run+1 for
-// AC, 16 for ZRL, 64 for EOB -- the consumer clamps to the end of the block).  0 = not resolved.
+// fast entry (uint16): bits 0-4 TOTAL bits the symbol occupies (code length + magnitude bits, 1..27),
+// bits 5-8 magnitude bits ("category"), bits 9-15 slot advance (number of zig-zag positions the
+// symbol consumes: 1 for DC, run+1 for AC, 16 for ZRL, 64 for EOB -- the consumer clamps to the
+// end of the block).  0 = not resolved.  The speculative passes only need the total and the advance.
 constexpr int LUT_BITS = 10;
 constexpr int LUT_SIZE = 1 << LUT_BITS;
-constexpr int LONG_CAP = 1024; // second-level table: one entry per left-aligned 16-bit window above the short codes
+constexpr int LONG_CAP = 512;  // second-level table: one entry per left-aligned 16-bit window above the short codes
 constexpr uint32_t ENTRY_INVALID = 17u | (0u << 5) | (1u << 9); // "needs more than 16 bits"
 constexpr int MAX_COMP = 3;
 constexpr int MAX_LUTS = MAX_COMP * 2; // [comp*2 + (0=DC,1=AC)]
@@ -66,7 +67,7 @@ KPEG_HD uint32_t pack_entry(uint32_t len, uint32_t sym, bool is_ac)
     uint32_t adv = 1u;
     if (is_ac)
         adv = (sym == 0x00u) ? 64u : (sym >> 4) + 1u;
-    return len | (size << 5) | (adv << 9);
+    return (len + size) | (size << 5) | (adv << 9);
 }
 
 // Device-side description of one decode job (one image, or a batch of same-plan images decoded as
@@ -115,7 +116,7 @@ constexpr uint32_t ST_SEG_COUNT = 32u;     // number of RSTn markers does not ma
 
 // Per-subsequence relay state: where the first symbol after the end of the subsequence starts and
 // in which decoder state, plus how many coefficient slots were produced on the way.
-struct SubState {
+struct alignas(16) SubState {
     uint32_t p;   // bit position (in the unstuffed stream) of the next symbol
     uint32_t n;   // slots produced since the entry of the subsequence, or since the last segment boundary crossed
     uint32_t cz;  // (component << 8) | zig-zag index of the next coefficient (0 = a DC symbol comes next)

@@ -209,7 +209,7 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
     TRY(ensure(ctx, ctx->tile_kept, (size_t)ntiles * 4u));
     TRY(ensure(ctx, ctx->tile_rst, (size_t)ntiles * 4u));
     TRY(ensure(ctx, ctx->state, (size_t)nsub_max * sizeof(SubState)));
-    TRY(ensure(ctx, ctx->used, (size_t)nsub_max * sizeof(uint2)));
+    TRY(ensure(ctx, ctx->used, (size_t)nsub_max * 2u * sizeof(uint32_t)));
     TRY(ensure(ctx, ctx->seg_hint, (size_t)nsub_max * 4u));
     TRY(ensure(ctx, ctx->start_slot, (size_t)nsub_max * 4u));
     TRY(ensure(ctx, ctx->scan_tiles, ((size_t)nsub_max / 1024u + 2u) * sizeof(uint2)));
@@ -247,7 +247,8 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
     ea.tables = (const DeviceTables *)ctx->tables.p;
     ea.meta = d_meta;
     ea.state = (SubState *)ctx->state.p;
-    ea.used = (uint2 *)ctx->used.p;
+    ea.worklist[0] = (uint32_t *)ctx->used.p;
+    ea.worklist[1] = (uint32_t *)ctx->used.p + nsub_max;
     ea.seg_hint = (uint32_t *)ctx->seg_hint.p;
     ea.start_slot = (uint32_t *)ctx->start_slot.p;
     ea.scan_tiles = (uint2 *)ctx->scan_tiles.p;
@@ -283,9 +284,7 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
     uint32_t extra_iterations = 0;
     for (;;) {
         // everything downstream of the relay; optimistic: issued before convergence is known
-        CK(cudaMemsetAsync(ctx->coef.p, 0, coef_bytes, s));
-        CK(cudaMemsetAsync(ctx->dcdiff.p, 0, (size_t)g.total_blocks * 2u, s));
-        mark(ctx, KPEG_T_MEMSET);
+        // no zero-fill of coef / dcdiff: the final pass writes every slot of every block it owns
         launch_entropy_scan(ea, s, &launches);
         mark(ctx, KPEG_T_ENTROPY_SCAN);
         launch_entropy_write(ea, s, &launches);
@@ -299,28 +298,30 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
         CK(cudaGetLastError());
         if (h_meta->status & (ST_BAD_MARKER | ST_SEG_COUNT))
             break; // malformed container-level structure: more rounds will not help
-        if (h_meta->changed[rounds] == 0u)
+        if (h_meta->changed[relay_slot(rounds)] == 0u)
             break; // the last relay round changed nothing: fixed point, results are final
-        // Rare: the relay needed more rounds than were pre-issued.  Run two at a time until a round
-        // changes nothing, then redo the downstream stages.
+        // Rare: the relay needed more rounds than were pre-issued.  Run two more at a time until a
+        // round changes nothing, then redo the downstream stages.
         bool converged = false;
         const uint32_t cap = h_meta->nsub / 2u + 4u;
         while (!converged && extra_iterations < cap) {
             ++extra_iterations;
-            CK(cudaMemsetAsync(&d_meta->changed[2], 0, 2 * sizeof(uint32_t), s));
-            launch_entropy_relay(ea, 2, s, &launches);
-            launch_entropy_relay(ea, 3, s, &launches);
+            for (int k = 0; k < 2; ++k) {
+                ++rounds;
+                CK(cudaMemsetAsync(&d_meta->changed[relay_slot(rounds)], 0, sizeof(uint32_t), s));
+                launch_entropy_relay(ea, rounds, s, &launches);
+            }
             mark(ctx, KPEG_T_ENTROPY_RELAY);
             CK(cudaMemcpyAsync(h_meta, d_meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
-            converged = h_meta->changed[3] == 0u;
+            converged = h_meta->changed[relay_slot(rounds)] == 0u;
         }
         if (!converged)
             return fail(ctx, KPEG_ERR_NOT_CONVERGED, "speculative decode did not reach a fixed point");
-        rounds = 3;
         CK(cudaMemsetAsync(&d_meta->status, 0, sizeof(uint32_t), s));
         CK(cudaMemsetAsync(&d_meta->exact_samples, 0, 2 * sizeof(uint32_t), s));
     }
+    const uint32_t rounds_run = (uint32_t)rounds;
 
     ctx->last_g = g;
     ctx->have_last = true;
@@ -334,11 +335,14 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
         stats->unstuffed_bytes = h_meta->total_kept;
         stats->segments = h_meta->total_rst + 1u;
         stats->subsequences = h_meta->nsub;
-        uint32_t used_rounds = 0;
-        for (int r = 1; r < MAX_RELAY_ROUNDS; ++r)
-            if (h_meta->changed[r])
-                used_rounds = (uint32_t)r;
-        stats->sync_rounds = used_rounds + 2u * extra_iterations;
+        uint32_t used_rounds = rounds_run;
+        if (extra_iterations == 0u) { // rounds that still changed something
+            used_rounds = 0;
+            for (int r = 1; r <= (int)rounds_run && r < MAX_RELAY_ROUNDS; ++r)
+                if (h_meta->changed[r])
+                    used_rounds = (uint32_t)r;
+        }
+        stats->sync_rounds = used_rounds;
         stats->exact_samples = h_meta->exact_samples;
         stats->kernel_launches = launches;
     }
@@ -407,7 +411,7 @@ extern "C" int kpeg_cuda_create(int device, kpeg_ctx **out)
     kernels_configure();
     if (const char *sb = getenv("KPEG_SUB_BITS")) {
         const long v = strtol(sb, nullptr, 10);
-        if (v >= 64 && v <= 65536 && v % 32 == 0)
+        if (v >= 64 && v <= 1024 && (v & (v - 1)) == 0)
             ctx->sub_bits = (uint32_t)v;
     }
     if (const char *rr = getenv("KPEG_RELAY_ROUNDS")) {
@@ -463,8 +467,8 @@ extern "C" int kpeg_cuda_set_tuning(kpeg_ctx *ctx, int sub_bits, int relay_round
     if (!ctx)
         return KPEG_ERR_ARG;
     if (sub_bits > 0) {
-        if (sub_bits < 64 || sub_bits > 65536 || sub_bits % 32)
-            return KPEG_ERR_ARG;
+        if (sub_bits < 64 || sub_bits > 1024 || (sub_bits & (sub_bits - 1)))
+            return KPEG_ERR_ARG; // power of two: the kernels address the staged stream with shifts
         ctx->sub_bits = (uint32_t)sub_bits;
     }
     if (relay_rounds > 0) {

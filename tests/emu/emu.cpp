@@ -94,7 +94,9 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
     uint32_t nsub = (total_bits + sub_bits - 1) / sub_bits;
     if (!nsub)
         nsub = 1;
-    StreamView S{(const uint32_t *)words.data(), seg_bit.data(), total_bits};
+    StreamView S{seg_bit.data(), total_bits};
+    const PlainWords PW{(const uint32_t *)words.data()};
+    const PlainLuts PL{&T->luts, T->canon};
 
     // K1 cold
     std::vector<SubState> X(nsub);
@@ -103,7 +105,7 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
         const uint32_t p0 = sub * sub_bits;
         const uint32_t end = std::min(p0 + sub_bits, total_bits);
         hint[sub] = g.nseg > 1 ? first_seg_at_or_after(seg_bit, g.nseg, p0) : (sub ? 1u : 0u);
-        X[sub] = decode_span<false>(S, g, T->luts, T->canon, end, p0, 0, 0, hint[sub], 0, nullptr, nullptr, nullptr);
+        X[sub] = decode_span<false>(PW, PL, S, g, end, p0, 0, 0, hint[sub], 0, nullptr, nullptr, nullptr);
         used_p[sub] = p0;
         used_cz[sub] = 0;
     }
@@ -118,7 +120,7 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
                 continue;
             const uint32_t end = std::min((sub + 1) * sub_bits, total_bits);
             const SubState out =
-                decode_span<false>(S, g, T->luts, T->canon, end, in.p, in.cz >> 8, in.cz & 0xFF, hint[sub], 0, nullptr, nullptr, nullptr);
+                decode_span<false>(PW, PL, S, g, end, in.p, in.cz >> 8, in.cz & 0xFF, hint[sub], 0, nullptr, nullptr, nullptr);
             used_p[sub] = in.p;
             used_cz[sub] = in.cz;
             if (out.p != X[sub].p || out.cz != X[sub].cz || out.n != X[sub].n || out.seg != X[sub].seg) {
@@ -163,7 +165,7 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
         if ((slot & 63u) != z || ((slot >> 6) % g.ncomp) != c)
             st |= ST_EXIT_MISMATCH;
         const uint32_t end = std::min((sub + 1) * sub_bits, total_bits);
-        const SubState out = decode_span<true>(S, g, T->luts, T->canon, end, p, c, z, hint[sub], slot, coef.data(), dcdiff.data(), &st);
+        const SubState out = decode_span<true>(PW, PL, S, g, end, p, c, z, hint[sub], slot, coef.data(), dcdiff.data(), &st);
         if (out.p != X[sub].p || out.cz != X[sub].cz)
             st |= ST_EXIT_MISMATCH;
         status |= st;

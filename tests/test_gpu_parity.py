@@ -57,7 +57,7 @@ def test_lena_coefficients_and_t81_mode(decoder, lena_jpg):
     check_against_oracle(decoder, lena_jpg, parity=False)
 
 
-@pytest.mark.parametrize("sub_bits", [64, 128, 256, 512, 1024, 4096])
+@pytest.mark.parametrize("sub_bits", [64, 128, 256, 512, 1024])
 def test_subsequence_sizes(decoder, lena_jpg, sub_bits):
     decoder.set_tuning(sub_bits=sub_bits)
     try:

@@ -59,8 +59,8 @@ def test_huffman_lut_kernel_code():
                 e = emu.emu_huff_lookup(counts.ctypes.data, syms.ctypes.data, is_ac, win, 0)
                 ec = emu.emu_huff_lookup(counts.ctypes.data, syms.ctypes.data, is_ac, win, 1)
                 assert e == ec, "LUT path and canonical search disagree"
-                assert (e & 31) == len(code)
                 assert ((e >> 5) & 15) == (s & 15)
+                assert (e & 31) - ((e >> 5) & 15) == len(code)  # bits 0-4: code length + magnitude bits
                 adv = e >> 9
                 assert adv == (1 if not is_ac else (64 if s == 0 else (s >> 4) + 1))
     # "1111111111111111" is no code: flagged as needing more than 16 bits
