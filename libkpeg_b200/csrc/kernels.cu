@@ -969,15 +969,19 @@ void launch_dc_scan(const DcArgs &a, cudaStream_t s, uint32_t *launches)
 // K3: fused dequantise + de-zigzag + IDCT + level shift + colour conversion + interleaved store
 // =================================================================================================
 //
-// One CTA reconstructs a strip of IDCT_MCUS_PER_CTA consecutive MCUs (a contiguous chunk of the
-// coefficient buffer, and -- when the strip does not wrap -- 8 contiguous runs of pixels).
+// idct_kernel: one CTA reconstructs a strip of IDCT_MCUS_PER_CTA consecutive MCUs (a contiguous chunk
+// of the coefficient buffer, and -- when the strip does not wrap -- 8 contiguous runs of pixels).
 //   stage 0  coalesced 16-byte loads of the strip's coefficients into shared memory (XOR-swizzled
 //            so that the per-thread 128-byte reads of stage 1 are bank-conflict free)
 //   stage 1  one thread per 8x8 block, all 64 values in registers: dequantise (AAN prescale folded
 //            into the quantiser), de-zigzag by register renaming, separable fp32 IDCT, rounding,
-//            tie-band test; samples inside the band are queued
-//   stage 2  the queued samples are re-evaluated in the reference's own operation order
-//   stage 3  per pixel row: YCbCr -> RGB (fp32 with proven margin, double otherwise), pack, store
+//            tie-band test (a 64-bit mask per block)
+//   stage 2  per pixel row: YCbCr -> RGB (fp32 with proven margin, double otherwise), pack, store;
+//            pixels with a sample inside the tie band are ALSO appended to a global record list
+// idct_patch_kernel: one thread per record re-evaluates the flagged samples in the reference's own
+// operation order (exact_sample), redoes the colour conversion and rewrites the pixel.  Keeping this
+// out of the fused kernel matters: it is a long, strictly serial double-precision chain on ~1 % of
+// the pixels; inside the strip kernel it kept two of three warps waiting at a barrier.
 
 __device__ __constant__ ZigZagTables c_zz = make_zigzag_tables();
 
@@ -986,36 +990,23 @@ struct ZzNat {
     static constexpr int value = zigzag_to_natural(I);
 };
 
-constexpr int IDCT_QUEUE_CAP = 1024;
+constexpr int IDCT_REC_CAP = 192;
 
 template <int NC>
 struct IdctSmem {
     static constexpr int NM = IDCT_MCUS_PER_CTA;
     static constexpr int NB = NM * NC;
-    uint4 coef[NB * 8];           // 16-byte chunks, chunk k of block b at b*8 + (k ^ (b & 7))
-    float4 samp[NC * 8 * 2 * NM]; // [comp][row][half][mcu] -> 4 samples (rounded, unshifted)
+    // The strip's coefficients (16-byte chunks, chunk k of block b at b*8 + (k ^ (b & 7))) are dead once
+    // every thread has pulled its block into registers; the rounded samples then reuse the space.
+    union {
+        uint4 coef[NB * 8];
+        float4 samp[NC * 8 * 2 * NM]; // [comp][row][half][mcu] -> 4 samples (rounded, unshifted)
+    };
     float qscale[NC][64];
-    int32_t qint[NC][64];
-    double cosd[8][8];
-    float cc[8][8];
-    uint16_t queue[IDCT_QUEUE_CAP];
-    uint32_t qcount;
+    uint2 tie[NB];                // per block: 64-bit mask of the samples inside the tie band
+    uint4 rec[IDCT_REC_CAP];      // tie records of this strip, flushed to the global list with ONE atomic
+    uint32_t nrec, rec_base;
 };
-
-template <int NC>
-__device__ __forceinline__ int smem_coef_at(const IdctSmem<NC> &sm, int bl, int zi)
-{
-    const int16_t *p = reinterpret_cast<const int16_t *>(&sm.coef[bl * 8 + ((zi >> 3) ^ (bl & 7))]);
-    return p[zi & 7];
-}
-
-template <int NC>
-__device__ __forceinline__ void store_sample(IdctSmem<NC> &sm, int comp, int ml, int s, float v)
-{
-    const int row = s >> 3, col = s & 7;
-    float *p = reinterpret_cast<float *>(&sm.samp[((comp * 8 + row) * 2 + (col >> 2)) * IdctSmem<NC>::NM + ml]);
-    p[col & 3] = v;
-}
 
 // coefficient I (zig-zag index) of a block held as eight 16-byte chunks
 template <int I>
@@ -1031,14 +1022,6 @@ __device__ __forceinline__ void dequant_dezigzag(const uint4 (&ch)[8], const flo
                                                  std::integer_sequence<int, Is...>)
 {
     ((f[ZzNat<Is>::value] = chunk_coef<Is>(ch) * q[Is]), ...);
-}
-
-// Out-of-line on purpose: called from 64 unrolled sites that almost never execute it.
-template <int NC>
-__device__ __noinline__ float resolve_exact(const IdctSmem<NC> *sm, int bl, int comp, int s)
-{
-    auto at = [&](int zi) { return smem_coef_at<NC>(*sm, bl, zi); };
-    return (float)exact_sample(at, sm->qint[comp], sm->cosd, sm->cc, c_zz.nat2zz, s >> 3, s & 7);
 }
 
 // Four ints -> four bytes with unsigned saturation (cvt.pack.sat: two values per instruction).
@@ -1060,8 +1043,159 @@ __device__ __noinline__ uint32_t colour_exact_px(float y, float cb, float cr)
     return (uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16);
 }
 
+// ---- exact pass ----------------------------------------------------------------------------------
+// Tables of the exact path in shared memory (lane-varying indices would serialise in the constant cache).
+struct ExactSmem {
+    double cosd[8][8];
+    float cc[8][8];
+    int32_t qint[MAX_COMP][64];
+    unsigned char nat2zz[64];
+};
+
+__device__ __forceinline__ void exact_smem_load(ExactSmem &es, const DeviceTables *t)
+{
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+        (&es.cosd[0][0])[i] = t->cosd[0][i];
+        (&es.cc[0][0])[i] = t->cc[0][i];
+        es.nat2zz[i] = c_zz.nat2zz[i];
+    }
+    for (int i = threadIdx.x; i < MAX_COMP * 64; i += blockDim.x)
+        (&es.qint[0][0])[i] = t->qint[0][i];
+    __syncthreads();
+}
+
+struct ExactCtx {
+    const int16_t *coef, *dc, *dcdiff;
+    uint8_t *pixels;
+    uint32_t parity;
+};
+
+__device__ __forceinline__ ExactCtx exact_ctx(const IdctArgs &a)
+{
+    ExactCtx x;
+    x.coef = a.coef;
+    x.dc = a.dc;
+    x.dcdiff = a.dcdiff;
+    x.pixels = a.pixels;
+    x.parity = a.g.flags & 1u;
+    return x;
+}
+
+template <int... Is>
+__device__ __forceinline__ void nonzero_mask_natural(const uint4 (&ch)[8], uint32_t &lo, uint32_t &hi,
+                                                     std::integer_sequence<int, Is...>)
+{
+    // bit NAT(i) set iff coefficient i (zig-zag index) is non-zero; all indices are compile-time
+    lo = 0;
+    hi = 0;
+    auto one = [&](auto I) {
+        constexpr int i = decltype(I)::value;
+        constexpr int nat = ZzNat<i>::value;
+        constexpr int k = i >> 3, j = (i & 7) >> 1, h = i & 1;
+        const uint32_t w = j == 0 ? ch[k].x : (j == 1 ? ch[k].y : (j == 2 ? ch[k].z : ch[k].w));
+        const bool nz = (h ? (w >> 16) : (w & 0xFFFFu)) != 0u;
+        if (nat < 32)
+            lo |= nz ? (1u << (nat & 31)) : 0u;
+        else
+            hi |= nz ? (1u << (nat & 31)) : 0u;
+    };
+    (one(std::integral_constant<int, Is>{}), ...);
+}
+
+// The reference's evaluation (idct_core.h exact_sample) of sample s of global block gb, visiting only the
+// non-zero coefficients, in ascending natural order (== u outer, v inner, MCU.cpp:184-187).
+__device__ __noinline__ int exact_sample_global(const int16_t *coef, const int16_t *dc, const int16_t *dcdiff,
+                                                const ExactSmem *es, uint32_t parity, uint32_t gb, uint32_t comp, int s)
+{
+    const int16_t *blk = coef + (size_t)gb * 64u;
+    uint4 ch[8];
+    const bool drop_ac = parity && dcdiff[gb] == 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        ch[k] = drop_ac ? make_uint4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uint4 *>(blk) + k);
+    const int dcv = dc[gb];
+    ch[0].x = (ch[0].x & 0xFFFF0000u) | ((uint32_t)dcv & 0xFFFFu);
+    uint32_t lo, hi;
+    nonzero_mask_natural(ch, lo, hi, std::make_integer_sequence<int, 64>{});
+    const int x = s >> 3, y = s & 7;
+    const int32_t *q = es->qint[comp];
+    float sum = 0.0f;
+    while (lo | hi) {
+        int nat;
+        if (lo) {
+            nat = __ffs(lo) - 1;
+            lo &= lo - 1;
+        } else {
+            nat = 32 + __ffs(hi) - 1;
+            hi &= hi - 1;
+        }
+        const int zi = es->nat2zz[nat];
+        const int cq = zi == 0 ? dcv : (int)blk[zi]; // L1 hit: the line was just loaded
+        const int u = nat >> 3, v = nat & 7;
+        const int F = cq * q[zi];
+        const float t = mul_f32(es->cc[u][v], (float)F);
+        const double d = mul_f64(mul_f64((double)t, es->cosd[x][u]), es->cosd[y][v]);
+        sum = (float)add_f64((double)sum, d);
+    }
+    const float out = (float)mul_f64(0.25, (double)sum);
+    return round_half_away(out);
+}
+
+// pixel (unshifted integer samples) -> packed bytes, fast path with exact fallback
 template <int NC>
-__global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA) idct_kernel(IdctArgs a)
+__device__ __forceinline__ uint32_t colour_px(float y, float cb, float cr)
+{
+    if (NC == 1) {
+        const int v = float_bits(y + (RINT_MAGIC + 128.0f)) - RINT_MAGIC_BITS;
+        return (uint32_t)clamp_u8(v);
+    }
+    int R, G, B;
+    if (!ycc_to_rgb_fast(y, cb, cr, R, G, B))
+        return colour_exact_px(y, cb, cr);
+    return (uint32_t)clamp_u8(R) | ((uint32_t)clamp_u8(G) << 8) | ((uint32_t)clamp_u8(B) << 16);
+}
+
+// Tie record: x = pixel index (image-major, row-major), y = global MCU index,
+// z = sample index in the block | mask of flagged components << 8, w = fast Y | fast Cb << 16 (int16),
+// and the fast Cr sample travels in the upper half of z.
+__device__ __forceinline__ uint4 make_tie_record(uint32_t pix, uint32_t mcu, int s, uint32_t mask, float y, float cb, float cr)
+{
+    uint4 r;
+    r.x = pix;
+    r.y = mcu;
+    r.z = (uint32_t)s | (mask << 8) | ((uint32_t)(uint16_t)(int)cr << 16);
+    r.w = (uint32_t)(uint16_t)(int)y | ((uint32_t)(uint16_t)(int)cb << 16);
+    return r;
+}
+
+template <int NC>
+__device__ __forceinline__ void resolve_and_store_pixel(const ExactCtx &a, const ExactSmem *es, const uint4 &r)
+{
+    const uint32_t mcu = r.y;
+    uint32_t mask = (r.z >> 8) & 7u;
+    const int s = (int)(r.z & 63u);
+    float v0 = (float)(short)(r.w & 0xFFFFu), v1 = (float)(short)(r.w >> 16), v2 = (float)(short)(r.z >> 16);
+    // lanes flag different components: one call site, lane-varying component, so the warp makes one
+    // pass per *number* of flagged components (almost always 1), not one per component
+    while (mask) {
+        const int c = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float e = (float)exact_sample_global(a.coef, a.dc, a.dcdiff, es, a.parity, mcu * NC + c, (uint32_t)c, s);
+        v0 = c == 0 ? e : v0;
+        v1 = c == 1 ? e : v1;
+        v2 = c == 2 ? e : v2;
+    }
+    const uint32_t px = colour_px<NC>(v0, v1, v2);
+    uint8_t *dst = a.pixels + (size_t)r.x * NC;
+    dst[0] = (uint8_t)px;
+    if (NC == 3) {
+        dst[1] = (uint8_t)(px >> 8);
+        dst[2] = (uint8_t)(px >> 16);
+    }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? 7 : 16) idct_kernel(IdctArgs a)
 {
     constexpr int NM = IDCT_MCUS_PER_CTA;
     constexpr int NB = NM * NC;
@@ -1077,17 +1211,11 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA) idct_kernel(IdctArgs a
     const uint32_t m = mcu0 + ml;
     const uint32_t blk0 = mcu0 * NC;
 
-    // ---- stage 0: tables + coefficients -> shared memory (coalesced 16-byte loads) -------------
-    for (int i = t; i < NC * 64; i += NB) {
+    // ---- stage 0: quantiser + coefficients -> shared memory (coalesced 16-byte loads) ---------------
+    for (int i = t; i < NC * 64; i += NB)
         (&sm.qscale[0][0])[i] = a.tables->qscale[0][i];
-        (&sm.qint[0][0])[i] = a.tables->qint[0][i];
-    }
-    for (int i = t; i < 64; i += NB) {
-        (&sm.cosd[0][0])[i] = a.tables->cosd[0][i];
-        (&sm.cc[0][0])[i] = a.tables->cc[0][i];
-    }
     if (t == 0)
-        sm.qcount = 0;
+        sm.nrec = 0;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.coef) + (size_t)blk0 * 8;
         const uint32_t nvalid = (a.g.total_blocks > blk0 ? min(a.g.total_blocks - blk0, (uint32_t)NB) : 0u) * 8u;
@@ -1104,25 +1232,22 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA) idct_kernel(IdctArgs a
     __syncthreads();
 
     // ---- stage 1: one thread = one 8x8 block ------------------------------------------------------
+    uint4 ch[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        ch[k] = sm.coef[bl * 8 + (k ^ (bl & 7))];
+    __syncthreads(); // everyone holds its block in registers: `samp` may now overwrite `coef`
     if (m < total_mcus) {
         const uint32_t gb = blk0 + bl;
         const int dcv = a.dc[gb];
         const bool drop_ac = (a.g.flags & 1u) && a.dcdiff[gb] == 0; // MCU.cpp:97-104
-        uint4 ch[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            ch[k] = sm.coef[bl * 8 + (k ^ (bl & 7))];
         if (drop_ac) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 8; ++k)
                 ch[k] = make_uint4(0, 0, 0, 0);
-                sm.coef[bl * 8 + (k ^ (bl & 7))] = ch[k];
-            }
         }
-        // The entropy stage leaves slot 0 empty; the integrated DC value comes from K2.  Patch it
-        // into the shared copy as well: stage 2 reads coefficients from there.
+        // the entropy stage leaves slot 0 empty; the integrated DC value comes from K2
         ch[0].x = (ch[0].x & 0xFFFF0000u) | ((uint32_t)dcv & 0xFFFFu);
-        sm.coef[bl * 8 + (bl & 7)] = ch[0];
 
         float f[64];
         dequant_dezigzag(ch, sm.qscale[comp], f, std::make_integer_sequence<int, 64>{});
@@ -1134,7 +1259,7 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA) idct_kernel(IdctArgs a
             energy = fmaf(f[s], f[s], energy);
         const float thresh = 0.5f - tie_band(energy);
         // (x + 1.5*2^23) - 1.5*2^23 == rint(x) for |x| < 2^22; samples inside the tie band are
-        // collected in a 64-bit mask (predicated ORs, no branches in the unrolled part)
+        // collected in a 64-bit mask (predicated ORs, no branches)
         uint32_t tie_lo = 0, tie_hi = 0;
 #pragma unroll
         for (int row = 0; row < 8; ++row) {
@@ -1153,51 +1278,26 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA) idct_kernel(IdctArgs a
             sm.samp[((comp * 8 + row) * 2 + 0) * NM + ml] = make_float4(r[0], r[1], r[2], r[3]);
             sm.samp[((comp * 8 + row) * 2 + 1) * NM + ml] = make_float4(r[4], r[5], r[6], r[7]);
         }
-        while (tie_lo | tie_hi) {
-            int s;
-            if (tie_lo) {
-                s = __ffs(tie_lo) - 1;
-                tie_lo &= tie_lo - 1;
-            } else {
-                s = 32 + __ffs(tie_hi) - 1;
-                tie_hi &= tie_hi - 1;
-            }
-            const uint32_t slot = atomicAdd(&sm.qcount, 1u);
-            if (slot < IDCT_QUEUE_CAP)
-                sm.queue[slot] = (uint16_t)((bl << 6) | s);
-            else // queue full (pathologically flat image): resolve on the spot
-                store_sample<NC>(sm, comp, ml, s, resolve_exact<NC>(&sm, bl, comp, s));
-        }
+        sm.tie[bl] = make_uint2(tie_lo, tie_hi);
     }
     __syncthreads();
 
-    // ---- stage 2: exact (reference-order) evaluation of the samples inside the tie band -------------
-    {
-        const uint32_t nq_all = sm.qcount;
-        const uint32_t nq = min(nq_all, (uint32_t)IDCT_QUEUE_CAP);
-        for (uint32_t e = t; e < nq; e += NB) {
-            const uint32_t ent = sm.queue[e];
-            const int ebl = ent >> 6, s = ent & 63;
-            const int ecomp = ebl % NC, eml = ebl / NC;
-            auto at = [&](int zi) { return smem_coef_at<NC>(sm, ebl, zi); };
-            const int r = exact_sample(at, sm.qint[ecomp], sm.cosd, sm.cc, c_zz.nat2zz, s >> 3, s & 7);
-            store_sample<NC>(sm, ecomp, eml, s, (float)r);
-        }
-        if (t == 0 && nq_all)
-            atomicAdd(&a.meta->exact_samples, nq_all);
-    }
-    __syncthreads();
-
-    // ---- stage 3: colour conversion + interleaved store -------------------------------------------
+    // ---- stage 2: colour conversion + interleaved store -------------------------------------------
     if (m < total_mcus) {
         const uint32_t img = m / a.g.mcus_per_image;
         const uint32_t mi = m - img * a.g.mcus_per_image;
         const uint32_t by = mi / a.g.mcus_x, bx = mi - by * a.g.mcus_x;
         const uint32_t W = a.g.width, H = a.g.height;
-        uint8_t *img_base = a.pixels + (size_t)img * W * H * NC;
+        const uint32_t img_pix0 = img * W * H;
+        uint8_t *img_base = a.pixels + (size_t)img_pix0 * NC;
         const bool full_w = bx * 8u + 8u <= W;
         const bool vec_ok = full_w && (W % 8u == 0u) && ((reinterpret_cast<uintptr_t>(a.pixels) & 7u) == 0);
         uint32_t colour_exact = 0;
+        bool overflow = false;
+        uint2 tmask[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            tmask[c] = sm.tie[ml * NC + c];
         for (int row = comp; row < 8; row += NC) { // the NC warps of the CTA share the 8 pixel rows
             const uint32_t y = by * 8u + row;
             if (y >= H)
@@ -1252,11 +1352,111 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA) idct_kernel(IdctArgs a
                     if ((uint32_t)j < nbytes)
                         dst[j] = (uint8_t)(out[j >> 2] >> (8 * (j & 3)));
             }
+            // pixels of this row with a sample inside the tie band: queue them for the exact pass
+            uint32_t rowmask[NC], any = 0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const uint32_t w = row < 4 ? tmask[c].x : tmask[c].y;
+                rowmask[c] = (w >> ((row & 3) * 8)) & 0xFFu;
+                any |= rowmask[c];
+            }
+            while (any) {
+                const int j = __ffs(any) - 1;
+                any &= any - 1;
+                const uint32_t x = bx * 8u + (uint32_t)j;
+                if (x >= W)
+                    continue;
+                uint32_t cm = 0;
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    cm |= ((rowmask[c] >> j) & 1u) << c;
+                // fast samples of this pixel, re-read from shared memory (dynamic index j)
+                const float *sp = reinterpret_cast<const float *>(sm.samp);
+                float fy, fcb = 0.0f, fcr = 0.0f;
+                fy = sp[(((0 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
+                if (NC == 3) {
+                    fcb = sp[(((1 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
+                    fcr = sp[((((NC - 1) * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
+                }
+                const uint4 rec = make_tie_record(img_pix0 + y * W + x, m, row * 8 + j, cm, fy, fcb, fcr);
+                const uint32_t at = atomicAdd(&sm.nrec, 1u); // shared-memory counter: one global atomic per strip
+                if (at < (uint32_t)IDCT_REC_CAP)
+                    sm.rec[at] = rec;
+                else
+                    overflow = true; // more tied pixels than a strip's list holds: the strip is redone wholesale
+            }
         }
         if (colour_exact)
             atomicAdd(&a.meta->colour_exact, colour_exact);
+        if (overflow)
+            a.overflow_mcu[blockIdx.x] = 1u; // this strip has pixels that did not fit the record list
+    }
+    // ---- flush the strip's tie records --------------------------------------------------------------
+    __syncthreads();
+    const uint32_t nrec = min(sm.nrec, (uint32_t)IDCT_REC_CAP);
+    if (nrec == 0u && sm.nrec == 0u)
+        return;
+    if (t == 0) {
+        sm.rec_base = atomicAdd(&a.meta->tie_records, nrec);
+        if (sm.nrec > (uint32_t)IDCT_REC_CAP)
+            atomicAdd(&a.meta->tie_inline, sm.nrec - (uint32_t)IDCT_REC_CAP);
+    }
+    __syncthreads();
+    const uint32_t base = sm.rec_base;
+    for (uint32_t i = t; i < nrec; i += NB) {
+        if (base + i < a.tie_cap)
+            a.tie_rec[base + i] = sm.rec[i];
+        else {
+            a.overflow_mcu[blockIdx.x] = 1u; // global list full
+            if (i == t)
+                atomicAdd(&a.meta->tie_inline, 1u);
+        }
     }
 }
+
+// One thread per tie record (grid-stride).
+template <int NC>
+__global__ void __launch_bounds__(128) idct_patch_kernel(IdctArgs a)
+{
+    __shared__ ExactSmem es;
+    const uint32_t n = min(a.meta->tie_records, a.tie_cap);
+    if (blockIdx.x * blockDim.x >= n && a.meta->tie_inline == 0u)
+        return;
+    exact_smem_load(es, a.tables);
+    const ExactCtx x = exact_ctx(a);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        resolve_and_store_pixel<NC>(x, &es, a.tie_rec[i]);
+    // Overflow (pathologically flat images: more tied pixels than the record list holds).  Strips that
+    // reported an overflow are redone wholesale on the exact path: every sample of every pixel.
+    if (a.meta->tie_inline == 0u)
+        return;
+    const uint32_t total_mcus = a.g.nimages * a.g.mcus_per_image;
+    const uint32_t nstrips = (total_mcus + IDCT_MCUS_PER_CTA - 1) / IDCT_MCUS_PER_CTA;
+    const uint32_t W = a.g.width, H = a.g.height;
+    for (uint32_t strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+        if (a.overflow_mcu[strip] == 0u)
+            continue;
+        for (uint32_t w = threadIdx.x; w < IDCT_MCUS_PER_CTA * 64u; w += blockDim.x) {
+            const uint32_t m = strip * IDCT_MCUS_PER_CTA + (w >> 6);
+            const int s = (int)(w & 63u);
+            if (m >= total_mcus)
+                continue;
+            const uint32_t img = m / a.g.mcus_per_image, mi = m - img * a.g.mcus_per_image;
+            const uint32_t by = mi / a.g.mcus_x, bx = mi - by * a.g.mcus_x;
+            const uint32_t px_x = bx * 8u + (uint32_t)(s & 7), px_y = by * 8u + (uint32_t)(s >> 3);
+            if (px_x >= W || px_y >= H)
+                continue;
+            uint4 rec;
+            rec.x = img * W * H + px_y * W + px_x;
+            rec.y = m;
+            rec.z = (uint32_t)s | ((NC == 3 ? 7u : 1u) << 8);
+            rec.w = 0;
+            resolve_and_store_pixel<NC>(x, &es, rec);
+        }
+    }
+}
+
+static uint32_t g_patch_grid = 148 * 8;
 
 void kernels_configure()
 {
@@ -1278,6 +1478,7 @@ void kernels_configure()
                                                           k1_write_smem_bytes(512)) != cudaSuccess || per_sm < 1)
             per_sm = 3;
         g_k1_write_grid_cap = (uint32_t)(sms * per_sm);
+        g_patch_grid = (uint32_t)(sms * 8);
     }
     cudaFuncSetAttribute(idct_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<3>));
     cudaFuncSetAttribute(idct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<1>));
@@ -1287,11 +1488,14 @@ void launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches)
 {
     const uint32_t total_mcus = a.g.nimages * a.g.mcus_per_image;
     const uint32_t grid = (total_mcus + IDCT_MCUS_PER_CTA - 1) / IDCT_MCUS_PER_CTA;
-    if (a.g.ncomp == 3)
+    if (a.g.ncomp == 3) {
         idct_kernel<3><<<grid, 3 * IDCT_MCUS_PER_CTA, sizeof(IdctSmem<3>), s>>>(a);
-    else
+        idct_patch_kernel<3><<<g_patch_grid, 128, 0, s>>>(a);
+    } else {
         idct_kernel<1><<<grid, IDCT_MCUS_PER_CTA, sizeof(IdctSmem<1>), s>>>(a);
-    ++*launches;
+        idct_patch_kernel<1><<<g_patch_grid, 128, 0, s>>>(a);
+    }
+    *launches += 2;
 }
 
 // =================================================================================================

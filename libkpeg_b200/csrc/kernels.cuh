@@ -25,6 +25,8 @@ struct DevMeta {
     uint32_t exact_samples;
     uint32_t colour_exact;
     uint32_t final_slot;   // absolute slot the last subsequence ended on
+    uint32_t tie_records;  // pixels queued for the exact (reference-order) re-evaluation
+    uint32_t tie_inline;   // pixels resolved inside K3 because the record buffer was full
     uint32_t changed[MAX_RELAY_ROUNDS];
 };
 
@@ -79,6 +81,9 @@ struct IdctArgs {
     const DeviceTables *tables;
     uint8_t *pixels; // [nimages][height][width][ncomp]
     DevMeta *meta;
+    uint4 *tie_rec;       // [tie_cap] pixels with at least one sample inside the tie band
+    uint32_t tie_cap;
+    uint32_t *overflow_mcu; // [strips] set when a strip had tied pixels that did not fit tie_rec
     JobGeom g;
 };
 constexpr int IDCT_MCUS_PER_CTA = 32;

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -49,7 +50,7 @@ struct kpeg_ctx {
     int relay_rounds = 8;
 
     DevBuf scan, words, seg_bit, tile_kept, tile_rst, state, used, seg_hint, start_slot, scan_tiles;
-    DevBuf coef, dcdiff, dc, tile_carry, pixels, tables, meta, merged;
+    DevBuf coef, dcdiff, dc, tile_carry, pixels, tables, meta, merged, tie_rec, overflow;
     PinBuf h_tables, h_meta, h_stage;
 
     kpeg_plan plan_cached;
@@ -217,6 +218,12 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
     TRY(ensure(ctx, ctx->dcdiff, (size_t)g.total_blocks * 2u + 16));
     TRY(ensure(ctx, ctx->dc, (size_t)g.total_blocks * 2u + 16));
     TRY(ensure(ctx, ctx->tile_carry, (size_t)dc_tiles * 16u));
+    // tie records: room for 1/8 of all pixels (typical: ~1 %); beyond that K3 resolves in place
+    const uint64_t npix_job = (uint64_t)g.nimages * g.width * g.height;
+    const uint32_t tie_cap = (uint32_t)std::min<uint64_t>(npix_job / 8u + 4096u, 1u << 27);
+    TRY(ensure(ctx, ctx->tie_rec, (size_t)tie_cap * sizeof(uint4)));
+    const size_t overflow_bytes = ((size_t)total_mcus / IDCT_MCUS_PER_CTA + 2u) * sizeof(uint32_t);
+    TRY(ensure(ctx, ctx->overflow, overflow_bytes));
     TRY(ensure(ctx, ctx->meta, sizeof(DevMeta)));
     TRY(ensure_pinned(ctx, ctx->h_meta, sizeof(DevMeta)));
 
@@ -226,6 +233,7 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
 
     CK(cudaMemsetAsync(d_meta, 0, sizeof(DevMeta), s));
     CK(cudaMemsetAsync(ctx->words.p, 0, words_bytes, s));
+    CK(cudaMemsetAsync(ctx->overflow.p, 0, overflow_bytes, s));
     mark(ctx, KPEG_T_MEMSET);
 
     UnstuffArgs ua;
@@ -271,6 +279,9 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
     ia.tables = (const DeviceTables *)ctx->tables.p;
     ia.pixels = d_pixels;
     ia.meta = d_meta;
+    ia.tie_rec = (uint4 *)ctx->tie_rec.p;
+    ia.tie_cap = tie_cap;
+    ia.overflow_mcu = (uint32_t *)ctx->overflow.p;
     ia.g = g;
 
     launch_entropy_cold(ea, s, &launches);
@@ -320,6 +331,7 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
             return fail(ctx, KPEG_ERR_NOT_CONVERGED, "speculative decode did not reach a fixed point");
         CK(cudaMemsetAsync(&d_meta->status, 0, sizeof(uint32_t), s));
         CK(cudaMemsetAsync(&d_meta->exact_samples, 0, 2 * sizeof(uint32_t), s));
+        CK(cudaMemsetAsync(&d_meta->tie_records, 0, 2 * sizeof(uint32_t), s));
     }
     const uint32_t rounds_run = (uint32_t)rounds;
 
@@ -343,7 +355,7 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
                     used_rounds = (uint32_t)r;
         }
         stats->sync_rounds = used_rounds;
-        stats->exact_samples = h_meta->exact_samples;
+        stats->exact_samples = h_meta->tie_records; // pixels with at least one sample on the exact path
         stats->kernel_launches = launches;
     }
     return status_to_rc(ctx, h_meta->status);
@@ -436,7 +448,7 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
         cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->scan,   &ctx->words,  &ctx->seg_bit,    &ctx->tile_kept, &ctx->tile_rst, &ctx->state,
                       &ctx->used,   &ctx->seg_hint, &ctx->start_slot, &ctx->scan_tiles, &ctx->coef,    &ctx->dcdiff,   &ctx->dc,
-                      &ctx->tile_carry, &ctx->pixels, &ctx->tables,  &ctx->meta,     &ctx->merged};
+                      &ctx->tile_carry, &ctx->pixels, &ctx->tables,  &ctx->meta,     &ctx->merged, &ctx->tie_rec, &ctx->overflow};
     for (DevBuf *b : bufs)
         if (b->p)
             cudaFree(b->p);

@@ -199,3 +199,24 @@ def test_against_compiled_reference_live(decoder, tmp_path):
         got = decoder.decode_file(jpg)
         assert hdr == K.ppm_header(w, h)
         assert np.array_equal(got, payload)
+
+
+def test_flat_images_flood_the_exact_path(decoder):
+    """Solid-colour images: every block is DC-only and, for suitable DC values, EVERY sample is an exact
+    x.5 tie -- far more than the tie-record buffer holds, so the in-kernel overflow path runs too."""
+    PIL = pytest.importorskip("PIL.Image")
+    import io
+    for colour in [(131, 131, 131), (4, 200, 77), (255, 0, 128), (100, 101, 102)]:
+        img = PIL.new("RGB", (512, 384), colour)
+        buf = io.BytesIO()
+        img.save(buf, "JPEG", quality=93, subsampling=0)
+        jpg = buf.getvalue()
+        check_against_oracle(decoder, jpg)
+    # a gradient with large flat areas
+    arr = np.zeros((256, 512, 3), dtype=np.uint8)
+    arr[:, :, 0] = (np.arange(512) // 64 * 36)[None, :]
+    arr[:, :, 1] = 140
+    arr[:, :, 2] = (np.arange(256) // 32 * 30)[:, None]
+    buf = io.BytesIO()
+    PIL.fromarray(arr).save(buf, "JPEG", quality=90, subsampling=0)
+    check_against_oracle(decoder, buf.getvalue())
