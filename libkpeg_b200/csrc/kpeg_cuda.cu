@@ -1,10 +1,15 @@
 // kpeg_cuda.cu -- C-ABI host side of the B200 decode path (include/kpeg_cuda.h).
 //
-// Owns a CUDA stream, grow-only device scratch and pinned staging per context, builds the device
-// tables from a kpeg_plan and enqueues K0..K3 (kernels.cu).  There is no CPU decode in here: the
-// only host arithmetic is table preparation (Huffman LUTs, AAN-prescaled quantisers, the 64 double
-// cosines the exact IDCT path needs -- evaluated with the host libm exactly as the reference
-// evaluates them, src/MCU.cpp:193).
+// A context owns two LANES (CUDA stream + grow-only device scratch + pinned bookkeeping each) and
+// the device tables built from a kpeg_plan.  A job is enqueued on a lane (K0..K3, kernels.cu) and
+// finished later (stream sync, device status word, and -- rarely -- extra relay rounds).  Single
+// decodes use lane 0; a large host-pointer batch is cut into chunks that alternate between the two
+// lanes so the H2D copy of one chunk, the kernels of another and the D2H copy of a third overlap
+// (the end-to-end path is PCIe-bound: 3 bytes per pixel have to leave the device).
+//
+// There is no CPU decode in here: the only host arithmetic is table preparation (Huffman LUTs,
+// AAN-prescaled quantisers, the 64 double cosines the exact IDCT path needs -- evaluated with the
+// host libm exactly as the reference evaluates them, src/MCU.cpp:193).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -34,31 +39,58 @@ struct PinBuf {
     size_t cap = 0;
 };
 
-constexpr int MAX_EVENTS = 160;
+constexpr int MAX_EVENTS = 192;
+constexpr int NLANES = 2;
+
+struct Copy {
+    void *dst;
+    const void *src;
+    size_t bytes;
+};
+
+// One in-flight job between job_enqueue and job_finish.
+struct Job {
+    bool active = false;
+    JobGeom g = {};
+    EntropyArgs ea = {};
+    DcArgs da = {};
+    IdctArgs ia = {};
+    int rounds = 0;
+    uint32_t launches = 0;
+    uint32_t extra_iterations = 0;
+    size_t scan_len = 0;
+    std::vector<Copy> d2h; // result copies to (re)issue after the downstream stages
+};
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    DevBuf scan, words, seg_bit, tile_kept, tile_rst, state, work, seg_hint, start_slot, scan_tiles;
+    DevBuf coef, dcdiff, dc, tile_carry, pixels, meta, tie_rec, overflow;
+    PinBuf h_meta;
+    cudaEvent_t ev[MAX_EVENTS] = {};
+    int ev_stage[MAX_EVENTS] = {};
+    int nev = 0;
+    Job job;
+};
 
 } // namespace
 
 struct kpeg_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
     std::string err;
     bool profiling = false;
-    cudaEvent_t ev[MAX_EVENTS] = {};
-    int ev_stage[MAX_EVENTS] = {}; // stage that ENDS at event i (-1 for the first)
-    int nev = 0;
     uint32_t sub_bits = 512;
     int relay_rounds = 8;
+    Lane lane[NLANES];
 
-    DevBuf scan, words, seg_bit, tile_kept, tile_rst, state, used, seg_hint, start_slot, scan_tiles;
-    DevBuf coef, dcdiff, dc, tile_carry, pixels, tables, meta, merged, tie_rec, overflow;
-    PinBuf h_tables, h_meta, h_stage;
-
+    DevBuf tables, merged;
+    PinBuf h_tables, h_sep;
+    cudaEvent_t tables_ready = nullptr;
     kpeg_plan plan_cached;
     bool have_plan = false;
 
-    // last job (for kpeg_cuda_read_coefficients)
+    int last_lane = -1; // lane of the last finished job (kpeg_cuda_read_coefficients)
     JobGeom last_g = {};
-    bool have_last = false;
 };
 
 namespace {
@@ -82,17 +114,24 @@ int fail(kpeg_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
             return fail(ctx, KPEG_ERR_CUDA, #call, e_);                                                                \
     } while (0)
 
-int ensure(kpeg_ctx *ctx, DevBuf &b, size_t bytes)
+#define TRY(expr)                                                                                                      \
+    do {                                                                                                               \
+        int rc_ = (expr);                                                                                              \
+        if (rc_ != KPEG_OK)                                                                                            \
+            return rc_;                                                                                                \
+    } while (0)
+
+int ensure(kpeg_ctx *ctx, cudaStream_t stream, DevBuf &b, size_t bytes)
 {
     if (bytes <= b.cap)
         return KPEG_OK;
     if (b.p) {
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamSynchronize(stream));
         CK(cudaFree(b.p));
         b.p = nullptr;
         b.cap = 0;
     }
-    size_t want = bytes + bytes / 8 + 256;
+    const size_t want = bytes + bytes / 8 + 256;
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e != cudaSuccess) {
         b.p = nullptr;
@@ -102,17 +141,17 @@ int ensure(kpeg_ctx *ctx, DevBuf &b, size_t bytes)
     return KPEG_OK;
 }
 
-int ensure_pinned(kpeg_ctx *ctx, PinBuf &b, size_t bytes)
+int ensure_pinned(kpeg_ctx *ctx, cudaStream_t stream, PinBuf &b, size_t bytes)
 {
     if (bytes <= b.cap)
         return KPEG_OK;
     if (b.p) {
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamSynchronize(stream));
         CK(cudaFreeHost(b.p));
         b.p = nullptr;
         b.cap = 0;
     }
-    size_t want = bytes + bytes / 8 + 256;
+    const size_t want = bytes + bytes / 8 + 256;
     cudaError_t e = cudaMallocHost(&b.p, want);
     if (e != cudaSuccess) {
         b.p = nullptr;
@@ -122,55 +161,63 @@ int ensure_pinned(kpeg_ctx *ctx, PinBuf &b, size_t bytes)
     return KPEG_OK;
 }
 
-#define TRY(expr)                                                                                                      \
-    do {                                                                                                               \
-        int rc_ = (expr);                                                                                              \
-        if (rc_ != KPEG_OK)                                                                                            \
-            return rc_;                                                                                                \
-    } while (0)
-
-int build_tables(kpeg_ctx *ctx, const kpeg_plan *pl, DeviceTables *T)
-{
-    const char *why = nullptr;
-    const int rc = build_device_tables(pl, T, &why);
-    return rc == KPEG_OK ? rc : fail(ctx, rc, why);
-}
-
+// ---- plan -> device tables (shared by both lanes) ---------------------------------------------------
 int upload_plan(kpeg_ctx *ctx, const kpeg_plan *pl)
 {
     if (ctx->have_plan && memcmp(&ctx->plan_cached, pl, sizeof *pl) == 0)
         return KPEG_OK;
-    TRY(ensure_pinned(ctx, ctx->h_tables, sizeof(DeviceTables)));
-    TRY(ensure(ctx, ctx->tables, sizeof(DeviceTables)));
-    CK(cudaStreamSynchronize(ctx->stream)); // the pinned copy may still be in flight from an earlier plan
-    TRY(build_tables(ctx, pl, (DeviceTables *)ctx->h_tables.p));
-    CK(cudaMemcpyAsync(ctx->tables.p, ctx->h_tables.p, sizeof(DeviceTables), cudaMemcpyHostToDevice, ctx->stream));
+    // a new plan: nothing may still be reading the old tables
+    for (Lane &L : ctx->lane)
+        CK(cudaStreamSynchronize(L.stream));
+    cudaStream_t s0 = ctx->lane[0].stream;
+    TRY(ensure_pinned(ctx, s0, ctx->h_tables, sizeof(DeviceTables)));
+    TRY(ensure(ctx, s0, ctx->tables, sizeof(DeviceTables)));
+    const char *why = nullptr;
+    const int rc = build_device_tables(pl, (DeviceTables *)ctx->h_tables.p, &why);
+    if (rc != KPEG_OK)
+        return fail(ctx, rc, why);
+    CK(cudaMemcpyAsync(ctx->tables.p, ctx->h_tables.p, sizeof(DeviceTables), cudaMemcpyHostToDevice, s0));
+    CK(cudaEventRecord(ctx->tables_ready, s0));
+    for (int i = 1; i < NLANES; ++i)
+        CK(cudaStreamWaitEvent(ctx->lane[i].stream, ctx->tables_ready, 0));
     ctx->plan_cached = *pl;
     ctx->have_plan = true;
     return KPEG_OK;
 }
 
-int make_geom(kpeg_ctx *ctx, const kpeg_plan *pl, uint32_t nimages, JobGeom *g)
-{
-    const char *why = nullptr;
-    const int rc = make_job_geom(pl, nimages, ctx->sub_bits, g, &why);
-    return rc == KPEG_OK ? rc : fail(ctx, rc, why);
-}
-
-// Profiling: an event after every stage; mark(ctx, -1) opens a call.
-void mark(kpeg_ctx *ctx, int stage)
+// ---- profiling: an event after every stage; mark(.., -1) opens a window on a lane -------------------
+void mark(kpeg_ctx *ctx, Lane &L, int stage)
 {
     if (!ctx->profiling)
         return;
     if (stage < 0)
-        ctx->nev = 0;
-    if (ctx->nev >= MAX_EVENTS)
+        L.nev = 0;
+    if (L.nev >= MAX_EVENTS)
         return;
-    if (!ctx->ev[ctx->nev])
-        cudaEventCreate(&ctx->ev[ctx->nev]);
-    cudaEventRecord(ctx->ev[ctx->nev], ctx->stream);
-    ctx->ev_stage[ctx->nev] = stage;
-    ++ctx->nev;
+    if (!L.ev[L.nev])
+        cudaEventCreate(&L.ev[L.nev]);
+    cudaEventRecord(L.ev[L.nev], L.stream);
+    L.ev_stage[L.nev] = stage;
+    ++L.nev;
+}
+
+void add_times(kpeg_ctx *ctx, Lane &L, kpeg_stats *stats)
+{
+    if (!stats || !ctx->profiling || L.nev < 2)
+        return;
+    for (int i = 1; i < L.nev; ++i) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, L.ev[i - 1], L.ev[i]) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        const int st = L.ev_stage[i];
+        if (st >= 0 && st < KPEG_T_COUNT) {
+            stats->ms[st] += ms;
+            stats->ms_total += ms;
+        }
+    }
+    L.nev = 0;
 }
 
 int status_to_rc(kpeg_ctx *ctx, uint32_t st)
@@ -186,13 +233,42 @@ int status_to_rc(kpeg_ctx *ctx, uint32_t st)
     return KPEG_ERR_STREAM;
 }
 
-// The whole device pipeline for one job whose stuffed bytes are already at d_scan.
-// The caller has opened the profiling window with mark(ctx, -1).
-int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t scan_len, uint32_t nimages,
-            uint8_t *d_pixels, kpeg_stats *stats, uint32_t *launches_out)
+// everything downstream of the relay + the result copies + the bookkeeping read-back
+int enqueue_downstream(kpeg_ctx *ctx, Lane &L)
 {
+    Job &J = L.job;
+    cudaStream_t s = L.stream;
+    // no zero-fill of coef / dcdiff: the final pass writes every slot of every block it owns
+    launch_entropy_scan(J.ea, s, &J.launches);
+    mark(ctx, L, KPEG_T_ENTROPY_SCAN);
+    launch_entropy_write(J.ea, s, &J.launches);
+    mark(ctx, L, KPEG_T_ENTROPY_WRITE);
+    launch_dc_scan(J.da, s, &J.launches);
+    mark(ctx, L, KPEG_T_DC_SCAN);
+    launch_idct(J.ia, s, &J.launches);
+    mark(ctx, L, KPEG_T_IDCT);
+    for (const Copy &c : J.d2h)
+        CK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, s));
+    if (!J.d2h.empty())
+        mark(ctx, L, KPEG_T_D2H);
+    CK(cudaMemcpyAsync(L.h_meta.p, L.meta.p, sizeof(DevMeta), cudaMemcpyDeviceToHost, s));
+    return KPEG_OK;
+}
+
+// Enqueue the whole device pipeline for one job whose stuffed bytes are (or will be, in stream
+// order) at d_scan.  Optimistic: the stages downstream of the relay are issued before it is known
+// whether the pre-issued relay rounds reached the fixed point; job_finish repairs that if not.
+int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_scan, size_t scan_len, uint32_t nimages,
+                uint8_t *d_pixels, std::vector<Copy> d2h)
+{
+    Lane &L = ctx->lane[li];
+    Job &J = L.job;
+    cudaStream_t s = L.stream;
     JobGeom g;
-    TRY(make_geom(ctx, pl, nimages, &g));
+    const char *why = nullptr;
+    int rc = make_job_geom(pl, nimages, ctx->sub_bits, &g, &why);
+    if (rc != KPEG_OK)
+        return fail(ctx, rc, why);
     if (scan_len == 0 || scan_len >= (1ull << 29))
         return fail(ctx, KPEG_ERR_ARG, "entropy-coded segment must be 1 byte .. 512 MiB");
     TRY(upload_plan(ctx, pl));
@@ -204,183 +280,171 @@ int run_job(kpeg_ctx *ctx, const kpeg_plan *pl, const uint8_t *d_scan, size_t sc
     const uint32_t dc_tiles = (total_mcus + DC_TILE - 1) / DC_TILE;
     const size_t words_bytes = ((size_t)S + 3u) / 4u * 4u + 32u;
     const size_t coef_bytes = (size_t)g.total_blocks * 128u;
-
-    TRY(ensure(ctx, ctx->words, words_bytes));
-    TRY(ensure(ctx, ctx->seg_bit, ((size_t)g.nseg + 2u) * 4u));
-    TRY(ensure(ctx, ctx->tile_kept, (size_t)ntiles * 4u));
-    TRY(ensure(ctx, ctx->tile_rst, (size_t)ntiles * 4u));
-    TRY(ensure(ctx, ctx->state, (size_t)nsub_max * sizeof(SubState)));
-    TRY(ensure(ctx, ctx->used, (size_t)nsub_max * 2u * sizeof(uint32_t)));
-    TRY(ensure(ctx, ctx->seg_hint, (size_t)nsub_max * 4u));
-    TRY(ensure(ctx, ctx->start_slot, (size_t)nsub_max * 4u));
-    TRY(ensure(ctx, ctx->scan_tiles, ((size_t)nsub_max / 1024u + 2u) * sizeof(uint2)));
-    TRY(ensure(ctx, ctx->coef, coef_bytes + 256));
-    TRY(ensure(ctx, ctx->dcdiff, (size_t)g.total_blocks * 2u + 16));
-    TRY(ensure(ctx, ctx->dc, (size_t)g.total_blocks * 2u + 16));
-    TRY(ensure(ctx, ctx->tile_carry, (size_t)dc_tiles * 16u));
-    // tie records: room for 1/8 of all pixels (typical: ~1 %); beyond that K3 resolves in place
+    // tie records: room for 1/8 of all pixels (typical: ~1 %); beyond that strips are redone wholesale
     const uint64_t npix_job = (uint64_t)g.nimages * g.width * g.height;
     const uint32_t tie_cap = (uint32_t)std::min<uint64_t>(npix_job / 8u + 4096u, 1u << 27);
-    TRY(ensure(ctx, ctx->tie_rec, (size_t)tie_cap * sizeof(uint4)));
     const size_t overflow_bytes = ((size_t)total_mcus / IDCT_MCUS_PER_CTA + 2u) * sizeof(uint32_t);
-    TRY(ensure(ctx, ctx->overflow, overflow_bytes));
-    TRY(ensure(ctx, ctx->meta, sizeof(DevMeta)));
-    TRY(ensure_pinned(ctx, ctx->h_meta, sizeof(DevMeta)));
 
-    cudaStream_t s = ctx->stream;
-    uint32_t launches = 0;
-    DevMeta *d_meta = (DevMeta *)ctx->meta.p;
+    TRY(ensure(ctx, s, L.words, words_bytes));
+    TRY(ensure(ctx, s, L.seg_bit, ((size_t)g.nseg + 2u) * 4u));
+    TRY(ensure(ctx, s, L.tile_kept, (size_t)ntiles * 4u));
+    TRY(ensure(ctx, s, L.tile_rst, (size_t)ntiles * 4u));
+    TRY(ensure(ctx, s, L.state, (size_t)nsub_max * sizeof(SubState)));
+    TRY(ensure(ctx, s, L.work, (size_t)nsub_max * 2u * sizeof(uint32_t)));
+    TRY(ensure(ctx, s, L.seg_hint, (size_t)nsub_max * 4u));
+    TRY(ensure(ctx, s, L.start_slot, (size_t)nsub_max * 4u));
+    TRY(ensure(ctx, s, L.scan_tiles, ((size_t)nsub_max / 1024u + 2u) * sizeof(uint2)));
+    TRY(ensure(ctx, s, L.coef, coef_bytes + 256));
+    TRY(ensure(ctx, s, L.dcdiff, (size_t)g.total_blocks * 2u + 16));
+    TRY(ensure(ctx, s, L.dc, (size_t)g.total_blocks * 2u + 16));
+    TRY(ensure(ctx, s, L.tile_carry, (size_t)dc_tiles * 16u));
+    TRY(ensure(ctx, s, L.tie_rec, (size_t)tie_cap * sizeof(uint4)));
+    TRY(ensure(ctx, s, L.overflow, overflow_bytes));
+    TRY(ensure(ctx, s, L.meta, sizeof(DevMeta)));
+    TRY(ensure_pinned(ctx, s, L.h_meta, sizeof(DevMeta)));
+
+    J = Job();
+    J.active = true;
+    J.g = g;
+    J.scan_len = scan_len;
+    J.d2h = std::move(d2h);
+    DevMeta *d_meta = (DevMeta *)L.meta.p;
 
     CK(cudaMemsetAsync(d_meta, 0, sizeof(DevMeta), s));
-    CK(cudaMemsetAsync(ctx->words.p, 0, words_bytes, s));
-    CK(cudaMemsetAsync(ctx->overflow.p, 0, overflow_bytes, s));
-    mark(ctx, KPEG_T_MEMSET);
+    CK(cudaMemsetAsync(L.words.p, 0, words_bytes, s));
+    CK(cudaMemsetAsync(L.overflow.p, 0, overflow_bytes, s));
+    mark(ctx, L, KPEG_T_MEMSET);
 
     UnstuffArgs ua;
     ua.scan = d_scan;
     ua.scan_len = S;
     ua.ntiles = ntiles;
-    ua.tile_kept = (uint32_t *)ctx->tile_kept.p;
-    ua.tile_rst = (uint32_t *)ctx->tile_rst.p;
-    ua.words = (uint8_t *)ctx->words.p;
-    ua.seg_bit = (uint32_t *)ctx->seg_bit.p;
+    ua.tile_kept = (uint32_t *)L.tile_kept.p;
+    ua.tile_rst = (uint32_t *)L.tile_rst.p;
+    ua.words = (uint8_t *)L.words.p;
+    ua.seg_bit = (uint32_t *)L.seg_bit.p;
     ua.nseg = g.nseg;
     ua.meta = d_meta;
-    launch_unstuff(ua, g.sub_bits, s, &launches);
-    mark(ctx, KPEG_T_UNSTUFF);
+    launch_unstuff(ua, g.sub_bits, s, &J.launches);
+    mark(ctx, L, KPEG_T_UNSTUFF);
 
-    EntropyArgs ea;
-    ea.words = (const uint32_t *)ctx->words.p;
-    ea.seg_bit = (const uint32_t *)ctx->seg_bit.p;
+    EntropyArgs &ea = J.ea;
+    ea.words = (const uint32_t *)L.words.p;
+    ea.seg_bit = (const uint32_t *)L.seg_bit.p;
     ea.tables = (const DeviceTables *)ctx->tables.p;
     ea.meta = d_meta;
-    ea.state = (SubState *)ctx->state.p;
-    ea.worklist[0] = (uint32_t *)ctx->used.p;
-    ea.worklist[1] = (uint32_t *)ctx->used.p + nsub_max;
-    ea.seg_hint = (uint32_t *)ctx->seg_hint.p;
-    ea.start_slot = (uint32_t *)ctx->start_slot.p;
-    ea.scan_tiles = (uint2 *)ctx->scan_tiles.p;
-    ea.coef = (int16_t *)ctx->coef.p;
-    ea.dcdiff = (int16_t *)ctx->dcdiff.p;
+    ea.state = (SubState *)L.state.p;
+    ea.worklist[0] = (uint32_t *)L.work.p;
+    ea.worklist[1] = (uint32_t *)L.work.p + nsub_max;
+    ea.seg_hint = (uint32_t *)L.seg_hint.p;
+    ea.start_slot = (uint32_t *)L.start_slot.p;
+    ea.scan_tiles = (uint2 *)L.scan_tiles.p;
+    ea.coef = (int16_t *)L.coef.p;
+    ea.dcdiff = (int16_t *)L.dcdiff.p;
     ea.nsub_max = nsub_max;
     ea.g = g;
 
-    DcArgs da;
-    da.dcdiff = (const int16_t *)ctx->dcdiff.p;
-    da.dc = (int16_t *)ctx->dc.p;
-    da.tile_carry = (int32_t *)ctx->tile_carry.p;
+    DcArgs &da = J.da;
+    da.dcdiff = (const int16_t *)L.dcdiff.p;
+    da.dc = (int16_t *)L.dc.p;
+    da.tile_carry = (int32_t *)L.tile_carry.p;
     da.ntiles = dc_tiles;
     da.g = g;
 
-    IdctArgs ia;
-    ia.coef = (const int16_t *)ctx->coef.p;
-    ia.dc = (const int16_t *)ctx->dc.p;
-    ia.dcdiff = (const int16_t *)ctx->dcdiff.p;
+    IdctArgs &ia = J.ia;
+    ia.coef = (const int16_t *)L.coef.p;
+    ia.dc = (const int16_t *)L.dc.p;
+    ia.dcdiff = (const int16_t *)L.dcdiff.p;
     ia.tables = (const DeviceTables *)ctx->tables.p;
     ia.pixels = d_pixels;
     ia.meta = d_meta;
-    ia.tie_rec = (uint4 *)ctx->tie_rec.p;
+    ia.tie_rec = (uint4 *)L.tie_rec.p;
     ia.tie_cap = tie_cap;
-    ia.overflow_mcu = (uint32_t *)ctx->overflow.p;
+    ia.overflow_mcu = (uint32_t *)L.overflow.p;
     ia.g = g;
 
-    launch_entropy_cold(ea, s, &launches);
-    mark(ctx, KPEG_T_ENTROPY_COLD);
-    int rounds = ctx->relay_rounds < 2 ? 2 : (ctx->relay_rounds > MAX_RELAY_ROUNDS - 1 ? MAX_RELAY_ROUNDS - 1 : ctx->relay_rounds);
-    for (int r = 1; r <= rounds; ++r)
-        launch_entropy_relay(ea, r, s, &launches);
-    mark(ctx, KPEG_T_ENTROPY_RELAY);
+    launch_entropy_cold(ea, s, &J.launches);
+    mark(ctx, L, KPEG_T_ENTROPY_COLD);
+    J.rounds = ctx->relay_rounds < 2 ? 2 : (ctx->relay_rounds > MAX_RELAY_ROUNDS - 1 ? MAX_RELAY_ROUNDS - 1 : ctx->relay_rounds);
+    for (int r = 1; r <= J.rounds; ++r)
+        launch_entropy_relay(ea, r, s, &J.launches);
+    mark(ctx, L, KPEG_T_ENTROPY_RELAY);
+    return enqueue_downstream(ctx, L);
+}
 
-    DevMeta *h_meta = (DevMeta *)ctx->h_meta.p;
-    uint32_t extra_iterations = 0;
+// Wait for the job, check the device status word and -- rarely -- run more relay rounds and redo the
+// downstream stages.  Adds the job's figures to *stats (which the caller zeroed).
+int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
+{
+    Lane &L = ctx->lane[li];
+    Job &J = L.job;
+    if (!J.active)
+        return KPEG_OK;
+    J.active = false;
+    cudaStream_t s = L.stream;
+    DevMeta *d_meta = (DevMeta *)L.meta.p;
+    DevMeta *h_meta = (DevMeta *)L.h_meta.p;
     for (;;) {
-        // everything downstream of the relay; optimistic: issued before convergence is known
-        // no zero-fill of coef / dcdiff: the final pass writes every slot of every block it owns
-        launch_entropy_scan(ea, s, &launches);
-        mark(ctx, KPEG_T_ENTROPY_SCAN);
-        launch_entropy_write(ea, s, &launches);
-        mark(ctx, KPEG_T_ENTROPY_WRITE);
-        launch_dc_scan(da, s, &launches);
-        mark(ctx, KPEG_T_DC_SCAN);
-        launch_idct(ia, s, &launches);
-        mark(ctx, KPEG_T_IDCT);
-        CK(cudaMemcpyAsync(h_meta, d_meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         CK(cudaGetLastError());
         if (h_meta->status & (ST_BAD_MARKER | ST_SEG_COUNT))
             break; // malformed container-level structure: more rounds will not help
-        if (h_meta->changed[relay_slot(rounds)] == 0u)
+        if (h_meta->changed[relay_slot(J.rounds)] == 0u)
             break; // the last relay round changed nothing: fixed point, results are final
         // Rare: the relay needed more rounds than were pre-issued.  Run two more at a time until a
         // round changes nothing, then redo the downstream stages.
         bool converged = false;
         const uint32_t cap = h_meta->nsub / 2u + 4u;
-        while (!converged && extra_iterations < cap) {
-            ++extra_iterations;
+        while (!converged && J.extra_iterations < cap) {
+            ++J.extra_iterations;
             for (int k = 0; k < 2; ++k) {
-                ++rounds;
-                CK(cudaMemsetAsync(&d_meta->changed[relay_slot(rounds)], 0, sizeof(uint32_t), s));
-                launch_entropy_relay(ea, rounds, s, &launches);
+                ++J.rounds;
+                CK(cudaMemsetAsync(&d_meta->changed[relay_slot(J.rounds)], 0, sizeof(uint32_t), s));
+                launch_entropy_relay(J.ea, J.rounds, s, &J.launches);
             }
-            mark(ctx, KPEG_T_ENTROPY_RELAY);
+            mark(ctx, L, KPEG_T_ENTROPY_RELAY);
             CK(cudaMemcpyAsync(h_meta, d_meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
-            converged = h_meta->changed[relay_slot(rounds)] == 0u;
+            converged = h_meta->changed[relay_slot(J.rounds)] == 0u;
         }
         if (!converged)
             return fail(ctx, KPEG_ERR_NOT_CONVERGED, "speculative decode did not reach a fixed point");
         CK(cudaMemsetAsync(&d_meta->status, 0, sizeof(uint32_t), s));
         CK(cudaMemsetAsync(&d_meta->exact_samples, 0, 2 * sizeof(uint32_t), s));
         CK(cudaMemsetAsync(&d_meta->tie_records, 0, 2 * sizeof(uint32_t), s));
+        CK(cudaMemsetAsync(L.overflow.p, 0,
+                           ((size_t)(J.g.nimages * J.g.mcus_per_image) / IDCT_MCUS_PER_CTA + 2u) * sizeof(uint32_t), s));
+        TRY(enqueue_downstream(ctx, L));
     }
-    const uint32_t rounds_run = (uint32_t)rounds;
-
-    ctx->last_g = g;
-    ctx->have_last = true;
-    if (launches_out)
-        *launches_out = launches;
+    ctx->last_lane = li;
+    ctx->last_g = J.g;
     if (stats) {
-        stats->width = g.width;
-        stats->height = g.height;
-        stats->ncomp = g.ncomp;
-        stats->scan_bytes = scan_len;
-        stats->unstuffed_bytes = h_meta->total_kept;
-        stats->segments = h_meta->total_rst + 1u;
-        stats->subsequences = h_meta->nsub;
-        uint32_t used_rounds = rounds_run;
-        if (extra_iterations == 0u) { // rounds that still changed something
+        stats->width = J.g.width;
+        stats->height = J.g.height;
+        stats->ncomp = J.g.ncomp;
+        stats->scan_bytes += J.scan_len;
+        stats->unstuffed_bytes += h_meta->total_kept;
+        stats->segments += h_meta->total_rst + 1u;
+        stats->subsequences += h_meta->nsub;
+        uint32_t used_rounds = (uint32_t)J.rounds;
+        if (J.extra_iterations == 0u) { // rounds that still changed something
             used_rounds = 0;
-            for (int r = 1; r <= (int)rounds_run && r < MAX_RELAY_ROUNDS; ++r)
+            for (int r = 1; r <= J.rounds && r < MAX_RELAY_ROUNDS; ++r)
                 if (h_meta->changed[r])
                     used_rounds = (uint32_t)r;
         }
-        stats->sync_rounds = used_rounds;
-        stats->exact_samples = h_meta->tie_records; // pixels with at least one sample on the exact path
-        stats->kernel_launches = launches;
+        stats->sync_rounds = std::max(stats->sync_rounds, used_rounds);
+        stats->exact_samples += h_meta->tie_records; // pixels with at least one sample on the exact path
+        stats->kernel_launches += J.launches;
+        add_times(ctx, L, stats);
     }
     return status_to_rc(ctx, h_meta->status);
 }
 
-void fill_times(kpeg_ctx *ctx, kpeg_stats *stats)
+void zero_stats(kpeg_stats *stats)
 {
-    if (!stats)
-        return;
-    for (int i = 0; i < KPEG_T_COUNT; ++i)
-        stats->ms[i] = 0.0f;
-    stats->ms_total = 0.0f;
-    if (!ctx->profiling || ctx->nev < 2)
-        return;
-    for (int i = 1; i < ctx->nev; ++i) {
-        float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, ctx->ev[i - 1], ctx->ev[i]) != cudaSuccess) {
-            cudaGetLastError();
-            continue;
-        }
-        const int st = ctx->ev_stage[i];
-        if (st >= 0 && st < KPEG_T_COUNT)
-            stats->ms[st] += ms;
-        stats->ms_total += ms;
-    }
+    if (stats)
+        memset(stats, 0, sizeof *stats);
 }
 
 } // namespace
@@ -416,10 +480,13 @@ extern "C" int kpeg_cuda_create(int device, kpeg_ctx **out)
     if (!ctx)
         return KPEG_ERR_NOMEM;
     ctx->device = device;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        delete ctx;
-        return KPEG_ERR_CUDA;
+    for (Lane &L : ctx->lane) {
+        if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) {
+            kpeg_cuda_destroy(ctx);
+            return KPEG_ERR_CUDA;
+        }
     }
+    cudaEventCreateWithFlags(&ctx->tables_ready, cudaEventDisableTiming);
     kernels_configure();
     if (const char *sb = getenv("KPEG_SUB_BITS")) {
         const long v = strtol(sb, nullptr, 10);
@@ -431,7 +498,17 @@ extern "C" int kpeg_cuda_create(int device, kpeg_ctx **out)
         if (v >= 2 && v < MAX_RELAY_ROUNDS)
             ctx->relay_rounds = (int)v;
     }
-    if (cudaGetLastError() != cudaSuccess) {
+    // 8 RSTn separators for packed batches
+    cudaMallocHost(&ctx->h_sep.p, 64);
+    if (ctx->h_sep.p) {
+        ctx->h_sep.cap = 64;
+        uint8_t *sep = (uint8_t *)ctx->h_sep.p;
+        for (int k = 0; k < 8; ++k) {
+            sep[2 * k] = 0xFF;
+            sep[2 * k + 1] = (uint8_t)(0xD0 + k);
+        }
+    }
+    if (cudaGetLastError() != cudaSuccess || !ctx->h_sep.p) {
         kpeg_cuda_destroy(ctx);
         return KPEG_ERR_CUDA;
     }
@@ -444,23 +521,33 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
     if (!ctx)
         return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream)
-        cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->scan,   &ctx->words,  &ctx->seg_bit,    &ctx->tile_kept, &ctx->tile_rst, &ctx->state,
-                      &ctx->used,   &ctx->seg_hint, &ctx->start_slot, &ctx->scan_tiles, &ctx->coef,    &ctx->dcdiff,   &ctx->dc,
-                      &ctx->tile_carry, &ctx->pixels, &ctx->tables,  &ctx->meta,     &ctx->merged, &ctx->tie_rec, &ctx->overflow};
-    for (DevBuf *b : bufs)
-        if (b->p)
-            cudaFree(b->p);
-    PinBuf *pins[] = {&ctx->h_tables, &ctx->h_meta, &ctx->h_stage};
-    for (PinBuf *b : pins)
-        if (b->p)
-            cudaFreeHost(b->p);
-    for (int i = 0; i < MAX_EVENTS; ++i)
-        if (ctx->ev[i])
-            cudaEventDestroy(ctx->ev[i]);
-    if (ctx->stream)
-        cudaStreamDestroy(ctx->stream);
+    for (Lane &L : ctx->lane) {
+        if (L.stream)
+            cudaStreamSynchronize(L.stream);
+        DevBuf *bufs[] = {&L.scan, &L.words,    &L.seg_bit,    &L.tile_kept,  &L.tile_rst, &L.state,
+                          &L.work, &L.seg_hint, &L.start_slot, &L.scan_tiles, &L.coef,     &L.dcdiff,
+                          &L.dc,   &L.tile_carry, &L.pixels,   &L.meta,       &L.tie_rec,  &L.overflow};
+        for (DevBuf *b : bufs)
+            if (b->p)
+                cudaFree(b->p);
+        if (L.h_meta.p)
+            cudaFreeHost(L.h_meta.p);
+        for (int i = 0; i < MAX_EVENTS; ++i)
+            if (L.ev[i])
+                cudaEventDestroy(L.ev[i]);
+        if (L.stream)
+            cudaStreamDestroy(L.stream);
+    }
+    if (ctx->tables.p)
+        cudaFree(ctx->tables.p);
+    if (ctx->merged.p)
+        cudaFree(ctx->merged.p);
+    if (ctx->h_tables.p)
+        cudaFreeHost(ctx->h_tables.p);
+    if (ctx->h_sep.p)
+        cudaFreeHost(ctx->h_sep.p);
+    if (ctx->tables_ready)
+        cudaEventDestroy(ctx->tables_ready);
     delete ctx;
 }
 
@@ -491,7 +578,7 @@ extern "C" int kpeg_cuda_set_tuning(kpeg_ctx *ctx, int sub_bits, int relay_round
     return KPEG_OK;
 }
 
-extern "C" void *kpeg_cuda_stream(kpeg_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" void *kpeg_cuda_stream(kpeg_ctx *ctx) { return ctx ? (void *)ctx->lane[0].stream : nullptr; }
 
 extern "C" void *kpeg_cuda_host_alloc(size_t bytes)
 {
@@ -526,7 +613,8 @@ extern "C" void kpeg_cuda_device_free(kpeg_ctx *ctx, void *p)
 {
     if (ctx && p) {
         cudaSetDevice(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
+        for (Lane &L : ctx->lane)
+            cudaStreamSynchronize(L.stream);
         cudaFree(p);
     }
 }
@@ -536,8 +624,8 @@ extern "C" int kpeg_cuda_memcpy_h2d(kpeg_ctx *ctx, void *dst, const void *src, s
     if (!ctx)
         return KPEG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->lane[0].stream));
+    CK(cudaStreamSynchronize(ctx->lane[0].stream));
     return KPEG_OK;
 }
 
@@ -546,8 +634,8 @@ extern "C" int kpeg_cuda_memcpy_d2h(kpeg_ctx *ctx, void *dst, const void *src, s
     if (!ctx)
         return KPEG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->lane[0].stream));
+    CK(cudaStreamSynchronize(ctx->lane[0].stream));
     return KPEG_OK;
 }
 
@@ -557,12 +645,10 @@ extern "C" int kpeg_cuda_decode_device(kpeg_ctx *ctx, const kpeg_plan *plan, con
     if (!ctx || !plan || !d_scan || !d_pixels_out)
         return KPEG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    if (stats)
-        memset(stats, 0, sizeof *stats);
-    mark(ctx, -1);
-    const int rc = run_job(ctx, plan, d_scan, scan_len, 1, d_pixels_out, stats, nullptr);
-    fill_times(ctx, stats);
-    return rc;
+    zero_stats(stats);
+    mark(ctx, ctx->lane[0], -1);
+    TRY(job_enqueue(ctx, 0, plan, d_scan, scan_len, 1, d_pixels_out, {}));
+    return job_finish(ctx, 0, stats);
 }
 
 extern "C" int kpeg_cuda_decode(kpeg_ctx *ctx, const kpeg_plan *plan, const uint8_t *scan, size_t scan_len,
@@ -571,22 +657,17 @@ extern "C" int kpeg_cuda_decode(kpeg_ctx *ctx, const kpeg_plan *plan, const uint
     if (!ctx || !plan || !scan || !pixels_out)
         return KPEG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    if (stats)
-        memset(stats, 0, sizeof *stats);
+    zero_stats(stats);
+    Lane &L = ctx->lane[0];
     const size_t npix = (size_t)plan->width * plan->height * plan->ncomp;
-    TRY(ensure(ctx, ctx->scan, scan_len + 64));
-    TRY(ensure(ctx, ctx->pixels, npix + 64));
-    mark(ctx, -1);
-    CK(cudaMemcpyAsync(ctx->scan.p, scan, scan_len, cudaMemcpyHostToDevice, ctx->stream));
-    mark(ctx, KPEG_T_H2D);
-    const int rc = run_job(ctx, plan, (const uint8_t *)ctx->scan.p, scan_len, 1, (uint8_t *)ctx->pixels.p, stats, nullptr);
-    if (rc != KPEG_OK && rc != KPEG_ERR_STREAM)
-        return rc;
-    CK(cudaMemcpyAsync(pixels_out, ctx->pixels.p, npix, cudaMemcpyDeviceToHost, ctx->stream));
-    mark(ctx, KPEG_T_D2H);
-    CK(cudaStreamSynchronize(ctx->stream));
-    fill_times(ctx, stats);
-    return rc;
+    TRY(ensure(ctx, L.stream, L.scan, scan_len + 64));
+    TRY(ensure(ctx, L.stream, L.pixels, npix + 64));
+    mark(ctx, L, -1);
+    CK(cudaMemcpyAsync(L.scan.p, scan, scan_len, cudaMemcpyHostToDevice, L.stream));
+    mark(ctx, L, KPEG_T_H2D);
+    TRY(job_enqueue(ctx, 0, plan, (const uint8_t *)L.scan.p, scan_len, 1, (uint8_t *)L.pixels.p,
+                    {Copy{pixels_out, L.pixels.p, npix}}));
+    return job_finish(ctx, 0, stats);
 }
 
 // Batch stream format: the n stuffed scans back to back, each followed by one 2-byte RSTn marker
@@ -619,68 +700,97 @@ extern "C" int kpeg_cuda_decode_batch_packed_device(kpeg_ctx *ctx, const kpeg_pl
     if (!ctx || !plan || n <= 0 || !d_packed || !d_pixels_out)
         return KPEG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    if (stats)
-        memset(stats, 0, sizeof *stats);
-    mark(ctx, -1);
-    const int rc = run_job(ctx, plan, d_packed, packed_len, (uint32_t)n, d_pixels_out, stats, nullptr);
-    fill_times(ctx, stats);
-    return rc;
+    zero_stats(stats);
+    mark(ctx, ctx->lane[0], -1);
+    TRY(job_enqueue(ctx, 0, plan, d_packed, packed_len, (uint32_t)n, d_pixels_out, {}));
+    return job_finish(ctx, 0, stats);
 }
 
 extern "C" int kpeg_cuda_decode_batch_device(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *d_scans,
                                              const uint64_t *scan_offsets, uint8_t *d_pixels_out, kpeg_stats *stats)
 {
-    // Device-resident scans without separators: re-pack on the device side with n small copies.
+    // Device-resident scans without separators: re-pack on the device with n small copies.
     if (!ctx || !plan || n <= 0 || !d_scans || !scan_offsets || !d_pixels_out)
         return KPEG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
+    zero_stats(stats);
+    Lane &L = ctx->lane[0];
     const size_t total = (size_t)(scan_offsets[n] - scan_offsets[0]) + 2u * (size_t)n;
-    TRY(ensure(ctx, ctx->scan, total + 64));
-    TRY(ensure_pinned(ctx, ctx->h_stage, 16));
-    CK(cudaStreamSynchronize(ctx->stream));
-    uint8_t *sep = (uint8_t *)ctx->h_stage.p;
-    for (int k = 0; k < 8; ++k) {
-        sep[2 * k] = 0xFF;
-        sep[2 * k + 1] = (uint8_t)(0xD0 + k);
-    }
+    TRY(ensure(ctx, L.stream, L.scan, total + 64));
+    const uint8_t *sep = (const uint8_t *)ctx->h_sep.p;
     size_t o = 0;
+    mark(ctx, L, -1);
     for (int i = 0; i < n; ++i) {
         const size_t len = (size_t)(scan_offsets[i + 1] - scan_offsets[i]);
-        CK(cudaMemcpyAsync((uint8_t *)ctx->scan.p + o, d_scans + scan_offsets[i], len, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync((uint8_t *)L.scan.p + o, d_scans + scan_offsets[i], len, cudaMemcpyDeviceToDevice, L.stream));
         o += len;
-        CK(cudaMemcpyAsync((uint8_t *)ctx->scan.p + o, sep + 2 * (i & 7), 2, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync((uint8_t *)L.scan.p + o, sep + 2 * (i & 7), 2, cudaMemcpyHostToDevice, L.stream));
         o += 2;
     }
-    return kpeg_cuda_decode_batch_packed_device(ctx, plan, n, (const uint8_t *)ctx->scan.p, total, d_pixels_out, stats);
+    mark(ctx, L, KPEG_T_H2D);
+    TRY(job_enqueue(ctx, 0, plan, (const uint8_t *)L.scan.p, total, (uint32_t)n, d_pixels_out, {}));
+    return job_finish(ctx, 0, stats);
 }
 
+// Host-pointer batch.  Scans go straight from the caller's buffers into the lane's packed stream
+// (no host-side packing pass); a batch large enough for it to matter is cut into chunks that
+// alternate between the two lanes, so copies in, kernels and copies out of different chunks overlap.
 extern "C" int kpeg_cuda_decode_batch(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *const *scans,
                                       const size_t *scan_lens, uint8_t *const *pixels_out, kpeg_stats *stats)
 {
     if (!ctx || !plan || n <= 0 || !scans || !scan_lens || !pixels_out)
         return KPEG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    if (stats)
-        memset(stats, 0, sizeof *stats);
-    const size_t total = kpeg_batch_packed_size(n, scan_lens);
+    zero_stats(stats);
     const size_t npix = (size_t)plan->width * plan->height * plan->ncomp;
-    TRY(ensure_pinned(ctx, ctx->h_stage, total));
-    TRY(ensure(ctx, ctx->scan, total + 64));
-    TRY(ensure(ctx, ctx->pixels, npix * (size_t)n + 64));
-    CK(cudaStreamSynchronize(ctx->stream));
-    TRY(kpeg_batch_pack(n, scans, scan_lens, (uint8_t *)ctx->h_stage.p, ctx->h_stage.cap));
-    mark(ctx, -1);
-    CK(cudaMemcpyAsync(ctx->scan.p, ctx->h_stage.p, total, cudaMemcpyHostToDevice, ctx->stream));
-    mark(ctx, KPEG_T_H2D);
-    const int rc = run_job(ctx, plan, (const uint8_t *)ctx->scan.p, total, (uint32_t)n, (uint8_t *)ctx->pixels.p, stats, nullptr);
-    if (rc != KPEG_OK && rc != KPEG_ERR_STREAM)
-        return rc;
-    for (int i = 0; i < n; ++i)
-        CK(cudaMemcpyAsync(pixels_out[i], (uint8_t *)ctx->pixels.p + npix * (size_t)i, npix, cudaMemcpyDeviceToHost, ctx->stream));
-    mark(ctx, KPEG_T_D2H);
-    CK(cudaStreamSynchronize(ctx->stream));
-    fill_times(ctx, stats);
-    return rc;
+    // chunking: pipeline only when the pixel traffic is worth it (>= 32 MB); about four chunks
+    int per_chunk = n;
+    if (n >= 2 && npix * (size_t)n >= (32u << 20))
+        per_chunk = std::max(1, (n + 3) / 4);
+    const int nchunks = (n + per_chunk - 1) / per_chunk;
+    const uint8_t *sep = (const uint8_t *)ctx->h_sep.p;
+    int rc_all = KPEG_OK;
+
+    for (int c = 0; c < nchunks; ++c) {
+        const int li = nchunks > 1 ? (c & 1) : 0;
+        Lane &L = ctx->lane[li];
+        // the lane's previous chunk must be complete before its buffers are reused
+        if (L.job.active) {
+            const int rc = job_finish(ctx, li, stats);
+            if (rc != KPEG_OK && rc != KPEG_ERR_STREAM)
+                return rc;
+            if (rc != KPEG_OK)
+                rc_all = rc;
+        }
+        const int i0 = c * per_chunk, i1 = std::min(n, i0 + per_chunk), m = i1 - i0;
+        size_t total = 0;
+        for (int i = i0; i < i1; ++i)
+            total += scan_lens[i] + 2;
+        TRY(ensure(ctx, L.stream, L.scan, total + 64));
+        TRY(ensure(ctx, L.stream, L.pixels, npix * (size_t)m + 64));
+        mark(ctx, L, -1);
+        size_t o = 0;
+        for (int i = i0; i < i1; ++i) {
+            CK(cudaMemcpyAsync((uint8_t *)L.scan.p + o, scans[i], scan_lens[i], cudaMemcpyHostToDevice, L.stream));
+            o += scan_lens[i];
+            CK(cudaMemcpyAsync((uint8_t *)L.scan.p + o, sep + 2 * (i & 7), 2, cudaMemcpyHostToDevice, L.stream));
+            o += 2;
+        }
+        mark(ctx, L, KPEG_T_H2D);
+        std::vector<Copy> d2h;
+        d2h.reserve((size_t)m);
+        for (int i = i0; i < i1; ++i)
+            d2h.push_back(Copy{pixels_out[i], (uint8_t *)L.pixels.p + npix * (size_t)(i - i0), npix});
+        TRY(job_enqueue(ctx, li, plan, (const uint8_t *)L.scan.p, total, (uint32_t)m, (uint8_t *)L.pixels.p, std::move(d2h)));
+    }
+    for (int li = 0; li < NLANES; ++li) {
+        const int rc = job_finish(ctx, li, stats);
+        if (rc != KPEG_OK && rc != KPEG_ERR_STREAM)
+            return rc;
+        if (rc != KPEG_OK)
+            rc_all = rc;
+    }
+    return rc_all;
 }
 
 extern "C" int kpeg_cuda_decode_file(kpeg_ctx *ctx, const uint8_t *file, size_t len, uint32_t flags, uint8_t *pixels_out,
@@ -705,17 +815,18 @@ extern "C" int kpeg_cuda_read_coefficients(kpeg_ctx *ctx, int16_t *out, size_t c
 {
     if (!ctx || !out)
         return KPEG_ERR_ARG;
-    if (!ctx->have_last)
+    if (ctx->last_lane < 0)
         return fail(ctx, KPEG_ERR_ARG, "no decode has run on this context");
     CK(cudaSetDevice(ctx->device));
+    Lane &L = ctx->lane[ctx->last_lane];
     const size_t n = (size_t)ctx->last_g.total_blocks * 64u;
     if (cap < n)
         return fail(ctx, KPEG_ERR_ARG, "coefficient buffer too small");
-    TRY(ensure(ctx, ctx->merged, n * 2u));
-    launch_merge_dc((int16_t *)ctx->merged.p, (const int16_t *)ctx->coef.p, (const int16_t *)ctx->dc.p,
-                    (const int16_t *)ctx->dcdiff.p, ctx->last_g.total_blocks, ctx->last_g.flags, ctx->stream);
-    CK(cudaMemcpyAsync(out, ctx->merged.p, n * 2u, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    TRY(ensure(ctx, L.stream, ctx->merged, n * 2u));
+    launch_merge_dc((int16_t *)ctx->merged.p, (const int16_t *)L.coef.p, (const int16_t *)L.dc.p,
+                    (const int16_t *)L.dcdiff.p, ctx->last_g.total_blocks, ctx->last_g.flags, L.stream);
+    CK(cudaMemcpyAsync(out, ctx->merged.p, n * 2u, cudaMemcpyDeviceToHost, L.stream));
+    CK(cudaStreamSynchronize(L.stream));
     CK(cudaGetLastError());
     return KPEG_OK;
 }
