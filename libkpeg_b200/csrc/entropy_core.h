@@ -66,11 +66,13 @@ struct PlainLuts {
     const HuffCanon *canon;
     // toff = table index * LUT_SIZE
     KPEG_HD uint32_t fast(uint32_t toff, uint32_t idx) const { return (&set->fast[0][0])[toff + idx]; }
-    KPEG_HD uint32_t slow(uint32_t toff, uint32_t win) const
+    // e = first-level entry with (e & 31) == 0: pointer to a sub-table, or 0
+    KPEG_HD uint32_t slow(uint32_t toff, uint32_t win, uint32_t e) const
     {
         const uint32_t ti = toff >> LUT_BITS;
-        const uint32_t li = (win >> 16) - set->long_base[ti];
-        return li < set->long_n[ti] ? (uint32_t)set->longlut[ti][li] : huff_slow_lookup(canon[ti], win);
+        if (e)
+            return set->longlut[ti][((e >> 5) - 1u) * 64u + ((win >> 16) & 63u)];
+        return huff_slow_lookup(canon[ti], win);
     }
 };
 
@@ -87,17 +89,25 @@ struct StreamView {
 };
 
 // ---- coefficient sinks (final pass) ------------------------------------------------------------------
+// put(is_dc, slot, adv, valid, value): a DC difference belongs to block slot >> 6, an AC coefficient
+// to absolute slot (slot + adv - 1); `valid` is false for symbols that carry no value (EOB, ZRL).
 struct NullSink {
-    KPEG_HD void ac(uint32_t, int32_t) const {}
-    KPEG_HD void dc(uint32_t, int32_t) const {}
+    KPEG_HD void put(bool, uint32_t, uint32_t, bool, int32_t) const {}
 };
 
 // straight to global memory: coef[] must be zero-filled beforehand
 struct GlobalSink {
     int16_t *coef;   // [blocks][64]
     int16_t *dcdiff; // [blocks]
-    KPEG_HD void ac(uint32_t pos, int32_t v) const { coef[pos] = (int16_t)v; }
-    KPEG_HD void dc(uint32_t block, int32_t v) const { dcdiff[block] = (int16_t)v; }
+    KPEG_HD void put(bool is_dc, uint32_t slot, uint32_t adv, bool valid, int32_t v) const
+    {
+        if (!valid)
+            return;
+        if (is_dc)
+            dcdiff[slot >> 6] = (int16_t)v;
+        else if ((slot & 63u) + adv <= 64u)
+            coef[slot + adv - 1u] = (int16_t)v;
+    }
 };
 
 // Resumable decoder state of one subsequence.
@@ -169,8 +179,8 @@ KPEG_HD void decode_run(DecState &d, const Words &W, const Luts &L, const Stream
         const uint32_t nxt = W(j + 2u); // consumed at the bottom of the iteration, if at all
         const uint32_t win = funnel_left(w0, w1, sh);
         uint32_t e = L.fast(toff, win >> (32 - LUT_BITS));
-        if (e == 0u) // code longer than LUT_BITS (or no code at all)
-            e = L.slow(toff, win);
+        if ((e & 31u) == 0u) // code longer than LUT_BITS (or no code at all)
+            e = L.slow(toff, win, e);
         const uint32_t T = e & 31u;
         if (p + T > segend) {
             // The symbol would straddle a restart / image boundary: we are in its padding.
@@ -196,18 +206,13 @@ KPEG_HD void decode_run(DecState &d, const Words &W, const Luts &L, const Stream
         const uint32_t adv = e >> 9;
         if (WRITE) {
             const uint32_t size = (e >> 5) & 15u;
-            if (T - size > 16u)
-                st |= ST_BAD_CODE;
-            if (size) {
-                const uint32_t raw = (win << (T - size)) >> (32u - size);
-                const int32_t val = extend_value(raw, size);
-                if (slot + adv > total_slots || z + adv > 64u)
-                    st |= ST_SLOT_OVERFLOW;
-                else if (z == 0u)
-                    sink.dc(slot >> 6, val);
-                else
-                    sink.ac(slot + adv - 1u, val);
-            }
+            // status bits without branches: an invalid pattern has T == 17 and size == 0
+            st |= ((T - size) >> 4) & ((T - size) & 1u);      // ST_BAD_CODE (== 1): code "length" 17
+            st |= (size != 0u && z + adv > 64u) ? ST_SLOT_OVERFLOW : 0u; // a coefficient beyond the block (EOB's 64 is clamped)
+            // one store site for DC differences and AC coefficients
+            const uint32_t raw = (win << (T - size)) >> ((32u - size) & 31u);
+            const int32_t val = extend_value(raw, size | (size == 0u ? 1u : 0u));
+            sink.put(z == 0u, slot, adv, size != 0u && slot + adv <= total_slots, val);
         }
         p += T;
         sh += T;

@@ -46,13 +46,17 @@ inline int build_huff_lut(const uint8_t counts[16], const uint8_t *symbols, bool
                 set->fast[ti][w] = (uint16_t)e;
         }
     }
-    // second level: windows in [bound[LUT_BITS], 65536)
-    const uint32_t base = canon->bound[LUT_BITS];
-    set->long_base[ti] = base;
+    // second level: one 64-entry sub-table per 10-bit prefix that starts a longer code
     set->long_n[ti] = 0;
-    if (65536u - base <= (uint32_t)LONG_CAP) {
-        set->long_n[ti] = 65536u - base;
-        for (uint32_t w = base; w < 65536u; ++w) {
+    for (uint32_t prefix = canon->bound[LUT_BITS] >> (16 - LUT_BITS); prefix < (uint32_t)LUT_SIZE; ++prefix) {
+        // does any code start with this prefix?  (windows [prefix<<6, (prefix+1)<<6) below bound[16])
+        if ((prefix << (16 - LUT_BITS)) >= canon->bound[16])
+            break;
+        if (set->long_n[ti] + 64u > (uint32_t)LONG_CAP)
+            break; // no room: these prefixes keep entry 0 and use the canonical search
+        const uint32_t sub = set->long_n[ti] / 64u;
+        for (uint32_t low = 0; low < 64u; ++low) {
+            const uint32_t w = (prefix << (16 - LUT_BITS)) | low;
             uint32_t e = ENTRY_INVALID;
             for (int L = LUT_BITS + 1; L <= 16; ++L) {
                 if (w < canon->bound[L]) {
@@ -61,8 +65,10 @@ inline int build_huff_lut(const uint8_t counts[16], const uint8_t *symbols, bool
                     break;
                 }
             }
-            set->longlut[ti][w - base] = (uint16_t)e;
+            set->longlut[ti][sub * 64u + low] = (uint16_t)e;
         }
+        set->fast[ti][prefix] = (uint16_t)((sub + 1u) << 5);
+        set->long_n[ti] += 64u;
     }
     return 0;
 }

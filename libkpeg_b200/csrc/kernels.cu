@@ -190,7 +190,6 @@ void launch_unstuff(const UnstuffArgs &a, uint32_t sub_bits, cudaStream_t s, uin
 struct K1Smem {
     uint16_t fast[MAX_LUTS * LUT_SIZE];
     uint16_t longlut[MAX_LUTS * LONG_CAP];
-    uint32_t long_base[8];
     uint32_t long_n[8];
     uint32_t words[1]; // padded(ENTROPY_THREADS * words_per_subsequence + 4), sized at launch
 };
@@ -218,6 +217,7 @@ struct SmemWords {
 
 struct SmemLuts {
     uint32_t fast_addr; // shared byte address of fast[0]
+    uint32_t long_addr; // shared byte address of longlut[0]
     const K1Smem *sm;
     const HuffCanon *canon; // global
     __device__ __forceinline__ uint32_t fast(uint32_t toff, uint32_t idx) const
@@ -226,11 +226,16 @@ struct SmemLuts {
         asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(fast_addr + 2u * (toff + idx)));
         return v;
     }
-    __device__ __forceinline__ uint32_t slow(uint32_t toff, uint32_t win) const
+    __device__ __forceinline__ uint32_t slow(uint32_t toff, uint32_t win, uint32_t e) const
     {
         const uint32_t ti = toff >> LUT_BITS;
-        const uint32_t li = (win >> 16) - sm->long_base[ti];
-        return li < sm->long_n[ti] ? (uint32_t)sm->longlut[ti * LONG_CAP + li] : huff_slow_lookup(canon[ti], win);
+        if (e) { // pointer to a 64-entry sub-table indexed by stream bits 10..15
+            uint16_t v;
+            const uint32_t idx = ti * (uint32_t)LONG_CAP + ((e >> 5) - 1u) * 64u + ((win >> 16) & 63u);
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(long_addr + 2u * idx));
+            return v;
+        }
+        return huff_slow_lookup(canon[ti], win);
     }
 };
 
@@ -246,10 +251,8 @@ __device__ __forceinline__ void k1_stage_tables(K1Smem &sm, const EntropyArgs &a
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
             dst[i] = __ldg(src + i);
     }
-    if (threadIdx.x < MAX_LUTS) {
-        sm.long_base[threadIdx.x] = t->luts.long_base[threadIdx.x];
+    if (threadIdx.x < MAX_LUTS)
         sm.long_n[threadIdx.x] = t->luts.long_n[threadIdx.x];
-    }
     for (uint32_t ti = 0; ti < nt; ++ti) {
         const uint32_t n = (t->luts.long_n[ti] * (uint32_t)sizeof(uint16_t) + 15u) / 16u;
         const uint4 *src = reinterpret_cast<const uint4 *>(&t->luts.longlut[ti][0]);
@@ -292,6 +295,7 @@ __device__ __forceinline__ SmemLuts k1_luts(const K1Smem &sm, const EntropyArgs 
 {
     SmemLuts L;
     L.fast_addr = (uint32_t)__cvta_generic_to_shared(sm.fast);
+    L.long_addr = (uint32_t)__cvta_generic_to_shared(sm.longlut);
     L.sm = &sm;
     L.canon = a.tables->canon;
     return L;
@@ -586,17 +590,14 @@ __host__ __device__ inline size_t k1_write_smem_bytes(uint32_t sub_bits)
 struct SmemSink {
     uint32_t obuf_addr, dc_addr; // shared byte addresses
     uint32_t slot0, block0;      // first slot / block of the window
-    __device__ __forceinline__ void ac(uint32_t pos, int32_t v) const
+    // one predicated store: DC difference -> dcbuf[block - block0], AC coefficient -> obuf[pos - slot0]
+    __device__ __forceinline__ void put(bool is_dc, uint32_t slot, uint32_t adv, bool valid, int32_t v) const
     {
-        const uint32_t off = pos - slot0;
-        if (off < (uint32_t)(WRITE_WIN_BLOCKS * 64))
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(obuf_addr + 2u * off), "h"((uint16_t)v));
-    }
-    __device__ __forceinline__ void dc(uint32_t block, int32_t v) const
-    {
-        const uint32_t off = block - block0;
-        if (off < (uint32_t)WRITE_WIN_BLOCKS)
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(dc_addr + 2u * off), "h"((uint16_t)v));
+        const uint32_t off = is_dc ? (slot >> 6) - block0 : slot + adv - 1u - slot0;
+        const uint32_t lim = is_dc ? (uint32_t)WRITE_WIN_BLOCKS : (uint32_t)(WRITE_WIN_BLOCKS * 64);
+        const uint32_t addr = (is_dc ? dc_addr : obuf_addr) + 2u * off;
+        if (valid && off < lim)
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v));
     }
 };
 

@@ -31,7 +31,7 @@ namespace kpeg {
 // end of the block).  0 = not resolved.  The speculative passes only need the total and the advance.
 constexpr int LUT_BITS = 10;
 constexpr int LUT_SIZE = 1 << LUT_BITS;
-constexpr int LONG_CAP = 512;  // second-level table: one entry per left-aligned 16-bit window above the short codes
+constexpr int LONG_CAP = 512;  // second-level entries per table: 8 sub-tables of 64 (one per 10-bit prefix of long codes)
 constexpr uint32_t ENTRY_INVALID = 17u | (0u << 5) | (1u << 9); // "needs more than 16 bits"
 constexpr int MAX_COMP = 3;
 constexpr int MAX_LUTS = MAX_COMP * 2; // [comp*2 + (0=DC,1=AC)]
@@ -46,15 +46,17 @@ struct HuffCanon {
     uint32_t pad_[3];
 };
 
-// What the entropy kernels keep in shared memory.  Canonical codes are assigned in increasing order,
-// so every code longer than LUT_BITS lives in the window range [long_base, 65536): a direct table
-// over that (small: 320 entries for the Annex K AC tables) resolves long codes in one more load.
+// What the entropy kernels keep in shared memory: a classic two-level table.  A first-level entry
+// whose low five bits are zero is not a symbol: non-zero, it points at a 64-entry sub-table
+// ((entry >> 5) - 1) indexed by stream bits 10..15, which resolves every code of up to 16 bits that
+// starts with this 10-bit prefix in ONE more load (the Annex K AC tables need 5-6 sub-tables);
+// zero, the prefix has no sub-table (more than LONG_CAP/64 long prefixes, or no code at all) and
+// the canonical search decides.
 struct LutSet {
     uint16_t fast[MAX_LUTS][LUT_SIZE];
     uint16_t longlut[MAX_LUTS][LONG_CAP];
-    uint32_t long_base[MAX_LUTS]; // == bound[LUT_BITS]
-    uint32_t long_n[MAX_LUTS];    // entries of longlut in use; 0 if the range does not fit (-> canonical search)
-    uint32_t pad_[4];
+    uint32_t long_n[MAX_LUTS]; // entries of longlut in use (multiple of 64)
+    uint32_t pad_[2];
 };
 static_assert(sizeof(LutSet) % 16 == 0, "LutSet is copied to shared memory in 16-byte units");
 

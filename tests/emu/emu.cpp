@@ -316,11 +316,10 @@ uint32_t emu_huff_lookup(const uint8_t counts[16], const uint8_t *symbols, int i
                     break;
                 }
         } else {
-            e = L->fast[0][win >> (32 - LUT_BITS)];
-            if (!e) {
-                const uint32_t li = (win >> 16) - L->long_base[0];
-                e = li < L->long_n[0] ? (uint32_t)L->longlut[0][li] : huff_slow_lookup(canon, win);
-            }
+            const PlainLuts PL{L, &canon};
+            e = PL.fast(0, win >> (32 - LUT_BITS));
+            if ((e & 31u) == 0u)
+                e = PL.slow(0, win, e);
         }
     }
     delete L;
