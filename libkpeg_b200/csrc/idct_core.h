@@ -141,14 +141,14 @@ KPEG_HD void idct8x8_fast(float f[64])
                   f[8 * r + 7]);
 }
 
-// |fast - reference| <= TIE_REL * A + TIE_ABS with A = sum |dequantised coefficient| (derivation in
-// DESIGN.md "K3 rounding"; margin checked by tests/test_idct_core.py).  Because the 2-D DCT
-// basis is orthonormal, A <= 8 * sqrt(sum over the 64 outputs of y^2); the kernel uses that
-// energy, which costs one FMA per sample.
+// |fast - reference| <= TIE_REL * A + TIE_ABS with A = sum |dequantised coefficient| = sum |c_i| * q_i
+// (derivation in DESIGN.md "K3 rounding"; margin checked by tests/test_emu_logic.py).  The kernel
+// gets A exactly, in integers, for one instruction per coefficient pair (SIMD abs + dp2a on the
+// packed int16 coefficients and the 8-bit quantisers).
 constexpr float TIE_REL = 1.5e-6f;
 constexpr float TIE_ABS = 2.0e-5f;
 
-KPEG_HD float tie_band(float energy) { return TIE_REL * 8.0f * sqrtf(energy) + TIE_ABS; }
+KPEG_HD float tie_band(float A) { return TIE_REL * A + TIE_ABS; }
 
 // round-half-away-from-zero of a float, as roundl() does on the promoted value (MCU.cpp:228).
 KPEG_HD int round_half_away(float out)

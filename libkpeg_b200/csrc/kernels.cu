@@ -92,33 +92,28 @@ __global__ void __launch_bounds__(UNSTUFF_THREADS) unstuff_count_kernel(UnstuffA
         atomicOr(&a.meta->status, ST_BAD_MARKER);
 }
 
-// One block: exclusive scan of the per-tile counts, stream totals, segment-table prefill.
+// One block: exclusive scan of the per-tile counts, stream totals, segment-table prefill.  Every thread
+// takes a run of consecutive tiles (serial), the runs are combined with ONE block scan.
 __global__ void __launch_bounds__(1024) unstuff_scan_kernel(UnstuffArgs a, uint32_t sub_bits)
 {
     __shared__ uint32_t s_w[1024 / 32 + 1];
-    __shared__ uint32_t s_carry[2];
-    if (threadIdx.x == 0)
-        s_carry[0] = s_carry[1] = 0;
-    __syncthreads();
-    for (uint32_t t0 = 0; t0 < a.ntiles; t0 += 1024) {
-        const uint32_t t = t0 + threadIdx.x;
-        const uint32_t k = t < a.ntiles ? a.tile_kept[t] : 0u;
-        const uint32_t r = t < a.ntiles ? a.tile_rst[t] : 0u;
-        uint32_t tk, tr;
-        const uint32_t ek = block_exclusive_sum<1024>(k, s_w, tk);
-        const uint32_t er = block_exclusive_sum<1024>(r, s_w, tr);
-        if (t < a.ntiles) {
-            a.tile_kept[t] = s_carry[0] + ek;
-            a.tile_rst[t] = s_carry[1] + er;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            s_carry[0] += tk;
-            s_carry[1] += tr;
-        }
-        __syncthreads();
+    const uint32_t per = (a.ntiles + 1023u) / 1024u;
+    const uint32_t t0 = threadIdx.x * per, t1 = min(t0 + per, a.ntiles);
+    uint32_t sk = 0, sr = 0;
+    for (uint32_t t = t0; t < t1; ++t) {
+        sk += a.tile_kept[t];
+        sr += a.tile_rst[t];
     }
-    const uint32_t total_kept = s_carry[0], total_rst = s_carry[1];
+    uint32_t total_kept, total_rst;
+    uint32_t ek = block_exclusive_sum<1024>(sk, s_w, total_kept);
+    uint32_t er = block_exclusive_sum<1024>(sr, s_w, total_rst);
+    for (uint32_t t = t0; t < t1; ++t) {
+        const uint32_t k = a.tile_kept[t], r = a.tile_rst[t];
+        a.tile_kept[t] = ek;
+        a.tile_rst[t] = er;
+        ek += k;
+        er += r;
+    }
     const uint32_t total_bits = total_kept * 8u;
     for (uint32_t k = threadIdx.x; k < a.nseg + 2u; k += 1024)
         a.seg_bit[k] = k == 0u ? 0u : (k <= a.nseg ? total_bits : 0xFFFFFFFFu);
@@ -133,9 +128,14 @@ __global__ void __launch_bounds__(1024) unstuff_scan_kernel(UnstuffArgs a, uint3
     }
 }
 
+// Compaction: the tile's surviving bytes are gathered in shared memory at their final phase within a
+// 32-bit word, then written out as whole byte-swapped words (coalesced); only the at most three
+// bytes at either end of the tile's output range, which share a word with a neighbouring tile, go out
+// as single bytes.
 __global__ void __launch_bounds__(UNSTUFF_THREADS) unstuff_write_kernel(UnstuffArgs a)
 {
     __shared__ uint32_t s_w[UNSTUFF_THREADS / 32 + 1];
+    __shared__ __align__(16) uint8_t s_out[UNSTUFF_TILE + 16];
     const uint32_t base = (blockIdx.x * UNSTUFF_THREADS + threadIdx.x) * UNSTUFF_BYTES_PER_THREAD;
     ByteClass c;
     c.keep = c.rst = 0;
@@ -143,29 +143,53 @@ __global__ void __launch_bounds__(UNSTUFF_THREADS) unstuff_write_kernel(UnstuffA
         c = classify16(a.scan, a.scan_len, base);
     uint32_t tot;
     const uint32_t ex = block_exclusive_sum<UNSTUFF_THREADS>(__popc(c.keep) | (__popc(c.rst) << 16), s_w, tot);
-    uint32_t pos = a.tile_kept[blockIdx.x] + (ex & 0xFFFFu);
+    const uint32_t pos0 = a.tile_kept[blockIdx.x]; // first output byte of the tile
+    const uint32_t nkept = tot & 0xFFFFu;
+    const uint32_t phase = pos0 & 3u;
+    uint32_t lpos = phase + (ex & 0xFFFFu); // position inside s_out
     uint32_t ridx = a.tile_rst[blockIdx.x] + (ex >> 16);
-    if ((c.keep | c.rst) == 0u)
-        return;
-    if (c.keep == 0xFFFFu && (pos & 3u) == 0u) {
-        // common case: 16 surviving bytes landing word-aligned -> four byte-swapped word stores
-        uint32_t *w = reinterpret_cast<uint32_t *>(a.words + pos);
+    if (c.keep == 0xFFFFu && (lpos & 3u) == 0u) {
+        uint32_t *w = reinterpret_cast<uint32_t *>(s_out + lpos);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            w[k] = __byte_perm(c.b[k], 0, 0x0123);
-        return;
-    }
+            w[k] = c.b[k];
+    } else if (c.keep | c.rst) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        if (c.rst & (1u << i)) {
-            ++ridx;
-            if (ridx < a.nseg)
-                a.seg_bit[ridx] = pos * 8u;
+        for (int i = 0; i < 16; ++i) {
+            if (c.rst & (1u << i)) {
+                ++ridx;
+                if (ridx < a.nseg)
+                    a.seg_bit[ridx] = (pos0 - phase + lpos) * 8u;
+            }
+            if (c.keep & (1u << i)) {
+                s_out[lpos] = (uint8_t)(c.b[i >> 2] >> (8 * (i & 3)));
+                ++lpos;
+            }
         }
-        if (c.keep & (1u << i)) {
-            a.words[pos ^ 3u] = (uint8_t)(c.b[i >> 2] >> (8 * (i & 3)));
-            ++pos;
-        }
+    }
+    __syncthreads();
+    // s_out[phase .. phase + nkept) -> global bytes [pos0, pos0 + nkept); word g of the stream is
+    // s_out word (g - pos0/4), stored big-endian
+    const uint32_t g0 = pos0 >> 2;
+    const uint32_t first_full = phase ? 1u : 0u;          // word 0 is shared with the previous tile
+    const uint32_t end_byte = phase + nkept;              // in s_out coordinates
+    const uint32_t nfull_end = end_byte >> 2;             // words [first_full, nfull_end) are complete
+    uint32_t *gw = reinterpret_cast<uint32_t *>(a.words) + g0;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(s_out);
+    for (uint32_t w = first_full + threadIdx.x; w < nfull_end; w += UNSTUFF_THREADS)
+        gw[w] = __byte_perm(sw[w], 0, 0x0123);
+    if (threadIdx.x < 8u) {
+        // head bytes (phase .. 3 of word 0) and tail bytes (the incomplete last word), one per thread
+        uint32_t l;
+        if (threadIdx.x < 4u)
+            l = threadIdx.x; // candidate head byte
+        else
+            l = (nfull_end << 2) + (threadIdx.x - 4u); // candidate tail byte
+        const bool head = threadIdx.x < 4u && phase && l >= phase && l < end_byte && l < 4u;
+        const bool tail = threadIdx.x >= 4u && l < end_byte && l >= phase && (nfull_end >= first_full) &&
+                          !(phase && nfull_end == 0u); // word 0 incomplete at both ends: the head threads own it
+        if (head || tail)
+            a.words[((g0 << 2) + l) ^ 3u] = s_out[l];
     }
 }
 
@@ -389,8 +413,25 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_full_kernel(Ent
     }
 }
 
+// words of ONE subsequence, staged by its own thread (stride odd -> few bank conflicts)
+struct PrivateWords {
+    uint32_t addr; // shared byte address of this thread's first word
+    uint32_t gw0;  // global index of that word
+    __device__ __forceinline__ uint32_t operator()(uint32_t gw) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr + 4u * (gw - gw0)));
+        return v;
+    }
+};
+
+__host__ __device__ inline size_t k1_sparse_smem_bytes(uint32_t sub_bits)
+{
+    return sizeof(K1Smem) + (size_t)ENTROPY_THREADS * (sub_bits / 32u + 5u) * sizeof(uint32_t);
+}
+
 __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_sparse_kernel(EntropyArgs a, int round, int slot_prev,
-                                                                               int slot_cur)
+                                                                               int slot_cur, uint32_t wlog)
 {
     const uint32_t count = a.meta->changed[slot_prev];
     if (blockIdx.x * ENTROPY_THREADS >= count)
@@ -398,19 +439,29 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_sparse_kernel(E
     extern __shared__ __align__(16) unsigned char k1_raw[];
     K1Smem &sm = *reinterpret_cast<K1Smem *>(k1_raw);
     k1_stage_tables(sm, a);
-    __syncthreads();
     const uint32_t w = blockIdx.x * ENTROPY_THREADS + threadIdx.x;
-    if (w >= count)
-        return;
-    const uint32_t sub = a.worklist[(round - 1) & 1][w];
     const uint32_t nsub = a.meta->nsub, total_bits = a.meta->total_bits;
-    if (sub >= nsub)
+    const uint32_t sub = w < count ? a.worklist[(round - 1) & 1][w] : 0xFFFFFFFFu;
+    const bool active = sub < nsub;
+    uint4 inraw = make_uint4(0, 0, 0, 0);
+    const uint32_t stride = (1u << wlog) + 5u;
+    uint32_t *mine = sm.words + threadIdx.x * stride;
+    if (active) {
+        inraw = __ldcg(reinterpret_cast<const uint4 *>(&a.state[sub - 1]));
+        const uint32_t j0 = inraw.x >> 5;
+        const uint32_t total_words = ((total_bits + 31u) >> 5) + 4u;
+        for (uint32_t k = 0; k < stride - 1u; ++k)
+            mine[k] = j0 + k < total_words ? __ldg(a.words + j0 + k) : 0u;
+    }
+    __syncthreads(); // tables staged
+    if (!active)
         return;
     const SmemLuts L = k1_luts(sm, a);
-    const PlainWords W{a.words};
+    PrivateWords W;
+    W.addr = (uint32_t)__cvta_generic_to_shared(mine);
+    W.gw0 = inraw.x >> 5;
     StreamView S{a.seg_bit, total_bits};
-    const uint4 inraw = __ldcg(reinterpret_cast<const uint4 *>(&a.state[sub - 1]));
-    const uint32_t end = min((sub + 1u) * a.g.sub_bits, total_bits);
+    const uint32_t end = min((sub + 1u) << (wlog + 5u), total_bits);
     const SubState out = decode_span<false>(W, L, S, a.g, end, inraw.x, inraw.z >> 8, inraw.z & 0xFFu, a.seg_hint[sub], 0u,
                                             nullptr, nullptr, nullptr);
     relay_publish(a, sub, out, nsub, a.worklist[round & 1], &a.meta->changed[slot_cur]);
@@ -748,8 +799,9 @@ void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint3
         entropy_relay_full_kernel<<<k1_grid(a), ENTROPY_THREADS, k1_smem_bytes(a.g.sub_bits), s>>>(a, wlog);
     } else {
         const uint32_t grid = (a.nsub_max + ENTROPY_THREADS - 1) / ENTROPY_THREADS;
-        entropy_relay_sparse_kernel<<<grid, ENTROPY_THREADS, sizeof(K1Smem), s>>>(a, round, relay_slot(round - 1),
-                                                                                  relay_slot(round));
+        const uint32_t wlog = ilog2(a.g.sub_bits / 32u);
+        entropy_relay_sparse_kernel<<<grid, ENTROPY_THREADS, k1_sparse_smem_bytes(a.g.sub_bits), s>>>(
+            a, round, relay_slot(round - 1), relay_slot(round), wlog);
     }
     ++*launches;
 }
@@ -1004,6 +1056,7 @@ struct IdctSmem {
         float4 samp[NC * 8 * 2 * NM]; // [comp][row][half][mcu] -> 4 samples (rounded, unshifted)
     };
     float qscale[NC][64];
+    uint32_t qbytes[NC][16];      // the 8-bit quantisers, zig-zag order, four per word (for dp2a)
     uint2 tie[NB];                // per block: 64-bit mask of the samples inside the tie band
     uint4 rec[IDCT_REC_CAP];      // tie records of this strip, flushed to the global list with ONE atomic
     uint32_t nrec, rec_base;
@@ -1215,6 +1268,10 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? 7 : 16) idct
     // ---- stage 0: quantiser + coefficients -> shared memory (coalesced 16-byte loads) ---------------
     for (int i = t; i < NC * 64; i += NB)
         (&sm.qscale[0][0])[i] = a.tables->qscale[0][i];
+    for (int i = t; i < NC * 16; i += NB) {
+        const int32_t *q = &a.tables->qint[0][0] + i * 4;
+        (&sm.qbytes[0][0])[i] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+    }
     if (t == 0)
         sm.nrec = 0;
     {
@@ -1250,15 +1307,24 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? 7 : 16) idct
         // the entropy stage leaves slot 0 empty; the integrated DC value comes from K2
         ch[0].x = (ch[0].x & 0xFFFF0000u) | ((uint32_t)dcv & 0xFFFFu);
 
+        // A = sum |c_i| * q_i, exactly: SIMD abs on the int16 pairs, 16x8-bit dot product against the quantisers
+        uint32_t A = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t w[4] = {ch[k].x, ch[k].y, ch[k].z, ch[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t qb = sm.qbytes[comp][k * 2 + (j >> 1)];
+                const uint32_t aw = __vabsss2(w[j]);
+                A = (j & 1) ? __dp2a_hi(aw, qb, A) : __dp2a_lo(aw, qb, A);
+            }
+        }
+        const float thresh = 0.5f - tie_band((float)A);
+
         float f[64];
         dequant_dezigzag(ch, sm.qscale[comp], f, std::make_integer_sequence<int, 64>{});
         idct8x8_fast(f);
 
-        float energy = 0.0f;
-#pragma unroll
-        for (int s = 0; s < 64; ++s)
-            energy = fmaf(f[s], f[s], energy);
-        const float thresh = 0.5f - tie_band(energy);
         // (x + 1.5*2^23) - 1.5*2^23 == rint(x) for |x| < 2^22; samples inside the tie band are
         // collected in a 64-bit mask (predicated ORs, no branches)
         uint32_t tie_lo = 0, tie_hi = 0;
@@ -1464,7 +1530,8 @@ void kernels_configure()
     const int k1max = (int)k1_smem_bytes(1024);
     cudaFuncSetAttribute(entropy_cold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k1max);
     cudaFuncSetAttribute(entropy_relay_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k1max);
-    cudaFuncSetAttribute(entropy_relay_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
+    cudaFuncSetAttribute(entropy_relay_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)k1_sparse_smem_bytes(1024));
     {
         int dev = 0, sms = 148, per_sm = 8;
         cudaGetDevice(&dev);

@@ -212,10 +212,10 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
                 for (int i = 0; i < 64; ++i)
                     fb[zz.zz2nat[i]] = (float)cz[i] * T->qscale[c][i];
                 idct8x8_fast(fb);
-                float energy = 0.0f;
-                for (int s = 0; s < 64; ++s)
-                    energy = fmaf(fb[s], fb[s], energy);
-                const float thresh = 0.5f - tie_band(energy);
+                uint32_t A = 0;
+                for (int i = 0; i < 64; ++i)
+                    A += (uint32_t)abs((int)cz[i]) * (uint32_t)T->qint[c][i];
+                const float thresh = 0.5f - tie_band((float)A);
                 const float MAGIC = 12582912.0f;
                 for (int s = 0; s < 64; ++s) {
                     volatile float t = fb[s] + MAGIC;
@@ -290,12 +290,12 @@ float emu_idct_fast(const int16_t zzc[64], const uint16_t qt[64], float out[64])
         fb[nat] = (float)zzc[i] * qs;
     }
     idct8x8_fast(fb);
-    float energy = 0.0f;
-    for (int s = 0; s < 64; ++s) {
+    uint32_t A = 0;
+    for (int i = 0; i < 64; ++i)
+        A += (uint32_t)abs((int)zzc[i]) * (uint32_t)qt[i];
+    for (int s = 0; s < 64; ++s)
         out[s] = fb[s];
-        energy = fmaf(fb[s], fb[s], energy);
-    }
-    return tie_band(energy);
+    return tie_band((float)A);
 }
 
 // Huffman LUT lookup of a left-aligned 32-bit window: returns the packed entry.
