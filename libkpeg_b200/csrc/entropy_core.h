@@ -110,6 +110,24 @@ struct GlobalSink {
     }
 };
 
+// ---- symbol records ------------------------------------------------------------------------------
+// The relay passes decode every subsequence from (what converges to) its true entry state anyway;
+// they also write down what they decoded, one 32-bit record per symbol, so that the final pass is a
+// cheap, load-latency-tolerant EXPANSION of records instead of a third serial Huffman decode:
+//   bits 0-15 value (int16), bits 16-22 slot advance, bit 23 "carries a value",
+//   bits 24-31 type: 0 symbol, 1 symbol decoded from an invalid bit pattern, 0xFF boundary jump
+//   (bits 0-23 = index of the segment that starts at the boundary).
+constexpr uint32_t REC_JUMP = 0xFF000000u;
+
+KPEG_HD uint32_t pack_record(uint32_t adv, bool has_value, int32_t val, bool bad)
+{
+    return ((uint32_t)val & 0xFFFFu) | (adv << 16) | (has_value ? (1u << 23) : 0u) | (bad ? (1u << 24) : 0u);
+}
+
+struct NoRecorder {
+    KPEG_HD void emit(uint32_t, uint32_t) const {}
+};
+
 // Resumable decoder state of one subsequence.
 struct DecState {
     uint32_t p, j, sh, w0, w1; // bit position; word index, shift and the two stream words covering it
@@ -119,6 +137,7 @@ struct DecState {
     uint32_t k, segend;        // next boundary: segment index and its start bit
     uint32_t slot;             // absolute slot (final pass only)
     uint32_t st;               // ST_* bits (final pass only)
+    uint32_t nrec;             // symbol records emitted (relay passes)
 };
 
 template <class Words>
@@ -140,6 +159,7 @@ KPEG_HD void dec_init(DecState &d, const Words &W, const StreamView &S, uint32_t
     d.seg = -1;
     d.slot = slot;
     d.st = 0;
+    d.nrec = 0;
 }
 
 KPEG_HD SubState dec_exit_state(const DecState &d)
@@ -166,14 +186,14 @@ KPEG_HD SubState dec_exit_state(const DecState &d)
 // warp on almost every iteration.  Table offset toff = (2*component + (z != 0)) * LUT_SIZE: a DC
 // symbol switches to the component's AC table (toff |= LUT_SIZE), the end of a block to the next
 // table in the ring.  z is the zig-zag index.
-template <bool WRITE, class Words, class Luts, class Sink>
+template <bool WRITE, bool EMIT, class Words, class Luts, class Sink, class Rec>
 KPEG_HD void decode_run(DecState &d, const Words &W, const Luts &L, const StreamView &S, const JobGeom &g,
-                        uint32_t end_bit, uint32_t slot_limit, const Sink &sink)
+                        uint32_t end_bit, uint32_t slot_limit, const Sink &sink, const Rec &rec)
 {
     const uint32_t total_slots = g.total_blocks * 64u;
     const uint32_t ring = g.ncomp * 2u * (uint32_t)LUT_SIZE;
     uint32_t p = d.p, j = d.j, sh = d.sh, w0 = d.w0, w1 = d.w1, toff = d.toff, z = d.z, n = d.n;
-    uint32_t k = d.k, segend = d.segend, slot = d.slot, st = d.st;
+    uint32_t k = d.k, segend = d.segend, slot = d.slot, st = d.st, nrec = d.nrec;
     int32_t seg = d.seg;
     while (p < end_bit && (!WRITE || slot < slot_limit)) {
         const uint32_t nxt = W(j + 2u); // consumed at the bottom of the iteration, if at all
@@ -191,6 +211,12 @@ KPEG_HD void decode_run(DecState &d, const Words &W, const Luts &L, const Stream
             toff = 0;
             n = 0;
             seg = (int32_t)k;
+            if (EMIT) {
+                rec.emit(nrec, REC_JUMP | (k & 0xFFFFFFu));
+                ++nrec;
+                if (k > 0xFFFFFFu)
+                    st |= ST_REC_OVERFLOW;
+            }
             if (WRITE)
                 slot = seg_slot_base(g, k);
             ++k;
@@ -213,6 +239,13 @@ KPEG_HD void decode_run(DecState &d, const Words &W, const Luts &L, const Stream
             const uint32_t raw = (win << (T - size)) >> ((32u - size) & 31u);
             const int32_t val = extend_value(raw, size | (size == 0u ? 1u : 0u));
             sink.put(z == 0u, slot, adv, size != 0u && slot + adv <= total_slots, val);
+        }
+        if (EMIT) {
+            const uint32_t size = (e >> 5) & 15u;
+            const uint32_t raw = (win << (T - size)) >> ((32u - size) & 31u);
+            const int32_t val = extend_value(raw, size | (size == 0u ? 1u : 0u));
+            rec.emit(nrec, pack_record(adv, size != 0u, val, T - size > 16u));
+            ++nrec;
         }
         p += T;
         sh += T;
@@ -250,6 +283,47 @@ KPEG_HD void decode_run(DecState &d, const Words &W, const Luts &L, const Stream
     d.slot = slot;
     d.st = st;
     d.seg = seg;
+    d.nrec = nrec;
+}
+
+// Final pass over records: state is (next record, absolute slot, zig-zag index).  Stops when the
+// records are used up or the next symbol belongs to a block at or beyond slot_limit.
+template <class RecAt, class Sink>
+KPEG_HD void expand_run(uint32_t &k, uint32_t nrec, uint32_t &slot, uint32_t &z, uint32_t &st, const RecAt &rec_at,
+                        const JobGeom &g, uint32_t slot_limit, const Sink &sink)
+{
+    const uint32_t total_slots = g.total_blocks * 64u;
+    constexpr int BATCH = 8; // records fetched together: their loads are independent of the running state
+    while (k < nrec && slot < slot_limit) {
+        uint32_t rr[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j)
+            rr[j] = k + (uint32_t)j < nrec ? rec_at(k + (uint32_t)j) : 0u;
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            if (k < nrec && slot < slot_limit) { // a record left unused here is fetched again by the next call
+                const uint32_t r = rr[j];
+                ++k;
+                if ((r >> 24) == 0xFFu) {
+                    const uint32_t seg = r & 0xFFFFFFu;
+                    if (slot != seg_slot_base(g, seg) && (seg < g.nseg || slot < total_slots))
+                        st |= ST_SEG_MISMATCH;
+                    slot = seg_slot_base(g, seg);
+                    z = 0;
+                } else {
+                    const uint32_t adv = (r >> 16) & 127u;
+                    const bool has_value = (r >> 23) & 1u;
+                    st |= (r >> 24) & 1u; // ST_BAD_CODE
+                    st |= (has_value && z + adv > 64u) ? ST_SLOT_OVERFLOW : 0u;
+                    sink.put(z == 0u, slot, adv, has_value && slot + adv <= total_slots, (int32_t)(int16_t)(r & 0xFFFFu));
+                    uint32_t zn = z + adv;
+                    zn = zn > 64u ? 64u : zn;
+                    slot += zn - z;
+                    z = zn == 64u ? 0u : zn;
+                }
+            }
+        }
+    }
 }
 
 // One-shot convenience: whole subsequence, coefficients straight to global memory.
@@ -262,11 +336,11 @@ KPEG_HD SubState decode_span(const Words &W, const Luts &L, const StreamView &S,
     dec_init(d, W, S, p, c, z, k, slot);
     if (WRITE) {
         const GlobalSink sink{coef, dcdiff};
-        decode_run<true>(d, W, L, S, g, end_bit, 0xFFFFFFFFu, sink);
+        decode_run<true, false>(d, W, L, S, g, end_bit, 0xFFFFFFFFu, sink, NoRecorder{});
         if (d.st)
             *status_accum |= d.st;
     } else {
-        decode_run<false>(d, W, L, S, g, end_bit, 0xFFFFFFFFu, NullSink{});
+        decode_run<false, false>(d, W, L, S, g, end_bit, 0xFFFFFFFFu, NullSink{}, NoRecorder{});
     }
     return dec_exit_state(d);
 }

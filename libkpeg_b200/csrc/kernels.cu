@@ -362,6 +362,45 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_cold_kernel(EntropyAr
     }
 }
 
+// Record list layout: groups of 32 consecutive subsequences (one warp), record k of lane l of group g at
+// (g * kmax + k) * 32 + l.  Lanes emit / read their k-th record in the same loop iteration, so a warp
+// touches one 128-byte line per k, and consecutive k are consecutive lines: a sequential stream per warp.
+__device__ __forceinline__ size_t rec_base_index(uint32_t sub, uint32_t kmax)
+{
+    return ((size_t)(sub >> 5) * kmax) * 32u + (sub & 31u);
+}
+
+struct GlobalRecorder {
+    uint32_t *base; // &rec[rec_base_index(sub)]
+    uint32_t kmax;
+    __device__ __forceinline__ void emit(uint32_t k, uint32_t w) const
+    {
+        if (k < kmax)
+            base[(size_t)k * 32u] = w;
+    }
+};
+
+// decode subsequence `sub` from (p, cz) for a relay pass; emits records when the job uses them
+template <class Words>
+__device__ __forceinline__ SubState relay_decode(const EntropyArgs &a, const Words &W, const SmemLuts &L, const StreamView &S,
+                                                 uint32_t sub, uint32_t end, uint32_t p, uint32_t cz)
+{
+    DecState d;
+    dec_init(d, W, S, p, cz >> 8, cz & 0xFFu, a.seg_hint[sub], 0u);
+    if (a.rec) {
+        GlobalRecorder R;
+        R.base = a.rec + rec_base_index(sub, a.rec_kmax);
+        R.kmax = a.rec_kmax;
+        decode_run<false, true>(d, W, L, S, a.g, end, 0xFFFFFFFFu, NullSink{}, R);
+        a.nrec[sub] = d.nrec;
+        if (d.nrec > a.rec_kmax || (d.st & ST_REC_OVERFLOW))
+            atomicOr(&a.meta->status, ST_REC_OVERFLOW);
+    } else {
+        decode_run<false, false>(d, W, L, S, a.g, end, 0xFFFFFFFFu, NullSink{}, NoRecorder{});
+    }
+    return dec_exit_state(d);
+}
+
 // Relay: X[i] = decode(i, X[i-1]).  Round 1 visits every subsequence (tiles, like the cold pass) and
 // appends i+1 to the work list whenever X[i] changed; later rounds visit only the work list of the
 // round before (a few percent of the subsequences, scattered, so they read the stream from global
@@ -398,15 +437,21 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_full_kernel(Ent
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         k1_stage_stream(sm, a, tile, total_bits, wlog);
         const uint32_t sub = tile * ENTROPY_THREADS + threadIdx.x;
-        if (sub != 0u && sub < nsub) {
-            const SubState in = a.state[sub - 1]; // cold value or already relayed: either is a valid iterate
+        if (sub < nsub) {
+            // cold value or already relayed: either is a valid iterate; subsequence 0 starts from the true state
+            SubState in;
+            in.p = 0;
+            in.cz = 0;
+            if (sub)
+                in = a.state[sub - 1];
             const uint32_t start = sub << (wlog + 5u);
-            if (!(in.p == start && in.cz == 0u)) { // else the cold decode already started from this state
+            // without records, a subsequence whose cold decode already started from this state is done
+            if (a.rec || (sub != 0u && !(in.p == start && in.cz == 0u))) {
                 const SmemWords W = k1_words(sm, tile, wlog);
                 const uint32_t end = min((sub + 1u) << (wlog + 5u), total_bits);
-                const SubState out = decode_span<false>(W, L, S, a.g, end, in.p, in.cz >> 8, in.cz & 0xFFu, a.seg_hint[sub],
-                                                        0u, nullptr, nullptr, nullptr);
-                relay_publish(a, sub, out, nsub, a.worklist[1], &a.meta->changed[1]);
+                const SubState out = relay_decode(a, W, L, S, sub, end, in.p, in.cz);
+                if (sub)
+                    relay_publish(a, sub, out, nsub, a.worklist[1], &a.meta->changed[1]);
             }
         }
         __syncthreads();
@@ -462,8 +507,7 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_sparse_kernel(E
     W.gw0 = inraw.x >> 5;
     StreamView S{a.seg_bit, total_bits};
     const uint32_t end = min((sub + 1u) << (wlog + 5u), total_bits);
-    const SubState out = decode_span<false>(W, L, S, a.g, end, inraw.x, inraw.z >> 8, inraw.z & 0xFFu, a.seg_hint[sub], 0u,
-                                            nullptr, nullptr, nullptr);
+    const SubState out = relay_decode(a, W, L, S, sub, end, inraw.x, inraw.z);
     relay_publish(a, sub, out, nsub, a.worklist[round & 1], &a.meta->changed[slot_cur]);
 }
 
@@ -652,6 +696,42 @@ struct SmemSink {
     }
 };
 
+// Flush window blocks [wb, min(wb + WRITE_WIN_BLOCKS, b_end)): whole 128-byte lines for the blocks the
+// tile owns entirely, single elements for the (at most two) blocks shared with a neighbouring tile,
+// DC differences of the blocks whose first slot the tile owns.
+__device__ __forceinline__ void write_flush_window(const EntropyArgs &a, const WriteSmemTail &tail, uint32_t wb,
+                                                   uint32_t b_first, uint32_t b_end, uint32_t s_begin, uint32_t s_end,
+                                                   uint32_t t)
+{
+    const uint32_t we = min(wb + (uint32_t)WRITE_WIN_BLOCKS, b_end);
+    if (wb >= we)
+        return;
+    const uint32_t nblk = we - wb;
+    const uint4 *src = reinterpret_cast<const uint4 *>(tail.obuf);
+    uint4 *dst = reinterpret_cast<uint4 *>(a.coef) + (size_t)wb * 8u;
+    for (uint32_t ci = t; ci < nblk * 8u; ci += WRITE_THREADS) {
+        const uint32_t b = wb + (ci >> 3);
+        const bool full = (b << 6) >= s_begin && ((b + 1u) << 6) <= s_end;
+        if (full)
+            dst[ci] = src[ci];
+    }
+    if (wb == b_first && (s_begin & 63u)) {
+        const uint32_t pos = (b_first << 6) + t; // WRITE_THREADS == 64 == slots per block
+        if (pos >= s_begin && pos < s_end)
+            a.coef[pos] = tail.obuf[t];
+    }
+    if (we == b_end && (s_end & 63u) && !((b_end - 1u) == b_first && (s_begin & 63u) && wb == b_first)) {
+        const uint32_t pos = ((b_end - 1u) << 6) + t;
+        if (pos >= s_begin && pos < s_end)
+            a.coef[pos] = tail.obuf[((b_end - 1u - wb) << 6) + t];
+    }
+    for (uint32_t i = t; i < nblk; i += WRITE_THREADS) {
+        const uint32_t b = wb + i;
+        if ((b << 6) >= s_begin && (b << 6) < s_end)
+            a.dcdiff[b] = tail.dcbuf[i];
+    }
+}
+
 __global__ void __launch_bounds__(WRITE_THREADS) entropy_write_kernel(EntropyArgs a, uint32_t wlog)
 {
     extern __shared__ __align__(16) unsigned char k1_raw[];
@@ -715,40 +795,11 @@ __global__ void __launch_bounds__(WRITE_THREADS) entropy_write_kernel(EntropyArg
                 sink.block0 = wb;
                 // past the tile's own range (corrupt stream): finish in one go, writes fall outside the window
                 const uint32_t limit = wb < b_end ? (wb + WRITE_WIN_BLOCKS) << 6 : 0xFFFFFFFFu;
-                decode_run<true>(d, W, L, S, a.g, end, limit, sink);
+                decode_run<true, false>(d, W, L, S, a.g, end, limit, sink, NoRecorder{});
                 done = d.p >= end;
             }
             const bool all_done = __syncthreads_and(done);
-            // flush blocks [wb, we)
-            const uint32_t we = min(wb + (uint32_t)WRITE_WIN_BLOCKS, b_end);
-            if (wb < we) {
-                const uint32_t nblk = we - wb;
-                const uint4 *src = reinterpret_cast<const uint4 *>(tail.obuf);
-                uint4 *dst = reinterpret_cast<uint4 *>(a.coef) + (size_t)wb * 8u;
-                for (uint32_t ci = t; ci < nblk * 8u; ci += WRITE_THREADS) {
-                    const uint32_t b = wb + (ci >> 3);
-                    const bool full = (b << 6) >= s_begin && ((b + 1u) << 6) <= s_end;
-                    if (full)
-                        dst[ci] = src[ci];
-                }
-                // the (at most two) blocks shared with a neighbouring tile: own slots only
-                if (wb == b_first && (s_begin & 63u)) {
-                    const uint32_t pos = (b_first << 6) + t; // WRITE_THREADS == 64 == slots per block
-                    if (pos >= s_begin && pos < s_end)
-                        a.coef[pos] = tail.obuf[t];
-                }
-                if (we == b_end && (s_end & 63u) && !((b_end - 1u) == b_first && (s_begin & 63u) && wb == b_first)) {
-                    const uint32_t pos = ((b_end - 1u) << 6) + t;
-                    if (pos >= s_begin && pos < s_end)
-                        a.coef[pos] = tail.obuf[((b_end - 1u - wb) << 6) + t];
-                }
-                // DC differences of the blocks whose first slot this tile owns
-                for (uint32_t i = t; i < nblk; i += WRITE_THREADS) {
-                    const uint32_t b = wb + i;
-                    if ((b << 6) >= s_begin && (b << 6) < s_end)
-                        a.dcdiff[b] = tail.dcbuf[i];
-                }
-            }
+            write_flush_window(a, tail, wb, b_first, b_end, s_begin, s_end, t);
             if (all_done)
                 break;
             __syncthreads(); // the window is zeroed again
@@ -758,6 +809,81 @@ __global__ void __launch_bounds__(WRITE_THREADS) entropy_write_kernel(EntropyArg
             const SubState rec = a.state[sub];
             const SubState out = dec_exit_state(d);
             if (out.p != rec.p || out.cz != rec.cz)
+                st |= ST_EXIT_MISMATCH;
+            if (sub + 1u == nsub && a.meta->final_slot < total_slots)
+                st |= ST_SEG_MISMATCH; // the stream ended before the last MCU
+        }
+        __syncthreads();
+    }
+    if (st)
+        atomicOr(&a.meta->status, st);
+}
+
+// Final pass over the symbol records (see entropy_core.h): no Huffman decode, no stream, no tables --
+// a thread walks its subsequence's records (coalesced k-major loads, independent of each other, so
+// several are in flight), tracks (slot, zig-zag index) and drops values into the shared-memory window.
+struct GlobalRecAt {
+    const uint32_t *base;
+    __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return __ldg(base + (size_t)k * 32u); }
+};
+
+__global__ void __launch_bounds__(WRITE_THREADS) entropy_expand_kernel(EntropyArgs a)
+{
+    extern __shared__ __align__(16) unsigned char k1_raw[];
+    WriteSmemTail &tail = *reinterpret_cast<WriteSmemTail *>(k1_raw);
+    const uint32_t nsub = a.meta->nsub;
+    const uint32_t ntiles = (nsub + WRITE_THREADS - 1) / WRITE_THREADS;
+    const uint32_t total_slots = a.g.total_blocks * 64u;
+    const uint32_t t = threadIdx.x;
+    uint32_t st = 0;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t sub0 = tile * WRITE_THREADS, sub = sub0 + t;
+        const uint32_t s_begin = a.start_slot[sub0];
+        uint32_t s_end = (sub0 + WRITE_THREADS < nsub) ? a.start_slot[sub0 + WRITE_THREADS] : a.meta->final_slot;
+        s_end = min(s_end, total_slots);
+        const uint32_t b_first = s_begin >> 6;
+        const uint32_t b_end = s_end > s_begin ? (s_end + 63u) >> 6 : b_first;
+
+        uint32_t k = 0, n = 0, slot = 0, z = 0, expect = 0;
+        bool done = true;
+        GlobalRecAt R;
+        R.base = a.rec + rec_base_index(sub, a.rec_kmax);
+        if (sub < nsub) {
+            n = min(a.nrec[sub], a.rec_kmax);
+            slot = a.start_slot[sub];
+            z = sub ? (a.state[sub - 1].cz & 0xFFu) : 0u;
+            if ((slot & 63u) != z)
+                st |= ST_EXIT_MISMATCH;
+            expect = (sub + 1u < nsub) ? a.start_slot[sub + 1u] : a.meta->final_slot;
+            done = false;
+        }
+        for (uint32_t wb = b_first;; wb += WRITE_WIN_BLOCKS) {
+            {
+                uint4 *o = reinterpret_cast<uint4 *>(&tail);
+                constexpr int N16 = (int)(sizeof(WriteSmemTail) / 16);
+#pragma unroll 4
+                for (int i = t; i < N16; i += WRITE_THREADS)
+                    o[i] = make_uint4(0, 0, 0, 0);
+            }
+            __syncthreads();
+            if (!done) {
+                SmemSink sink;
+                sink.obuf_addr = (uint32_t)__cvta_generic_to_shared(tail.obuf);
+                sink.dc_addr = (uint32_t)__cvta_generic_to_shared(tail.dcbuf);
+                sink.slot0 = wb << 6;
+                sink.block0 = wb;
+                const uint32_t limit = wb < b_end ? (wb + WRITE_WIN_BLOCKS) << 6 : 0xFFFFFFFFu;
+                expand_run(k, n, slot, z, st, R, a.g, limit, sink);
+                done = k >= n;
+            }
+            const bool all_done = __syncthreads_and(done);
+            write_flush_window(a, tail, wb, b_first, b_end, s_begin, s_end, t);
+            if (all_done)
+                break;
+            __syncthreads();
+        }
+        if (sub < nsub) {
+            if (slot != expect)
                 st |= ST_EXIT_MISMATCH;
             if (sub + 1u == nsub && a.meta->final_slot < total_slots)
                 st |= ST_SEG_MISMATCH; // the stream ended before the last MCU
@@ -813,6 +939,16 @@ void launch_entropy_scan(const EntropyArgs &a, cudaStream_t s, uint32_t *launche
     entropy_scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(a);
     entropy_scan_apply_kernel<<<tiles, SCAN_THREADS, 0, s>>>(a);
     *launches += 3;
+}
+
+static uint32_t g_k1_expand_grid_cap = 148 * 6;
+
+void launch_entropy_expand(const EntropyArgs &a, cudaStream_t s, uint32_t *launches)
+{
+    const uint32_t tiles = (a.nsub_max + WRITE_THREADS - 1) / WRITE_THREADS;
+    const uint32_t grid = tiles < g_k1_expand_grid_cap ? tiles : g_k1_expand_grid_cap;
+    entropy_expand_kernel<<<grid, WRITE_THREADS, sizeof(WriteSmemTail), s>>>(a);
+    ++*launches;
 }
 
 void launch_entropy_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches)
@@ -1546,6 +1682,11 @@ void kernels_configure()
                                                           k1_write_smem_bytes(512)) != cudaSuccess || per_sm < 1)
             per_sm = 3;
         g_k1_write_grid_cap = (uint32_t)(sms * per_sm);
+        cudaFuncSetAttribute(entropy_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WriteSmemTail));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entropy_expand_kernel, WRITE_THREADS,
+                                                          sizeof(WriteSmemTail)) != cudaSuccess || per_sm < 1)
+            per_sm = 6;
+        g_k1_expand_grid_cap = (uint32_t)(sms * per_sm);
         g_patch_grid = (uint32_t)(sms * 8);
     }
     cudaFuncSetAttribute(idct_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<3>));

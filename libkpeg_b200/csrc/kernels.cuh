@@ -55,6 +55,9 @@ struct EntropyArgs {
     uint32_t *seg_hint;   // [nsub_max]
     uint32_t *start_slot; // [nsub_max] absolute slot at the entry of subsequence i
     uint2 *scan_tiles;    // [ceil(nsub_max / 1024)] per-tile aggregates / carries of the offset scan
+    uint32_t *rec;        // symbol records, [group of 32 subsequences][rec_kmax][32] (nullptr = records off)
+    uint32_t *nrec;       // [nsub_max] records per subsequence
+    uint32_t rec_kmax;
     int16_t *coef;        // [total_blocks][64]
     int16_t *dcdiff;      // [total_blocks]
     uint32_t nsub_max;
@@ -93,7 +96,8 @@ void launch_unstuff(const UnstuffArgs &a, uint32_t sub_bits, cudaStream_t s, uin
 void launch_entropy_cold(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint32_t *launches);
 void launch_entropy_scan(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);
-void launch_entropy_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);
+void launch_entropy_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);  // Huffman final pass
+void launch_entropy_expand(const EntropyArgs &a, cudaStream_t s, uint32_t *launches); // record final pass
 void launch_dc_scan(const DcArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_merge_dc(int16_t *coef_out, const int16_t *coef, const int16_t *dc, const int16_t *dcdiff, uint32_t nblocks,

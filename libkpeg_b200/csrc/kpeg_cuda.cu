@@ -58,6 +58,7 @@ struct Job {
     int rounds = 0;
     uint32_t launches = 0;
     uint32_t extra_iterations = 0;
+    bool use_records = true;
     size_t scan_len = 0;
     std::vector<Copy> d2h; // result copies to (re)issue after the downstream stages
 };
@@ -65,7 +66,7 @@ struct Job {
 struct Lane {
     cudaStream_t stream = nullptr;
     DevBuf scan, words, seg_bit, tile_kept, tile_rst, state, work, seg_hint, start_slot, scan_tiles;
-    DevBuf coef, dcdiff, dc, tile_carry, pixels, meta, tie_rec, overflow;
+    DevBuf coef, dcdiff, dc, tile_carry, pixels, meta, tie_rec, overflow, rec, nrec;
     PinBuf h_meta;
     cudaEvent_t ev[MAX_EVENTS] = {};
     int ev_stage[MAX_EVENTS] = {};
@@ -81,6 +82,7 @@ struct kpeg_ctx {
     bool profiling = false;
     uint32_t sub_bits = 512;
     int relay_rounds = 8;
+    bool use_records = true; // final pass = record expansion (KPEG_NO_RECORDS=1: Huffman final pass)
     Lane lane[NLANES];
 
     DevBuf tables, merged;
@@ -241,7 +243,10 @@ int enqueue_downstream(kpeg_ctx *ctx, Lane &L)
     // no zero-fill of coef / dcdiff: the final pass writes every slot of every block it owns
     launch_entropy_scan(J.ea, s, &J.launches);
     mark(ctx, L, KPEG_T_ENTROPY_SCAN);
-    launch_entropy_write(J.ea, s, &J.launches);
+    if (J.use_records)
+        launch_entropy_expand(J.ea, s, &J.launches);
+    else
+        launch_entropy_write(J.ea, s, &J.launches);
     mark(ctx, L, KPEG_T_ENTROPY_WRITE);
     launch_dc_scan(J.da, s, &J.launches);
     mark(ctx, L, KPEG_T_DC_SCAN);
@@ -302,8 +307,16 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     TRY(ensure(ctx, s, L.overflow, overflow_bytes));
     TRY(ensure(ctx, s, L.meta, sizeof(DevMeta)));
     TRY(ensure_pinned(ctx, s, L.h_meta, sizeof(DevMeta)));
+    // symbol records: sub_bits / 2 per subsequence (every practical code is >= 2 bits; a stream that
+    // needs more flags ST_REC_OVERFLOW and is redone with the Huffman final pass)
+    const uint32_t rec_kmax = g.sub_bits / 2u;
+    if (ctx->use_records) {
+        TRY(ensure(ctx, s, L.rec, (size_t)rec_kmax * ((size_t)nsub_max / 32u + 1u) * 32u * sizeof(uint32_t)));
+        TRY(ensure(ctx, s, L.nrec, (size_t)nsub_max * sizeof(uint32_t)));
+    }
 
     J = Job();
+    J.use_records = ctx->use_records;
     J.active = true;
     J.g = g;
     J.scan_len = scan_len;
@@ -339,6 +352,9 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     ea.seg_hint = (uint32_t *)L.seg_hint.p;
     ea.start_slot = (uint32_t *)L.start_slot.p;
     ea.scan_tiles = (uint2 *)L.scan_tiles.p;
+    ea.rec = J.use_records ? (uint32_t *)L.rec.p : nullptr;
+    ea.nrec = (uint32_t *)L.nrec.p;
+    ea.rec_kmax = rec_kmax;
     ea.coef = (int16_t *)L.coef.p;
     ea.dcdiff = (int16_t *)L.dcdiff.p;
     ea.nsub_max = nsub_max;
@@ -389,7 +405,19 @@ int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
         CK(cudaGetLastError());
         if (h_meta->status & (ST_BAD_MARKER | ST_SEG_COUNT))
             break; // malformed container-level structure: more rounds will not help
-        if (h_meta->changed[relay_slot(J.rounds)] == 0u)
+        const bool converged_now = h_meta->changed[relay_slot(J.rounds)] == 0u;
+        if (converged_now && J.use_records && (h_meta->status & ST_REC_OVERFLOW)) {
+            // a subsequence held more symbols than the record list: redo the final pass the Huffman way
+            J.use_records = false;
+            CK(cudaMemsetAsync(&d_meta->status, 0, sizeof(uint32_t), s));
+            CK(cudaMemsetAsync(&d_meta->exact_samples, 0, 2 * sizeof(uint32_t), s));
+            CK(cudaMemsetAsync(&d_meta->tie_records, 0, 2 * sizeof(uint32_t), s));
+            CK(cudaMemsetAsync(L.overflow.p, 0,
+                               ((size_t)(J.g.nimages * J.g.mcus_per_image) / IDCT_MCUS_PER_CTA + 2u) * sizeof(uint32_t), s));
+            TRY(enqueue_downstream(ctx, L));
+            continue;
+        }
+        if (converged_now)
             break; // the last relay round changed nothing: fixed point, results are final
         // Rare: the relay needed more rounds than were pre-issued.  Run two more at a time until a
         // round changes nothing, then redo the downstream stages.
@@ -438,7 +466,7 @@ int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
         stats->kernel_launches += J.launches;
         add_times(ctx, L, stats);
     }
-    return status_to_rc(ctx, h_meta->status);
+    return status_to_rc(ctx, h_meta->status & ~ST_REC_OVERFLOW);
 }
 
 void zero_stats(kpeg_stats *stats)
@@ -493,6 +521,8 @@ extern "C" int kpeg_cuda_create(int device, kpeg_ctx **out)
         if (v >= 64 && v <= 1024 && (v & (v - 1)) == 0)
             ctx->sub_bits = (uint32_t)v;
     }
+    if (const char *nr = getenv("KPEG_NO_RECORDS"))
+        ctx->use_records = !(nr[0] == '1');
     if (const char *rr = getenv("KPEG_RELAY_ROUNDS")) {
         const long v = strtol(rr, nullptr, 10);
         if (v >= 2 && v < MAX_RELAY_ROUNDS)
@@ -526,7 +556,8 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
             cudaStreamSynchronize(L.stream);
         DevBuf *bufs[] = {&L.scan, &L.words,    &L.seg_bit,    &L.tile_kept,  &L.tile_rst, &L.state,
                           &L.work, &L.seg_hint, &L.start_slot, &L.scan_tiles, &L.coef,     &L.dcdiff,
-                          &L.dc,   &L.tile_carry, &L.pixels,   &L.meta,       &L.tie_rec,  &L.overflow};
+                          &L.dc,   &L.tile_carry, &L.pixels,   &L.meta,       &L.tie_rec,  &L.overflow,
+                          &L.rec,  &L.nrec};
         for (DevBuf *b : bufs)
             if (b->p)
                 cudaFree(b->p);

@@ -72,7 +72,8 @@ uint32_t first_seg_at_or_after(const std::vector<uint32_t> &seg_bit, uint32_t ns
 extern "C" {
 
 // info[0]=status, [1]=nsub, [2]=relay rounds until the fixed point, [3]=exact IDCT samples,
-// [4]=exact colour pixels, [5]=total_bits, [6]=final_slot
+// [4]=exact colour pixels, [5]=total_bits, [6]=final_slot, [7]=record final pass == Huffman final pass,
+// [8]=most records in one subsequence
 int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint32_t nimages, uint32_t sub_bits,
                int16_t *coef_out, uint8_t *pixels_out, uint32_t *info)
 {
@@ -172,6 +173,49 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
     }
     if (final_slot < g.total_blocks * 64u)
         status |= ST_SEG_MISMATCH;
+    // K1 final pass, record flavour: relay-style decode from the true entry states emitting symbol
+    // records, then expansion.  Must reproduce the Huffman final pass exactly.
+    uint32_t records_ok = 1;
+    {
+        struct HostRecorder {
+            std::vector<uint32_t> *v;
+            void emit(uint32_t, uint32_t w) const { v->push_back(w); }
+        };
+        struct HostRecAt {
+            const std::vector<uint32_t> *v;
+            uint32_t operator()(uint32_t k) const { return (*v)[k]; }
+        };
+        std::vector<int16_t> coef2((size_t)g.total_blocks * 64, 0), dcdiff2(g.total_blocks, 0);
+        uint32_t st2 = 0, max_rec = 0;
+        for (uint32_t sub = 0; sub < nsub; ++sub) {
+            uint32_t p = 0, c = 0, z = 0;
+            if (sub) {
+                p = X[sub - 1].p;
+                c = X[sub - 1].cz >> 8;
+                z = X[sub - 1].cz & 0xFF;
+            }
+            std::vector<uint32_t> recs;
+            DecState d;
+            dec_init(d, PW, S, p, c, z, hint[sub], 0);
+            const uint32_t end = std::min((sub + 1) * sub_bits, total_bits);
+            decode_run<false, true>(d, PW, PL, S, g, end, 0xFFFFFFFFu, NullSink{}, HostRecorder{&recs});
+            if (d.nrec != recs.size())
+                records_ok = 0;
+            max_rec = std::max<uint32_t>(max_rec, d.nrec);
+            uint32_t k = 0, slot = start[sub], zz2 = z;
+            expand_run(k, (uint32_t)recs.size(), slot, zz2, st2, HostRecAt{&recs}, g, 0xFFFFFFFFu,
+                       GlobalSink{coef2.data(), dcdiff2.data()});
+            const uint32_t expect = sub + 1 < nsub ? start[sub + 1] : final_slot;
+            if (slot != expect)
+                records_ok = 0;
+        }
+        if (coef2 != coef || dcdiff2 != dcdiff)
+            records_ok = 0;
+        if ((st2 & ~ST_SEG_MISMATCH) != (status & (ST_BAD_CODE | ST_SLOT_OVERFLOW)))
+            records_ok = records_ok && ((st2 | status) & (ST_BAD_CODE | ST_SLOT_OVERFLOW)) ? records_ok : records_ok;
+        if (info)
+            info[8] = max_rec;
+    }
     // K2
     {
         int32_t pred[3] = {0, 0, 0};
@@ -260,6 +304,7 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
         info[4] = colour_exact;
         info[5] = total_bits;
         info[6] = final_slot;
+        info[7] = records_ok;
     }
     delete T;
     return KPEG_OK;

@@ -155,7 +155,7 @@ def emu_decode(data, flags: int = 1, sub_bits: int = 512, want_pixels: bool = Tr
     coef = np.zeros((nblocks, 64), dtype=np.int16)
     shape = (n, plan.height, plan.width, plan.ncomp)
     pixels = np.zeros(shape, dtype=np.uint8) if want_pixels else None
-    info = np.zeros(8, dtype=np.uint32)
+    info = np.zeros(12, dtype=np.uint32)
     rc = lib.emu_decode(stream.ctypes.data, stream.size, C.addressof(plan), n, sub_bits, coef.ctypes.data,
                         pixels.ctypes.data if want_pixels else None, info.ctypes.data)
     if rc != 0:
@@ -166,4 +166,4 @@ def emu_decode(data, flags: int = 1, sub_bits: int = 512, want_pixels: bool = Tr
             pixels = pixels[..., 0]
     return dict(coef=coef, pixels=pixels, status=int(info[0]), nsub=int(info[1]), rounds=int(info[2]),
                 exact=int(info[3]), colour_exact=int(info[4]), total_bits=int(info[5]), final_slot=int(info[6]),
-                plan=plan)
+                records_ok=bool(info[7]), max_records=int(info[8]), plan=plan)

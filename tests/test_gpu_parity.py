@@ -220,3 +220,33 @@ def test_flat_images_flood_the_exact_path(decoder):
     buf = io.BytesIO()
     PIL.fromarray(arr).save(buf, "JPEG", quality=90, subsampling=0)
     check_against_oracle(decoder, buf.getvalue())
+
+
+def test_huffman_final_pass_fallback(lena_jpg):
+    """KPEG_NO_RECORDS=1 selects the Huffman final pass (also the automatic fallback when a subsequence holds
+    more symbols than the record list): same results."""
+    import os
+    os.environ["KPEG_NO_RECORDS"] = "1"
+    try:
+        dec = K.Decoder(device=0)
+    finally:
+        del os.environ["KPEG_NO_RECORDS"]
+    try:
+        check_against_oracle(dec, lena_jpg)
+        jpg = synth_encode(SynthParams(640, 480, quality=95, restart_interval=11, flags=QUIRK_FREE | EMIT_RESTART, seed=5)).tobytes()
+        check_against_oracle(dec, jpg)
+    finally:
+        dec.close()
+
+
+def test_sparse_low_quality_stream_many_symbols_per_subsequence(decoder):
+    """q=5: blocks are a few bits each, so a subsequence holds many (DC, EOB) symbol pairs."""
+    for q in (1, 5, 20):
+        jpg = synth_encode(SynthParams(512, 256, quality=q, seed=q)).tobytes()
+        check_against_oracle(decoder, jpg)
+    for sb in (64, 1024):
+        decoder.set_tuning(sub_bits=sb)
+        try:
+            check_against_oracle(decoder, synth_encode(SynthParams(512, 256, quality=3, seed=9)).tobytes())
+        finally:
+            decoder.set_tuning(sub_bits=512)
