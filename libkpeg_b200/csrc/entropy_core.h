@@ -114,14 +114,17 @@ struct GlobalSink {
 // The relay passes decode every subsequence from (what converges to) its true entry state anyway;
 // they also write down what they decoded, one 32-bit record per symbol, so that the final pass is a
 // cheap, load-latency-tolerant EXPANSION of records instead of a third serial Huffman decode:
-//   bits 0-15 value (int16), bits 16-22 slot advance, bit 23 "carries a value",
-//   bits 24-31 type: 0 symbol, 1 symbol decoded from an invalid bit pattern, 0xFF boundary jump
-//   (bits 0-23 = index of the segment that starts at the boundary).
-constexpr uint32_t REC_JUMP = 0xFF000000u;
+//   bits 0-15 the raw magnitude bits as they sit in the stream (EXTEND is applied by the expander),
+//   bits 16-26 the table entry's (magnitude bits | slot advance << 4), bit 27 "invalid bit pattern",
+//   bits 28-31 type: 0 symbol, 0xF boundary jump (bits 0-23 = index of the segment that starts there).
+constexpr uint32_t REC_JUMP = 0xF0000000u;
 
-KPEG_HD uint32_t pack_record(uint32_t adv, bool has_value, int32_t val, bool bad)
+// e = table entry (total bits | size << 5 | adv << 9), raw = the `size` magnitude bits (garbage when size == 0)
+KPEG_HD uint32_t pack_record(uint32_t e, uint32_t raw)
 {
-    return ((uint32_t)val & 0xFFFFu) | (adv << 16) | (has_value ? (1u << 23) : 0u) | (bad ? (1u << 24) : 0u);
+    const uint32_t T = e & 31u, size = (e >> 5) & 15u, len = T - size;
+    const uint32_t bad = (len >> 4) & len & 1u; // code "length" 17: no code matched
+    return (raw & 0xFFFFu) | ((e >> 5) << 16) | (bad << 27);
 }
 
 struct NoRecorder {
@@ -243,8 +246,7 @@ KPEG_HD void decode_run(DecState &d, const Words &W, const Luts &L, const Stream
         if (EMIT) {
             const uint32_t size = (e >> 5) & 15u;
             const uint32_t raw = (win << (T - size)) >> ((32u - size) & 31u);
-            const int32_t val = extend_value(raw, size | (size == 0u ? 1u : 0u));
-            rec.emit(nrec, pack_record(adv, size != 0u, val, T - size > 16u));
+            rec.emit(nrec, pack_record(e, raw));
             ++nrec;
         }
         p += T;
@@ -304,18 +306,19 @@ KPEG_HD void expand_run(uint32_t &k, uint32_t nrec, uint32_t &slot, uint32_t &z,
             if (k < nrec && slot < slot_limit) { // a record left unused here is fetched again by the next call
                 const uint32_t r = rr[j];
                 ++k;
-                if ((r >> 24) == 0xFFu) {
+                if ((r >> 28) == 0xFu) {
                     const uint32_t seg = r & 0xFFFFFFu;
                     if (slot != seg_slot_base(g, seg) && (seg < g.nseg || slot < total_slots))
                         st |= ST_SEG_MISMATCH;
                     slot = seg_slot_base(g, seg);
                     z = 0;
                 } else {
-                    const uint32_t adv = (r >> 16) & 127u;
-                    const bool has_value = (r >> 23) & 1u;
-                    st |= (r >> 24) & 1u; // ST_BAD_CODE
+                    const uint32_t size = (r >> 16) & 15u, adv = (r >> 20) & 127u;
+                    const bool has_value = size != 0u;
+                    st |= (r >> 27) & 1u; // ST_BAD_CODE
                     st |= (has_value && z + adv > 64u) ? ST_SLOT_OVERFLOW : 0u;
-                    sink.put(z == 0u, slot, adv, has_value && slot + adv <= total_slots, (int32_t)(int16_t)(r & 0xFFFFu));
+                    const int32_t val = extend_value(r & 0xFFFFu, size | (size == 0u ? 1u : 0u));
+                    sink.put(z == 0u, slot, adv, has_value && slot + adv <= total_slots, val);
                     uint32_t zn = z + adv;
                     zn = zn > 64u ? 64u : zn;
                     slot += zn - z;

@@ -117,6 +117,10 @@ __global__ void __launch_bounds__(1024) unstuff_scan_kernel(UnstuffArgs a, uint3
     const uint32_t total_bits = total_kept * 8u;
     for (uint32_t k = threadIdx.x; k < a.nseg + 2u; k += 1024)
         a.seg_bit[k] = k == 0u ? 0u : (k <= a.nseg ? total_bits : 0xFFFFFFFFu);
+    // the stream buffer is not zero-filled: define the last (partial) word and the slack the bit window
+    // may look at; the compaction kernel, which runs after this one, stores the real tail bytes
+    if (threadIdx.x < 12u)
+        reinterpret_cast<uint32_t *>(a.words)[(total_kept >> 2) + threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
         a.meta->total_kept = total_kept;
         a.meta->total_rst = total_rst;

@@ -283,7 +283,7 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     const uint32_t nsub_max = (uint32_t)(((uint64_t)S * 8u + g.sub_bits - 1u) / g.sub_bits) + 1u;
     const uint32_t total_mcus = g.nimages * g.mcus_per_image;
     const uint32_t dc_tiles = (total_mcus + DC_TILE - 1) / DC_TILE;
-    const size_t words_bytes = ((size_t)S + 3u) / 4u * 4u + 32u;
+    const size_t words_bytes = ((size_t)S + 3u) / 4u * 4u + 64u;
     const size_t coef_bytes = (size_t)g.total_blocks * 128u;
     // tie records: room for 1/8 of all pixels (typical: ~1 %); beyond that strips are redone wholesale
     const uint64_t npix_job = (uint64_t)g.nimages * g.width * g.height;
@@ -324,7 +324,6 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     DevMeta *d_meta = (DevMeta *)L.meta.p;
 
     CK(cudaMemsetAsync(d_meta, 0, sizeof(DevMeta), s));
-    CK(cudaMemsetAsync(L.words.p, 0, words_bytes, s));
     CK(cudaMemsetAsync(L.overflow.p, 0, overflow_bytes, s));
     mark(ctx, L, KPEG_T_MEMSET);
 
