@@ -67,12 +67,14 @@ enum {
     KPEG_T_MEMSET,         /* zero-fill of bookkeeping, bit stream tail and coefficient buffer            */
     KPEG_T_UNSTUFF,        /* K0: unstuff_count + unstuff_scan + unstuff_write                            */
     KPEG_T_ENTROPY_COLD,   /* K1: speculative cold decode of every subsequence                            */
-    KPEG_T_ENTROPY_RELAY,  /* K1: relay rounds up to the fixed point                                      */
+    KPEG_T_ENTROPY_RELAY,  /* K1: first relay round (every subsequence, emits symbol records)             */
     KPEG_T_ENTROPY_SCAN,   /* K1: segmented offset scan                                                   */
-    KPEG_T_ENTROPY_WRITE,  /* K1: final decode writing coefficients                                       */
+    KPEG_T_ENTROPY_WRITE,  /* K1: final pass (record expansion, or Huffman decode) writing coefficients   */
     KPEG_T_DC_SCAN,        /* K2                                                                          */
     KPEG_T_IDCT,           /* K3: fused dequant + IDCT + colour + store                                   */
     KPEG_T_D2H,            /* device -> host copy of the pixels (host-pointer entry points only)          */
+    KPEG_T_RELAY_SPARSE,   /* K1: later relay rounds (work list only) up to the fixed point               */
+    KPEG_T_IDCT_PATCH,     /* K3: exact (reference-order) re-evaluation of the pixels inside the tie band  */
     KPEG_T_COUNT
 };
 
@@ -165,6 +167,10 @@ size_t kpeg_batch_packed_size(int n, const size_t *scan_lens);
 int kpeg_batch_pack(int n, const uint8_t *const *scans, const size_t *scan_lens, uint8_t *dst, size_t cap);
 int kpeg_cuda_decode_batch_packed_device(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *d_packed,
                                          size_t packed_len, uint8_t *d_pixels_out, kpeg_stats *stats);
+/* Same, given the offsets of the n scans inside the packed stream (packed_offsets[n] = its length): the
+ * two halves of the batch run as concurrent jobs on the context's two lanes. */
+int kpeg_cuda_decode_batch_packed_device_split(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *d_packed,
+                                               const uint64_t *packed_offsets, uint8_t *d_pixels_out, kpeg_stats *stats);
 
 /* Whole-file convenience used by the JPEGDecoder drop-in: parse + decode.  pixels_out must hold
  * width*height*ncomp bytes (query with kpeg_parse_jfif first) -- cap is checked. */

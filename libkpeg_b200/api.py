@@ -53,12 +53,12 @@ class Stats(C.Structure):
         ("scan_bytes", C.c_uint64), ("unstuffed_bytes", C.c_uint64),
         ("segments", C.c_uint32), ("subsequences", C.c_uint32), ("sync_rounds", C.c_uint32),
         ("exact_samples", C.c_uint32),
-        ("ms", C.c_float * 10), ("ms_total", C.c_float),
+        ("ms", C.c_float * 12), ("ms_total", C.c_float),
         ("kernel_launches", C.c_uint32),
     ]
 
     STAGES = ("h2d", "memset", "unstuff", "entropy_cold", "entropy_relay", "entropy_scan", "entropy_write", "dc_scan",
-              "idct", "d2h")
+              "idct", "d2h", "relay_sparse", "idct_patch")
 
     def stage_ms(self) -> dict:
         return {name: float(self.ms[i]) for i, name in enumerate(self.STAGES)}
@@ -97,6 +97,8 @@ SYMBOLS = {
     "kpeg_batch_pack": (C.c_int, [C.c_int, C.POINTER(_vp), C.POINTER(C.c_size_t), _vp, C.c_size_t]),
     "kpeg_cuda_decode_batch_packed_device": (C.c_int, [_vp, C.POINTER(Plan), C.c_int, _vp, C.c_size_t, _vp,
                                                       C.POINTER(Stats)]),
+    "kpeg_cuda_decode_batch_packed_device_split": (C.c_int, [_vp, C.POINTER(Plan), C.c_int, _vp, C.POINTER(C.c_uint64), _vp,
+                                                            C.POINTER(Stats)]),
     "kpeg_cuda_decode_file": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, C.c_size_t, C.POINTER(Plan),
                                        C.POINTER(Stats)]),
     "kpeg_cuda_read_coefficients": (C.c_int, [_vp, _vp, C.c_size_t]),
@@ -280,10 +282,24 @@ class Decoder:
                                                C.byref(self.last_stats))
         self._check(rc, "kpeg_cuda_decode_device")
 
+    def decode_batch_packed_device_split(self, plan: Plan, n: int, d_packed: int, offsets: np.ndarray, d_out: int):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        rc = self._lib.kpeg_cuda_decode_batch_packed_device_split(
+            self._h, C.byref(plan), n, d_packed, offsets.ctypes.data_as(C.POINTER(C.c_uint64)), d_out,
+            C.byref(self.last_stats))
+        self._check(rc, "kpeg_cuda_decode_batch_packed_device_split")
+
     def decode_batch_packed_device(self, plan: Plan, n: int, d_packed: int, packed_len: int, d_out: int):
         rc = self._lib.kpeg_cuda_decode_batch_packed_device(self._h, C.byref(plan), n, d_packed, packed_len, d_out,
                                                             C.byref(self.last_stats))
         self._check(rc, "kpeg_cuda_decode_batch_packed_device")
+
+
+def packed_offsets(scans: list[np.ndarray]) -> np.ndarray:
+    """Offsets of the scans inside the packed batch stream (each scan is followed by a 2-byte RSTn)."""
+    off = np.zeros(len(scans) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([int(s.size) + 2 for s in scans])
+    return off
 
 
 def pack_batch(scans: list[np.ndarray]) -> np.ndarray:

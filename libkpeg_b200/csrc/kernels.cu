@@ -405,6 +405,8 @@ __device__ __forceinline__ SubState relay_decode(const EntropyArgs &a, const Wor
     return dec_exit_state(d);
 }
 
+__device__ __forceinline__ int relay_slot_dev(int r) { return r < MAX_RELAY_ROUNDS ? r : 2 + ((r - 2) % (MAX_RELAY_ROUNDS - 2)); }
+
 // Relay: X[i] = decode(i, X[i-1]).  Round 1 visits every subsequence (tiles, like the cold pass) and
 // appends i+1 to the work list whenever X[i] changed; later rounds visit only the work list of the
 // round before (a few percent of the subsequences, scattered, so they read the stream from global
@@ -513,6 +515,68 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_sparse_kernel(E
     const uint32_t end = min((sub + 1u) << (wlog + 5u), total_bits);
     const SubState out = relay_decode(a, W, L, S, sub, end, inraw.x, inraw.z);
     relay_publish(a, sub, out, nsub, a.worklist[round & 1], &a.meta->changed[slot_cur]);
+}
+
+// The later relay rounds as one launch.  Each round touches only a work list that shrinks quickly
+// (5 %, 0.5 %, ... of the subsequences) but costs the full latency of one serial subsequence decode;
+// as separate launches every round also paid launch latency, table staging and a tail.  Here a small
+// cooperative grid stages the tables once and loops: process the list, grid barrier, next list.
+__device__ __forceinline__ void grid_barrier(uint32_t *counter, uint32_t &generation)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++generation;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const uint32_t target = generation * gridDim.x;
+        while (*reinterpret_cast<volatile uint32_t *>(counter) < target)
+            __nanosleep(64);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_loop_kernel(EntropyArgs a, int first, int last,
+                                                                             uint32_t wlog)
+{
+    extern __shared__ __align__(16) unsigned char k1_raw[];
+    K1Smem &sm = *reinterpret_cast<K1Smem *>(k1_raw);
+    const uint32_t nsub = a.meta->nsub, total_bits = a.meta->total_bits;
+    k1_stage_tables(sm, a);
+    __syncthreads();
+    const SmemLuts L = k1_luts(sm, a);
+    StreamView S{a.seg_bit, total_bits};
+    const uint32_t stride = (1u << wlog) + 5u;
+    uint32_t *mine = sm.words + threadIdx.x * stride;
+    PrivateWords W;
+    W.addr = (uint32_t)__cvta_generic_to_shared(mine);
+    const uint32_t total_words = ((total_bits + 31u) >> 5) + 4u;
+    uint32_t generation = 0;
+    int round = first;
+    for (; round <= last; ++round) {
+        const uint32_t count = *reinterpret_cast<volatile uint32_t *>(&a.meta->changed[relay_slot_dev(round - 1)]);
+        if (count == 0u)
+            break; // fixed point (uniform across the grid: read after the barrier)
+        const uint32_t *list_in = a.worklist[(round - 1) & 1];
+        uint32_t *list_out = a.worklist[round & 1];
+        uint32_t *count_out = &a.meta->changed[relay_slot_dev(round)];
+        for (uint32_t w = blockIdx.x * ENTROPY_THREADS + threadIdx.x; w < count; w += gridDim.x * ENTROPY_THREADS) {
+            const uint32_t sub = __ldcg(list_in + w);
+            if (sub >= nsub)
+                continue;
+            const uint4 inraw = __ldcg(reinterpret_cast<const uint4 *>(&a.state[sub - 1]));
+            const uint32_t j0 = inraw.x >> 5;
+            for (uint32_t k = 0; k < stride - 1u; ++k)
+                mine[k] = j0 + k < total_words ? __ldg(a.words + j0 + k) : 0u;
+            W.gw0 = j0;
+            const uint32_t end = min((sub + 1u) << (wlog + 5u), total_bits);
+            const SubState out = relay_decode(a, W, L, S, sub, end, inraw.x, inraw.z);
+            relay_publish(a, sub, out, nsub, list_out, count_out);
+        }
+        grid_barrier(&a.meta->grid_bar, generation);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        a.meta->relay_rounds = (uint32_t)(round <= last ? round - 1 : last);
 }
 
 // Segmented exclusive scan of the slot counts: start_slot[i] = absolute coefficient slot at the
@@ -933,6 +997,18 @@ void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint3
         entropy_relay_sparse_kernel<<<grid, ENTROPY_THREADS, k1_sparse_smem_bytes(a.g.sub_bits), s>>>(
             a, round, relay_slot(round - 1), relay_slot(round), wlog);
     }
+    ++*launches;
+}
+
+static uint32_t g_relay_loop_grid = 148;
+
+void launch_entropy_relay_loop(const EntropyArgs &a, int first, int last, cudaStream_t s, uint32_t *launches)
+{
+    uint32_t wlog = ilog2(a.g.sub_bits / 32u);
+    EntropyArgs args = a;
+    void *params[] = {&args, &first, &last, &wlog};
+    cudaLaunchCooperativeKernel((const void *)entropy_relay_loop_kernel, dim3(g_relay_loop_grid), dim3(ENTROPY_THREADS), params,
+                                k1_sparse_smem_bytes(a.g.sub_bits), s);
     ++*launches;
 }
 
@@ -1692,6 +1768,9 @@ void kernels_configure()
             per_sm = 6;
         g_k1_expand_grid_cap = (uint32_t)(sms * per_sm);
         g_patch_grid = (uint32_t)(sms * 8);
+        cudaFuncSetAttribute(entropy_relay_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)k1_sparse_smem_bytes(1024));
+        g_relay_loop_grid = (uint32_t)sms * 2u; // co-resident by a wide margin (cooperative launch checks it)
     }
     cudaFuncSetAttribute(idct_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<3>));
     cudaFuncSetAttribute(idct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<1>));
@@ -1701,14 +1780,20 @@ void launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches)
 {
     const uint32_t total_mcus = a.g.nimages * a.g.mcus_per_image;
     const uint32_t grid = (total_mcus + IDCT_MCUS_PER_CTA - 1) / IDCT_MCUS_PER_CTA;
-    if (a.g.ncomp == 3) {
+    if (a.g.ncomp == 3)
         idct_kernel<3><<<grid, 3 * IDCT_MCUS_PER_CTA, sizeof(IdctSmem<3>), s>>>(a);
-        idct_patch_kernel<3><<<g_patch_grid, 128, 0, s>>>(a);
-    } else {
+    else
         idct_kernel<1><<<grid, IDCT_MCUS_PER_CTA, sizeof(IdctSmem<1>), s>>>(a);
+    ++*launches;
+}
+
+void launch_idct_patch(const IdctArgs &a, cudaStream_t s, uint32_t *launches)
+{
+    if (a.g.ncomp == 3)
+        idct_patch_kernel<3><<<g_patch_grid, 128, 0, s>>>(a);
+    else
         idct_patch_kernel<1><<<g_patch_grid, 128, 0, s>>>(a);
-    }
-    *launches += 2;
+    ++*launches;
 }
 
 // =================================================================================================

@@ -27,6 +27,8 @@ struct DevMeta {
     uint32_t final_slot;   // absolute slot the last subsequence ended on
     uint32_t tie_records;  // pixels queued for the exact (reference-order) re-evaluation
     uint32_t tie_inline;   // pixels resolved inside K3 because the record buffer was full
+    uint32_t relay_rounds; // last relay round that ran (device-side round loop)
+    uint32_t grid_bar;     // arrival counter of the relay loop's grid barrier
     uint32_t changed[MAX_RELAY_ROUNDS];
 };
 
@@ -95,11 +97,15 @@ void kernels_configure(); // per-device function attributes (call once after cud
 void launch_unstuff(const UnstuffArgs &a, uint32_t sub_bits, cudaStream_t s, uint32_t *launches);
 void launch_entropy_cold(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint32_t *launches);
+// rounds first..last (first >= 2) in ONE cooperative launch: a device-side loop with a grid barrier
+// between rounds, stopping early at the fixed point; DevMeta::relay_rounds = last round that ran
+void launch_entropy_relay_loop(const EntropyArgs &a, int first, int last, cudaStream_t s, uint32_t *launches);
 void launch_entropy_scan(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_entropy_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);  // Huffman final pass
 void launch_entropy_expand(const EntropyArgs &a, cudaStream_t s, uint32_t *launches); // record final pass
 void launch_dc_scan(const DcArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches);
+void launch_idct_patch(const IdctArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_merge_dc(int16_t *coef_out, const int16_t *coef, const int16_t *dc, const int16_t *dcdiff, uint32_t nblocks,
                      uint32_t flags, cudaStream_t s);
 

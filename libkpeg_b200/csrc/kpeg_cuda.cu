@@ -252,6 +252,8 @@ int enqueue_downstream(kpeg_ctx *ctx, Lane &L)
     mark(ctx, L, KPEG_T_DC_SCAN);
     launch_idct(J.ia, s, &J.launches);
     mark(ctx, L, KPEG_T_IDCT);
+    launch_idct_patch(J.ia, s, &J.launches);
+    mark(ctx, L, KPEG_T_IDCT_PATCH);
     for (const Copy &c : J.d2h)
         CK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, s));
     if (!J.d2h.empty())
@@ -381,9 +383,13 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     launch_entropy_cold(ea, s, &J.launches);
     mark(ctx, L, KPEG_T_ENTROPY_COLD);
     J.rounds = ctx->relay_rounds < 2 ? 2 : (ctx->relay_rounds > MAX_RELAY_ROUNDS - 1 ? MAX_RELAY_ROUNDS - 1 : ctx->relay_rounds);
-    for (int r = 1; r <= J.rounds; ++r)
-        launch_entropy_relay(ea, r, s, &J.launches);
+    launch_entropy_relay(ea, 1, s, &J.launches);
     mark(ctx, L, KPEG_T_ENTROPY_RELAY);
+    // rounds 2.. in one cooperative launch (device-side loop, stops at the fixed point); the cap only
+    // bounds the loop -- a stream that needs more is finished by job_finish
+    J.rounds = MAX_RELAY_ROUNDS - 2;
+    launch_entropy_relay_loop(ea, 2, J.rounds, s, &J.launches);
+    mark(ctx, L, KPEG_T_RELAY_SPARSE);
     return enqueue_downstream(ctx, L);
 }
 
@@ -404,6 +410,8 @@ int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
         CK(cudaGetLastError());
         if (h_meta->status & (ST_BAD_MARKER | ST_SEG_COUNT))
             break; // malformed container-level structure: more rounds will not help
+        if (J.extra_iterations == 0u)
+            J.rounds = (int)std::max<uint32_t>(h_meta->relay_rounds, 1u); // last round the device loop ran
         const bool converged_now = h_meta->changed[relay_slot(J.rounds)] == 0u;
         if (converged_now && J.use_records && (h_meta->status & ST_REC_OVERFLOW)) {
             // a subsequence held more symbols than the record list: redo the final pass the Huffman way
@@ -429,7 +437,7 @@ int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
                 CK(cudaMemsetAsync(&d_meta->changed[relay_slot(J.rounds)], 0, sizeof(uint32_t), s));
                 launch_entropy_relay(J.ea, J.rounds, s, &J.launches);
             }
-            mark(ctx, L, KPEG_T_ENTROPY_RELAY);
+            mark(ctx, L, KPEG_T_RELAY_SPARSE);
             CK(cudaMemcpyAsync(h_meta, d_meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
             converged = h_meta->changed[relay_slot(J.rounds)] == 0u;
@@ -734,6 +742,39 @@ extern "C" int kpeg_cuda_decode_batch_packed_device(kpeg_ctx *ctx, const kpeg_pl
     mark(ctx, ctx->lane[0], -1);
     TRY(job_enqueue(ctx, 0, plan, d_packed, packed_len, (uint32_t)n, d_pixels_out, {}));
     return job_finish(ctx, 0, stats);
+}
+
+// Same, with the offsets of the n scans inside the packed stream (packed_offsets[n] = its length): the
+// batch is decoded as two concurrent jobs, one per lane, so the latency-bound phases of one half
+// (late relay rounds, record expansion) overlap the issue-bound phases of the other.
+extern "C" int kpeg_cuda_decode_batch_packed_device_split(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *d_packed,
+                                                          const uint64_t *packed_offsets, uint8_t *d_pixels_out,
+                                                          kpeg_stats *stats)
+{
+    if (!ctx || !plan || n <= 0 || !d_packed || !packed_offsets || !d_pixels_out)
+        return KPEG_ERR_ARG;
+    if (n < 2 || ctx->profiling) // per-kernel event times are only meaningful without a concurrent lane
+        return kpeg_cuda_decode_batch_packed_device(ctx, plan, n, d_packed, (size_t)(packed_offsets[n] - packed_offsets[0]),
+                                                    d_pixels_out, stats);
+    CK(cudaSetDevice(ctx->device));
+    zero_stats(stats);
+    const size_t npix = (size_t)plan->width * plan->height * plan->ncomp;
+    const int h = n / 2;
+    const int lo[2] = {0, h}, hi[2] = {h, n};
+    for (int li = 0; li < 2; ++li) {
+        mark(ctx, ctx->lane[li], -1);
+        TRY(job_enqueue(ctx, li, plan, d_packed + packed_offsets[lo[li]], (size_t)(packed_offsets[hi[li]] - packed_offsets[lo[li]]),
+                        (uint32_t)(hi[li] - lo[li]), d_pixels_out + npix * (size_t)lo[li], {}));
+    }
+    int rc_all = KPEG_OK;
+    for (int li = 0; li < 2; ++li) {
+        const int rc = job_finish(ctx, li, stats);
+        if (rc != KPEG_OK && rc != KPEG_ERR_STREAM)
+            return rc;
+        if (rc != KPEG_OK)
+            rc_all = rc;
+    }
+    return rc_all;
 }
 
 extern "C" int kpeg_cuda_decode_batch_device(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *d_scans,
