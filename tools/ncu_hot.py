@@ -4,9 +4,15 @@ import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
 thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.012
-hdr = rows[1]
+hi = next(i for i, r in enumerate(rows) if 'Source' in r and '# Samples' in r)
+hdr = rows[hi]
 idx = {h: i for i, h in enumerate(hdr)}
-data = rows[2:]
+seen = set()
+data = []
+for r in rows[hi + 1:]:
+    if len(r) == len(hdr) and r[idx['# Samples']].isdigit() and r[idx['Address']] not in seen:
+        seen.add(r[idx['Address']])
+        data.append(r)
 tot = sum(int(r[idx['# Samples']]) for r in data)
 texec = sum(int(r[idx['Instructions Executed']]) for r in data)
 print('total samples', tot, 'warp instructions executed', texec, 'SASS lines', len(data))
