@@ -59,6 +59,17 @@ def env_int(name, default):
         return default
 
 
+def ncu_traffic(kernel, pixels):
+    """DRAM bytes per launch of `kernel` (read + write) scaled from the committed ncu capture; None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        k = t["kernels"][kernel]
+        return (k["read_mb"] + k["write_mb"]) * 1e6 / t["pixels_per_captured_launch"] * pixels
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -364,8 +375,14 @@ def run_cuda_arm(args):
                 e["frac_of_hbm_peak"] = e["achieved_gbs"] / peak
             kernels[k] = e
         dom = max((k for k in kernels if k not in ("memset", "relay_sparse")), key=lambda k: kernels[k]["ms_per_step"])
-        roof = lambda k: {"kernel": k, "bound": "hbm", "achieved": kernels[k].get("achieved_gbs"), "peak": peak,
-                          "unit": "GB/s", "frac": kernels[k].get("frac_of_hbm_peak"), "traffic": None,
+        px_per_launch = NB * npix_img  # the per-kernel pass runs the whole batch as one job: one launch per kernel
+        ncu_names = {"idct": "idct_kernel<3>", "entropy_write": "entropy_expand_kernel", "entropy_relay": "entropy_relay_full_kernel",
+                     "entropy_cold": "entropy_cold_kernel", "unstuff": "unstuff_count/scan/write_kernel"}
+        roof = lambda k: {"kernel": k, "cuda_kernel": ncu_names.get(k, k), "bound": "hbm", "achieved": kernels[k].get("achieved_gbs"), "peak": peak,
+                          "unit": "GB/s", "frac": kernels[k].get("frac_of_hbm_peak"),
+                          "algorithmic_bytes_per_launch": kernels[k].get("algorithmic_bytes"),
+                          "traffic": ncu_traffic(k, px_per_launch) if (W, Hh, args.quality) == (W4K, H4K, Q4K) else None,
+                          "traffic_source": "profiles/ncu_traffic.json (ncu --set full dram bytes per pixel x pixels per launch)",
                           "peak_source": peak_src, "ms_per_launch_group": kernels[k]["ms_per_step"],
                           "share_of_step": kernels[k]["ms_per_step"] / sum(x["ms_per_step"] for x in kernels.values())}
         entropy_ms = sum(per_step[k] for k in ("memset", "unstuff", "entropy_cold", "entropy_relay", "relay_sparse",
