@@ -168,7 +168,7 @@ int kpeg_batch_pack(int n, const uint8_t *const *scans, const size_t *scan_lens,
 int kpeg_cuda_decode_batch_packed_device(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *d_packed,
                                          size_t packed_len, uint8_t *d_pixels_out, kpeg_stats *stats);
 /* Same, given the offsets of the n scans inside the packed stream (packed_offsets[n] = its length): the
- * two halves of the batch run as concurrent jobs on the context's two lanes. */
+ * batch is cut into up to four parts that run as concurrent jobs on the context's lanes (streams). */
 int kpeg_cuda_decode_batch_packed_device_split(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *d_packed,
                                                const uint64_t *packed_offsets, uint8_t *d_pixels_out, kpeg_stats *stats);
 

@@ -296,11 +296,19 @@ KPEG_HD void expand_run(uint32_t &k, uint32_t nrec, uint32_t &slot, uint32_t &z,
 {
     const uint32_t total_slots = g.total_blocks * 64u;
     constexpr int BATCH = 8; // records fetched together: their loads are independent of the running state
+    // software pipeline: the batch after the one being expanded is already in flight
+    uint32_t nx[BATCH];
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j)
+        nx[j] = (k < nrec && slot < slot_limit && k + (uint32_t)j < nrec) ? rec_at(k + (uint32_t)j) : 0u;
     while (k < nrec && slot < slot_limit) {
         uint32_t rr[BATCH];
 #pragma unroll
         for (int j = 0; j < BATCH; ++j)
-            rr[j] = k + (uint32_t)j < nrec ? rec_at(k + (uint32_t)j) : 0u;
+            rr[j] = nx[j];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j)
+            nx[j] = k + (uint32_t)(BATCH + j) < nrec ? rec_at(k + (uint32_t)(BATCH + j)) : 0u;
 #pragma unroll
         for (int j = 0; j < BATCH; ++j) {
             if (k < nrec && slot < slot_limit) { // a record left unused here is fetched again by the next call

@@ -10,6 +10,8 @@
 // All file:line citations are relative to /root/reference.  The arithmetic lives in
 // entropy_core.h / idct_core.h (host+device inline, also exercised on the CPU by tests/emu).
 #include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdlib>
 #include <stddef.h>
 #include <stdint.h>
 
@@ -374,20 +376,27 @@ __device__ __forceinline__ size_t rec_base_index(uint32_t sub, uint32_t kmax)
     return ((size_t)(sub >> 5) * kmax) * 32u + (sub & 31u);
 }
 
+// A subsequence that is decoded again in a sparse relay round would overwrite its column of that layout
+// with lone 4-byte stores, one per 128-byte line (each a DRAM sector read-modify-write).  It gets a
+// private, contiguous area of kmax records in rec_alt instead (allocated once, on its first sparse
+// visit); nrec[sub] = count | (area index + 1) << 10 tells the final pass where to read.
+constexpr uint32_t NREC_MASK = 1023u;
+
 struct GlobalRecorder {
-    uint32_t *base; // &rec[rec_base_index(sub)]
+    uint32_t *base; // &rec[rec_base_index(sub)], or the subsequence's private area
     uint32_t kmax;
+    uint32_t stride; // 32 in the warp-interleaved layout, 1 in a private area
     __device__ __forceinline__ void emit(uint32_t k, uint32_t w) const
     {
         if (k < kmax)
-            base[(size_t)k * 32u] = w;
+            base[(size_t)k * stride] = w;
     }
 };
 
 // decode subsequence `sub` from (p, cz) for a relay pass; emits records when the job uses them
 template <class Words>
 __device__ __forceinline__ SubState relay_decode(const EntropyArgs &a, const Words &W, const SmemLuts &L, const StreamView &S,
-                                                 uint32_t sub, uint32_t end, uint32_t p, uint32_t cz)
+                                                 uint32_t sub, uint32_t end, uint32_t p, uint32_t cz, bool sparse)
 {
     DecState d;
     dec_init(d, W, S, p, cz >> 8, cz & 0xFFu, a.seg_hint[sub], 0u);
@@ -395,8 +404,21 @@ __device__ __forceinline__ SubState relay_decode(const EntropyArgs &a, const Wor
         GlobalRecorder R;
         R.base = a.rec + rec_base_index(sub, a.rec_kmax);
         R.kmax = a.rec_kmax;
+        R.stride = 32u;
+        uint32_t area = 0;
+        if (sparse) {
+            area = a.nrec[sub] >> 10;
+            if (area == 0u) {
+                const uint32_t idx = atomicAdd(&a.meta->rec_alt_count, 1u);
+                area = idx < a.rec_alt_cap ? idx + 1u : 0u;
+            }
+            if (area) {
+                R.base = a.rec_alt + (size_t)(area - 1u) * a.rec_kmax;
+                R.stride = 1u;
+            }
+        }
         decode_run<false, true>(d, W, L, S, a.g, end, 0xFFFFFFFFu, NullSink{}, R);
-        a.nrec[sub] = d.nrec;
+        a.nrec[sub] = min(d.nrec, NREC_MASK) | (area << 10);
         if (d.nrec > a.rec_kmax || (d.st & ST_REC_OVERFLOW))
             atomicOr(&a.meta->status, ST_REC_OVERFLOW);
     } else {
@@ -455,7 +477,7 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_full_kernel(Ent
             if (a.rec || (sub != 0u && !(in.p == start && in.cz == 0u))) {
                 const SmemWords W = k1_words(sm, tile, wlog);
                 const uint32_t end = min((sub + 1u) << (wlog + 5u), total_bits);
-                const SubState out = relay_decode(a, W, L, S, sub, end, in.p, in.cz);
+                const SubState out = relay_decode(a, W, L, S, sub, end, in.p, in.cz, false);
                 if (sub)
                     relay_publish(a, sub, out, nsub, a.worklist[1], &a.meta->changed[1]);
             }
@@ -513,7 +535,7 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_sparse_kernel(E
     W.gw0 = inraw.x >> 5;
     StreamView S{a.seg_bit, total_bits};
     const uint32_t end = min((sub + 1u) << (wlog + 5u), total_bits);
-    const SubState out = relay_decode(a, W, L, S, sub, end, inraw.x, inraw.z);
+    const SubState out = relay_decode(a, W, L, S, sub, end, inraw.x, inraw.z, true);
     relay_publish(a, sub, out, nsub, a.worklist[round & 1], &a.meta->changed[slot_cur]);
 }
 
@@ -521,6 +543,13 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_sparse_kernel(E
 // (5 %, 0.5 %, ... of the subsequences) but costs the full latency of one serial subsequence decode;
 // as separate launches every round also paid launch latency, table staging and a tail.  Here a small
 // cooperative grid stages the tables once and loops: process the list, grid barrier, next list.
+__device__ __forceinline__ uint32_t load_acquire_gpu(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void grid_barrier(uint32_t *counter, uint32_t &generation)
 {
     __syncthreads();
@@ -529,8 +558,13 @@ __device__ __forceinline__ void grid_barrier(uint32_t *counter, uint32_t &genera
         __threadfence();
         atomicAdd(counter, 1u);
         const uint32_t target = generation * gridDim.x;
-        while (*reinterpret_cast<volatile uint32_t *>(counter) < target)
-            __nanosleep(64);
+        // Back off between polls: CTAs without work arrive at once, and a thousand of them re-reading one
+        // L2 line back to back slow the memory requests of the CTAs that are still decoding.
+        uint32_t ns = 128;
+        while (load_acquire_gpu(counter) < target) {
+            __nanosleep(ns);
+            ns = ns < 1024u ? ns * 2u : ns;
+        }
         __threadfence();
     }
     __syncthreads();
@@ -553,27 +587,65 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_loop_kernel(Ent
     const uint32_t total_words = ((total_bits + 31u) >> 5) + 4u;
     uint32_t generation = 0;
     int round = first;
+#ifdef KPEG_RELAY_DEBUG
+    const long long t_start = clock64();
+#endif
+    // A round whose list fits one CTA is run by CTA 0 alone (the others leave): the tail rounds then cost a
+    // __syncthreads() each instead of a grid barrier.
+    constexpr uint32_t SOLO_ITEMS = ENTROPY_THREADS;
+    bool solo = false;
     for (; round <= last; ++round) {
-        const uint32_t count = *reinterpret_cast<volatile uint32_t *>(&a.meta->changed[relay_slot_dev(round - 1)]);
+        const uint32_t count = load_acquire_gpu(&a.meta->changed[relay_slot_dev(round - 1)]);
         if (count == 0u)
             break; // fixed point (uniform across the grid: read after the barrier)
+        if (!solo && count <= SOLO_ITEMS) {
+            if (blockIdx.x != 0u)
+                return;
+            solo = true;
+        }
         const uint32_t *list_in = a.worklist[(round - 1) & 1];
         uint32_t *list_out = a.worklist[round & 1];
         uint32_t *count_out = &a.meta->changed[relay_slot_dev(round)];
-        for (uint32_t w = blockIdx.x * ENTROPY_THREADS + threadIdx.x; w < count; w += gridDim.x * ENTROPY_THREADS) {
+        const uint32_t w0 = solo ? threadIdx.x : blockIdx.x * ENTROPY_THREADS + threadIdx.x;
+        const uint32_t wstep = solo ? ENTROPY_THREADS : gridDim.x * ENTROPY_THREADS;
+        for (uint32_t w = w0; w < count; w += wstep) {
             const uint32_t sub = __ldcg(list_in + w);
             if (sub >= nsub)
                 continue;
+#ifdef KPEG_RELAY_DEBUG
+            const long long t_item = clock64();
+#endif
             const uint4 inraw = __ldcg(reinterpret_cast<const uint4 *>(&a.state[sub - 1]));
             const uint32_t j0 = inraw.x >> 5;
             for (uint32_t k = 0; k < stride - 1u; ++k)
                 mine[k] = j0 + k < total_words ? __ldg(a.words + j0 + k) : 0u;
             W.gw0 = j0;
             const uint32_t end = min((sub + 1u) << (wlog + 5u), total_bits);
-            const SubState out = relay_decode(a, W, L, S, sub, end, inraw.x, inraw.z);
+            const SubState out = relay_decode(a, W, L, S, sub, end, inraw.x, inraw.z, true);
             relay_publish(a, sub, out, nsub, list_out, count_out);
+#ifdef KPEG_RELAY_DEBUG
+            atomicMax(&a.meta->dbg[16], (uint32_t)(clock64() - t_item));
+            atomicMax(&a.meta->dbg[17], end - inraw.x);
+#endif
         }
-        grid_barrier(&a.meta->grid_bar, generation);
+#ifdef KPEG_RELAY_DEBUG
+        const long long t_b0 = clock64();
+#endif
+        if (solo) {
+            __threadfence();
+            __syncthreads();
+        } else {
+            grid_barrier(&a.meta->grid_bar, generation);
+        }
+#ifdef KPEG_RELAY_DEBUG
+        if (threadIdx.x == 0) {
+            atomicMax(&a.meta->dbg[18], (uint32_t)(clock64() - t_b0));
+            if (blockIdx.x == 0 && round - first < 8) {
+                a.meta->dbg[round - first] = (uint32_t)(clock64() - t_start);
+                a.meta->dbg[8 + round - first] = count;
+            }
+        }
+#endif
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
         a.meta->relay_rounds = (uint32_t)(round <= last ? round - 1 : last);
@@ -892,7 +964,8 @@ __global__ void __launch_bounds__(WRITE_THREADS) entropy_write_kernel(EntropyArg
 // several are in flight), tracks (slot, zig-zag index) and drops values into the shared-memory window.
 struct GlobalRecAt {
     const uint32_t *base;
-    __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return __ldg(base + (size_t)k * 32u); }
+    uint32_t stride;
+    __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return __ldg(base + (size_t)k * stride); }
 };
 
 __global__ void __launch_bounds__(WRITE_THREADS) entropy_expand_kernel(EntropyArgs a)
@@ -916,8 +989,14 @@ __global__ void __launch_bounds__(WRITE_THREADS) entropy_expand_kernel(EntropyAr
         bool done = true;
         GlobalRecAt R;
         R.base = a.rec + rec_base_index(sub, a.rec_kmax);
+        R.stride = 32u;
         if (sub < nsub) {
-            n = min(a.nrec[sub], a.rec_kmax);
+            const uint32_t nr = a.nrec[sub];
+            n = min(nr & NREC_MASK, a.rec_kmax);
+            if (nr >> 10) { // redone in a sparse relay round: private contiguous area
+                R.base = a.rec_alt + (size_t)((nr >> 10) - 1u) * a.rec_kmax;
+                R.stride = 1u;
+            }
             slot = a.start_slot[sub];
             z = sub ? (a.state[sub - 1].cz & 0xFFu) : 0u;
             if ((slot & 63u) != z)
@@ -1000,15 +1079,30 @@ void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint3
     ++*launches;
 }
 
-static uint32_t g_relay_loop_grid = 148;
+static uint32_t g_sm_count = 148;
+static int g_relay_loop_per_sm_cap = 0; // experiments: cap of the cooperative relay loop's grid in CTAs per SM (0 = default rule)
 
 void launch_entropy_relay_loop(const EntropyArgs &a, int first, int last, cudaStream_t s, uint32_t *launches)
 {
     uint32_t wlog = ilog2(a.g.sub_bits / 32u);
     EntropyArgs args = a;
     void *params[] = {&args, &first, &last, &wlog};
-    cudaLaunchCooperativeKernel((const void *)entropy_relay_loop_kernel, dim3(g_relay_loop_grid), dim3(ENTROPY_THREADS), params,
-                                k1_sparse_smem_bytes(a.g.sub_bits), s);
+    const size_t smem = k1_sparse_smem_bytes(a.g.sub_bits);
+    int per_sm = 2;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entropy_relay_loop_kernel, ENTROPY_THREADS, smem) != cudaSuccess ||
+        per_sm < 1)
+        per_sm = 1;
+    uint32_t cap = g_sm_count * (uint32_t)per_sm / 4u; // up to four lanes may run their loops at the same time
+    if (g_relay_loop_per_sm_cap > 0)
+        cap = g_sm_count * (uint32_t)std::min(per_sm, g_relay_loop_per_sm_cap);
+    // Round 2 redoes a few percent of the subsequences (~6 % at 4K q95) and every later round far fewer, each
+    // at the latency of one serial subsequence decode: a small grid is enough, makes the grid barrier cheap,
+    // leaves the SMs to the other lanes' kernels, and keeps the sum of the lanes' cooperative grids far
+    // below what is co-resident (so concurrent loops can never wait on each other's CTAs).
+    uint32_t grid = a.nsub_max / (ENTROPY_THREADS * 12u) + 1u;
+    grid = grid < 32u ? 32u : grid;
+    grid = grid > cap ? cap : grid;
+    cudaLaunchCooperativeKernel((const void *)entropy_relay_loop_kernel, dim3(grid), dim3(ENTROPY_THREADS), params, smem, s);
     ++*launches;
 }
 
@@ -1770,7 +1864,9 @@ void kernels_configure()
         g_patch_grid = (uint32_t)(sms * 8);
         cudaFuncSetAttribute(entropy_relay_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)k1_sparse_smem_bytes(1024));
-        g_relay_loop_grid = (uint32_t)sms * 2u; // co-resident by a wide margin (cooperative launch checks it)
+        g_sm_count = (uint32_t)sms;
+        if (const char *e = getenv("KPEG_RELAY_LOOP_PER_SM"))
+            g_relay_loop_per_sm_cap = atoi(e);
     }
     cudaFuncSetAttribute(idct_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<3>));
     cudaFuncSetAttribute(idct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<1>));

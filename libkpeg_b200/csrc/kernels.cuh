@@ -29,6 +29,8 @@ struct DevMeta {
     uint32_t tie_inline;   // pixels resolved inside K3 because the record buffer was full
     uint32_t relay_rounds; // last relay round that ran (device-side round loop)
     uint32_t grid_bar;     // arrival counter of the relay loop's grid barrier
+    uint32_t rec_alt_count; // private record areas handed out by the sparse relay rounds
+    uint32_t dbg[24];      // scratch for experiments (KPEG_DEBUG_META=1 prints it)
     uint32_t changed[MAX_RELAY_ROUNDS];
 };
 
@@ -58,7 +60,9 @@ struct EntropyArgs {
     uint32_t *start_slot; // [nsub_max] absolute slot at the entry of subsequence i
     uint2 *scan_tiles;    // [ceil(nsub_max / 1024)] per-tile aggregates / carries of the offset scan
     uint32_t *rec;        // symbol records, [group of 32 subsequences][rec_kmax][32] (nullptr = records off)
-    uint32_t *nrec;       // [nsub_max] records per subsequence
+    uint32_t *nrec;       // [nsub_max] records per subsequence | (private area index + 1) << 10
+    uint32_t *rec_alt;    // [rec_alt_cap][rec_kmax] private record areas of subsequences redone in sparse rounds
+    uint32_t rec_alt_cap;
     uint32_t rec_kmax;
     int16_t *coef;        // [total_blocks][64]
     int16_t *dcdiff;      // [total_blocks]

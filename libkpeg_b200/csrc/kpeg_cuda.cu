@@ -1,9 +1,9 @@
 // kpeg_cuda.cu -- C-ABI host side of the B200 decode path (include/kpeg_cuda.h).
 //
-// A context owns two LANES (CUDA stream + grow-only device scratch + pinned bookkeeping each) and
+// A context owns four LANES (CUDA stream + grow-only device scratch + pinned bookkeeping each) and
 // the device tables built from a kpeg_plan.  A job is enqueued on a lane (K0..K3, kernels.cu) and
 // finished later (stream sync, device status word, and -- rarely -- extra relay rounds).  Single
-// decodes use lane 0; a large host-pointer batch is cut into chunks that alternate between the two
+// decodes use lane 0; a large host-pointer batch is cut into chunks that rotate through the
 // lanes so the H2D copy of one chunk, the kernels of another and the D2H copy of a third overlap
 // (the end-to-end path is PCIe-bound: 3 bytes per pixel have to leave the device).
 //
@@ -40,7 +40,7 @@ struct PinBuf {
 };
 
 constexpr int MAX_EVENTS = 192;
-constexpr int NLANES = 2;
+constexpr int NLANES = 4;
 
 struct Copy {
     void *dst;
@@ -66,7 +66,7 @@ struct Job {
 struct Lane {
     cudaStream_t stream = nullptr;
     DevBuf scan, words, seg_bit, tile_kept, tile_rst, state, work, seg_hint, start_slot, scan_tiles;
-    DevBuf coef, dcdiff, dc, tile_carry, pixels, meta, tie_rec, overflow, rec, nrec;
+    DevBuf coef, dcdiff, dc, tile_carry, pixels, meta, tie_rec, overflow, rec, nrec, rec_alt;
     PinBuf h_meta;
     cudaEvent_t ev[MAX_EVENTS] = {};
     int ev_stage[MAX_EVENTS] = {};
@@ -83,6 +83,8 @@ struct kpeg_ctx {
     uint32_t sub_bits = 512;
     int relay_rounds = 8;
     bool use_records = true; // final pass = record expansion (KPEG_NO_RECORDS=1: Huffman final pass)
+    int split_parts = 4;     // concurrent jobs a device-resident batch is cut into (KPEG_SPLIT)
+    int host_chunks = 8;     // pipeline depth of a host-pointer batch (KPEG_HOST_CHUNKS)
     Lane lane[NLANES];
 
     DevBuf tables, merged;
@@ -163,7 +165,7 @@ int ensure_pinned(kpeg_ctx *ctx, cudaStream_t stream, PinBuf &b, size_t bytes)
     return KPEG_OK;
 }
 
-// ---- plan -> device tables (shared by both lanes) ---------------------------------------------------
+// ---- plan -> device tables (shared by all lanes) ---------------------------------------------------
 int upload_plan(kpeg_ctx *ctx, const kpeg_plan *pl)
 {
     if (ctx->have_plan && memcmp(&ctx->plan_cached, pl, sizeof *pl) == 0)
@@ -312,9 +314,11 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     // symbol records: sub_bits / 2 per subsequence (every practical code is >= 2 bits; a stream that
     // needs more flags ST_REC_OVERFLOW and is redone with the Huffman final pass)
     const uint32_t rec_kmax = g.sub_bits / 2u;
+    const uint32_t rec_alt_cap = nsub_max / 4u + 1024u; // beyond it a redone subsequence rewrites its interleaved column
     if (ctx->use_records) {
         TRY(ensure(ctx, s, L.rec, (size_t)rec_kmax * ((size_t)nsub_max / 32u + 1u) * 32u * sizeof(uint32_t)));
         TRY(ensure(ctx, s, L.nrec, (size_t)nsub_max * sizeof(uint32_t)));
+        TRY(ensure(ctx, s, L.rec_alt, (size_t)rec_alt_cap * rec_kmax * sizeof(uint32_t)));
     }
 
     J = Job();
@@ -356,6 +360,8 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     ea.rec = J.use_records ? (uint32_t *)L.rec.p : nullptr;
     ea.nrec = (uint32_t *)L.nrec.p;
     ea.rec_kmax = rec_kmax;
+    ea.rec_alt = (uint32_t *)L.rec_alt.p;
+    ea.rec_alt_cap = rec_alt_cap;
     ea.coef = (int16_t *)L.coef.p;
     ea.dcdiff = (int16_t *)L.dcdiff.p;
     ea.nsub_max = nsub_max;
@@ -469,6 +475,12 @@ int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
                     used_rounds = (uint32_t)r;
         }
         stats->sync_rounds = std::max(stats->sync_rounds, used_rounds);
+        if (getenv("KPEG_DEBUG_META")) {
+            fprintf(stderr, "kpeg dbg:");
+            for (int i = 0; i < 24; ++i)
+                fprintf(stderr, " %u", h_meta->dbg[i]);
+            fprintf(stderr, " alt=%u\n", h_meta->rec_alt_count);
+        }
         stats->exact_samples += h_meta->tie_records; // pixels with at least one sample on the exact path
         stats->kernel_launches += J.launches;
         add_times(ctx, L, stats);
@@ -530,6 +542,10 @@ extern "C" int kpeg_cuda_create(int device, kpeg_ctx **out)
     }
     if (const char *nr = getenv("KPEG_NO_RECORDS"))
         ctx->use_records = !(nr[0] == '1');
+    if (const char *e = getenv("KPEG_SPLIT"))
+        ctx->split_parts = std::max(1, std::min(NLANES, atoi(e)));
+    if (const char *e = getenv("KPEG_HOST_CHUNKS"))
+        ctx->host_chunks = std::max(1, std::min(64, atoi(e)));
     if (const char *rr = getenv("KPEG_RELAY_ROUNDS")) {
         const long v = strtol(rr, nullptr, 10);
         if (v >= 2 && v < MAX_RELAY_ROUNDS)
@@ -564,7 +580,7 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
         DevBuf *bufs[] = {&L.scan, &L.words,    &L.seg_bit,    &L.tile_kept,  &L.tile_rst, &L.state,
                           &L.work, &L.seg_hint, &L.start_slot, &L.scan_tiles, &L.coef,     &L.dcdiff,
                           &L.dc,   &L.tile_carry, &L.pixels,   &L.meta,       &L.tie_rec,  &L.overflow,
-                          &L.rec,  &L.nrec};
+                          &L.rec,  &L.nrec,       &L.rec_alt};
         for (DevBuf *b : bufs)
             if (b->p)
                 cudaFree(b->p);
@@ -745,8 +761,8 @@ extern "C" int kpeg_cuda_decode_batch_packed_device(kpeg_ctx *ctx, const kpeg_pl
 }
 
 // Same, with the offsets of the n scans inside the packed stream (packed_offsets[n] = its length): the
-// batch is decoded as two concurrent jobs, one per lane, so the latency-bound phases of one half
-// (late relay rounds, record expansion) overlap the issue-bound phases of the other.
+// batch is decoded as up to four concurrent jobs, one per lane, so the latency-bound phases of one part
+// (late relay rounds, record expansion) overlap the issue-bound phases of the others.
 extern "C" int kpeg_cuda_decode_batch_packed_device_split(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *d_packed,
                                                           const uint64_t *packed_offsets, uint8_t *d_pixels_out,
                                                           kpeg_stats *stats)
@@ -759,15 +775,15 @@ extern "C" int kpeg_cuda_decode_batch_packed_device_split(kpeg_ctx *ctx, const k
     CK(cudaSetDevice(ctx->device));
     zero_stats(stats);
     const size_t npix = (size_t)plan->width * plan->height * plan->ncomp;
-    const int h = n / 2;
-    const int lo[2] = {0, h}, hi[2] = {h, n};
-    for (int li = 0; li < 2; ++li) {
+    const int parts = std::max(1, std::min({n, NLANES, ctx->split_parts}));
+    for (int li = 0; li < parts; ++li) {
+        const int lo = (int)((long long)n * li / parts), hi = (int)((long long)n * (li + 1) / parts);
         mark(ctx, ctx->lane[li], -1);
-        TRY(job_enqueue(ctx, li, plan, d_packed + packed_offsets[lo[li]], (size_t)(packed_offsets[hi[li]] - packed_offsets[lo[li]]),
-                        (uint32_t)(hi[li] - lo[li]), d_pixels_out + npix * (size_t)lo[li], {}));
+        TRY(job_enqueue(ctx, li, plan, d_packed + packed_offsets[lo], (size_t)(packed_offsets[hi] - packed_offsets[lo]),
+                        (uint32_t)(hi - lo), d_pixels_out + npix * (size_t)lo, {}));
     }
     int rc_all = KPEG_OK;
-    for (int li = 0; li < 2; ++li) {
+    for (int li = 0; li < parts; ++li) {
         const int rc = job_finish(ctx, li, stats);
         if (rc != KPEG_OK && rc != KPEG_ERR_STREAM)
             return rc;
@@ -805,7 +821,7 @@ extern "C" int kpeg_cuda_decode_batch_device(kpeg_ctx *ctx, const kpeg_plan *pla
 
 // Host-pointer batch.  Scans go straight from the caller's buffers into the lane's packed stream
 // (no host-side packing pass); a batch large enough for it to matter is cut into chunks that
-// alternate between the two lanes, so copies in, kernels and copies out of different chunks overlap.
+// rotate through the lanes, so copies in, kernels and copies out of different chunks overlap.
 extern "C" int kpeg_cuda_decode_batch(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *const *scans,
                                       const size_t *scan_lens, uint8_t *const *pixels_out, kpeg_stats *stats)
 {
@@ -814,16 +830,20 @@ extern "C" int kpeg_cuda_decode_batch(kpeg_ctx *ctx, const kpeg_plan *plan, int 
     CK(cudaSetDevice(ctx->device));
     zero_stats(stats);
     const size_t npix = (size_t)plan->width * plan->height * plan->ncomp;
-    // chunking: pipeline only when the pixel traffic is worth it (>= 32 MB); about four chunks
+    // chunking: pipeline only when the pixel traffic is worth it (>= 32 MB); the copy out dominates (3 B per
+    // pixel over PCIe), so chunks are small -- about 8 MB of pixels or more each, at most host_chunks of them --
+    // to start it early and keep it busy
     int per_chunk = n;
-    if (n >= 2 && npix * (size_t)n >= (32u << 20))
-        per_chunk = std::max(1, (n + 3) / 4);
+    if (n >= 2 && npix * (size_t)n >= (32u << 20)) {
+        const int min_imgs = (int)std::max<size_t>(1, (8u << 20) / std::max<size_t>(npix, 1));
+        per_chunk = std::max(min_imgs, (n + ctx->host_chunks - 1) / ctx->host_chunks);
+    }
     const int nchunks = (n + per_chunk - 1) / per_chunk;
     const uint8_t *sep = (const uint8_t *)ctx->h_sep.p;
     int rc_all = KPEG_OK;
 
     for (int c = 0; c < nchunks; ++c) {
-        const int li = nchunks > 1 ? (c & 1) : 0;
+        const int li = nchunks > 1 ? (c % NLANES) : 0;
         Lane &L = ctx->lane[li];
         // the lane's previous chunk must be complete before its buffers are reused
         if (L.job.active) {
