@@ -259,6 +259,7 @@ def run_cuda_arm(args):
     packed = pack_batch(scans)
     d_packed = dec.device_alloc(packed.size + 64)
     d_out = dec.device_alloc(NB * pix_bytes_img + 64)
+    d_outs = [d_out, dec.device_alloc(NB * pix_bytes_img + 64)]
     dec.h2d(d_packed, packed)
 
     stream = torch.cuda.ExternalStream(dec.stream, device=torch.device("cuda", device))
@@ -288,22 +289,34 @@ def run_cuda_arm(args):
     #     per-kernel events;  (2) the same steps again with an event after every kernel, one lane, for the
     #     per-kernel / roofline figures (kernel times are only meaningful without a concurrent lane).
     offsets = packed_offsets(scans)
-    for _ in range(max(args.warmup, 3)):
-        dec.decode_batch_packed_device_split(plan, NB, d_packed, offsets, d_out)
+    # every step is SUBMITTED (kpeg_cuda_submit_batch_packed_device: enqueue only), one wait at the end of the
+    # timed region completes and checks all of them: consecutive steps overlap on the device, as they do for
+    # any caller that keeps a decoder fed.  --sync-steps completes every step before the next is submitted.
+    def run_steps(k):
+        n_launch = 0
+        for _ in range(k):
+            if args.sync_steps:
+                dec.decode_batch_packed_device_split(plan, NB, d_packed, offsets, d_out)
+                n_launch += dec.last_stats.kernel_launches
+            else:
+                dec.submit_batch_packed_device(plan, NB, d_packed, offsets, d_outs[_ & 1])  # steps in flight never share an output
+        if not args.sync_steps:
+            dec.wait()
+            n_launch += dec.last_stats.kernel_launches
+        return n_launch
+
+    run_steps(max(args.warmup, 3) + 8)  # + enough steps for every lane of the context to have sized its scratch
     sampler = ClockSampler(device)
-    launches = 0
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        dec.decode_batch_packed_device_split(plan, NB, d_packed, offsets, d_out)
-        launches += dec.last_stats.kernel_launches
+    launches = run_steps(args.steps)
     t_wall = time.perf_counter() - t_wall0
     ev1.record(stream)
     barrier()
-    # both lanes are drained when the call returns, so the event pair on lane 0 brackets all the work;
+    # all lanes are drained when wait() returns, so the event pair on lane 0 brackets all the work;
     # take the larger of the event time and the host wall clock around the same region
     dev_ms = max(ev0.elapsed_time(ev1), t_wall * 1e3)
     clocks = sampler.stop()
@@ -397,7 +410,7 @@ def run_cuda_arm(args):
                        "l2_policy": "inputs larger than L2 (no flush): per step %.0f MB bit stream + %.0f MB coefficients + %.0f MB pixels"
                                     % (packed.size / 1e6, coef_bytes / 1e6, NB * pix_bytes_img / 1e6),
                        "sub_bits": args.sub_bits or "default", "parity_mode": "reference (F1 quirk on)",
-                       "concurrency": "each step = two half-batches on the two lanes (streams) of one context"},
+                       "concurrency": ("steps completed one at a time; " if args.sync_steps else "steps submitted back to back, one wait at the end of the timed region; ") + ("each step = up to 4 concurrent jobs on the lanes (streams) of one context" if args.sync_steps else "each step = one job, consecutive steps on different lanes (streams) of one context")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(packed.size),
                     "d2h_bytes_per_step": int(NB * pix_bytes_img), "ms_per_step": e2e_ms_max / args.steps,
                     "timer": "host wall clock around kpeg_cuda_decode_batch (pinned host buffers in and out)",
@@ -431,7 +444,8 @@ def run_cuda_arm(args):
     for p in pin_in + pin_out:
         p.free()
     dec.device_free(d_packed)
-    dec.device_free(d_out)
+    for p in d_outs:
+        dec.device_free(p)
     dec.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -452,6 +466,7 @@ def main():
     ap.add_argument("--relay-rounds", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-pixel-check", action="store_true")
+    ap.add_argument("--sync-steps", action="store_true", help="complete every step before submitting the next")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -172,6 +172,14 @@ int kpeg_cuda_decode_batch_packed_device(kpeg_ctx *ctx, const kpeg_plan *plan, i
 int kpeg_cuda_decode_batch_packed_device_split(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *d_packed,
                                                const uint64_t *packed_offsets, uint8_t *d_pixels_out, kpeg_stats *stats);
 
+/* Deferred form: enqueue the batch and return at once; kpeg_cuda_wait completes everything submitted since the
+ * last wait and returns the first failure (stats: accumulated over those batches).  Consecutive submissions
+ * overlap on the device.  d_packed / d_pixels_out must stay valid until kpeg_cuda_wait returns.  Any other
+ * decode call on the context completes pending submissions first. */
+int kpeg_cuda_submit_batch_packed_device(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *d_packed,
+                                         const uint64_t *packed_offsets, uint8_t *d_pixels_out);
+int kpeg_cuda_wait(kpeg_ctx *ctx, kpeg_stats *stats);
+
 /* Whole-file convenience used by the JPEGDecoder drop-in: parse + decode.  pixels_out must hold
  * width*height*ncomp bytes (query with kpeg_parse_jfif first) -- cap is checked. */
 int kpeg_cuda_decode_file(kpeg_ctx *ctx, const uint8_t *file, size_t len, uint32_t flags, uint8_t *pixels_out,

@@ -99,6 +99,8 @@ SYMBOLS = {
                                                       C.POINTER(Stats)]),
     "kpeg_cuda_decode_batch_packed_device_split": (C.c_int, [_vp, C.POINTER(Plan), C.c_int, _vp, C.POINTER(C.c_uint64), _vp,
                                                             C.POINTER(Stats)]),
+    "kpeg_cuda_submit_batch_packed_device": (C.c_int, [_vp, C.POINTER(Plan), C.c_int, _vp, C.POINTER(C.c_uint64), _vp]),
+    "kpeg_cuda_wait": (C.c_int, [_vp, C.POINTER(Stats)]),
     "kpeg_cuda_decode_file": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, C.c_size_t, C.POINTER(Plan),
                                        C.POINTER(Stats)]),
     "kpeg_cuda_read_coefficients": (C.c_int, [_vp, _vp, C.c_size_t]),
@@ -288,6 +290,17 @@ class Decoder:
             self._h, C.byref(plan), n, d_packed, offsets.ctypes.data_as(C.POINTER(C.c_uint64)), d_out,
             C.byref(self.last_stats))
         self._check(rc, "kpeg_cuda_decode_batch_packed_device_split")
+
+    def submit_batch_packed_device(self, plan: Plan, n: int, d_packed: int, offsets: np.ndarray, d_out: int):
+        """Enqueue only (kpeg_cuda_submit_batch_packed_device); `wait()` completes and checks everything submitted."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        rc = self._lib.kpeg_cuda_submit_batch_packed_device(
+            self._h, C.byref(plan), n, d_packed, offsets.ctypes.data_as(C.POINTER(C.c_uint64)), d_out)
+        self._check(rc, "kpeg_cuda_submit_batch_packed_device")
+
+    def wait(self):
+        rc = self._lib.kpeg_cuda_wait(self._h, C.byref(self.last_stats))
+        self._check(rc, "kpeg_cuda_wait")
 
     def decode_batch_packed_device(self, plan: Plan, n: int, d_packed: int, packed_len: int, d_out: int):
         rc = self._lib.kpeg_cuda_decode_batch_packed_device(self._h, C.byref(plan), n, d_packed, packed_len, d_out,

@@ -11,6 +11,7 @@
 // entropy_core.h / idct_core.h (host+device inline, also exercised on the CPU by tests/emu).
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <stddef.h>
 #include <stdint.h>
@@ -1080,6 +1081,11 @@ void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint3
 }
 
 static uint32_t g_sm_count = 148;
+static uint32_t g_max_concurrent_loops = 8;
+static std::atomic<int> g_live_contexts{0};
+
+void kernels_context_created() { ++g_live_contexts; }
+void kernels_context_destroyed() { --g_live_contexts; }
 static int g_relay_loop_per_sm_cap = 0; // experiments: cap of the cooperative relay loop's grid in CTAs per SM (0 = default rule)
 
 void launch_entropy_relay_loop(const EntropyArgs &a, int first, int last, cudaStream_t s, uint32_t *launches)
@@ -1092,15 +1098,18 @@ void launch_entropy_relay_loop(const EntropyArgs &a, int first, int last, cudaSt
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entropy_relay_loop_kernel, ENTROPY_THREADS, smem) != cudaSuccess ||
         per_sm < 1)
         per_sm = 1;
-    uint32_t cap = g_sm_count * (uint32_t)per_sm / 4u; // up to four lanes may run their loops at the same time
-    if (g_relay_loop_per_sm_cap > 0)
+    // every lane of a context may be inside its loop at the same time: together they must stay co-resident,
+    // or CTAs spinning at one loop's barrier could keep another loop's CTAs from ever being scheduled
+    uint32_t cap = g_sm_count * (uint32_t)per_sm / (g_max_concurrent_loops * (uint32_t)std::max(1, g_live_contexts.load()));
+    if (g_relay_loop_per_sm_cap > 0) // experiments only
         cap = g_sm_count * (uint32_t)std::min(per_sm, g_relay_loop_per_sm_cap);
+    cap = cap < 1u ? 1u : cap;
     // Round 2 redoes a few percent of the subsequences (~6 % at 4K q95) and every later round far fewer, each
     // at the latency of one serial subsequence decode: a small grid is enough, makes the grid barrier cheap,
     // leaves the SMs to the other lanes' kernels, and keeps the sum of the lanes' cooperative grids far
     // below what is co-resident (so concurrent loops can never wait on each other's CTAs).
     uint32_t grid = a.nsub_max / (ENTROPY_THREADS * 12u) + 1u;
-    grid = grid < 32u ? 32u : grid;
+    grid = grid < 16u ? 16u : grid;
     grid = grid > cap ? cap : grid;
     cudaLaunchCooperativeKernel((const void *)entropy_relay_loop_kernel, dim3(grid), dim3(ENTROPY_THREADS), params, smem, s);
     ++*launches;
@@ -1835,8 +1844,9 @@ __global__ void __launch_bounds__(128) idct_patch_kernel(IdctArgs a)
 
 static uint32_t g_patch_grid = 148 * 8;
 
-void kernels_configure()
+void kernels_configure(int max_concurrent_jobs)
 {
+    g_max_concurrent_loops = (uint32_t)(max_concurrent_jobs > 0 ? max_concurrent_jobs : 1);
     const int k1max = (int)k1_smem_bytes(1024);
     cudaFuncSetAttribute(entropy_cold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k1max);
     cudaFuncSetAttribute(entropy_relay_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k1max);

@@ -40,7 +40,7 @@ struct PinBuf {
 };
 
 constexpr int MAX_EVENTS = 192;
-constexpr int NLANES = 4;
+constexpr int NLANES = 8;
 
 struct Copy {
     void *dst;
@@ -85,6 +85,7 @@ struct kpeg_ctx {
     bool use_records = true; // final pass = record expansion (KPEG_NO_RECORDS=1: Huffman final pass)
     int split_parts = 4;     // concurrent jobs a device-resident batch is cut into (KPEG_SPLIT)
     int host_chunks = 8;     // pipeline depth of a host-pointer batch (KPEG_HOST_CHUNKS)
+    int submit_parts = 1;    // jobs one deferred submission is cut into (KPEG_SUBMIT_SPLIT)
     Lane lane[NLANES];
 
     DevBuf tables, merged;
@@ -95,6 +96,14 @@ struct kpeg_ctx {
 
     int last_lane = -1; // lane of the last finished job (kpeg_cuda_read_coefficients)
     JobGeom last_g = {};
+
+    // deferred submissions (kpeg_cuda_submit_* / kpeg_cuda_wait): lanes are handed out round-robin and a
+    // lane's previous job is finished only when the lane comes up again, so several batches are in flight
+    bool counted = false; // registered with kernels_context_created
+    int next_lane = 0;
+    int deferred_rc = KPEG_OK;
+    std::string deferred_err;
+    kpeg_stats deferred_stats = {};
 };
 
 namespace {
@@ -264,6 +273,18 @@ int enqueue_downstream(kpeg_ctx *ctx, Lane &L)
     return KPEG_OK;
 }
 
+int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats);
+
+// complete a deferred job; its outcome is reported by the next kpeg_cuda_wait
+void finish_deferred(kpeg_ctx *ctx, int li)
+{
+    const int rc = job_finish(ctx, li, &ctx->deferred_stats);
+    if (rc != KPEG_OK && ctx->deferred_rc == KPEG_OK) {
+        ctx->deferred_rc = rc;
+        ctx->deferred_err = ctx->err;
+    }
+}
+
 // Enqueue the whole device pipeline for one job whose stuffed bytes are (or will be, in stream
 // order) at d_scan.  Optimistic: the stages downstream of the relay are issued before it is known
 // whether the pre-issued relay rounds reached the fixed point; job_finish repairs that if not.
@@ -273,6 +294,12 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     Lane &L = ctx->lane[li];
     Job &J = L.job;
     cudaStream_t s = L.stream;
+    if (J.active) // a deferred job still owns this lane's scratch: complete it first
+        finish_deferred(ctx, li);
+    if (ctx->have_plan && memcmp(&ctx->plan_cached, pl, sizeof *pl) != 0)
+        for (int i = 0; i < NLANES; ++i) // the tables are shared: nothing deferred may outlive them
+            if (ctx->lane[i].job.active)
+                finish_deferred(ctx, i);
     JobGeom g;
     const char *why = nullptr;
     int rc = make_job_geom(pl, nimages, ctx->sub_bits, &g, &why);
@@ -534,7 +561,9 @@ extern "C" int kpeg_cuda_create(int device, kpeg_ctx **out)
         }
     }
     cudaEventCreateWithFlags(&ctx->tables_ready, cudaEventDisableTiming);
-    kernels_configure();
+    kernels_configure(NLANES);
+    kernels_context_created();
+    ctx->counted = true;
     if (const char *sb = getenv("KPEG_SUB_BITS")) {
         const long v = strtol(sb, nullptr, 10);
         if (v >= 64 && v <= 1024 && (v & (v - 1)) == 0)
@@ -544,6 +573,8 @@ extern "C" int kpeg_cuda_create(int device, kpeg_ctx **out)
         ctx->use_records = !(nr[0] == '1');
     if (const char *e = getenv("KPEG_SPLIT"))
         ctx->split_parts = std::max(1, std::min(NLANES, atoi(e)));
+    if (const char *e = getenv("KPEG_SUBMIT_SPLIT"))
+        ctx->submit_parts = std::max(1, std::min(NLANES, atoi(e)));
     if (const char *e = getenv("KPEG_HOST_CHUNKS"))
         ctx->host_chunks = std::max(1, std::min(64, atoi(e)));
     if (const char *rr = getenv("KPEG_RELAY_ROUNDS")) {
@@ -574,6 +605,8 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
     if (!ctx)
         return;
     cudaSetDevice(ctx->device);
+    if (ctx->counted)
+        kernels_context_destroyed();
     for (Lane &L : ctx->lane) {
         if (L.stream)
             cudaStreamSynchronize(L.stream);
@@ -791,6 +824,56 @@ extern "C" int kpeg_cuda_decode_batch_packed_device_split(kpeg_ctx *ctx, const k
             rc_all = rc;
     }
     return rc_all;
+}
+
+// Deferred form of the call above: enqueue and return.  Lanes are taken round-robin; a lane's previous job is
+// completed (its status checked, the rare slow path run) only when the lane is needed again or in
+// kpeg_cuda_wait, so consecutive batches overlap on the device: the latency-bound phases of one (late relay
+// rounds, one-block scans, kernel tails) are filled by the wide kernels of another.  d_packed and
+// d_pixels_out must stay valid until kpeg_cuda_wait returns.
+extern "C" int kpeg_cuda_submit_batch_packed_device(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *d_packed,
+                                                    const uint64_t *packed_offsets, uint8_t *d_pixels_out)
+{
+    if (!ctx || !plan || n <= 0 || !d_packed || !packed_offsets || !d_pixels_out)
+        return KPEG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)plan->width * plan->height * plan->ncomp;
+    // consecutive submissions already overlap; cutting one further only shortens its kernels (measured)
+    const int parts = ctx->profiling ? 1 : std::max(1, std::min({n, NLANES, ctx->submit_parts}));
+    for (int k = 0; k < parts; ++k) {
+        const int lo = (int)((long long)n * k / parts), hi = (int)((long long)n * (k + 1) / parts);
+        const int li = ctx->next_lane;
+        ctx->next_lane = (ctx->next_lane + 1) % NLANES;
+        if (ctx->lane[li].job.active)
+            finish_deferred(ctx, li);
+        mark(ctx, ctx->lane[li], -1);
+        TRY(job_enqueue(ctx, li, plan, d_packed + packed_offsets[lo], (size_t)(packed_offsets[hi] - packed_offsets[lo]),
+                        (uint32_t)(hi - lo), d_pixels_out + npix * (size_t)lo, {}));
+    }
+    return KPEG_OK;
+}
+
+// Complete everything submitted since the last wait.  Returns the first failure among those jobs (its text
+// in kpeg_cuda_last_error); *stats receives their accumulated figures.
+extern "C" int kpeg_cuda_wait(kpeg_ctx *ctx, kpeg_stats *stats)
+{
+    if (!ctx)
+        return KPEG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    for (int k = 0; k < NLANES; ++k) { // oldest submission first
+        const int li = (ctx->next_lane + k) % NLANES;
+        if (ctx->lane[li].job.active)
+            finish_deferred(ctx, li);
+    }
+    if (stats)
+        *stats = ctx->deferred_stats;
+    const int rc = ctx->deferred_rc;
+    if (rc != KPEG_OK)
+        ctx->err = ctx->deferred_err;
+    ctx->deferred_rc = KPEG_OK;
+    ctx->deferred_err.clear();
+    memset(&ctx->deferred_stats, 0, sizeof ctx->deferred_stats);
+    return rc;
 }
 
 extern "C" int kpeg_cuda_decode_batch_device(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *d_scans,

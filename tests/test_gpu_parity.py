@@ -250,3 +250,54 @@ def test_sparse_low_quality_stream_many_symbols_per_subsequence(decoder):
             check_against_oracle(decoder, synth_encode(SynthParams(512, 256, quality=3, seed=9)).tobytes())
         finally:
             decoder.set_tuning(sub_bits=512)
+
+
+def test_deferred_submissions_overlap_and_report_errors(decoder):
+    """kpeg_cuda_submit_batch_packed_device / kpeg_cuda_wait: several batches in flight (more than there are
+    lanes, so lanes are recycled), each into its own output; results equal the oracle's; a corrupt batch
+    surfaces as KPEG_ERR_STREAM from wait and does not poison the next submissions."""
+    from libkpeg_b200.api import pack_batch, packed_offsets
+    nb, w, h = 5, 160, 96
+    rounds = []
+    for r in range(7):
+        jpgs = [synth_encode(SynthParams(w, h, quality=93, flags=QUIRK_FREE, seed=900 + 10 * r + i)) for i in range(nb)]
+        parsed = [K.parse_jfif(j) for j in jpgs]
+        scans = [j[o:o + n] for j, (_, o, n) in zip(jpgs, parsed)]
+        rounds.append((jpgs, parsed[0][0], scans))
+    plan = rounds[0][1]
+    plan.flags = K.KPEG_FLAG_REF_PARITY
+    npix = w * h * 3
+    bufs = []
+    for jpgs, _, scans in rounds:
+        packed = pack_batch(scans)
+        d_in = decoder.device_alloc(packed.size + 64)
+        d_out = decoder.device_alloc(nb * npix + 64)
+        decoder.h2d(d_in, packed)
+        bufs.append((d_in, d_out, packed_offsets(scans)))
+    for d_in, d_out, off in bufs:
+        decoder.submit_batch_packed_device(plan, nb, d_in, off, d_out)
+    decoder.wait()
+    assert decoder.last_stats.kernel_launches > 0
+    for (jpgs, _, _), (_, d_out, _) in zip(rounds, bufs):
+        got = np.empty(nb * npix, dtype=np.uint8)
+        decoder.d2h(got, d_out)
+        for i, j in enumerate(jpgs):
+            ref = H.oracle_decode(j.tobytes())["pixels"]
+            assert np.array_equal(got[i * npix:(i + 1) * npix].reshape(h, w, 3), ref), f"image {i}"
+    # corrupt the middle of one packed stream (never 0xFF: the markers between the scans stay intact)
+    d_in, d_out, off = bufs[2]
+    bad = pack_batch(rounds[2][2]).copy()
+    rng = np.random.default_rng(11)
+    idx = rng.integers(int(off[1]) + 50, int(off[2]) - 50, size=24)
+    bad[idx] = rng.integers(1, 255, size=24).astype(np.uint8)
+    decoder.h2d(d_in, bad)
+    for k in (1, 2, 3):
+        decoder.submit_batch_packed_device(plan, nb, bufs[k][0], bufs[k][2], bufs[k][1])
+    with pytest.raises(K.KpegError) as ei:
+        decoder.wait()
+    assert ei.value.code == K.api.KPEG_ERR_STREAM
+    decoder.submit_batch_packed_device(plan, nb, bufs[4][0], bufs[4][2], bufs[4][1])
+    decoder.wait()
+    for d_in, d_out, _ in bufs:
+        decoder.device_free(d_in)
+        decoder.device_free(d_out)
