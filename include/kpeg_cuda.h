@@ -179,6 +179,11 @@ int kpeg_cuda_decode_batch_packed_device_split(kpeg_ctx *ctx, const kpeg_plan *p
 int kpeg_cuda_submit_batch_packed_device(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *d_packed,
                                          const uint64_t *packed_offsets, uint8_t *d_pixels_out);
 int kpeg_cuda_wait(kpeg_ctx *ctx, kpeg_stats *stats);
+/* Deferred form of kpeg_cuda_decode_batch (host buffers, ideally pinned, in and out): returns once the copies
+ * and kernels are enqueued; the pixels are valid after kpeg_cuda_wait.  scans[i] / pixels_out[i] must stay
+ * valid and untouched until then (the pointer arrays themselves are read before the call returns). */
+int kpeg_cuda_submit_batch(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *const *scans,
+                           const size_t *scan_lens, uint8_t *const *pixels_out);
 
 /* Whole-file convenience used by the JPEGDecoder drop-in: parse + decode.  pixels_out must hold
  * width*height*ncomp bytes (query with kpeg_parse_jfif first) -- cap is checked. */

@@ -101,6 +101,8 @@ SYMBOLS = {
                                                             C.POINTER(Stats)]),
     "kpeg_cuda_submit_batch_packed_device": (C.c_int, [_vp, C.POINTER(Plan), C.c_int, _vp, C.POINTER(C.c_uint64), _vp]),
     "kpeg_cuda_wait": (C.c_int, [_vp, C.POINTER(Stats)]),
+    "kpeg_cuda_submit_batch": (C.c_int, [_vp, C.POINTER(Plan), C.c_int, C.POINTER(_vp), C.POINTER(C.c_size_t),
+                                        C.POINTER(_vp)]),
     "kpeg_cuda_decode_file": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, C.c_size_t, C.POINTER(Plan),
                                        C.POINTER(Stats)]),
     "kpeg_cuda_read_coefficients": (C.c_int, [_vp, _vp, C.c_size_t]),
@@ -192,6 +194,7 @@ class Decoder:
         self._h = h
         self.device = device
         self.last_stats = Stats()
+        self._pending = []
         if profiling:
             self.set_profiling(True)
 
@@ -298,8 +301,22 @@ class Decoder:
             self._h, C.byref(plan), n, d_packed, offsets.ctypes.data_as(C.POINTER(C.c_uint64)), d_out)
         self._check(rc, "kpeg_cuda_submit_batch_packed_device")
 
+    def submit_batch(self, plan: Plan, scans: list[np.ndarray], outs: list[np.ndarray]):
+        """Enqueue only (kpeg_cuda_submit_batch, host buffers): `outs` are valid after `wait()`."""
+        n = len(scans)
+        for a in list(scans) + list(outs):
+            if not (a.flags["C_CONTIGUOUS"] and a.dtype == np.uint8):
+                raise ValueError("submit_batch needs contiguous uint8 arrays (they are used in place)")
+        sp = (_vp * n)(*[_ptr(s) for s in scans])
+        sl = (C.c_size_t * n)(*[s.size for s in scans])
+        op = (_vp * n)(*[_ptr(o) for o in outs])
+        self._pending.append((scans, outs))  # keep the buffers alive until wait()
+        rc = self._lib.kpeg_cuda_submit_batch(self._h, C.byref(plan), n, sp, sl, op)
+        self._check(rc, "kpeg_cuda_submit_batch")
+
     def wait(self):
         rc = self._lib.kpeg_cuda_wait(self._h, C.byref(self.last_stats))
+        self._pending.clear()
         self._check(rc, "kpeg_cuda_wait")
 
     def decode_batch_packed_device(self, plan: Plan, n: int, d_packed: int, packed_len: int, d_out: int):

@@ -902,20 +902,20 @@ extern "C" int kpeg_cuda_decode_batch_device(kpeg_ctx *ctx, const kpeg_plan *pla
     return job_finish(ctx, 0, stats);
 }
 
-// Host-pointer batch.  Scans go straight from the caller's buffers into the lane's packed stream
-// (no host-side packing pass); a batch large enough for it to matter is cut into chunks that
-// rotate through the lanes, so copies in, kernels and copies out of different chunks overlap.
-extern "C" int kpeg_cuda_decode_batch(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *const *scans,
-                                      const size_t *scan_lens, uint8_t *const *pixels_out, kpeg_stats *stats)
+// Host-pointer batch, deferred.  Scans go straight from the caller's (ideally pinned) buffers into a lane's
+// packed stream (no host-side packing pass); a batch large enough for it to matter is cut into chunks that
+// rotate through the lanes, so copies in, kernels and copies out of different chunks -- and of consecutive
+// submissions -- overlap.  The end-to-end path is bound by the copy out (3 bytes per pixel over PCIe): the
+// point is to keep that copy engine busy from the first chunk to the last.
+extern "C" int kpeg_cuda_submit_batch(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *const *scans,
+                                      const size_t *scan_lens, uint8_t *const *pixels_out)
 {
     if (!ctx || !plan || n <= 0 || !scans || !scan_lens || !pixels_out)
         return KPEG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    zero_stats(stats);
     const size_t npix = (size_t)plan->width * plan->height * plan->ncomp;
-    // chunking: pipeline only when the pixel traffic is worth it (>= 32 MB); the copy out dominates (3 B per
-    // pixel over PCIe), so chunks are small -- about 8 MB of pixels or more each, at most host_chunks of them --
-    // to start it early and keep it busy
+    // chunking: pipeline only when the pixel traffic is worth it (>= 32 MB); chunks of about 8 MB of pixels
+    // or more each, at most host_chunks of them
     int per_chunk = n;
     if (n >= 2 && npix * (size_t)n >= (32u << 20)) {
         const int min_imgs = (int)std::max<size_t>(1, (8u << 20) / std::max<size_t>(npix, 1));
@@ -923,19 +923,13 @@ extern "C" int kpeg_cuda_decode_batch(kpeg_ctx *ctx, const kpeg_plan *plan, int 
     }
     const int nchunks = (n + per_chunk - 1) / per_chunk;
     const uint8_t *sep = (const uint8_t *)ctx->h_sep.p;
-    int rc_all = KPEG_OK;
 
     for (int c = 0; c < nchunks; ++c) {
-        const int li = nchunks > 1 ? (c % NLANES) : 0;
+        const int li = ctx->next_lane;
+        ctx->next_lane = (ctx->next_lane + 1) % NLANES;
         Lane &L = ctx->lane[li];
-        // the lane's previous chunk must be complete before its buffers are reused
-        if (L.job.active) {
-            const int rc = job_finish(ctx, li, stats);
-            if (rc != KPEG_OK && rc != KPEG_ERR_STREAM)
-                return rc;
-            if (rc != KPEG_OK)
-                rc_all = rc;
-        }
+        if (L.job.active) // the lane's previous chunk must be complete before its buffers are reused
+            finish_deferred(ctx, li);
         const int i0 = c * per_chunk, i1 = std::min(n, i0 + per_chunk), m = i1 - i0;
         size_t total = 0;
         for (int i = i0; i < i1; ++i)
@@ -957,14 +951,36 @@ extern "C" int kpeg_cuda_decode_batch(kpeg_ctx *ctx, const kpeg_plan *plan, int 
             d2h.push_back(Copy{pixels_out[i], (uint8_t *)L.pixels.p + npix * (size_t)(i - i0), npix});
         TRY(job_enqueue(ctx, li, plan, (const uint8_t *)L.scan.p, total, (uint32_t)m, (uint8_t *)L.pixels.p, std::move(d2h)));
     }
-    for (int li = 0; li < NLANES; ++li) {
-        const int rc = job_finish(ctx, li, stats);
-        if (rc != KPEG_OK && rc != KPEG_ERR_STREAM)
-            return rc;
-        if (rc != KPEG_OK)
-            rc_all = rc;
-    }
-    return rc_all;
+    return KPEG_OK;
+}
+
+// Host-pointer batch, complete on return: a submission followed by a wait of its own.
+extern "C" int kpeg_cuda_decode_batch(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *const *scans,
+                                      const size_t *scan_lens, uint8_t *const *pixels_out, kpeg_stats *stats)
+{
+    if (!ctx || !plan || n <= 0 || !scans || !scan_lens || !pixels_out)
+        return KPEG_ERR_ARG;
+    zero_stats(stats);
+    // earlier deferred submissions keep their own outcome for the caller's kpeg_cuda_wait
+    for (int i = 0; i < NLANES; ++i)
+        if (ctx->lane[i].job.active)
+            finish_deferred(ctx, i);
+    const int saved_rc = ctx->deferred_rc;
+    const std::string saved_err = ctx->deferred_err;
+    const kpeg_stats saved_stats = ctx->deferred_stats;
+    ctx->deferred_rc = KPEG_OK;
+    ctx->deferred_err.clear();
+    memset(&ctx->deferred_stats, 0, sizeof ctx->deferred_stats);
+    int rc = kpeg_cuda_submit_batch(ctx, plan, n, scans, scan_lens, pixels_out);
+    const int wrc = kpeg_cuda_wait(ctx, stats);
+    if (rc == KPEG_OK)
+        rc = wrc;
+    const std::string my_err = ctx->err;
+    ctx->deferred_rc = saved_rc;
+    ctx->deferred_err = saved_err;
+    ctx->deferred_stats = saved_stats;
+    ctx->err = my_err;
+    return rc;
 }
 
 extern "C" int kpeg_cuda_decode_file(kpeg_ctx *ctx, const uint8_t *file, size_t len, uint32_t flags, uint8_t *pixels_out,
