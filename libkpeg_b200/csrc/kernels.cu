@@ -1362,7 +1362,7 @@ struct ZzNat {
     static constexpr int value = zigzag_to_natural(I);
 };
 
-constexpr int IDCT_REC_CAP = 192;
+constexpr int IDCT_REC_CAP = 176;
 
 template <int NC>
 struct IdctSmem {
@@ -1377,7 +1377,7 @@ struct IdctSmem {
     float qscale[NC][64];
     uint32_t qbytes[NC][16];      // the 8-bit quantisers, zig-zag order, four per word (for dp2a)
     uint2 tie[NB];                // per block: 64-bit mask of the samples inside the tie band
-    uint4 rec[IDCT_REC_CAP];      // tie records of this strip, flushed to the global list with ONE atomic
+    uint2 rec[IDCT_REC_CAP];      // tie records of this strip (compact form), flushed to the global list with ONE atomic
     uint32_t nrec, rec_base;
 };
 
@@ -1568,7 +1568,7 @@ __device__ __forceinline__ void resolve_and_store_pixel(const ExactCtx &a, const
 }
 
 template <int NC>
-__global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? 7 : 16) idct_kernel(IdctArgs a)
+__global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? 8 : 16) idct_kernel(IdctArgs a)
 {
     constexpr int NM = IDCT_MCUS_PER_CTA;
     constexpr int NB = NM * NC;
@@ -1764,7 +1764,11 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? 7 : 16) idct
                     fcb = sp[(((1 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
                     fcr = sp[((((NC - 1) * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
                 }
-                const uint4 rec = make_tie_record(img_pix0 + y * W + x, m, row * 8 + j, cm, fy, fcb, fcr);
+                // compact strip-local form: x = mcu in strip | sample << 5 | components << 11 | fast Cr << 16,
+                // y = fast Y | fast Cb << 16; expanded to the global record when the strip's list is flushed
+                const uint2 rec = make_uint2((uint32_t)ml | ((uint32_t)(row * 8 + j) << 5) | (cm << 11) |
+                                                 ((uint32_t)(uint16_t)(int)fcr << 16),
+                                             (uint32_t)(uint16_t)(int)fy | ((uint32_t)(uint16_t)(int)fcb << 16));
                 const uint32_t at = atomicAdd(&sm.nrec, 1u); // shared-memory counter: one global atomic per strip
                 if (at < (uint32_t)IDCT_REC_CAP)
                     sm.rec[at] = rec;
@@ -1790,9 +1794,18 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? 7 : 16) idct
     __syncthreads();
     const uint32_t base = sm.rec_base;
     for (uint32_t i = t; i < nrec; i += NB) {
-        if (base + i < a.tie_cap)
-            a.tie_rec[base + i] = sm.rec[i];
-        else {
+        if (base + i < a.tie_cap) {
+            const uint2 c = sm.rec[i];
+            const uint32_t rm = mcu0 + (c.x & 31u), rs = (c.x >> 5) & 63u;
+            const uint32_t img = rm / a.g.mcus_per_image, mi = rm - img * a.g.mcus_per_image;
+            const uint32_t by = mi / a.g.mcus_x, bx = mi - by * a.g.mcus_x;
+            uint4 r; // the record format of make_tie_record
+            r.x = img * a.g.width * a.g.height + (by * 8u + (rs >> 3)) * a.g.width + bx * 8u + (rs & 7u);
+            r.y = rm;
+            r.z = rs | (((c.x >> 11) & 7u) << 8) | (c.x & 0xFFFF0000u);
+            r.w = c.y;
+            a.tie_rec[base + i] = r;
+        } else {
             a.overflow_mcu[blockIdx.x] = 1u; // global list full
             if (i == t)
                 atomicAdd(&a.meta->tie_inline, 1u);
