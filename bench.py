@@ -305,7 +305,7 @@ def run_cuda_arm(args):
             n_launch += dec.last_stats.kernel_launches
         return n_launch
 
-    run_steps(max(args.warmup, 3) + 8)  # + enough steps for every lane of the context to have sized its scratch
+    run_steps(max(args.warmup, 3) + 16)  # + enough steps for every lane of the context to have sized its scratch
     sampler = ClockSampler(device)
     barrier()
     sampler.start()

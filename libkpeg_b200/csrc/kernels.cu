@@ -799,7 +799,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) entropy_scan_apply_kernel(Entrop
 // first and last block of a tile can be shared with a neighbouring tile; those are written
 // element-wise, each tile touching exactly its own slots.
 constexpr int WRITE_THREADS = 64;
-constexpr int WRITE_WIN_BLOCKS = 256;
+#ifndef KPEG_WIN_BLOCKS
+#define KPEG_WIN_BLOCKS 256
+#endif
+constexpr int WRITE_WIN_BLOCKS = KPEG_WIN_BLOCKS;
 
 struct WriteSmemTail {
     int16_t obuf[WRITE_WIN_BLOCKS * 64];
