@@ -198,6 +198,48 @@ KPEG_HD void decode_run(DecState &d, const Words &W, const Luts &L, const Stream
     uint32_t p = d.p, j = d.j, sh = d.sh, w0 = d.w0, w1 = d.w1, toff = d.toff, z = d.z, n = d.n;
     uint32_t k = d.k, segend = d.segend, slot = d.slot, st = d.st, nrec = d.nrec;
     int32_t seg = d.seg;
+    // Fast lane of the speculative / relay passes.  When the next boundary lies at least a symbol beyond
+    // end_bit (always, without restart markers, except next to an image end) no symbol of this call can
+    // straddle it, and with a word-aligned end_bit "p < end_bit" is "j < end_bit / 32": the loop carries
+    // neither p nor the slot count (64 * blocks completed + z_exit - z_entry, added afterwards).
+    if (!WRITE && p < end_bit && (end_bit & 31u) == 0u && segend >= end_bit + 32u) {
+        const uint32_t jend = end_bit >> 5, z_entry = z;
+        uint32_t nblk = 0;
+        while (j < jend) {
+            const uint32_t nxt = W(j + 2u);
+            const uint32_t win = funnel_left(w0, w1, sh);
+            uint32_t e = L.fast(toff, win >> (32 - LUT_BITS));
+            if ((e & 31u) == 0u)
+                e = L.slow(toff, win, e);
+            const uint32_t T = e & 31u, adv = e >> 9;
+            if (EMIT) {
+                const uint32_t size = (e >> 5) & 15u;
+                const uint32_t raw = (win << (T - size)) >> ((32u - size) & 31u);
+                rec.emit(nrec, pack_record(e, raw));
+                ++nrec;
+            }
+            sh += T;
+            {
+                const bool cross = sh >= 32u;
+                sh = cross ? sh - 32u : sh;
+                j = cross ? j + 1u : j;
+                w0 = cross ? w1 : w0;
+                w1 = cross ? nxt : w1;
+            }
+            const uint32_t zn = z + adv;
+            if (zn >= 64u) {
+                z = 0;
+                ++nblk;
+                toff += (uint32_t)LUT_SIZE;
+                toff = toff == ring ? 0u : toff;
+            } else {
+                z = zn;
+                toff |= (uint32_t)LUT_SIZE;
+            }
+        }
+        p = (j << 5) + sh;
+        n += nblk * 64u + z - z_entry;
+    }
     while (p < end_bit && (!WRITE || slot < slot_limit)) {
         const uint32_t nxt = W(j + 2u); // consumed at the bottom of the iteration, if at all
         const uint32_t win = funnel_left(w0, w1, sh);

@@ -452,7 +452,7 @@ __device__ __forceinline__ void relay_publish(const EntropyArgs &a, uint32_t sub
     }
 }
 
-__global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_full_kernel(EntropyArgs a, uint32_t wlog)
+__global__ void __launch_bounds__(ENTROPY_THREADS, 10) entropy_relay_full_kernel(EntropyArgs a, uint32_t wlog)
 {
     extern __shared__ __align__(16) unsigned char k1_raw[];
     K1Smem &sm = *reinterpret_cast<K1Smem *>(k1_raw);
@@ -571,7 +571,7 @@ __device__ __forceinline__ void grid_barrier(uint32_t *counter, uint32_t &genera
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_loop_kernel(EntropyArgs a, int first, int last,
+__global__ void __launch_bounds__(ENTROPY_THREADS, 8) entropy_relay_loop_kernel(EntropyArgs a, int first, int last,
                                                                              uint32_t wlog)
 {
     extern __shared__ __align__(16) unsigned char k1_raw[];
