@@ -114,18 +114,26 @@ struct GlobalSink {
 // The relay passes decode every subsequence from (what converges to) its true entry state anyway;
 // they also write down what they decoded, one 32-bit record per symbol, so that the final pass is a
 // cheap, load-latency-tolerant EXPANSION of records instead of a third serial Huffman decode:
-//   bits 0-15 the raw magnitude bits as they sit in the stream (EXTEND is applied by the expander),
-//   bits 16-26 the table entry's (magnitude bits | slot advance << 4), bit 27 "invalid bit pattern",
-//   bits 28-31 type: 0 symbol, 0xF boundary jump (bits 0-23 = index of the segment that starts there).
+//   a symbol     : the table entry shifted left by 11 (total bits 11-15, magnitude size 16-19, slot
+//                  advance 20-26) + the raw magnitude bits as they sit in the stream in bits 0-10 (at most
+//                  11 of them in baseline JPEG; EXTEND is applied by the expander).  An invalid bit
+//                  pattern is the entry ENTRY_INVALID: advance 127.
+//   boundary jump: 0xF0000000 | index of the segment that starts there.
 constexpr uint32_t REC_JUMP = 0xF0000000u;
+constexpr uint32_t REC_RAW_MASK = 0x7FFu;
 
-// e = table entry (total bits | size << 5 | adv << 9), raw = the `size` magnitude bits (garbage when size == 0)
-KPEG_HD uint32_t pack_record(uint32_t e, uint32_t raw)
+// raw = the `size` magnitude bits that follow the code in the left-aligned window (0 when size == 0)
+KPEG_HD uint32_t record_raw_bits(uint32_t win, uint32_t T, uint32_t size)
 {
-    const uint32_t T = e & 31u, size = (e >> 5) & 15u, len = T - size;
-    const uint32_t bad = (len >> 4) & len & 1u; // code "length" 17: no code matched
-    return (raw & 0xFFFFu) | ((e >> 5) << 16) | (bad << 27);
+    const uint32_t x = win << (T - size);
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_rc(x, 0u, 32u - size); // clamped shift: size == 0 gives 0
+#else
+    return size ? x >> (32u - size) : 0u;
+#endif
 }
+
+KPEG_HD uint32_t pack_record(uint32_t e, uint32_t raw) { return (e << 11) + raw; }
 
 struct NoRecorder {
     KPEG_HD void emit(uint32_t, uint32_t) const {}
@@ -213,9 +221,7 @@ KPEG_HD void decode_run(DecState &d, const Words &W, const Luts &L, const Stream
                 e = L.slow(toff, win, e);
             const uint32_t T = e & 31u, adv = e >> 9;
             if (EMIT) {
-                const uint32_t size = (e >> 5) & 15u;
-                const uint32_t raw = (win << (T - size)) >> ((32u - size) & 31u);
-                rec.emit(nrec, pack_record(e, raw));
+                rec.emit(nrec, pack_record(e, record_raw_bits(win, T, (e >> 5) & 15u)));
                 ++nrec;
             }
             sh += T;
@@ -286,9 +292,7 @@ KPEG_HD void decode_run(DecState &d, const Words &W, const Luts &L, const Stream
             sink.put(z == 0u, slot, adv, size != 0u && slot + adv <= total_slots, val);
         }
         if (EMIT) {
-            const uint32_t size = (e >> 5) & 15u;
-            const uint32_t raw = (win << (T - size)) >> ((32u - size) & 31u);
-            rec.emit(nrec, pack_record(e, raw));
+            rec.emit(nrec, pack_record(e, record_raw_bits(win, T, (e >> 5) & 15u)));
             ++nrec;
         }
         p += T;
@@ -365,9 +369,9 @@ KPEG_HD void expand_run(uint32_t &k, uint32_t nrec, uint32_t &slot, uint32_t &z,
                 } else {
                     const uint32_t size = (r >> 16) & 15u, adv = (r >> 20) & 127u;
                     const bool has_value = size != 0u;
-                    st |= (r >> 27) & 1u; // ST_BAD_CODE
+                    st |= adv == ENTRY_ADV_INVALID ? ST_BAD_CODE : 0u;
                     st |= (has_value && z + adv > 64u) ? ST_SLOT_OVERFLOW : 0u;
-                    const int32_t val = extend_value(r & 0xFFFFu, size | (size == 0u ? 1u : 0u));
+                    const int32_t val = extend_value(r & REC_RAW_MASK, size | (size == 0u ? 1u : 0u));
                     sink.put(z == 0u, slot, adv, has_value && slot + adv <= total_slots, val);
                     uint32_t zn = z + adv;
                     zn = zn > 64u ? 64u : zn;

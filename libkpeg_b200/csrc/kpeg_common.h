@@ -32,7 +32,10 @@ namespace kpeg {
 constexpr int LUT_BITS = 10;
 constexpr int LUT_SIZE = 1 << LUT_BITS;
 constexpr int LONG_CAP = 512;  // second-level entries per table: 8 sub-tables of 64 (one per 10-bit prefix of long codes)
-constexpr uint32_t ENTRY_INVALID = 17u | (0u << 5) | (1u << 9); // "needs more than 16 bits"
+// no code matches: "length" 17, no magnitude bits, and a slot advance no real symbol has (records carry the
+// entry, so the expander recognises the pattern by it)
+constexpr uint32_t ENTRY_ADV_INVALID = 127u;
+constexpr uint32_t ENTRY_INVALID = 17u | (0u << 5) | (ENTRY_ADV_INVALID << 9);
 constexpr int MAX_COMP = 3;
 constexpr int MAX_LUTS = MAX_COMP * 2; // [comp*2 + (0=DC,1=AC)]
 

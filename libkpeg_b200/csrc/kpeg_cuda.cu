@@ -100,6 +100,7 @@ struct kpeg_ctx {
     // deferred submissions (kpeg_cuda_submit_* / kpeg_cuda_wait): lanes are handed out round-robin and a
     // lane's previous job is finished only when the lane comes up again, so several batches are in flight
     bool counted = false; // registered with kernels_context_created
+    bool plan_fits_records = true;
     int next_lane = 0;
     int deferred_rc = KPEG_OK;
     std::string deferred_err;
@@ -195,6 +196,20 @@ int upload_plan(kpeg_ctx *ctx, const kpeg_plan *pl)
         CK(cudaStreamWaitEvent(ctx->lane[i].stream, ctx->tables_ready, 0));
     ctx->plan_cached = *pl;
     ctx->have_plan = true;
+    // symbol records keep 11 magnitude bits (all baseline JPEG has: DC categories 0..11, AC 0..10, T.81
+    // F.1.2.1.2 / F.1.2.2.1); a table that declares wider ones is decoded with the Huffman final pass
+    ctx->plan_fits_records = true;
+    for (int cls = 0; cls < 2; ++cls)
+        for (int id = 0; id < 4; ++id) {
+            if (!pl->ht_present[cls][id])
+                continue;
+            int nsym = 0;
+            for (int L = 0; L < 16; ++L)
+                nsym += pl->ht[cls][id].counts[L];
+            for (int i = 0; i < nsym && i < 256; ++i)
+                if ((pl->ht[cls][id].symbols[i] & 15) > 11)
+                    ctx->plan_fits_records = false;
+        }
     return KPEG_OK;
 }
 
@@ -349,7 +364,7 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     }
 
     J = Job();
-    J.use_records = ctx->use_records;
+    J.use_records = ctx->use_records && ctx->plan_fits_records;
     J.active = true;
     J.g = g;
     J.scan_len = scan_len;
