@@ -230,8 +230,6 @@ def run_cuda_arm(args):
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     dist = None
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
@@ -487,6 +485,12 @@ def main():
     ap.add_argument("--skip-pixel-check", action="store_true")
     ap.add_argument("--sync-steps", action="store_true", help="complete every step before submitting the next")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: whatever libraries write to file descriptor 1 (NCCL's version
+    # banner, for one) is sent to stderr, and Python's own stdout keeps the original descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_cuda_arm(args)
