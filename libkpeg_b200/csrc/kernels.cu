@@ -73,20 +73,41 @@ __device__ __forceinline__ uint32_t block_exclusive_sum(uint32_t v, uint32_t *s_
 // a restart marker (segment boundary); FF FF is a fill byte; anything else is flagged.  The
 // reference drops only the 00 (Decoder.cpp:631-650) and cannot handle RSTn.
 
+// Classification happens once, here: the keep / RSTn masks of every 16-byte chunk are stored for the
+// compaction kernel (4 bytes per 16 of input).  Chunks inside the segment are classified sixteen bytes at a
+// time (classify16_swar); the neighbouring bytes come from the adjacent lanes.
 __global__ void __launch_bounds__(UNSTUFF_THREADS) unstuff_count_kernel(UnstuffArgs a)
 {
     __shared__ uint32_t s_w[UNSTUFF_THREADS / 32 + 1];
-    const uint32_t base = (blockIdx.x * UNSTUFF_THREADS + threadIdx.x) * UNSTUFF_BYTES_PER_THREAD;
-    uint32_t kept = 0, rst = 0, bad = 0;
-    if (base < a.scan_len) {
-        const ByteClass c = classify16(a.scan, a.scan_len, base);
-        kept = __popc(c.keep);
-        rst = __popc(c.rst);
+    const uint32_t chunk = blockIdx.x * UNSTUFF_THREADS + threadIdx.x;
+    const uint32_t base = chunk * UNSTUFF_BYTES_PER_THREAD;
+    const int lane = threadIdx.x & 31;
+    uint32_t keep = 0, rst = 0, bad = 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(a.scan) & 15u) == 0;
+    const bool whole = aligned && base + 16u <= a.scan_len; // warp-uniform except in the last warp of the stream
+    uint32_t b[4] = {0, 0, 0, 0};
+    if (whole)
+        ld_16bytes(a.scan + base, b);
+    // bytes on either side of the chunk: from the neighbouring lanes, from memory at the warp's edges
+    uint32_t prev = __shfl_up_sync(0xffffffffu, b[3] >> 24, 1);
+    uint32_t next = __shfl_down_sync(0xffffffffu, b[0] & 0xFFu, 1);
+    const bool next_whole = __shfl_down_sync(0xffffffffu, whole ? 1 : 0, 1) != 0;
+    if (whole) {
+        if (lane == 0)
+            prev = base ? (uint32_t)ld_byte(a.scan + base - 1) : 0u;
+        if (lane == 31 || !next_whole)
+            next = base + 16u < a.scan_len ? (uint32_t)ld_byte(a.scan + base + 16) : 0xFFu;
+        classify16_swar(b, prev, next, keep, rst, bad);
+    } else if (base < a.scan_len) {
+        const ByteClass c = classify16(a.scan, a.scan_len, base); // the stream's ragged tail (or an unaligned buffer)
+        keep = c.keep;
+        rst = c.rst;
         bad = c.bad;
     }
+    a.cls[chunk] = keep | (rst << 16);
     // pack both counts into one reduction: kept <= 4096 per tile, rst <= 2048
     uint32_t tot;
-    block_exclusive_sum<UNSTUFF_THREADS>(kept | (rst << 16), s_w, tot);
+    block_exclusive_sum<UNSTUFF_THREADS>(__popc(keep) | (__popc(rst) << 16), s_w, tot);
     if (threadIdx.x == 0) {
         a.tile_kept[blockIdx.x] = tot & 0xFFFFu;
         a.tile_rst[blockIdx.x] = tot >> 16;
@@ -138,39 +159,85 @@ __global__ void __launch_bounds__(1024) unstuff_scan_kernel(UnstuffArgs a, uint3
 // Compaction: the tile's surviving bytes are gathered in shared memory at their final phase within a
 // 32-bit word, then written out as whole byte-swapped words (coalesced); only the at most three
 // bytes at either end of the tile's output range, which share a word with a neighbouring tile, go out
-// as single bytes.
+// as single bytes.  A thread deletes its chunk's dropped bytes in registers (rarely more than one), then
+// stores the survivors at their byte offset: whole words where it owns the word, an OR into the zeroed
+// buffer where a word is shared with the neighbouring chunk.
+__device__ __forceinline__ void delete_byte(uint32_t (&b)[4], uint32_t q) // bytes above q move down by one
+{
+    const uint32_t t0 = __funnelshift_r(b[0], b[1], 8), t1 = __funnelshift_r(b[1], b[2], 8),
+                   t2 = __funnelshift_r(b[2], b[3], 8), t3 = b[3] >> 8;
+    const uint32_t wq = q >> 2, low = (1u << (8u * (q & 3u))) - 1u; // bytes of word wq below q stay
+    b[0] = wq == 0u ? (b[0] & low) | (t0 & ~low) : b[0];
+    b[1] = wq == 1u ? (b[1] & low) | (t1 & ~low) : (wq < 1u ? t1 : b[1]);
+    b[2] = wq == 2u ? (b[2] & low) | (t2 & ~low) : (wq < 2u ? t2 : b[2]);
+    b[3] = wq == 3u ? (b[3] & low) | (t3 & ~low) : t3;
+}
+
 __global__ void __launch_bounds__(UNSTUFF_THREADS) unstuff_write_kernel(UnstuffArgs a)
 {
     __shared__ uint32_t s_w[UNSTUFF_THREADS / 32 + 1];
     __shared__ __align__(16) uint8_t s_out[UNSTUFF_TILE + 16];
-    const uint32_t base = (blockIdx.x * UNSTUFF_THREADS + threadIdx.x) * UNSTUFF_BYTES_PER_THREAD;
-    ByteClass c;
-    c.keep = c.rst = 0;
-    if (base < a.scan_len)
-        c = classify16(a.scan, a.scan_len, base);
+    const uint32_t chunk = blockIdx.x * UNSTUFF_THREADS + threadIdx.x;
+    const uint32_t base = chunk * UNSTUFF_BYTES_PER_THREAD;
+    reinterpret_cast<uint4 *>(s_out)[threadIdx.x] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0)
+        reinterpret_cast<uint4 *>(s_out)[UNSTUFF_THREADS] = make_uint4(0, 0, 0, 0);
+    const uint32_t cls = a.cls[chunk];
+    uint32_t keep = cls & 0xFFFFu;
+    const uint32_t rst = cls >> 16;
+    uint32_t b[4] = {0, 0, 0, 0};
+    if (keep) {
+        if (base + 16u <= a.scan_len && (reinterpret_cast<uintptr_t>(a.scan) & 15u) == 0) {
+            ld_16bytes(a.scan + base, b);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (base + i < a.scan_len)
+                    b[i >> 2] |= (uint32_t)ld_byte(a.scan + base + i) << (8 * (i & 3));
+        }
+    }
+    const uint32_t n = __popc(keep);
     uint32_t tot;
-    const uint32_t ex = block_exclusive_sum<UNSTUFF_THREADS>(__popc(c.keep) | (__popc(c.rst) << 16), s_w, tot);
+    const uint32_t ex = block_exclusive_sum<UNSTUFF_THREADS>(n | (__popc(rst) << 16), s_w, tot); // syncs: s_out is zero
     const uint32_t pos0 = a.tile_kept[blockIdx.x]; // first output byte of the tile
     const uint32_t nkept = tot & 0xFFFFu;
     const uint32_t phase = pos0 & 3u;
-    uint32_t lpos = phase + (ex & 0xFFFFu); // position inside s_out
-    uint32_t ridx = a.tile_rst[blockIdx.x] + (ex >> 16);
-    if (c.keep == 0xFFFFu && (lpos & 3u) == 0u) {
-        uint32_t *w = reinterpret_cast<uint32_t *>(s_out + lpos);
+    const uint32_t lpos = phase + (ex & 0xFFFFu); // position inside s_out
+    if (rst) { // restart markers: the segment that follows starts at the next surviving byte
+        uint32_t ridx = a.tile_rst[blockIdx.x] + (ex >> 16);
+        uint32_t r = rst;
+        while (r) {
+            const int i = __ffs(r) - 1;
+            r &= r - 1u;
+            ++ridx;
+            if (ridx < a.nseg)
+                a.seg_bit[ridx] = (pos0 - phase + lpos + __popc(keep & ((1u << i) - 1u))) * 8u;
+        }
+    }
+    if (n) {
+        uint32_t drop = ~keep & 0xFFFFu;
+        while (drop) { // highest dropped byte first: the indices below it stay valid
+            const uint32_t q = 31u - (uint32_t)__clz(drop);
+            drop &= ~(1u << q);
+            delete_byte(b, q);
+        }
+        // survivors b[0..n) -> s_out[lpos .. lpos + n)
+        const uint32_t sh = 8u * (lpos & 3u);
+        uint32_t *w = reinterpret_cast<uint32_t *>(s_out) + (lpos >> 2);
+        const uint32_t o[5] = {b[0] << sh, __funnelshift_l(b[0], b[1], sh), __funnelshift_l(b[1], b[2], sh),
+                               __funnelshift_l(b[2], b[3], sh), sh ? b[3] >> (32u - sh) : 0u};
+        const uint32_t first = lpos & 3u, end = first + n; // byte range [first, end) of the five words
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            w[k] = c.b[k];
-    } else if (c.keep | c.rst) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if (c.rst & (1u << i)) {
-                ++ridx;
-                if (ridx < a.nseg)
-                    a.seg_bit[ridx] = (pos0 - phase + lpos) * 8u;
-            }
-            if (c.keep & (1u << i)) {
-                s_out[lpos] = (uint8_t)(c.b[i >> 2] >> (8 * (i & 3)));
-                ++lpos;
+        for (int k = 0; k < 5; ++k) {
+            const uint32_t lo = max(first, 4u * k), hi = min(end, 4u * k + 4u);
+            if (hi > lo) {
+                if (hi - lo == 4u) {
+                    w[k] = o[k];
+                } else {
+                    const uint32_t m = (hi - 4u * k == 4u ? 0xFFFFFFFFu : (1u << (8u * (hi - 4u * k))) - 1u) &
+                                       ~((1u << (8u * (lo - 4u * k))) - 1u);
+                    atomicOr(&w[k], o[k] & m);
+                }
             }
         }
     }

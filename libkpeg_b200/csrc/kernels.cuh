@@ -39,6 +39,7 @@ struct UnstuffArgs {
     uint32_t scan_len;
     uint32_t ntiles;
     uint32_t *tile_kept, *tile_rst;      // per-tile counts, then (after the scan kernel) exclusive offsets
+    uint32_t *cls;                       // [ntiles * UNSTUFF_THREADS] per 16-byte chunk: keep mask | RSTn mask << 16
     uint8_t *words;                      // unstuffed stream as big-endian 32-bit words (byte address ^ 3)
     uint32_t *seg_bit;                   // [nseg + 2]
     uint32_t nseg;                       // expected number of segments

@@ -65,7 +65,7 @@ struct Job {
 
 struct Lane {
     cudaStream_t stream = nullptr;
-    DevBuf scan, words, seg_bit, tile_kept, tile_rst, state, work, seg_hint, start_slot, scan_tiles;
+    DevBuf scan, words, seg_bit, tile_kept, tile_rst, cls, state, work, seg_hint, start_slot, scan_tiles;
     DevBuf coef, dcdiff, dc, tile_carry, pixels, meta, tie_rec, overflow, rec, nrec, rec_alt;
     PinBuf h_meta;
     cudaEvent_t ev[MAX_EVENTS] = {};
@@ -340,6 +340,7 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     TRY(ensure(ctx, s, L.seg_bit, ((size_t)g.nseg + 2u) * 4u));
     TRY(ensure(ctx, s, L.tile_kept, (size_t)ntiles * 4u));
     TRY(ensure(ctx, s, L.tile_rst, (size_t)ntiles * 4u));
+    TRY(ensure(ctx, s, L.cls, (size_t)ntiles * UNSTUFF_THREADS * 4u));
     TRY(ensure(ctx, s, L.state, (size_t)nsub_max * sizeof(SubState)));
     TRY(ensure(ctx, s, L.work, (size_t)nsub_max * 2u * sizeof(uint32_t)));
     TRY(ensure(ctx, s, L.seg_hint, (size_t)nsub_max * 4u));
@@ -381,6 +382,7 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     ua.ntiles = ntiles;
     ua.tile_kept = (uint32_t *)L.tile_kept.p;
     ua.tile_rst = (uint32_t *)L.tile_rst.p;
+    ua.cls = (uint32_t *)L.cls.p;
     ua.words = (uint8_t *)L.words.p;
     ua.seg_bit = (uint32_t *)L.seg_bit.p;
     ua.nseg = g.nseg;
@@ -625,7 +627,7 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
     for (Lane &L : ctx->lane) {
         if (L.stream)
             cudaStreamSynchronize(L.stream);
-        DevBuf *bufs[] = {&L.scan, &L.words,    &L.seg_bit,    &L.tile_kept,  &L.tile_rst, &L.state,
+        DevBuf *bufs[] = {&L.cls,  &L.scan, &L.words,    &L.seg_bit,    &L.tile_kept,  &L.tile_rst, &L.state,
                           &L.work, &L.seg_hint, &L.start_slot, &L.scan_tiles, &L.coef,     &L.dcdiff,
                           &L.dc,   &L.tile_carry, &L.pixels,   &L.meta,       &L.tie_rec,  &L.overflow,
                           &L.rec,  &L.nrec,       &L.rec_alt};

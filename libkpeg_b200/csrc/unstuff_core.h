@@ -89,5 +89,56 @@ KPEG_HD ByteClass classify16(const uint8_t *scan, uint32_t len, uint32_t base)
     return c;
 }
 
+// ---- the same classification, sixteen bytes at a time ------------------------------------------------
+// Byte-parallel form for a chunk that lies entirely inside the segment; b[] holds the bytes little-endian
+// (byte i = b[i >> 2] >> 8 * (i & 3)), prev / next are the bytes on either side (next = 0xFF past the end).
+// Masks carry 0x80 in the byte lanes where a predicate holds.
+KPEG_HD uint32_t swar_zero_bytes(uint32_t v) // exact: 0x80 where the byte is 0
+{
+    return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v | 0x7F7F7F7Fu);
+}
+
+KPEG_HD uint32_t swar_nibble(uint32_t m) // 0x80-per-byte mask -> 4 bits, byte 0 in bit 0
+{
+    return (((m >> 7) * 0x00204081u) >> 21) & 0xFu;
+}
+
+KPEG_HD void classify16_swar(const uint32_t b[4], uint32_t prev, uint32_t next, uint32_t &keep, uint32_t &rst, uint32_t &bad)
+{
+    uint32_t ff[4], zz[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        ff[w] = swar_zero_bytes(~b[w]);
+        zz[w] = swar_zero_bytes(b[w]);
+    }
+    keep = 0;
+    rst = 0;
+    bad = 0;
+    uint32_t second = 0; // bytes that follow an FF and are neither 00 nor FF: the second byte of a marker
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t fprev = (ff[w] << 8) | (w ? ff[w - 1] >> 24 : (prev == 0xFFu ? 0x80u : 0u));
+        const uint32_t znext = (zz[w] >> 8) | (w < 3 ? zz[w + 1] << 24 : (next == 0x00u ? 0x80000000u : 0u));
+        // an FF survives iff a stuffed 00 follows; any other byte survives iff it does not follow an FF
+        const uint32_t k = (ff[w] & znext) | (~ff[w] & ~fprev & 0x80808080u);
+        keep |= swar_nibble(k) << (4 * w);
+        second |= ~ff[w] & ~zz[w] & fprev;
+    }
+    if (second) { // rare: markers
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t fprev = (ff[w] << 8) | (w ? ff[w - 1] >> 24 : (prev == 0xFFu ? 0x80u : 0u));
+            const uint32_t sec = ~ff[w] & ~zz[w] & fprev;
+            const uint32_t d0d7 = swar_zero_bytes((b[w] & 0xF8F8F8F8u) ^ 0xD0D0D0D0u);
+            const uint32_t d9 = swar_zero_bytes(b[w] ^ 0xD9D9D9D9u);
+            rst |= swar_nibble(sec & d0d7) << (4 * w);
+            bad |= sec & ~d0d7 & ~d9;
+        }
+    }
+    // (an unexpected marker is flagged where its second byte lies; classify16 flags it at the FF -- the
+    // status word is the OR over all chunks either way)
+    bad = bad ? 1u : 0u;
+}
+
 } // namespace kpeg
 #endif

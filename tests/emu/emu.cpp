@@ -373,4 +373,28 @@ uint32_t emu_huff_lookup(const uint8_t counts[16], const uint8_t *symbols, int i
 
 int emu_zigzag(int i) { return zigzag_to_natural(i); }
 
+// Byte-parallel classification (classify16_swar) against the byte-wise one (classify16) on every whole
+// 16-byte chunk of a buffer: returns the number of chunks whose keep / RSTn masks differ, *bad_differs says
+// whether the "unexpected marker" verdict over the whole buffer differs.
+uint32_t emu_classify_compare(const uint8_t *scan, uint32_t len, int *bad_differs)
+{
+    uint32_t mismatches = 0, bad_ref = 0, bad_swar = 0;
+    for (uint32_t base = 0; base + 16u <= len; base += 16u) {
+        const ByteClass c = classify16(scan, len, base);
+        uint32_t b[4];
+        memcpy(b, scan + base, 16);
+        const uint32_t prev = base ? scan[base - 1] : 0u;
+        const uint32_t next = base + 16u < len ? scan[base + 16] : 0xFFu;
+        uint32_t keep, rst, bad;
+        classify16_swar(b, prev, next, keep, rst, bad);
+        if (keep != c.keep || rst != c.rst)
+            ++mismatches;
+        bad_ref |= c.bad;
+        bad_swar |= bad;
+    }
+    if (bad_differs)
+        *bad_differs = (bad_ref != 0) != (bad_swar != 0);
+    return mismatches;
+}
+
 } // extern "C"

@@ -129,6 +129,8 @@ def emu():
         lib.emu_colour.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.emu_idct_fast.restype = C.c_float
         lib.emu_idct_fast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.emu_classify_compare.restype = C.c_uint32
+        lib.emu_classify_compare.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_int)]
         lib.emu_huff_lookup.restype = C.c_uint32
         lib.emu_huff_lookup.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_int]
         lib.emu_zigzag.restype = C.c_int

@@ -158,3 +158,24 @@ def test_colour_rb_integer_points():
             emu.emu_colour(y, d, d, got)
             orc.kpo_ycbcr_to_rgb(y + 128, d + 128, d + 128, want)
             assert list(got) == list(want)
+
+
+def test_byte_parallel_unstuff_classification_matches_bytewise():
+    """K0's sixteen-bytes-at-a-time classification (classify16_swar, what the count kernel runs) against the
+    byte-wise classify16 on adversarial byte soup: dense FF / 00 / RSTn / fill / stray markers, chunk-edge cases."""
+    import ctypes as C
+    lib = H.emu()
+    rng = np.random.default_rng(0xFF00)
+    alphabet = np.array([0xFF, 0xFF, 0xFF, 0x00, 0x00, 0xD0, 0xD3, 0xD7, 0xD9, 0xC4, 0x01, 0x7F, 0x80, 0xFE, 0xD8, 0xCF],
+                        dtype=np.uint8)
+    for trial in range(40):
+        n = int(rng.integers(16, 4096))
+        if trial % 3 == 0:
+            buf = rng.integers(0, 256, size=n, dtype=np.uint8)          # FF is rare
+        else:
+            buf = alphabet[rng.integers(0, alphabet.size, size=n)]      # FF / 00 / markers everywhere
+        buf = np.ascontiguousarray(buf)
+        bad = C.c_int(0)
+        mism = lib.emu_classify_compare(buf.ctypes.data, n, C.byref(bad))
+        assert mism == 0, f"trial {trial}: {mism} chunks classified differently"
+        assert bad.value == 0, f"trial {trial}: unexpected-marker verdict differs"
