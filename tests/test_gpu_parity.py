@@ -301,3 +301,34 @@ def test_deferred_submissions_overlap_and_report_errors(decoder):
     for d_in, d_out, _ in bufs:
         decoder.device_free(d_in)
         decoder.device_free(d_out)
+
+
+def test_split_batch_unaligned_parts(decoder):
+    """kpeg_cuda_decode_batch_packed_device_split: the parts start at arbitrary byte offsets of the packed stream,
+    so K0 runs on unaligned device pointers (its byte-wise classification path) next to aligned ones."""
+    from libkpeg_b200.api import pack_batch, packed_offsets
+    nb, w, h = 7, 136, 72
+    jpgs = [synth_encode(SynthParams(w, h, quality=91, restart_interval=3 if i % 2 else 0,
+                                     flags=QUIRK_FREE | (EMIT_RESTART if i % 2 else 0), seed=4000 + i)) for i in range(nb)]
+    # same plan for all: restart interval is part of the plan, so use the no-restart images only for the batch
+    jpgs = [j for i, j in enumerate(jpgs) if i % 2 == 0]
+    nb = len(jpgs)
+    parsed = [K.parse_jfif(j) for j in jpgs]
+    plan = parsed[0][0]
+    plan.flags = K.KPEG_FLAG_REF_PARITY
+    scans = [j[o:o + n] for j, (_, o, n) in zip(jpgs, parsed)]
+    packed = pack_batch(scans)
+    off = packed_offsets(scans)
+    assert any(int(o) % 16 for o in off[1:-1]), "offsets happen to be aligned: the test would not exercise the unaligned path"
+    npix = w * h * 3
+    d_in = decoder.device_alloc(packed.size + 64)
+    d_out = decoder.device_alloc(nb * npix + 64)
+    decoder.h2d(d_in, packed)
+    decoder.decode_batch_packed_device_split(plan, nb, d_in, off, d_out)
+    got = np.empty(nb * npix, dtype=np.uint8)
+    decoder.d2h(got, d_out)
+    for i, j in enumerate(jpgs):
+        ref = H.oracle_decode(j.tobytes())["pixels"]
+        assert np.array_equal(got[i * npix:(i + 1) * npix].reshape(h, w, 3), ref), f"image {i}"
+    decoder.device_free(d_in)
+    decoder.device_free(d_out)
