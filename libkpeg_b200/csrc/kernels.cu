@@ -80,29 +80,46 @@ __global__ void __launch_bounds__(UNSTUFF_THREADS) unstuff_count_kernel(UnstuffA
 {
     __shared__ uint32_t s_w[UNSTUFF_THREADS / 32 + 1];
     const uint32_t chunk = blockIdx.x * UNSTUFF_THREADS + threadIdx.x;
-    const uint32_t base = chunk * UNSTUFF_BYTES_PER_THREAD;
+    // chunks are cut on 16-byte ADDRESS boundaries: chunk c covers stream bytes [16c - mis, 16c - mis + 16), so
+    // that a segment that starts anywhere (a part of a packed batch) is still read with aligned 16-byte loads
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(a.scan) & 15u);
+    const int32_t start = (int32_t)(chunk * UNSTUFF_BYTES_PER_THREAD) - (int32_t)mis; // segments are < 2^29 bytes
     const int lane = threadIdx.x & 31;
     uint32_t keep = 0, rst = 0, bad = 0;
-    const bool aligned = (reinterpret_cast<uintptr_t>(a.scan) & 15u) == 0;
-    const bool whole = aligned && base + 16u <= a.scan_len; // warp-uniform except in the last warp of the stream
+    const bool whole = start >= 0 && start + 16 <= (int32_t)a.scan_len; // not whole: first / last chunk, or beyond the end
+    const bool some = start + 16 > 0 && start < (int32_t)a.scan_len;
     uint32_t b[4] = {0, 0, 0, 0};
-    if (whole)
-        ld_16bytes(a.scan + base, b);
+    uint32_t in_range = 0xFFFFu;
+    if (whole) {
+        ld_16bytes(a.scan + start, b);
+    } else if (some) {
+        // ragged first / last chunk: bytes before the stream read as 00 (no effect on what follows), bytes after
+        // it as FF (what classify16 assumes past the end); only the bits of real bytes count
+        in_range = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int32_t at = start + i;
+            uint32_t v = at < 0 ? 0x00u : 0xFFu;
+            if (at >= 0 && at < (int32_t)a.scan_len) {
+                v = ld_byte(a.scan + at);
+                in_range |= 1u << i;
+            }
+            b[i >> 2] |= v << (8 * (i & 3));
+        }
+    }
     // bytes on either side of the chunk: from the neighbouring lanes, from memory at the warp's edges
     uint32_t prev = __shfl_up_sync(0xffffffffu, b[3] >> 24, 1);
     uint32_t next = __shfl_down_sync(0xffffffffu, b[0] & 0xFFu, 1);
-    const bool next_whole = __shfl_down_sync(0xffffffffu, whole ? 1 : 0, 1) != 0;
-    if (whole) {
+    if (__shfl_down_sync(0xffffffffu, some ? 1 : 0, 1) == 0)
+        next = 0xFFu; // the next chunk lies past the end
+    if (some) {
         if (lane == 0)
-            prev = base ? (uint32_t)ld_byte(a.scan + base - 1) : 0u;
-        if (lane == 31 || !next_whole)
-            next = base + 16u < a.scan_len ? (uint32_t)ld_byte(a.scan + base + 16) : 0xFFu;
+            prev = start > 0 ? (uint32_t)ld_byte(a.scan + start - 1) : 0u;
+        if (lane == 31)
+            next = start + 16 < (int32_t)a.scan_len ? (uint32_t)ld_byte(a.scan + start + 16) : 0xFFu;
         classify16_swar(b, prev, next, keep, rst, bad);
-    } else if (base < a.scan_len) {
-        const ByteClass c = classify16(a.scan, a.scan_len, base); // the stream's ragged tail (or an unaligned buffer)
-        keep = c.keep;
-        rst = c.rst;
-        bad = c.bad;
+        keep &= in_range;
+        rst &= in_range;
     }
     a.cls[chunk] = keep | (rst << 16);
     // pack both counts into one reduction: kept <= 4096 per tile, rst <= 2048
@@ -178,7 +195,8 @@ __global__ void __launch_bounds__(UNSTUFF_THREADS) unstuff_write_kernel(UnstuffA
     __shared__ uint32_t s_w[UNSTUFF_THREADS / 32 + 1];
     __shared__ __align__(16) uint8_t s_out[UNSTUFF_TILE + 16];
     const uint32_t chunk = blockIdx.x * UNSTUFF_THREADS + threadIdx.x;
-    const uint32_t base = chunk * UNSTUFF_BYTES_PER_THREAD;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(a.scan) & 15u); // chunks as in the count kernel
+    const int32_t start = (int32_t)(chunk * UNSTUFF_BYTES_PER_THREAD) - (int32_t)mis; // segments are < 2^29 bytes
     reinterpret_cast<uint4 *>(s_out)[threadIdx.x] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0)
         reinterpret_cast<uint4 *>(s_out)[UNSTUFF_THREADS] = make_uint4(0, 0, 0, 0);
@@ -187,13 +205,13 @@ __global__ void __launch_bounds__(UNSTUFF_THREADS) unstuff_write_kernel(UnstuffA
     const uint32_t rst = cls >> 16;
     uint32_t b[4] = {0, 0, 0, 0};
     if (keep) {
-        if (base + 16u <= a.scan_len && (reinterpret_cast<uintptr_t>(a.scan) & 15u) == 0) {
-            ld_16bytes(a.scan + base, b);
+        if (start >= 0 && start + 16 <= (int32_t)a.scan_len) {
+            ld_16bytes(a.scan + start, b);
         } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-                if (base + i < a.scan_len)
-                    b[i >> 2] |= (uint32_t)ld_byte(a.scan + base + i) << (8 * (i & 3));
+                if (start + i >= 0 && start + i < (int32_t)a.scan_len)
+                    b[i >> 2] |= (uint32_t)ld_byte(a.scan + start + i) << (8 * (i & 3));
         }
     }
     const uint32_t n = __popc(keep);

@@ -325,7 +325,7 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     TRY(upload_plan(ctx, pl));
 
     const uint32_t S = (uint32_t)scan_len;
-    const uint32_t ntiles = (S + UNSTUFF_TILE - 1) / UNSTUFF_TILE;
+    const uint32_t ntiles = (S + 15u + UNSTUFF_TILE - 1) / UNSTUFF_TILE; // + 15: chunks are cut on address boundaries
     const uint32_t nsub_max = (uint32_t)(((uint64_t)S * 8u + g.sub_bits - 1u) / g.sub_bits) + 1u;
     const uint32_t total_mcus = g.nimages * g.mcus_per_image;
     const uint32_t dc_tiles = (total_mcus + DC_TILE - 1) / DC_TILE;
