@@ -673,9 +673,6 @@ __global__ void __launch_bounds__(ENTROPY_THREADS, 8) entropy_relay_loop_kernel(
     const uint32_t total_words = ((total_bits + 31u) >> 5) + 4u;
     uint32_t generation = 0;
     int round = first;
-#ifdef KPEG_RELAY_DEBUG
-    const long long t_start = clock64();
-#endif
     // A round whose list fits one CTA is run by CTA 0 alone (the others leave): the tail rounds then cost a
     // __syncthreads() each instead of a grid barrier.
     constexpr uint32_t SOLO_ITEMS = ENTROPY_THREADS;
@@ -698,9 +695,6 @@ __global__ void __launch_bounds__(ENTROPY_THREADS, 8) entropy_relay_loop_kernel(
             const uint32_t sub = __ldcg(list_in + w);
             if (sub >= nsub)
                 continue;
-#ifdef KPEG_RELAY_DEBUG
-            const long long t_item = clock64();
-#endif
             const uint4 inraw = __ldcg(reinterpret_cast<const uint4 *>(&a.state[sub - 1]));
             const uint32_t j0 = inraw.x >> 5;
             for (uint32_t k = 0; k < stride - 1u; ++k)
@@ -709,29 +703,13 @@ __global__ void __launch_bounds__(ENTROPY_THREADS, 8) entropy_relay_loop_kernel(
             const uint32_t end = min((sub + 1u) << (wlog + 5u), total_bits);
             const SubState out = relay_decode(a, W, L, S, sub, end, inraw.x, inraw.z, true);
             relay_publish(a, sub, out, nsub, list_out, count_out);
-#ifdef KPEG_RELAY_DEBUG
-            atomicMax(&a.meta->dbg[16], (uint32_t)(clock64() - t_item));
-            atomicMax(&a.meta->dbg[17], end - inraw.x);
-#endif
         }
-#ifdef KPEG_RELAY_DEBUG
-        const long long t_b0 = clock64();
-#endif
         if (solo) {
             __threadfence();
             __syncthreads();
         } else {
             grid_barrier(&a.meta->grid_bar, generation);
         }
-#ifdef KPEG_RELAY_DEBUG
-        if (threadIdx.x == 0) {
-            atomicMax(&a.meta->dbg[18], (uint32_t)(clock64() - t_b0));
-            if (blockIdx.x == 0 && round - first < 8) {
-                a.meta->dbg[round - first] = (uint32_t)(clock64() - t_start);
-                a.meta->dbg[8 + round - first] = count;
-            }
-        }
-#endif
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
         a.meta->relay_rounds = (uint32_t)(round <= last ? round - 1 : last);

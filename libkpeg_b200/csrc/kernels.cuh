@@ -30,7 +30,6 @@ struct DevMeta {
     uint32_t relay_rounds; // last relay round that ran (device-side round loop)
     uint32_t grid_bar;     // arrival counter of the relay loop's grid barrier
     uint32_t rec_alt_count; // private record areas handed out by the sparse relay rounds
-    uint32_t dbg[24];      // scratch for experiments (KPEG_DEBUG_META=1 prints it)
     uint32_t changed[MAX_RELAY_ROUNDS];
 };
 

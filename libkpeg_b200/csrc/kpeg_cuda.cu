@@ -519,12 +519,6 @@ int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
                     used_rounds = (uint32_t)r;
         }
         stats->sync_rounds = std::max(stats->sync_rounds, used_rounds);
-        if (getenv("KPEG_DEBUG_META")) {
-            fprintf(stderr, "kpeg dbg:");
-            for (int i = 0; i < 24; ++i)
-                fprintf(stderr, " %u", h_meta->dbg[i]);
-            fprintf(stderr, " alt=%u\n", h_meta->rec_alt_count);
-        }
         stats->exact_samples += h_meta->tie_records; // pixels with at least one sample on the exact path
         stats->kernel_launches += J.launches;
         add_times(ctx, L, stats);
