@@ -332,3 +332,58 @@ def test_split_batch_unaligned_parts(decoder):
         assert np.array_equal(got[i * npix:(i + 1) * npix].reshape(h, w, 3), ref), f"image {i}"
     decoder.device_free(d_in)
     decoder.device_free(d_out)
+
+
+def test_config3_full_size_gray_batch(decoder):
+    """BASELINE config 3 at full size: a batch of 4096 512x512 one-component JPEGs in one call (256 distinct
+    images, each 16 times, to keep the encoder out of the way).  Properties: every replica decodes to the
+    same bytes wherever it sits in the batch; a sample equals the oracle bit for bit."""
+    distinct, copies, w, h = 256, 16, 512, 512
+    jpgs = [synth_encode(SynthParams(w, h, file_components=1, quality=90, flags=QUIRK_FREE | GRAY_CONTENT, seed=0xC3 + i))
+            for i in range(distinct)]
+    parsed = [K.parse_jfif(j) for j in jpgs]
+    plan = parsed[0][0]
+    plan.flags = K.KPEG_FLAG_REF_PARITY
+    scans1 = [j[o:o + n] for j, (_, o, n) in zip(jpgs, parsed)]
+    scans = [scans1[i % distinct] for i in range(distinct * copies)]
+    outs = decoder.decode_batch(plan, scans)
+    assert len(outs) == 4096
+    for i in range(distinct, len(outs)):
+        assert np.array_equal(outs[i], outs[i % distinct]), f"replica {i} differs from image {i % distinct}"
+    for i in (0, 1, 77, 128, 255):
+        assert np.array_equal(outs[i], H.oracle_decode(jpgs[i].tobytes())["pixels"]), f"image {i} vs oracle"
+    print(f"config 3: 4096 x 512x512 gray, {decoder.last_stats.kernel_launches} kernel launches")
+
+
+def _band_as_jpeg(jpg: np.ndarray, scan_off: int, band) -> bytes:
+    """A restart band is a complete image of the same width and tables: same header with the band's height."""
+    head = bytearray(jpg[:scan_off].tobytes())
+    i = head.find(b"\xff\xc0")
+    assert i > 0
+    head[i + 5:i + 7] = int(band.rows).to_bytes(2, "big")
+    return bytes(head) + band.scan.tobytes() + b"\xff\xd9"
+
+
+def test_config4_full_size_restart_bands(decoder):
+    """BASELINE config 4 at full size: 16384x16384 RGB, one restart interval per MCU row.  The image decoded
+    whole equals the image decoded as 8 independent bands (what 8 GPUs would each do), and narrow bands equal
+    the oracle's decode of the same band (the oracle finishes 16384x64 in about a second)."""
+    from libkpeg_b200.shard import split_restart_bands
+    w = h = 16384
+    jpg = synth_encode(SynthParams(w, h, quality=90, restart_interval=w // 8, flags=QUIRK_FREE | EMIT_RESTART, seed=0xC4))
+    plan, off, n = K.parse_jfif(jpg)
+    plan.flags = K.KPEG_FLAG_REF_PARITY
+    scan = jpg[off:off + n]
+    whole = decoder.decode_scan(plan, scan)
+    assert whole.shape == (h, w, 3)
+    st = decoder.last_stats
+    print(f"config 4: scan {st.scan_bytes} B, {st.segments} segments, {st.subsequences} subsequences, {st.sync_rounds} relay rounds")
+    bands = split_restart_bands(plan, scan, 8)
+    assert sum(b.rows for b in bands) == h
+    for b in bands:
+        got = decoder.decode_scan(b.plan, b.scan)
+        assert np.array_equal(got, whole[b.row0:b.row0 + b.rows]), f"band at row {b.row0}"
+    narrow = split_restart_bands(plan, scan, 256)
+    for b in (narrow[0], narrow[101], narrow[255]):
+        ref = H.oracle_decode(_band_as_jpeg(jpg, off, b))["pixels"]
+        assert np.array_equal(ref, whole[b.row0:b.row0 + b.rows]), f"narrow band at row {b.row0} vs oracle"
