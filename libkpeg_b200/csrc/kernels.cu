@@ -1032,7 +1032,7 @@ __global__ void __launch_bounds__(WRITE_THREADS) entropy_write_kernel(EntropyArg
 struct GlobalRecAt {
     const uint32_t *base;
     uint32_t stride;
-    __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return __ldg(base + (size_t)k * stride); }
+    __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return __ldg(base + k * stride); }
 };
 
 __global__ void __launch_bounds__(WRITE_THREADS) entropy_expand_kernel(EntropyArgs a)
