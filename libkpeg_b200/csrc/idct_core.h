@@ -93,6 +93,15 @@ KPEG_HD constexpr ZigZagTables make_zigzag_tables()
 }
 
 // AAN prescale factors: s[0] = 1, s[k] = sqrt(2) * cos(k*pi/16).
+KPEG_HD constexpr double aan_scale_c(int k)
+{
+    return k == 0 ? 1.0 : k == 1 ? 1.387039845322148 : k == 2 ? 1.306562964876377 : k == 3 ? 1.175875602419359
+         : k == 4 ? 1.0 : k == 5 ? 0.785694958387102 : k == 6 ? 0.541196100146197 : 0.275899379282943;
+}
+
+// 1 / (prescale of the coefficient at natural index nat): |prescaled dequantised coefficient| * this = |c| * q
+KPEG_HD constexpr float aan_unscale(int nat) { return (float)(8.0 / (aan_scale_c(nat >> 3) * aan_scale_c(nat & 7))); }
+
 inline double aan_scale(int k)
 {
     const double s[8] = {1.0, 1.387039845322148, 1.306562964876377, 1.175875602419359,

@@ -1441,7 +1441,6 @@ struct IdctSmem {
         float4 samp[NC * 8 * 2 * NM]; // [comp][row][half][mcu] -> 4 samples (rounded, unshifted)
     };
     float qscale[NC][64];
-    uint32_t qbytes[NC][16];      // the 8-bit quantisers, zig-zag order, four per word (for dp2a)
     uint2 tie[NB];                // per block: 64-bit mask of the samples inside the tie band
     uint2 rec[IDCT_REC_CAP];      // tie records of this strip (compact form), flushed to the global list with ONE atomic
     uint32_t nrec, rec_base;
@@ -1456,11 +1455,19 @@ __device__ __forceinline__ float chunk_coef(const uint4 (&ch)[8])
     return (float)(short)(hi ? (w >> 16) : (w & 0xFFFFu));
 }
 
+// Dequantise (AAN prescale folded into q) and de-zigzag by register renaming; on the way, A = sum |c_i| * q_i,
+// the magnitude the tie band is proportional to: |f| * (1 / prescale) with the reciprocal an immediate and the
+// absolute value a free operand modifier -- one FFMA per coefficient.  (fp32 accumulation is off by < 1e-5
+// relative; the band carries a 10 % margin.)
 template <int... Is>
-__device__ __forceinline__ void dequant_dezigzag(const uint4 (&ch)[8], const float *q, float (&f)[64],
-                                                 std::integer_sequence<int, Is...>)
+__device__ __forceinline__ float dequant_dezigzag(const uint4 (&ch)[8], const float *q, float (&f)[64],
+                                                  std::integer_sequence<int, Is...>)
 {
-    ((f[ZzNat<Is>::value] = chunk_coef<Is>(ch) * q[Is]), ...);
+    float A = 0.0f;
+    (((f[ZzNat<Is>::value] = chunk_coef<Is>(ch) * q[Is]),
+      (A = fmaf(fabsf(f[ZzNat<Is>::value]), aan_unscale(ZzNat<Is>::value), A))),
+     ...);
+    return A;
 }
 
 // Four ints -> four bytes with unsigned saturation (cvt.pack.sat: two values per instruction).
@@ -1653,10 +1660,6 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? 8 : 16) idct
     // ---- stage 0: quantiser + coefficients -> shared memory (coalesced 16-byte loads) ---------------
     for (int i = t; i < NC * 64; i += NB)
         (&sm.qscale[0][0])[i] = a.tables->qscale[0][i];
-    for (int i = t; i < NC * 16; i += NB) {
-        const int32_t *q = &a.tables->qint[0][0] + i * 4;
-        (&sm.qbytes[0][0])[i] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
-    }
     if (t == 0)
         sm.nrec = 0;
     {
@@ -1692,22 +1695,9 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? 8 : 16) idct
         // the entropy stage leaves slot 0 empty; the integrated DC value comes from K2
         ch[0].x = (ch[0].x & 0xFFFF0000u) | ((uint32_t)dcv & 0xFFFFu);
 
-        // A = sum |c_i| * q_i, exactly: SIMD abs on the int16 pairs, 16x8-bit dot product against the quantisers
-        uint32_t A = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t w[4] = {ch[k].x, ch[k].y, ch[k].z, ch[k].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t qb = sm.qbytes[comp][k * 2 + (j >> 1)];
-                const uint32_t aw = __vabsss2(w[j]);
-                A = (j & 1) ? __dp2a_hi(aw, qb, A) : __dp2a_lo(aw, qb, A);
-            }
-        }
-        const float thresh = 0.5f - tie_band((float)A);
-
         float f[64];
-        dequant_dezigzag(ch, sm.qscale[comp], f, std::make_integer_sequence<int, 64>{});
+        const float A = dequant_dezigzag(ch, sm.qscale[comp], f, std::make_integer_sequence<int, 64>{});
+        const float thresh = 0.5f - tie_band(A);
         idct8x8_fast(f);
 
         // (x + 1.5*2^23) - 1.5*2^23 == rint(x) for |x| < 2^22; samples inside the tie band are
