@@ -387,3 +387,27 @@ def test_config4_full_size_restart_bands(decoder):
     for b in (narrow[0], narrow[101], narrow[255]):
         ref = H.oracle_decode(_band_as_jpeg(jpg, off, b))["pixels"]
         assert np.array_equal(ref, whole[b.row0:b.row0 + b.rows]), f"narrow band at row {b.row0} vs oracle"
+
+
+def test_random_streams_on_the_gpu(decoder):
+    """Seeded sweep over sizes (ragged included), qualities 5..100, restart intervals, one / three components and
+    subsequence sizes: coefficients and pixels equal the oracle bit for bit.  Non-QUIRK_FREE streams exercise the
+    reference's DC-difference quirk as well."""
+    rng = np.random.default_rng(0x6B706567)
+    try:
+        for trial in range(60):
+            w, h = int(rng.integers(1, 200)), int(rng.integers(1, 120))
+            q = int(rng.integers(5, 101))
+            ri = int(rng.integers(0, 12))
+            nc = int(rng.choice([1, 3]))
+            sb = int(rng.choice([64, 128, 256, 512, 1024]))
+            flags = (QUIRK_FREE if trial % 4 else 0) | (EMIT_RESTART if ri else 0) | (GRAY_CONTENT if nc == 1 else 0)
+            jpg = synth_encode(SynthParams(w, h, file_components=nc, quality=q, restart_interval=ri, flags=flags,
+                                           seed=int(rng.integers(0, 2 ** 31)), noise_amp=int(rng.integers(1, 61)))).tobytes()
+            decoder.set_tuning(sub_bits=sb)
+            try:
+                check_against_oracle(decoder, jpg, parity=bool(trial % 3))
+            except AssertionError as e:
+                raise AssertionError(f"trial {trial}: {w}x{h} q{q} ri{ri} nc{nc} sub_bits {sb}: {e}") from e
+    finally:
+        decoder.set_tuning(sub_bits=512)
