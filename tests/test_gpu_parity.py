@@ -411,3 +411,29 @@ def test_random_streams_on_the_gpu(decoder):
                 raise AssertionError(f"trial {trial}: {w}x{h} q{q} ri{ri} nc{nc} sub_bits {sb}: {e}") from e
     finally:
         decoder.set_tuning(sub_bits=512)
+
+
+def test_pil_encoded_files_with_optimised_tables(decoder):
+    """Files from another encoder (libjpeg via PIL, 4:4:4): standard and per-image OPTIMISED Huffman tables (code
+    lengths up to 16, symbols in another order, tables shared between components or not), comment segments, natural
+    and synthetic content, low and high quality.  Coefficients and pixels equal the oracle bit for bit."""
+    PIL = pytest.importorskip("PIL.Image")
+    import io
+    from PIL import ImageFile
+    ImageFile.MAXBLOCK = max(ImageFile.MAXBLOCK, 1 << 22)  # optimised tables need the whole image in one output block
+    rng = np.random.default_rng(77)
+    yy, xx = np.mgrid[0:208, 0:312]
+    smooth = np.stack([128 + 90 * np.sin(xx / 23.0) * np.cos(yy / 31.0), 128 + 100 * np.sin((xx + yy) / 17.0),
+                       255 * ((xx // 24 + yy // 24) % 2)], axis=-1)
+    noisy = np.clip(smooth + rng.normal(0, 25, smooth.shape), 0, 255)
+    lena = np.asarray(PIL.open(ROOT / "tests" / "golden" / "lena.jpg").convert("RGB"))[100:308, 60:372]
+    for name, arr in (("smooth", smooth), ("noisy", noisy), ("lena-crop", lena)):
+        img = PIL.fromarray(arr.astype(np.uint8), "RGB")
+        for kw in (dict(quality=30, optimize=True), dict(quality=75, optimize=True, comment=b"kpeg test"),
+                   dict(quality=97, optimize=True), dict(quality=88, optimize=False), dict(quality=100, optimize=True)):
+            buf = io.BytesIO()
+            img.save(buf, "JPEG", subsampling=0, **kw)
+            try:
+                check_against_oracle(decoder, buf.getvalue())
+            except AssertionError as e:
+                raise AssertionError(f"{name} {kw}: {e}") from e
