@@ -30,9 +30,15 @@ using namespace kpeg;
 namespace {
 
 struct DevBuf {
-    void *p = nullptr;
+    void *p = nullptr;   // what the kernels get
     size_t cap = 0;
+    void *raw = nullptr; // the allocation (== p, or p - GUARD_BYTES in guard mode)
 };
+
+// KPEG_GUARD=1 (debugging aid; the pool this was developed on has no compute-sanitizer): every device buffer is
+// allocated at exactly the size asked for, between two guard areas of a known byte, which are checked after each job.
+constexpr size_t GUARD_BYTES = 256;
+constexpr int GUARD_PATTERN = 0xA5;
 
 struct PinBuf {
     void *p = nullptr;
@@ -100,6 +106,7 @@ struct kpeg_ctx {
     // deferred submissions (kpeg_cuda_submit_* / kpeg_cuda_wait): lanes are handed out round-robin and a
     // lane's previous job is finished only when the lane comes up again, so several batches are in flight
     bool counted = false; // registered with kernels_context_created
+    bool guard = false;   // KPEG_GUARD=1
     bool plan_fits_records = true;
     int next_lane = 0;
     int deferred_rc = KPEG_OK;
@@ -135,21 +142,34 @@ int fail(kpeg_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
             return rc_;                                                                                                \
     } while (0)
 
+void dev_free(DevBuf &b)
+{
+    if (b.raw)
+        cudaFree(b.raw);
+    b.raw = b.p = nullptr;
+    b.cap = 0;
+}
+
 int ensure(kpeg_ctx *ctx, cudaStream_t stream, DevBuf &b, size_t bytes)
 {
     if (bytes <= b.cap)
         return KPEG_OK;
-    if (b.p) {
+    if (b.raw) {
         CK(cudaStreamSynchronize(stream));
-        CK(cudaFree(b.p));
-        b.p = nullptr;
-        b.cap = 0;
+        dev_free(b);
     }
-    const size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&b.p, want);
+    const bool guard = ctx->guard;
+    const size_t want = guard ? ((bytes + 15u) & ~(size_t)15u) : bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.raw, want + (guard ? 2 * GUARD_BYTES : 0));
     if (e != cudaSuccess) {
-        b.p = nullptr;
+        b.raw = nullptr;
         return fail(ctx, KPEG_ERR_NOMEM, "cudaMalloc", e);
+    }
+    b.p = b.raw;
+    if (guard) {
+        b.p = (uint8_t *)b.raw + GUARD_BYTES;
+        CK(cudaMemsetAsync(b.raw, GUARD_PATTERN, GUARD_BYTES, stream));
+        CK(cudaMemsetAsync((uint8_t *)b.p + want, GUARD_PATTERN, GUARD_BYTES, stream));
     }
     b.cap = want;
     return KPEG_OK;
@@ -443,6 +463,38 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     return enqueue_downstream(ctx, L);
 }
 
+struct NamedBuf {
+    const char *name;
+    DevBuf *buf;
+};
+
+// guard mode: the bytes on either side of every device buffer of the lane must still hold the pattern
+int check_guards(kpeg_ctx *ctx, Lane &L)
+{
+    NamedBuf bufs[] = {{"cls", &L.cls},           {"scan", &L.scan},         {"words", &L.words},       {"seg_bit", &L.seg_bit},
+                       {"tile_kept", &L.tile_kept}, {"tile_rst", &L.tile_rst}, {"state", &L.state},       {"work", &L.work},
+                       {"seg_hint", &L.seg_hint}, {"start_slot", &L.start_slot}, {"scan_tiles", &L.scan_tiles},
+                       {"coef", &L.coef},         {"dcdiff", &L.dcdiff},     {"dc", &L.dc},             {"tile_carry", &L.tile_carry},
+                       {"pixels", &L.pixels},     {"meta", &L.meta},         {"tie_rec", &L.tie_rec},   {"overflow", &L.overflow},
+                       {"rec", &L.rec},           {"nrec", &L.nrec},         {"rec_alt", &L.rec_alt},   {"tables", &ctx->tables}};
+    uint8_t host[2 * GUARD_BYTES];
+    for (const NamedBuf &nb : bufs) {
+        const DevBuf &b = *nb.buf;
+        if (!b.raw || b.raw == b.p)
+            continue;
+        CK(cudaMemcpy(host, b.raw, GUARD_BYTES, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(host + GUARD_BYTES, (const uint8_t *)b.p + b.cap, GUARD_BYTES, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < 2 * GUARD_BYTES; ++i)
+            if (host[i] != (uint8_t)GUARD_PATTERN) {
+                char msg[160];
+                snprintf(msg, sizeof msg, "guard bytes %s device buffer '%s' (%zu bytes) were overwritten at offset %zu",
+                         i < GUARD_BYTES ? "before" : "after", nb.name, b.cap, i % GUARD_BYTES);
+                return fail(ctx, KPEG_ERR_CUDA, msg);
+            }
+    }
+    return KPEG_OK;
+}
+
 // Wait for the job, check the device status word and -- rarely -- run more relay rounds and redo the
 // downstream stages.  Adds the job's figures to *stats (which the caller zeroed).
 int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
@@ -501,6 +553,8 @@ int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
                            ((size_t)(J.g.nimages * J.g.mcus_per_image) / IDCT_MCUS_PER_CTA + 2u) * sizeof(uint32_t), s));
         TRY(enqueue_downstream(ctx, L));
     }
+    if (ctx->guard)
+        TRY(check_guards(ctx, L));
     ctx->last_lane = li;
     ctx->last_g = J.g;
     if (stats) {
@@ -582,6 +636,8 @@ extern "C" int kpeg_cuda_create(int device, kpeg_ctx **out)
     }
     if (const char *nr = getenv("KPEG_NO_RECORDS"))
         ctx->use_records = !(nr[0] == '1');
+    if (const char *e = getenv("KPEG_GUARD"))
+        ctx->guard = e[0] == '1';
     if (const char *e = getenv("KPEG_SPLIT"))
         ctx->split_parts = std::max(1, std::min(NLANES, atoi(e)));
     if (const char *e = getenv("KPEG_SUBMIT_SPLIT"))
@@ -626,8 +682,7 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
                           &L.dc,   &L.tile_carry, &L.pixels,   &L.meta,       &L.tie_rec,  &L.overflow,
                           &L.rec,  &L.nrec,       &L.rec_alt};
         for (DevBuf *b : bufs)
-            if (b->p)
-                cudaFree(b->p);
+            dev_free(*b);
         if (L.h_meta.p)
             cudaFreeHost(L.h_meta.p);
         for (int i = 0; i < MAX_EVENTS; ++i)
@@ -636,10 +691,8 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
         if (L.stream)
             cudaStreamDestroy(L.stream);
     }
-    if (ctx->tables.p)
-        cudaFree(ctx->tables.p);
-    if (ctx->merged.p)
-        cudaFree(ctx->merged.p);
+    dev_free(ctx->tables);
+    dev_free(ctx->merged);
     if (ctx->h_tables.p)
         cudaFreeHost(ctx->h_tables.p);
     if (ctx->h_sep.p)

@@ -437,3 +437,30 @@ def test_pil_encoded_files_with_optimised_tables(decoder):
                 check_against_oracle(decoder, buf.getvalue())
             except AssertionError as e:
                 raise AssertionError(f"{name} {kw}: {e}") from e
+
+
+def test_guard_mode_finds_no_stray_writes(monkeypatch, lena_jpg):
+    """KPEG_GUARD=1: every device buffer is allocated at exactly the requested size between guard areas that are
+    checked after each job (a stand-in for compute-sanitizer).  Valid, ragged, batched and corrupt inputs must
+    leave them intact."""
+    monkeypatch.setenv("KPEG_GUARD", "1")
+    dec = K.Decoder(0)
+    try:
+        check_against_oracle(dec, lena_jpg)
+        for w, h, ri in ((17, 9, 0), (200, 120, 7), (1000, 3, 5)):
+            jpg = synth_encode(SynthParams(w, h, quality=80, restart_interval=ri, flags=QUIRK_FREE | (EMIT_RESTART if ri else 0),
+                                           seed=w + h)).tobytes()
+            check_against_oracle(dec, jpg)
+        buf = np.frombuffer(lena_jpg, dtype=np.uint8).copy()
+        plan, off, n = K.parse_jfif(buf)
+        rng = np.random.default_rng(9)
+        for trial in range(6):
+            bad = buf.copy()
+            idx = rng.integers(off + 10, off + n - 10, size=48)
+            bad[idx] = rng.integers(1, 255, size=48).astype(np.uint8)
+            try:
+                dec.decode_file(bad)
+            except K.KpegError as e:
+                assert e.code == K.api.KPEG_ERR_STREAM, f"trial {trial}: {e}"  # a guard violation would be KPEG_ERR_CUDA
+    finally:
+        dec.close()
