@@ -102,6 +102,10 @@ KPEG_HD constexpr double aan_scale_c(int k)
 // 1 / (prescale of the coefficient at natural index nat): |prescaled dequantised coefficient| * this = |c| * q
 KPEG_HD constexpr float aan_unscale(int nat) { return (float)(8.0 / (aan_scale_c(nat >> 3) * aan_scale_c(nat & 7))); }
 
+// Pair layout of a block going into the packed transform (kernels.cu): pair p = rp * 8 + c holds the natural
+// positions (2 rp, c) and (2 rp + 1, c) -- two rows side by side, so the row pass transforms two rows per instruction.
+KPEG_HD constexpr int pair_nat(int p, int half) { return ((p >> 3) * 2 + half) * 8 + (p & 7); }
+
 inline double aan_scale(int k)
 {
     const double s[8] = {1.0, 1.387039845322148, 1.306562964876377, 1.175875602419359,
@@ -109,45 +113,69 @@ inline double aan_scale(int k)
     return s[k];
 }
 
-// One 8-point AAN inverse DCT on prescaled inputs, in place.
-KPEG_HD void idct8_aan(float &v0, float &v1, float &v2, float &v3, float &v4, float &v5, float &v6, float &v7)
+// Lane operations of the fast IDCT.  The transform is written once (idct8_aan below) over a lane type V:
+// `float` here (host single-stepper, scalar device code) and the packed two-lane type of kernels.cu (sm_100a
+// FADD2 / FMUL2 / FFMA2: two independent IEEE fp32 lanes per instruction).  Every fused multiply-add is explicit,
+// so all instantiations round identically, lane for lane.
+KPEG_HD float lane_add(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+KPEG_HD float lane_sub(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+KPEG_HD float lane_mul_k(float a, float k) { return mul_f32(a, k); }
+KPEG_HD float lane_fma_k(float a, float k, float c) { return fmaf(a, k, c); } // a * k + c, one rounding
+
+// One 8-point AAN inverse DCT on prescaled inputs, in place: 25 adds, 1 multiply, 4 fused multiply-adds.
+template <class V>
+KPEG_HD void idct8_aan(V &v0, V &v1, V &v2, V &v3, V &v4, V &v5, V &v6, V &v7)
 {
     // even part
-    const float t10 = v0 + v4, t11 = v0 - v4;
-    const float t13 = v2 + v6;
-    const float t12 = (v2 - v6) * 1.414213562373095f - t13;
-    const float e0 = t10 + t13, e3 = t10 - t13, e1 = t11 + t12, e2 = t11 - t12;
+    const V t10 = lane_add(v0, v4), t11 = lane_sub(v0, v4);
+    const V t13 = lane_add(v2, v6);
+    const V n12 = lane_fma_k(lane_sub(v2, v6), -1.414213562373095f, t13); // -(t12)
+    const V e0 = lane_add(t10, t13), e3 = lane_sub(t10, t13), e1 = lane_sub(t11, n12), e2 = lane_add(t11, n12);
     // odd part
-    const float z13 = v5 + v3, z10 = v5 - v3, z11 = v1 + v7, z12 = v1 - v7;
-    const float o7 = z11 + z13;
-    const float t21 = (z11 - z13) * 1.414213562373095f;
-    const float z5 = (z10 + z12) * 1.847759065022573f;
-    const float t20 = z5 - z12 * 1.082392200292394f;
-    const float t22 = z5 - z10 * 2.613125929752753f;
-    const float o6 = t22 - o7;
-    const float o5 = t21 - o6;
-    const float o4 = t20 - o5;
-    v0 = e0 + o7;
-    v7 = e0 - o7;
-    v1 = e1 + o6;
-    v6 = e1 - o6;
-    v2 = e2 + o5;
-    v5 = e2 - o5;
-    v3 = e3 + o4;
-    v4 = e3 - o4;
+    const V z13 = lane_add(v5, v3), z10 = lane_sub(v5, v3), z11 = lane_add(v1, v7), z12 = lane_sub(v1, v7);
+    const V o7 = lane_add(z11, z13);
+    const V z5 = lane_mul_k(lane_add(z10, z12), 1.847759065022573f);
+    const V t20 = lane_fma_k(z12, -1.082392200292394f, z5);
+    const V t22 = lane_fma_k(z10, -2.613125929752753f, z5);
+    const V o6 = lane_sub(t22, o7);
+    const V n5 = lane_fma_k(lane_sub(z11, z13), -1.414213562373095f, o6); // -(o5)
+    const V o4 = lane_add(t20, n5);
+    v0 = lane_add(e0, o7);
+    v7 = lane_sub(e0, o7);
+    v1 = lane_add(e1, o6);
+    v6 = lane_sub(e1, o6);
+    v2 = lane_sub(e2, n5);
+    v5 = lane_add(e2, n5);
+    v3 = lane_add(e3, o4);
+    v4 = lane_sub(e3, o4);
 }
 
 // Fast 2-D IDCT of one block held as 64 prescaled floats in NATURAL order (f[row*8+col]);
-// result overwrites f: f[row*8+col] = sample before the +128 level shift.
+// result overwrites f: f[row*8+col] = sample before the +128 level shift.  Rows first, then columns -- the
+// order of the packed device version (kernels.cu idct8x8_packed), which this scalar form matches bit for bit.
 KPEG_HD void idct8x8_fast(float f[64])
 {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) // columns
-        idct8_aan(f[c], f[8 + c], f[16 + c], f[24 + c], f[32 + c], f[40 + c], f[48 + c], f[56 + c]);
 #pragma unroll
     for (int r = 0; r < 8; ++r) // rows
         idct8_aan(f[8 * r], f[8 * r + 1], f[8 * r + 2], f[8 * r + 3], f[8 * r + 4], f[8 * r + 5], f[8 * r + 6],
                   f[8 * r + 7]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) // columns
+        idct8_aan(f[c], f[8 + c], f[16 + c], f[24 + c], f[32 + c], f[40 + c], f[48 + c], f[56 + c]);
 }
 
 // |fast - reference| <= TIE_REL * A + TIE_ABS with A = sum |dequantised coefficient| = sum |c_i| * q_i

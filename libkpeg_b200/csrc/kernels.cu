@@ -1428,7 +1428,21 @@ struct ZzNat {
     static constexpr int value = zigzag_to_natural(I);
 };
 
-constexpr int IDCT_REC_CAP = 176;
+constexpr int IDCT_REC_CAP = 144;
+#ifndef KPEG_IDCT_PREFETCH_STRIPS
+#define KPEG_IDCT_PREFETCH_STRIPS (148 * 8) // CTAs resident on the device at a time
+#endif
+constexpr uint32_t IDCT_PREFETCH_STRIPS = KPEG_IDCT_PREFETCH_STRIPS;
+#ifndef KPEG_IDCT_MIN_CTAS
+#define KPEG_IDCT_MIN_CTAS 8
+#endif
+
+// Per-block facts the colour stage needs, derived from A = sum |dequantised coefficient| (every sample of the
+// block is bounded by A / 4: the 64 basis functions are bounded by 1/4):
+//   BLK_NONZERO  some coefficient is non-zero (otherwise all 64 samples are 0)
+//   BLK_WIDE     A > COLOUR_SAFE_A: samples may leave the range the fp32 colour path is proven for
+constexpr uint32_t BLK_NONZERO = 1u, BLK_WIDE = 2u;
+constexpr float COLOUR_SAFE_A = 4.0f * (COLOUR_FAST_RANGE - 8.0f);
 
 template <int NC>
 struct IdctSmem {
@@ -1440,11 +1454,68 @@ struct IdctSmem {
         uint4 coef[NB * 8];
         float4 samp[NC * 8 * 2 * NM]; // [comp][row][half][mcu] -> 4 samples (rounded, unshifted)
     };
-    float qscale[NC][64];
+    float2 qpair[NC][32];         // prescaled quantisers in the pair order of the transform (pair_nat)
+    float2 qdc[NC][32];           // the same with every AC entry zero: what a block that loses its AC terms (F1) multiplies by
     uint2 tie[NB];                // per block: 64-bit mask of the samples inside the tie band
+    uint8_t flag[NB];             // per block: BLK_NONZERO | BLK_WIDE (decides the colour variant of its MCU)
     uint2 rec[IDCT_REC_CAP];      // tie records of this strip (compact form), flushed to the global list with ONE atomic
     uint32_t nrec, rec_base;
 };
+
+// ---- two fp32 lanes per instruction (sm_100a FADD2 / FMUL2 / FFMA2) -------------------------------
+// K3 is bound by instruction issue, not by HBM or by the FMA pipe, and most of what it issues are fp32 adds of
+// the IDCT butterflies.  Blackwell's packed fp32 instructions do two independent IEEE lanes per issue slot, so the
+// transform, the dequantisation, the rounding and the colour arithmetic run on register pairs.  A pair is a
+// 64-bit register; packing / unpacking is register naming (mov.b64), not arithmetic.
+struct F2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ F2 pack2(float lo, float hi)
+{
+    F2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(F2 a, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ float lo2(F2 a)
+{
+    float lo, hi;
+    unpack2(a, lo, hi);
+    return lo;
+}
+__device__ __forceinline__ float hi2(F2 a)
+{
+    float lo, hi;
+    unpack2(a, lo, hi);
+    return hi;
+}
+__device__ __forceinline__ F2 splat2(float k) { return pack2(k, k); }
+__device__ __forceinline__ F2 lane_add(F2 a, F2 b)
+{
+    F2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 lane_sub(F2 a, F2 b)
+{
+    F2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 lane_mul(F2 a, F2 b)
+{
+    F2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 lane_fma(F2 a, F2 b, F2 c)
+{
+    F2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ F2 lane_mul_k(F2 a, float k) { return lane_mul(a, splat2(k)); }
+__device__ __forceinline__ F2 lane_fma_k(F2 a, float k, F2 c) { return lane_fma(a, splat2(k), c); }
 
 // coefficient I (zig-zag index) of a block held as eight 16-byte chunks
 template <int I>
@@ -1455,19 +1526,57 @@ __device__ __forceinline__ float chunk_coef(const uint4 (&ch)[8])
     return (float)(short)(hi ? (w >> 16) : (w & 0xFFFFu));
 }
 
-// Dequantise (AAN prescale folded into q) and de-zigzag by register renaming; on the way, A = sum |c_i| * q_i,
-// the magnitude the tie band is proportional to: |f| * (1 / prescale) with the reciprocal an immediate and the
-// absolute value a free operand modifier -- one FFMA per coefficient.  (fp32 accumulation is off by < 1e-5
-// relative; the band carries a 10 % margin.)
-template <int... Is>
-__device__ __forceinline__ float dequant_dezigzag(const uint4 (&ch)[8], const float *q, float (&f)[64],
-                                                  std::integer_sequence<int, Is...>)
+template <int NAT>
+struct NatZz {
+    static constexpr int value = make_zigzag_tables().nat2zz[NAT];
+};
+
+// Dequantise (AAN prescale folded into q; q arrives in pair order, see IdctSmem::qpair) and de-zigzag by register
+// renaming; on the way, A = sum |c_i| * q_i, the magnitude the tie band is proportional to: |f| * (1 / prescale)
+// with the reciprocal an immediate and the absolute value a free operand modifier -- one FFMA per coefficient.
+// (fp32 accumulation is off by < 1e-5 relative; the band carries a 10 % margin.)
+template <int... Ps>
+__device__ __forceinline__ float dequant_dezigzag(const uint4 (&ch)[8], const float2 *qpair, F2 (&P)[32],
+                                                  std::integer_sequence<int, Ps...>)
 {
-    float A = 0.0f;
-    (((f[ZzNat<Is>::value] = chunk_coef<Is>(ch) * q[Is]),
-      (A = fmaf(fabsf(f[ZzNat<Is>::value]), aan_unscale(ZzNat<Is>::value), A))),
-     ...);
-    return A;
+    float A[4] = {0.0f, 0.0f, 0.0f, 0.0f}; // four short dependent chains instead of one of 64
+    auto one = [&](auto PI) {
+        constexpr int p = decltype(PI)::value;
+        constexpr int n0 = pair_nat(p, 0), n1 = pair_nat(p, 1);
+        const float2 q = qpair[p];
+        P[p] = lane_mul(pack2(chunk_coef<NatZz<n0>::value>(ch), chunk_coef<NatZz<n1>::value>(ch)), pack2(q.x, q.y));
+        A[p & 1] = fmaf(fabsf(lo2(P[p])), aan_unscale(n0), A[p & 1]);
+        A[2 + (p & 1)] = fmaf(fabsf(hi2(P[p])), aan_unscale(n1), A[2 + (p & 1)]);
+    };
+    (one(std::integral_constant<int, Ps>{}), ...);
+    return (A[0] + A[1]) + (A[2] + A[3]);
+}
+
+// Packed 2-D transform, first half: the row pass, two rows per instruction.
+// P[rp * 8 + c] = rows 2rp, 2rp+1 at column c, in place.
+__device__ __forceinline__ void idct_rows_packed(F2 (&P)[32])
+{
+#pragma unroll
+    for (int rp = 0; rp < 4; ++rp)
+        idct8_aan(P[rp * 8 + 0], P[rp * 8 + 1], P[rp * 8 + 2], P[rp * 8 + 3], P[rp * 8 + 4], P[rp * 8 + 5],
+                  P[rp * 8 + 6], P[rp * 8 + 7]);
+}
+
+// Second half for the column pair cp (columns 2cp, 2cp+1): 2x2 register transposes of the row-pass output, then
+// the column pass, two columns per instruction.  Out: Q[r] = row r at columns 2cp, 2cp+1.
+// Same operations in the same order as idct8x8_fast (idct_core.h), lane for lane.
+template <int CP>
+__device__ __forceinline__ void idct_cols_packed(const F2 (&P)[32], F2 (&Q)[8])
+{
+#pragma unroll
+    for (int rp = 0; rp < 4; ++rp) {
+        float a, b, c, d; // a = (2rp, 2cp)  b = (2rp+1, 2cp)  c = (2rp, 2cp+1)  d = (2rp+1, 2cp+1)
+        unpack2(P[rp * 8 + 2 * CP], a, b);
+        unpack2(P[rp * 8 + 2 * CP + 1], c, d);
+        Q[2 * rp] = pack2(a, c);
+        Q[2 * rp + 1] = pack2(b, d);
+    }
+    idct8_aan(Q[0], Q[1], Q[2], Q[3], Q[4], Q[5], Q[6], Q[7]);
 }
 
 // Four ints -> four bytes with unsigned saturation (cvt.pack.sat: two values per instruction).
@@ -1588,6 +1697,9 @@ __device__ __noinline__ int exact_sample_global(const int16_t *coef, const int16
 }
 
 // pixel (unshifted integer samples) -> packed bytes, fast path with exact fallback
+// eight strips per SM: 228 KB of shared memory, 1 KB of each CTA's share taken by the driver
+static_assert(sizeof(IdctSmem<3>) <= (233472 / 8 - 1024), "idct_kernel<3> no longer fits eight CTAs per SM");
+
 template <int NC>
 __device__ __forceinline__ uint32_t colour_px(float y, float cb, float cr)
 {
@@ -1640,8 +1752,93 @@ __device__ __forceinline__ void resolve_and_store_pixel(const ExactCtx &a, const
     }
 }
 
+// Colour of the eight pixels of one row of an MCU -> 24 unclamped channel values, three variants chosen per MCU:
+//   COLOUR_PLAIN    ycc_to_rgb_fast's arithmetic on pixel pairs (FFMA2 / FADD2); its range precondition holds for
+//                   the whole MCU (no block is BLK_WIDE) and its flat-chroma special case cannot occur unnoticed
+//                   (a pixel with Cb = Cr = 0 fails the G test and takes the exact expression, which is right too)
+//   COLOUR_FLAT     both chroma blocks are all-zero (gray-as-YCbCr content): R = G = B = Y + 128
+//   COLOUR_GENERAL  ycc_to_rgb_fast itself, pixel by pixel, with its range and flat tests
+enum { COLOUR_PLAIN = 0, COLOUR_FLAT = 1, COLOUR_GENERAL = 2 };
+
+__device__ __noinline__ uint32_t colour_px_general(float y, float cb, float cr, uint32_t *exact)
+{
+    int R, G, B;
+    if (!ycc_to_rgb_fast(y, cb, cr, R, G, B)) {
+        ++*exact;
+        return colour_exact_px(y, cb, cr);
+    }
+    return (uint32_t)clamp_u8(R) | ((uint32_t)clamp_u8(G) << 8) | ((uint32_t)clamp_u8(B) << 16);
+}
+
+// -> the row's 24 bytes as six words; returns the number of pixels that took the double expression
+template <int MODE>
+__device__ __forceinline__ uint32_t colour_row8(const float4 (&yy)[2], const float4 (&bb)[2], const float4 (&cc)[2],
+                                                uint32_t (&out)[6])
+{
+    uint32_t exact = 0;
+    if constexpr (MODE == COLOUR_GENERAL) {
+        const float Y[8] = {yy[0].x, yy[0].y, yy[0].z, yy[0].w, yy[1].x, yy[1].y, yy[1].z, yy[1].w};
+        const float Cb[8] = {bb[0].x, bb[0].y, bb[0].z, bb[0].w, bb[1].x, bb[1].y, bb[1].z, bb[1].w};
+        const float Cr[8] = {cc[0].x, cc[0].y, cc[0].z, cc[0].w, cc[1].x, cc[1].y, cc[1].z, cc[1].w};
+        uint32_t p[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            p[j] = colour_px_general(Y[j], Cb[j], Cr[j], &exact);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            out[3 * q + 0] = p[4 * q] | (p[4 * q + 1] << 24);
+            out[3 * q + 1] = (p[4 * q + 1] >> 8) | (p[4 * q + 2] << 16);
+            out[3 * q + 2] = (p[4 * q + 2] >> 16) | (p[4 * q + 3] << 8);
+        }
+        return exact;
+    }
+    int px[24];
+    if constexpr (MODE == COLOUR_FLAT) {
+        const float Y[8] = {yy[0].x, yy[0].y, yy[0].z, yy[0].w, yy[1].x, yy[1].y, yy[1].z, yy[1].w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            px[3 * j] = px[3 * j + 1] = px[3 * j + 2] = float_bits(Y[j] + (RINT_MAGIC + 128.0f)) - RINT_MAGIC_BITS;
+    } else {
+        const F2 magic = splat2(RINT_MAGIC);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 &y4 = yy[k >> 1], &b4 = bb[k >> 1], &c4 = cc[k >> 1];
+            const F2 y = (k & 1) ? pack2(y4.z, y4.w) : pack2(y4.x, y4.y);
+            const F2 cb = (k & 1) ? pack2(b4.z, b4.w) : pack2(b4.x, b4.y);
+            const F2 cr = (k & 1) ? pack2(c4.z, c4.w) : pack2(c4.x, c4.y);
+            // ycc_to_rgb_fast (idct_core.h), two pixels per instruction
+            const F2 yr = lane_add(y, splat2(127.501f));
+            const F2 yg = lane_add(y, splat2(127.5f));
+            const F2 tr = lane_add(lane_fma_k(cr, 1.402f, yr), magic);
+            const F2 tb = lane_add(lane_fma_k(cb, 1.772f, yr), magic);
+            const F2 g = lane_fma_k(cr, -0.714136f, lane_fma_k(cb, -0.344136f, yg));
+            const F2 tg = lane_add(g, magic);
+            const F2 dg = lane_sub(g, lane_sub(tg, magic));
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * k + h;
+                int R = float_bits(h ? hi2(tr) : lo2(tr)) - RINT_MAGIC_BITS;
+                int G = float_bits(h ? hi2(tg) : lo2(tg)) - RINT_MAGIC_BITS;
+                int B = float_bits(h ? hi2(tb) : lo2(tb)) - RINT_MAGIC_BITS;
+                if (!(fabsf(h ? hi2(dg) : lo2(dg)) < 0.5f - COLOUR_G_BAND)) {
+                    const uint32_t e = colour_exact_px(h ? hi2(y) : lo2(y), h ? hi2(cb) : lo2(cb), h ? hi2(cr) : lo2(cr));
+                    R = (int)(e & 0xFFu);
+                    G = (int)((e >> 8) & 0xFFu);
+                    B = (int)(e >> 16);
+                    ++exact;
+                }
+                px[3 * j] = R, px[3 * j + 1] = G, px[3 * j + 2] = B;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        out[k] = pack4_sat(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
+    return exact;
+}
+
 template <int NC>
-__global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? 8 : 16) idct_kernel(IdctArgs a)
+__global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MIN_CTAS : 16) idct_kernel(IdctArgs a)
 {
     constexpr int NM = IDCT_MCUS_PER_CTA;
     constexpr int NB = NM * NC;
@@ -1658,8 +1855,24 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? 8 : 16) idct
     const uint32_t blk0 = mcu0 * NC;
 
     // ---- stage 0: quantiser + coefficients -> shared memory (coalesced 16-byte loads) ---------------
-    for (int i = t; i < NC * 64; i += NB)
-        (&sm.qscale[0][0])[i] = a.tables->qscale[0][i];
+    // warm L2 with the strip that will run in this CTA's slot next (CTAs are dispatched in index order)
+    {
+        const uint32_t ahead = blk0 + IDCT_PREFETCH_STRIPS * NB + t;
+        if (ahead < a.g.total_blocks)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.coef + (size_t)ahead * 64u));
+    }
+    // the block's DC value (from K2) and its DC difference: requested first, needed only in stage 1
+    int dcv = 0;
+    bool drop_ac = false;
+    if (m < total_mcus) {
+        dcv = a.dc[blk0 + bl];
+        drop_ac = (a.g.flags & 1u) && a.dcdiff[blk0 + bl] == 0; // MCU.cpp:97-104
+    }
+    for (int i = t; i < NC * 64; i += NB) {
+        const float q = a.tables->qpair[0][i];
+        (&sm.qpair[0][0].x)[i] = q;
+        (&sm.qdc[0][0].x)[i] = (i & 63) == 0 ? q : 0.0f;
+    }
     if (t == 0)
         sm.nrec = 0;
     {
@@ -1684,43 +1897,53 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? 8 : 16) idct
         ch[k] = sm.coef[bl * 8 + (k ^ (bl & 7))];
     __syncthreads(); // everyone holds its block in registers: `samp` may now overwrite `coef`
     if (m < total_mcus) {
-        const uint32_t gb = blk0 + bl;
-        const int dcv = a.dc[gb];
-        const bool drop_ac = (a.g.flags & 1u) && a.dcdiff[gb] == 0; // MCU.cpp:97-104
-        if (drop_ac) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                ch[k] = make_uint4(0, 0, 0, 0);
-        }
         // the entropy stage leaves slot 0 empty; the integrated DC value comes from K2
         ch[0].x = (ch[0].x & 0xFFFF0000u) | ((uint32_t)dcv & 0xFFFFu);
 
-        float f[64];
-        const float A = dequant_dezigzag(ch, sm.qscale[comp], f, std::make_integer_sequence<int, 64>{});
+        F2 P[32];
+        const float A = dequant_dezigzag(ch, drop_ac ? sm.qdc[comp] : sm.qpair[comp], P, std::make_integer_sequence<int, 32>{});
         const float thresh = 0.5f - tie_band(A);
-        idct8x8_fast(f);
+        idct_rows_packed(P);
 
         // (x + 1.5*2^23) - 1.5*2^23 == rint(x) for |x| < 2^22; samples inside the tie band are
         // collected in a 64-bit mask (predicated ORs, no branches)
         uint32_t tie_lo = 0, tie_hi = 0;
+        const F2 magic = splat2(RINT_MAGIC);
+        auto half_block = [&](auto HALF) { // columns 4 half .. 4 half + 3 of all eight rows
+            constexpr int half = decltype(HALF)::value;
+            F2 Q0[8], Q1[8];
+            idct_cols_packed<2 * half>(P, Q0);
+            idct_cols_packed<2 * half + 1>(P, Q1);
+            uint32_t tl = 0, th = 0; // this half's own accumulators: two short chains of predicated ORs, not one long one
 #pragma unroll
-        for (int row = 0; row < 8; ++row) {
-            float r[8];
+            for (int row = 0; row < 8; ++row) {
+                float r[4];
 #pragma unroll
-            for (int col = 0; col < 8; ++col) {
-                const float x = f[row * 8 + col];
-                r[col] = (x + RINT_MAGIC) - RINT_MAGIC;
-                if (fabsf(x - r[col]) > thresh) {
-                    if (row < 4)
-                        tie_lo |= 1u << (row * 8 + col);
-                    else
-                        tie_hi |= 1u << (row * 8 + col - 32);
+                for (int k = 0; k < 2; ++k) {
+                    const F2 x = k ? Q1[row] : Q0[row];
+                    const F2 rr = lane_sub(lane_add(x, magic), magic);
+                    const F2 d = lane_sub(x, rr);
+                    unpack2(rr, r[2 * k], r[2 * k + 1]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int col = 4 * half + 2 * k + h;
+                        if (fabsf(h ? hi2(d) : lo2(d)) > thresh) {
+                            if (row < 4)
+                                tl |= 1u << (row * 8 + col);
+                            else
+                                th |= 1u << (row * 8 + col - 32);
+                        }
+                    }
                 }
+                sm.samp[((comp * 8 + row) * 2 + half) * NM + ml] = make_float4(r[0], r[1], r[2], r[3]);
             }
-            sm.samp[((comp * 8 + row) * 2 + 0) * NM + ml] = make_float4(r[0], r[1], r[2], r[3]);
-            sm.samp[((comp * 8 + row) * 2 + 1) * NM + ml] = make_float4(r[4], r[5], r[6], r[7]);
-        }
+            tie_lo |= tl;
+            tie_hi |= th;
+        };
+        half_block(std::integral_constant<int, 0>{});
+        half_block(std::integral_constant<int, 1>{});
         sm.tie[bl] = make_uint2(tie_lo, tie_hi);
+        sm.flag[bl] = (uint8_t)((A != 0.0f ? BLK_NONZERO : 0u) | (A > COLOUR_SAFE_A ? BLK_WIDE : 0u));
     }
     __syncthreads();
 
@@ -1740,41 +1963,35 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? 8 : 16) idct
 #pragma unroll
         for (int c = 0; c < NC; ++c)
             tmask[c] = sm.tie[ml * NC + c];
+        int mode = COLOUR_PLAIN;
+        if constexpr (NC == 3) {
+            const uint32_t f0 = sm.flag[ml * NC], f1 = sm.flag[ml * NC + 1], f2 = sm.flag[ml * NC + 2];
+            mode = ((f0 | f1 | f2) & BLK_WIDE) ? COLOUR_GENERAL : (((f1 | f2) & BLK_NONZERO) ? COLOUR_PLAIN : COLOUR_FLAT);
+        }
         for (int row = comp; row < 8; row += NC) { // the NC warps of the CTA share the 8 pixel rows
             const uint32_t y = by * 8u + row;
             if (y >= H)
                 continue;
             const float4 y0 = sm.samp[((0 * 8 + row) * 2 + 0) * NM + ml];
             const float4 y1 = sm.samp[((0 * 8 + row) * 2 + 1) * NM + ml];
-            const float Y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
             uint32_t out[2 * NC];
             if constexpr (NC == 3) {
-                const float4 b0 = sm.samp[((1 * 8 + row) * 2 + 0) * NM + ml];
-                const float4 b1 = sm.samp[((1 * 8 + row) * 2 + 1) * NM + ml];
-                const float4 c0 = sm.samp[((2 * 8 + row) * 2 + 0) * NM + ml];
-                const float4 c1 = sm.samp[((2 * 8 + row) * 2 + 1) * NM + ml];
-                const float Cb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                const float Cr[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                int px[24];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    int R, G, B;
-                    if (!ycc_to_rgb_fast(Y[j], Cb[j], Cr[j], R, G, B)) {
-                        const uint32_t e = colour_exact_px(Y[j], Cb[j], Cr[j]);
-                        R = (int)(e & 0xFFu);
-                        G = (int)((e >> 8) & 0xFFu);
-                        B = (int)(e >> 16);
-                        ++colour_exact;
-                    }
-                    px[j * 3 + 0] = R;
-                    px[j * 3 + 1] = G;
-                    px[j * 3 + 2] = B;
-                }
+                const float4 yy[2] = {y0, y1};
+                const float4 bb[2] = {sm.samp[((1 * 8 + row) * 2 + 0) * NM + ml], sm.samp[((1 * 8 + row) * 2 + 1) * NM + ml]};
+                const float4 cc[2] = {sm.samp[((2 * 8 + row) * 2 + 0) * NM + ml], sm.samp[((2 * 8 + row) * 2 + 1) * NM + ml]};
+                uint32_t o6[6];
+                if (mode == COLOUR_PLAIN)
+                    colour_exact += colour_row8<COLOUR_PLAIN>(yy, bb, cc, o6);
+                else if (mode == COLOUR_FLAT)
+                    colour_exact += colour_row8<COLOUR_FLAT>(yy, bb, cc, o6);
+                else
+                    colour_exact += colour_row8<COLOUR_GENERAL>(yy, bb, cc, o6);
 #pragma unroll
                 for (int k = 0; k < 6; ++k)
-                    out[k] = pack4_sat(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
+                    out[k] = o6[k];
             } else {
                 // gray: the reference's colour path with Cb = Cr = 128 gives R = G = B = clamp(Y)
+                const float Y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
                 int v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
