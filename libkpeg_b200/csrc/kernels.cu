@@ -1428,7 +1428,7 @@ struct ZzNat {
     static constexpr int value = zigzag_to_natural(I);
 };
 
-constexpr int IDCT_REC_CAP = 144;
+constexpr int IDCT_REC_CAP = 136;
 #ifndef KPEG_IDCT_PREFETCH_STRIPS
 #define KPEG_IDCT_PREFETCH_STRIPS (148 * 8) // CTAs resident on the device at a time
 #endif
@@ -1460,6 +1460,7 @@ struct IdctSmem {
     uint8_t flag[NB];             // per block: BLK_NONZERO | BLK_WIDE (decides the colour variant of its MCU)
     uint2 rec[IDCT_REC_CAP];      // tie records of this strip (compact form), flushed to the global list with ONE atomic
     uint32_t nrec, rec_base;
+    uint32_t img0, by0, bx0;      // image / block row / block column of the strip's first MCU (divisions done once, by thread 0)
 };
 
 // ---- two fp32 lanes per instruction (sm_100a FADD2 / FMUL2 / FFMA2) -------------------------------
@@ -1760,20 +1761,20 @@ __device__ __forceinline__ void resolve_and_store_pixel(const ExactCtx &a, const
 //   COLOUR_GENERAL  ycc_to_rgb_fast itself, pixel by pixel, with its range and flat tests
 enum { COLOUR_PLAIN = 0, COLOUR_FLAT = 1, COLOUR_GENERAL = 2 };
 
-__device__ __noinline__ uint32_t colour_px_general(float y, float cb, float cr, uint32_t *exact)
+// bits 0..23 = R, G, B; bit 24 set when the double expression was needed
+__device__ __noinline__ uint32_t colour_px_general(float y, float cb, float cr)
 {
     int R, G, B;
-    if (!ycc_to_rgb_fast(y, cb, cr, R, G, B)) {
-        ++*exact;
-        return colour_exact_px(y, cb, cr);
-    }
+    if (!ycc_to_rgb_fast(y, cb, cr, R, G, B))
+        return colour_exact_px(y, cb, cr) | (1u << 24);
     return (uint32_t)clamp_u8(R) | ((uint32_t)clamp_u8(G) << 8) | ((uint32_t)clamp_u8(B) << 16);
 }
 
-// -> the row's 24 bytes as six words; returns the number of pixels that took the double expression
+// -> the row's 24 bytes as six words; returns the number of pixels that took the double expression.
+// redo (COLOUR_PLAIN only): bit j set = pixel j of the row must be replaced by colour_exact_px.
 template <int MODE>
 __device__ __forceinline__ uint32_t colour_row8(const float4 (&yy)[2], const float4 (&bb)[2], const float4 (&cc)[2],
-                                                uint32_t (&out)[6])
+                                                uint32_t (&out)[6], uint32_t &redo)
 {
     uint32_t exact = 0;
     if constexpr (MODE == COLOUR_GENERAL) {
@@ -1782,8 +1783,11 @@ __device__ __forceinline__ uint32_t colour_row8(const float4 (&yy)[2], const flo
         const float Cr[8] = {cc[0].x, cc[0].y, cc[0].z, cc[0].w, cc[1].x, cc[1].y, cc[1].z, cc[1].w};
         uint32_t p[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            p[j] = colour_px_general(Y[j], Cb[j], Cr[j], &exact);
+        for (int j = 0; j < 8; ++j) {
+            p[j] = colour_px_general(Y[j], Cb[j], Cr[j]);
+            exact += p[j] >> 24;
+            p[j] &= 0xFFFFFFu;
+        }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             out[3 * q + 0] = p[4 * q] | (p[4 * q + 1] << 24);
@@ -1800,6 +1804,7 @@ __device__ __forceinline__ uint32_t colour_row8(const float4 (&yy)[2], const flo
             px[3 * j] = px[3 * j + 1] = px[3 * j + 2] = float_bits(Y[j] + (RINT_MAGIC + 128.0f)) - RINT_MAGIC_BITS;
     } else {
         const F2 magic = splat2(RINT_MAGIC);
+        F2 dg[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float4 &y4 = yy[k >> 1], &b4 = bb[k >> 1], &c4 = cc[k >> 1];
@@ -1813,22 +1818,26 @@ __device__ __forceinline__ uint32_t colour_row8(const float4 (&yy)[2], const flo
             const F2 tb = lane_add(lane_fma_k(cb, 1.772f, yr), magic);
             const F2 g = lane_fma_k(cr, -0.714136f, lane_fma_k(cb, -0.344136f, yg));
             const F2 tg = lane_add(g, magic);
-            const F2 dg = lane_sub(g, lane_sub(tg, magic));
+            dg[k] = lane_sub(g, lane_sub(tg, magic));
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int j = 2 * k + h;
-                int R = float_bits(h ? hi2(tr) : lo2(tr)) - RINT_MAGIC_BITS;
-                int G = float_bits(h ? hi2(tg) : lo2(tg)) - RINT_MAGIC_BITS;
-                int B = float_bits(h ? hi2(tb) : lo2(tb)) - RINT_MAGIC_BITS;
-                if (!(fabsf(h ? hi2(dg) : lo2(dg)) < 0.5f - COLOUR_G_BAND)) {
-                    const uint32_t e = colour_exact_px(h ? hi2(y) : lo2(y), h ? hi2(cb) : lo2(cb), h ? hi2(cr) : lo2(cr));
-                    R = (int)(e & 0xFFu);
-                    G = (int)((e >> 8) & 0xFFu);
-                    B = (int)(e >> 16);
-                    ++exact;
-                }
-                px[3 * j] = R, px[3 * j + 1] = G, px[3 * j + 2] = B;
+                px[3 * j] = float_bits(h ? hi2(tr) : lo2(tr)) - RINT_MAGIC_BITS;
+                px[3 * j + 1] = float_bits(h ? hi2(tg) : lo2(tg)) - RINT_MAGIC_BITS;
+                px[3 * j + 2] = float_bits(h ? hi2(tb) : lo2(tb)) - RINT_MAGIC_BITS;
             }
+        }
+        // G within COLOUR_G_BAND of an integer somewhere in the row (0.2 % of the pixels): ONE test per row on the
+        // largest |dg|; the caller replaces the listed pixels by the double expression after the row is stored
+        float worst = fmaxf(fabsf(lo2(dg[0])), fabsf(hi2(dg[0])));
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+            worst = fmaxf(worst, fmaxf(fabsf(lo2(dg[k])), fabsf(hi2(dg[k]))));
+        if (!(worst < 0.5f - COLOUR_G_BAND)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (!(fabsf((j & 1) ? hi2(dg[j >> 1]) : lo2(dg[j >> 1])) < 0.5f - COLOUR_G_BAND))
+                    redo |= 1u << j;
         }
     }
 #pragma unroll
@@ -1873,8 +1882,13 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
         (&sm.qpair[0][0].x)[i] = q;
         (&sm.qdc[0][0].x)[i] = (i & 63) == 0 ? q : 0.0f;
     }
-    if (t == 0)
+    if (t == 0) {
         sm.nrec = 0;
+        const uint32_t img = mcu0 / a.g.mcus_per_image, mi = mcu0 - img * a.g.mcus_per_image;
+        sm.img0 = img;
+        sm.by0 = mi / a.g.mcus_x;
+        sm.bx0 = mi - sm.by0 * a.g.mcus_x;
+    }
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.coef) + (size_t)blk0 * 8;
         const uint32_t nvalid = (a.g.total_blocks > blk0 ? min(a.g.total_blocks - blk0, (uint32_t)NB) : 0u) * 8u;
@@ -1949,9 +1963,21 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
 
     // ---- stage 2: colour conversion + interleaved store -------------------------------------------
     if (m < total_mcus) {
-        const uint32_t img = m / a.g.mcus_per_image;
-        const uint32_t mi = m - img * a.g.mcus_per_image;
-        const uint32_t by = mi / a.g.mcus_x, bx = mi - by * a.g.mcus_x;
+        uint32_t img = sm.img0, by = sm.by0, bx = sm.bx0 + (uint32_t)ml;
+        if (a.g.mcus_x >= (uint32_t)NM) { // the strip wraps at most once
+            if (bx >= a.g.mcus_x) {
+                bx -= a.g.mcus_x;
+                if (++by == a.g.mcus_y) {
+                    by = 0;
+                    ++img;
+                }
+            }
+        } else { // images narrower than a strip
+            img = m / a.g.mcus_per_image;
+            const uint32_t mi = m - img * a.g.mcus_per_image;
+            by = mi / a.g.mcus_x;
+            bx = mi - by * a.g.mcus_x;
+        }
         const uint32_t W = a.g.width, H = a.g.height;
         const uint32_t img_pix0 = img * W * H;
         uint8_t *img_base = a.pixels + (size_t)img_pix0 * NC;
@@ -1975,17 +2001,18 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
             const float4 y0 = sm.samp[((0 * 8 + row) * 2 + 0) * NM + ml];
             const float4 y1 = sm.samp[((0 * 8 + row) * 2 + 1) * NM + ml];
             uint32_t out[2 * NC];
+            uint32_t redo = 0;
             if constexpr (NC == 3) {
                 const float4 yy[2] = {y0, y1};
                 const float4 bb[2] = {sm.samp[((1 * 8 + row) * 2 + 0) * NM + ml], sm.samp[((1 * 8 + row) * 2 + 1) * NM + ml]};
                 const float4 cc[2] = {sm.samp[((2 * 8 + row) * 2 + 0) * NM + ml], sm.samp[((2 * 8 + row) * 2 + 1) * NM + ml]};
                 uint32_t o6[6];
                 if (mode == COLOUR_PLAIN)
-                    colour_exact += colour_row8<COLOUR_PLAIN>(yy, bb, cc, o6);
+                    colour_exact += colour_row8<COLOUR_PLAIN>(yy, bb, cc, o6, redo);
                 else if (mode == COLOUR_FLAT)
-                    colour_exact += colour_row8<COLOUR_FLAT>(yy, bb, cc, o6);
+                    colour_exact += colour_row8<COLOUR_FLAT>(yy, bb, cc, o6, redo);
                 else
-                    colour_exact += colour_row8<COLOUR_GENERAL>(yy, bb, cc, o6);
+                    colour_exact += colour_row8<COLOUR_GENERAL>(yy, bb, cc, o6, redo);
 #pragma unroll
                 for (int k = 0; k < 6; ++k)
                     out[k] = o6[k];
@@ -2011,43 +2038,66 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
                     if ((uint32_t)j < nbytes)
                         dst[j] = (uint8_t)(out[j >> 2] >> (8 * (j & 3)));
             }
-            // pixels of this row with a sample inside the tie band: queue them for the exact pass
-            uint32_t rowmask[NC], any = 0;
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const uint32_t w = row < 4 ? tmask[c].x : tmask[c].y;
-                rowmask[c] = (w >> ((row & 3) * 8)) & 0xFFu;
-                any |= rowmask[c];
-            }
-            while (any) {
-                const int j = __ffs(any) - 1;
-                any &= any - 1;
-                const uint32_t x = bx * 8u + (uint32_t)j;
-                if (x >= W)
+            while (redo) { // rare: this thread's own later byte stores replace what it has just written
+                const int j = __ffs(redo) - 1;
+                redo &= redo - 1;
+                if (bx * 8u + (uint32_t)j >= W)
                     continue;
-                uint32_t cm = 0;
-#pragma unroll
-                for (int c = 0; c < NC; ++c)
-                    cm |= ((rowmask[c] >> j) & 1u) << c;
-                // fast samples of this pixel, re-read from shared memory (dynamic index j)
                 const float *sp = reinterpret_cast<const float *>(sm.samp);
-                float fy, fcb = 0.0f, fcr = 0.0f;
-                fy = sp[(((0 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
-                if (NC == 3) {
-                    fcb = sp[(((1 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
-                    fcr = sp[((((NC - 1) * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
-                }
-                // compact strip-local form: x = mcu in strip | sample << 5 | components << 11 | fast Cr << 16,
-                // y = fast Y | fast Cb << 16; expanded to the global record when the strip's list is flushed
-                const uint2 rec = make_uint2((uint32_t)ml | ((uint32_t)(row * 8 + j) << 5) | (cm << 11) |
-                                                 ((uint32_t)(uint16_t)(int)fcr << 16),
-                                             (uint32_t)(uint16_t)(int)fy | ((uint32_t)(uint16_t)(int)fcb << 16));
-                const uint32_t at = atomicAdd(&sm.nrec, 1u); // shared-memory counter: one global atomic per strip
-                if (at < (uint32_t)IDCT_REC_CAP)
-                    sm.rec[at] = rec;
-                else
-                    overflow = true; // more tied pixels than a strip's list holds: the strip is redone wholesale
+                const uint32_t e = colour_exact_px(sp[(((0 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)],
+                                                   sp[(((1 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)],
+                                                   sp[((((NC - 1) * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)]);
+                dst[3 * j] = (uint8_t)e;
+                dst[3 * j + 1] = (uint8_t)(e >> 8);
+                dst[3 * j + 2] = (uint8_t)(e >> 16);
+                ++colour_exact;
             }
+        }
+        // pixels with a sample inside the tie band, in the rows this thread converted: queue them for the exact
+        // pass.  One pass over the set bits of the MCU's combined mask after the row loop (most MCUs have none).
+        uint32_t plo = 0, phi = 0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            plo |= tmask[c].x;
+            phi |= tmask[c].y;
+        }
+        if (NC == 3) { // rows comp, comp + 3, comp + 6; row r = bits 8r .. 8r+7
+            plo &= comp == 0 ? 0xFF0000FFu : (comp == 1 ? 0x0000FF00u : 0x00FF0000u);
+            phi &= comp == 0 ? 0x00FF0000u : (comp == 1 ? 0xFF0000FFu : 0x0000FF00u);
+        }
+        while (plo | phi) {
+            int s;
+            if (plo) {
+                s = __ffs(plo) - 1;
+                plo &= plo - 1;
+            } else {
+                s = 32 + __ffs(phi) - 1;
+                phi &= phi - 1;
+            }
+            const int row = s >> 3, j = s & 7;
+            if (by * 8u + (uint32_t)row >= H || bx * 8u + (uint32_t)j >= W)
+                continue;
+            uint32_t cm = 0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                cm |= (((s < 32 ? tmask[c].x : tmask[c].y) >> (s & 31)) & 1u) << c;
+            // fast samples of this pixel, re-read from shared memory
+            const float *sp = reinterpret_cast<const float *>(sm.samp);
+            float fy, fcb = 0.0f, fcr = 0.0f;
+            fy = sp[(((0 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
+            if (NC == 3) {
+                fcb = sp[(((1 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
+                fcr = sp[((((NC - 1) * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
+            }
+            // compact strip-local form: x = mcu in strip | sample << 5 | components << 11 | fast Cr << 16,
+            // y = fast Y | fast Cb << 16; expanded to the global record when the strip's list is flushed
+            const uint2 rec = make_uint2((uint32_t)ml | ((uint32_t)s << 5) | (cm << 11) | ((uint32_t)(uint16_t)(int)fcr << 16),
+                                         (uint32_t)(uint16_t)(int)fy | ((uint32_t)(uint16_t)(int)fcb << 16));
+            const uint32_t at = atomicAdd(&sm.nrec, 1u); // shared-memory counter: one global atomic per strip
+            if (at < (uint32_t)IDCT_REC_CAP)
+                sm.rec[at] = rec;
+            else
+                overflow = true; // more tied pixels than a strip's list holds: the strip is redone wholesale
         }
         if (colour_exact)
             atomicAdd(&a.meta->colour_exact, colour_exact);
