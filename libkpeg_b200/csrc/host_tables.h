@@ -38,8 +38,10 @@ inline int build_device_tables(const kpeg_plan *pl, DeviceTables *T, const char 
             T->qscale[c][i] = (float)((double)pl->qt[tq][i] * s);
             T->qint[c][i] = (int32_t)pl->qt[tq][i];
         }
-        for (int j = 0; j < 64; ++j)
+        for (int j = 0; j < 64; ++j) {
             T->qpair[c][j] = T->qscale[c][zz.nat2zz[pair_nat(j >> 1, j & 1)]];
+            T->qdc[c][j] = pair_nat(j >> 1, j & 1) == 0 ? T->qpair[c][j] : 0.0f;
+        }
     }
     for (int x = 0; x < 8; ++x)
         for (int u = 0; u < 8; ++u)

@@ -9,6 +9,7 @@
 //
 // All file:line citations are relative to /root/reference.  The arithmetic lives in
 // entropy_core.h / idct_core.h (host+device inline, also exercised on the CPU by tests/emu).
+#include <cuda.h> // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <atomic>
@@ -1428,7 +1429,7 @@ struct ZzNat {
     static constexpr int value = zigzag_to_natural(I);
 };
 
-constexpr int IDCT_REC_CAP = 136;
+constexpr int IDCT_REC_CAP = 134;
 #ifndef KPEG_IDCT_PREFETCH_STRIPS
 #define KPEG_IDCT_PREFETCH_STRIPS (148 * 8) // CTAs resident on the device at a time
 #endif
@@ -1461,6 +1462,8 @@ struct IdctSmem {
     uint2 rec[IDCT_REC_CAP];      // tie records of this strip (compact form), flushed to the global list with ONE atomic
     uint32_t nrec, rec_base;
     uint32_t img0, by0, bx0;      // image / block row / block column of the strip's first MCU (divisions done once, by thread 0)
+    uint32_t pad_;
+    unsigned long long mbar;      // completion barrier of the stage-0 bulk copies
 };
 
 // ---- two fp32 lanes per instruction (sm_100a FADD2 / FMUL2 / FFMA2) -------------------------------
@@ -1753,6 +1756,44 @@ __device__ __forceinline__ void resolve_and_store_pixel(const ExactCtx &a, const
     }
 }
 
+// ---- stage 0 by the copy engine (TMA) ------------------------------------------------------------------
+// One elected thread asks for the strip's coefficients as a 2-D tile of the coefficient matrix [blocks][64] through a
+// tensor map with the 128-byte swizzle -- 16-byte chunk k of block b lands at chunk (k ^ (b & 7)), which is the
+// bank-conflict-free layout stage 1 reads -- and for the two quantiser tables as plain bulk copies.  No thread spends
+// an instruction on addresses, loads or stores; rows past the end of the matrix arrive as zeros.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "KPEG_MBAR_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra KPEG_MBAR_DONE;\n"
+                 "bra KPEG_MBAR_WAIT;\n"
+                 "KPEG_MBAR_DONE:\n"
+                 "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_tile_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // Colour of the eight pixels of one row of an MCU -> 24 unclamped channel values, three variants chosen per MCU:
 //   COLOUR_PLAIN    ycc_to_rgb_fast's arithmetic on pixel pairs (FFMA2 / FADD2); its range precondition holds for
 //                   the whole MCU (no block is BLK_WIDE) and its flat-chroma special case cannot occur unnoticed
@@ -1847,11 +1888,12 @@ __device__ __forceinline__ uint32_t colour_row8(const float4 (&yy)[2], const flo
 }
 
 template <int NC>
-__global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MIN_CTAS : 16) idct_kernel(IdctArgs a)
+__global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MIN_CTAS : 16)
+    idct_kernel(IdctArgs a, const __grid_constant__ CUtensorMap coef_map)
 {
     constexpr int NM = IDCT_MCUS_PER_CTA;
     constexpr int NB = NM * NC;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[]; // the swizzled tile needs 1024-byte alignment
     IdctSmem<NC> &sm = *reinterpret_cast<IdctSmem<NC> *>(smem_raw);
 
     const int t = threadIdx.x;
@@ -1863,46 +1905,30 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
     const uint32_t m = mcu0 + ml;
     const uint32_t blk0 = mcu0 * NC;
 
-    // ---- stage 0: quantiser + coefficients -> shared memory (coalesced 16-byte loads) ---------------
-    // warm L2 with the strip that will run in this CTA's slot next (CTAs are dispatched in index order)
-    {
-        const uint32_t ahead = blk0 + IDCT_PREFETCH_STRIPS * NB + t;
-        if (ahead < a.g.total_blocks)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.coef + (size_t)ahead * 64u));
-    }
-    // the block's DC value (from K2) and its DC difference: requested first, needed only in stage 1
-    int dcv = 0;
-    bool drop_ac = false;
-    if (m < total_mcus) {
-        dcv = a.dc[blk0 + bl];
-        drop_ac = (a.g.flags & 1u) && a.dcdiff[blk0 + bl] == 0; // MCU.cpp:97-104 (SURVEY F1)
-    }
-    for (int i = t; i < NC * 64; i += NB) {
-        const float q = a.tables->qpair[0][i];
-        (&sm.qpair[0][0].x)[i] = q;
-        (&sm.qdc[0][0].x)[i] = (i & 63) == 0 ? q : 0.0f;
-    }
+    // ---- stage 0: quantisers + coefficients -> shared memory, by the copy engine -----------------------
+    const uint32_t bar = smem_u32(&sm.mbar);
     if (t == 0) {
+        constexpr uint32_t tile_bytes = NB * 128u, table_bytes = NC * 64u * 4u;
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, tile_bytes + 2u * table_bytes);
+        tma_load_tile_2d(smem_u32(sm.coef), &coef_map, 0, (int)blk0, bar);
+        bulk_load(smem_u32(sm.qpair), a.tables->qpair, table_bytes, bar);
+        bulk_load(smem_u32(sm.qdc), a.tables->qdc, table_bytes, bar);
         sm.nrec = 0;
         const uint32_t img = mcu0 / a.g.mcus_per_image, mi = mcu0 - img * a.g.mcus_per_image;
         sm.img0 = img;
         sm.by0 = mi / a.g.mcus_x;
         sm.bx0 = mi - sm.by0 * a.g.mcus_x;
     }
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.coef) + (size_t)blk0 * 8;
-        const uint32_t nvalid = (a.g.total_blocks > blk0 ? min(a.g.total_blocks - blk0, (uint32_t)NB) : 0u) * 8u;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t ci = (uint32_t)(k * NB + t);
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (ci < nvalid)
-                v = __ldg(src + ci);
-            const uint32_t b = ci >> 3, kk = ci & 7u;
-            sm.coef[b * 8 + (kk ^ (b & 7u))] = v;
-        }
+    // the block's DC value (from K2) and its DC difference: requested now, needed in stage 1
+    int dcv = 0;
+    bool drop_ac = false;
+    if (m < total_mcus) {
+        dcv = a.dc[blk0 + bl];
+        drop_ac = (a.g.flags & 1u) && a.dcdiff[blk0 + bl] == 0; // MCU.cpp:97-104 (SURVEY F1)
     }
-    __syncthreads();
+    __syncthreads(); // the barrier object is initialised: everyone may wait on it
+    mbar_wait(bar, 0);
 
     // ---- stage 1: one thread = one 8x8 block ------------------------------------------------------
     uint4 ch[8];
@@ -2218,15 +2244,51 @@ void kernels_configure(int max_concurrent_jobs)
     cudaFuncSetAttribute(idct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<1>));
 }
 
-void launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches)
+// Tensor map of the coefficient matrix [total_blocks][64] of int16, tiles of `box_blocks` whole blocks, 128-byte
+// swizzle, zeros past the end.  Encoding is a host-side computation (no driver call reaches the device).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+static bool make_coef_map(CUtensorMap *map, const int16_t *coef, uint32_t total_blocks, uint32_t box_blocks)
+{
+    const EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc)
+        return false;
+    const cuuint64_t dims[2] = {64, total_blocks};
+    const cuuint64_t strides[1] = {128}; // bytes between blocks
+    const cuuint32_t box[2] = {64, box_blocks};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<int16_t *>(coef), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+cudaError_t launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches)
 {
     const uint32_t total_mcus = a.g.nimages * a.g.mcus_per_image;
     const uint32_t grid = (total_mcus + IDCT_MCUS_PER_CTA - 1) / IDCT_MCUS_PER_CTA;
+    alignas(64) CUtensorMap map;
+    if (!make_coef_map(&map, a.coef, a.g.total_blocks, a.g.ncomp * IDCT_MCUS_PER_CTA))
+        return cudaErrorNotSupported; // no cuTensorMapEncodeTiled in this driver, or it rejected the geometry
     if (a.g.ncomp == 3)
-        idct_kernel<3><<<grid, 3 * IDCT_MCUS_PER_CTA, sizeof(IdctSmem<3>), s>>>(a);
+        idct_kernel<3><<<grid, 3 * IDCT_MCUS_PER_CTA, sizeof(IdctSmem<3>), s>>>(a, map);
     else
-        idct_kernel<1><<<grid, IDCT_MCUS_PER_CTA, sizeof(IdctSmem<1>), s>>>(a);
+        idct_kernel<1><<<grid, IDCT_MCUS_PER_CTA, sizeof(IdctSmem<1>), s>>>(a, map);
     ++*launches;
+    return cudaSuccess;
 }
 
 void launch_idct_patch(const IdctArgs &a, cudaStream_t s, uint32_t *launches)

@@ -110,7 +110,7 @@ void launch_entropy_scan(const EntropyArgs &a, cudaStream_t s, uint32_t *launche
 void launch_entropy_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);  // Huffman final pass
 void launch_entropy_expand(const EntropyArgs &a, cudaStream_t s, uint32_t *launches); // record final pass
 void launch_dc_scan(const DcArgs &a, cudaStream_t s, uint32_t *launches);
-void launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches);
+cudaError_t launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches); // fails without a tensor-map encoder in the driver
 void launch_idct_patch(const IdctArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_merge_dc(int16_t *coef_out, const int16_t *coef, const int16_t *dc, const int16_t *dcdiff, uint32_t nblocks,
                      uint32_t flags, cudaStream_t s);

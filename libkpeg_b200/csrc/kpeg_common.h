@@ -81,7 +81,9 @@ struct DeviceTables {
     LutSet luts;
     HuffCanon canon[MAX_LUTS];
     float qscale[MAX_COMP][64]; // zig-zag order: quantiser * AAN prescale (fast IDCT path)
-    float qpair[MAX_COMP][64];  // the same values in the pair order of the packed transform: [2 p + h] = position pair_nat(p, h)
+    // K3 stages the next two arrays in shared memory with one bulk copy each (16-byte aligned, contiguous):
+    alignas(16) float qpair[MAX_COMP][64]; // qscale in the pair order of the packed transform: [2 p + h] = position pair_nat(p, h)
+    alignas(16) float qdc[MAX_COMP][64];   // qpair with every AC entry zero: what a block that loses its AC terms (F1) multiplies by
     int32_t qint[MAX_COMP][64]; // zig-zag order: plain quantiser (exact path), MCU.cpp:110-112
     double cosd[8][8];          // cosd[x][u] = cos((2x+1)*u*pi/16) in double, host libm -- the factor of MCU.cpp:193
     float cc[8][8];             // (float)Cu*(float)Cv of MCU.cpp:190-193

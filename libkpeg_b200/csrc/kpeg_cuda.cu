@@ -296,7 +296,7 @@ int enqueue_downstream(kpeg_ctx *ctx, Lane &L)
     mark(ctx, L, KPEG_T_ENTROPY_WRITE);
     launch_dc_scan(J.da, s, &J.launches);
     mark(ctx, L, KPEG_T_DC_SCAN);
-    launch_idct(J.ia, s, &J.launches);
+    CK(launch_idct(J.ia, s, &J.launches));
     mark(ctx, L, KPEG_T_IDCT);
     launch_idct_patch(J.ia, s, &J.launches);
     mark(ctx, L, KPEG_T_IDCT_PATCH);
