@@ -102,9 +102,12 @@ KPEG_HD constexpr double aan_scale_c(int k)
 // 1 / (prescale of the coefficient at natural index nat): |prescaled dequantised coefficient| * this = |c| * q
 KPEG_HD constexpr float aan_unscale(int nat) { return (float)(8.0 / (aan_scale_c(nat >> 3) * aan_scale_c(nat & 7))); }
 
-// Pair layout of a block going into the packed transform (kernels.cu): pair p = rp * 8 + c holds the natural
-// positions (2 rp, c) and (2 rp + 1, c) -- two rows side by side, so the row pass transforms two rows per instruction.
-KPEG_HD constexpr int pair_nat(int p, int half) { return ((p >> 3) * 2 + half) * 8 + (p & 7); }
+// Pair layout of a block going into the packed transform (kernels.cu): pair p = rp * 8 + c holds column c of two
+// rows side by side -- rows (0,1), (4,7), (2,5), (6,3) for rp = 0..3.  The row pass transforms two rows per
+// instruction; in the column pass these are exactly the operand pairs of the first two butterfly stages
+// (v0 +- v4 beside v1 +- v7, v2 +- v6 beside v5 +- v3), so it needs no register transposition.
+KPEG_HD constexpr int pair_row(int rp, int half) { return rp == 0 ? (half ? 1 : 0) : rp == 1 ? (half ? 7 : 4) : rp == 2 ? (half ? 5 : 2) : (half ? 3 : 6); }
+KPEG_HD constexpr int pair_nat(int p, int half) { return pair_row(p >> 3, half) * 8 + (p & 7); }
 
 inline double aan_scale(int k)
 {

@@ -1445,6 +1445,18 @@ constexpr uint32_t IDCT_PREFETCH_STRIPS = KPEG_IDCT_PREFETCH_STRIPS;
 constexpr uint32_t BLK_NONZERO = 1u, BLK_WIDE = 2u;
 constexpr float COLOUR_SAFE_A = 4.0f * (COLOUR_FAST_RANGE - 8.0f);
 
+// Bit layout of a block's 64-bit tie mask (x = rows 0..3, y = rows 4..7): the bit of sample (row, col) in its word.
+// The upper 16 bits hold columns 0..3, the lower 16 columns 4..7; inside, earlier samples sit higher.
+__host__ __device__ constexpr int tie_bit(int row, int col) { return ((col & 4) ? 0 : 16) + 15 - (4 * (row & 3) + (col & 3)); }
+// bits of one row in its word
+__host__ __device__ constexpr uint32_t tie_row_bits(int row) { return (0xFu << (28 - 4 * (row & 3))) | (0xFu << (12 - 4 * (row & 3))); }
+// inverse: bit index b of word w (0 = rows 0..3, 1 = rows 4..7) -> sample index row * 8 + col
+__device__ __forceinline__ int tie_sample(int w, int b)
+{
+    const int k = 15 - (b & 15);
+    return (4 * w + (k >> 2)) * 8 + ((b & 16) ? 0 : 4) + (k & 3);
+}
+
 template <int NC>
 struct IdctSmem {
     static constexpr int NM = IDCT_MCUS_PER_CTA;
@@ -1557,7 +1569,7 @@ __device__ __forceinline__ float dequant_dezigzag(const uint4 (&ch)[8], const fl
 }
 
 // Packed 2-D transform, first half: the row pass, two rows per instruction.
-// P[rp * 8 + c] = rows 2rp, 2rp+1 at column c, in place.
+// P[rp * 8 + c] = rows pair_row(rp, 0), pair_row(rp, 1) at column c, in place.
 __device__ __forceinline__ void idct_rows_packed(F2 (&P)[32])
 {
 #pragma unroll
@@ -1566,21 +1578,35 @@ __device__ __forceinline__ void idct_rows_packed(F2 (&P)[32])
                   P[rp * 8 + 6], P[rp * 8 + 7]);
 }
 
-// Second half for the column pair cp (columns 2cp, 2cp+1): 2x2 register transposes of the row-pass output, then
-// the column pass, two columns per instruction.  Out: Q[r] = row r at columns 2cp, 2cp+1.
-// Same operations in the same order as idct8x8_fast (idct_core.h), lane for lane.
-template <int CP>
-__device__ __forceinline__ void idct_cols_packed(const F2 (&P)[32], F2 (&Q)[8])
+// Second half, one column: idct8_aan (idct_core.h) over the eight rows, same operations in the same order.
+// With X = (v0, v1), Y = (v4, v7), X2 = (v2, v5), Y2 = (v6, v3) the first two butterfly stages of the even part
+// (low lanes) and of the odd part (high lanes) are the same instruction, so they run packed; the rest is scalar on
+// the halves.  Nothing is moved between registers.  v[r] = row r of this column.
+__device__ __forceinline__ void idct8_column(F2 X, F2 Y, F2 X2, F2 Y2, float (&v)[8])
 {
-#pragma unroll
-    for (int rp = 0; rp < 4; ++rp) {
-        float a, b, c, d; // a = (2rp, 2cp)  b = (2rp+1, 2cp)  c = (2rp, 2cp+1)  d = (2rp+1, 2cp+1)
-        unpack2(P[rp * 8 + 2 * CP], a, b);
-        unpack2(P[rp * 8 + 2 * CP + 1], c, d);
-        Q[2 * rp] = pack2(a, c);
-        Q[2 * rp + 1] = pack2(b, d);
-    }
-    idct8_aan(Q[0], Q[1], Q[2], Q[3], Q[4], Q[5], Q[6], Q[7]);
+    const F2 S1 = lane_add(X, Y), D1 = lane_sub(X, Y);     // (t10, z11)  (t11, z12)
+    const F2 S2 = lane_add(X2, Y2), D2 = lane_sub(X2, Y2); // (t13, z13)  (v2 - v6, z10)
+    const F2 E = lane_add(S1, S2), F = lane_sub(S1, S2);   // (e0, o7)    (e3, z11 - z13)
+    // even part
+    const float t11 = lo2(D1), t13 = lo2(S2), e0 = lo2(E), e3 = lo2(F);
+    const float n12 = lane_fma_k(lo2(D2), -1.414213562373095f, t13); // -(t12)
+    const float e1 = lane_sub(t11, n12), e2 = lane_add(t11, n12);
+    // odd part
+    const float z12 = hi2(D1), z10 = hi2(D2), o7 = hi2(E);
+    const float z5 = lane_mul_k(lane_add(z10, z12), 1.847759065022573f);
+    const float t20 = lane_fma_k(z12, -1.082392200292394f, z5);
+    const float t22 = lane_fma_k(z10, -2.613125929752753f, z5);
+    const float o6 = lane_sub(t22, o7);
+    const float n5 = lane_fma_k(hi2(F), -1.414213562373095f, o6); // -(o5)
+    const float o4 = lane_add(t20, n5);
+    v[0] = lane_add(e0, o7);
+    v[7] = lane_sub(e0, o7);
+    v[1] = lane_add(e1, o6);
+    v[6] = lane_sub(e1, o6);
+    v[2] = lane_sub(e2, n5);
+    v[5] = lane_add(e2, n5);
+    v[3] = lane_add(e3, o4);
+    v[4] = lane_sub(e3, o4);
 }
 
 // Four ints -> four bytes with unsigned saturation (cvt.pack.sat: two values per instruction).
@@ -1945,44 +1971,49 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
         const float thresh = 0.5f - tie_band(A);
         idct_rows_packed(P);
 
-        // (x + 1.5*2^23) - 1.5*2^23 == rint(x) for |x| < 2^22; samples inside the tie band are
-        // collected in a 64-bit mask (predicated ORs, no branches)
-        uint32_t tie_lo = 0, tie_hi = 0;
+        // (x + 1.5*2^23) - 1.5*2^23 == rint(x) for |x| < 2^22.  A sample is inside the tie band when its distance d
+        // from the rounded value exceeds thresh, i.e. when d*d - thresh^2 >= 0: one FFMA2 per sample pair, and the
+        // complement of the sign bit is shifted into the block's mask with one funnel shift per sample (no compares,
+        // no predicates).  thresh^2 is taken a hair low, so the packed test can only flag more than |d| > thresh does.
+        // Bit layout of the masks: tie_bit(row, col) below.
+        const float t2 = thresh > 0.0f ? thresh * thresh * (1.0f - 1.0f / 2097152.0f) : 0.0f;
+        const F2 neg_t2 = splat2(-t2);
         const F2 magic = splat2(RINT_MAGIC);
+        uint32_t keep[2][2]; // [half][word]: sign bits = "outside the band", 16 per half and word
         auto half_block = [&](auto HALF) { // columns 4 half .. 4 half + 3 of all eight rows
             constexpr int half = decltype(HALF)::value;
-            F2 Q0[8], Q1[8];
-            idct_cols_packed<2 * half>(P, Q0);
-            idct_cols_packed<2 * half + 1>(P, Q1);
-            uint32_t tl = 0, th = 0; // this half's own accumulators: two short chains of predicated ORs, not one long one
+            float v[4][8]; // [column - 4 half][row]
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                idct8_column(P[0 * 8 + 4 * half + c], P[1 * 8 + 4 * half + c], P[2 * 8 + 4 * half + c], P[3 * 8 + 4 * half + c], v[c]);
+            uint32_t kl = 0, kh = 0;
 #pragma unroll
             for (int row = 0; row < 8; ++row) {
                 float r[4];
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    const F2 x = k ? Q1[row] : Q0[row];
+                    const F2 x = pack2(v[2 * k][row], v[2 * k + 1][row]);
                     const F2 rr = lane_sub(lane_add(x, magic), magic);
                     const F2 d = lane_sub(x, rr);
+                    const F2 e = lane_fma(d, d, neg_t2);
                     unpack2(rr, r[2 * k], r[2 * k + 1]);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int col = 4 * half + 2 * k + h;
-                        if (fabsf(h ? hi2(d) : lo2(d)) > thresh) {
-                            if (row < 4)
-                                tl |= 1u << (row * 8 + col);
-                            else
-                                th |= 1u << (row * 8 + col - 32);
-                        }
+                    if (row < 4) {
+                        kl = __funnelshift_l((uint32_t)float_bits(lo2(e)), kl, 1);
+                        kl = __funnelshift_l((uint32_t)float_bits(hi2(e)), kl, 1);
+                    } else {
+                        kh = __funnelshift_l((uint32_t)float_bits(lo2(e)), kh, 1);
+                        kh = __funnelshift_l((uint32_t)float_bits(hi2(e)), kh, 1);
                     }
                 }
                 sm.samp[((comp * 8 + row) * 2 + half) * NM + ml] = make_float4(r[0], r[1], r[2], r[3]);
             }
-            tie_lo |= tl;
-            tie_hi |= th;
+            keep[half][0] = kl;
+            keep[half][1] = kh;
         };
         half_block(std::integral_constant<int, 0>{});
         half_block(std::integral_constant<int, 1>{});
-        sm.tie[bl] = make_uint2(tie_lo, tie_hi);
+        // 16 bits per (half, word), first sample shifted in ends up highest: bit 15 - (4 (row & 3) + (col & 3))
+        sm.tie[bl] = make_uint2(~((keep[0][0] << 16) | (keep[1][0] & 0xFFFFu)), ~((keep[0][1] << 16) | (keep[1][1] & 0xFFFFu)));
         sm.flag[bl] = (uint8_t)((A != 0.0f ? BLK_NONZERO : 0u) | (A > COLOUR_SAFE_A ? BLK_WIDE : 0u));
     }
     __syncthreads();
@@ -2087,26 +2118,29 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
             plo |= tmask[c].x;
             phi |= tmask[c].y;
         }
-        if (NC == 3) { // rows comp, comp + 3, comp + 6; row r = bits 8r .. 8r+7
-            plo &= comp == 0 ? 0xFF0000FFu : (comp == 1 ? 0x0000FF00u : 0x00FF0000u);
-            phi &= comp == 0 ? 0x00FF0000u : (comp == 1 ? 0xFF0000FFu : 0x0000FF00u);
+        if (NC == 3) { // rows comp, comp + 3, comp + 6
+            plo &= comp == 0 ? (tie_row_bits(0) | tie_row_bits(3)) : (comp == 1 ? tie_row_bits(1) : tie_row_bits(2));
+            phi &= comp == 0 ? tie_row_bits(6) : (comp == 1 ? (tie_row_bits(4) | tie_row_bits(7)) : tie_row_bits(5));
         }
         while (plo | phi) {
-            int s;
+            int w, b;
             if (plo) {
-                s = __ffs(plo) - 1;
+                w = 0;
+                b = __ffs(plo) - 1;
                 plo &= plo - 1;
             } else {
-                s = 32 + __ffs(phi) - 1;
+                w = 1;
+                b = __ffs(phi) - 1;
                 phi &= phi - 1;
             }
+            const int s = tie_sample(w, b);
             const int row = s >> 3, j = s & 7;
             if (by * 8u + (uint32_t)row >= H || bx * 8u + (uint32_t)j >= W)
                 continue;
             uint32_t cm = 0;
 #pragma unroll
             for (int c = 0; c < NC; ++c)
-                cm |= (((s < 32 ? tmask[c].x : tmask[c].y) >> (s & 31)) & 1u) << c;
+                cm |= (((w ? tmask[c].y : tmask[c].x) >> b) & 1u) << c;
             // fast samples of this pixel, re-read from shared memory
             const float *sp = reinterpret_cast<const float *>(sm.samp);
             float fy, fcb = 0.0f, fcr = 0.0f;
