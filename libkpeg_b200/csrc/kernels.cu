@@ -1430,10 +1430,6 @@ struct ZzNat {
 };
 
 constexpr int IDCT_REC_CAP = 134;
-#ifndef KPEG_IDCT_PREFETCH_STRIPS
-#define KPEG_IDCT_PREFETCH_STRIPS (148 * 8) // CTAs resident on the device at a time
-#endif
-constexpr uint32_t IDCT_PREFETCH_STRIPS = KPEG_IDCT_PREFETCH_STRIPS;
 #ifndef KPEG_IDCT_MIN_CTAS
 #define KPEG_IDCT_MIN_CTAS 8
 #endif
@@ -1871,6 +1867,7 @@ __device__ __forceinline__ uint32_t colour_row8(const float4 (&yy)[2], const flo
             px[3 * j] = px[3 * j + 1] = px[3 * j + 2] = float_bits(Y[j] + (RINT_MAGIC + 128.0f)) - RINT_MAGIC_BITS;
     } else {
         const F2 magic = splat2(RINT_MAGIC);
+        const F2 tiny = splat2(__int_as_float(1)); // 2^-149
         F2 dg[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -1881,17 +1878,20 @@ __device__ __forceinline__ uint32_t colour_row8(const float4 (&yy)[2], const flo
             // ycc_to_rgb_fast (idct_core.h), two pixels per instruction
             const F2 yr = lane_add(y, splat2(127.501f));
             const F2 yg = lane_add(y, splat2(127.5f));
-            const F2 tr = lane_add(lane_fma_k(cr, 1.402f, yr), magic);
-            const F2 tb = lane_add(lane_fma_k(cb, 1.772f, yr), magic);
+            const F2 r = lane_fma_k(cr, 1.402f, yr);
+            const F2 b = lane_fma_k(cb, 1.772f, yr);
             const F2 g = lane_fma_k(cr, -0.714136f, lane_fma_k(cb, -0.344136f, yg));
-            const F2 tg = lane_add(g, magic);
-            dg[k] = lane_sub(g, lane_sub(tg, magic));
+            dg[k] = lane_sub(g, lane_sub(lane_add(g, magic), magic));
+            // rint() to an integer WITHOUT the magic-number bias: v * 2^-149 is a denormal whose bit pattern is
+            // rint(v) itself (round to nearest even, like the magic add) when v >= 0, and has the sign bit set -- a
+            // large negative int -- when v < 0, which the saturating pack turns into 0 just as it would -|v|.
+            const F2 ri = lane_mul(r, tiny), gi = lane_mul(g, tiny), bi = lane_mul(b, tiny);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int j = 2 * k + h;
-                px[3 * j] = float_bits(h ? hi2(tr) : lo2(tr)) - RINT_MAGIC_BITS;
-                px[3 * j + 1] = float_bits(h ? hi2(tg) : lo2(tg)) - RINT_MAGIC_BITS;
-                px[3 * j + 2] = float_bits(h ? hi2(tb) : lo2(tb)) - RINT_MAGIC_BITS;
+                px[3 * j] = float_bits(h ? hi2(ri) : lo2(ri));
+                px[3 * j + 1] = float_bits(h ? hi2(gi) : lo2(gi));
+                px[3 * j + 2] = float_bits(h ? hi2(bi) : lo2(bi));
             }
         }
         // G within COLOUR_G_BAND of an integer somewhere in the row (0.2 % of the pixels): ONE test per row on the
