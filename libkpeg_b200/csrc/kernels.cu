@@ -1430,6 +1430,7 @@ struct ZzNat {
 };
 
 constexpr int IDCT_REC_CAP = 134;
+constexpr uint32_t IDCT_PREFETCH_AHEAD = 148u * 8u; // strips resident on the device at a time
 #ifndef KPEG_IDCT_MIN_CTAS
 #define KPEG_IDCT_MIN_CTAS 8
 #endif
@@ -1810,6 +1811,10 @@ __device__ __forceinline__ void tma_load_tile_2d(uint32_t dst, const CUtensorMap
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_tile_2d(const CUtensorMap *map, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -1940,6 +1945,9 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
         tma_load_tile_2d(smem_u32(sm.coef), &coef_map, 0, (int)blk0, bar);
         bulk_load(smem_u32(sm.qpair), a.tables->qpair, table_bytes, bar);
         bulk_load(smem_u32(sm.qdc), a.tables->qdc, table_bytes, bar);
+        // the strip that will run in this CTA's slot next (CTAs are dispatched in index order): pull it into L2 now
+        if (blk0 + IDCT_PREFETCH_AHEAD * NB < a.g.total_blocks)
+            tma_prefetch_tile_2d(&coef_map, 0, (int)(blk0 + IDCT_PREFETCH_AHEAD * NB));
         sm.nrec = 0;
         const uint32_t img = mcu0 / a.g.mcus_per_image, mi = mcu0 - img * a.g.mcus_per_image;
         sm.img0 = img;
