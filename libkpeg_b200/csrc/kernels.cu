@@ -1663,29 +1663,37 @@ __device__ __forceinline__ ExactCtx exact_ctx(const IdctArgs &a)
     return x;
 }
 
-template <int... Is>
-__device__ __forceinline__ void nonzero_mask_natural(const uint4 (&ch)[8], uint32_t &lo, uint32_t &hi,
-                                                     std::integer_sequence<int, Is...>)
+// coefficient I (zig-zag index) of a block held as eight 16-byte chunks, as an integer
+template <int I>
+__device__ __forceinline__ int chunk_coef_int(const uint4 (&ch)[8])
 {
-    // bit NAT(i) set iff coefficient i (zig-zag index) is non-zero; all indices are compile-time
-    lo = 0;
-    hi = 0;
-    auto one = [&](auto I) {
-        constexpr int i = decltype(I)::value;
-        constexpr int nat = ZzNat<i>::value;
-        constexpr int k = i >> 3, j = (i & 7) >> 1, h = i & 1;
-        const uint32_t w = j == 0 ? ch[k].x : (j == 1 ? ch[k].y : (j == 2 ? ch[k].z : ch[k].w));
-        const bool nz = (h ? (w >> 16) : (w & 0xFFFFu)) != 0u;
-        if (nat < 32)
-            lo |= nz ? (1u << (nat & 31)) : 0u;
-        else
-            hi |= nz ? (1u << (nat & 31)) : 0u;
-    };
-    (one(std::integral_constant<int, Is>{}), ...);
+    constexpr int k = I >> 3, j = (I & 7) >> 1, hi = I & 1;
+    const uint32_t w = j == 0 ? ch[k].x : (j == 1 ? ch[k].y : (j == 2 ? ch[k].z : ch[k].w));
+    return (int)(short)(hi ? (w >> 16) : (w & 0xFFFFu));
 }
 
-// The reference's evaluation (idct_core.h exact_sample) of sample s of global block gb, visiting only the
-// non-zero coefficients, in ascending natural order (== u outer, v inner, MCU.cpp:184-187).
+// The 64 terms of the reference's sum (idct_core.h exact_sample, MCU.cpp:184-198) in ascending natural order
+// (== u outer, v inner), fully unrolled: every index is a compile-time constant, the block stays in registers, and
+// there is no branch and no load in the chain.  A zero coefficient contributes +-0, which leaves the float
+// accumulator unchanged, so evaluating all 64 terms gives the same bits as skipping the zero ones.
+template <int... Ns>
+__device__ __forceinline__ float exact_terms(const uint4 (&ch)[8], const int32_t *q, const double (&cx)[8],
+                                             const double (&cy)[8], float c00, float c01, std::integer_sequence<int, Ns...>)
+{
+    float sum = 0.0f;
+    auto term = [&](auto N) {
+        constexpr int nat = decltype(N)::value, zi = NatZz<nat>::value, u = nat >> 3, v = nat & 7;
+        const int F = chunk_coef_int<zi>(ch) * q[zi];                                   // MCU.cpp:110-112, :115-120
+        const float cc = (u == 0 && v == 0) ? c00 : ((u == 0 || v == 0) ? c01 : 1.0f); // Cu * Cv
+        const float t = mul_f32(cc, (float)F);
+        const double d = mul_f64(mul_f64((double)t, cx[u]), cy[v]);
+        sum = (float)add_f64((double)sum, d); // float accumulator, rounded every term
+    };
+    (term(std::integral_constant<int, Ns>{}), ...);
+    return sum;
+}
+
+// The reference's evaluation of sample s of global block gb (component comp).
 __device__ __noinline__ int exact_sample_global(const int16_t *coef, const int16_t *dc, const int16_t *dcdiff,
                                                 const ExactSmem *es, uint32_t parity, uint32_t gb, uint32_t comp, int s)
 {
@@ -1697,28 +1705,14 @@ __device__ __noinline__ int exact_sample_global(const int16_t *coef, const int16
         ch[k] = drop_ac ? make_uint4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uint4 *>(blk) + k);
     const int dcv = dc[gb];
     ch[0].x = (ch[0].x & 0xFFFF0000u) | ((uint32_t)dcv & 0xFFFFu);
-    uint32_t lo, hi;
-    nonzero_mask_natural(ch, lo, hi, std::make_integer_sequence<int, 64>{});
     const int x = s >> 3, y = s & 7;
-    const int32_t *q = es->qint[comp];
-    float sum = 0.0f;
-    while (lo | hi) {
-        int nat;
-        if (lo) {
-            nat = __ffs(lo) - 1;
-            lo &= lo - 1;
-        } else {
-            nat = 32 + __ffs(hi) - 1;
-            hi &= hi - 1;
-        }
-        const int zi = es->nat2zz[nat];
-        const int cq = zi == 0 ? dcv : (int)blk[zi]; // L1 hit: the line was just loaded
-        const int u = nat >> 3, v = nat & 7;
-        const int F = cq * q[zi];
-        const float t = mul_f32(es->cc[u][v], (float)F);
-        const double d = mul_f64(mul_f64((double)t, es->cosd[x][u]), es->cosd[y][v]);
-        sum = (float)add_f64((double)sum, d);
+    double cx[8], cy[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        cx[k] = es->cosd[x][k];
+        cy[k] = es->cosd[y][k];
     }
+    const float sum = exact_terms(ch, es->qint[comp], cx, cy, es->cc[0][0], es->cc[0][1], std::make_integer_sequence<int, 64>{});
     const float out = (float)mul_f64(0.25, (double)sum);
     return round_half_away(out);
 }
@@ -2275,7 +2269,7 @@ void kernels_configure(int max_concurrent_jobs)
                                                           sizeof(WriteSmemTail)) != cudaSuccess || per_sm < 1)
             per_sm = 6;
         g_k1_expand_grid_cap = (uint32_t)(sms * per_sm);
-        g_patch_grid = (uint32_t)(sms * 8);
+        g_patch_grid = (uint32_t)(sms * 16); // one record per thread for up to 300 k records; CTAs beyond the list return at once
         cudaFuncSetAttribute(entropy_relay_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)k1_sparse_smem_bytes(1024));
         g_sm_count = (uint32_t)sms;
