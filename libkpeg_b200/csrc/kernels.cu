@@ -1284,24 +1284,62 @@ __device__ __forceinline__ Dc3 dc_block_scan(Dc3 x, Dc3 *s_w /*[DC_THREADS/32]*/
     return x;
 }
 
+// The thread's DC_MCUS_PER_THREAD consecutive MCUs: their DC differences (as 8-byte words when the run is whole and
+// aligned) and the running inclusive values.  The reset predicate (mcu_is_reset) is evaluated once with two
+// divisions and then stepped.
 __device__ __forceinline__ Dc3 dc_thread_local(const DcArgs &a, uint32_t m0, uint32_t total_mcus, Dc3 incl[DC_MCUS_PER_THREAD])
 {
+    static_assert(DC_MCUS_PER_THREAD == 4, "the 8-byte access pattern below is written for four MCUs per thread");
+    const uint32_t nc = a.g.ncomp;
+    int16_t v[DC_MCUS_PER_THREAD * 3];
+#pragma unroll
+    for (int i = 0; i < DC_MCUS_PER_THREAD * 3; ++i)
+        v[i] = 0;
+    const int16_t *src = a.dcdiff + (size_t)m0 * nc;
+    const bool whole = m0 + DC_MCUS_PER_THREAD <= total_mcus && (reinterpret_cast<uintptr_t>(src) & 7u) == 0;
+    if (whole && nc == 3) {
+        uint2 w[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            w[i] = __ldg(reinterpret_cast<const uint2 *>(src) + i);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const uint32_t x = (i & 2) ? w[i >> 2].y : w[i >> 2].x;
+            v[i] = (int16_t)((i & 1) ? (x >> 16) : (x & 0xFFFFu));
+        }
+    } else if (whole && nc == 1) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(src));
+        v[0] = (int16_t)(w.x & 0xFFFFu), v[3] = (int16_t)(w.x >> 16), v[6] = (int16_t)(w.y & 0xFFFFu), v[9] = (int16_t)(w.y >> 16);
+    } else {
+#pragma unroll
+        for (int k = 0; k < DC_MCUS_PER_THREAD; ++k)
+            if (m0 + k < total_mcus)
+                for (uint32_t c = 0; c < nc; ++c)
+                    v[k * 3 + c] = src[k * nc + c];
+    }
+    uint32_t mi = m0 % a.g.mcus_per_image;
+    uint32_t ri = a.g.restart_interval ? mi % a.g.restart_interval : mi;
     Dc3 run;
     run.f = 0;
     run.v[0] = run.v[1] = run.v[2] = 0;
 #pragma unroll
     for (int k = 0; k < DC_MCUS_PER_THREAD; ++k) {
-        const uint32_t m = m0 + k;
         Dc3 e;
         e.f = 0;
         e.v[0] = e.v[1] = e.v[2] = 0;
-        if (m < total_mcus) {
-            e.f = mcu_is_reset(a.g, m) ? 1u : 0u;
-            for (uint32_t c = 0; c < a.g.ncomp; ++c)
-                e.v[c] = a.dcdiff[m * a.g.ncomp + c];
+        if (m0 + k < total_mcus) {
+            e.f = ri == 0u ? 1u : 0u; // == mcu_is_reset(a.g, m0 + k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                e.v[c] = v[k * 3 + c];
         }
         run = dc_combine(run, e);
         incl[k] = run;
+        ++mi, ++ri;
+        if (mi == a.g.mcus_per_image)
+            mi = 0, ri = 0;
+        else if (a.g.restart_interval && ri == a.g.restart_interval)
+            ri = 0;
     }
     return run;
 }
@@ -1385,14 +1423,26 @@ __global__ void __launch_bounds__(DC_THREADS) dc_apply_kernel(DcArgs a)
     pre.v[2] = a.tile_carry[blockIdx.x * 4 + 2];
     if (threadIdx.x > 0)
         pre = dc_combine(pre, s_incl[threadIdx.x - 1]);
+    const uint32_t nc = a.g.ncomp;
+    int16_t *dst = a.dc + (size_t)m0 * nc;
+    Dc3 r[DC_MCUS_PER_THREAD];
 #pragma unroll
-    for (int k = 0; k < DC_MCUS_PER_THREAD; ++k) {
-        const uint32_t m = m0 + k;
-        if (m < total_mcus) {
-            const Dc3 r = dc_combine(pre, incl[k]);
-            for (uint32_t c = 0; c < a.g.ncomp; ++c)
-                a.dc[m * a.g.ncomp + c] = (int16_t)r.v[c];
-        }
+    for (int k = 0; k < DC_MCUS_PER_THREAD; ++k)
+        r[k] = dc_combine(pre, incl[k]);
+    const bool whole = m0 + DC_MCUS_PER_THREAD <= total_mcus && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0;
+    auto h = [](int32_t x) { return (uint32_t)x & 0xFFFFu; };
+    if (whole && nc == 3) { // 12 values = three 8-byte stores
+        reinterpret_cast<uint2 *>(dst)[0] = make_uint2(h(r[0].v[0]) | (h(r[0].v[1]) << 16), h(r[0].v[2]) | (h(r[1].v[0]) << 16));
+        reinterpret_cast<uint2 *>(dst)[1] = make_uint2(h(r[1].v[1]) | (h(r[1].v[2]) << 16), h(r[2].v[0]) | (h(r[2].v[1]) << 16));
+        reinterpret_cast<uint2 *>(dst)[2] = make_uint2(h(r[2].v[2]) | (h(r[3].v[0]) << 16), h(r[3].v[1]) | (h(r[3].v[2]) << 16));
+    } else if (whole && nc == 1) {
+        reinterpret_cast<uint2 *>(dst)[0] = make_uint2(h(r[0].v[0]) | (h(r[1].v[0]) << 16), h(r[2].v[0]) | (h(r[3].v[0]) << 16));
+    } else {
+#pragma unroll
+        for (int k = 0; k < DC_MCUS_PER_THREAD; ++k)
+            if (m0 + k < total_mcus)
+                for (uint32_t c = 0; c < nc; ++c)
+                    dst[k * nc + c] = (int16_t)r[k].v[c];
     }
 }
 
