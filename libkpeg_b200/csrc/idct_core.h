@@ -7,7 +7,7 @@
 // *float* accumulator and *double* products, then rounds half away from zero.  About 0.7 % of all
 // samples of a natural image are exact x.5 ties in real arithmetic and the reference resolves them
 // by its own rounding noise, so no "accurate" IDCT reproduces its integers.  We therefore run
-//   (1) a fast separable fp32 IDCT (AAN factorisation, 5 multiplies + 29 adds per 8 points) and
+//   (1) a fast separable fp32 IDCT (AAN factorisation: 25 adds, 1 multiply, 4 fused multiply-adds per 8 points) and
 //       accept its rounding wherever the value is provably further from a tie than the combined
 //       error bound of both evaluations, and
 //   (2) for the few samples inside that band, the reference's own operation sequence
@@ -183,8 +183,7 @@ KPEG_HD void idct8x8_fast(float f[64])
 
 // |fast - reference| <= TIE_REL * A + TIE_ABS with A = sum |dequantised coefficient| = sum |c_i| * q_i
 // (derivation in DESIGN.md "K3 rounding"; margin checked by tests/test_emu_logic.py).  The kernel
-// gets A exactly, in integers, for one instruction per coefficient pair (SIMD abs + dp2a on the
-// packed int16 coefficients and the 8-bit quantisers).
+// accumulates A with one FFMA per coefficient while dequantising.
 constexpr float TIE_REL = 1.5e-6f;
 constexpr float TIE_ABS = 2.0e-5f;
 

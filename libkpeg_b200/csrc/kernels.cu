@@ -1460,16 +1460,16 @@ void launch_dc_scan(const DcArgs &a, cudaStream_t s, uint32_t *launches)
 //
 // idct_kernel: one CTA reconstructs a strip of IDCT_MCUS_PER_CTA consecutive MCUs (a contiguous chunk
 // of the coefficient buffer, and -- when the strip does not wrap -- 8 contiguous runs of pixels).
-//   stage 0  coalesced 16-byte loads of the strip's coefficients into shared memory (XOR-swizzled
-//            so that the per-thread 128-byte reads of stage 1 are bank-conflict free)
-//   stage 1  one thread per 8x8 block, all 64 values in registers: dequantise (AAN prescale folded
-//            into the quantiser), de-zigzag by register renaming, separable fp32 IDCT, rounding,
-//            tie-band test (a 64-bit mask per block)
-//   stage 2  per pixel row: YCbCr -> RGB (fp32 with proven margin, double otherwise), pack, store;
+//   stage 0  the copy engine brings the strip's coefficients (2-D TMA tile, 128-byte swizzle: the per-thread
+//            128-byte reads of stage 1 are bank-conflict free) and the quantiser tables into shared memory
+//   stage 1  one thread per 8x8 block, all 64 values in registers, two fp32 lanes per instruction (FADD2 / FMUL2 /
+//            FFMA2): dequantise (AAN prescale folded into the quantiser), de-zigzag by register renaming, separable
+//            fp32 IDCT, rounding, tie-band test (a 64-bit mask per block)
+//   stage 2  per pixel row: YCbCr -> RGB on pixel pairs (fp32 with proven margin, double otherwise), pack, store;
 //            pixels with a sample inside the tie band are ALSO appended to a global record list
 // idct_patch_kernel: one thread per record re-evaluates the flagged samples in the reference's own
 // operation order (exact_sample), redoes the colour conversion and rewrites the pixel.  Keeping this
-// out of the fused kernel matters: it is a long, strictly serial double-precision chain on ~1 % of
+// out of the fused kernel matters: it is a long, strictly serial double-precision chain on ~0.3 % of
 // the pixels; inside the strip kernel it kept two of three warps waiting at a barrier.
 
 __device__ __constant__ ZigZagTables c_zz = make_zigzag_tables();
