@@ -1480,6 +1480,8 @@ struct ZzNat {
 };
 
 constexpr int IDCT_REC_CAP = 134;
+constexpr int IDCT_REC_FIXED = 16;          // slots of the global record list every strip owns
+constexpr uint32_t TIE_EMPTY = 0xFFFFFFFFu; // pixel index of an unused slot
 constexpr uint32_t IDCT_PREFETCH_AHEAD = 148u * 8u; // strips resident on the device at a time
 #ifndef KPEG_IDCT_MIN_CTAS
 #define KPEG_IDCT_MIN_CTAS 8
@@ -2217,49 +2219,92 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
             a.overflow_mcu[blockIdx.x] = 1u; // this strip has pixels that did not fit the record list
     }
     // ---- flush the strip's tie records --------------------------------------------------------------
+    // Strip i owns slots [i * IDCT_REC_FIXED, (i + 1) * IDCT_REC_FIXED) of the global list and always writes all of
+    // them (unused ones as TIE_EMPTY): the common case needs no reservation, so no CTA ends on the round trip of a
+    // global atomic.  Records beyond the strip's own slots (rare) go to the shared tail of the list.
     __syncthreads();
-    const uint32_t nrec = min(sm.nrec, (uint32_t)IDCT_REC_CAP);
-    if (nrec == 0u && sm.nrec == 0u)
+    const uint32_t found = sm.nrec, nrec = min(found, (uint32_t)IDCT_REC_CAP);
+    auto global_record = [&](uint32_t i) {
+        const uint2 c = sm.rec[i];
+        const uint32_t rm = mcu0 + (c.x & 31u), rs = (c.x >> 5) & 63u;
+        const uint32_t img = rm / a.g.mcus_per_image, mi = rm - img * a.g.mcus_per_image;
+        const uint32_t by = mi / a.g.mcus_x, bx = mi - by * a.g.mcus_x;
+        uint4 r; // the record format of make_tie_record
+        r.x = img * a.g.width * a.g.height + (by * 8u + (rs >> 3)) * a.g.width + bx * 8u + (rs & 7u);
+        r.y = rm;
+        r.z = rs | (((c.x >> 11) & 7u) << 8) | (c.x & 0xFFFF0000u);
+        r.w = c.y;
+        return r;
+    };
+    if (t < IDCT_REC_FIXED)
+        a.tie_rec[(size_t)blockIdx.x * IDCT_REC_FIXED + t] = (uint32_t)t < nrec ? global_record(t) : make_uint4(TIE_EMPTY, 0, 0, 0);
+    if (found <= (uint32_t)IDCT_REC_FIXED) {
+        if (t == 0 && found)
+            atomicAdd(&a.meta->exact_samples, found); // statistics only: nobody waits for it
         return;
+    }
     if (t == 0) {
-        sm.rec_base = atomicAdd(&a.meta->tie_records, nrec);
-        if (sm.nrec > (uint32_t)IDCT_REC_CAP)
-            atomicAdd(&a.meta->tie_inline, sm.nrec - (uint32_t)IDCT_REC_CAP);
+        sm.rec_base = atomicAdd(&a.meta->tie_records, nrec - (uint32_t)IDCT_REC_FIXED);
+        atomicAdd(&a.meta->exact_samples, (uint32_t)IDCT_REC_FIXED);
+        if (found > (uint32_t)IDCT_REC_CAP)
+            atomicAdd(&a.meta->tie_inline, found - (uint32_t)IDCT_REC_CAP);
     }
     __syncthreads();
-    const uint32_t base = sm.rec_base;
-    for (uint32_t i = t; i < nrec; i += NB) {
-        if (base + i < a.tie_cap) {
-            const uint2 c = sm.rec[i];
-            const uint32_t rm = mcu0 + (c.x & 31u), rs = (c.x >> 5) & 63u;
-            const uint32_t img = rm / a.g.mcus_per_image, mi = rm - img * a.g.mcus_per_image;
-            const uint32_t by = mi / a.g.mcus_x, bx = mi - by * a.g.mcus_x;
-            uint4 r; // the record format of make_tie_record
-            r.x = img * a.g.width * a.g.height + (by * 8u + (rs >> 3)) * a.g.width + bx * 8u + (rs & 7u);
-            r.y = rm;
-            r.z = rs | (((c.x >> 11) & 7u) << 8) | (c.x & 0xFFFF0000u);
-            r.w = c.y;
-            a.tie_rec[base + i] = r;
+    const uint32_t base = gridDim.x * (uint32_t)IDCT_REC_FIXED + sm.rec_base; // the tail starts after every strip's own slots
+    for (uint32_t i = IDCT_REC_FIXED + t; i < nrec; i += NB) {
+        const uint32_t at = base + (i - IDCT_REC_FIXED);
+        if (at < a.tie_cap) {
+            a.tie_rec[at] = global_record(i);
         } else {
             a.overflow_mcu[blockIdx.x] = 1u; // global list full
-            if (i == t)
-                atomicAdd(&a.meta->tie_inline, 1u);
+            atomicAdd(&a.meta->tie_inline, 1u);
         }
     }
 }
 
-// One thread per tie record (grid-stride).
+// The record list: strips * IDCT_REC_FIXED slots owned by the strips (sparse: unused slots are TIE_EMPTY) followed by
+// a compact tail of meta->tie_records entries.  A warp walks its share of the sparse part 32 slots at a time,
+// collects the used ones in a small shared-memory stack and resolves them 32 at a time, so the long serial
+// evaluation always runs with full warps.
 template <int NC>
 __global__ void __launch_bounds__(128) idct_patch_kernel(IdctArgs a)
 {
     __shared__ ExactSmem es;
-    const uint32_t n = min(a.meta->tie_records, a.tie_cap);
-    if (blockIdx.x * blockDim.x >= n && a.meta->tie_inline == 0u)
-        return;
+    __shared__ uint4 s_q[4][64];
     exact_smem_load(es, a.tables);
     const ExactCtx x = exact_ctx(a);
+    const uint32_t total_mcus_ = a.g.nimages * a.g.mcus_per_image;
+    const uint32_t nslots = ((total_mcus_ + IDCT_MCUS_PER_CTA - 1) / IDCT_MCUS_PER_CTA) * (uint32_t)IDCT_REC_FIXED;
+    {
+        const uint32_t lane = threadIdx.x & 31u, wl = threadIdx.x >> 5;
+        const uint32_t nwarps = gridDim.x * 4u, w = blockIdx.x * 4u + wl;
+        const uint32_t per = (((nslots + nwarps - 1u) / nwarps) + 31u) & ~31u;
+        const uint32_t s0 = w * per, s1 = min(s0 + per, nslots);
+        uint32_t qn = 0; // warp-uniform
+        for (uint32_t sl = s0; sl < s1; sl += 32u) {
+            uint4 r = make_uint4(TIE_EMPTY, 0, 0, 0);
+            if (sl + lane < s1)
+                r = a.tie_rec[sl + lane];
+            const bool used = r.x != TIE_EMPTY;
+            const uint32_t bal = __ballot_sync(0xffffffffu, used);
+            if (used)
+                s_q[wl][qn + __popc(bal & ((1u << lane) - 1u))] = r;
+            qn += __popc(bal);
+            __syncwarp();
+            if (qn >= 32u) {
+                r = s_q[wl][qn - 32u + lane];
+                __syncwarp();
+                qn -= 32u;
+                resolve_and_store_pixel<NC>(x, &es, r);
+                __syncwarp();
+            }
+        }
+        if (lane < qn)
+            resolve_and_store_pixel<NC>(x, &es, s_q[wl][lane]);
+    }
+    const uint32_t n = a.tie_cap > nslots ? min(a.meta->tie_records, a.tie_cap - nslots) : 0u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        resolve_and_store_pixel<NC>(x, &es, a.tie_rec[i]);
+        resolve_and_store_pixel<NC>(x, &es, a.tie_rec[nslots + i]);
     // Overflow (pathologically flat images: more tied pixels than the record list holds).  Strips that
     // reported an overflow are redone wholesale on the exact path: every sample of every pixel.
     if (a.meta->tie_inline == 0u)
@@ -2290,7 +2335,7 @@ __global__ void __launch_bounds__(128) idct_patch_kernel(IdctArgs a)
     }
 }
 
-static uint32_t g_patch_grid = 148 * 8;
+static uint32_t g_patch_grid = 148 * 4;
 
 void kernels_configure(int max_concurrent_jobs)
 {
@@ -2319,7 +2364,7 @@ void kernels_configure(int max_concurrent_jobs)
                                                           sizeof(WriteSmemTail)) != cudaSuccess || per_sm < 1)
             per_sm = 6;
         g_k1_expand_grid_cap = (uint32_t)(sms * per_sm);
-        g_patch_grid = (uint32_t)(sms * 16); // one record per thread for up to 300 k records; CTAs beyond the list return at once
+        g_patch_grid = (uint32_t)(sms * 4); // warps take contiguous shares of the record list: enough records each to fill whole batches
         cudaFuncSetAttribute(entropy_relay_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)k1_sparse_smem_bytes(1024));
         g_sm_count = (uint32_t)sms;

@@ -573,7 +573,7 @@ int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
                     used_rounds = (uint32_t)r;
         }
         stats->sync_rounds = std::max(stats->sync_rounds, used_rounds);
-        stats->exact_samples += h_meta->tie_records; // pixels with at least one sample on the exact path
+        stats->exact_samples += h_meta->tie_records + h_meta->exact_samples; // pixels with at least one sample on the exact path (tail + strips' own slots)
         stats->kernel_launches += J.launches;
         add_times(ctx, L, stats);
     }
