@@ -344,6 +344,7 @@ KPEG_HD void expand_run(uint32_t &k, uint32_t nrec, uint32_t &slot, uint32_t &z,
     constexpr int BATCH = 8; // records fetched together: their loads are independent of the running state
     // software pipeline: the batch after the one being expanded is already in flight
     uint32_t nx[BATCH];
+    uint32_t adv_max = 0, reach_max = 0;
 #pragma unroll
     for (int j = 0; j < BATCH; ++j)
         nx[j] = (k < nrec && slot < slot_limit && k + (uint32_t)j < nrec) ? rec_at(k + (uint32_t)j) : 0u;
@@ -369,11 +370,13 @@ KPEG_HD void expand_run(uint32_t &k, uint32_t nrec, uint32_t &slot, uint32_t &z,
                 } else {
                     const uint32_t size = (r >> 16) & 15u, adv = (r >> 20) & 127u;
                     const bool has_value = size != 0u;
-                    st |= adv == ENTRY_ADV_INVALID ? ST_BAD_CODE : 0u;
-                    st |= (has_value && z + adv > 64u) ? ST_SLOT_OVERFLOW : 0u;
+                    uint32_t zn = z + adv;
+                    // error flags as two running maxima, folded into st after the loop: an invalid code has the
+                    // (otherwise impossible) advance 127; a coefficient may not land beyond slot 63 of its block
+                    adv_max = adv > adv_max ? adv : adv_max;
+                    reach_max = (has_value && zn > reach_max) ? zn : reach_max;
                     const int32_t val = extend_value(r & REC_RAW_MASK, size | (size == 0u ? 1u : 0u));
                     sink.put(z == 0u, slot, adv, has_value && slot + adv <= total_slots, val);
-                    uint32_t zn = z + adv;
                     zn = zn > 64u ? 64u : zn;
                     slot += zn - z;
                     z = zn == 64u ? 0u : zn;
@@ -381,6 +384,8 @@ KPEG_HD void expand_run(uint32_t &k, uint32_t nrec, uint32_t &slot, uint32_t &z,
             }
         }
     }
+    st |= adv_max == ENTRY_ADV_INVALID ? ST_BAD_CODE : 0u;
+    st |= reach_max > 64u ? ST_SLOT_OVERFLOW : 0u;
 }
 
 // One-shot convenience: whole subsequence, coefficients straight to global memory.

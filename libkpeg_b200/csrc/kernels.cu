@@ -1032,8 +1032,11 @@ __global__ void __launch_bounds__(WRITE_THREADS) entropy_write_kernel(EntropyArg
 // several are in flight), tracks (slot, zig-zag index) and drops values into the shared-memory window.
 struct GlobalRecAt {
     const uint32_t *base;
-    uint32_t stride;
-    __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return __ldg(base + k * stride); }
+    uint32_t stride_bytes; // 128 in the warp-interleaved list, 4 in a private area: one IMAD.WIDE per address
+    __device__ __forceinline__ uint32_t operator()(uint32_t k) const
+    {
+        return __ldg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(base) + (size_t)k * stride_bytes));
+    }
 };
 
 __global__ void __launch_bounds__(WRITE_THREADS) entropy_expand_kernel(EntropyArgs a)
@@ -1045,6 +1048,10 @@ __global__ void __launch_bounds__(WRITE_THREADS) entropy_expand_kernel(EntropyAr
     const uint32_t total_slots = a.g.total_blocks * 64u;
     const uint32_t t = threadIdx.x;
     uint32_t st = 0;
+    // shared addresses of the window: made opaque, or the compiler re-derives them from the CTA's shared window
+    // base (S2R + LEA) for every record instead of keeping two registers
+    uint32_t win_obuf = (uint32_t)__cvta_generic_to_shared(tail.obuf), win_dcbuf = (uint32_t)__cvta_generic_to_shared(tail.dcbuf);
+    asm volatile("" : "+r"(win_obuf), "+r"(win_dcbuf));
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t sub0 = tile * WRITE_THREADS, sub = sub0 + t;
         const uint32_t s_begin = a.start_slot[sub0];
@@ -1057,13 +1064,13 @@ __global__ void __launch_bounds__(WRITE_THREADS) entropy_expand_kernel(EntropyAr
         bool done = true;
         GlobalRecAt R;
         R.base = a.rec + rec_base_index(sub, a.rec_kmax);
-        R.stride = 32u;
+        R.stride_bytes = 128u;
         if (sub < nsub) {
             const uint32_t nr = a.nrec[sub];
             n = min(nr & NREC_MASK, a.rec_kmax);
             if (nr >> 10) { // redone in a sparse relay round: private contiguous area
                 R.base = a.rec_alt + (size_t)((nr >> 10) - 1u) * a.rec_kmax;
-                R.stride = 1u;
+                R.stride_bytes = 4u;
             }
             slot = a.start_slot[sub];
             z = sub ? (a.state[sub - 1].cz & 0xFFu) : 0u;
@@ -1083,8 +1090,8 @@ __global__ void __launch_bounds__(WRITE_THREADS) entropy_expand_kernel(EntropyAr
             __syncthreads();
             if (!done) {
                 SmemSink sink;
-                sink.obuf_addr = (uint32_t)__cvta_generic_to_shared(tail.obuf);
-                sink.dc_addr = (uint32_t)__cvta_generic_to_shared(tail.dcbuf);
+                sink.obuf_addr = win_obuf;
+                sink.dc_addr = win_dcbuf;
                 sink.slot0 = wb << 6;
                 sink.block0 = wb;
                 const uint32_t limit = wb < b_end ? (wb + WRITE_WIN_BLOCKS) << 6 : 0xFFFFFFFFu;
