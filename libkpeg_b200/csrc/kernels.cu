@@ -869,8 +869,7 @@ constexpr int WRITE_THREADS = 64;
 constexpr int WRITE_WIN_BLOCKS = KPEG_WIN_BLOCKS;
 
 struct WriteSmemTail {
-    int16_t obuf[WRITE_WIN_BLOCKS * 64];
-    int16_t dcbuf[WRITE_WIN_BLOCKS];
+    int16_t obuf[WRITE_WIN_BLOCKS * 64]; // slot 0 of a block carries its DC difference until the flush
 };
 
 __host__ __device__ inline size_t k1_write_words_bytes(uint32_t sub_bits)
@@ -891,16 +890,16 @@ __host__ __device__ inline size_t k1_write_smem_bytes(uint32_t sub_bits)
 }
 
 struct SmemSink {
-    uint32_t obuf_addr, dc_addr; // shared byte addresses
-    uint32_t slot0, block0;      // first slot / block of the window
-    // one predicated store: DC difference -> dcbuf[block - block0], AC coefficient -> obuf[pos - slot0]
-    __device__ __forceinline__ void put(bool is_dc, uint32_t slot, uint32_t adv, bool valid, int32_t v) const
+    uint32_t obuf_addr; // shared byte address of the window
+    uint32_t slot0;     // first slot of the window
+    // One predicated store, one address formula: an AC coefficient goes to slot (slot + adv - 1); a DC difference
+    // arrives with z == 0 and advance 1, i.e. the same formula puts it into slot 0 of its block -- the slot the
+    // coefficient buffer leaves to K2's integrated DC value.  The window flush copies slot 0 of every block to dcdiff[].
+    __device__ __forceinline__ void put(bool, uint32_t slot, uint32_t adv, bool valid, int32_t v) const
     {
-        const uint32_t off = is_dc ? (slot >> 6) - block0 : slot + adv - 1u - slot0;
-        const uint32_t lim = is_dc ? (uint32_t)WRITE_WIN_BLOCKS : (uint32_t)(WRITE_WIN_BLOCKS * 64);
-        const uint32_t addr = (is_dc ? dc_addr : obuf_addr) + 2u * off;
-        if (valid && off < lim)
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v));
+        const uint32_t off = slot + adv - 1u - slot0;
+        if (valid && off < (uint32_t)(WRITE_WIN_BLOCKS * 64))
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(obuf_addr + 2u * off), "h"((uint16_t)v));
     }
 };
 
@@ -936,7 +935,7 @@ __device__ __forceinline__ void write_flush_window(const EntropyArgs &a, const W
     for (uint32_t i = t; i < nblk; i += WRITE_THREADS) {
         const uint32_t b = wb + i;
         if ((b << 6) >= s_begin && (b << 6) < s_end)
-            a.dcdiff[b] = tail.dcbuf[i];
+            a.dcdiff[b] = tail.obuf[i << 6];
     }
 }
 
@@ -998,9 +997,7 @@ __global__ void __launch_bounds__(WRITE_THREADS) entropy_write_kernel(EntropyArg
             if (!done) {
                 SmemSink sink;
                 sink.obuf_addr = (uint32_t)__cvta_generic_to_shared(tail.obuf);
-                sink.dc_addr = (uint32_t)__cvta_generic_to_shared(tail.dcbuf);
                 sink.slot0 = wb << 6;
-                sink.block0 = wb;
                 // past the tile's own range (corrupt stream): finish in one go, writes fall outside the window
                 const uint32_t limit = wb < b_end ? (wb + WRITE_WIN_BLOCKS) << 6 : 0xFFFFFFFFu;
                 decode_run<true, false>(d, W, L, S, a.g, end, limit, sink, NoRecorder{});
@@ -1050,8 +1047,8 @@ __global__ void __launch_bounds__(WRITE_THREADS) entropy_expand_kernel(EntropyAr
     uint32_t st = 0;
     // shared addresses of the window: made opaque, or the compiler re-derives them from the CTA's shared window
     // base (S2R + LEA) for every record instead of keeping two registers
-    uint32_t win_obuf = (uint32_t)__cvta_generic_to_shared(tail.obuf), win_dcbuf = (uint32_t)__cvta_generic_to_shared(tail.dcbuf);
-    asm volatile("" : "+r"(win_obuf), "+r"(win_dcbuf));
+    uint32_t win_obuf = (uint32_t)__cvta_generic_to_shared(tail.obuf);
+    asm volatile("" : "+r"(win_obuf));
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t sub0 = tile * WRITE_THREADS, sub = sub0 + t;
         const uint32_t s_begin = a.start_slot[sub0];
@@ -1091,9 +1088,7 @@ __global__ void __launch_bounds__(WRITE_THREADS) entropy_expand_kernel(EntropyAr
             if (!done) {
                 SmemSink sink;
                 sink.obuf_addr = win_obuf;
-                sink.dc_addr = win_dcbuf;
                 sink.slot0 = wb << 6;
-                sink.block0 = wb;
                 const uint32_t limit = wb < b_end ? (wb + WRITE_WIN_BLOCKS) << 6 : 0xFFFFFFFFu;
                 expand_run(k, n, slot, z, st, R, a.g, limit, sink);
                 done = k >= n;
