@@ -472,11 +472,11 @@ constexpr uint32_t NREC_MASK = 1023u;
 struct GlobalRecorder {
     uint32_t *base; // &rec[rec_base_index(sub)], or the subsequence's private area
     uint32_t kmax;
-    uint32_t stride; // 32 in the warp-interleaved layout, 1 in a private area
+    uint32_t stride_bytes; // 128 in the warp-interleaved layout, 4 in a private area: one IMAD.WIDE per address
     __device__ __forceinline__ void emit(uint32_t k, uint32_t w) const
     {
         if (k < kmax)
-            base[(size_t)k * stride] = w;
+            *reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(base) + (size_t)k * stride_bytes) = w;
     }
 };
 
@@ -491,7 +491,8 @@ __device__ __forceinline__ SubState relay_decode(const EntropyArgs &a, const Wor
         GlobalRecorder R;
         R.base = a.rec + rec_base_index(sub, a.rec_kmax);
         R.kmax = a.rec_kmax;
-        R.stride = 32u;
+        asm volatile("" : "+r"(R.kmax)); // a register, not a reload of the kernel parameter per symbol
+        R.stride_bytes = 128u;
         uint32_t area = 0;
         if (sparse) {
             area = a.nrec[sub] >> 10;
@@ -501,7 +502,7 @@ __device__ __forceinline__ SubState relay_decode(const EntropyArgs &a, const Wor
             }
             if (area) {
                 R.base = a.rec_alt + (size_t)(area - 1u) * a.rec_kmax;
-                R.stride = 1u;
+                R.stride_bytes = 4u;
             }
         }
         decode_run<false, true>(d, W, L, S, a.g, end, 0xFFFFFFFFu, NullSink{}, R);
