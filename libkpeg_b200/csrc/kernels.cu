@@ -2010,8 +2010,11 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
         dcv = a.dc[blk0 + bl];
         drop_ac = (a.g.flags & 1u) && a.dcdiff[blk0 + bl] == 0; // MCU.cpp:97-104
     }
-    __syncthreads(); // the barrier object is initialised: everyone may wait on it
-    mbar_wait(bar, 0);
+    // One thread waits for the copy engine (its wait acquires the tile), the CTA barrier hands the data on: the other
+    // warps sleep at the barrier instead of polling, and the barrier object never needs to be visible to them.
+    if (t == 0)
+        mbar_wait(bar, 0);
+    __syncthreads();
 
     // ---- stage 1: one thread = one 8x8 block ------------------------------------------------------
     uint4 ch[8];
@@ -2230,8 +2233,22 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
     auto global_record = [&](uint32_t i) {
         const uint2 c = sm.rec[i];
         const uint32_t rm = mcu0 + (c.x & 31u), rs = (c.x >> 5) & 63u;
-        const uint32_t img = rm / a.g.mcus_per_image, mi = rm - img * a.g.mcus_per_image;
-        const uint32_t by = mi / a.g.mcus_x, bx = mi - by * a.g.mcus_x;
+        // position of the record's MCU from the strip's origin (as in stage 2: no division when the strip wraps at most once)
+        uint32_t img = sm.img0, by = sm.by0, bx = sm.bx0 + (c.x & 31u);
+        if (a.g.mcus_x >= (uint32_t)NM) {
+            if (bx >= a.g.mcus_x) {
+                bx -= a.g.mcus_x;
+                if (++by == a.g.mcus_y) {
+                    by = 0;
+                    ++img;
+                }
+            }
+        } else {
+            img = rm / a.g.mcus_per_image;
+            const uint32_t mi = rm - img * a.g.mcus_per_image;
+            by = mi / a.g.mcus_x;
+            bx = mi - by * a.g.mcus_x;
+        }
         uint4 r; // the record format of make_tie_record
         r.x = img * a.g.width * a.g.height + (by * 8u + (rs >> 3)) * a.g.width + bx * 8u + (rs & 7u);
         r.y = rm;
