@@ -2385,6 +2385,8 @@ void kernels_configure(int max_concurrent_jobs)
             per_sm = 6;
         g_k1_expand_grid_cap = (uint32_t)(sms * per_sm);
         g_patch_grid = (uint32_t)(sms * 4); // warps take contiguous shares of the record list: enough records each to fill whole batches
+        if (const char *e = getenv("KPEG_PATCH_PER_SM")) // experiments
+            g_patch_grid = (uint32_t)(sms * std::max(1, atoi(e)));
         cudaFuncSetAttribute(entropy_relay_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)k1_sparse_smem_bytes(1024));
         g_sm_count = (uint32_t)sms;
