@@ -123,10 +123,17 @@ __global__ void __launch_bounds__(UNSTUFF_THREADS) unstuff_count_kernel(UnstuffA
         rst &= in_range;
     }
     a.cls[chunk] = keep | (rst << 16);
-    // pack both counts into one reduction: kept <= 4096 per tile, rst <= 2048
-    uint32_t tot;
-    block_exclusive_sum<UNSTUFF_THREADS>(__popc(keep) | (__popc(rst) << 16), s_w, tot);
+    // only the tile's totals are needed here: one warp-wide integer reduction (REDUX) per warp and one barrier.
+    // Both counts in one word: kept <= 4096 per tile, rst <= 2048.
+    const uint32_t wsum = __reduce_add_sync(0xffffffffu, __popc(keep) | (__popc(rst) << 16));
+    if (lane == 0)
+        s_w[threadIdx.x >> 5] = wsum;
+    __syncthreads();
     if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < UNSTUFF_THREADS / 32; ++w)
+            tot += s_w[w];
         a.tile_kept[blockIdx.x] = tot & 0xFFFFu;
         a.tile_rst[blockIdx.x] = tot >> 16;
     }
