@@ -397,4 +397,22 @@ uint32_t emu_classify_compare(const uint8_t *scan, uint32_t len, int *bad_differ
     return mismatches;
 }
 
+// The quantiser tables K3 stages by bulk copy (host_tables.h): qscale in zig-zag order, qpair / qdc in the pair
+// order of the packed transform; pair_nat_out[2 p + h] = natural position of half h of pair p.
+int emu_pair_tables(const kpeg_plan *plan, float *qscale_out, float *qpair_out, float *qdc_out, int *pair_nat_out)
+{
+    DeviceTables *T = new DeviceTables;
+    const char *why = nullptr;
+    const int rc = build_device_tables(plan, T, &why);
+    if (rc == KPEG_OK) {
+        memcpy(qscale_out, T->qscale, sizeof T->qscale);
+        memcpy(qpair_out, T->qpair, sizeof T->qpair);
+        memcpy(qdc_out, T->qdc, sizeof T->qdc);
+        for (int j = 0; j < 64; ++j)
+            pair_nat_out[j] = pair_nat(j >> 1, j & 1);
+    }
+    delete T;
+    return rc;
+}
+
 } // extern "C"

@@ -135,6 +135,8 @@ def emu():
         lib.emu_huff_lookup.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_int]
         lib.emu_zigzag.restype = C.c_int
         lib.emu_zigzag.argtypes = [C.c_int]
+        lib.emu_pair_tables.restype = C.c_int
+        lib.emu_pair_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _emu = lib
     return _emu
 

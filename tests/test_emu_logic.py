@@ -179,3 +179,28 @@ def test_byte_parallel_unstuff_classification_matches_bytewise():
         mism = lib.emu_classify_compare(buf.ctypes.data, n, C.byref(bad))
         assert mism == 0, f"trial {trial}: {mism} chunks classified differently"
         assert bad.value == 0, f"trial {trial}: unexpected-marker verdict differs"
+
+
+def test_pair_order_quantiser_tables(lena_jpg):
+    """The tables K3 stages by bulk copy (host_tables.h): `qpair` is `qscale` permuted into the pair order of the
+    packed transform, `qdc` keeps only the DC entry; the pair order is a permutation of the 64 positions that puts
+    rows (0,1), (4,7), (2,5), (6,3) side by side at every column -- the operand pairs of the first two butterfly
+    stages of the column pass (idct_core.h pair_nat, kernels.cu idct8_column)."""
+    plan, _, _ = K.parse_jfif(np.frombuffer(lena_jpg, dtype=np.uint8))
+    emu = H.emu()
+    qscale = np.zeros((3, 64), dtype=np.float32)
+    qpair = np.zeros((3, 64), dtype=np.float32)
+    qdc = np.zeros((3, 64), dtype=np.float32)
+    pn = np.zeros(64, dtype=np.int32)
+    assert emu.emu_pair_tables(C.addressof(plan), qscale.ctypes.data, qpair.ctypes.data, qdc.ctypes.data, pn.ctypes.data) == 0
+    assert sorted(pn.tolist()) == list(range(64))
+    rows = {(int(pn[2 * p]) // 8, int(pn[2 * p + 1]) // 8) for p in range(32)}
+    assert rows == {(0, 1), (4, 7), (2, 5), (6, 3)}
+    for p in range(32):
+        assert pn[2 * p] % 8 == pn[2 * p + 1] % 8 == p % 8  # both halves of a pair sit in the same column
+    nat2zz = {emu.emu_zigzag(i): i for i in range(64)}  # emu_zigzag: zig-zag index -> natural position
+    for c in range(plan.ncomp):
+        assert (qscale[c] > 0).all()
+        for j in range(64):
+            assert qpair[c, j] == qscale[c, nat2zz[int(pn[j])]]
+            assert qdc[c, j] == (qpair[c, j] if pn[j] == 0 else 0.0)
