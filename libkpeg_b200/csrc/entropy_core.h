@@ -83,6 +83,16 @@ KPEG_HD int32_t extend_value(uint32_t v, uint32_t n)
     return (v >> (n - 1u)) ? (int32_t)v : (int32_t)v - (int32_t)((1u << n) - 1u);
 }
 
+// The same for n in 0..15 where the result for n == 0 is never used (a symbol without a value): no fix-up of n.
+KPEG_HD int32_t extend_value_or_any(uint32_t v, uint32_t n)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_rc(v, 0u, n - 1u) ? (int32_t)v : (int32_t)v - (int32_t)((1u << n) - 1u); // clamped shift: defined for n == 0
+#else
+    return extend_value(v, n | (n == 0u ? 1u : 0u));
+#endif
+}
+
 struct StreamView {
     const uint32_t *seg_bit; // [nseg + 2]: start bit of every restart segment, then total_bits, then 0xFFFFFFFF
     uint32_t total_bits;
@@ -92,11 +102,13 @@ struct StreamView {
 // put(is_dc, slot, adv, valid, value): a DC difference belongs to block slot >> 6, an AC coefficient
 // to absolute slot (slot + adv - 1); `valid` is false for symbols that carry no value (EOB, ZRL).
 struct NullSink {
+    static constexpr bool bounds_itself = false;
     KPEG_HD void put(bool, uint32_t, uint32_t, bool, int32_t) const {}
 };
 
 // straight to global memory: coef[] must be zero-filled beforehand
 struct GlobalSink {
+    static constexpr bool bounds_itself = false;
     int16_t *coef;   // [blocks][64]
     int16_t *dcdiff; // [blocks]
     KPEG_HD void put(bool is_dc, uint32_t slot, uint32_t adv, bool valid, int32_t v) const
@@ -375,8 +387,10 @@ KPEG_HD void expand_run(uint32_t &k, uint32_t nrec, uint32_t &slot, uint32_t &z,
                     // (otherwise impossible) advance 127; a coefficient may not land beyond slot 63 of its block
                     adv_max = adv > adv_max ? adv : adv_max;
                     reach_max = (has_value && zn > reach_max) ? zn : reach_max;
-                    const int32_t val = extend_value(r & REC_RAW_MASK, size | (size == 0u ? 1u : 0u));
-                    sink.put(z == 0u, slot, adv, has_value && slot + adv <= total_slots, val);
+                    const int32_t val = extend_value_or_any(r & REC_RAW_MASK, size);
+                    // a sink that bounds its own writes (the shared-memory window) needs no check against the end of
+                    // the coefficient buffer: what lands beyond it stays in the window and is never flushed
+                    sink.put(z == 0u, slot, adv, Sink::bounds_itself ? has_value : (has_value && slot + adv <= total_slots), val);
                     zn = zn > 64u ? 64u : zn;
                     slot += zn - z;
                     z = zn == 64u ? 0u : zn;

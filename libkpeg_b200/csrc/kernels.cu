@@ -898,6 +898,7 @@ __host__ __device__ inline size_t k1_write_smem_bytes(uint32_t sub_bits)
 }
 
 struct SmemSink {
+    static constexpr bool bounds_itself = true; // put() drops whatever falls outside the window
     uint32_t obuf_addr; // shared byte address of the window
     uint32_t slot0;     // first slot of the window
     // One predicated store, one address formula: an AC coefficient goes to slot (slot + adv - 1); a DC difference
