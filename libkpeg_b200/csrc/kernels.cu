@@ -1531,7 +1531,7 @@ struct IdctSmem {
     float2 qdc[NC][32];           // the same with every AC entry zero: what a block that loses its AC terms (F1) multiplies by
     uint2 tie[NB];                // per block: 64-bit mask of the samples inside the tie band
     uint8_t flag[NB];             // per block: BLK_NONZERO | BLK_WIDE (decides the colour variant of its MCU)
-    uint2 rec[IDCT_REC_CAP];      // tie records of this strip (compact form), flushed to the global list with ONE atomic
+    uint2 rec[IDCT_REC_CAP];      // tie records of this strip (compact form): the first IDCT_REC_FIXED go to the strip's own slots of the global list
     uint32_t nrec, rec_base;
     uint32_t img0, by0, bx0;      // image / block row / block column of the strip's first MCU (divisions done once, by thread 0)
     uint32_t pad_;
@@ -2221,7 +2221,7 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
             // y = fast Y | fast Cb << 16; expanded to the global record when the strip's list is flushed
             const uint2 rec = make_uint2((uint32_t)ml | ((uint32_t)s << 5) | (cm << 11) | ((uint32_t)(uint16_t)(int)fcr << 16),
                                          (uint32_t)(uint16_t)(int)fy | ((uint32_t)(uint16_t)(int)fcb << 16));
-            const uint32_t at = atomicAdd(&sm.nrec, 1u); // shared-memory counter: one global atomic per strip
+            const uint32_t at = atomicAdd(&sm.nrec, 1u); // shared-memory counter: no global atomic unless the strip outgrows its own slots
             if (at < (uint32_t)IDCT_REC_CAP)
                 sm.rec[at] = rec;
             else

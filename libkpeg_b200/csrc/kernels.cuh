@@ -22,10 +22,10 @@ struct DevMeta {
     uint32_t total_bits;   // 8 * total_kept
     uint32_t nsub;         // subsequences actually used
     uint32_t status;       // ST_* bits
-    uint32_t exact_samples;
+    uint32_t exact_samples; // tie records written to the strips' own slots of the list (statistics)
     uint32_t colour_exact;
     uint32_t final_slot;   // absolute slot the last subsequence ended on
-    uint32_t tie_records;  // pixels queued for the exact (reference-order) re-evaluation
+    uint32_t tie_records;  // records in the shared tail of the tie list (beyond the strips' own slots)
     uint32_t tie_inline;   // pixels resolved inside K3 because the record buffer was full
     uint32_t relay_rounds; // last relay round that ran (device-side round loop)
     uint32_t grid_bar;     // arrival counter of the relay loop's grid barrier
@@ -90,7 +90,7 @@ struct IdctArgs {
     const DeviceTables *tables;
     uint8_t *pixels; // [nimages][height][width][ncomp]
     DevMeta *meta;
-    uint4 *tie_rec;       // [tie_cap] pixels with at least one sample inside the tie band
+    uint4 *tie_rec;       // [tie_cap] pixels with at least one sample inside the tie band: 16 slots per strip, then a shared tail
     uint32_t tie_cap;
     uint32_t *overflow_mcu; // [strips] set when a strip had tied pixels that did not fit tie_rec
     JobGeom g;
