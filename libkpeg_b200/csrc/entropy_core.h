@@ -71,7 +71,7 @@ struct PlainLuts {
     {
         const uint32_t ti = toff >> LUT_BITS;
         if (e)
-            return set->longlut[ti][((e >> 5) - 1u) * 64u + ((win >> 16) & 63u)];
+            return set->longlut[ti][((e >> 5) - 1u) * (uint32_t)SUB_SIZE + ((win >> 16) & (uint32_t)(SUB_SIZE - 1))];
         return huff_slow_lookup(canon[ti], win);
     }
 };

@@ -52,10 +52,10 @@ inline int build_huff_lut(const uint8_t counts[16], const uint8_t *symbols, bool
         // does any code start with this prefix?  (windows [prefix<<6, (prefix+1)<<6) below bound[16])
         if ((prefix << (16 - LUT_BITS)) >= canon->bound[16])
             break;
-        if (set->long_n[ti] + 64u > (uint32_t)LONG_CAP)
+        if (set->long_n[ti] + (uint32_t)SUB_SIZE > (uint32_t)LONG_CAP)
             break; // no room: these prefixes keep entry 0 and use the canonical search
-        const uint32_t sub = set->long_n[ti] / 64u;
-        for (uint32_t low = 0; low < 64u; ++low) {
+        const uint32_t sub = set->long_n[ti] / (uint32_t)SUB_SIZE;
+        for (uint32_t low = 0; low < (uint32_t)SUB_SIZE; ++low) {
             const uint32_t w = (prefix << (16 - LUT_BITS)) | low;
             uint32_t e = ENTRY_INVALID;
             for (int L = LUT_BITS + 1; L <= 16; ++L) {
@@ -65,10 +65,10 @@ inline int build_huff_lut(const uint8_t counts[16], const uint8_t *symbols, bool
                     break;
                 }
             }
-            set->longlut[ti][sub * 64u + low] = (uint16_t)e;
+            set->longlut[ti][sub * (uint32_t)SUB_SIZE + low] = (uint16_t)e;
         }
         set->fast[ti][prefix] = (uint16_t)((sub + 1u) << 5);
-        set->long_n[ti] += 64u;
+        set->long_n[ti] += (uint32_t)SUB_SIZE;
     }
     return 0;
 }

@@ -355,7 +355,7 @@ struct SmemLuts {
         const uint32_t ti = toff >> LUT_BITS;
         if (e) { // pointer to a 64-entry sub-table indexed by stream bits 10..15
             uint16_t v;
-            const uint32_t idx = ti * (uint32_t)LONG_CAP + ((e >> 5) - 1u) * 64u + ((win >> 16) & 63u);
+            const uint32_t idx = ti * (uint32_t)LONG_CAP + ((e >> 5) - 1u) * (uint32_t)SUB_SIZE + ((win >> 16) & (uint32_t)(SUB_SIZE - 1));
             asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(long_addr + 2u * idx));
             return v;
         }

@@ -29,9 +29,14 @@ namespace kpeg {
 // bits 5-8 magnitude bits ("category"), bits 9-15 slot advance (number of zig-zag positions the
 // symbol consumes: 1 for DC, run+1 for AC, 16 for ZRL, 64 for EOB -- the consumer clamps to the
 // end of the block).  0 = not resolved.  The speculative passes only need the total and the advance.
-constexpr int LUT_BITS = 10;
+#ifndef KPEG_LUT_BITS
+#define KPEG_LUT_BITS 10
+#endif
+constexpr int LUT_BITS = KPEG_LUT_BITS;
 constexpr int LUT_SIZE = 1 << LUT_BITS;
-constexpr int LONG_CAP = 512;  // second-level entries per table: 8 sub-tables of 64 (one per 10-bit prefix of long codes)
+constexpr int SUB_BITS = 16 - LUT_BITS;   // a sub-table resolves the rest of a 16-bit window
+constexpr int SUB_SIZE = 1 << SUB_BITS;
+constexpr int LONG_CAP = LUT_BITS >= 10 ? 512 : 640; // second-level entries per table: 8 sub-tables of 64, or 5 of 128
 // no code matches: "length" 17, no magnitude bits, and a slot advance no real symbol has (records carry the
 // entry, so the expander recognises the pattern by it)
 constexpr uint32_t ENTRY_ADV_INVALID = 127u;
