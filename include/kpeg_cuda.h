@@ -104,8 +104,8 @@ typedef struct kpeg_ctx kpeg_ctx;
 int kpeg_parse_jfif(const uint8_t *file, size_t len, kpeg_plan *plan, size_t *scan_off, size_t *scan_len);
 
 /* ---- context ------------------------------------------------------------------------------ */
-/* One context per (thread, device): owns a CUDA stream, device scratch and pinned staging,
- * all grown on demand and reused across decodes.  Not thread-safe; use one context per thread. */
+/* One context per (thread, device): owns eight lanes (a CUDA stream with its own device scratch and pinned
+ * bookkeeping each), all grown on demand and reused across decodes.  Not thread-safe; use one context per thread. */
 int kpeg_cuda_create(int device, kpeg_ctx **out);
 void kpeg_cuda_destroy(kpeg_ctx *ctx);
 const char *kpeg_cuda_last_error(const kpeg_ctx *ctx); /* never NULL */

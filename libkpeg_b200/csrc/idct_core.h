@@ -247,7 +247,7 @@ KPEG_HD void ycc_to_rgb_exact(int y, int cb, int cr, int &R, int &G, int &B)
 //  * 1.402 d = 701 d / 500 and 1.772 d = 443 d / 250 are either integers or at least 0.002 away
 //    from one; with a +0.001 bias and < 5e-4 of accumulated fp32 error the floor cannot flip, and
 //    for the integer case the reference's double expression yields that integer too (checked
-//    exhaustively by tests/test_idct_core.py);
+//    exhaustively by tests/test_emu_logic.py);
 //  * G's fraction is a multiple of 8e-6: if the fp32 value is closer than COLOUR_G_BAND to an
 //    integer the caller must use ycc_to_rgb_exact (returns false);
 //  * floor(v) is taken as rint(v - 0.5) through the 1.5*2^23 magic-number add, which is exact for

@@ -18,14 +18,13 @@ namespace {
 inline unsigned be16(const uint8_t *p) { return (unsigned)((p[0] << 8) | p[1]); }
 
 // End of the entropy-coded segment that starts at `s`: the first marker that is neither a stuffed
-// FF00, an RSTn nor a fill byte.  scanImageData (Decoder.cpp:532-577) stops at FF D9 only; both
-// agree on well-formed single-scan files.
+// FF00, an RSTn nor a fill byte.  scanImageData (Decoder.cpp:532-577) stops at the first FF D9 only; both
+// agree on well-formed single-scan files, including ones with bytes (or whole images) after the first EOI.
 size_t find_scan_end(const uint8_t *f, size_t n, size_t s)
 {
-    // Fast path: a baseline single-scan file ends "... <entropy data> FF D9".  The kernels flag any
-    // other marker they meet inside the data (ST_BAD_MARKER), so trusting the tail is safe.
-    if (n >= s + 2 && f[n - 2] == 0xFF && f[n - 1] == 0xD9)
-        return n - 2;
+    // Always walk the markers (a memchr per FF byte: cheap next to the PCIe copy of the same bytes).  Trusting a
+    // trailing FF D9 instead would send files that carry data after the first EOI (MPO, concatenated JPEGs, appended
+    // previews) to the GPU whole; the reference stops at the first FF D9 (Decoder.cpp:546-557), and so does this.
     size_t e = s;
     while (e + 1 < n) {
         const uint8_t *q = (const uint8_t *)memchr(f + e, 0xFF, n - 1 - e);
@@ -210,11 +209,13 @@ extern "C" int kpeg_split_restart_bands(const uint8_t *scan, size_t len, const k
     if (ri == 0 || !((ri % mx) == 0 || (mx % ri) == 0))
         return KPEG_ERR_UNSUPPORTED; // bands must begin on a restart marker
     const uint32_t row_step = (ri % mx) == 0 ? ri / mx : 1u; // MCU rows between candidate cut points
-    const uint32_t used = (uint32_t)parts < (my + row_step - 1) / row_step ? (uint32_t)parts : (my + row_step - 1) / row_step;
-    // first MCU row of band k: balanced, rounded down to a cut point
-    for (uint32_t k = 0; k <= used; ++k) {
-        uint32_t r = (uint32_t)(((uint64_t)my * k) / used);
-        out_row[k] = k == used ? my : r - r % row_step;
+    // balance in CUT UNITS (groups of row_step MCU rows), not in rows: rounding a balanced row down to a cut point
+    // can give two bands the same first row when row_step > 1 and parts is close to the number of units
+    const uint32_t units = (my + row_step - 1) / row_step;
+    const uint32_t used = (uint32_t)parts < units ? (uint32_t)parts : units;
+    for (uint32_t k = 0; k <= used; ++k) { // strictly increasing: used <= units
+        const uint64_t r = ((uint64_t)units * k / used) * row_step;
+        out_row[k] = r < my ? (uint32_t)r : my;
     }
     for (uint32_t k = used + 1; k <= (uint32_t)parts; ++k)
         out_row[k] = my;

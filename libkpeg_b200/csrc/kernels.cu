@@ -645,7 +645,11 @@ __device__ __forceinline__ uint32_t load_acquire_gpu(const uint32_t *p)
     return v;
 }
 
-__device__ __forceinline__ void grid_barrier(uint32_t *counter, uint32_t &generation)
+// Returns false when the other CTAs did not arrive within `spin_limit` polls (about a microsecond each once the
+// back-off has grown): the grid is not co-resident -- another process or an MPS client holds the SMs the launch-time
+// cap assumed free.  The caller then leaves the loop; ST_RELAY_TIMEOUT tells the host to finish the relay with
+// per-round launches (entropy_relay_sparse), which need no co-residency.  A decode never hangs on this barrier.
+__device__ __forceinline__ bool grid_barrier(uint32_t *counter, uint32_t &generation, uint32_t spin_limit, uint32_t *s_ok)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -655,19 +659,27 @@ __device__ __forceinline__ void grid_barrier(uint32_t *counter, uint32_t &genera
         const uint32_t target = generation * gridDim.x;
         // Back off between polls: CTAs without work arrive at once, and a thousand of them re-reading one
         // L2 line back to back slow the memory requests of the CTAs that are still decoding.
-        uint32_t ns = 128;
+        uint32_t ns = 128, polls = 0;
+        bool ok = true;
         while (load_acquire_gpu(counter) < target) {
+            if (++polls > spin_limit) {
+                ok = false;
+                break;
+            }
             __nanosleep(ns);
             ns = ns < 1024u ? ns * 2u : ns;
         }
         __threadfence();
+        *s_ok = ok ? 1u : 0u;
     }
     __syncthreads();
+    return *s_ok != 0u;
 }
 
 __global__ void __launch_bounds__(ENTROPY_THREADS, 8) entropy_relay_loop_kernel(EntropyArgs a, int first, int last,
-                                                                             uint32_t wlog)
+                                                                             uint32_t wlog, uint32_t spin_limit)
 {
+    __shared__ uint32_t s_bar_ok;
     extern __shared__ __align__(16) unsigned char k1_raw[];
     K1Smem &sm = *reinterpret_cast<K1Smem *>(k1_raw);
     const uint32_t nsub = a.meta->nsub, total_bits = a.meta->total_bits;
@@ -716,12 +728,20 @@ __global__ void __launch_bounds__(ENTROPY_THREADS, 8) entropy_relay_loop_kernel(
         if (solo) {
             __threadfence();
             __syncthreads();
-        } else {
-            grid_barrier(&a.meta->grid_bar, generation);
+        } else if (!grid_barrier(&a.meta->grid_bar, generation, spin_limit, &s_bar_ok)) {
+            // round `round` may be incomplete (CTAs that never became resident have not run their share): the host
+            // repeats it -- items done twice change nothing and append nothing -- and goes on from there
+            if (threadIdx.x == 0)
+                atomicOr(&a.meta->status, ST_RELAY_TIMEOUT);
+            return;
         }
+        // last COMPLETE round, as seen by ANY CTA (after a timeout the CTAs disagree on how far they got; the host
+        // repeats the round after the furthest one, the only one that can be partly done)
+        if (threadIdx.x == 0)
+            atomicMax(&a.meta->relay_rounds, (uint32_t)round);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
-        a.meta->relay_rounds = (uint32_t)(round <= last ? round - 1 : last);
+        atomicMax(&a.meta->relay_rounds, (uint32_t)(round <= last ? round - 1 : last));
 }
 
 // Segmented exclusive scan of the slot counts: start_slot[i] = absolute coefficient slot at the
@@ -1164,13 +1184,16 @@ static std::atomic<int> g_live_contexts{0};
 
 void kernels_context_created() { ++g_live_contexts; }
 void kernels_context_destroyed() { --g_live_contexts; }
+// polls (~1 us each) a CTA waits at the relay loop's grid barrier before it gives up: ~2 s
+static uint32_t g_relay_spin_limit = 2000000u;
 static int g_relay_loop_per_sm_cap = 0; // experiments: cap of the cooperative relay loop's grid in CTAs per SM (0 = default rule)
 
-void launch_entropy_relay_loop(const EntropyArgs &a, int first, int last, cudaStream_t s, uint32_t *launches)
+cudaError_t launch_entropy_relay_loop(const EntropyArgs &a, int first, int last, cudaStream_t s, uint32_t *launches)
 {
     uint32_t wlog = ilog2(a.g.sub_bits / 32u);
     EntropyArgs args = a;
-    void *params[] = {&args, &first, &last, &wlog};
+    uint32_t spin_limit = g_relay_spin_limit;
+    void *params[] = {&args, &first, &last, &wlog, &spin_limit};
     const size_t smem = k1_sparse_smem_bytes(a.g.sub_bits);
     int per_sm = 2;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entropy_relay_loop_kernel, ENTROPY_THREADS, smem) != cudaSuccess ||
@@ -1189,8 +1212,14 @@ void launch_entropy_relay_loop(const EntropyArgs &a, int first, int last, cudaSt
     uint32_t grid = a.nsub_max / (ENTROPY_THREADS * 12u) + 1u;
     grid = grid < 16u ? 16u : grid;
     grid = grid > cap ? cap : grid;
-    cudaLaunchCooperativeKernel((const void *)entropy_relay_loop_kernel, dim3(grid), dim3(ENTROPY_THREADS), params, smem, s);
+    const cudaError_t e =
+        cudaLaunchCooperativeKernel((const void *)entropy_relay_loop_kernel, dim3(grid), dim3(ENTROPY_THREADS), params, smem, s);
+    if (e != cudaSuccess) {
+        cudaGetLastError(); // not sticky: the caller issues the rounds as separate launches instead
+        return e;
+    }
     ++*launches;
+    return cudaSuccess;
 }
 
 void launch_entropy_scan(const EntropyArgs &a, cudaStream_t s, uint32_t *launches)
@@ -2400,6 +2429,8 @@ void kernels_configure(int max_concurrent_jobs)
         g_sm_count = (uint32_t)sms;
         if (const char *e = getenv("KPEG_RELAY_LOOP_PER_SM"))
             g_relay_loop_per_sm_cap = atoi(e);
+        if (const char *e = getenv("KPEG_RELAY_SPIN_LIMIT")) // tests: 0 = give up at the first poll that finds a CTA missing
+            g_relay_spin_limit = (uint32_t)strtoul(e, nullptr, 10);
     }
     cudaFuncSetAttribute(idct_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<3>));
     cudaFuncSetAttribute(idct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<1>));

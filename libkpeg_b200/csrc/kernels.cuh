@@ -105,7 +105,8 @@ void launch_entropy_cold(const EntropyArgs &a, cudaStream_t s, uint32_t *launche
 void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint32_t *launches);
 // rounds first..last (first >= 2) in ONE cooperative launch: a device-side loop with a grid barrier
 // between rounds, stopping early at the fixed point; DevMeta::relay_rounds = last round that ran
-void launch_entropy_relay_loop(const EntropyArgs &a, int first, int last, cudaStream_t s, uint32_t *launches);
+// fails (nothing launched) when the driver refuses the cooperative launch; the caller then issues the rounds one by one
+cudaError_t launch_entropy_relay_loop(const EntropyArgs &a, int first, int last, cudaStream_t s, uint32_t *launches);
 void launch_entropy_scan(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_entropy_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);  // Huffman final pass
 void launch_entropy_expand(const EntropyArgs &a, cudaStream_t s, uint32_t *launches); // record final pass

@@ -126,7 +126,9 @@ constexpr uint32_t ST_SEG_MISMATCH = 4u;   // a restart interval did not hold th
 constexpr uint32_t ST_BAD_MARKER = 8u;     // a marker other than RSTn inside the entropy-coded segment
 constexpr uint32_t ST_EXIT_MISMATCH = 16u; // final decode left a subsequence in a different state than the relay recorded
 constexpr uint32_t ST_SEG_COUNT = 32u;     // number of RSTn markers does not match the DRI interval
-constexpr uint32_t ST_REC_OVERFLOW = 64u;  // a subsequence held more symbols than the record list has room for (-> Huffman final pass)
+constexpr uint32_t ST_REC_OVERFLOW = 64u;   // a subsequence held more symbols than the record list has room for (-> Huffman final pass)
+
+constexpr uint32_t ST_RELAY_TIMEOUT = 128u; // the relay loop's grid barrier gave up waiting (grid not co-resident): the host finishes the relay round by round
 
 // Per-subsequence relay state: where the first symbol after the end of the subsequence starts and
 // in which decoder state, plus how many coefficient slots were produced on the way.

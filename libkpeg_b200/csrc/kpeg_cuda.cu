@@ -1,6 +1,6 @@
 // kpeg_cuda.cu -- C-ABI host side of the B200 decode path (include/kpeg_cuda.h).
 //
-// A context owns four LANES (CUDA stream + grow-only device scratch + pinned bookkeeping each) and
+// A context owns eight LANES (CUDA stream + grow-only device scratch + pinned bookkeeping each) and
 // the device tables built from a kpeg_plan.  A job is enqueued on a lane (K0..K3, kernels.cu) and
 // finished later (stream sync, device status word, and -- rarely -- extra relay rounds).  Single
 // decodes use lane 0; a large host-pointer batch is cut into chunks that rotate through the
@@ -65,6 +65,7 @@ struct Job {
     uint32_t launches = 0;
     uint32_t extra_iterations = 0;
     bool use_records = true;
+    bool loop_used = true; // relay rounds 2.. ran as the cooperative device-side loop (DevMeta::relay_rounds is meaningful)
     size_t scan_len = 0;
     std::vector<Copy> d2h; // result copies to (re)issue after the downstream stages
 };
@@ -353,7 +354,9 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     const size_t coef_bytes = (size_t)g.total_blocks * 128u;
     // tie records: room for 1/8 of all pixels (typical: ~1 %); beyond that strips are redone wholesale
     const uint64_t npix_job = (uint64_t)g.nimages * g.width * g.height;
-    const uint32_t tie_cap = (uint32_t)std::min<uint64_t>(npix_job / 8u + 4096u, 1u << 27);
+    // (never less than the strips' own slots: a batch of very small images has more padded MCUs than pixels / 8)
+    const uint64_t nstrips_job = ((uint64_t)total_mcus + IDCT_MCUS_PER_CTA - 1) / IDCT_MCUS_PER_CTA;
+    const uint32_t tie_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(npix_job / 8u, nstrips_job * 16u) + 4096u, 1u << 27);
     const size_t overflow_bytes = ((size_t)total_mcus / IDCT_MCUS_PER_CTA + 2u) * sizeof(uint32_t);
 
     TRY(ensure(ctx, s, L.words, words_bytes));
@@ -458,7 +461,14 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     // rounds 2.. in one cooperative launch (device-side loop, stops at the fixed point); the cap only
     // bounds the loop -- a stream that needs more is finished by job_finish
     J.rounds = MAX_RELAY_ROUNDS - 2;
-    launch_entropy_relay_loop(ea, 2, J.rounds, s, &J.launches);
+    if (launch_entropy_relay_loop(ea, 2, J.rounds, s, &J.launches) != cudaSuccess) {
+        // the driver refused the cooperative launch (MPS / a partitioned device): the same rounds as separate
+        // launches; job_finish adds more if these do not reach the fixed point
+        J.loop_used = false;
+        J.rounds = std::max(2, std::min(ctx->relay_rounds, MAX_RELAY_ROUNDS - 1));
+        for (int r = 2; r <= J.rounds; ++r)
+            launch_entropy_relay(ea, r, s, &J.launches);
+    }
     mark(ctx, L, KPEG_T_RELAY_SPARSE);
     return enqueue_downstream(ctx, L);
 }
@@ -512,9 +522,12 @@ int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
         CK(cudaGetLastError());
         if (h_meta->status & (ST_BAD_MARKER | ST_SEG_COUNT))
             break; // malformed container-level structure: more rounds will not help
-        if (J.extra_iterations == 0u)
-            J.rounds = (int)std::max<uint32_t>(h_meta->relay_rounds, 1u); // last round the device loop ran
-        const bool converged_now = h_meta->changed[relay_slot(J.rounds)] == 0u;
+        // the loop's grid barrier gave up (its CTAs were not co-resident: another process on the device): rounds up
+        // to relay_rounds are complete, the next one may be partly done and is repeated on its partly filled list
+        const bool timed_out = (h_meta->status & ST_RELAY_TIMEOUT) != 0u;
+        if (J.extra_iterations == 0u && J.loop_used)
+            J.rounds = (int)std::max<uint32_t>(h_meta->relay_rounds, 1u); // last round the device loop completed
+        const bool converged_now = !timed_out && h_meta->changed[relay_slot(J.rounds)] == 0u;
         if (converged_now && J.use_records && (h_meta->status & ST_REC_OVERFLOW)) {
             // a subsequence held more symbols than the record list: redo the final pass the Huffman way
             J.use_records = false;
@@ -531,12 +544,15 @@ int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
         // Rare: the relay needed more rounds than were pre-issued.  Run two more at a time until a
         // round changes nothing, then redo the downstream stages.
         bool converged = false;
+        bool repeat = timed_out; // the first round issued here continues a partly filled list: its count is kept
         const uint32_t cap = h_meta->nsub / 2u + 4u;
         while (!converged && J.extra_iterations < cap) {
             ++J.extra_iterations;
             for (int k = 0; k < 2; ++k) {
                 ++J.rounds;
-                CK(cudaMemsetAsync(&d_meta->changed[relay_slot(J.rounds)], 0, sizeof(uint32_t), s));
+                if (!repeat)
+                    CK(cudaMemsetAsync(&d_meta->changed[relay_slot(J.rounds)], 0, sizeof(uint32_t), s));
+                repeat = false;
                 launch_entropy_relay(J.ea, J.rounds, s, &J.launches);
             }
             mark(ctx, L, KPEG_T_RELAY_SPARSE);
@@ -577,7 +593,7 @@ int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
         stats->kernel_launches += J.launches;
         add_times(ctx, L, stats);
     }
-    return status_to_rc(ctx, h_meta->status & ~ST_REC_OVERFLOW);
+    return status_to_rc(ctx, h_meta->status & ~(ST_REC_OVERFLOW | ST_RELAY_TIMEOUT));
 }
 
 void zero_stats(kpeg_stats *stats)
@@ -810,6 +826,8 @@ extern "C" int kpeg_cuda_decode(kpeg_ctx *ctx, const kpeg_plan *plan, const uint
     CK(cudaSetDevice(ctx->device));
     zero_stats(stats);
     Lane &L = ctx->lane[0];
+    if (L.job.active) // a deferred job still reads this lane's scan / pixel buffers: complete it before they can move
+        finish_deferred(ctx, 0);
     const size_t npix = (size_t)plan->width * plan->height * plan->ncomp;
     TRY(ensure(ctx, L.stream, L.scan, scan_len + 64));
     TRY(ensure(ctx, L.stream, L.pixels, npix + 64));
@@ -876,16 +894,21 @@ extern "C" int kpeg_cuda_decode_batch_packed_device_split(kpeg_ctx *ctx, const k
     for (int li = 0; li < parts; ++li) {
         const int lo = (int)((long long)n * li / parts), hi = (int)((long long)n * (li + 1) / parts);
         mark(ctx, ctx->lane[li], -1);
-        TRY(job_enqueue(ctx, li, plan, d_packed + packed_offsets[lo], (size_t)(packed_offsets[hi] - packed_offsets[lo]),
-                        (uint32_t)(hi - lo), d_pixels_out + npix * (size_t)lo, {}));
+        const int erc = job_enqueue(ctx, li, plan, d_packed + packed_offsets[lo], (size_t)(packed_offsets[hi] - packed_offsets[lo]),
+                                    (uint32_t)(hi - lo), d_pixels_out + npix * (size_t)lo, {});
+        if (erc != KPEG_OK) { // the parts already enqueued hold the caller's pointers: complete them before returning
+            const std::string why = ctx->err;
+            for (int k = 0; k < li; ++k)
+                job_finish(ctx, k, nullptr);
+            ctx->err = why;
+            return erc;
+        }
     }
     int rc_all = KPEG_OK;
     for (int li = 0; li < parts; ++li) {
         const int rc = job_finish(ctx, li, stats);
-        if (rc != KPEG_OK && rc != KPEG_ERR_STREAM)
-            return rc;
-        if (rc != KPEG_OK)
-            rc_all = rc;
+        if (rc != KPEG_OK && (rc_all == KPEG_OK || rc_all == KPEG_ERR_STREAM))
+            rc_all = rc; // every lane is completed whatever the outcome; a hard failure outranks a corrupt stream
     }
     return rc_all;
 }
@@ -949,6 +972,8 @@ extern "C" int kpeg_cuda_decode_batch_device(kpeg_ctx *ctx, const kpeg_plan *pla
     CK(cudaSetDevice(ctx->device));
     zero_stats(stats);
     Lane &L = ctx->lane[0];
+    if (L.job.active) // as in kpeg_cuda_decode
+        finish_deferred(ctx, 0);
     const size_t total = (size_t)(scan_offsets[n] - scan_offsets[0]) + 2u * (size_t)n;
     TRY(ensure(ctx, L.stream, L.scan, total + 64));
     const uint8_t *sep = (const uint8_t *)ctx->h_sep.p;

@@ -464,3 +464,40 @@ def test_guard_mode_finds_no_stray_writes(monkeypatch, lena_jpg):
                 assert e.code == K.api.KPEG_ERR_STREAM, f"trial {trial}: {e}"  # a guard violation would be KPEG_ERR_CUDA
     finally:
         dec.close()
+
+
+def test_distinct_tables_per_component(decoder):
+    """Distinct Cb / Cr Huffman AND quantiser tables with a non-default Tq / Td / Ta mapping (three quantisers, three
+    DC and three AC tables, ids unlike 0/1/1, component ids 7/3/9): K1's table ring and K3's quantiser staging index
+    by component, not by "luma / chroma".  With and without restart-free relay work, several subsequence sizes."""
+    import jpeg_writer as JW
+    for (w, h, q, seed) in ((96, 64, 88, 21), (320, 200, 95, 22), (64, 64, 30, 23)):
+        base = synth_encode(SynthParams(w, h, quality=q, seed=seed, flags=QUIRK_FREE)).tobytes()
+        jpg = JW.distinct_tables_variant(base, H.oracle_decode, K.parse_jfif, seed=seed)
+        for sb in (64, 512):
+            decoder.set_tuning(sub_bits=sb)
+            try:
+                check_against_oracle(decoder, jpg)
+                check_against_oracle(decoder, jpg, parity=False)
+            finally:
+                decoder.set_tuning(sub_bits=512)
+
+
+def test_relay_barrier_timeout_falls_back_to_host_rounds(monkeypatch, lena_jpg):
+    """KPEG_RELAY_SPIN_LIMIT=0: a CTA of the cooperative relay loop gives up at its grid barrier as soon as one poll
+    finds another CTA missing (what happens when the grid is not co-resident: a second process on the GPU).  The
+    decode must neither hang nor change: the host finishes the relay with per-round launches."""
+    monkeypatch.setenv("KPEG_RELAY_SPIN_LIMIT", "0")
+    dec = K.Decoder(0)
+    try:
+        check_against_oracle(dec, lena_jpg)
+        # no restart markers, 16 images in one job: several relay rounds with long work lists
+        jpgs = [synth_encode(SynthParams(512, 512, quality=95, seed=300 + i, flags=QUIRK_FREE)) for i in range(16)]
+        plans = [K.parse_jfif(j) for j in jpgs]
+        plan = plans[0][0]
+        plan.flags = K.KPEG_FLAG_REF_PARITY
+        outs = dec.decode_batch(plan, [j[o:o + n] for j, (_, o, n) in zip(jpgs, plans)])
+        for j, o in zip(jpgs, outs):
+            assert np.array_equal(o, H.oracle_decode(j.tobytes())["pixels"])
+    finally:
+        dec.close()

@@ -73,3 +73,55 @@ def test_malformed_containers(lena_jpg):
     # trailing bytes after EOI: the scan still ends at the marker
     plan, off, n = K.parse_jfif(lena_jpg + b"\x00\x01\x02")
     assert n == 104113
+
+
+def test_restart_bands_balanced_in_cut_units():
+    """DRI spanning more than one MCU row, parts close to the number of cut units, my % row_step != 0:
+    every band must begin on a distinct cut point and the bands must reassemble the image."""
+    from libkpeg_b200.shard import split_restart_bands
+    from libkpeg_b200.synth import EMIT_RESTART, QUIRK_FREE, SynthParams, synth_encode
+    # 16x40: mx = 2, my = 5; DRI = 4 MCUs = 2 MCU rows -> row_step = 2, units = 3
+    jpg = synth_encode(SynthParams(16, 40, quality=90, restart_interval=4, flags=QUIRK_FREE | EMIT_RESTART, seed=5,
+                                   file_components=1))
+    plan, off, n = K.parse_jfif(jpg)
+    scan = jpg[off:off + n]
+    whole = H.emu_decode(jpg)["pixels"]
+    for parts in (1, 2, 3, 4, 7):
+        bands = split_restart_bands(plan, scan, parts)
+        rows = [b.row0 for b in bands if b.rows]
+        assert rows == sorted(set(rows)) and rows[0] == 0 and all(r % 16 == 0 for r in rows), (parts, rows)
+        assert sum(b.rows for b in bands) == 40
+        for b in bands:
+            if not b.rows:
+                assert b.scan.size == 0
+                continue
+            got = H.emu_decode(None, scans=[b.scan], plan=b.plan)["pixels"][0]
+            assert np.array_equal(got, whole[b.row0:b.row0 + b.rows]), (parts, b.row0)
+
+
+def test_scan_ends_at_first_eoi(lena_jpg):
+    """Files with data after the first EOI that also END in FF D9 (concatenated JPEGs, MPO): the scan stops at the
+    first EOI, as the reference's scanImageData does (Decoder.cpp:546-557)."""
+    plan, off, n = K.parse_jfif(lena_jpg + lena_jpg)
+    assert n == 104113
+    plan, off, n = K.parse_jfif(lena_jpg + b"\x00\x01\xff\xd9")
+    assert n == 104113
+
+
+def test_distinct_tables_per_component_cpu():
+    """Three quantiser tables and a Huffman table pair of its own per component, table / component ids unlike the
+    0/1/1 mapping the reference hard-wires: kernel logic (CPU single-stepper) == oracle, and the result
+    differs from a decode that ignores the selectors."""
+    import jpeg_writer as JW
+    from libkpeg_b200.synth import QUIRK_FREE, SynthParams, synth_encode
+    base = synth_encode(SynthParams(96, 64, quality=88, seed=21, flags=QUIRK_FREE)).tobytes()
+    jpg = JW.distinct_tables_variant(base, H.oracle_decode, K.parse_jfif)
+    plan, off, n = K.parse_jfif(jpg)
+    assert tuple(plan.comp_tq) == (2, 0, 1) and tuple(plan.comp_td) == (1, 0, 2) and tuple(plan.comp_ta) == (2, 0, 1)
+    o = H.oracle_decode(jpg)
+    assert np.array_equal(o["coef"], H.oracle_decode(base)["coef"])  # same coefficients, other tables
+    assert not np.array_equal(o["pixels"], H.oracle_decode(base)["pixels"])
+    for sb in (64, 512):
+        e = H.emu_decode(jpg, sub_bits=sb)
+        assert e["status"] == 0 and e["records_ok"]
+        assert np.array_equal(o["coef"], e["coef"]) and np.array_equal(o["pixels"], e["pixels"])
