@@ -22,6 +22,8 @@
 
 namespace kpeg {
 
+KPEG_HD uint32_t max_u32(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
 KPEG_HD uint32_t funnel_left(uint32_t hi, uint32_t lo, uint32_t s)
 {
 #if defined(__CUDA_ARCH__)
@@ -83,16 +85,6 @@ KPEG_HD int32_t extend_value(uint32_t v, uint32_t n)
     return (v >> (n - 1u)) ? (int32_t)v : (int32_t)v - (int32_t)((1u << n) - 1u);
 }
 
-// The same for n in 0..15 where the result for n == 0 is never used (a symbol without a value): no fix-up of n.
-KPEG_HD int32_t extend_value_or_any(uint32_t v, uint32_t n)
-{
-#if defined(__CUDA_ARCH__)
-    return __funnelshift_rc(v, 0u, n - 1u) ? (int32_t)v : (int32_t)v - (int32_t)((1u << n) - 1u); // clamped shift: defined for n == 0
-#else
-    return extend_value(v, n | (n == 0u ? 1u : 0u));
-#endif
-}
-
 struct StreamView {
     const uint32_t *seg_bit; // [nseg + 2]: start bit of every restart segment, then total_bits, then 0xFFFFFFFF
     uint32_t total_bits;
@@ -122,30 +114,40 @@ struct GlobalSink {
     }
 };
 
-// ---- symbol records ------------------------------------------------------------------------------
-// The relay passes decode every subsequence from (what converges to) its true entry state anyway;
-// they also write down what they decoded, one 32-bit record per symbol, so that the final pass is a
-// cheap, load-latency-tolerant EXPANSION of records instead of a third serial Huffman decode:
-//   a symbol     : the table entry shifted left by 11 (total bits 11-15, magnitude size 16-19, slot
-//                  advance 20-26) + the raw magnitude bits as they sit in the stream in bits 0-10 (at most
-//                  11 of them in baseline JPEG; EXTEND is applied by the expander).  An invalid bit
-//                  pattern is the entry ENTRY_INVALID: advance 127.
-//   boundary jump: 0xF0000000 | index of the segment that starts there.
-constexpr uint32_t REC_JUMP = 0xF0000000u;
-constexpr uint32_t REC_RAW_MASK = 0x7FFu;
+// ---- coefficient records -------------------------------------------------------------------------
+// The relay passes decode every subsequence from (what converges to) its true entry state anyway; they also write
+// down what they decoded, so that nothing downstream has to Huffman-decode a third time.  One 32-bit record per
+// symbol that CARRIES A VALUE (EOB, ZRL and zero DC differences leave no record):
+//     bits 31..16  position: coefficient slot counted from the first slot of the block the subsequence was entered in
+//                  (slot = block * 64 + zig-zag index; a DC difference sits in slot 0 of its block)
+//     bits 15..0   value + 0x8000 (EXTEND already applied: T.81 F.2.2.1 == bitStringtoValue, src/Image.cpp:285-302)
+// A record is self-contained: absolute slot = (start_slot[subsequence] & ~63) + position.  The consumer (K3's
+// expansion stage, kernels.cu) needs no running state, so any thread can take any record.  Positions run on
+// ACROSS restart / image boundaries: in a valid stream a boundary falls exactly where the slot count says the
+// interval ends, so crossing it only rounds the position up to the next block; whether that held is checked once
+// per subsequence by the offset scan (RELAY_* annotations below), not per record.
+KPEG_HD uint32_t record_pack(uint32_t pos, uint32_t biased_value) { return (pos << 16) + biased_value; }
+KPEG_HD uint32_t record_pos(uint32_t r) { return r >> 16; }
+KPEG_HD int32_t record_value(uint32_t r) { return (int32_t)(r & 0xFFFFu) - 0x8000; }
+constexpr uint32_t COEF_BIAS = 0x8000u; // coefficients travel as value + COEF_BIAS in 16 bits (records, K3's tile)
 
-// raw = the `size` magnitude bits that follow the code in the left-aligned window (0 when size == 0)
-KPEG_HD uint32_t record_raw_bits(uint32_t win, uint32_t T, uint32_t size)
+// value + COEF_BIAS of a symbol with `size` (1..15) magnitude bits that follow the code in the left-aligned window
+KPEG_HD uint32_t biased_extend(uint32_t win, uint32_t T, uint32_t size)
 {
-    const uint32_t x = win << (T - size);
-#if defined(__CUDA_ARCH__)
-    return __funnelshift_rc(x, 0u, 32u - size); // clamped shift: size == 0 gives 0
-#else
-    return size ? x >> (32u - size) : 0u;
-#endif
+    const uint32_t x = win << (T - size);      // magnitude bits left-aligned
+    const uint32_t raw = x >> (32u - size);
+    // leading 1: the value itself; leading 0: value - (2^size - 1)
+    return raw + ((int32_t)x < 0 ? COEF_BIAS : COEF_BIAS + 1u - (1u << size));
 }
 
-KPEG_HD uint32_t pack_record(uint32_t e, uint32_t raw) { return (e << 11) + raw; }
+// SubState::cz = (component << 8) | zig-zag index in the low 10 bits -- the decoder STATE, the part the relay's
+// fixed point is about -- plus annotations of the decode that produced it (they never decide convergence):
+constexpr uint32_t CZ_STATE_MASK = 0x3FFu;
+constexpr uint32_t CZ_BAD_CODE = 1u << 10;      // a bit pattern that is no Huffman code was consumed
+constexpr uint32_t CZ_SLOT_OVERFLOW = 1u << 11; // a coefficient beyond slot 63 of its block
+constexpr uint32_t CZ_SEG_MISMATCH = 1u << 12;  // an interval lying wholly inside the subsequence had the wrong number of MCUs
+constexpr uint32_t CZ_FLAGS = CZ_BAD_CODE | CZ_SLOT_OVERFLOW | CZ_SEG_MISMATCH;
+constexpr uint32_t CZ_POS_SHIFT = 16;           // bits 31..16: position (as in a record) the subsequence ended on
 
 struct NoRecorder {
     KPEG_HD void emit(uint32_t, uint32_t) const {}
@@ -160,7 +162,9 @@ struct DecState {
     uint32_t k, segend;        // next boundary: segment index and its start bit
     uint32_t slot;             // absolute slot (final pass only)
     uint32_t st;               // ST_* bits (final pass only)
-    uint32_t nrec;             // symbol records emitted (relay passes)
+    uint32_t nrec;             // records emitted (relay passes)
+    uint32_t q, qj;            // relay passes: running record position; its value at entry / after the last boundary
+    uint32_t flags;            // relay passes: CZ_* annotations
 };
 
 template <class Words>
@@ -183,6 +187,8 @@ KPEG_HD void dec_init(DecState &d, const Words &W, const StreamView &S, uint32_t
     d.slot = slot;
     d.st = 0;
     d.nrec = 0;
+    d.q = d.qj = z;
+    d.flags = 0;
 }
 
 KPEG_HD SubState dec_exit_state(const DecState &d)
@@ -195,70 +201,85 @@ KPEG_HD SubState dec_exit_state(const DecState &d)
     return out;
 }
 
-// Decode until the first symbol boundary at or after `end_bit` -- or, in the final pass, until the
-// next symbol would belong to a block at or beyond `slot_limit` (a multiple of 64), so that a CTA can
-// assemble its output in shared-memory windows; call again with a larger limit to resume.
-//   WRITE == false : speculative / relay pass, only the exit state and slot count are produced.
-//   WRITE == true  : final pass; d.slot is the absolute coefficient slot, AC coefficients go to
-//                    sink.ac(absolute slot, value), DC differences to sink.dc(block, value).
-//
-// Loop state: bit position p with the words j, j+1 of the stream in registers, sh = p & 31 (a symbol
-// is at most 27 bits, so two words always cover it); word j+2 is fetched unconditionally at the top
-// of every iteration and rotated in, branch-free, when sh crosses 32 -- lanes of a warp cross word
-// boundaries at different symbols, a conditional refill would be executed (mostly masked) by every
-// warp on almost every iteration.  Table offset toff = (2*component + (z != 0)) * LUT_SIZE: a DC
-// symbol switches to the component's AC table (toff |= LUT_SIZE), the end of a block to the next
-// table in the ring.  z is the zig-zag index.
-template <bool WRITE, bool EMIT, class Words, class Luts, class Sink, class Rec>
-KPEG_HD void decode_run(DecState &d, const Words &W, const Luts &L, const StreamView &S, const JobGeom &g,
-                        uint32_t end_bit, uint32_t slot_limit, const Sink &sink, const Rec &rec)
+// exit state of a relay pass (relay_run): the position runs on across blocks, the zig-zag index is its low six bits
+KPEG_HD SubState relay_exit_state(const DecState &d)
 {
-    const uint32_t total_slots = g.total_blocks * 64u;
+    SubState out;
+    out.p = d.p;
+    out.n = d.q - d.qj;
+    out.cz = ((d.toff >> (LUT_BITS + 1)) << 8) | (d.q & 63u) | d.flags | (d.q << CZ_POS_SHIFT);
+    out.seg = d.seg;
+    return out;
+}
+
+// ---- relay passes (cold / relay rounds) ----------------------------------------------------------------
+// Decode from the state in `d` until the first symbol boundary at or after `end_bit`; produces the exit state, the
+// slot count and -- EMIT -- one record per value-carrying symbol.
+//
+// Loop state: bit position p with the words j, j+1 of the stream in registers, sh = p & 31 (a symbol is at most 27
+// bits, so two words always cover it); word j+2 is fetched unconditionally at the top of every iteration and rotated
+// in, branch-free, when sh crosses 32 -- lanes of a warp cross word boundaries at different symbols, a conditional
+// refill would be executed (mostly masked) by every warp on almost every iteration.  Table offset
+// toff = (2*component + (z != 0)) * LUT_SIZE: a DC symbol switches to the component's AC table (toff |= LUT_SIZE),
+// the end of a block to the next table in the ring.  q is the running record position (block * 64 + zig-zag index,
+// counted from the first slot of the entry block); the zig-zag index is q & 63.
+//
+// Errors of the decode are annotations of the exit state (CZ_*), not device status bits: a speculative decode from a
+// wrong entry state meets "errors" that mean nothing; only the annotations of the LAST decode of a subsequence -- the
+// one from its true entry state -- survive in state[], and the offset scan turns those into status bits.
+template <bool EMIT, class Words, class Luts, class Rec>
+KPEG_HD void relay_run(DecState &d, const Words &W, const Luts &L, const StreamView &S, const JobGeom &g, uint32_t end_bit,
+                       const Rec &rec)
+{
     const uint32_t ring = g.ncomp * 2u * (uint32_t)LUT_SIZE;
-    uint32_t p = d.p, j = d.j, sh = d.sh, w0 = d.w0, w1 = d.w1, toff = d.toff, z = d.z, n = d.n;
-    uint32_t k = d.k, segend = d.segend, slot = d.slot, st = d.st, nrec = d.nrec;
+    uint32_t p = d.p, j = d.j, sh = d.sh, w0 = d.w0, w1 = d.w1, toff = d.toff, q = d.q, qj = d.qj;
+    uint32_t k = d.k, segend = d.segend, nrec = d.nrec, flags = d.flags;
     int32_t seg = d.seg;
-    // Fast lane of the speculative / relay passes.  When the next boundary lies at least a symbol beyond
-    // end_bit (always, without restart markers, except next to an image end) no symbol of this call can
-    // straddle it, and with a word-aligned end_bit "p < end_bit" is "j < end_bit / 32": the loop carries
-    // neither p nor the slot count (64 * blocks completed + z_exit - z_entry, added afterwards).
-    if (!WRITE && p < end_bit && (end_bit & 31u) == 0u && segend >= end_bit + 32u) {
-        const uint32_t jend = end_bit >> 5, z_entry = z;
-        uint32_t nblk = 0;
+    // one running maximum finds both kinds of bad symbol: a value-carrying symbol must end inside its block
+    // (zig-zag index + advance <= 64), a symbol without a value must have a real advance (1, 16 or 64; "no code
+    // matches" is the entry with the impossible advance 127)
+    uint32_t worst = 0;
+    auto symbol = [&](uint32_t win, uint32_t e) { // everything a symbol does except moving the bit position
+        const uint32_t T = e & 31u, adv = e >> 9, size = (e >> 5) & 15u;
+        const uint32_t zn = (q & 63u) + adv;
+        if (EMIT) {
+            worst = max_u32(worst, size ? zn : adv);
+            if (size) {
+                rec.emit(nrec, record_pack(q + adv - 1u, biased_extend(win, T, size)));
+                ++nrec;
+            }
+        }
+        if (zn >= 64u) { // end of the block: next table of the ring
+            q = (q | 63u) + 1u;
+            toff += (uint32_t)LUT_SIZE;
+            toff = toff == ring ? 0u : toff;
+        } else {
+            q += adv;
+            toff |= (uint32_t)LUT_SIZE;
+        }
+    };
+    // Fast lane.  When the next boundary lies at least a symbol beyond end_bit (always, without restart markers,
+    // except next to an image end) no symbol of this call can straddle it, and with a word-aligned end_bit
+    // "p < end_bit" is "j < end_bit / 32": the loop carries neither p nor a boundary test.
+    if (p < end_bit && (end_bit & 31u) == 0u && segend >= end_bit + 32u) {
+        const uint32_t jend = end_bit >> 5;
         while (j < jend) {
             const uint32_t nxt = W(j + 2u);
             const uint32_t win = funnel_left(w0, w1, sh);
             uint32_t e = L.fast(toff, win >> (32 - LUT_BITS));
             if ((e & 31u) == 0u)
                 e = L.slow(toff, win, e);
-            const uint32_t T = e & 31u, adv = e >> 9;
-            if (EMIT) {
-                rec.emit(nrec, pack_record(e, record_raw_bits(win, T, (e >> 5) & 15u)));
-                ++nrec;
-            }
-            sh += T;
-            {
-                const bool cross = sh >= 32u;
-                sh = cross ? sh - 32u : sh;
-                j = cross ? j + 1u : j;
-                w0 = cross ? w1 : w0;
-                w1 = cross ? nxt : w1;
-            }
-            const uint32_t zn = z + adv;
-            if (zn >= 64u) {
-                z = 0;
-                ++nblk;
-                toff += (uint32_t)LUT_SIZE;
-                toff = toff == ring ? 0u : toff;
-            } else {
-                z = zn;
-                toff |= (uint32_t)LUT_SIZE;
-            }
+            symbol(win, e);
+            sh += e & 31u;
+            const bool cross = sh >= 32u;
+            sh = cross ? sh - 32u : sh;
+            j = cross ? j + 1u : j;
+            w0 = cross ? w1 : w0;
+            w1 = cross ? nxt : w1;
         }
         p = (j << 5) + sh;
-        n += nblk * 64u + z - z_entry;
     }
-    while (p < end_bit && (!WRITE || slot < slot_limit)) {
+    while (p < end_bit) {
         const uint32_t nxt = W(j + 2u); // consumed at the bottom of the iteration, if at all
         const uint32_t win = funnel_left(w0, w1, sh);
         uint32_t e = L.fast(toff, win >> (32 - LUT_BITS));
@@ -266,22 +287,82 @@ KPEG_HD void decode_run(DecState &d, const Words &W, const Luts &L, const Stream
             e = L.slow(toff, win, e);
         const uint32_t T = e & 31u;
         if (p + T > segend) {
-            // The symbol would straddle a restart / image boundary: we are in its padding.
-            if (WRITE && slot != seg_slot_base(g, k) && (k < g.nseg || slot < total_slots))
+            // The symbol would straddle a restart / image boundary: we are in its padding (T.81 F.2.2.4 / E.2.4).
+            // A valid stream is at the end of an MCU here, so the position is already a multiple of 64.
+            q = (q + 63u) & ~63u;
+            if (seg >= 0 && q - qj != seg_slot_base(g, k) - seg_slot_base(g, (uint32_t)seg))
+                flags |= CZ_SEG_MISMATCH; // the interval between the last boundary and this one
+            qj = q;
+            seg = (int32_t)k;
+            p = segend;
+            toff = 0;
+            ++k;
+            segend = S.seg_bit[k];
+            if (p >= S.total_bits)
+                break;
+            j = p >> 5;
+            sh = p & 31u;
+            w0 = W(j);
+            w1 = W(j + 1u);
+            continue;
+        }
+        symbol(win, e);
+        p += T;
+        sh += T;
+        const bool cross = sh >= 32u; // selects, not a branch
+        sh = cross ? sh - 32u : sh;
+        j = cross ? j + 1u : j;
+        w0 = cross ? w1 : w0;
+        w1 = cross ? nxt : w1;
+    }
+    if (EMIT)
+        flags |= worst == ENTRY_ADV_INVALID ? CZ_BAD_CODE : (worst > 64u ? CZ_SLOT_OVERFLOW : 0u);
+    d.p = p;
+    d.j = j;
+    d.sh = sh;
+    d.w0 = w0;
+    d.w1 = w1;
+    d.toff = toff;
+    d.z = q & 63u;
+    d.q = q;
+    d.qj = qj;
+    d.n = q - qj;
+    d.k = k;
+    d.segend = segend;
+    d.seg = seg;
+    d.nrec = nrec;
+    d.flags = flags;
+}
+
+// ---- Huffman final pass (fallback when records cannot be used) ---------------------------------------
+// Decode until the first symbol boundary at or after `end_bit` or until the next symbol would belong to a block at or
+// beyond `slot_limit` (a multiple of 64), so that a CTA can assemble its output in shared-memory windows; call again
+// with a larger limit to resume.  d.slot is the absolute coefficient slot; values go to sink.put().
+template <class Words, class Luts, class Sink>
+KPEG_HD void write_run(DecState &d, const Words &W, const Luts &L, const StreamView &S, const JobGeom &g, uint32_t end_bit,
+                       uint32_t slot_limit, const Sink &sink)
+{
+    const uint32_t total_slots = g.total_blocks * 64u;
+    const uint32_t ring = g.ncomp * 2u * (uint32_t)LUT_SIZE;
+    uint32_t p = d.p, j = d.j, sh = d.sh, w0 = d.w0, w1 = d.w1, toff = d.toff, z = d.z, n = d.n;
+    uint32_t k = d.k, segend = d.segend, slot = d.slot, st = d.st;
+    int32_t seg = d.seg;
+    while (p < end_bit && slot < slot_limit) {
+        const uint32_t nxt = W(j + 2u);
+        const uint32_t win = funnel_left(w0, w1, sh);
+        uint32_t e = L.fast(toff, win >> (32 - LUT_BITS));
+        if ((e & 31u) == 0u)
+            e = L.slow(toff, win, e);
+        const uint32_t T = e & 31u;
+        if (p + T > segend) {
+            if (slot != seg_slot_base(g, k) && (k < g.nseg || slot < total_slots))
                 st |= ST_SEG_MISMATCH;
             p = segend;
             z = 0;
             toff = 0;
             n = 0;
             seg = (int32_t)k;
-            if (EMIT) {
-                rec.emit(nrec, REC_JUMP | (k & 0xFFFFFFu));
-                ++nrec;
-                if (k > 0xFFFFFFu)
-                    st |= ST_REC_OVERFLOW;
-            }
-            if (WRITE)
-                slot = seg_slot_base(g, k);
+            slot = seg_slot_base(g, k);
             ++k;
             segend = S.seg_bit[k];
             if (p >= S.total_bits)
@@ -293,34 +374,25 @@ KPEG_HD void decode_run(DecState &d, const Words &W, const Luts &L, const Stream
             continue;
         }
         const uint32_t adv = e >> 9;
-        if (WRITE) {
-            const uint32_t size = (e >> 5) & 15u;
-            // status bits without branches: an invalid pattern has T == 17 and size == 0
-            st |= ((T - size) >> 4) & ((T - size) & 1u);      // ST_BAD_CODE (== 1): code "length" 17
-            st |= (size != 0u && z + adv > 64u) ? ST_SLOT_OVERFLOW : 0u; // a coefficient beyond the block (EOB's 64 is clamped)
-            // one store site for DC differences and AC coefficients
-            const uint32_t raw = (win << (T - size)) >> ((32u - size) & 31u);
-            const int32_t val = extend_value(raw, size | (size == 0u ? 1u : 0u));
-            sink.put(z == 0u, slot, adv, size != 0u && slot + adv <= total_slots, val);
-        }
-        if (EMIT) {
-            rec.emit(nrec, pack_record(e, record_raw_bits(win, T, (e >> 5) & 15u)));
-            ++nrec;
-        }
+        const uint32_t size = (e >> 5) & 15u;
+        // status bits without branches: an invalid pattern has T == 17 and size == 0
+        st |= ((T - size) >> 4) & ((T - size) & 1u);                 // ST_BAD_CODE (== 1): code "length" 17
+        st |= (size != 0u && z + adv > 64u) ? ST_SLOT_OVERFLOW : 0u; // a coefficient beyond the block (EOB's 64 is clamped)
+        // one store site for DC differences and AC coefficients
+        const uint32_t raw = (win << (T - size)) >> ((32u - size) & 31u);
+        const int32_t val = extend_value(raw, size | (size == 0u ? 1u : 0u));
+        sink.put(z == 0u, slot, adv, size != 0u && slot + adv <= total_slots, val);
         p += T;
         sh += T;
-        {
-            const bool cross = sh >= 32u; // selects, not a branch
-            sh = cross ? sh - 32u : sh;
-            j = cross ? j + 1u : j;
-            w0 = cross ? w1 : w0;
-            w1 = cross ? nxt : w1;
-        }
+        const bool cross = sh >= 32u;
+        sh = cross ? sh - 32u : sh;
+        j = cross ? j + 1u : j;
+        w0 = cross ? w1 : w0;
+        w1 = cross ? nxt : w1;
         uint32_t zn = z + adv;
         zn = zn > 64u ? 64u : zn;
         n += zn - z;
-        if (WRITE)
-            slot += zn - z;
+        slot += zn - z;
         if (zn == 64u) {
             z = 0;
             toff += (uint32_t)LUT_SIZE;
@@ -343,81 +415,31 @@ KPEG_HD void decode_run(DecState &d, const Words &W, const Luts &L, const Stream
     d.slot = slot;
     d.st = st;
     d.seg = seg;
-    d.nrec = nrec;
 }
 
-// Final pass over records: state is (next record, absolute slot, zig-zag index).  Stops when the
-// records are used up or the next symbol belongs to a block at or beyond slot_limit.
-template <class RecAt, class Sink>
-KPEG_HD void expand_run(uint32_t &k, uint32_t nrec, uint32_t &slot, uint32_t &z, uint32_t &st, const RecAt &rec_at,
-                        const JobGeom &g, uint32_t slot_limit, const Sink &sink)
+// One-shot conveniences over a whole subsequence (CPU single-stepper, cold pass).
+template <class Words, class Luts>
+KPEG_HD SubState relay_span(const Words &W, const Luts &L, const StreamView &S, const JobGeom &g, uint32_t end_bit, uint32_t p,
+                            uint32_t c, uint32_t z, uint32_t k)
 {
-    const uint32_t total_slots = g.total_blocks * 64u;
-    constexpr int BATCH = 8; // records fetched together: their loads are independent of the running state
-    // software pipeline: the batch after the one being expanded is already in flight
-    uint32_t nx[BATCH];
-    uint32_t adv_max = 0, reach_max = 0;
-#pragma unroll
-    for (int j = 0; j < BATCH; ++j)
-        nx[j] = (k < nrec && slot < slot_limit && k + (uint32_t)j < nrec) ? rec_at(k + (uint32_t)j) : 0u;
-    while (k < nrec && slot < slot_limit) {
-        uint32_t rr[BATCH];
-#pragma unroll
-        for (int j = 0; j < BATCH; ++j)
-            rr[j] = nx[j];
-#pragma unroll
-        for (int j = 0; j < BATCH; ++j)
-            nx[j] = k + (uint32_t)(BATCH + j) < nrec ? rec_at(k + (uint32_t)(BATCH + j)) : 0u;
-#pragma unroll
-        for (int j = 0; j < BATCH; ++j) {
-            if (k < nrec && slot < slot_limit) { // a record left unused here is fetched again by the next call
-                const uint32_t r = rr[j];
-                ++k;
-                if ((r >> 28) == 0xFu) {
-                    const uint32_t seg = r & 0xFFFFFFu;
-                    if (slot != seg_slot_base(g, seg) && (seg < g.nseg || slot < total_slots))
-                        st |= ST_SEG_MISMATCH;
-                    slot = seg_slot_base(g, seg);
-                    z = 0;
-                } else {
-                    const uint32_t size = (r >> 16) & 15u, adv = (r >> 20) & 127u;
-                    const bool has_value = size != 0u;
-                    uint32_t zn = z + adv;
-                    // error flags as two running maxima, folded into st after the loop: an invalid code has the
-                    // (otherwise impossible) advance 127; a coefficient may not land beyond slot 63 of its block
-                    adv_max = adv > adv_max ? adv : adv_max;
-                    reach_max = (has_value && zn > reach_max) ? zn : reach_max;
-                    const int32_t val = extend_value_or_any(r & REC_RAW_MASK, size);
-                    // a sink that bounds its own writes (the shared-memory window) needs no check against the end of
-                    // the coefficient buffer: what lands beyond it stays in the window and is never flushed
-                    sink.put(z == 0u, slot, adv, Sink::bounds_itself ? has_value : (has_value && slot + adv <= total_slots), val);
-                    zn = zn > 64u ? 64u : zn;
-                    slot += zn - z;
-                    z = zn == 64u ? 0u : zn;
-                }
-            }
-        }
-    }
-    st |= adv_max == ENTRY_ADV_INVALID ? ST_BAD_CODE : 0u;
-    st |= reach_max > 64u ? ST_SLOT_OVERFLOW : 0u;
+    DecState d;
+    dec_init(d, W, S, p, c, z, k, 0u);
+    relay_run<false>(d, W, L, S, g, end_bit, NoRecorder{});
+    return relay_exit_state(d);
 }
 
-// One-shot convenience: whole subsequence, coefficients straight to global memory.
-template <bool WRITE, class Words, class Luts>
-KPEG_HD SubState decode_span(const Words &W, const Luts &L, const StreamView &S, const JobGeom &g, uint32_t end_bit,
-                             uint32_t p, uint32_t c, uint32_t z, uint32_t k, uint32_t slot, int16_t *coef,
-                             int16_t *dcdiff, uint32_t *status_accum)
+// coefficients straight to global memory
+template <class Words, class Luts>
+KPEG_HD SubState write_span(const Words &W, const Luts &L, const StreamView &S, const JobGeom &g, uint32_t end_bit, uint32_t p,
+                            uint32_t c, uint32_t z, uint32_t k, uint32_t slot, int16_t *coef, int16_t *dcdiff,
+                            uint32_t *status_accum)
 {
     DecState d;
     dec_init(d, W, S, p, c, z, k, slot);
-    if (WRITE) {
-        const GlobalSink sink{coef, dcdiff};
-        decode_run<true, false>(d, W, L, S, g, end_bit, 0xFFFFFFFFu, sink, NoRecorder{});
-        if (d.st)
-            *status_accum |= d.st;
-    } else {
-        decode_run<false, false>(d, W, L, S, g, end_bit, 0xFFFFFFFFu, NullSink{}, NoRecorder{});
-    }
+    const GlobalSink sink{coef, dcdiff};
+    write_run(d, W, L, S, g, end_bit, 0xFFFFFFFFu, sink);
+    if (d.st)
+        *status_accum |= d.st;
     return dec_exit_state(d);
 }
 

@@ -3,13 +3,11 @@
 //   K0  unstuff_*      FF00 / RSTn removal + restart-segment table     (Decoder.cpp:532-577, 621-653)
 //   K1  entropy_*      Huffman + run-length decode, parallel over fixed-size subsequences with a
 //                      self-synchronising relay and a segmented offset scan (Decoder.cpp:655-855)
-//   K2  dc_*           DC prediction as a segmented prefix scan           (MCU.cpp:107-108)
-//   K3  idct_kernel    dequantise + de-zigzag + 8x8 IDCT + level shift + YCbCr->RGB + interleaved
-//                      store, one pass over HBM                           (MCU.cpp:110-279, Image.cpp:51-70)
+//   K2 + K3 live in k3_fused.cu: record expansion + DC prediction + dequantise + de-zigzag + 8x8 IDCT + level
+//                      shift + YCbCr->RGB + interleaved store as ONE kernel (MCU.cpp:93-279, Image.cpp:51-70)
 //
 // All file:line citations are relative to /root/reference.  The arithmetic lives in
 // entropy_core.h / idct_core.h (host+device inline, also exercised on the CPU by tests/emu).
-#include <cuda.h> // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <atomic>
@@ -20,7 +18,6 @@
 #include <utility>
 
 #include "entropy_core.h"
-#include "idct_core.h"
 #include "kernels.cuh"
 #include "unstuff_core.h"
 #include "kpeg_common.h"
@@ -455,8 +452,7 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_cold_kernel(EntropyAr
             const uint32_t end = min(p0 + a.g.sub_bits, total_bits);
             const uint32_t hint = a.g.nseg > 1u ? first_seg_at_or_after(a.seg_bit, a.g.nseg, p0) : (sub ? 1u : 0u);
             a.seg_hint[sub] = hint;
-            const SubState out = decode_span<false>(W, L, S, a.g, end, p0, 0u, 0u, hint, 0u, nullptr, nullptr, nullptr);
-            a.state[sub] = out;
+            a.state[sub] = relay_span(W, L, S, a.g, end, p0, 0u, 0u, hint);
         }
         __syncthreads(); // the slice is overwritten by the next tile
     }
@@ -493,7 +489,7 @@ __device__ __forceinline__ SubState relay_decode(const EntropyArgs &a, const Wor
                                                  uint32_t sub, uint32_t end, uint32_t p, uint32_t cz, bool sparse)
 {
     DecState d;
-    dec_init(d, W, S, p, cz >> 8, cz & 0xFFu, a.seg_hint[sub], 0u);
+    dec_init(d, W, S, p, (cz >> 8) & 3u, cz & 0xFFu, a.seg_hint[sub], 0u);
     if (a.rec) {
         GlobalRecorder R;
         R.base = a.rec + rec_base_index(sub, a.rec_kmax);
@@ -512,14 +508,14 @@ __device__ __forceinline__ SubState relay_decode(const EntropyArgs &a, const Wor
                 R.stride_bytes = 4u;
             }
         }
-        decode_run<false, true>(d, W, L, S, a.g, end, 0xFFFFFFFFu, NullSink{}, R);
+        relay_run<true>(d, W, L, S, a.g, end, R);
         a.nrec[sub] = min(d.nrec, NREC_MASK) | (area << 10);
-        if (d.nrec > a.rec_kmax || (d.st & ST_REC_OVERFLOW))
+        if (d.nrec > a.rec_kmax)
             atomicOr(&a.meta->status, ST_REC_OVERFLOW);
     } else {
-        decode_run<false, false>(d, W, L, S, a.g, end, 0xFFFFFFFFu, NullSink{}, NoRecorder{});
+        relay_run<false>(d, W, L, S, a.g, end, NoRecorder{});
     }
-    return dec_exit_state(d);
+    return relay_exit_state(d);
 }
 
 __device__ __forceinline__ int relay_slot_dev(int r) { return r < MAX_RELAY_ROUNDS ? r : 2 + ((r - 2) % (MAX_RELAY_ROUNDS - 2)); }
@@ -541,7 +537,7 @@ __device__ __forceinline__ void relay_publish(const EntropyArgs &a, uint32_t sub
         __stcg(reinterpret_cast<uint4 *>(&a.state[sub]), o);
         // Only a change of the exit STATE (position, component, zig-zag index) matters downstream; the
         // slot count of a subsequence changes almost always when its entry does, its exit state rarely.
-        if ((old.p != out.p || old.cz != out.cz) && sub + 1u < nsub)
+        if ((old.p != out.p || ((old.cz ^ out.cz) & CZ_STATE_MASK) != 0u) && sub + 1u < nsub)
             list_out[atomicAdd(count_out, 1u)] = sub + 1u;
     }
 }
@@ -569,12 +565,14 @@ __global__ void __launch_bounds__(ENTROPY_THREADS, 10) entropy_relay_full_kernel
                 in = a.state[sub - 1];
             const uint32_t start = sub << (wlog + 5u);
             // without records, a subsequence whose cold decode already started from this state is done
-            if (a.rec || (sub != 0u && !(in.p == start && in.cz == 0u))) {
+            if (a.rec || (sub != 0u && !(in.p == start && (in.cz & CZ_STATE_MASK) == 0u))) {
                 const SmemWords W = k1_words(sm, tile, wlog);
                 const uint32_t end = min((sub + 1u) << (wlog + 5u), total_bits);
-                const SubState out = relay_decode(a, W, L, S, sub, end, in.p, in.cz, false);
+                const SubState out = relay_decode(a, W, L, S, sub, end, in.p, in.cz & CZ_STATE_MASK, false);
                 if (sub)
                     relay_publish(a, sub, out, nsub, a.worklist[1], &a.meta->changed[1]);
+                else
+                    a.state[0] = out; // same state as the cold pass found (the entry is the true one), now with its annotations
             }
         }
         __syncthreads();
@@ -630,7 +628,7 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_sparse_kernel(E
     W.gw0 = inraw.x >> 5;
     StreamView S{a.seg_bit, total_bits};
     const uint32_t end = min((sub + 1u) << (wlog + 5u), total_bits);
-    const SubState out = relay_decode(a, W, L, S, sub, end, inraw.x, inraw.z, true);
+    const SubState out = relay_decode(a, W, L, S, sub, end, inraw.x, inraw.z & CZ_STATE_MASK, true);
     relay_publish(a, sub, out, nsub, a.worklist[round & 1], &a.meta->changed[slot_cur]);
 }
 
@@ -722,7 +720,7 @@ __global__ void __launch_bounds__(ENTROPY_THREADS, 8) entropy_relay_loop_kernel(
                 mine[k] = j0 + k < total_words ? __ldg(a.words + j0 + k) : 0u;
             W.gw0 = j0;
             const uint32_t end = min((sub + 1u) << (wlog + 5u), total_bits);
-            const SubState out = relay_decode(a, W, L, S, sub, end, inraw.x, inraw.z, true);
+            const SubState out = relay_decode(a, W, L, S, sub, end, inraw.x, inraw.z & CZ_STATE_MASK, true);
             relay_publish(a, sub, out, nsub, list_out, count_out);
         }
         if (solo) {
@@ -851,8 +849,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) entropy_scan_tiles_kernel(Entrop
         if (t < ntiles) {
             const SegVal ex = threadIdx.x == 0 ? s_carry : s_incl[threadIdx.x - 1];
             a.scan_tiles[t] = make_uint2(ex.f, ex.v);
-            if (t + 1u == ntiles)
+            if (t + 1u == ntiles) {
                 a.meta->final_slot = incl.v;
+                if (incl.v < a.g.total_blocks * 64u)
+                    atomicOr(&a.meta->status, ST_SEG_MISMATCH); // the stream ended before the last MCU
+            }
         }
         __syncthreads();
         if (threadIdx.x == SCAN_THREADS - 1)
@@ -861,9 +862,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) entropy_scan_tiles_kernel(Entrop
     }
 }
 
+// Third phase.  Besides start_slot[] it is the one place that looks at every subsequence's FINAL relay state, so it
+// also (1) turns the annotations of the last decode of every subsequence into device status bits, (2) cross-checks
+// the exit state against the slot count (the zig-zag index and component a subsequence ends in must be the ones its
+// end slot implies) and the record positions against the restart structure (a subsequence that crossed a boundary
+// must end, counting on across it, on the slot the boundary's absolute position gives: T.81 F.2.2.4 -- every
+// interval holds exactly Ri MCUs), and (3) notes for every strip of K3 the subsequence its first slot lies in.
 __global__ void __launch_bounds__(SCAN_THREADS) entropy_scan_apply_kernel(EntropyArgs a)
 {
     __shared__ SegVal s_w[SCAN_THREADS / 32];
+    __shared__ SegVal s_incl[SCAN_THREADS];
     const uint32_t nsub = a.meta->nsub;
     if (blockIdx.x * SCAN_THREADS >= nsub)
         return;
@@ -880,6 +888,33 @@ __global__ void __launch_bounds__(SCAN_THREADS) entropy_scan_apply_kernel(Entrop
         a.start_slot[i + 1u] = incl.v;
     if (i == 0u)
         a.start_slot[0] = 0u;
+    s_incl[threadIdx.x] = incl;
+    __syncthreads();
+    if (i >= nsub)
+        return;
+    const uint32_t begin = threadIdx.x ? s_incl[threadIdx.x - 1].v : (i ? carry.v : 0u), end = incl.v;
+    const SubState st = a.state[i];
+    uint32_t status = 0;
+    if (a.rec) { // annotations exist only for decodes that emitted records (the Huffman final pass checks for itself)
+        status |= (st.cz & CZ_BAD_CODE) ? ST_BAD_CODE : 0u;
+        status |= (st.cz & CZ_SLOT_OVERFLOW) ? ST_SLOT_OVERFLOW : 0u;
+        status |= (st.cz & CZ_SEG_MISMATCH) ? ST_SEG_MISMATCH : 0u;
+        const uint32_t total_slots = a.g.total_blocks * 64u;
+        // surplus symbols after the last MCU of the stream are not an error (as in the Huffman final pass)
+        if (st.seg >= 0 && (begin & ~63u) + (st.cz >> CZ_POS_SHIFT) != end && !((uint32_t)st.seg >= a.g.nseg && end >= total_slots))
+            status |= ST_SEG_MISMATCH;
+        if ((end & 63u) != (st.cz & 63u) || ((end >> 6) % a.g.ncomp) != ((st.cz >> 8) & 3u))
+            status |= ST_EXIT_MISMATCH;
+    }
+    if (status)
+        atomicOr(&a.meta->status, status);
+    // strips of K3 whose first slot lies in [begin, end): a subsequence spans at most a handful
+    if (a.strip_sub && end > begin) {
+        const uint32_t sps = a.strip_slots;
+        uint32_t s0 = (begin + sps - 1u) / sps;
+        for (uint32_t k = 0; k < 64u && s0 < a.nstrips && s0 * sps < end; ++k, ++s0)
+            a.strip_sub[s0] = i;
+    }
 }
 
 // ---- final pass -------------------------------------------------------------------------------------
@@ -1002,7 +1037,7 @@ __global__ void __launch_bounds__(WRITE_THREADS) entropy_write_kernel(EntropyArg
             if (sub) {
                 const SubState in = a.state[sub - 1];
                 p = in.p;
-                c = in.cz >> 8;
+                c = (in.cz >> 8) & 3u;
                 z = in.cz & 0xFFu;
             }
             const uint32_t slot = a.start_slot[sub];
@@ -1029,7 +1064,7 @@ __global__ void __launch_bounds__(WRITE_THREADS) entropy_write_kernel(EntropyArg
                 sink.slot0 = wb << 6;
                 // past the tile's own range (corrupt stream): finish in one go, writes fall outside the window
                 const uint32_t limit = wb < b_end ? (wb + WRITE_WIN_BLOCKS) << 6 : 0xFFFFFFFFu;
-                decode_run<true, false>(d, W, L, S, a.g, end, limit, sink, NoRecorder{});
+                write_run(d, W, L, S, a.g, end, limit, sink);
                 done = d.p >= end;
             }
             const bool all_done = __syncthreads_and(done);
@@ -1042,94 +1077,7 @@ __global__ void __launch_bounds__(WRITE_THREADS) entropy_write_kernel(EntropyArg
             st |= d.st;
             const SubState rec = a.state[sub];
             const SubState out = dec_exit_state(d);
-            if (out.p != rec.p || out.cz != rec.cz)
-                st |= ST_EXIT_MISMATCH;
-            if (sub + 1u == nsub && a.meta->final_slot < total_slots)
-                st |= ST_SEG_MISMATCH; // the stream ended before the last MCU
-        }
-        __syncthreads();
-    }
-    if (st)
-        atomicOr(&a.meta->status, st);
-}
-
-// Final pass over the symbol records (see entropy_core.h): no Huffman decode, no stream, no tables --
-// a thread walks its subsequence's records (coalesced k-major loads, independent of each other, so
-// several are in flight), tracks (slot, zig-zag index) and drops values into the shared-memory window.
-struct GlobalRecAt {
-    const uint32_t *base;
-    uint32_t stride_bytes; // 128 in the warp-interleaved list, 4 in a private area: one IMAD.WIDE per address
-    __device__ __forceinline__ uint32_t operator()(uint32_t k) const
-    {
-        return __ldg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(base) + (size_t)k * stride_bytes));
-    }
-};
-
-__global__ void __launch_bounds__(WRITE_THREADS) entropy_expand_kernel(EntropyArgs a)
-{
-    extern __shared__ __align__(16) unsigned char k1_raw[];
-    WriteSmemTail &tail = *reinterpret_cast<WriteSmemTail *>(k1_raw);
-    const uint32_t nsub = a.meta->nsub;
-    const uint32_t ntiles = (nsub + WRITE_THREADS - 1) / WRITE_THREADS;
-    const uint32_t total_slots = a.g.total_blocks * 64u;
-    const uint32_t t = threadIdx.x;
-    uint32_t st = 0;
-    // shared addresses of the window: made opaque, or the compiler re-derives them from the CTA's shared window
-    // base (S2R + LEA) for every record instead of keeping two registers
-    uint32_t win_obuf = (uint32_t)__cvta_generic_to_shared(tail.obuf);
-    asm volatile("" : "+r"(win_obuf));
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint32_t sub0 = tile * WRITE_THREADS, sub = sub0 + t;
-        const uint32_t s_begin = a.start_slot[sub0];
-        uint32_t s_end = (sub0 + WRITE_THREADS < nsub) ? a.start_slot[sub0 + WRITE_THREADS] : a.meta->final_slot;
-        s_end = min(s_end, total_slots);
-        const uint32_t b_first = s_begin >> 6;
-        const uint32_t b_end = s_end > s_begin ? (s_end + 63u) >> 6 : b_first;
-
-        uint32_t k = 0, n = 0, slot = 0, z = 0, expect = 0;
-        bool done = true;
-        GlobalRecAt R;
-        R.base = a.rec + rec_base_index(sub, a.rec_kmax);
-        R.stride_bytes = 128u;
-        if (sub < nsub) {
-            const uint32_t nr = a.nrec[sub];
-            n = min(nr & NREC_MASK, a.rec_kmax);
-            if (nr >> 10) { // redone in a sparse relay round: private contiguous area
-                R.base = a.rec_alt + (size_t)((nr >> 10) - 1u) * a.rec_kmax;
-                R.stride_bytes = 4u;
-            }
-            slot = a.start_slot[sub];
-            z = sub ? (a.state[sub - 1].cz & 0xFFu) : 0u;
-            if ((slot & 63u) != z)
-                st |= ST_EXIT_MISMATCH;
-            expect = (sub + 1u < nsub) ? a.start_slot[sub + 1u] : a.meta->final_slot;
-            done = false;
-        }
-        for (uint32_t wb = b_first;; wb += WRITE_WIN_BLOCKS) {
-            {
-                uint4 *o = reinterpret_cast<uint4 *>(&tail);
-                constexpr int N16 = (int)(sizeof(WriteSmemTail) / 16);
-#pragma unroll 4
-                for (int i = t; i < N16; i += WRITE_THREADS)
-                    o[i] = make_uint4(0, 0, 0, 0);
-            }
-            __syncthreads();
-            if (!done) {
-                SmemSink sink;
-                sink.obuf_addr = win_obuf;
-                sink.slot0 = wb << 6;
-                const uint32_t limit = wb < b_end ? (wb + WRITE_WIN_BLOCKS) << 6 : 0xFFFFFFFFu;
-                expand_run(k, n, slot, z, st, R, a.g, limit, sink);
-                done = k >= n;
-            }
-            const bool all_done = __syncthreads_and(done);
-            write_flush_window(a, tail, wb, b_first, b_end, s_begin, s_end, t);
-            if (all_done)
-                break;
-            __syncthreads();
-        }
-        if (sub < nsub) {
-            if (slot != expect)
+            if (out.p != rec.p || out.cz != (rec.cz & CZ_STATE_MASK))
                 st |= ST_EXIT_MISMATCH;
             if (sub + 1u == nsub && a.meta->final_slot < total_slots)
                 st |= ST_SEG_MISMATCH; // the stream ended before the last MCU
@@ -1231,16 +1179,6 @@ void launch_entropy_scan(const EntropyArgs &a, cudaStream_t s, uint32_t *launche
     *launches += 3;
 }
 
-static uint32_t g_k1_expand_grid_cap = 148 * 6;
-
-void launch_entropy_expand(const EntropyArgs &a, cudaStream_t s, uint32_t *launches)
-{
-    const uint32_t tiles = (a.nsub_max + WRITE_THREADS - 1) / WRITE_THREADS;
-    const uint32_t grid = tiles < g_k1_expand_grid_cap ? tiles : g_k1_expand_grid_cap;
-    entropy_expand_kernel<<<grid, WRITE_THREADS, sizeof(WriteSmemTail), s>>>(a);
-    ++*launches;
-}
-
 void launch_entropy_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches)
 {
     const uint32_t wlog = ilog2(a.g.sub_bits / 32u);
@@ -1249,1150 +1187,6 @@ void launch_entropy_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launch
     entropy_write_kernel<<<grid, WRITE_THREADS, k1_write_smem_bytes(a.g.sub_bits), s>>>(a, wlog);
     ++*launches;
 }
-
-// =================================================================================================
-// K2: DC prediction = segmented prefix sum of the DC differences (MCU.cpp:107-108; predictor reset at
-// every restart interval / image start, T.81 F.2.1.3.1 -- the reference never resets)
-// =================================================================================================
-
-__device__ __forceinline__ bool mcu_is_reset(const JobGeom &g, uint32_t m)
-{
-    const uint32_t mi = m % g.mcus_per_image;
-    return g.restart_interval ? (mi % g.restart_interval) == 0u : mi == 0u;
-}
-
-struct Dc3 {
-    int32_t v[3];
-    uint32_t f;
-};
-
-__device__ __forceinline__ Dc3 dc_combine(const Dc3 &a, const Dc3 &b) // a then b
-{
-    Dc3 r;
-    r.f = a.f | b.f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-        r.v[c] = b.f ? b.v[c] : a.v[c] + b.v[c];
-    return r;
-}
-
-__device__ __forceinline__ Dc3 dc_shfl_up(const Dc3 &x, int d)
-{
-    Dc3 r;
-    r.f = __shfl_up_sync(0xffffffffu, x.f, d);
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-        r.v[c] = __shfl_up_sync(0xffffffffu, x.v[c], d);
-    return r;
-}
-
-// Inclusive segmented scan across the block of one Dc3 per thread; returns the inclusive value and
-// the block aggregate.
-__device__ __forceinline__ Dc3 dc_block_scan(Dc3 x, Dc3 *s_w /*[DC_THREADS/32]*/, Dc3 &aggregate)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const Dc3 o = dc_shfl_up(x, d);
-        if (lane >= d)
-            x = dc_combine(o, x);
-    }
-    if (lane == 31)
-        s_w[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-        Dc3 w;
-        if (lane < DC_THREADS / 32)
-            w = s_w[lane];
-        else {
-            w.f = 0;
-            w.v[0] = w.v[1] = w.v[2] = 0;
-        }
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const Dc3 o = dc_shfl_up(w, d);
-            if (lane >= d)
-                w = dc_combine(o, w);
-        }
-        if (lane < DC_THREADS / 32)
-            s_w[lane] = w;
-    }
-    __syncthreads();
-    if (warp > 0)
-        x = dc_combine(s_w[warp - 1], x);
-    aggregate = s_w[DC_THREADS / 32 - 1];
-    return x;
-}
-
-// The thread's DC_MCUS_PER_THREAD consecutive MCUs: their DC differences (as 8-byte words when the run is whole and
-// aligned) and the running inclusive values.  The reset predicate (mcu_is_reset) is evaluated once with two
-// divisions and then stepped.
-__device__ __forceinline__ Dc3 dc_thread_local(const DcArgs &a, uint32_t m0, uint32_t total_mcus, Dc3 incl[DC_MCUS_PER_THREAD])
-{
-    static_assert(DC_MCUS_PER_THREAD == 4, "the 8-byte access pattern below is written for four MCUs per thread");
-    const uint32_t nc = a.g.ncomp;
-    int16_t v[DC_MCUS_PER_THREAD * 3];
-#pragma unroll
-    for (int i = 0; i < DC_MCUS_PER_THREAD * 3; ++i)
-        v[i] = 0;
-    const int16_t *src = a.dcdiff + (size_t)m0 * nc;
-    const bool whole = m0 + DC_MCUS_PER_THREAD <= total_mcus && (reinterpret_cast<uintptr_t>(src) & 7u) == 0;
-    if (whole && nc == 3) {
-        uint2 w[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-            w[i] = __ldg(reinterpret_cast<const uint2 *>(src) + i);
-#pragma unroll
-        for (int i = 0; i < 12; ++i) {
-            const uint32_t x = (i & 2) ? w[i >> 2].y : w[i >> 2].x;
-            v[i] = (int16_t)((i & 1) ? (x >> 16) : (x & 0xFFFFu));
-        }
-    } else if (whole && nc == 1) {
-        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(src));
-        v[0] = (int16_t)(w.x & 0xFFFFu), v[3] = (int16_t)(w.x >> 16), v[6] = (int16_t)(w.y & 0xFFFFu), v[9] = (int16_t)(w.y >> 16);
-    } else {
-#pragma unroll
-        for (int k = 0; k < DC_MCUS_PER_THREAD; ++k)
-            if (m0 + k < total_mcus)
-                for (uint32_t c = 0; c < nc; ++c)
-                    v[k * 3 + c] = src[k * nc + c];
-    }
-    uint32_t mi = m0 % a.g.mcus_per_image;
-    uint32_t ri = a.g.restart_interval ? mi % a.g.restart_interval : mi;
-    Dc3 run;
-    run.f = 0;
-    run.v[0] = run.v[1] = run.v[2] = 0;
-#pragma unroll
-    for (int k = 0; k < DC_MCUS_PER_THREAD; ++k) {
-        Dc3 e;
-        e.f = 0;
-        e.v[0] = e.v[1] = e.v[2] = 0;
-        if (m0 + k < total_mcus) {
-            e.f = ri == 0u ? 1u : 0u; // == mcu_is_reset(a.g, m0 + k)
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                e.v[c] = v[k * 3 + c];
-        }
-        run = dc_combine(run, e);
-        incl[k] = run;
-        ++mi, ++ri;
-        if (mi == a.g.mcus_per_image)
-            mi = 0, ri = 0;
-        else if (a.g.restart_interval && ri == a.g.restart_interval)
-            ri = 0;
-    }
-    return run;
-}
-
-__global__ void __launch_bounds__(DC_THREADS) dc_reduce_kernel(DcArgs a)
-{
-    __shared__ Dc3 s_w[DC_THREADS / 32];
-    const uint32_t total_mcus = a.g.nimages * a.g.mcus_per_image;
-    const uint32_t m0 = (blockIdx.x * DC_THREADS + threadIdx.x) * DC_MCUS_PER_THREAD;
-    Dc3 incl[DC_MCUS_PER_THREAD];
-    const Dc3 mine = dc_thread_local(a, m0, total_mcus, incl);
-    Dc3 agg;
-    dc_block_scan(mine, s_w, agg);
-    if (threadIdx.x == 0) {
-        a.tile_carry[blockIdx.x * 4 + 0] = agg.v[0];
-        a.tile_carry[blockIdx.x * 4 + 1] = agg.v[1];
-        a.tile_carry[blockIdx.x * 4 + 2] = agg.v[2];
-        a.tile_carry[blockIdx.x * 4 + 3] = (int32_t)agg.f;
-    }
-}
-
-// one block: tile_carry[t] <- exclusive segmented scan (value carried INTO tile t)
-__global__ void __launch_bounds__(DC_THREADS) dc_tile_scan_kernel(DcArgs a)
-{
-    __shared__ Dc3 s_w[DC_THREADS / 32];
-    __shared__ Dc3 s_carry;
-    __shared__ Dc3 s_incl[DC_THREADS];
-    if (threadIdx.x == 0) {
-        s_carry.f = 0;
-        s_carry.v[0] = s_carry.v[1] = s_carry.v[2] = 0;
-    }
-    __syncthreads();
-    for (uint32_t t0 = 0; t0 < a.ntiles; t0 += DC_THREADS) {
-        const uint32_t t = t0 + threadIdx.x;
-        Dc3 e;
-        e.f = 0;
-        e.v[0] = e.v[1] = e.v[2] = 0;
-        if (t < a.ntiles) {
-            e.v[0] = a.tile_carry[t * 4 + 0];
-            e.v[1] = a.tile_carry[t * 4 + 1];
-            e.v[2] = a.tile_carry[t * 4 + 2];
-            e.f = (uint32_t)a.tile_carry[t * 4 + 3];
-        }
-        Dc3 agg;
-        const Dc3 incl = dc_block_scan(e, s_w, agg);
-        const Dc3 carry = s_carry;
-        const Dc3 full = dc_combine(carry, incl); // inclusive up to tile t
-        // exclusive value = inclusive of t-1: shuffle through shared memory
-        s_incl[threadIdx.x] = full;
-        __syncthreads();
-        if (t < a.ntiles) {
-            const Dc3 ex = threadIdx.x == 0 ? carry : s_incl[threadIdx.x - 1];
-            a.tile_carry[t * 4 + 0] = ex.v[0];
-            a.tile_carry[t * 4 + 1] = ex.v[1];
-            a.tile_carry[t * 4 + 2] = ex.v[2];
-        }
-        __syncthreads();
-        if (threadIdx.x == DC_THREADS - 1)
-            s_carry = full;
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(DC_THREADS) dc_apply_kernel(DcArgs a)
-{
-    __shared__ Dc3 s_w[DC_THREADS / 32];
-    const uint32_t total_mcus = a.g.nimages * a.g.mcus_per_image;
-    const uint32_t m0 = (blockIdx.x * DC_THREADS + threadIdx.x) * DC_MCUS_PER_THREAD;
-    Dc3 incl[DC_MCUS_PER_THREAD];
-    const Dc3 mine = dc_thread_local(a, m0, total_mcus, incl);
-    Dc3 agg;
-    const Dc3 inc = dc_block_scan(mine, s_w, agg);
-    // exclusive prefix of this thread = inclusive of the previous thread (through shared memory)
-    __shared__ Dc3 s_incl[DC_THREADS];
-    s_incl[threadIdx.x] = inc;
-    __syncthreads();
-    Dc3 pre;
-    pre.f = 0;
-    pre.v[0] = a.tile_carry[blockIdx.x * 4 + 0];
-    pre.v[1] = a.tile_carry[blockIdx.x * 4 + 1];
-    pre.v[2] = a.tile_carry[blockIdx.x * 4 + 2];
-    if (threadIdx.x > 0)
-        pre = dc_combine(pre, s_incl[threadIdx.x - 1]);
-    const uint32_t nc = a.g.ncomp;
-    int16_t *dst = a.dc + (size_t)m0 * nc;
-    Dc3 r[DC_MCUS_PER_THREAD];
-#pragma unroll
-    for (int k = 0; k < DC_MCUS_PER_THREAD; ++k)
-        r[k] = dc_combine(pre, incl[k]);
-    const bool whole = m0 + DC_MCUS_PER_THREAD <= total_mcus && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0;
-    auto h = [](int32_t x) { return (uint32_t)x & 0xFFFFu; };
-    if (whole && nc == 3) { // 12 values = three 8-byte stores
-        reinterpret_cast<uint2 *>(dst)[0] = make_uint2(h(r[0].v[0]) | (h(r[0].v[1]) << 16), h(r[0].v[2]) | (h(r[1].v[0]) << 16));
-        reinterpret_cast<uint2 *>(dst)[1] = make_uint2(h(r[1].v[1]) | (h(r[1].v[2]) << 16), h(r[2].v[0]) | (h(r[2].v[1]) << 16));
-        reinterpret_cast<uint2 *>(dst)[2] = make_uint2(h(r[2].v[2]) | (h(r[3].v[0]) << 16), h(r[3].v[1]) | (h(r[3].v[2]) << 16));
-    } else if (whole && nc == 1) {
-        reinterpret_cast<uint2 *>(dst)[0] = make_uint2(h(r[0].v[0]) | (h(r[1].v[0]) << 16), h(r[2].v[0]) | (h(r[3].v[0]) << 16));
-    } else {
-#pragma unroll
-        for (int k = 0; k < DC_MCUS_PER_THREAD; ++k)
-            if (m0 + k < total_mcus)
-                for (uint32_t c = 0; c < nc; ++c)
-                    dst[k * nc + c] = (int16_t)r[k].v[c];
-    }
-}
-
-void launch_dc_scan(const DcArgs &a, cudaStream_t s, uint32_t *launches)
-{
-    dc_reduce_kernel<<<a.ntiles, DC_THREADS, 0, s>>>(a);
-    dc_tile_scan_kernel<<<1, DC_THREADS, 0, s>>>(a);
-    dc_apply_kernel<<<a.ntiles, DC_THREADS, 0, s>>>(a);
-    *launches += 3;
-}
-
-// =================================================================================================
-// K3: fused dequantise + de-zigzag + IDCT + level shift + colour conversion + interleaved store
-// =================================================================================================
-//
-// idct_kernel: one CTA reconstructs a strip of IDCT_MCUS_PER_CTA consecutive MCUs (a contiguous chunk
-// of the coefficient buffer, and -- when the strip does not wrap -- 8 contiguous runs of pixels).
-//   stage 0  the copy engine brings the strip's coefficients (2-D TMA tile, 128-byte swizzle: the per-thread
-//            128-byte reads of stage 1 are bank-conflict free) and the quantiser tables into shared memory
-//   stage 1  one thread per 8x8 block, all 64 values in registers, two fp32 lanes per instruction (FADD2 / FMUL2 /
-//            FFMA2): dequantise (AAN prescale folded into the quantiser), de-zigzag by register renaming, separable
-//            fp32 IDCT, rounding, tie-band test (a 64-bit mask per block)
-//   stage 2  per pixel row: YCbCr -> RGB on pixel pairs (fp32 with proven margin, double otherwise), pack, store;
-//            pixels with a sample inside the tie band are ALSO appended to a global record list
-// idct_patch_kernel: one thread per record re-evaluates the flagged samples in the reference's own
-// operation order (exact_sample), redoes the colour conversion and rewrites the pixel.  Keeping this
-// out of the fused kernel matters: it is a long, strictly serial double-precision chain on ~0.3 % of
-// the pixels; inside the strip kernel it kept two of three warps waiting at a barrier.
-
-__device__ __constant__ ZigZagTables c_zz = make_zigzag_tables();
-
-template <int I>
-struct ZzNat {
-    static constexpr int value = zigzag_to_natural(I);
-};
-
-constexpr int IDCT_REC_CAP = 134;
-constexpr int IDCT_REC_FIXED = 16;          // slots of the global record list every strip owns
-constexpr uint32_t TIE_EMPTY = 0xFFFFFFFFu; // pixel index of an unused slot
-constexpr uint32_t IDCT_PREFETCH_AHEAD = 148u * 8u; // strips resident on the device at a time
-#ifndef KPEG_IDCT_MIN_CTAS
-#define KPEG_IDCT_MIN_CTAS 8
-#endif
-
-// Per-block facts the colour stage needs, derived from A = sum |dequantised coefficient| (every sample of the
-// block is bounded by A / 4: the 64 basis functions are bounded by 1/4):
-//   BLK_NONZERO  some coefficient is non-zero (otherwise all 64 samples are 0)
-//   BLK_WIDE     A > COLOUR_SAFE_A: samples may leave the range the fp32 colour path is proven for
-constexpr uint32_t BLK_NONZERO = 1u, BLK_WIDE = 2u;
-constexpr float COLOUR_SAFE_A = 4.0f * (COLOUR_FAST_RANGE - 8.0f);
-
-// Bit layout of a block's 64-bit tie mask (x = rows 0..3, y = rows 4..7): the bit of sample (row, col) in its word.
-// The upper 16 bits hold columns 0..3, the lower 16 columns 4..7; inside, earlier samples sit higher.
-__host__ __device__ constexpr int tie_bit(int row, int col) { return ((col & 4) ? 0 : 16) + 15 - (4 * (row & 3) + (col & 3)); }
-// bits of one row in its word
-__host__ __device__ constexpr uint32_t tie_row_bits(int row) { return (0xFu << (28 - 4 * (row & 3))) | (0xFu << (12 - 4 * (row & 3))); }
-// inverse: bit index b of word w (0 = rows 0..3, 1 = rows 4..7) -> sample index row * 8 + col
-__device__ __forceinline__ int tie_sample(int w, int b)
-{
-    const int k = 15 - (b & 15);
-    return (4 * w + (k >> 2)) * 8 + ((b & 16) ? 0 : 4) + (k & 3);
-}
-
-template <int NC>
-struct IdctSmem {
-    static constexpr int NM = IDCT_MCUS_PER_CTA;
-    static constexpr int NB = NM * NC;
-    // The strip's coefficients (16-byte chunks, chunk k of block b at b*8 + (k ^ (b & 7))) are dead once
-    // every thread has pulled its block into registers; the rounded samples then reuse the space.
-    union {
-        uint4 coef[NB * 8];
-        float4 samp[NC * 8 * 2 * NM]; // [comp][row][half][mcu] -> 4 samples (rounded, unshifted)
-    };
-    float2 qpair[NC][32];         // prescaled quantisers in the pair order of the transform (pair_nat)
-    float2 qdc[NC][32];           // the same with every AC entry zero: what a block that loses its AC terms (F1) multiplies by
-    uint2 tie[NB];                // per block: 64-bit mask of the samples inside the tie band
-    uint8_t flag[NB];             // per block: BLK_NONZERO | BLK_WIDE (decides the colour variant of its MCU)
-    uint2 rec[IDCT_REC_CAP];      // tie records of this strip (compact form): the first IDCT_REC_FIXED go to the strip's own slots of the global list
-    uint32_t nrec, rec_base;
-    uint32_t img0, by0, bx0;      // image / block row / block column of the strip's first MCU (divisions done once, by thread 0)
-    uint32_t pad_;
-    unsigned long long mbar;      // completion barrier of the stage-0 bulk copies
-};
-
-// ---- two fp32 lanes per instruction (sm_100a FADD2 / FMUL2 / FFMA2) -------------------------------
-// K3 is bound by instruction issue, not by HBM or by the FMA pipe, and most of what it issues are fp32 adds of
-// the IDCT butterflies.  Blackwell's packed fp32 instructions do two independent IEEE lanes per issue slot, so the
-// transform, the dequantisation, the rounding and the colour arithmetic run on register pairs.  A pair is a
-// 64-bit register; packing / unpacking is register naming (mov.b64), not arithmetic.
-struct F2 {
-    unsigned long long v;
-};
-__device__ __forceinline__ F2 pack2(float lo, float hi)
-{
-    F2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(F2 a, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
-__device__ __forceinline__ float lo2(F2 a)
-{
-    float lo, hi;
-    unpack2(a, lo, hi);
-    return lo;
-}
-__device__ __forceinline__ float hi2(F2 a)
-{
-    float lo, hi;
-    unpack2(a, lo, hi);
-    return hi;
-}
-__device__ __forceinline__ F2 splat2(float k) { return pack2(k, k); }
-__device__ __forceinline__ F2 lane_add(F2 a, F2 b)
-{
-    F2 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-    return r;
-}
-__device__ __forceinline__ F2 lane_sub(F2 a, F2 b)
-{
-    F2 r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-    return r;
-}
-__device__ __forceinline__ F2 lane_mul(F2 a, F2 b)
-{
-    F2 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-    return r;
-}
-__device__ __forceinline__ F2 lane_fma(F2 a, F2 b, F2 c)
-{
-    F2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
-    return r;
-}
-__device__ __forceinline__ F2 lane_mul_k(F2 a, float k) { return lane_mul(a, splat2(k)); }
-__device__ __forceinline__ F2 lane_fma_k(F2 a, float k, F2 c) { return lane_fma(a, splat2(k), c); }
-
-// coefficient I (zig-zag index) of a block held as eight 16-byte chunks
-template <int I>
-__device__ __forceinline__ float chunk_coef(const uint4 (&ch)[8])
-{
-    constexpr int k = I >> 3, j = (I & 7) >> 1, hi = I & 1;
-    const uint32_t w = j == 0 ? ch[k].x : (j == 1 ? ch[k].y : (j == 2 ? ch[k].z : ch[k].w));
-    return (float)(short)(hi ? (w >> 16) : (w & 0xFFFFu));
-}
-
-template <int NAT>
-struct NatZz {
-    static constexpr int value = make_zigzag_tables().nat2zz[NAT];
-};
-
-// Dequantise (AAN prescale folded into q; q arrives in pair order, see IdctSmem::qpair) and de-zigzag by register
-// renaming; on the way, A = sum |c_i| * q_i, the magnitude the tie band is proportional to: |f| * (1 / prescale)
-// with the reciprocal an immediate and the absolute value a free operand modifier -- one FFMA per coefficient.
-// (fp32 accumulation is off by < 1e-5 relative; the band carries a 10 % margin.)
-template <int... Ps>
-__device__ __forceinline__ float dequant_dezigzag(const uint4 (&ch)[8], const float2 *qpair, F2 (&P)[32],
-                                                  std::integer_sequence<int, Ps...>)
-{
-    float A[4] = {0.0f, 0.0f, 0.0f, 0.0f}; // four short dependent chains instead of one of 64
-    auto one = [&](auto PI) {
-        constexpr int p = decltype(PI)::value;
-        constexpr int n0 = pair_nat(p, 0), n1 = pair_nat(p, 1);
-        const float2 q = qpair[p];
-        P[p] = lane_mul(pack2(chunk_coef<NatZz<n0>::value>(ch), chunk_coef<NatZz<n1>::value>(ch)), pack2(q.x, q.y));
-        A[p & 1] = fmaf(fabsf(lo2(P[p])), aan_unscale(n0), A[p & 1]);
-        A[2 + (p & 1)] = fmaf(fabsf(hi2(P[p])), aan_unscale(n1), A[2 + (p & 1)]);
-    };
-    (one(std::integral_constant<int, Ps>{}), ...);
-    return (A[0] + A[1]) + (A[2] + A[3]);
-}
-
-// Packed 2-D transform, first half: the row pass, two rows per instruction.
-// P[rp * 8 + c] = rows pair_row(rp, 0), pair_row(rp, 1) at column c, in place.
-__device__ __forceinline__ void idct_rows_packed(F2 (&P)[32])
-{
-#pragma unroll
-    for (int rp = 0; rp < 4; ++rp)
-        idct8_aan(P[rp * 8 + 0], P[rp * 8 + 1], P[rp * 8 + 2], P[rp * 8 + 3], P[rp * 8 + 4], P[rp * 8 + 5],
-                  P[rp * 8 + 6], P[rp * 8 + 7]);
-}
-
-// Second half, one column: idct8_aan (idct_core.h) over the eight rows, same operations in the same order.
-// With X = (v0, v1), Y = (v4, v7), X2 = (v2, v5), Y2 = (v6, v3) the first two butterfly stages of the even part
-// (low lanes) and of the odd part (high lanes) are the same instruction, so they run packed; the rest is scalar on
-// the halves.  Nothing is moved between registers.  v[r] = row r of this column.
-__device__ __forceinline__ void idct8_column(F2 X, F2 Y, F2 X2, F2 Y2, float (&v)[8])
-{
-    const F2 S1 = lane_add(X, Y), D1 = lane_sub(X, Y);     // (t10, z11)  (t11, z12)
-    const F2 S2 = lane_add(X2, Y2), D2 = lane_sub(X2, Y2); // (t13, z13)  (v2 - v6, z10)
-    const F2 E = lane_add(S1, S2), F = lane_sub(S1, S2);   // (e0, o7)    (e3, z11 - z13)
-    // even part
-    const float t11 = lo2(D1), t13 = lo2(S2), e0 = lo2(E), e3 = lo2(F);
-    const float n12 = lane_fma_k(lo2(D2), -1.414213562373095f, t13); // -(t12)
-    const float e1 = lane_sub(t11, n12), e2 = lane_add(t11, n12);
-    // odd part
-    const float z12 = hi2(D1), z10 = hi2(D2), o7 = hi2(E);
-    const float z5 = lane_mul_k(lane_add(z10, z12), 1.847759065022573f);
-    const float t20 = lane_fma_k(z12, -1.082392200292394f, z5);
-    const float t22 = lane_fma_k(z10, -2.613125929752753f, z5);
-    const float o6 = lane_sub(t22, o7);
-    const float n5 = lane_fma_k(hi2(F), -1.414213562373095f, o6); // -(o5)
-    const float o4 = lane_add(t20, n5);
-    v[0] = lane_add(e0, o7);
-    v[7] = lane_sub(e0, o7);
-    v[1] = lane_add(e1, o6);
-    v[6] = lane_sub(e1, o6);
-    v[2] = lane_sub(e2, n5);
-    v[5] = lane_add(e2, n5);
-    v[3] = lane_add(e3, o4);
-    v[4] = lane_sub(e3, o4);
-}
-
-// Four ints -> four bytes with unsigned saturation (cvt.pack.sat: two values per instruction).
-__device__ __forceinline__ uint32_t pack4_sat(int a, int b, int c, int d)
-{
-    // cvt.pack.sat.u8.s32.b32 d, x, y, z:  d = (z << 16) | (sat(x) << 8) | sat(y)
-    uint32_t hi, r;
-    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(d), "r"(c));
-    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(a), "r"(hi));
-    return r;
-}
-
-// Rare path (G within 1e-3 of an integer, or samples out of the fp32-safe range): the reference's
-// own double expression.  Out of line: eight unrolled call sites.
-__device__ __noinline__ uint32_t colour_exact_px(float y, float cb, float cr)
-{
-    int R, G, B;
-    ycc_to_rgb_exact((int)y, (int)cb, (int)cr, R, G, B); // clamped to [0,255]
-    return (uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16);
-}
-
-// ---- exact pass ----------------------------------------------------------------------------------
-// Tables of the exact path in shared memory (lane-varying indices would serialise in the constant cache).
-struct ExactSmem {
-    double cosd[8][8];
-    float cc[8][8];
-    int32_t qint[MAX_COMP][64];
-    unsigned char nat2zz[64];
-};
-
-__device__ __forceinline__ void exact_smem_load(ExactSmem &es, const DeviceTables *t)
-{
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
-        (&es.cosd[0][0])[i] = t->cosd[0][i];
-        (&es.cc[0][0])[i] = t->cc[0][i];
-        es.nat2zz[i] = c_zz.nat2zz[i];
-    }
-    for (int i = threadIdx.x; i < MAX_COMP * 64; i += blockDim.x)
-        (&es.qint[0][0])[i] = t->qint[0][i];
-    __syncthreads();
-}
-
-struct ExactCtx {
-    const int16_t *coef, *dc, *dcdiff;
-    uint8_t *pixels;
-    uint32_t parity;
-};
-
-__device__ __forceinline__ ExactCtx exact_ctx(const IdctArgs &a)
-{
-    ExactCtx x;
-    x.coef = a.coef;
-    x.dc = a.dc;
-    x.dcdiff = a.dcdiff;
-    x.pixels = a.pixels;
-    x.parity = a.g.flags & 1u;
-    return x;
-}
-
-// coefficient I (zig-zag index) of a block held as eight 16-byte chunks, as an integer
-template <int I>
-__device__ __forceinline__ int chunk_coef_int(const uint4 (&ch)[8])
-{
-    constexpr int k = I >> 3, j = (I & 7) >> 1, hi = I & 1;
-    const uint32_t w = j == 0 ? ch[k].x : (j == 1 ? ch[k].y : (j == 2 ? ch[k].z : ch[k].w));
-    return (int)(short)(hi ? (w >> 16) : (w & 0xFFFFu));
-}
-
-// The 64 terms of the reference's sum (idct_core.h exact_sample, MCU.cpp:184-198) in ascending natural order
-// (== u outer, v inner), fully unrolled: every index is a compile-time constant, the block stays in registers, and
-// there is no branch and no load in the chain.  A zero coefficient contributes +-0, which leaves the float
-// accumulator unchanged, so evaluating all 64 terms gives the same bits as skipping the zero ones.
-template <int... Ns>
-__device__ __forceinline__ float exact_terms(const uint4 (&ch)[8], const int32_t *q, const double (&cx)[8],
-                                             const double (&cy)[8], float c00, float c01, std::integer_sequence<int, Ns...>)
-{
-    float sum = 0.0f;
-    auto term = [&](auto N) {
-        constexpr int nat = decltype(N)::value, zi = NatZz<nat>::value, u = nat >> 3, v = nat & 7;
-        const int F = chunk_coef_int<zi>(ch) * q[zi];                                   // MCU.cpp:110-112, :115-120
-        const float cc = (u == 0 && v == 0) ? c00 : ((u == 0 || v == 0) ? c01 : 1.0f); // Cu * Cv
-        const float t = mul_f32(cc, (float)F);
-        const double d = mul_f64(mul_f64((double)t, cx[u]), cy[v]);
-        sum = (float)add_f64((double)sum, d); // float accumulator, rounded every term
-    };
-    (term(std::integral_constant<int, Ns>{}), ...);
-    return sum;
-}
-
-// The reference's evaluation of sample s of global block gb (component comp).
-__device__ __noinline__ int exact_sample_global(const int16_t *coef, const int16_t *dc, const int16_t *dcdiff,
-                                                const ExactSmem *es, uint32_t parity, uint32_t gb, uint32_t comp, int s)
-{
-    const int16_t *blk = coef + (size_t)gb * 64u;
-    uint4 ch[8];
-    const bool drop_ac = parity && dcdiff[gb] == 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-        ch[k] = drop_ac ? make_uint4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uint4 *>(blk) + k);
-    const int dcv = dc[gb];
-    ch[0].x = (ch[0].x & 0xFFFF0000u) | ((uint32_t)dcv & 0xFFFFu);
-    const int x = s >> 3, y = s & 7;
-    double cx[8], cy[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        cx[k] = es->cosd[x][k];
-        cy[k] = es->cosd[y][k];
-    }
-    const float sum = exact_terms(ch, es->qint[comp], cx, cy, es->cc[0][0], es->cc[0][1], std::make_integer_sequence<int, 64>{});
-    const float out = (float)mul_f64(0.25, (double)sum);
-    return round_half_away(out);
-}
-
-// pixel (unshifted integer samples) -> packed bytes, fast path with exact fallback
-// eight strips per SM: 228 KB of shared memory, 1 KB of each CTA's share taken by the driver
-static_assert(sizeof(IdctSmem<3>) <= (233472 / 8 - 1024), "idct_kernel<3> no longer fits eight CTAs per SM");
-
-template <int NC>
-__device__ __forceinline__ uint32_t colour_px(float y, float cb, float cr)
-{
-    if (NC == 1) {
-        const int v = float_bits(y + (RINT_MAGIC + 128.0f)) - RINT_MAGIC_BITS;
-        return (uint32_t)clamp_u8(v);
-    }
-    int R, G, B;
-    if (!ycc_to_rgb_fast(y, cb, cr, R, G, B))
-        return colour_exact_px(y, cb, cr);
-    return (uint32_t)clamp_u8(R) | ((uint32_t)clamp_u8(G) << 8) | ((uint32_t)clamp_u8(B) << 16);
-}
-
-// Tie record: x = pixel index (image-major, row-major), y = global MCU index,
-// z = sample index in the block | mask of flagged components << 8, w = fast Y | fast Cb << 16 (int16),
-// and the fast Cr sample travels in the upper half of z.
-__device__ __forceinline__ uint4 make_tie_record(uint32_t pix, uint32_t mcu, int s, uint32_t mask, float y, float cb, float cr)
-{
-    uint4 r;
-    r.x = pix;
-    r.y = mcu;
-    r.z = (uint32_t)s | (mask << 8) | ((uint32_t)(uint16_t)(int)cr << 16);
-    r.w = (uint32_t)(uint16_t)(int)y | ((uint32_t)(uint16_t)(int)cb << 16);
-    return r;
-}
-
-template <int NC>
-__device__ __forceinline__ void resolve_and_store_pixel(const ExactCtx &a, const ExactSmem *es, const uint4 &r)
-{
-    const uint32_t mcu = r.y;
-    uint32_t mask = (r.z >> 8) & 7u;
-    const int s = (int)(r.z & 63u);
-    float v0 = (float)(short)(r.w & 0xFFFFu), v1 = (float)(short)(r.w >> 16), v2 = (float)(short)(r.z >> 16);
-    // lanes flag different components: one call site, lane-varying component, so the warp makes one
-    // pass per *number* of flagged components (almost always 1), not one per component
-    while (mask) {
-        const int c = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const float e = (float)exact_sample_global(a.coef, a.dc, a.dcdiff, es, a.parity, mcu * NC + c, (uint32_t)c, s);
-        v0 = c == 0 ? e : v0;
-        v1 = c == 1 ? e : v1;
-        v2 = c == 2 ? e : v2;
-    }
-    const uint32_t px = colour_px<NC>(v0, v1, v2);
-    uint8_t *dst = a.pixels + (size_t)r.x * NC;
-    dst[0] = (uint8_t)px;
-    if (NC == 3) {
-        dst[1] = (uint8_t)(px >> 8);
-        dst[2] = (uint8_t)(px >> 16);
-    }
-}
-
-// ---- stage 0 by the copy engine (TMA) ------------------------------------------------------------------
-// One elected thread asks for the strip's coefficients as a 2-D tile of the coefficient matrix [blocks][64] through a
-// tensor map with the 128-byte swizzle -- 16-byte chunk k of block b lands at chunk (k ^ (b & 7)), which is the
-// bank-conflict-free layout stage 1 reads -- and for the two quantiser tables as plain bulk copies.  No thread spends
-// an instruction on addresses, loads or stores; rows past the end of the matrix arrive as zeros.
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile("{\n"
-                 ".reg .pred p;\n"
-                 "KPEG_MBAR_WAIT:\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-                 "@p bra KPEG_MBAR_DONE;\n"
-                 "bra KPEG_MBAR_WAIT;\n"
-                 "KPEG_MBAR_DONE:\n"
-                 "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_tile_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_tile_2d(const CUtensorMap *map, int c0, int c1)
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-// Colour of the eight pixels of one row of an MCU -> 24 unclamped channel values, three variants chosen per MCU:
-//   COLOUR_PLAIN    ycc_to_rgb_fast's arithmetic on pixel pairs (FFMA2 / FADD2); its range precondition holds for
-//                   the whole MCU (no block is BLK_WIDE) and its flat-chroma special case cannot occur unnoticed
-//                   (a pixel with Cb = Cr = 0 fails the G test and takes the exact expression, which is right too)
-//   COLOUR_FLAT     both chroma blocks are all-zero (gray-as-YCbCr content): R = G = B = Y + 128
-//   COLOUR_GENERAL  ycc_to_rgb_fast itself, pixel by pixel, with its range and flat tests
-enum { COLOUR_PLAIN = 0, COLOUR_FLAT = 1, COLOUR_GENERAL = 2 };
-
-// bits 0..23 = R, G, B; bit 24 set when the double expression was needed
-__device__ __noinline__ uint32_t colour_px_general(float y, float cb, float cr)
-{
-    int R, G, B;
-    if (!ycc_to_rgb_fast(y, cb, cr, R, G, B))
-        return colour_exact_px(y, cb, cr) | (1u << 24);
-    return (uint32_t)clamp_u8(R) | ((uint32_t)clamp_u8(G) << 8) | ((uint32_t)clamp_u8(B) << 16);
-}
-
-// -> the row's 24 bytes as six words; returns the number of pixels that took the double expression.
-// redo (COLOUR_PLAIN only): bit j set = pixel j of the row must be replaced by colour_exact_px.
-template <int MODE>
-__device__ __forceinline__ uint32_t colour_row8(const float4 (&yy)[2], const float4 (&bb)[2], const float4 (&cc)[2],
-                                                uint32_t (&out)[6], uint32_t &redo)
-{
-    uint32_t exact = 0;
-    if constexpr (MODE == COLOUR_GENERAL) {
-        const float Y[8] = {yy[0].x, yy[0].y, yy[0].z, yy[0].w, yy[1].x, yy[1].y, yy[1].z, yy[1].w};
-        const float Cb[8] = {bb[0].x, bb[0].y, bb[0].z, bb[0].w, bb[1].x, bb[1].y, bb[1].z, bb[1].w};
-        const float Cr[8] = {cc[0].x, cc[0].y, cc[0].z, cc[0].w, cc[1].x, cc[1].y, cc[1].z, cc[1].w};
-        uint32_t p[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            p[j] = colour_px_general(Y[j], Cb[j], Cr[j]);
-            exact += p[j] >> 24;
-            p[j] &= 0xFFFFFFu;
-        }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            out[3 * q + 0] = p[4 * q] | (p[4 * q + 1] << 24);
-            out[3 * q + 1] = (p[4 * q + 1] >> 8) | (p[4 * q + 2] << 16);
-            out[3 * q + 2] = (p[4 * q + 2] >> 16) | (p[4 * q + 3] << 8);
-        }
-        return exact;
-    }
-    int px[24];
-    if constexpr (MODE == COLOUR_FLAT) {
-        const float Y[8] = {yy[0].x, yy[0].y, yy[0].z, yy[0].w, yy[1].x, yy[1].y, yy[1].z, yy[1].w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            px[3 * j] = px[3 * j + 1] = px[3 * j + 2] = float_bits(Y[j] + (RINT_MAGIC + 128.0f)) - RINT_MAGIC_BITS;
-    } else {
-        const F2 magic = splat2(RINT_MAGIC);
-        const F2 tiny = splat2(__int_as_float(1)); // 2^-149
-        F2 dg[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float4 &y4 = yy[k >> 1], &b4 = bb[k >> 1], &c4 = cc[k >> 1];
-            const F2 y = (k & 1) ? pack2(y4.z, y4.w) : pack2(y4.x, y4.y);
-            const F2 cb = (k & 1) ? pack2(b4.z, b4.w) : pack2(b4.x, b4.y);
-            const F2 cr = (k & 1) ? pack2(c4.z, c4.w) : pack2(c4.x, c4.y);
-            // ycc_to_rgb_fast (idct_core.h), two pixels per instruction
-            const F2 yr = lane_add(y, splat2(127.501f));
-            const F2 yg = lane_add(y, splat2(127.5f));
-            const F2 r = lane_fma_k(cr, 1.402f, yr);
-            const F2 b = lane_fma_k(cb, 1.772f, yr);
-            const F2 g = lane_fma_k(cr, -0.714136f, lane_fma_k(cb, -0.344136f, yg));
-            dg[k] = lane_sub(g, lane_sub(lane_add(g, magic), magic));
-            // rint() to an integer WITHOUT the magic-number bias: v * 2^-149 is a denormal whose bit pattern is
-            // rint(v) itself (round to nearest even, like the magic add) when v >= 0, and has the sign bit set -- a
-            // large negative int -- when v < 0, which the saturating pack turns into 0 just as it would -|v|.
-            const F2 ri = lane_mul(r, tiny), gi = lane_mul(g, tiny), bi = lane_mul(b, tiny);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j = 2 * k + h;
-                px[3 * j] = float_bits(h ? hi2(ri) : lo2(ri));
-                px[3 * j + 1] = float_bits(h ? hi2(gi) : lo2(gi));
-                px[3 * j + 2] = float_bits(h ? hi2(bi) : lo2(bi));
-            }
-        }
-        // G within COLOUR_G_BAND of an integer somewhere in the row (0.2 % of the pixels): ONE test per row on the
-        // largest |dg|; the caller replaces the listed pixels by the double expression after the row is stored
-        float worst = fmaxf(fabsf(lo2(dg[0])), fabsf(hi2(dg[0])));
-#pragma unroll
-        for (int k = 1; k < 4; ++k)
-            worst = fmaxf(worst, fmaxf(fabsf(lo2(dg[k])), fabsf(hi2(dg[k]))));
-        if (!(worst < 0.5f - COLOUR_G_BAND)) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (!(fabsf((j & 1) ? hi2(dg[j >> 1]) : lo2(dg[j >> 1])) < 0.5f - COLOUR_G_BAND))
-                    redo |= 1u << j;
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
-        out[k] = pack4_sat(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
-    return exact;
-}
-
-template <int NC>
-__global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MIN_CTAS : 16)
-    idct_kernel(IdctArgs a, const __grid_constant__ CUtensorMap coef_map)
-{
-    constexpr int NM = IDCT_MCUS_PER_CTA;
-    constexpr int NB = NM * NC;
-    extern __shared__ __align__(1024) unsigned char smem_raw[]; // the swizzled tile needs 1024-byte alignment
-    IdctSmem<NC> &sm = *reinterpret_cast<IdctSmem<NC> *>(smem_raw);
-
-    const int t = threadIdx.x;
-    const int comp = t / NM; // warp-uniform
-    const int ml = t % NM;
-    const int bl = ml * NC + comp; // block index inside the CTA's strip (MCU-interleaved)
-    const uint32_t total_mcus = a.g.nimages * a.g.mcus_per_image;
-    const uint32_t mcu0 = blockIdx.x * NM;
-    const uint32_t m = mcu0 + ml;
-    const uint32_t blk0 = mcu0 * NC;
-
-    // ---- stage 0: quantisers + coefficients -> shared memory, by the copy engine -----------------------
-    const uint32_t bar = smem_u32(&sm.mbar);
-    if (t == 0) {
-        constexpr uint32_t tile_bytes = NB * 128u, table_bytes = NC * 64u * 4u;
-        mbar_init(bar, 1);
-        mbar_expect_tx(bar, tile_bytes + 2u * table_bytes);
-        tma_load_tile_2d(smem_u32(sm.coef), &coef_map, 0, (int)blk0, bar);
-        bulk_load(smem_u32(sm.qpair), a.tables->qpair, table_bytes, bar);
-        bulk_load(smem_u32(sm.qdc), a.tables->qdc, table_bytes, bar);
-        // the strip that will run in this CTA's slot next (CTAs are dispatched in index order): pull it into L2 now
-        if (blk0 + IDCT_PREFETCH_AHEAD * NB < a.g.total_blocks)
-            tma_prefetch_tile_2d(&coef_map, 0, (int)(blk0 + IDCT_PREFETCH_AHEAD * NB));
-        sm.nrec = 0;
-        const uint32_t img = mcu0 / a.g.mcus_per_image, mi = mcu0 - img * a.g.mcus_per_image;
-        sm.img0 = img;
-        sm.by0 = mi / a.g.mcus_x;
-        sm.bx0 = mi - sm.by0 * a.g.mcus_x;
-    }
-    // the block's DC value (from K2) and its DC difference: requested now, needed in stage 1
-    int dcv = 0;
-    bool drop_ac = false;
-    if (m < total_mcus) {
-        dcv = a.dc[blk0 + bl];
-        drop_ac = (a.g.flags & 1u) && a.dcdiff[blk0 + bl] == 0; // MCU.cpp:97-104
-    }
-    // One thread waits for the copy engine (its wait acquires the tile), the CTA barrier hands the data on: the other
-    // warps sleep at the barrier instead of polling, and the barrier object never needs to be visible to them.
-    if (t == 0)
-        mbar_wait(bar, 0);
-    __syncthreads();
-
-    // ---- stage 1: one thread = one 8x8 block ------------------------------------------------------
-    uint4 ch[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-        ch[k] = sm.coef[bl * 8 + (k ^ (bl & 7))];
-    __syncthreads(); // everyone holds its block in registers: `samp` may now overwrite `coef`
-    if (m < total_mcus) {
-        // the entropy stage leaves slot 0 empty; the integrated DC value comes from K2
-        ch[0].x = (ch[0].x & 0xFFFF0000u) | ((uint32_t)dcv & 0xFFFFu);
-
-        F2 P[32];
-        const float A = dequant_dezigzag(ch, drop_ac ? sm.qdc[comp] : sm.qpair[comp], P, std::make_integer_sequence<int, 32>{});
-        const float thresh = 0.5f - tie_band(A);
-        idct_rows_packed(P);
-
-        // (x + 1.5*2^23) - 1.5*2^23 == rint(x) for |x| < 2^22.  A sample is inside the tie band when its distance d
-        // from the rounded value exceeds thresh, i.e. when d*d - thresh^2 >= 0: one FFMA2 per sample pair, and the
-        // complement of the sign bit is shifted into the block's mask with one funnel shift per sample (no compares,
-        // no predicates).  thresh^2 is taken a hair low, so the packed test can only flag more than |d| > thresh does.
-        // Bit layout of the masks: tie_bit(row, col) below.
-        const float t2 = thresh > 0.0f ? thresh * thresh * (1.0f - 1.0f / 2097152.0f) : 0.0f;
-        const F2 neg_t2 = splat2(-t2);
-        const F2 magic = splat2(RINT_MAGIC);
-        uint32_t keep[2][2]; // [half][word]: sign bits = "outside the band", 16 per half and word
-        auto half_block = [&](auto HALF) { // columns 4 half .. 4 half + 3 of all eight rows
-            constexpr int half = decltype(HALF)::value;
-            float v[4][8]; // [column - 4 half][row]
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                idct8_column(P[0 * 8 + 4 * half + c], P[1 * 8 + 4 * half + c], P[2 * 8 + 4 * half + c], P[3 * 8 + 4 * half + c], v[c]);
-            uint32_t kl = 0, kh = 0;
-#pragma unroll
-            for (int row = 0; row < 8; ++row) {
-                float r[4];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const F2 x = pack2(v[2 * k][row], v[2 * k + 1][row]);
-                    const F2 rr = lane_sub(lane_add(x, magic), magic);
-                    const F2 d = lane_sub(x, rr);
-                    const F2 e = lane_fma(d, d, neg_t2);
-                    unpack2(rr, r[2 * k], r[2 * k + 1]);
-                    if (row < 4) {
-                        kl = __funnelshift_l((uint32_t)float_bits(lo2(e)), kl, 1);
-                        kl = __funnelshift_l((uint32_t)float_bits(hi2(e)), kl, 1);
-                    } else {
-                        kh = __funnelshift_l((uint32_t)float_bits(lo2(e)), kh, 1);
-                        kh = __funnelshift_l((uint32_t)float_bits(hi2(e)), kh, 1);
-                    }
-                }
-                sm.samp[((comp * 8 + row) * 2 + half) * NM + ml] = make_float4(r[0], r[1], r[2], r[3]);
-            }
-            keep[half][0] = kl;
-            keep[half][1] = kh;
-        };
-        half_block(std::integral_constant<int, 0>{});
-        half_block(std::integral_constant<int, 1>{});
-        // 16 bits per (half, word), first sample shifted in ends up highest: bit 15 - (4 (row & 3) + (col & 3))
-        sm.tie[bl] = make_uint2(~((keep[0][0] << 16) | (keep[1][0] & 0xFFFFu)), ~((keep[0][1] << 16) | (keep[1][1] & 0xFFFFu)));
-        sm.flag[bl] = (uint8_t)((A != 0.0f ? BLK_NONZERO : 0u) | (A > COLOUR_SAFE_A ? BLK_WIDE : 0u));
-    }
-    __syncthreads();
-
-    // ---- stage 2: colour conversion + interleaved store -------------------------------------------
-    if (m < total_mcus) {
-        uint32_t img = sm.img0, by = sm.by0, bx = sm.bx0 + (uint32_t)ml;
-        if (a.g.mcus_x >= (uint32_t)NM) { // the strip wraps at most once
-            if (bx >= a.g.mcus_x) {
-                bx -= a.g.mcus_x;
-                if (++by == a.g.mcus_y) {
-                    by = 0;
-                    ++img;
-                }
-            }
-        } else { // images narrower than a strip
-            img = m / a.g.mcus_per_image;
-            const uint32_t mi = m - img * a.g.mcus_per_image;
-            by = mi / a.g.mcus_x;
-            bx = mi - by * a.g.mcus_x;
-        }
-        const uint32_t W = a.g.width, H = a.g.height;
-        const uint32_t img_pix0 = img * W * H;
-        uint8_t *img_base = a.pixels + (size_t)img_pix0 * NC;
-        const bool full_w = bx * 8u + 8u <= W;
-        const bool vec_ok = full_w && (W % 8u == 0u) && ((reinterpret_cast<uintptr_t>(a.pixels) & 7u) == 0);
-        uint32_t colour_exact = 0;
-        bool overflow = false;
-        uint2 tmask[NC];
-#pragma unroll
-        for (int c = 0; c < NC; ++c)
-            tmask[c] = sm.tie[ml * NC + c];
-        int mode = COLOUR_PLAIN;
-        if constexpr (NC == 3) {
-            const uint32_t f0 = sm.flag[ml * NC], f1 = sm.flag[ml * NC + 1], f2 = sm.flag[ml * NC + 2];
-            mode = ((f0 | f1 | f2) & BLK_WIDE) ? COLOUR_GENERAL : (((f1 | f2) & BLK_NONZERO) ? COLOUR_PLAIN : COLOUR_FLAT);
-        }
-        for (int row = comp; row < 8; row += NC) { // the NC warps of the CTA share the 8 pixel rows
-            const uint32_t y = by * 8u + row;
-            if (y >= H)
-                continue;
-            const float4 y0 = sm.samp[((0 * 8 + row) * 2 + 0) * NM + ml];
-            const float4 y1 = sm.samp[((0 * 8 + row) * 2 + 1) * NM + ml];
-            uint32_t out[2 * NC];
-            uint32_t redo = 0;
-            if constexpr (NC == 3) {
-                const float4 yy[2] = {y0, y1};
-                const float4 bb[2] = {sm.samp[((1 * 8 + row) * 2 + 0) * NM + ml], sm.samp[((1 * 8 + row) * 2 + 1) * NM + ml]};
-                const float4 cc[2] = {sm.samp[((2 * 8 + row) * 2 + 0) * NM + ml], sm.samp[((2 * 8 + row) * 2 + 1) * NM + ml]};
-                uint32_t o6[6];
-                if (mode == COLOUR_PLAIN)
-                    colour_exact += colour_row8<COLOUR_PLAIN>(yy, bb, cc, o6, redo);
-                else if (mode == COLOUR_FLAT)
-                    colour_exact += colour_row8<COLOUR_FLAT>(yy, bb, cc, o6, redo);
-                else
-                    colour_exact += colour_row8<COLOUR_GENERAL>(yy, bb, cc, o6, redo);
-#pragma unroll
-                for (int k = 0; k < 6; ++k)
-                    out[k] = o6[k];
-            } else {
-                // gray: the reference's colour path with Cb = Cr = 128 gives R = G = B = clamp(Y)
-                const float Y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-                int v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    v[j] = float_bits(Y[j] + (RINT_MAGIC + 128.0f)) - RINT_MAGIC_BITS; // integer-valued: exact
-                out[0] = pack4_sat(v[0], v[1], v[2], v[3]);
-                out[1] = pack4_sat(v[4], v[5], v[6], v[7]);
-            }
-            uint8_t *dst = img_base + ((size_t)y * W + bx * 8u) * NC;
-            if (vec_ok) {
-#pragma unroll
-                for (int k = 0; k < NC; ++k)
-                    reinterpret_cast<uint2 *>(dst)[k] = make_uint2(out[2 * k], out[2 * k + 1]);
-            } else {
-                const uint32_t nbytes = (full_w ? 8u : W - bx * 8u) * NC;
-#pragma unroll
-                for (int j = 0; j < 8 * NC; ++j) // compile-time indices: `out` stays in registers
-                    if ((uint32_t)j < nbytes)
-                        dst[j] = (uint8_t)(out[j >> 2] >> (8 * (j & 3)));
-            }
-            while (redo) { // rare: this thread's own later byte stores replace what it has just written
-                const int j = __ffs(redo) - 1;
-                redo &= redo - 1;
-                if (bx * 8u + (uint32_t)j >= W)
-                    continue;
-                const float *sp = reinterpret_cast<const float *>(sm.samp);
-                const uint32_t e = colour_exact_px(sp[(((0 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)],
-                                                   sp[(((1 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)],
-                                                   sp[((((NC - 1) * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)]);
-                dst[3 * j] = (uint8_t)e;
-                dst[3 * j + 1] = (uint8_t)(e >> 8);
-                dst[3 * j + 2] = (uint8_t)(e >> 16);
-                ++colour_exact;
-            }
-        }
-        // pixels with a sample inside the tie band, in the rows this thread converted: queue them for the exact
-        // pass.  One pass over the set bits of the MCU's combined mask after the row loop (most MCUs have none).
-        uint32_t plo = 0, phi = 0;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            plo |= tmask[c].x;
-            phi |= tmask[c].y;
-        }
-        if (NC == 3) { // rows comp, comp + 3, comp + 6
-            plo &= comp == 0 ? (tie_row_bits(0) | tie_row_bits(3)) : (comp == 1 ? tie_row_bits(1) : tie_row_bits(2));
-            phi &= comp == 0 ? tie_row_bits(6) : (comp == 1 ? (tie_row_bits(4) | tie_row_bits(7)) : tie_row_bits(5));
-        }
-        while (plo | phi) {
-            int w, b;
-            if (plo) {
-                w = 0;
-                b = __ffs(plo) - 1;
-                plo &= plo - 1;
-            } else {
-                w = 1;
-                b = __ffs(phi) - 1;
-                phi &= phi - 1;
-            }
-            const int s = tie_sample(w, b);
-            const int row = s >> 3, j = s & 7;
-            if (by * 8u + (uint32_t)row >= H || bx * 8u + (uint32_t)j >= W)
-                continue;
-            uint32_t cm = 0;
-#pragma unroll
-            for (int c = 0; c < NC; ++c)
-                cm |= (((w ? tmask[c].y : tmask[c].x) >> b) & 1u) << c;
-            // fast samples of this pixel, re-read from shared memory
-            const float *sp = reinterpret_cast<const float *>(sm.samp);
-            float fy, fcb = 0.0f, fcr = 0.0f;
-            fy = sp[(((0 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
-            if (NC == 3) {
-                fcb = sp[(((1 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
-                fcr = sp[((((NC - 1) * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
-            }
-            // compact strip-local form: x = mcu in strip | sample << 5 | components << 11 | fast Cr << 16,
-            // y = fast Y | fast Cb << 16; expanded to the global record when the strip's list is flushed
-            const uint2 rec = make_uint2((uint32_t)ml | ((uint32_t)s << 5) | (cm << 11) | ((uint32_t)(uint16_t)(int)fcr << 16),
-                                         (uint32_t)(uint16_t)(int)fy | ((uint32_t)(uint16_t)(int)fcb << 16));
-            const uint32_t at = atomicAdd(&sm.nrec, 1u); // shared-memory counter: no global atomic unless the strip outgrows its own slots
-            if (at < (uint32_t)IDCT_REC_CAP)
-                sm.rec[at] = rec;
-            else
-                overflow = true; // more tied pixels than a strip's list holds: the strip is redone wholesale
-        }
-        if (colour_exact)
-            atomicAdd(&a.meta->colour_exact, colour_exact);
-        if (overflow)
-            a.overflow_mcu[blockIdx.x] = 1u; // this strip has pixels that did not fit the record list
-    }
-    // ---- flush the strip's tie records --------------------------------------------------------------
-    // Strip i owns slots [i * IDCT_REC_FIXED, (i + 1) * IDCT_REC_FIXED) of the global list and always writes all of
-    // them (unused ones as TIE_EMPTY): the common case needs no reservation, so no CTA ends on the round trip of a
-    // global atomic.  Records beyond the strip's own slots (rare) go to the shared tail of the list.
-    __syncthreads();
-    const uint32_t found = sm.nrec, nrec = min(found, (uint32_t)IDCT_REC_CAP);
-    auto global_record = [&](uint32_t i) {
-        const uint2 c = sm.rec[i];
-        const uint32_t rm = mcu0 + (c.x & 31u), rs = (c.x >> 5) & 63u;
-        // position of the record's MCU from the strip's origin (as in stage 2: no division when the strip wraps at most once)
-        uint32_t img = sm.img0, by = sm.by0, bx = sm.bx0 + (c.x & 31u);
-        if (a.g.mcus_x >= (uint32_t)NM) {
-            if (bx >= a.g.mcus_x) {
-                bx -= a.g.mcus_x;
-                if (++by == a.g.mcus_y) {
-                    by = 0;
-                    ++img;
-                }
-            }
-        } else {
-            img = rm / a.g.mcus_per_image;
-            const uint32_t mi = rm - img * a.g.mcus_per_image;
-            by = mi / a.g.mcus_x;
-            bx = mi - by * a.g.mcus_x;
-        }
-        uint4 r; // the record format of make_tie_record
-        r.x = img * a.g.width * a.g.height + (by * 8u + (rs >> 3)) * a.g.width + bx * 8u + (rs & 7u);
-        r.y = rm;
-        r.z = rs | (((c.x >> 11) & 7u) << 8) | (c.x & 0xFFFF0000u);
-        r.w = c.y;
-        return r;
-    };
-    if (t < IDCT_REC_FIXED)
-        a.tie_rec[(size_t)blockIdx.x * IDCT_REC_FIXED + t] = (uint32_t)t < nrec ? global_record(t) : make_uint4(TIE_EMPTY, 0, 0, 0);
-    if (found <= (uint32_t)IDCT_REC_FIXED) {
-        if (t == 0 && found)
-            atomicAdd(&a.meta->exact_samples, found); // statistics only: nobody waits for it
-        return;
-    }
-    if (t == 0) {
-        sm.rec_base = atomicAdd(&a.meta->tie_records, nrec - (uint32_t)IDCT_REC_FIXED);
-        atomicAdd(&a.meta->exact_samples, (uint32_t)IDCT_REC_FIXED);
-        if (found > (uint32_t)IDCT_REC_CAP)
-            atomicAdd(&a.meta->tie_inline, found - (uint32_t)IDCT_REC_CAP);
-    }
-    __syncthreads();
-    const uint32_t base = gridDim.x * (uint32_t)IDCT_REC_FIXED + sm.rec_base; // the tail starts after every strip's own slots
-    for (uint32_t i = IDCT_REC_FIXED + t; i < nrec; i += NB) {
-        const uint32_t at = base + (i - IDCT_REC_FIXED);
-        if (at < a.tie_cap) {
-            a.tie_rec[at] = global_record(i);
-        } else {
-            a.overflow_mcu[blockIdx.x] = 1u; // global list full
-            atomicAdd(&a.meta->tie_inline, 1u);
-        }
-    }
-}
-
-// The record list: strips * IDCT_REC_FIXED slots owned by the strips (sparse: unused slots are TIE_EMPTY) followed by
-// a compact tail of meta->tie_records entries.  A warp walks its share of the sparse part 32 slots at a time,
-// collects the used ones in a small shared-memory stack and resolves them 32 at a time, so the long serial
-// evaluation always runs with full warps.
-template <int NC>
-__global__ void __launch_bounds__(128) idct_patch_kernel(IdctArgs a)
-{
-    __shared__ ExactSmem es;
-    __shared__ uint4 s_q[4][64];
-    exact_smem_load(es, a.tables);
-    const ExactCtx x = exact_ctx(a);
-    const uint32_t total_mcus_ = a.g.nimages * a.g.mcus_per_image;
-    const uint32_t nslots = ((total_mcus_ + IDCT_MCUS_PER_CTA - 1) / IDCT_MCUS_PER_CTA) * (uint32_t)IDCT_REC_FIXED;
-    {
-        const uint32_t lane = threadIdx.x & 31u, wl = threadIdx.x >> 5;
-        const uint32_t nwarps = gridDim.x * 4u, w = blockIdx.x * 4u + wl;
-        const uint32_t per = (((nslots + nwarps - 1u) / nwarps) + 31u) & ~31u;
-        const uint32_t s0 = w * per, s1 = min(s0 + per, nslots);
-        uint32_t qn = 0; // warp-uniform
-        for (uint32_t sl = s0; sl < s1; sl += 32u) {
-            uint4 r = make_uint4(TIE_EMPTY, 0, 0, 0);
-            if (sl + lane < s1)
-                r = a.tie_rec[sl + lane];
-            const bool used = r.x != TIE_EMPTY;
-            const uint32_t bal = __ballot_sync(0xffffffffu, used);
-            if (used)
-                s_q[wl][qn + __popc(bal & ((1u << lane) - 1u))] = r;
-            qn += __popc(bal);
-            __syncwarp();
-            if (qn >= 32u) {
-                r = s_q[wl][qn - 32u + lane];
-                __syncwarp();
-                qn -= 32u;
-                resolve_and_store_pixel<NC>(x, &es, r);
-                __syncwarp();
-            }
-        }
-        if (lane < qn)
-            resolve_and_store_pixel<NC>(x, &es, s_q[wl][lane]);
-    }
-    const uint32_t n = a.tie_cap > nslots ? min(a.meta->tie_records, a.tie_cap - nslots) : 0u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        resolve_and_store_pixel<NC>(x, &es, a.tie_rec[nslots + i]);
-    // Overflow (pathologically flat images: more tied pixels than the record list holds).  Strips that
-    // reported an overflow are redone wholesale on the exact path: every sample of every pixel.
-    if (a.meta->tie_inline == 0u)
-        return;
-    const uint32_t total_mcus = a.g.nimages * a.g.mcus_per_image;
-    const uint32_t nstrips = (total_mcus + IDCT_MCUS_PER_CTA - 1) / IDCT_MCUS_PER_CTA;
-    const uint32_t W = a.g.width, H = a.g.height;
-    for (uint32_t strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
-        if (a.overflow_mcu[strip] == 0u)
-            continue;
-        for (uint32_t w = threadIdx.x; w < IDCT_MCUS_PER_CTA * 64u; w += blockDim.x) {
-            const uint32_t m = strip * IDCT_MCUS_PER_CTA + (w >> 6);
-            const int s = (int)(w & 63u);
-            if (m >= total_mcus)
-                continue;
-            const uint32_t img = m / a.g.mcus_per_image, mi = m - img * a.g.mcus_per_image;
-            const uint32_t by = mi / a.g.mcus_x, bx = mi - by * a.g.mcus_x;
-            const uint32_t px_x = bx * 8u + (uint32_t)(s & 7), px_y = by * 8u + (uint32_t)(s >> 3);
-            if (px_x >= W || px_y >= H)
-                continue;
-            uint4 rec;
-            rec.x = img * W * H + px_y * W + px_x;
-            rec.y = m;
-            rec.z = (uint32_t)s | ((NC == 3 ? 7u : 1u) << 8);
-            rec.w = 0;
-            resolve_and_store_pixel<NC>(x, &es, rec);
-        }
-    }
-}
-
-static uint32_t g_patch_grid = 148 * 4;
 
 void kernels_configure(int max_concurrent_jobs)
 {
@@ -2416,14 +1210,6 @@ void kernels_configure(int max_concurrent_jobs)
                                                           k1_write_smem_bytes(512)) != cudaSuccess || per_sm < 1)
             per_sm = 3;
         g_k1_write_grid_cap = (uint32_t)(sms * per_sm);
-        cudaFuncSetAttribute(entropy_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WriteSmemTail));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entropy_expand_kernel, WRITE_THREADS,
-                                                          sizeof(WriteSmemTail)) != cudaSuccess || per_sm < 1)
-            per_sm = 6;
-        g_k1_expand_grid_cap = (uint32_t)(sms * per_sm);
-        g_patch_grid = (uint32_t)(sms * 4); // warps take contiguous shares of the record list: enough records each to fill whole batches
-        if (const char *e = getenv("KPEG_PATCH_PER_SM")) // experiments
-            g_patch_grid = (uint32_t)(sms * std::max(1, atoi(e)));
         cudaFuncSetAttribute(entropy_relay_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)k1_sparse_smem_bytes(1024));
         g_sm_count = (uint32_t)sms;
@@ -2432,89 +1218,7 @@ void kernels_configure(int max_concurrent_jobs)
         if (const char *e = getenv("KPEG_RELAY_SPIN_LIMIT")) // tests: 0 = give up at the first poll that finds a CTA missing
             g_relay_spin_limit = (uint32_t)strtoul(e, nullptr, 10);
     }
-    cudaFuncSetAttribute(idct_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<3>));
-    cudaFuncSetAttribute(idct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<1>));
-}
-
-// Tensor map of the coefficient matrix [total_blocks][64] of int16, tiles of `box_blocks` whole blocks, 128-byte
-// swizzle, zeros past the end.  Encoding is a host-side computation (no driver call reaches the device).
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn()
-{
-    static EncodeTiledFn fn = [] {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            p = nullptr;
-        return (EncodeTiledFn)p;
-    }();
-    return fn;
-}
-
-static bool make_coef_map(CUtensorMap *map, const int16_t *coef, uint32_t total_blocks, uint32_t box_blocks)
-{
-    const EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc)
-        return false;
-    const cuuint64_t dims[2] = {64, total_blocks};
-    const cuuint64_t strides[1] = {128}; // bytes between blocks
-    const cuuint32_t box[2] = {64, box_blocks};
-    const cuuint32_t estr[2] = {1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<int16_t *>(coef), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-cudaError_t launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches)
-{
-    const uint32_t total_mcus = a.g.nimages * a.g.mcus_per_image;
-    const uint32_t grid = (total_mcus + IDCT_MCUS_PER_CTA - 1) / IDCT_MCUS_PER_CTA;
-    alignas(64) CUtensorMap map;
-    if (!make_coef_map(&map, a.coef, a.g.total_blocks, a.g.ncomp * IDCT_MCUS_PER_CTA))
-        return cudaErrorNotSupported; // no cuTensorMapEncodeTiled in this driver, or it rejected the geometry
-    if (a.g.ncomp == 3)
-        idct_kernel<3><<<grid, 3 * IDCT_MCUS_PER_CTA, sizeof(IdctSmem<3>), s>>>(a, map);
-    else
-        idct_kernel<1><<<grid, IDCT_MCUS_PER_CTA, sizeof(IdctSmem<1>), s>>>(a, map);
-    ++*launches;
-    return cudaSuccess;
-}
-
-void launch_idct_patch(const IdctArgs &a, cudaStream_t s, uint32_t *launches)
-{
-    if (a.g.ncomp == 3)
-        idct_patch_kernel<3><<<g_patch_grid, 128, 0, s>>>(a);
-    else
-        idct_patch_kernel<1><<<g_patch_grid, 128, 0, s>>>(a);
-    ++*launches;
-}
-
-// =================================================================================================
-// parity hook: coefficients with the DC value merged in and the F1 rule applied
-// =================================================================================================
-__global__ void merge_dc_kernel(int16_t *out, const int16_t *coef, const int16_t *dc, const int16_t *dcdiff,
-                                uint32_t nblocks, uint32_t flags)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nblocks * 64u)
-        return;
-    const uint32_t b = i >> 6, z = i & 63u;
-    int16_t v;
-    if (z == 0u)
-        v = dc[b];
-    else
-        v = ((flags & 1u) && dcdiff[b] == 0) ? (int16_t)0 : coef[i];
-    out[i] = v;
-}
-
-void launch_merge_dc(int16_t *coef_out, const int16_t *coef, const int16_t *dc, const int16_t *dcdiff, uint32_t nblocks,
-                     uint32_t flags, cudaStream_t s)
-{
-    const uint32_t n = nblocks * 64u;
-    merge_dc_kernel<<<(n + 255) / 256, 256, 0, s>>>(coef_out, coef, dc, dcdiff, nblocks, flags);
+    k3_configure();
 }
 
 } // namespace kpeg

@@ -22,11 +22,10 @@ struct DevMeta {
     uint32_t total_bits;   // 8 * total_kept
     uint32_t nsub;         // subsequences actually used
     uint32_t status;       // ST_* bits
-    uint32_t exact_samples; // tie records written to the strips' own slots of the list (statistics)
-    uint32_t colour_exact;
+    uint32_t exact_samples; // IDCT samples re-evaluated in the reference's operation order (statistics)
+    uint32_t colour_exact; // pixels whose colour took the double expression (statistics)
     uint32_t final_slot;   // absolute slot the last subsequence ended on
-    uint32_t tie_records;  // records in the shared tail of the tie list (beyond the strips' own slots)
-    uint32_t tie_inline;   // pixels resolved inside K3 because the record buffer was full
+    uint32_t reserved_[2];
     uint32_t relay_rounds; // last relay round that ran (device-side round loop)
     uint32_t grid_bar;     // arrival counter of the relay loop's grid barrier
     uint32_t rec_alt_count; // private record areas handed out by the sparse relay rounds
@@ -64,35 +63,34 @@ struct EntropyArgs {
     uint32_t *rec_alt;    // [rec_alt_cap][rec_kmax] private record areas of subsequences redone in sparse rounds
     uint32_t rec_alt_cap;
     uint32_t rec_kmax;
-    int16_t *coef;        // [total_blocks][64]
-    int16_t *dcdiff;      // [total_blocks]
+    int16_t *coef;        // [total_blocks][64]  (Huffman final pass only: records off)
+    int16_t *dcdiff;      // [total_blocks]      (Huffman final pass only)
+    uint32_t *strip_sub;  // [nstrips] subsequence in which the first slot of every K3 strip lies (written by the offset scan)
+    uint32_t strip_slots; // coefficient slots per strip
+    uint32_t nstrips;
     uint32_t nsub_max;
     JobGeom g;
 };
 
 constexpr int ENTROPY_THREADS = 128;
 
-struct DcArgs {
-    const int16_t *dcdiff;
-    int16_t *dc;
-    int32_t *tile_carry; // [ntiles][4]: per component running value at the end of the tile, [3] = "tile contains a reset"
-    uint32_t ntiles;
-    JobGeom g;
-};
-constexpr int DC_THREADS = 256;
-constexpr int DC_MCUS_PER_THREAD = 4;
-constexpr int DC_TILE = DC_THREADS * DC_MCUS_PER_THREAD;
-
+// K2 + K3 (k3_fused.cu).  The strip's coefficients come from the records (rec != nullptr: expansion inside the kernel)
+// or, in the fallback, from the coefficient matrix the Huffman final pass wrote (coef_in).
 struct IdctArgs {
-    const int16_t *coef;
-    const int16_t *dc;
-    const int16_t *dcdiff;
+    const uint32_t *rec;      // [group of 32 subsequences][rec_kmax][32]
+    const uint32_t *nrec;     // [nsub]
+    const uint32_t *rec_alt;  // private record areas (subsequences redone in sparse relay rounds)
+    uint32_t rec_kmax;
+    const uint32_t *start_slot; // [nsub]
+    const uint32_t *strip_sub;  // [nstrips]
+    const int16_t *coef_in;   // fallback input: [total_blocks][64], slot 0 = DC difference
+    int16_t *coef_out;        // optional: the strip's coefficients as the reference holds them (DC integrated, F1 applied)
+    unsigned long long *strip_state; // [nstrips] look-back words of the DC prediction
+    uint32_t lb_tag;          // tag of this launch in the look-back words (1 .. 2^14 - 1)
+    uint32_t lb_spin_limit;
     const DeviceTables *tables;
-    uint8_t *pixels; // [nimages][height][width][ncomp]
+    uint8_t *pixels;          // [nimages][height][width][ncomp]; nullptr with coef_out = coefficients only
     DevMeta *meta;
-    uint4 *tie_rec;       // [tie_cap] pixels with at least one sample inside the tie band: 16 slots per strip, then a shared tail
-    uint32_t tie_cap;
-    uint32_t *overflow_mcu; // [strips] set when a strip had tied pixels that did not fit tie_rec
     JobGeom g;
 };
 constexpr int IDCT_MCUS_PER_CTA = 32;
@@ -109,12 +107,9 @@ void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint3
 cudaError_t launch_entropy_relay_loop(const EntropyArgs &a, int first, int last, cudaStream_t s, uint32_t *launches);
 void launch_entropy_scan(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_entropy_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);  // Huffman final pass
-void launch_entropy_expand(const EntropyArgs &a, cudaStream_t s, uint32_t *launches); // record final pass
-void launch_dc_scan(const DcArgs &a, cudaStream_t s, uint32_t *launches);
-cudaError_t launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches); // fails without a tensor-map encoder in the driver
-void launch_idct_patch(const IdctArgs &a, cudaStream_t s, uint32_t *launches);
-void launch_merge_dc(int16_t *coef_out, const int16_t *coef, const int16_t *dc, const int16_t *dcdiff, uint32_t nblocks,
-                     uint32_t flags, cudaStream_t s);
+cudaError_t launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches);
+void k3_configure();                      // function attributes of the K3 kernels (called by kernels_configure)
+uint32_t k3_strip_slots(uint32_t ncomp);  // coefficient slots one K3 strip covers
 
 } // namespace kpeg
 #endif

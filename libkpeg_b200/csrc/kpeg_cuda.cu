@@ -59,7 +59,6 @@ struct Job {
     bool active = false;
     JobGeom g = {};
     EntropyArgs ea = {};
-    DcArgs da = {};
     IdctArgs ia = {};
     int rounds = 0;
     uint32_t launches = 0;
@@ -73,7 +72,8 @@ struct Job {
 struct Lane {
     cudaStream_t stream = nullptr;
     DevBuf scan, words, seg_bit, tile_kept, tile_rst, cls, state, work, seg_hint, start_slot, scan_tiles;
-    DevBuf coef, dcdiff, dc, tile_carry, pixels, meta, tie_rec, overflow, rec, nrec, rec_alt;
+    DevBuf coef, dcdiff, pixels, meta, rec, nrec, rec_alt, strip_sub, strip_state;
+    uint32_t lb_tag = 0; // tag of the last K3 launch in strip_state (the look-back words of another launch read as absent)
     PinBuf h_meta;
     cudaEvent_t ev[MAX_EVENTS] = {};
     int ev_stage[MAX_EVENTS] = {};
@@ -282,25 +282,40 @@ int status_to_rc(kpeg_ctx *ctx, uint32_t st)
     return KPEG_ERR_STREAM;
 }
 
+// K3's look-back words carry a 14-bit launch tag instead of being cleared per launch; clear them when the tag wraps
+int next_lb_tag(kpeg_ctx *ctx, Lane &L, uint32_t *tag)
+{
+    if (++L.lb_tag >= (1u << 14)) {
+        CK(cudaMemsetAsync(L.strip_state.p, 0, L.strip_state.cap, L.stream));
+        L.lb_tag = 1;
+    }
+    *tag = L.lb_tag;
+    return KPEG_OK;
+}
+
 // everything downstream of the relay + the result copies + the bookkeeping read-back
 int enqueue_downstream(kpeg_ctx *ctx, Lane &L)
 {
     Job &J = L.job;
     cudaStream_t s = L.stream;
-    // no zero-fill of coef / dcdiff: the final pass writes every slot of every block it owns
     launch_entropy_scan(J.ea, s, &J.launches);
     mark(ctx, L, KPEG_T_ENTROPY_SCAN);
-    if (J.use_records)
-        launch_entropy_expand(J.ea, s, &J.launches);
-    else
+    if (!J.use_records) {
+        // fallback: the Huffman final pass writes a coefficient matrix (every slot of every block: no zero-fill) and
+        // K3 takes its tiles from there
+        const size_t coef_bytes = (size_t)J.g.total_blocks * 128u;
+        TRY(ensure(ctx, s, L.coef, coef_bytes + 256));
+        TRY(ensure(ctx, s, L.dcdiff, (size_t)J.g.total_blocks * 2u + 16));
+        J.ea.coef = (int16_t *)L.coef.p;
+        J.ea.dcdiff = (int16_t *)L.dcdiff.p;
+        J.ia.rec = nullptr;
+        J.ia.coef_in = (const int16_t *)L.coef.p;
         launch_entropy_write(J.ea, s, &J.launches);
-    mark(ctx, L, KPEG_T_ENTROPY_WRITE);
-    launch_dc_scan(J.da, s, &J.launches);
-    mark(ctx, L, KPEG_T_DC_SCAN);
+        mark(ctx, L, KPEG_T_ENTROPY_WRITE);
+    }
+    TRY(next_lb_tag(ctx, L, &J.ia.lb_tag));
     CK(launch_idct(J.ia, s, &J.launches));
     mark(ctx, L, KPEG_T_IDCT);
-    launch_idct_patch(J.ia, s, &J.launches);
-    mark(ctx, L, KPEG_T_IDCT_PATCH);
     for (const Copy &c : J.d2h)
         CK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, s));
     if (!J.d2h.empty())
@@ -349,15 +364,8 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     const uint32_t ntiles = (S + 15u + UNSTUFF_TILE - 1) / UNSTUFF_TILE; // + 15: chunks are cut on address boundaries
     const uint32_t nsub_max = (uint32_t)(((uint64_t)S * 8u + g.sub_bits - 1u) / g.sub_bits) + 1u;
     const uint32_t total_mcus = g.nimages * g.mcus_per_image;
-    const uint32_t dc_tiles = (total_mcus + DC_TILE - 1) / DC_TILE;
+    const uint32_t nstrips = (total_mcus + IDCT_MCUS_PER_CTA - 1) / IDCT_MCUS_PER_CTA;
     const size_t words_bytes = ((size_t)S + 3u) / 4u * 4u + 64u;
-    const size_t coef_bytes = (size_t)g.total_blocks * 128u;
-    // tie records: room for 1/8 of all pixels (typical: ~1 %); beyond that strips are redone wholesale
-    const uint64_t npix_job = (uint64_t)g.nimages * g.width * g.height;
-    // (never less than the strips' own slots: a batch of very small images has more padded MCUs than pixels / 8)
-    const uint64_t nstrips_job = ((uint64_t)total_mcus + IDCT_MCUS_PER_CTA - 1) / IDCT_MCUS_PER_CTA;
-    const uint32_t tie_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(npix_job / 8u, nstrips_job * 16u) + 4096u, 1u << 27);
-    const size_t overflow_bytes = ((size_t)total_mcus / IDCT_MCUS_PER_CTA + 2u) * sizeof(uint32_t);
 
     TRY(ensure(ctx, s, L.words, words_bytes));
     TRY(ensure(ctx, s, L.seg_bit, ((size_t)g.nseg + 2u) * 4u));
@@ -369,17 +377,21 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     TRY(ensure(ctx, s, L.seg_hint, (size_t)nsub_max * 4u));
     TRY(ensure(ctx, s, L.start_slot, (size_t)nsub_max * 4u));
     TRY(ensure(ctx, s, L.scan_tiles, ((size_t)nsub_max / 1024u + 2u) * sizeof(uint2)));
-    TRY(ensure(ctx, s, L.coef, coef_bytes + 256));
-    TRY(ensure(ctx, s, L.dcdiff, (size_t)g.total_blocks * 2u + 16));
-    TRY(ensure(ctx, s, L.dc, (size_t)g.total_blocks * 2u + 16));
-    TRY(ensure(ctx, s, L.tile_carry, (size_t)dc_tiles * 16u));
-    TRY(ensure(ctx, s, L.tie_rec, (size_t)tie_cap * sizeof(uint4)));
-    TRY(ensure(ctx, s, L.overflow, overflow_bytes));
+    TRY(ensure(ctx, s, L.strip_sub, ((size_t)nstrips + 1u) * sizeof(uint32_t)));
+    {
+        const void *before = L.strip_state.p;
+        TRY(ensure(ctx, s, L.strip_state, ((size_t)nstrips + 1u) * sizeof(unsigned long long)));
+        if (L.strip_state.p != before) { // fresh memory: no word may look like one of a launch to come
+            CK(cudaMemsetAsync(L.strip_state.p, 0, L.strip_state.cap, s));
+            L.lb_tag = 0;
+        }
+    }
     TRY(ensure(ctx, s, L.meta, sizeof(DevMeta)));
     TRY(ensure_pinned(ctx, s, L.h_meta, sizeof(DevMeta)));
-    // symbol records: sub_bits / 2 per subsequence (every practical code is >= 2 bits; a stream that
-    // needs more flags ST_REC_OVERFLOW and is redone with the Huffman final pass)
-    const uint32_t rec_kmax = g.sub_bits / 2u;
+    // records: one per value-carrying symbol.  3/8 of the subsequence's bits covers every table whose value-carrying
+    // symbols take at least 3 bits (code >= 2 bits + value >= 1 bit: all of Annex K); a stream that needs more sets
+    // ST_REC_OVERFLOW and is redone with the Huffman final pass
+    const uint32_t rec_kmax = (g.sub_bits * 3u / 8u + 7u) & ~7u;
     const uint32_t rec_alt_cap = nsub_max / 4u + 1024u; // beyond it a redone subsequence rewrites its interleaved column
     if (ctx->use_records) {
         TRY(ensure(ctx, s, L.rec, (size_t)rec_kmax * ((size_t)nsub_max / 32u + 1u) * 32u * sizeof(uint32_t)));
@@ -396,7 +408,6 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     DevMeta *d_meta = (DevMeta *)L.meta.p;
 
     CK(cudaMemsetAsync(d_meta, 0, sizeof(DevMeta), s));
-    CK(cudaMemsetAsync(L.overflow.p, 0, overflow_bytes, s));
     mark(ctx, L, KPEG_T_MEMSET);
 
     UnstuffArgs ua;
@@ -429,28 +440,29 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     ea.rec_kmax = rec_kmax;
     ea.rec_alt = (uint32_t *)L.rec_alt.p;
     ea.rec_alt_cap = rec_alt_cap;
-    ea.coef = (int16_t *)L.coef.p;
-    ea.dcdiff = (int16_t *)L.dcdiff.p;
+    ea.coef = nullptr; // only the Huffman final pass writes coefficients to global memory (enqueue_downstream)
+    ea.dcdiff = nullptr;
+    ea.strip_sub = (uint32_t *)L.strip_sub.p;
+    ea.strip_slots = k3_strip_slots(g.ncomp);
+    ea.nstrips = nstrips;
     ea.nsub_max = nsub_max;
     ea.g = g;
 
-    DcArgs &da = J.da;
-    da.dcdiff = (const int16_t *)L.dcdiff.p;
-    da.dc = (int16_t *)L.dc.p;
-    da.tile_carry = (int32_t *)L.tile_carry.p;
-    da.ntiles = dc_tiles;
-    da.g = g;
-
     IdctArgs &ia = J.ia;
-    ia.coef = (const int16_t *)L.coef.p;
-    ia.dc = (const int16_t *)L.dc.p;
-    ia.dcdiff = (const int16_t *)L.dcdiff.p;
+    ia.rec = ea.rec;
+    ia.nrec = ea.nrec;
+    ia.rec_alt = ea.rec_alt;
+    ia.rec_kmax = rec_kmax;
+    ia.start_slot = ea.start_slot;
+    ia.strip_sub = ea.strip_sub;
+    ia.coef_in = nullptr;
+    ia.coef_out = nullptr;
+    ia.strip_state = (unsigned long long *)L.strip_state.p;
+    ia.lb_tag = 0;
+    ia.lb_spin_limit = 0;
     ia.tables = (const DeviceTables *)ctx->tables.p;
     ia.pixels = d_pixels;
     ia.meta = d_meta;
-    ia.tie_rec = (uint4 *)L.tie_rec.p;
-    ia.tie_cap = tie_cap;
-    ia.overflow_mcu = (uint32_t *)L.overflow.p;
     ia.g = g;
 
     launch_entropy_cold(ea, s, &J.launches);
@@ -484,8 +496,8 @@ int check_guards(kpeg_ctx *ctx, Lane &L)
     NamedBuf bufs[] = {{"cls", &L.cls},           {"scan", &L.scan},         {"words", &L.words},       {"seg_bit", &L.seg_bit},
                        {"tile_kept", &L.tile_kept}, {"tile_rst", &L.tile_rst}, {"state", &L.state},       {"work", &L.work},
                        {"seg_hint", &L.seg_hint}, {"start_slot", &L.start_slot}, {"scan_tiles", &L.scan_tiles},
-                       {"coef", &L.coef},         {"dcdiff", &L.dcdiff},     {"dc", &L.dc},             {"tile_carry", &L.tile_carry},
-                       {"pixels", &L.pixels},     {"meta", &L.meta},         {"tie_rec", &L.tie_rec},   {"overflow", &L.overflow},
+                       {"coef", &L.coef},         {"dcdiff", &L.dcdiff},     {"strip_sub", &L.strip_sub}, {"strip_state", &L.strip_state},
+                       {"pixels", &L.pixels},     {"meta", &L.meta},
                        {"rec", &L.rec},           {"nrec", &L.nrec},         {"rec_alt", &L.rec_alt},   {"tables", &ctx->tables}};
     uint8_t host[2 * GUARD_BYTES];
     for (const NamedBuf &nb : bufs) {
@@ -533,9 +545,6 @@ int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
             J.use_records = false;
             CK(cudaMemsetAsync(&d_meta->status, 0, sizeof(uint32_t), s));
             CK(cudaMemsetAsync(&d_meta->exact_samples, 0, 2 * sizeof(uint32_t), s));
-            CK(cudaMemsetAsync(&d_meta->tie_records, 0, 2 * sizeof(uint32_t), s));
-            CK(cudaMemsetAsync(L.overflow.p, 0,
-                               ((size_t)(J.g.nimages * J.g.mcus_per_image) / IDCT_MCUS_PER_CTA + 2u) * sizeof(uint32_t), s));
             TRY(enqueue_downstream(ctx, L));
             continue;
         }
@@ -564,9 +573,6 @@ int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
             return fail(ctx, KPEG_ERR_NOT_CONVERGED, "speculative decode did not reach a fixed point");
         CK(cudaMemsetAsync(&d_meta->status, 0, sizeof(uint32_t), s));
         CK(cudaMemsetAsync(&d_meta->exact_samples, 0, 2 * sizeof(uint32_t), s));
-        CK(cudaMemsetAsync(&d_meta->tie_records, 0, 2 * sizeof(uint32_t), s));
-        CK(cudaMemsetAsync(L.overflow.p, 0,
-                           ((size_t)(J.g.nimages * J.g.mcus_per_image) / IDCT_MCUS_PER_CTA + 2u) * sizeof(uint32_t), s));
         TRY(enqueue_downstream(ctx, L));
     }
     if (ctx->guard)
@@ -589,10 +595,12 @@ int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
                     used_rounds = (uint32_t)r;
         }
         stats->sync_rounds = std::max(stats->sync_rounds, used_rounds);
-        stats->exact_samples += h_meta->tie_records + h_meta->exact_samples; // pixels with at least one sample on the exact path (tail + strips' own slots)
+        stats->exact_samples += h_meta->exact_samples; // IDCT samples re-evaluated in the reference's operation order
         stats->kernel_launches += J.launches;
         add_times(ctx, L, stats);
     }
+    if (h_meta->status & ST_LOOKBACK_TIMEOUT)
+        return fail(ctx, KPEG_ERR_CUDA, "K3: a strip's DC look-back timed out (strips were not dispatched in order?)");
     return status_to_rc(ctx, h_meta->status & ~(ST_REC_OVERFLOW | ST_RELAY_TIMEOUT));
 }
 
@@ -695,7 +703,7 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
             cudaStreamSynchronize(L.stream);
         DevBuf *bufs[] = {&L.cls,  &L.scan, &L.words,    &L.seg_bit,    &L.tile_kept,  &L.tile_rst, &L.state,
                           &L.work, &L.seg_hint, &L.start_slot, &L.scan_tiles, &L.coef,     &L.dcdiff,
-                          &L.dc,   &L.tile_carry, &L.pixels,   &L.meta,       &L.tie_rec,  &L.overflow,
+                          &L.strip_sub, &L.strip_state, &L.pixels, &L.meta,
                           &L.rec,  &L.nrec,       &L.rec_alt};
         for (DevBuf *b : bufs)
             dev_free(*b);
@@ -1098,12 +1106,21 @@ extern "C" int kpeg_cuda_read_coefficients(kpeg_ctx *ctx, int16_t *out, size_t c
         return fail(ctx, KPEG_ERR_ARG, "no decode has run on this context");
     CK(cudaSetDevice(ctx->device));
     Lane &L = ctx->lane[ctx->last_lane];
+    if (L.job.active)
+        return fail(ctx, KPEG_ERR_ARG, "the lane of the last decode is busy with a deferred submission");
     const size_t n = (size_t)ctx->last_g.total_blocks * 64u;
     if (cap < n)
         return fail(ctx, KPEG_ERR_ARG, "coefficient buffer too small");
     TRY(ensure(ctx, L.stream, ctx->merged, n * 2u));
-    launch_merge_dc((int16_t *)ctx->merged.p, (const int16_t *)L.coef.p, (const int16_t *)L.dc.p,
-                    (const int16_t *)L.dcdiff.p, ctx->last_g.total_blocks, ctx->last_g.flags, L.stream);
+    // The coefficients of a decode exist only strip by strip in K3's shared memory.  The records (or, after the
+    // Huffman final pass, the coefficient matrix) of the lane's last job are still resident, so K3 runs once more in
+    // its coefficients-only form: expansion + DC prediction + F1 rule, tiles written out, no pixels.
+    IdctArgs ia = L.job.ia;
+    ia.coef_out = (int16_t *)ctx->merged.p;
+    ia.pixels = nullptr;
+    TRY(next_lb_tag(ctx, L, &ia.lb_tag));
+    uint32_t launches = 0;
+    CK(launch_idct(ia, L.stream, &launches));
     CK(cudaMemcpyAsync(out, ctx->merged.p, n * 2u, cudaMemcpyDeviceToHost, L.stream));
     CK(cudaStreamSynchronize(L.stream));
     CK(cudaGetLastError());

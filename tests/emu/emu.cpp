@@ -106,7 +106,7 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
         const uint32_t p0 = sub * sub_bits;
         const uint32_t end = std::min(p0 + sub_bits, total_bits);
         hint[sub] = g.nseg > 1 ? first_seg_at_or_after(seg_bit, g.nseg, p0) : (sub ? 1u : 0u);
-        X[sub] = decode_span<false>(PW, PL, S, g, end, p0, 0, 0, hint[sub], 0, nullptr, nullptr, nullptr);
+        X[sub] = relay_span(PW, PL, S, g, end, p0, 0, 0, hint[sub]);
         used_p[sub] = p0;
         used_cz[sub] = 0;
     }
@@ -117,13 +117,12 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
         const std::vector<SubState> prev = X;
         for (uint32_t sub = 1; sub < nsub; ++sub) {
             const SubState in = prev[sub - 1];
-            if (used_p[sub] == in.p && used_cz[sub] == in.cz)
+            if (used_p[sub] == in.p && used_cz[sub] == (in.cz & CZ_STATE_MASK))
                 continue;
             const uint32_t end = std::min((sub + 1) * sub_bits, total_bits);
-            const SubState out =
-                decode_span<false>(PW, PL, S, g, end, in.p, in.cz >> 8, in.cz & 0xFF, hint[sub], 0, nullptr, nullptr, nullptr);
+            const SubState out = relay_span(PW, PL, S, g, end, in.p, (in.cz >> 8) & 3u, in.cz & 0xFF, hint[sub]);
             used_p[sub] = in.p;
-            used_cz[sub] = in.cz;
+            used_cz[sub] = in.cz & CZ_STATE_MASK;
             if (out.p != X[sub].p || out.cz != X[sub].cz || out.n != X[sub].n || out.seg != X[sub].seg) {
                 X[sub] = out;
                 ++changed;
@@ -158,7 +157,7 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
         uint32_t p = 0, c = 0, z = 0;
         if (sub) {
             p = X[sub - 1].p;
-            c = X[sub - 1].cz >> 8;
+            c = (X[sub - 1].cz >> 8) & 3u;
             z = X[sub - 1].cz & 0xFF;
         }
         const uint32_t slot = start[sub];
@@ -166,53 +165,71 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
         if ((slot & 63u) != z || ((slot >> 6) % g.ncomp) != c)
             st |= ST_EXIT_MISMATCH;
         const uint32_t end = std::min((sub + 1) * sub_bits, total_bits);
-        const SubState out = decode_span<true>(PW, PL, S, g, end, p, c, z, hint[sub], slot, coef.data(), dcdiff.data(), &st);
-        if (out.p != X[sub].p || out.cz != X[sub].cz)
+        const SubState out = write_span(PW, PL, S, g, end, p, c, z, hint[sub], slot, coef.data(), dcdiff.data(), &st);
+        if (out.p != X[sub].p || out.cz != (X[sub].cz & CZ_STATE_MASK))
             st |= ST_EXIT_MISMATCH;
         status |= st;
     }
     if (final_slot < g.total_blocks * 64u)
         status |= ST_SEG_MISMATCH;
-    // K1 final pass, record flavour: relay-style decode from the true entry states emitting symbol
-    // records, then expansion.  Must reproduce the Huffman final pass exactly.
+    // Record flavour, as the product runs it: relay-style decode from the true entry states emitting one record per
+    // value-carrying symbol (relay_run<true>), the checks of the offset scan's last phase (entropy_scan_apply_kernel),
+    // then K3's expansion (k3_fused.cu stage B): every record is dropped at (entry block of its subsequence) * 64 +
+    // position, no running state.  Must reproduce the Huffman final pass: coefficients, DC differences and verdict.
     uint32_t records_ok = 1;
     {
         struct HostRecorder {
             std::vector<uint32_t> *v;
             void emit(uint32_t, uint32_t w) const { v->push_back(w); }
         };
-        struct HostRecAt {
-            const std::vector<uint32_t> *v;
-            uint32_t operator()(uint32_t k) const { return (*v)[k]; }
-        };
-        std::vector<int16_t> coef2((size_t)g.total_blocks * 64, 0), dcdiff2(g.total_blocks, 0);
+        std::vector<int16_t> coef2((size_t)g.total_blocks * 64, 0);
+        const uint32_t total_slots = g.total_blocks * 64u;
         uint32_t st2 = 0, max_rec = 0;
         for (uint32_t sub = 0; sub < nsub; ++sub) {
             uint32_t p = 0, c = 0, z = 0;
             if (sub) {
                 p = X[sub - 1].p;
-                c = X[sub - 1].cz >> 8;
+                c = (X[sub - 1].cz >> 8) & 3u;
                 z = X[sub - 1].cz & 0xFF;
             }
             std::vector<uint32_t> recs;
             DecState d;
             dec_init(d, PW, S, p, c, z, hint[sub], 0);
             const uint32_t end = std::min((sub + 1) * sub_bits, total_bits);
-            decode_run<false, true>(d, PW, PL, S, g, end, 0xFFFFFFFFu, NullSink{}, HostRecorder{&recs});
+            relay_run<true>(d, PW, PL, S, g, end, HostRecorder{&recs});
+            const SubState out = relay_exit_state(d);
             if (d.nrec != recs.size())
                 records_ok = 0;
-            max_rec = std::max<uint32_t>(max_rec, d.nrec);
-            uint32_t k = 0, slot = start[sub], zz2 = z;
-            expand_run(k, (uint32_t)recs.size(), slot, zz2, st2, HostRecAt{&recs}, g, 0xFFFFFFFFu,
-                       GlobalSink{coef2.data(), dcdiff2.data()});
-            const uint32_t expect = sub + 1 < nsub ? start[sub + 1] : final_slot;
-            if (slot != expect)
+            // the emitting decode ends in the state (and slot count) the relay's fixed point holds
+            if (out.p != X[sub].p || ((out.cz ^ X[sub].cz) & CZ_STATE_MASK) || out.n != X[sub].n || out.seg != X[sub].seg)
                 records_ok = 0;
+            max_rec = std::max<uint32_t>(max_rec, d.nrec);
+            // entropy_scan_apply_kernel
+            const uint32_t begin = start[sub], fin = sub + 1 < nsub ? start[sub + 1] : final_slot;
+            st2 |= (out.cz & CZ_BAD_CODE) ? ST_BAD_CODE : 0u;
+            st2 |= (out.cz & CZ_SLOT_OVERFLOW) ? ST_SLOT_OVERFLOW : 0u;
+            st2 |= (out.cz & CZ_SEG_MISMATCH) ? ST_SEG_MISMATCH : 0u;
+            if (out.seg >= 0 && (begin & ~63u) + (out.cz >> CZ_POS_SHIFT) != fin && !((uint32_t)out.seg >= g.nseg && fin >= total_slots))
+                st2 |= ST_SEG_MISMATCH;
+            if ((fin & 63u) != (out.cz & 63u) || ((fin >> 6) % g.ncomp) != ((out.cz >> 8) & 3u))
+                st2 |= ST_EXIT_MISMATCH;
+            // K3 stage B
+            for (uint32_t r : recs) {
+                const uint32_t at = (begin & ~63u) + record_pos(r);
+                if (at < total_slots)
+                    coef2[at] = (int16_t)record_value(r);
+            }
         }
-        if (coef2 != coef || dcdiff2 != dcdiff)
+        if (final_slot < total_slots)
+            st2 |= ST_SEG_MISMATCH;
+        // the Huffman final pass keeps DC differences apart; the records put them into slot 0 of their blocks
+        std::vector<int16_t> coef1 = coef;
+        for (uint32_t b = 0; b < g.total_blocks; ++b)
+            coef1[(size_t)b * 64] = dcdiff[b];
+        if (status == 0 && (coef2 != coef1 || st2 != 0))
             records_ok = 0;
-        if ((st2 & ~ST_SEG_MISMATCH) != (status & (ST_BAD_CODE | ST_SLOT_OVERFLOW)))
-            records_ok = records_ok && ((st2 | status) & (ST_BAD_CODE | ST_SLOT_OVERFLOW)) ? records_ok : records_ok;
+        if ((status != 0) != (st2 != 0)) // a stream one flavour rejects, the other must reject too
+            records_ok = 0;
         if (info)
             info[8] = max_rec;
     }
