@@ -132,12 +132,18 @@ KPEG_HD int32_t record_value(uint32_t r) { return (int32_t)(r & 0xFFFFu) - 0x800
 constexpr uint32_t COEF_BIAS = 0x8000u; // coefficients travel as value + COEF_BIAS in 16 bits (records, K3's tile)
 
 // value + COEF_BIAS of a symbol with `size` (1..15) magnitude bits that follow the code in the left-aligned window
+// (size == 0 is tolerated -- the result is then meaningless and the caller does not store it)
 KPEG_HD uint32_t biased_extend(uint32_t win, uint32_t T, uint32_t size)
 {
-    const uint32_t x = win << (T - size);      // magnitude bits left-aligned
-    const uint32_t raw = x >> (32u - size);
-    // leading 1: the value itself; leading 0: value - (2^size - 1)
-    return raw + ((int32_t)x < 0 ? COEF_BIAS : COEF_BIAS + 1u - (1u << size));
+    const uint32_t x = win << (T - size);            // magnitude bits left-aligned
+    const uint32_t m = (uint32_t)((int32_t)x >> 31); // all ones: leading 1, the value itself; zero: leading 0, value - (2^size - 1)
+#if defined(__CUDA_ARCH__)
+    const uint32_t raw = __funnelshift_rc(x, 0u, 32u - size); // one clamped shift (size == 0: 32 bits)
+#else
+    const uint32_t raw = (x >> 16) >> (16u - size);
+#endif
+    // raw - (2^size - 1 where the leading bit is 0) == raw + ((-1 << size) | m) + 1
+    return raw + ((0xFFFFFFFFu << size) | m) + (COEF_BIAS + 1u);
 }
 
 // SubState::cz = (component << 8) | zig-zag index in the low 10 bits -- the decoder STATE, the part the relay's
@@ -150,7 +156,7 @@ constexpr uint32_t CZ_FLAGS = CZ_BAD_CODE | CZ_SLOT_OVERFLOW | CZ_SEG_MISMATCH;
 constexpr uint32_t CZ_POS_SHIFT = 16;           // bits 31..16: position (as in a record) the subsequence ended on
 
 struct NoRecorder {
-    KPEG_HD void emit(uint32_t, uint32_t) const {}
+    KPEG_HD void emit(bool, uint32_t, uint32_t) const {}
 };
 
 // Resumable decoder state of one subsequence.
@@ -243,11 +249,11 @@ KPEG_HD void relay_run(DecState &d, const Words &W, const Luts &L, const StreamV
         const uint32_t T = e & 31u, adv = e >> 9, size = (e >> 5) & 15u;
         const uint32_t zn = (q & 63u) + adv;
         if (EMIT) {
+            // no branch: the record word is computed for every symbol (nearly all of them carry a value) and the
+            // store alone is predicated
             worst = max_u32(worst, size ? zn : adv);
-            if (size) {
-                rec.emit(nrec, record_pack(q + adv - 1u, biased_extend(win, T, size)));
-                ++nrec;
-            }
+            rec.emit(size != 0u, nrec, record_pack(q + adv - 1u, biased_extend(win, T, size)));
+            nrec += size ? 1u : 0u;
         }
         if (zn >= 64u) { // end of the block: next table of the ring
             q = (q | 63u) + 1u;

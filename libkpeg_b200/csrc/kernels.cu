@@ -290,6 +290,24 @@ __global__ void __launch_bounds__(UNSTUFF_THREADS) unstuff_write_kernel(UnstuffA
     }
 }
 
+// Host-buffer batches: the scans of a chunk are copied into the lane's stream buffer one after another, leaving two
+// bytes after each; this kernel writes the RSTn separators there (ends[i] = offset just past scan i), so the host
+// issues no 2-byte copies.
+__global__ void __launch_bounds__(256) write_separators_kernel(uint8_t *scan, const uint64_t *ends, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i < n) {
+        const uint64_t e = ends[i];
+        scan[e] = 0xFFu;
+        scan[e + 1u] = (uint8_t)(0xD0u + (i & 7u));
+    }
+}
+
+void launch_write_separators(uint8_t *scan, const uint64_t *ends, uint32_t n, cudaStream_t s)
+{
+    write_separators_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(scan, ends, n);
+}
+
 void launch_unstuff(const UnstuffArgs &a, uint32_t sub_bits, cudaStream_t s, uint32_t *launches)
 {
     unstuff_count_kernel<<<a.ntiles, UNSTUFF_THREADS, 0, s>>>(a);
@@ -473,13 +491,13 @@ __device__ __forceinline__ size_t rec_base_index(uint32_t sub, uint32_t kmax)
 constexpr uint32_t NREC_MASK = 1023u;
 
 struct GlobalRecorder {
-    uint32_t *base; // &rec[rec_base_index(sub)], or the subsequence's private area
+    char *base; // &rec[rec_base_index(sub)], or the subsequence's private area
     uint32_t kmax;
     uint32_t stride_bytes; // 128 in the warp-interleaved layout, 4 in a private area: one IMAD.WIDE per address
-    __device__ __forceinline__ void emit(uint32_t k, uint32_t w) const
+    __device__ __forceinline__ void emit(bool on, uint32_t k, uint32_t w) const
     {
-        if (k < kmax)
-            *reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(base) + (size_t)k * stride_bytes) = w;
+        if (on && k < kmax)
+            asm volatile("st.global.u32 [%0], %1;" ::"l"(base + (size_t)k * stride_bytes), "r"(w) : "memory");
     }
 };
 
@@ -492,9 +510,8 @@ __device__ __forceinline__ SubState relay_decode(const EntropyArgs &a, const Wor
     dec_init(d, W, S, p, (cz >> 8) & 3u, cz & 0xFFu, a.seg_hint[sub], 0u);
     if (a.rec) {
         GlobalRecorder R;
-        R.base = a.rec + rec_base_index(sub, a.rec_kmax);
+        R.base = reinterpret_cast<char *>(a.rec + rec_base_index(sub, a.rec_kmax));
         R.kmax = a.rec_kmax;
-        asm volatile("" : "+r"(R.kmax)); // a register, not a reload of the kernel parameter per symbol
         R.stride_bytes = 128u;
         uint32_t area = 0;
         if (sparse) {
@@ -504,10 +521,13 @@ __device__ __forceinline__ SubState relay_decode(const EntropyArgs &a, const Wor
                 area = idx < a.rec_alt_cap ? idx + 1u : 0u;
             }
             if (area) {
-                R.base = a.rec_alt + (size_t)(area - 1u) * a.rec_kmax;
+                R.base = reinterpret_cast<char *>(a.rec_alt + (size_t)(area - 1u) * a.rec_kmax);
                 R.stride_bytes = 4u;
             }
         }
+        // registers, not values the compiler recomputes from the kernel parameters for every symbol (it did: seven
+        // instructions of address arithmetic per record)
+        asm volatile("" : "+l"(R.base), "+r"(R.kmax), "+r"(R.stride_bytes));
         relay_run<true>(d, W, L, S, a.g, end, R);
         a.nrec[sub] = min(d.nrec, NREC_MASK) | (area << 10);
         if (d.nrec > a.rec_kmax)

@@ -98,6 +98,7 @@ constexpr int IDCT_MCUS_PER_CTA = 32;
 void kernels_context_created();   // contexts of this process share the device: the cooperative relay loops of
 void kernels_context_destroyed(); // all of them together must stay co-resident
 void kernels_configure(int max_concurrent_jobs); // jobs (lanes) that may be on the device at the same time // per-device function attributes (call once after cudaSetDevice)
+void launch_write_separators(uint8_t *scan, const uint64_t *ends, uint32_t n, cudaStream_t s); // RSTn after every scan of a packed batch
 void launch_unstuff(const UnstuffArgs &a, uint32_t sub_bits, cudaStream_t s, uint32_t *launches);
 void launch_entropy_cold(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint32_t *launches);

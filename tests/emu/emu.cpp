@@ -180,7 +180,7 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
     {
         struct HostRecorder {
             std::vector<uint32_t> *v;
-            void emit(uint32_t, uint32_t w) const { v->push_back(w); }
+            void emit(bool on, uint32_t, uint32_t w) const { if (on) v->push_back(w); }
         };
         std::vector<int16_t> coef2((size_t)g.total_blocks * 64, 0);
         const uint32_t total_slots = g.total_blocks * 64u;
