@@ -118,9 +118,20 @@ int kpeg_cuda_set_tuning(kpeg_ctx *ctx, int sub_bits, int relay_rounds);
 /* The CUDA stream (cudaStream_t) all of this context's work is issued on. */
 void *kpeg_cuda_stream(kpeg_ctx *ctx);
 
-/* Pinned host memory for scan / pixel buffers (plain malloc'd memory also works, slower). */
+/* A process-wide pool of idle contexts: acquire hands out one for `device` (creating it when the pool has none),
+ * release puts it back with its scratch memory intact.  What kpeg::JPEGDecoder uses, so that decoding file after
+ * file (reference main.cpp:54-79 constructs a decoder per file) does not pay context creation every time.
+ * Thread-safe.  kpeg_cuda_pool_clear destroys the idle contexts. */
+int kpeg_cuda_acquire(int device, kpeg_ctx **out);
+void kpeg_cuda_release(int device, kpeg_ctx *ctx);
+void kpeg_cuda_pool_clear(void);
+
+/* Pinned host memory for scan / pixel buffers (plain malloc'd memory also works, slower); pinned for every device.
+ * kpeg_cuda_host_register pins memory the caller already owns (a frame shared between processes, say). */
 void *kpeg_cuda_host_alloc(size_t bytes);
 void kpeg_cuda_host_free(void *p);
+int kpeg_cuda_host_register(void *p, size_t bytes);
+void kpeg_cuda_host_unregister(void *p);
 /* Device memory helpers for callers that keep data resident (bench, pipelines). */
 void *kpeg_cuda_device_alloc(kpeg_ctx *ctx, size_t bytes);
 void kpeg_cuda_device_free(kpeg_ctx *ctx, void *p);
@@ -204,6 +215,37 @@ int kpeg_cuda_read_coefficients(kpeg_ctx *ctx, int16_t *out, size_t cap);
  * out_begin / out_end have `parts` entries, out_row has parts + 1. */
 int kpeg_split_restart_bands(const uint8_t *scan, size_t len, const kpeg_plan *plan, int parts, uint64_t *out_begin,
                              uint64_t *out_end, uint32_t *out_row);
+
+/* ---- one image over several GPUs (kpeg_tiled.cpp) ---------------------------------------------------------
+ * The restart-interval tiles of one very large image, one band of whole MCU rows per listed device (a device may be
+ * listed more than once), each band decoded by its own GPU straight into its rows of the caller's frame
+ * pixels_out (ideally pinned: kpeg_cuda_host_alloc) -- the frame Image::createImageFromMCUs assembles
+ * (Image.cpp:51-70), gathered on the host with no device-to-device traffic.  One host thread and one pooled context
+ * per device.  An image whose restart interval does not line up with MCU rows (or has none) does not shard: it is
+ * decoded whole on devices[0].  Errors: the return code; text in kpeg_tiled_last_error (per calling thread). */
+int kpeg_cuda_decode_tiled(const int *devices, int ndev, const kpeg_plan *plan, const uint8_t *scan, size_t scan_len,
+                           uint8_t *pixels_out, kpeg_stats *stats);
+int kpeg_cuda_decode_file_tiled(const int *devices, int ndev, const uint8_t *file, size_t len, uint32_t flags,
+                                uint8_t *pixels_out, size_t cap, kpeg_plan *plan_out, kpeg_stats *stats);
+/* Same, the frame assembled in DEVICE memory of dst_device (d_frame: height*width*ncomp bytes there): every band
+ * travels by one peer copy over NVLink (staged by the driver where there is no peer access), so a consumer on
+ * dst_device never pays PCIe. */
+int kpeg_cuda_decode_tiled_device(const int *devices, int ndev, const kpeg_plan *plan, const uint8_t *scan, size_t scan_len,
+                                  int dst_device, uint8_t *d_frame, kpeg_stats *stats);
+const char *kpeg_tiled_last_error(void);
+/* One band of such a decode: host scan in, pixels to device memory d_dst of dst_device (this context's own device:
+ * written in place by the kernels). */
+int kpeg_cuda_decode_to_peer(kpeg_ctx *ctx, const kpeg_plan *plan, const uint8_t *scan, size_t scan_len, int dst_device,
+                             uint8_t *d_dst, kpeg_stats *stats);
+
+/* ---- output formats written on the GPU ------------------------------------------------------------------------
+ * The file Image::dumpRawData writes (Image.cpp:108-140: P6 header, then R,G,B rows) assembled in device memory:
+ * d_out[*ppm_off, *ppm_off + *ppm_len) holds it (ppm_off < 16 keeps the payload aligned for the kernels' vector
+ * stores; d_out must be 16-byte aligned, cap >= 176 + 3*width*height).  One-component images come out as R = G = B. */
+int kpeg_cuda_decode_ppm_device(kpeg_ctx *ctx, const kpeg_plan *plan, const uint8_t *d_scan, size_t scan_len, uint8_t *d_out,
+                                size_t cap, size_t *ppm_off, size_t *ppm_len, kpeg_stats *stats);
+/* Interleaved R,G,B (the decode output) -> three planes [3][npixels], both in device memory. */
+int kpeg_cuda_interleaved_to_planar(kpeg_ctx *ctx, const uint8_t *d_rgb, uint8_t *d_planes, size_t npixels);
 
 /* Exact bytes of the PPM header Image::dumpRawData writes (Image.cpp:124-127); returns length. */
 int kpeg_ppm_header(int width, int height, char *buf, size_t cap);

@@ -109,6 +109,21 @@ SYMBOLS = {
     "kpeg_split_restart_bands": (C.c_int, [_vp, C.c_size_t, C.POINTER(Plan), C.c_int, C.POINTER(C.c_uint64),
                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "kpeg_ppm_header": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
+    "kpeg_cuda_acquire": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "kpeg_cuda_release": (None, [C.c_int, _vp]),
+    "kpeg_cuda_pool_clear": (None, []),
+    "kpeg_cuda_host_register": (C.c_int, [_vp, C.c_size_t]),
+    "kpeg_cuda_host_unregister": (None, [_vp]),
+    "kpeg_cuda_decode_tiled": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(Plan), _vp, C.c_size_t, _vp, C.POINTER(Stats)]),
+    "kpeg_cuda_decode_file_tiled": (C.c_int, [C.POINTER(C.c_int), C.c_int, _vp, C.c_size_t, C.c_uint32, _vp, C.c_size_t,
+                                             C.POINTER(Plan), C.POINTER(Stats)]),
+    "kpeg_cuda_decode_tiled_device": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(Plan), _vp, C.c_size_t, C.c_int, _vp,
+                                               C.POINTER(Stats)]),
+    "kpeg_tiled_last_error": (C.c_char_p, []),
+    "kpeg_cuda_decode_to_peer": (C.c_int, [_vp, C.POINTER(Plan), _vp, C.c_size_t, C.c_int, _vp, C.POINTER(Stats)]),
+    "kpeg_cuda_decode_ppm_device": (C.c_int, [_vp, C.POINTER(Plan), _vp, C.c_size_t, _vp, C.c_size_t, C.POINTER(C.c_size_t),
+                                             C.POINTER(C.c_size_t), C.POINTER(Stats)]),
+    "kpeg_cuda_interleaved_to_planar": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
 }
 
 _lib = None
@@ -319,10 +334,38 @@ class Decoder:
         self._pending.clear()
         self._check(rc, "kpeg_cuda_wait")
 
+    def decode_ppm_device(self, plan: Plan, d_scan: int, scan_len: int, d_out: int, cap: int):
+        """GPU-side PPM writer (kpeg_cuda_decode_ppm_device) -> (offset, length) of the file inside d_out."""
+        off, ln = C.c_size_t(0), C.c_size_t(0)
+        rc = self._lib.kpeg_cuda_decode_ppm_device(self._h, C.byref(plan), d_scan, scan_len, d_out, cap, C.byref(off),
+                                                   C.byref(ln), C.byref(self.last_stats))
+        self._check(rc, "kpeg_cuda_decode_ppm_device")
+        return off.value, ln.value
+
+    def interleaved_to_planar(self, d_rgb: int, d_planes: int, npixels: int):
+        self._check(self._lib.kpeg_cuda_interleaved_to_planar(self._h, d_rgb, d_planes, npixels), "interleaved_to_planar")
+
     def decode_batch_packed_device(self, plan: Plan, n: int, d_packed: int, packed_len: int, d_out: int):
         rc = self._lib.kpeg_cuda_decode_batch_packed_device(self._h, C.byref(plan), n, d_packed, packed_len, d_out,
                                                             C.byref(self.last_stats))
         self._check(rc, "kpeg_cuda_decode_batch_packed_device")
+
+
+def decode_file_tiled(devices: list[int], data, flags: int = KPEG_FLAG_REF_PARITY, out: np.ndarray | None = None):
+    """One image over several GPUs (kpeg_cuda_decode_file_tiled): restart-interval bands, one per listed device, each
+    decoded into its rows of ONE host frame.  Returns (pixels, Stats)."""
+    lib = load_cuda_library()
+    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    plan, _, _ = parse_jfif(buf)
+    shape = (plan.height, plan.width, plan.ncomp) if plan.ncomp == 3 else (plan.height, plan.width)
+    if out is None:
+        out = np.empty(shape, dtype=np.uint8)
+    dv = (C.c_int * len(devices))(*devices)
+    st = Stats()
+    rc = lib.kpeg_cuda_decode_file_tiled(dv, len(devices), _ptr(buf), buf.size, flags, _ptr(out), out.nbytes, None, C.byref(st))
+    if rc != KPEG_OK:
+        raise KpegError(rc, f"kpeg_cuda_decode_file_tiled: {lib.kpeg_tiled_last_error().decode(errors='replace')}")
+    return out.reshape(shape), st
 
 
 def packed_offsets(scans: list[np.ndarray]) -> np.ndarray:

@@ -171,7 +171,27 @@ struct DecState {
     uint32_t nrec;             // records emitted (relay passes)
     uint32_t q, qj;            // relay passes: running record position; its value at entry / after the last boundary
     uint32_t flags;            // relay passes: CZ_* annotations
+    long long dcs;             // relay passes (DCS): packed sums of the DC differences decoded since entry / the last boundary
 };
+
+// ---- DC sums (K2 as a device-wide scan at subsequence granularity) ----------------------------------------
+// DC prediction (MCU.cpp:107-108) needs, for every block, the sum of the DC differences of its component since the
+// last restart / image start.  The relay passes add up the DC differences each subsequence decodes, the offset scan
+// turns them into the predictor values at every subsequence entry, and a K3 strip adds the few DC differences between
+// the entry of the subsequence its first slot lies in and that slot.  The three component sums travel as ONE exact
+// 64-bit integer s0 + s1 * 2^15 + s2 * 2^30: adding two such numbers adds the components, and a component is
+// recovered as long as |s_c| < 2^14 (a sum of differences is a difference of two DC values: |.| <= 4094 in any
+// valid baseline stream; garbage decodes give garbage sums, which nothing trusts).
+constexpr uint32_t DCS_SHIFT = 15;
+KPEG_HD uint32_t dcs_weight(uint32_t c) { return 1u << (DCS_SHIFT * c); }
+KPEG_HD void dcs_unpack(long long s, int (&v)[3])
+{
+    for (int c = 0; c < 3; ++c) {
+        const int f = (int)((uint32_t)s & 0x7FFFu);
+        v[c] = f >= 0x4000 ? f - 0x8000 : f;
+        s = (s - v[c]) >> DCS_SHIFT; // exact: the difference is a multiple of 2^15
+    }
+}
 
 template <class Words>
 KPEG_HD void dec_init(DecState &d, const Words &W, const StreamView &S, uint32_t p, uint32_t c, uint32_t z, uint32_t k,
@@ -195,6 +215,7 @@ KPEG_HD void dec_init(DecState &d, const Words &W, const StreamView &S, uint32_t
     d.nrec = 0;
     d.q = d.qj = z;
     d.flags = 0;
+    d.dcs = 0;
 }
 
 KPEG_HD SubState dec_exit_state(const DecState &d)
@@ -233,11 +254,19 @@ KPEG_HD SubState relay_exit_state(const DecState &d)
 // Errors of the decode are annotations of the exit state (CZ_*), not device status bits: a speculative decode from a
 // wrong entry state meets "errors" that mean nothing; only the annotations of the LAST decode of a subsequence -- the
 // one from its true entry state -- survive in state[], and the offset scan turns those into status bits.
-template <bool EMIT, class Words, class Luts, class Rec>
+//
+// DCS: also add up the DC differences per component (dcs_weight / dcs_unpack above).  wd is the weight the NEXT
+// symbol's value is added with: 2^(15 component) when that symbol is a DC difference, 0 otherwise -- so the sum costs
+// one multiply-add per symbol and two selects, no test of what kind of symbol it was.  (biased_extend gives exactly
+// COEF_BIAS for a symbol without magnitude bits, i.e. the value 0.)
+template <bool EMIT, bool DCS = false, class Words, class Luts, class Rec>
 KPEG_HD void relay_run(DecState &d, const Words &W, const Luts &L, const StreamView &S, const JobGeom &g, uint32_t end_bit,
                        const Rec &rec)
 {
     const uint32_t ring = g.ncomp * 2u * (uint32_t)LUT_SIZE;
+    long long dcs = d.dcs;
+    uint32_t wc = dcs_weight(d.toff >> (LUT_BITS + 1));                    // weight of the current component
+    uint32_t wd = (d.toff & (uint32_t)LUT_SIZE) ? 0u : wc;                 // ... if the next symbol is its DC difference
     uint32_t p = d.p, j = d.j, sh = d.sh, w0 = d.w0, w1 = d.w1, toff = d.toff, q = d.q, qj = d.qj;
     uint32_t k = d.k, segend = d.segend, nrec = d.nrec, flags = d.flags;
     int32_t seg = d.seg;
@@ -248,21 +277,48 @@ KPEG_HD void relay_run(DecState &d, const Words &W, const Luts &L, const StreamV
     auto symbol = [&](uint32_t win, uint32_t e) { // everything a symbol does except moving the bit position
         const uint32_t T = e & 31u, adv = e >> 9, size = (e >> 5) & 15u;
         const uint32_t zn = (q & 63u) + adv;
-        if (EMIT) {
-            // no branch: the record word is computed for every symbol (nearly all of them carry a value) and the
-            // store alone is predicated
-            worst = max_u32(worst, size ? zn : adv);
-            rec.emit(size != 0u, nrec, record_pack(q + adv - 1u, biased_extend(win, T, size)));
-            nrec += size ? 1u : 0u;
+        if (EMIT || DCS) {
+            const uint32_t bv = biased_extend(win, T, size);
+            if (EMIT) {
+                // no branch: the record word is computed for every symbol (nearly all of them carry a value) and the
+                // store alone is predicated
+                worst = max_u32(worst, size ? zn : adv);
+                rec.emit(size != 0u, nrec, record_pack(q + adv - 1u, bv));
+                nrec += size ? 1u : 0u;
+            }
+            if (DCS)
+                dcs += (long long)(int32_t)(bv - COEF_BIAS) * (long long)(int32_t)wd;
         }
         if (zn >= 64u) { // end of the block: next table of the ring
             q = (q | 63u) + 1u;
             toff += (uint32_t)LUT_SIZE;
-            toff = toff == ring ? 0u : toff;
+            const bool wrap = toff == ring;
+            toff = wrap ? 0u : toff;
+            if (DCS) {
+                wc = wrap ? 1u : wc << DCS_SHIFT;
+                wd = wc;
+            }
         } else {
             q += adv;
             toff |= (uint32_t)LUT_SIZE;
+            if (DCS)
+                wd = 0u;
         }
+    };
+    auto cross_boundary = [&]() { // onto boundary k: state (segend, component 0, DC), position and DC sums restart
+        q = (q + 63u) & ~63u;
+        if (seg >= 0 && q - qj != seg_slot_base(g, k) - seg_slot_base(g, (uint32_t)seg))
+            flags |= CZ_SEG_MISMATCH; // the interval between the last boundary and this one
+        qj = q;
+        seg = (int32_t)k;
+        p = segend;
+        toff = 0;
+        if (DCS) { // predictors restart with the interval (T.81 F.2.1.3.1)
+            dcs = 0;
+            wc = wd = 1u;
+        }
+        ++k;
+        segend = S.seg_bit[k];
     };
     // Fast lane.  When the next boundary lies at least a symbol beyond end_bit (always, without restart markers,
     // except next to an image end) no symbol of this call can straddle it, and with a word-aligned end_bit
@@ -295,15 +351,7 @@ KPEG_HD void relay_run(DecState &d, const Words &W, const Luts &L, const StreamV
         if (p + T > segend) {
             // The symbol would straddle a restart / image boundary: we are in its padding (T.81 F.2.2.4 / E.2.4).
             // A valid stream is at the end of an MCU here, so the position is already a multiple of 64.
-            q = (q + 63u) & ~63u;
-            if (seg >= 0 && q - qj != seg_slot_base(g, k) - seg_slot_base(g, (uint32_t)seg))
-                flags |= CZ_SEG_MISMATCH; // the interval between the last boundary and this one
-            qj = q;
-            seg = (int32_t)k;
-            p = segend;
-            toff = 0;
-            ++k;
-            segend = S.seg_bit[k];
+            cross_boundary();
             if (p >= S.total_bits)
                 break;
             j = p >> 5;
@@ -320,6 +368,16 @@ KPEG_HD void relay_run(DecState &d, const Words &W, const Luts &L, const StreamV
         j = cross ? j + 1u : j;
         w0 = cross ? w1 : w0;
         w1 = cross ? nxt : w1;
+    }
+    // An interval without padding bits can end exactly where the subsequence stops: the boundary is crossed here, not
+    // skipped by the next subsequence's dec_init -- every restart of the predictors is then visible to the scans as a
+    // boundary some subsequence crossed.
+    if (p == segend && p < S.total_bits) {
+        cross_boundary();
+        j = p >> 5;
+        sh = p & 31u;
+        w0 = W(j);
+        w1 = W(j + 1u);
     }
     if (EMIT)
         flags |= worst == ENTRY_ADV_INVALID ? CZ_BAD_CODE : (worst > 64u ? CZ_SLOT_OVERFLOW : 0u);
@@ -338,6 +396,7 @@ KPEG_HD void relay_run(DecState &d, const Words &W, const Luts &L, const StreamV
     d.seg = seg;
     d.nrec = nrec;
     d.flags = flags;
+    d.dcs = dcs;
 }
 
 // ---- Huffman final pass (fallback when records cannot be used) ---------------------------------------

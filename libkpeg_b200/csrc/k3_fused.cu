@@ -18,9 +18,11 @@
 //            drop the values into the tile.  (Fallback: the tile is copied from a coefficient matrix the Huffman
 //            final pass wrote.)
 //   stage C  DC prediction (MCU.cpp:107-108): the DC differences sit in slot 0 of their blocks; a segmented warp scan
-//            over the strip's MCUs (reset at restart intervals / image starts) gives the values relative to the strip,
-//            a decoupled look-back over the preceding strips gives the carry: one 64-bit word per strip (three 16-bit
-//            sums + state), published before the strip looks back itself, so the chain never waits on a later strip
+//            over the strip's MCUs (reset at restart intervals / image starts) gives the values relative to the strip.
+//            The predictor values entering the strip come from K1: the offset scan left the predictors at the entry of
+//            every subsequence (a device-wide segmented scan of the per-subsequence DC sums), and the strip adds the DC
+//            differences between the entry of the subsequence its first slot lies in and that slot.  Strips do not
+//            depend on one another: no ordering assumption, nothing to wait for
 //   stage 1  one thread = one 8x8 block, all 64 values in registers, two fp32 lanes per instruction (FADD2 / FMUL2 /
 //            FFMA2): biased 16-bit -> fp32 by byte permute + one packed subtract (no I2F), dequantise (AAN prescale
 //            folded into the quantiser), de-zigzag by register renaming, separable fp32 IDCT, rounding, tie-band test;
@@ -80,6 +82,11 @@ __device__ __forceinline__ int tie_sample(int w, int b)
 #define KPEG_EXPAND_BATCH 8
 #endif
 constexpr int EXPAND_BATCH = KPEG_EXPAND_BATCH; // record loads in flight per lane in the expansion stage
+#ifndef KPEG_EXPAND_PREFETCH_AHEAD
+#define KPEG_EXPAND_PREFETCH_AHEAD 1024
+#endif
+constexpr uint32_t EXPAND_PREFETCH_AHEAD = KPEG_EXPAND_PREFETCH_AHEAD; // strips ahead whose record lines are pulled into L2
+constexpr int EXPAND_PREFETCH_LINES = 112;                            // record indices per group of 32 subsequences
 
 constexpr int TIE_LIST_CAP = 160; // (block, sample) entries per strip; a strip with more walks its blocks' masks instead
 
@@ -93,8 +100,8 @@ struct IdctSmem {
     float2 qdc[NC][32];           // the same with every AC entry zero: what a block that loses its AC terms (F1) multiplies by
     uint16_t ties[TIE_LIST_CAP];  // block in strip | sample << 7
     uint8_t flag[NB];             // per block: BLK_*
-    int32_t agg[4];               // DC: the components' sums over the strip (since its last reset), [3] = strip holds a reset
     int32_t carry[4];             // DC: predictor values entering the strip
+    uint32_t reset_slot;          // DC: slot of the last predictor restart at or before the strip's first MCU
     uint32_t ntie, any_huge;
     uint32_t img0, by0, bx0, mi0; // image / block row / block column / MCU-in-image of the strip's first MCU
     unsigned long long mbar;      // completion barrier of the stage-A bulk copies
@@ -466,73 +473,6 @@ __device__ __noinline__ int exact_sample_tile(const IdctSmem<NC> *sm, const Devi
     return round_half_away(out);
 }
 
-// ---- decoupled look-back over the strips (stage C) -------------------------------------------------------
-// One 64-bit word per strip: bits 63..50 = launch tag, 49..48 = state, 47..0 = three 16-bit sums (DC values are taken
-// modulo 2^16, as the int16 the reference's coefficients fit).  A word of another launch reads as "not there yet", so
-// the array needs no clearing between launches (the host clears it when the 14-bit tag wraps).
-constexpr uint32_t LB_AGGREGATE = 1u; // sums over this strip alone
-constexpr uint32_t LB_INCLUSIVE = 2u; // predictor values at the end of this strip
-
-__device__ __forceinline__ unsigned long long lb_pack(uint32_t tag, uint32_t state, int v0, int v1, int v2)
-{
-    return ((unsigned long long)((tag << 2) | state) << 48) | ((unsigned long long)((uint32_t)v2 & 0xFFFFu) << 32) |
-           (unsigned long long)((((uint32_t)v1 & 0xFFFFu) << 16) | ((uint32_t)v0 & 0xFFFFu));
-}
-__device__ __forceinline__ unsigned long long lb_load(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void lb_store(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// Predictor values entering strip `strip` (warp-wide: 32 predecessors per step).  Strips are dispatched in index
-// order, so every predecessor is running or done and publishes its word before it looks back itself: the wait is
-// bounded by their expansion stage.  The spin is bounded all the same (a decode never hangs): on a timeout the
-// status bit is set and the host reports an error.
-__device__ __forceinline__ void lookback_carry(const IdctArgs &a, uint32_t strip, int (&carry)[3])
-{
-    const uint32_t lane = threadIdx.x & 31u;
-    carry[0] = carry[1] = carry[2] = 0;
-    int base = (int)strip - 1;
-    for (;;) {
-        const int idx = base - (int)lane;
-        unsigned long long w = lb_pack(a.lb_tag, LB_INCLUSIVE, 0, 0, 0); // before the first strip: nothing
-        uint32_t polls = 0, ns = 32;
-        bool ready = idx < 0;
-        for (;;) {
-            if (!ready) {
-                w = lb_load(a.strip_state + idx);
-                ready = (uint32_t)(w >> 50) == a.lb_tag;
-            }
-            if (__all_sync(0xffffffffu, ready))
-                break;
-            if (++polls > a.lb_spin_limit) {
-                if (lane == 0)
-                    atomicOr(&a.meta->status, ST_LOOKBACK_TIMEOUT);
-                return;
-            }
-            __nanosleep(ns);
-            ns = ns < 512u ? ns * 2u : ns;
-        }
-        const uint32_t state = (uint32_t)(w >> 48) & 3u;
-        const uint32_t incl = __ballot_sync(0xffffffffu, state == LB_INCLUSIVE);
-        // lanes up to and including the nearest inclusive word contribute (lane 0 is the nearest predecessor)
-        const bool use = incl == 0u || lane <= (uint32_t)(__ffs((int)incl) - 1);
-        const int v0 = use ? (int)(short)(uint16_t)w : 0, v1 = use ? (int)(short)(uint16_t)(w >> 16) : 0,
-                  v2 = use ? (int)(short)(uint16_t)(w >> 32) : 0;
-        carry[0] += __reduce_add_sync(0xffffffffu, v0);
-        carry[1] += __reduce_add_sync(0xffffffffu, v1);
-        carry[2] += __reduce_add_sync(0xffffffffu, v2);
-        if (incl)
-            return;
-        base -= 32;
-    }
-}
-
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v)
 {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
@@ -576,6 +516,10 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
         sm.mi0 = mi;
         sm.by0 = mi / a.g.mcus_x;
         sm.bx0 = mi - sm.by0 * a.g.mcus_x;
+        // predictors restart at every restart interval and image (T.81 F.2.1.3.1)
+        const uint32_t mreset = a.g.restart_interval ? mi - mi % a.g.restart_interval : 0u;
+        sm.reset_slot = (img * a.g.mcus_per_image + mreset) * (uint32_t)NC * 64u;
+        sm.carry[0] = sm.carry[1] = sm.carry[2] = 0;
     }
     const uint32_t tile_addr = smem_u32(sm.coef);
     if (a.coef_in == nullptr) {
@@ -588,7 +532,23 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
         const uint32_t nsub = a.meta->nsub;
         const uint32_t s0 = blk0 * 64u; // first slot of the strip; slots are < 2^32 (host_tables.h)
         const uint32_t lane = (uint32_t)ml;
-        uint32_t first = min(__ldg(a.strip_sub + strip), nsub - 1u);
+        const uint32_t first0 = min(__ldg(a.strip_sub + strip), nsub - 1u);
+        {
+            // the record lines a strip that starts about one CTA lifetime from now will read: DRAM -> L2 now, so its
+            // batches below wait for L2, not for DRAM.  (Which strip that is need not be exact.)
+            const uint32_t ahead = strip + EXPAND_PREFETCH_AHEAD;
+            if (ahead < a.nstrips) {
+                const uint32_t fs = min(__ldg(a.strip_sub + ahead), nsub - 1u);
+                const char *g0 = reinterpret_cast<const char *>(a.rec + ((size_t)(fs >> 5) * a.rec_kmax) * 32u);
+                const uint32_t lines = min(a.rec_kmax, (uint32_t)EXPAND_PREFETCH_LINES);
+                for (uint32_t k = (uint32_t)t; k < 2u * lines; k += (uint32_t)NB) {
+                    const uint32_t grp = k >= lines ? 1u : 0u; // the strip's subsequences usually straddle two groups of 32
+                    const char *ptr = g0 + ((size_t)grp * a.rec_kmax + (k - grp * lines)) * 128u;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+                }
+            }
+        }
+        uint32_t first = first0;
         for (int chunk = 0; chunk < 128; ++chunk, first += 32u) { // a strip meets at most ~3 100 subsequences
             const uint32_t sub = first + lane;
             bool act = sub < nsub;
@@ -607,7 +567,9 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
                     base = a.rec + ((size_t)(sub >> 5) * a.rec_kmax) * 32u + (sub & 31u);
                 }
             }
-            const uint32_t off0 = (ss & ~63u) - s0; // slot of record position 0 relative to the tile (may be "negative")
+            // slot of record position 0 relative to the tile (may be "negative"); lanes without a subsequence get an
+            // offset that keeps the out-of-range marker of the batched loads below out of range
+            const uint32_t off0 = act ? (ss & ~63u) - s0 : TILE_SLOTS;
             const uint32_t nmax = __reduce_max_sync(0xffffffffu, n);
             // The loads of a batch are all issued before the first value is used: the expansion is a chain of DRAM
             // round trips otherwise (one per record index; measured: 60 % of the kernel's stall samples).  A record index
@@ -630,6 +592,46 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
             if (!__shfl_sync(0xffffffffu, act && sub + 1u < nsub ? 1 : 0, 31))
                 break;
         }
+        // ---- DC predictors entering the strip (K2) -----------------------------------------------------
+        // = the predictors at the entry of the subsequence the strip's first slot lies in (from the offset scan, unless
+        // they restart between that entry and the strip) + the DC differences that subsequence decoded before the strip
+        // (its records at slot 0 of a block, between the last restart and the strip's first slot).  Warp 0, lanes over
+        // the records of that one subsequence; the lines were just read by the loop above.
+        if (comp == 0) {
+            const uint32_t ss = __ldg(a.start_slot + first0);
+            const uint32_t reset_slot = sm.reset_slot;
+            int part[3] = {0, 0, 0};
+            if (ss < s0 && reset_slot < s0) {
+                const uint32_t nr = __ldg(a.nrec + first0);
+                const uint32_t n = min(nr & 1023u, a.rec_kmax);
+                const uint32_t *base = (nr >> 10) ? a.rec_alt + (size_t)((nr >> 10) - 1u) * a.rec_kmax
+                                                  : a.rec + ((size_t)(first0 >> 5) * a.rec_kmax) * 32u + (first0 & 31u);
+                const uint32_t stride = (nr >> 10) ? 1u : 32u; // in records
+                const uint32_t entry = ss & ~63u;
+                for (uint32_t k = lane; k < n; k += 32u) {
+                    const uint32_t r = __ldg(base + (size_t)k * stride);
+                    const uint32_t at = entry + record_pos(r);
+                    if ((at & 63u) == 0u && at < s0 && at >= reset_slot) {
+                        const uint32_t c = NC == 3 ? (at >> 6) % 3u : 0u;
+                        const int v = record_value(r);
+                        part[0] += c == 0u ? v : 0;
+                        part[1] += c == 1u ? v : 0;
+                        part[2] += c == 2u ? v : 0;
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                part[c] = __reduce_add_sync(0xffffffffu, part[c]);
+            if (lane == 0) {
+                int pre[3] = {0, 0, 0};
+                if (ss >= reset_slot && reset_slot < s0) // no restart between the subsequence's entry and the strip
+                    dcs_unpack(a.dcpre[first0], pre);
+                sm.carry[0] = pre[0] + part[0];
+                sm.carry[1] = pre[1] + part[1];
+                sm.carry[2] = pre[2] + part[2];
+            }
+        }
     } else {
         // fallback: the Huffman final pass (entropy_write) left a coefficient matrix in global memory
         for (uint32_t g = (uint32_t)t; g < (uint32_t)NB * 8u; g += (uint32_t)NB) {
@@ -640,6 +642,8 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
             sm.coef[b * 8u + (k ^ (b & 7u))] = make_uint4(v.x ^ BIAS2, v.y ^ BIAS2, v.z ^ BIAS2, v.w ^ BIAS2);
         }
     }
+    if (t == 0)
+        mbar_wait(bar, 0); // the quantiser tables: the barrier below hands them on
     __syncthreads();
 
     // ---- stage C: DC prediction -----------------------------------------------------------------------
@@ -648,7 +652,10 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
     const int dcdiff = active ? (int)(dcw & 0xFFFFu) - (int)COEF_BIAS : 0;
     const bool drop_ac = (a.g.flags & 1u) && dcdiff == 0;
     int dcv;
-    {
+    if (a.dc_in) {
+        // fallback: the predicted DC values come from dc_integrate_kernel (kernels.cu)
+        dcv = active ? (int)__ldg(a.dc_in + blk0 + (uint32_t)bl) : 0;
+    } else {
         bool reset = false;
         if (active) { // mcu_is_reset: predictors restart at every restart interval and image (T.81 F.2.1.3.1)
             uint32_t mi = sm.mi0 + (uint32_t)ml;
@@ -667,31 +674,6 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
                 f |= of;
             }
         }
-        if (ml == 31) {
-            sm.agg[comp] = v;
-            if (comp == 0)
-                sm.agg[3] = (int32_t)f;
-        }
-        __syncthreads();
-        if (t < 32) { // warp 0: publish, look back, publish again
-            const bool any_reset = sm.agg[3] != 0;
-            const int g0 = sm.agg[0], g1 = NC == 3 ? sm.agg[1] : 0, g2 = NC == 3 ? sm.agg[2] : 0;
-            if (t == 0)
-                lb_store(a.strip_state + strip, lb_pack(a.lb_tag, any_reset ? LB_INCLUSIVE : LB_AGGREGATE, g0, g1, g2));
-            int carry[3] = {0, 0, 0};
-            const bool first_is_reset = __shfl_sync(0xffffffffu, reset ? 1 : 0, 0) != 0;
-            if (!first_is_reset && strip != 0u)
-                lookback_carry(a, strip, carry);
-            if (t == 0) {
-                if (!any_reset)
-                    lb_store(a.strip_state + strip, lb_pack(a.lb_tag, LB_INCLUSIVE, carry[0] + g0, carry[1] + g1, carry[2] + g2));
-                sm.carry[0] = carry[0];
-                sm.carry[1] = carry[1];
-                sm.carry[2] = carry[2];
-                mbar_wait(bar, 0); // the quantiser tables: the barrier below hands them on
-            }
-        }
-        __syncthreads();
         dcv = (int)(short)(v + (f ? 0 : sm.carry[comp]));
     }
 
@@ -1016,8 +998,6 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
         atomicAdd(&a.meta->colour_exact, colour_exact);
 }
 
-static uint32_t g_lb_spin_limit = 4000000u; // polls (~0.5 us each) before a strip gives up on its predecessors: ~2 s
-
 void k3_configure()
 {
     cudaFuncSetAttribute(idct_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<3>));
@@ -1029,7 +1009,6 @@ uint32_t k3_strip_slots(uint32_t ncomp) { return (uint32_t)IDCT_MCUS_PER_CTA * n
 cudaError_t launch_idct(const IdctArgs &a_in, cudaStream_t s, uint32_t *launches)
 {
     IdctArgs a = a_in;
-    a.lb_spin_limit = g_lb_spin_limit;
     const uint32_t total_mcus = a.g.nimages * a.g.mcus_per_image;
     const uint32_t grid = (total_mcus + IDCT_MCUS_PER_CTA - 1) / IDCT_MCUS_PER_CTA;
     if (a.g.ncomp == 3)

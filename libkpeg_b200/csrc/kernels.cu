@@ -308,6 +308,57 @@ void launch_write_separators(uint8_t *scan, const uint64_t *ends, uint32_t n, cu
     write_separators_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(scan, ends, n);
 }
 
+// ---- output format helpers (GPU-side PPM / planar writers) ------------------------------------------------------
+// gray -> R = G = B triplets (what the reference's colour path yields for Cb = Cr = 128): four pixels
+// per thread, one 4-byte load and three 4-byte stores.
+__global__ void __launch_bounds__(256) gray_to_rgb_kernel(const uint8_t *gray, uint8_t *rgb, size_t n)
+{
+    const size_t q = (size_t)blockIdx.x * 256u + threadIdx.x; // quad of pixels
+    const size_t i = q * 4u;
+    if (i + 4u <= n && ((reinterpret_cast<uintptr_t>(gray) | reinterpret_cast<uintptr_t>(rgb)) & 3u) == 0) {
+        const uint32_t g = __ldg(reinterpret_cast<const uint32_t *>(gray) + q);
+        const uint32_t a = g & 0xFFu, b = (g >> 8) & 0xFFu, c = (g >> 16) & 0xFFu, d = g >> 24;
+        uint32_t *o = reinterpret_cast<uint32_t *>(rgb) + q * 3u;
+        o[0] = a * 0x010101u | (b << 24);
+        o[1] = b * 0x0101u | (c * 0x0101u << 16);
+        o[2] = c | (d * 0x010101u << 8);
+    } else {
+        for (size_t k = i; k < n && k < i + 4u; ++k)
+            rgb[3u * k] = rgb[3u * k + 1u] = rgb[3u * k + 2u] = gray[k];
+    }
+}
+
+// interleaved R,G,B -> three planes: four pixels per thread (three 4-byte loads, three 4-byte stores)
+__global__ void __launch_bounds__(256) rgb_to_planar_kernel(const uint8_t *rgb, uint8_t *planes, size_t n)
+{
+    const size_t q = (size_t)blockIdx.x * 256u + threadIdx.x;
+    const size_t i = q * 4u;
+    uint8_t *pr = planes, *pg = planes + n, *pb = planes + 2u * n;
+    if (i + 4u <= n && (n & 3u) == 0 && ((reinterpret_cast<uintptr_t>(rgb) | reinterpret_cast<uintptr_t>(planes)) & 3u) == 0) {
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(rgb) + q * 3u;
+        const uint32_t w0 = __ldg(in), w1 = __ldg(in + 1), w2 = __ldg(in + 2); // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+        reinterpret_cast<uint32_t *>(pr)[q] = __byte_perm(w0, w1, 0x6230) & 0x00FFFFFFu | ((w2 >> 8) & 0xFFu) << 24;
+        reinterpret_cast<uint32_t *>(pg)[q] = ((w0 >> 8) & 0xFFu) | (w1 & 0xFFu) << 8 | (w1 >> 24) << 16 | ((w2 >> 16) & 0xFFu) << 24;
+        reinterpret_cast<uint32_t *>(pb)[q] = ((w0 >> 16) & 0xFFu) | ((w1 >> 8) & 0xFFu) << 8 | (w2 & 0xFFu) << 16 | (w2 >> 24) << 24;
+    } else {
+        for (size_t k = i; k < n && k < i + 4u; ++k) {
+            pr[k] = rgb[3u * k];
+            pg[k] = rgb[3u * k + 1u];
+            pb[k] = rgb[3u * k + 2u];
+        }
+    }
+}
+
+void launch_gray_to_rgb(const uint8_t *gray, uint8_t *rgb, size_t n, cudaStream_t s)
+{
+    gray_to_rgb_kernel<<<(unsigned)((n + 1023u) / 1024u), 256, 0, s>>>(gray, rgb, n);
+}
+
+void launch_rgb_to_planar(const uint8_t *rgb, uint8_t *planes, size_t n, cudaStream_t s)
+{
+    rgb_to_planar_kernel<<<(unsigned)((n + 1023u) / 1024u), 256, 0, s>>>(rgb, planes, n);
+}
+
 void launch_unstuff(const UnstuffArgs &a, uint32_t sub_bits, cudaStream_t s, uint32_t *launches)
 {
     unstuff_count_kernel<<<a.ntiles, UNSTUFF_THREADS, 0, s>>>(a);
@@ -528,8 +579,9 @@ __device__ __forceinline__ SubState relay_decode(const EntropyArgs &a, const Wor
         // registers, not values the compiler recomputes from the kernel parameters for every symbol (it did: seven
         // instructions of address arithmetic per record)
         asm volatile("" : "+l"(R.base), "+r"(R.kmax), "+r"(R.stride_bytes));
-        relay_run<true>(d, W, L, S, a.g, end, R);
+        relay_run<true, true>(d, W, L, S, a.g, end, R);
         a.nrec[sub] = min(d.nrec, NREC_MASK) | (area << 10);
+        a.dcs[sub] = d.dcs;
         if (d.nrec > a.rec_kmax)
             atomicOr(&a.meta->status, ST_REC_OVERFLOW);
     } else {
@@ -768,6 +820,7 @@ __global__ void __launch_bounds__(ENTROPY_THREADS, 8) entropy_relay_loop_kernel(
 // aggregates, per-tile scan seeded with the tile's carry.
 struct SegVal {
     uint32_t f, v;
+    long long s; // packed DC sums (entropy_core.h, dcs_unpack): reset wherever the slot count is absolute
 };
 
 __device__ __forceinline__ SegVal seg_combine(const SegVal &a, const SegVal &b) // a then b
@@ -775,6 +828,7 @@ __device__ __forceinline__ SegVal seg_combine(const SegVal &a, const SegVal &b) 
     SegVal r;
     r.f = a.f | b.f;
     r.v = b.f ? b.v : a.v + b.v;
+    r.s = b.f ? b.s : a.s + b.s;
     return r;
 }
 
@@ -789,6 +843,7 @@ __device__ __forceinline__ SegVal block_seg_scan(SegVal x, SegVal *s_w, SegVal &
         SegVal o;
         o.f = __shfl_up_sync(0xffffffffu, x.f, d);
         o.v = __shfl_up_sync(0xffffffffu, x.v, d);
+        o.s = __shfl_up_sync(0xffffffffu, x.s, d);
         if (lane >= d)
             x = seg_combine(o, x);
     }
@@ -802,6 +857,7 @@ __device__ __forceinline__ SegVal block_seg_scan(SegVal x, SegVal *s_w, SegVal &
             SegVal o;
             o.f = __shfl_up_sync(0xffffffffu, w.f, d);
             o.v = __shfl_up_sync(0xffffffffu, w.v, d);
+            o.s = __shfl_up_sync(0xffffffffu, w.s, d);
             if (lane >= d)
                 w = seg_combine(o, w);
         }
@@ -819,10 +875,13 @@ __device__ __forceinline__ SegVal load_seg_val(const EntropyArgs &a, uint32_t i,
     SegVal e;
     e.f = 0;
     e.v = 0;
+    e.s = 0;
     if (i < nsub) {
         const SubState st = a.state[i];
         e.f = st.seg >= 0 ? 1u : 0u;
         e.v = st.n + (e.f ? seg_slot_base(a.g, (uint32_t)st.seg) : 0u);
+        if (a.rec)
+            e.s = a.dcs[i];
     }
     return e;
 }
@@ -835,8 +894,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) entropy_scan_reduce_kernel(Entro
         return;
     SegVal agg;
     block_seg_scan(load_seg_val(a, blockIdx.x * SCAN_THREADS + threadIdx.x, nsub), s_w, agg);
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
         a.scan_tiles[blockIdx.x] = make_uint2(agg.f, agg.v);
+        a.scan_tiles_dcs[blockIdx.x] = agg.s;
+    }
 }
 
 // one block: scan_tiles[t] <- value carried INTO tile t; also the final slot of the stream
@@ -850,6 +911,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) entropy_scan_tiles_kernel(Entrop
     if (threadIdx.x == 0) {
         s_carry.f = 1u; // virtual element -1: absolute slot 0 (segment 0 starts at bit 0)
         s_carry.v = 0u;
+        s_carry.s = 0;
     }
     __syncthreads();
     for (uint32_t t0 = 0; t0 < ntiles; t0 += SCAN_THREADS) {
@@ -857,10 +919,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) entropy_scan_tiles_kernel(Entrop
         SegVal e;
         e.f = 0;
         e.v = 0;
+        e.s = 0;
         if (t < ntiles) {
             const uint2 r = a.scan_tiles[t];
             e.f = r.x;
             e.v = r.y;
+            e.s = a.scan_tiles_dcs[t];
         }
         SegVal agg;
         const SegVal incl = seg_combine(s_carry, block_seg_scan(e, s_w, agg));
@@ -869,6 +933,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) entropy_scan_tiles_kernel(Entrop
         if (t < ntiles) {
             const SegVal ex = threadIdx.x == 0 ? s_carry : s_incl[threadIdx.x - 1];
             a.scan_tiles[t] = make_uint2(ex.f, ex.v);
+            a.scan_tiles_dcs[t] = ex.s;
             if (t + 1u == ntiles) {
                 a.meta->final_slot = incl.v;
                 if (incl.v < a.g.total_blocks * 64u)
@@ -902,12 +967,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) entropy_scan_apply_kernel(Entrop
     SegVal carry;
     carry.f = c.x;
     carry.v = c.y;
+    carry.s = a.scan_tiles_dcs[blockIdx.x];
     incl = seg_combine(carry, incl);
-    // incl = absolute slot at the END of subsequence i == entry of subsequence i+1
-    if (i + 1u < nsub)
+    // incl = absolute slot (and DC predictor values) at the END of subsequence i == entry of subsequence i+1
+    if (i + 1u < nsub) {
         a.start_slot[i + 1u] = incl.v;
-    if (i == 0u)
+        a.dcpre[i + 1u] = incl.s;
+    }
+    if (i == 0u) {
         a.start_slot[0] = 0u;
+        a.dcpre[0] = 0;
+    }
     s_incl[threadIdx.x] = incl;
     __syncthreads();
     if (i >= nsub)
@@ -1106,6 +1176,61 @@ __global__ void __launch_bounds__(WRITE_THREADS) entropy_write_kernel(EntropyArg
     }
     if (st)
         atomicOr(&a.meta->status, st);
+}
+
+// ---- fallback DC prediction -----------------------------------------------------------------------------
+// Only behind the Huffman final pass (degenerate tables, KPEG_NO_RECORDS=1): MCU.cpp:107-108 over the DC differences
+// entropy_write left, one CTA per restart segment (or image), 256 MCUs per step.  The record path needs none of this:
+// its predictors come out of the offset scan.
+__global__ void __launch_bounds__(256) dc_integrate_kernel(JobGeom g, const int16_t *dcdiff, int16_t *dc)
+{
+    __shared__ int s_w[8][3];
+    __shared__ int s_carry[3];
+    const uint32_t seg = blockIdx.x, img = seg / g.segs_per_image, r = seg - img * g.segs_per_image;
+    const uint32_t m0 = img * g.mcus_per_image + r * g.restart_interval; // restart_interval == 0: one segment per image
+    const uint32_t m1 = min(img * g.mcus_per_image + (g.restart_interval ? (r + 1u) * g.restart_interval : g.mcus_per_image),
+                            (img + 1u) * g.mcus_per_image);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 3)
+        s_carry[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t mb = m0; mb < m1; mb += 256u) {
+        const uint32_t m = mb + threadIdx.x;
+        int v[3] = {0, 0, 0};
+        if (m < m1)
+            for (uint32_t c = 0; c < g.ncomp; ++c)
+                v[c] = dcdiff[m * g.ncomp + c];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int o = __shfl_up_sync(0xffffffffu, v[c], d);
+                if (lane >= d)
+                    v[c] += o;
+            }
+        if (lane == 31)
+            for (int c = 0; c < 3; ++c)
+                s_w[warp][c] = v[c];
+        __syncthreads();
+        int before[3] = {s_carry[0], s_carry[1], s_carry[2]};
+        for (int w = 0; w < warp; ++w)
+            for (int c = 0; c < 3; ++c)
+                before[c] += s_w[w][c];
+        if (m < m1)
+            for (uint32_t c = 0; c < g.ncomp; ++c)
+                dc[m * g.ncomp + c] = (int16_t)(v[c] + before[c]);
+        __syncthreads();
+        if (threadIdx.x == 255)
+            for (int c = 0; c < 3; ++c)
+                s_carry[c] = v[c] + before[c];
+        __syncthreads();
+    }
+}
+
+void launch_dc_integrate(const JobGeom &g, const int16_t *dcdiff, int16_t *dc, cudaStream_t s, uint32_t *launches)
+{
+    dc_integrate_kernel<<<g.nseg, 256, 0, s>>>(g, dcdiff, dc);
+    ++*launches;
 }
 
 static uint32_t ilog2(uint32_t v)

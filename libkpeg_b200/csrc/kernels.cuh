@@ -58,6 +58,9 @@ struct EntropyArgs {
     uint32_t *seg_hint;   // [nsub_max]
     uint32_t *start_slot; // [nsub_max] absolute slot at the entry of subsequence i
     uint2 *scan_tiles;    // [ceil(nsub_max / 1024)] per-tile aggregates / carries of the offset scan
+    long long *scan_tiles_dcs; // the same for the packed DC sums
+    long long *dcs;       // [nsub_max] packed sums of the DC differences each subsequence decoded (entropy_core.h, dcs_unpack)
+    long long *dcpre;     // [nsub_max] ... scanned: the DC predictor values at the entry of every subsequence
     uint32_t *rec;        // symbol records, [group of 32 subsequences][rec_kmax][32] (nullptr = records off)
     uint32_t *nrec;       // [nsub_max] records per subsequence | (private area index + 1) << 10
     uint32_t *rec_alt;    // [rec_alt_cap][rec_kmax] private record areas of subsequences redone in sparse rounds
@@ -85,9 +88,9 @@ struct IdctArgs {
     const uint32_t *strip_sub;  // [nstrips]
     const int16_t *coef_in;   // fallback input: [total_blocks][64], slot 0 = DC difference
     int16_t *coef_out;        // optional: the strip's coefficients as the reference holds them (DC integrated, F1 applied)
-    unsigned long long *strip_state; // [nstrips] look-back words of the DC prediction
-    uint32_t lb_tag;          // tag of this launch in the look-back words (1 .. 2^14 - 1)
-    uint32_t lb_spin_limit;
+    const long long *dcpre;   // [nsub] packed DC predictor values at the entry of every subsequence (offset scan)
+    const int16_t *dc_in;     // fallback input: [total_blocks] predicted DC values (dc_integrate_kernel)
+    uint32_t nstrips;
     const DeviceTables *tables;
     uint8_t *pixels;          // [nimages][height][width][ncomp]; nullptr with coef_out = coefficients only
     DevMeta *meta;
@@ -99,6 +102,8 @@ void kernels_context_created();   // contexts of this process share the device: 
 void kernels_context_destroyed(); // all of them together must stay co-resident
 void kernels_configure(int max_concurrent_jobs); // jobs (lanes) that may be on the device at the same time // per-device function attributes (call once after cudaSetDevice)
 void launch_write_separators(uint8_t *scan, const uint64_t *ends, uint32_t n, cudaStream_t s); // RSTn after every scan of a packed batch
+void launch_gray_to_rgb(const uint8_t *gray, uint8_t *rgb, size_t npixels, cudaStream_t s);     // PPM payload of a one-component image
+void launch_rgb_to_planar(const uint8_t *rgb, uint8_t *planes, size_t npixels, cudaStream_t s); // [3][H][W] planes
 void launch_unstuff(const UnstuffArgs &a, uint32_t sub_bits, cudaStream_t s, uint32_t *launches);
 void launch_entropy_cold(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint32_t *launches);
@@ -108,6 +113,8 @@ void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint3
 cudaError_t launch_entropy_relay_loop(const EntropyArgs &a, int first, int last, cudaStream_t s, uint32_t *launches);
 void launch_entropy_scan(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);
 void launch_entropy_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);  // Huffman final pass
+// fallback only: DC prediction over the DC differences the Huffman final pass left (dcdiff -> dc), one CTA per restart segment
+void launch_dc_integrate(const JobGeom &g, const int16_t *dcdiff, int16_t *dc, cudaStream_t s, uint32_t *launches);
 cudaError_t launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches);
 void k3_configure();                      // function attributes of the K3 kernels (called by kernels_configure)
 uint32_t k3_strip_slots(uint32_t ncomp);  // coefficient slots one K3 strip covers

@@ -130,7 +130,6 @@ constexpr uint32_t ST_REC_OVERFLOW = 64u;   // a subsequence held more symbols t
 
 constexpr uint32_t ST_RELAY_TIMEOUT = 128u; // the relay loop's grid barrier gave up waiting (grid not co-resident): the host finishes the relay round by round
 
-constexpr uint32_t ST_LOOKBACK_TIMEOUT = 256u; // a K3 strip gave up waiting for its predecessors' DC sums (never seen: strips are dispatched in order)
 
 // Per-subsequence relay state: where the first symbol after the end of the subsequence starts and
 // in which decoder state, plus how many coefficient slots were produced on the way.

@@ -52,6 +52,7 @@ struct Copy {
     void *dst;
     const void *src;
     size_t bytes;
+    int peer = -1; // >= 0: dst is device memory of that device (peer copy), otherwise host memory
 };
 
 // One in-flight job between job_enqueue and job_finish.
@@ -72,8 +73,7 @@ struct Job {
 struct Lane {
     cudaStream_t stream = nullptr;
     DevBuf scan, words, seg_bit, tile_kept, tile_rst, cls, state, work, seg_hint, start_slot, scan_tiles;
-    DevBuf coef, dcdiff, pixels, meta, rec, nrec, rec_alt, strip_sub, strip_state;
-    uint32_t lb_tag = 0; // tag of the last K3 launch in strip_state (the look-back words of another launch read as absent)
+    DevBuf coef, dcdiff, dc, pixels, meta, rec, nrec, rec_alt, strip_sub, dcs, dcpre, scan_tiles_dcs;
     PinBuf h_meta;
     // host-buffer batches: pinned staging of the small scans + the separator positions, and their device copy
     PinBuf h_stage, h_ends;
@@ -285,17 +285,6 @@ int status_to_rc(kpeg_ctx *ctx, uint32_t st)
     return KPEG_ERR_STREAM;
 }
 
-// K3's look-back words carry a 14-bit launch tag instead of being cleared per launch; clear them when the tag wraps
-int next_lb_tag(kpeg_ctx *ctx, Lane &L, uint32_t *tag)
-{
-    if (++L.lb_tag >= (1u << 14)) {
-        CK(cudaMemsetAsync(L.strip_state.p, 0, L.strip_state.cap, L.stream));
-        L.lb_tag = 1;
-    }
-    *tag = L.lb_tag;
-    return KPEG_OK;
-}
-
 // everything downstream of the relay + the result copies + the bookkeeping read-back
 int enqueue_downstream(kpeg_ctx *ctx, Lane &L)
 {
@@ -309,18 +298,25 @@ int enqueue_downstream(kpeg_ctx *ctx, Lane &L)
         const size_t coef_bytes = (size_t)J.g.total_blocks * 128u;
         TRY(ensure(ctx, s, L.coef, coef_bytes + 256));
         TRY(ensure(ctx, s, L.dcdiff, (size_t)J.g.total_blocks * 2u + 16));
+        TRY(ensure(ctx, s, L.dc, (size_t)J.g.total_blocks * 2u + 16));
         J.ea.coef = (int16_t *)L.coef.p;
         J.ea.dcdiff = (int16_t *)L.dcdiff.p;
         J.ia.rec = nullptr;
         J.ia.coef_in = (const int16_t *)L.coef.p;
+        J.ia.dc_in = (const int16_t *)L.dc.p;
         launch_entropy_write(J.ea, s, &J.launches);
         mark(ctx, L, KPEG_T_ENTROPY_WRITE);
+        launch_dc_integrate(J.g, (const int16_t *)L.dcdiff.p, (int16_t *)L.dc.p, s, &J.launches);
+        mark(ctx, L, KPEG_T_DC_SCAN);
     }
-    TRY(next_lb_tag(ctx, L, &J.ia.lb_tag));
     CK(launch_idct(J.ia, s, &J.launches));
     mark(ctx, L, KPEG_T_IDCT);
-    for (const Copy &c : J.d2h)
-        CK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, s));
+    for (const Copy &c : J.d2h) {
+        if (c.peer >= 0)
+            CK(cudaMemcpyPeerAsync(c.dst, c.peer, c.src, ctx->device, c.bytes, s));
+        else
+            CK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, s));
+    }
     if (!J.d2h.empty())
         mark(ctx, L, KPEG_T_D2H);
     CK(cudaMemcpyAsync(L.h_meta.p, L.meta.p, sizeof(DevMeta), cudaMemcpyDeviceToHost, s));
@@ -381,14 +377,9 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     TRY(ensure(ctx, s, L.start_slot, (size_t)nsub_max * 4u));
     TRY(ensure(ctx, s, L.scan_tiles, ((size_t)nsub_max / 1024u + 2u) * sizeof(uint2)));
     TRY(ensure(ctx, s, L.strip_sub, ((size_t)nstrips + 1u) * sizeof(uint32_t)));
-    {
-        const void *before = L.strip_state.p;
-        TRY(ensure(ctx, s, L.strip_state, ((size_t)nstrips + 1u) * sizeof(unsigned long long)));
-        if (L.strip_state.p != before) { // fresh memory: no word may look like one of a launch to come
-            CK(cudaMemsetAsync(L.strip_state.p, 0, L.strip_state.cap, s));
-            L.lb_tag = 0;
-        }
-    }
+    TRY(ensure(ctx, s, L.dcs, (size_t)nsub_max * sizeof(long long)));
+    TRY(ensure(ctx, s, L.dcpre, (size_t)nsub_max * sizeof(long long)));
+    TRY(ensure(ctx, s, L.scan_tiles_dcs, ((size_t)nsub_max / 1024u + 2u) * sizeof(long long)));
     TRY(ensure(ctx, s, L.meta, sizeof(DevMeta)));
     TRY(ensure_pinned(ctx, s, L.h_meta, sizeof(DevMeta)));
     // records: one per value-carrying symbol.  3/8 of the subsequence's bits covers every table whose value-carrying
@@ -438,6 +429,9 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     ea.seg_hint = (uint32_t *)L.seg_hint.p;
     ea.start_slot = (uint32_t *)L.start_slot.p;
     ea.scan_tiles = (uint2 *)L.scan_tiles.p;
+    ea.scan_tiles_dcs = (long long *)L.scan_tiles_dcs.p;
+    ea.dcs = (long long *)L.dcs.p;
+    ea.dcpre = (long long *)L.dcpre.p;
     ea.rec = J.use_records ? (uint32_t *)L.rec.p : nullptr;
     ea.nrec = (uint32_t *)L.nrec.p;
     ea.rec_kmax = rec_kmax;
@@ -460,9 +454,9 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     ia.strip_sub = ea.strip_sub;
     ia.coef_in = nullptr;
     ia.coef_out = nullptr;
-    ia.strip_state = (unsigned long long *)L.strip_state.p;
-    ia.lb_tag = 0;
-    ia.lb_spin_limit = 0;
+    ia.dcpre = ea.dcpre;
+    ia.dc_in = nullptr;
+    ia.nstrips = nstrips;
     ia.tables = (const DeviceTables *)ctx->tables.p;
     ia.pixels = d_pixels;
     ia.meta = d_meta;
@@ -499,7 +493,7 @@ int check_guards(kpeg_ctx *ctx, Lane &L)
     NamedBuf bufs[] = {{"cls", &L.cls},           {"scan", &L.scan},         {"words", &L.words},       {"seg_bit", &L.seg_bit},
                        {"tile_kept", &L.tile_kept}, {"tile_rst", &L.tile_rst}, {"state", &L.state},       {"work", &L.work},
                        {"seg_hint", &L.seg_hint}, {"start_slot", &L.start_slot}, {"scan_tiles", &L.scan_tiles},
-                       {"coef", &L.coef},         {"dcdiff", &L.dcdiff},     {"strip_sub", &L.strip_sub}, {"strip_state", &L.strip_state},
+                       {"coef", &L.coef},         {"dcdiff", &L.dcdiff},     {"strip_sub", &L.strip_sub}, {"dc", &L.dc}, {"dcs", &L.dcs}, {"dcpre", &L.dcpre}, {"scan_tiles_dcs", &L.scan_tiles_dcs}, {"d_ends", &L.d_ends},
                        {"pixels", &L.pixels},     {"meta", &L.meta},
                        {"rec", &L.rec},           {"nrec", &L.nrec},         {"rec_alt", &L.rec_alt},   {"tables", &ctx->tables}};
     uint8_t host[2 * GUARD_BYTES];
@@ -602,8 +596,6 @@ int job_finish(kpeg_ctx *ctx, int li, kpeg_stats *stats)
         stats->kernel_launches += J.launches;
         add_times(ctx, L, stats);
     }
-    if (h_meta->status & ST_LOOKBACK_TIMEOUT)
-        return fail(ctx, KPEG_ERR_CUDA, "K3: a strip's DC look-back timed out (strips were not dispatched in order?)");
     return status_to_rc(ctx, h_meta->status & ~(ST_REC_OVERFLOW | ST_RELAY_TIMEOUT));
 }
 
@@ -706,7 +698,7 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
             cudaStreamSynchronize(L.stream);
         DevBuf *bufs[] = {&L.cls,  &L.scan, &L.words,    &L.seg_bit,    &L.tile_kept,  &L.tile_rst, &L.state,
                           &L.work, &L.seg_hint, &L.start_slot, &L.scan_tiles, &L.coef,     &L.dcdiff,
-                          &L.strip_sub, &L.strip_state, &L.pixels, &L.meta,
+                          &L.strip_sub, &L.dc, &L.dcs, &L.dcpre, &L.scan_tiles_dcs, &L.pixels, &L.meta,
                           &L.rec,  &L.nrec,       &L.rec_alt};
         for (DevBuf *b : bufs)
             dev_free(*b);
@@ -766,11 +758,28 @@ extern "C" void *kpeg_cuda_stream(kpeg_ctx *ctx) { return ctx ? (void *)ctx->lan
 extern "C" void *kpeg_cuda_host_alloc(size_t bytes)
 {
     void *p = nullptr;
-    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { // pinned for every device's context
         cudaGetLastError();
         return nullptr;
     }
     return p;
+}
+
+extern "C" int kpeg_cuda_host_register(void *p, size_t bytes)
+{
+    if (!p || !bytes)
+        return KPEG_ERR_ARG;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return KPEG_ERR_CUDA;
+    }
+    return KPEG_OK;
+}
+
+extern "C" void kpeg_cuda_host_unregister(void *p)
+{
+    if (p && cudaHostUnregister(p) != cudaSuccess)
+        cudaGetLastError();
 }
 
 extern "C" void kpeg_cuda_host_free(void *p)
@@ -1125,6 +1134,103 @@ extern "C" int kpeg_cuda_decode_batch(kpeg_ctx *ctx, const kpeg_plan *plan, int 
     return rc;
 }
 
+// One band of a tiled decode whose frame lives on another GPU: decode here, then one peer copy of the band's rows
+// (NVLink where peer access exists, staged by the driver otherwise).  With dst_device == this context's device the
+// kernels write straight into the frame.
+extern "C" int kpeg_cuda_decode_to_peer(kpeg_ctx *ctx, const kpeg_plan *plan, const uint8_t *scan, size_t scan_len, int dst_device,
+                                        uint8_t *d_dst, kpeg_stats *stats)
+{
+    if (!ctx || !plan || !scan || !d_dst || dst_device < 0)
+        return KPEG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    zero_stats(stats);
+    Lane &L = ctx->lane[0];
+    if (L.job.active)
+        finish_deferred(ctx, 0);
+    const size_t npix = (size_t)plan->width * plan->height * plan->ncomp;
+    const bool local = dst_device == ctx->device && (reinterpret_cast<uintptr_t>(d_dst) & 7u) == 0;
+    TRY(ensure(ctx, L.stream, L.scan, scan_len + 64));
+    if (!local) {
+        TRY(ensure(ctx, L.stream, L.pixels, npix + 64));
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, ctx->device, dst_device) == cudaSuccess && can) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(dst_device, 0);
+            if (e != cudaSuccess) // already enabled is fine; anything else leaves the staged path
+                cudaGetLastError();
+        } else {
+            cudaGetLastError();
+        }
+    }
+    mark(ctx, L, -1);
+    CK(cudaMemcpyAsync(L.scan.p, scan, scan_len, cudaMemcpyHostToDevice, L.stream));
+    mark(ctx, L, KPEG_T_H2D);
+    std::vector<Copy> out;
+    if (!local) {
+        Copy c{d_dst, L.pixels.p, npix};
+        c.peer = dst_device;
+        out.push_back(c);
+    }
+    TRY(job_enqueue(ctx, 0, plan, (const uint8_t *)L.scan.p, scan_len, 1, local ? d_dst : (uint8_t *)L.pixels.p, std::move(out)));
+    return job_finish(ctx, 0, stats);
+}
+
+// GPU-side PPM writer: the bytes Image::dumpRawData puts into <name>.ppm (reference src/Image.cpp:108-140: the P6
+// header of Image.cpp:124-127, then the R,G,B rows) assembled in device memory, so a consumer that stores or ships the
+// file from the GPU never sees a separate header/payload pair.  The payload is written by K3 itself; only the header
+// (about a hundred bytes) is copied in.  The file occupies d_out[*ppm_off, *ppm_off + *ppm_len): the offset (< 16)
+// keeps the payload 16-byte aligned for K3's vector stores.  One-component images are expanded to R = G = B
+// (SURVEY A.8), as kpeg::JPEGDecoder::dumpRawData does on the host.
+extern "C" int kpeg_cuda_decode_ppm_device(kpeg_ctx *ctx, const kpeg_plan *plan, const uint8_t *d_scan, size_t scan_len,
+                                           uint8_t *d_out, size_t cap, size_t *ppm_off, size_t *ppm_len, kpeg_stats *stats)
+{
+    if (!ctx || !plan || !d_scan || !d_out || !ppm_off || !ppm_len)
+        return KPEG_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(d_out) & 15u)
+        return fail(ctx, KPEG_ERR_ARG, "PPM buffer must be 16-byte aligned");
+    CK(cudaSetDevice(ctx->device));
+    zero_stats(stats);
+    Lane &L = ctx->lane[0];
+    if (L.job.active)
+        finish_deferred(ctx, 0);
+    char header[160];
+    const int hl = kpeg_ppm_header(plan->width, plan->height, header, sizeof header);
+    const size_t pad = (16u - (size_t)hl % 16u) % 16u;
+    const size_t npx = (size_t)plan->width * plan->height;
+    if (pad + (size_t)hl + npx * 3u > cap)
+        return fail(ctx, KPEG_ERR_ARG, "PPM buffer too small");
+    TRY(ensure_pinned(ctx, L.stream, L.h_stage, 256));
+    memcpy(L.h_stage.p, header, (size_t)hl);
+    uint8_t *payload = d_out + pad + (size_t)hl;
+    uint8_t *k3_out = payload;
+    if (plan->ncomp == 1) {
+        TRY(ensure(ctx, L.stream, L.pixels, npx + 64));
+        k3_out = (uint8_t *)L.pixels.p;
+    }
+    mark(ctx, L, -1);
+    CK(cudaMemcpyAsync(d_out + pad, L.h_stage.p, (size_t)hl, cudaMemcpyHostToDevice, L.stream));
+    TRY(job_enqueue(ctx, 0, plan, d_scan, scan_len, 1, k3_out, {}));
+    if (plan->ncomp == 1)
+        launch_gray_to_rgb((const uint8_t *)L.pixels.p, payload, npx, L.stream);
+    *ppm_off = pad;
+    *ppm_len = (size_t)hl + npx * 3u;
+    return job_finish(ctx, 0, stats);
+}
+
+// Planar writer: interleaved R,G,B rows (K3's output) -> three planes [3][H][W] in device memory.
+extern "C" int kpeg_cuda_interleaved_to_planar(kpeg_ctx *ctx, const uint8_t *d_rgb, uint8_t *d_planes, size_t npixels)
+{
+    if (!ctx || !d_rgb || !d_planes)
+        return KPEG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    Lane &L = ctx->lane[0];
+    if (L.job.active)
+        finish_deferred(ctx, 0);
+    launch_rgb_to_planar(d_rgb, d_planes, npixels, L.stream);
+    CK(cudaStreamSynchronize(L.stream));
+    CK(cudaGetLastError());
+    return KPEG_OK;
+}
+
 extern "C" int kpeg_cuda_decode_file(kpeg_ctx *ctx, const uint8_t *file, size_t len, uint32_t flags, uint8_t *pixels_out,
                                      size_t cap, kpeg_plan *plan_out, kpeg_stats *stats)
 {
@@ -1163,7 +1269,6 @@ extern "C" int kpeg_cuda_read_coefficients(kpeg_ctx *ctx, int16_t *out, size_t c
     IdctArgs ia = L.job.ia;
     ia.coef_out = (int16_t *)ctx->merged.p;
     ia.pixels = nullptr;
-    TRY(next_lb_tag(ctx, L, &ia.lb_tag));
     uint32_t launches = 0;
     CK(launch_idct(ia, L.stream, &launches));
     CK(cudaMemcpyAsync(out, ctx->merged.p, n * 2u, cudaMemcpyDeviceToHost, L.stream));

@@ -177,6 +177,7 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
     // then K3's expansion (k3_fused.cu stage B): every record is dropped at (entry block of its subsequence) * 64 +
     // position, no running state.  Must reproduce the Huffman final pass: coefficients, DC differences and verdict.
     uint32_t records_ok = 1;
+    std::vector<int16_t> dc2; // DC values as K3 derives them (scan-based predictors); empty = not computed
     {
         struct HostRecorder {
             std::vector<uint32_t> *v;
@@ -185,6 +186,8 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
         std::vector<int16_t> coef2((size_t)g.total_blocks * 64, 0);
         const uint32_t total_slots = g.total_blocks * 64u;
         uint32_t st2 = 0, max_rec = 0;
+        std::vector<long long> dcs(nsub, 0), dcpre(nsub, 0); // K2 as a scan: per-subsequence DC sums and their segmented prefix
+        std::vector<std::vector<uint32_t>> all_recs(nsub);
         for (uint32_t sub = 0; sub < nsub; ++sub) {
             uint32_t p = 0, c = 0, z = 0;
             if (sub) {
@@ -196,8 +199,10 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
             DecState d;
             dec_init(d, PW, S, p, c, z, hint[sub], 0);
             const uint32_t end = std::min((sub + 1) * sub_bits, total_bits);
-            relay_run<true>(d, PW, PL, S, g, end, HostRecorder{&recs});
+            relay_run<true, true>(d, PW, PL, S, g, end, HostRecorder{&recs});
             const SubState out = relay_exit_state(d);
+            dcs[sub] = d.dcs;
+            all_recs[sub] = recs;
             if (d.nrec != recs.size())
                 records_ok = 0;
             // the emitting decode ends in the state (and slot count) the relay's fixed point holds
@@ -222,6 +227,54 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
         }
         if (final_slot < total_slots)
             st2 |= ST_SEG_MISMATCH;
+        // entropy_scan_*: segmented prefix of the DC sums (reset wherever a subsequence crossed a boundary)
+        {
+            long long run = 0;
+            for (uint32_t i = 0; i < nsub; ++i) {
+                dcpre[i] = run;
+                run = X[i].seg >= 0 ? dcs[i] : run + dcs[i];
+            }
+        }
+        // K3 stages B/C (k3_fused.cu): the DC predictors entering every strip of 32 MCUs, from dcpre[] and the records of
+        // the subsequence the strip's first slot lies in; then the segmented scan inside the strip.  Must give the
+        // values the plain sequential prediction (K2 below) gives.
+        if (status == 0 && st2 == 0) {
+            dc2.assign(g.total_blocks, 0);
+            const uint32_t nc = g.ncomp, total_mcus = g.nimages * g.mcus_per_image;
+            const uint32_t sps = 32u * nc * 64u, nstrips = (total_mcus + 31u) / 32u;
+            std::vector<uint32_t> strip_sub(nstrips, 0); // entropy_scan_apply_kernel: subsequence whose [begin, end) holds the strip's first slot
+            for (uint32_t i = 0; i < nsub; ++i) {
+                const uint32_t b = start[i], e = i + 1 < nsub ? start[i + 1] : final_slot;
+                for (uint32_t s0i = (b + sps - 1u) / sps; e > b && s0i < nstrips && s0i * sps < e; ++s0i)
+                    strip_sub[s0i] = i;
+            }
+            for (uint32_t strip = 0; strip < nstrips; ++strip) {
+                const uint32_t mcu0 = strip * 32u, s0 = mcu0 * nc * 64u, first0 = strip_sub[strip];
+                const uint32_t img = mcu0 / g.mcus_per_image, mi = mcu0 % g.mcus_per_image;
+                const uint32_t mreset = g.restart_interval ? mi - mi % g.restart_interval : 0u;
+                const uint32_t reset_slot = (img * g.mcus_per_image + mreset) * nc * 64u;
+                const uint32_t ss = start[first0];
+                int carry[3] = {0, 0, 0};
+                if (ss >= reset_slot && reset_slot < s0)
+                    dcs_unpack(dcpre[first0], carry);
+                if (ss < s0 && reset_slot < s0)
+                    for (uint32_t r : all_recs[first0]) {
+                        const uint32_t at = (ss & ~63u) + record_pos(r);
+                        if ((at & 63u) == 0u && at < s0 && at >= reset_slot)
+                            carry[(at >> 6) % nc] += record_value(r);
+                    }
+                int pred[3] = {carry[0], carry[1], carry[2]};
+                for (uint32_t m = mcu0; m < std::min(mcu0 + 32u, total_mcus); ++m) {
+                    const uint32_t mm = m % g.mcus_per_image;
+                    if (g.restart_interval ? (mm % g.restart_interval) == 0 : mm == 0)
+                        pred[0] = pred[1] = pred[2] = 0;
+                    for (uint32_t c = 0; c < nc; ++c) {
+                        pred[c] += coef2[((size_t)m * nc + c) * 64];
+                        dc2[m * nc + c] = (int16_t)pred[c];
+                    }
+                }
+            }
+        }
         // the Huffman final pass keeps DC differences apart; the records put them into slot 0 of their blocks
         std::vector<int16_t> coef1 = coef;
         for (uint32_t b = 0; b < g.total_blocks; ++b)
@@ -248,6 +301,8 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
             }
         }
     }
+    if (status == 0 && !dc2.empty() && dc2 != dc)
+        records_ok = 0; // the scan-based predictors differ from the sequential prediction
     // merged coefficients (what kpeg_cuda_read_coefficients returns)
     std::vector<int16_t> merged((size_t)g.total_blocks * 64);
     for (uint32_t b = 0; b < g.total_blocks; ++b) {
