@@ -1,28 +1,15 @@
-// k3_fused.cu -- K2 + K3 of the B200 decode path as ONE sm_100a kernel: record expansion, DC prediction,
-// dequantisation, de-zigzag, 8x8 IDCT, level shift, YCbCr->RGB and the interleaved store.
+// k3_fused.cu -- K3 of the B200 decode path as ONE sm_100a kernel: dequantisation, de-zigzag, 8x8 IDCT, level shift,
+// YCbCr->RGB and the interleaved store, with the exact re-evaluation of the samples near a rounding tie in the same kernel.
 //
-// What it replaces in the reference: MCU::constructMCU (run-length expansion with the DC-difference quirk, DC
-// prediction, dequantisation, de-zigzag: src/MCU.cpp:93-120), MCU::computeIDCT (:172-216), performLevelShift
-// (:218-245), convertYCbCrToRGB (:247-279) and Image::createImageFromMCUs (src/Image.cpp:51-70).
+// What it replaces in the reference: the dequantisation and de-zigzag of MCU::constructMCU (src/MCU.cpp:110-120),
+// MCU::computeIDCT (:172-216), performLevelShift (:218-245), convertYCbCrToRGB (:247-279) and
+// Image::createImageFromMCUs (src/Image.cpp:51-70).
 //
-// One CTA reconstructs a strip of IDCT_MCUS_PER_CTA consecutive MCUs.  The quantised coefficients of the strip
-// exist only in shared memory: the relay pass of K1 (kernels.cu) left one self-contained record per non-zero
-// coefficient, and the strip gathers its own (stage B below), so no coefficient buffer ever travels through HBM.
+// One CTA reconstructs a strip of IDCT_MCUS_PER_CTA consecutive MCUs from the strip's coefficient tile, which K2
+// (k2_expand.cu) left in global memory as the image of this kernel's shared-memory tile (kernels.cuh).
 //
-//   stage A  zero the strip's coefficient tile (16-bit, biased by COEF_BIAS, 128-byte blocks with a 16-byte-chunk
-//            swizzle so that stage 1's per-thread 128-byte reads are bank-conflict free); the copy engine fetches
-//            the quantiser tables (cp.async.bulk + mbarrier)
-//   stage B  expansion: the subsequences that intersect the strip are known from the offset scan (strip_sub[] and
-//            start_slot[]); every record is (position, value), so the warps share the records k-major -- warp w takes
-//            records w, w + NW, ... of 32 subsequences at a time, a coalesced 128-byte line per record index -- and
-//            drop the values into the tile.  (Fallback: the tile is copied from a coefficient matrix the Huffman
-//            final pass wrote.)
-//   stage C  DC prediction (MCU.cpp:107-108): the DC differences sit in slot 0 of their blocks; a segmented warp scan
-//            over the strip's MCUs (reset at restart intervals / image starts) gives the values relative to the strip.
-//            The predictor values entering the strip come from K1: the offset scan left the predictors at the entry of
-//            every subsequence (a device-wide segmented scan of the per-subsequence DC sums), and the strip adds the DC
-//            differences between the entry of the subsequence its first slot lies in and that slot.  Strips do not
-//            depend on one another: no ordering assumption, nothing to wait for
+//   stage 0  by the copy engine: the tile (12 KB for RGB) and the quantiser table arrive with bulk copies
+//            (cp.async.bulk + mbarrier, SASS UBLKCP); the tile that will run in this CTA's slot next is pulled into L2
 //   stage 1  one thread = one 8x8 block, all 64 values in registers, two fp32 lanes per instruction (FADD2 / FMUL2 /
 //            FFMA2): biased 16-bit -> fp32 by byte permute + one packed subtract (no I2F), dequantise (AAN prescale
 //            folded into the quantiser), de-zigzag by register renaming, separable fp32 IDCT, rounding, tie-band test;
@@ -78,15 +65,10 @@ __device__ __forceinline__ int tie_sample(int w, int b)
     return (4 * w + (k >> 2)) * 8 + ((b & 16) ? 0 : 4) + (k & 3);
 }
 
-#ifndef KPEG_EXPAND_BATCH
-#define KPEG_EXPAND_BATCH 8
+#ifndef KPEG_IDCT_PREFETCH_AHEAD
+#define KPEG_IDCT_PREFETCH_AHEAD 1184
 #endif
-constexpr int EXPAND_BATCH = KPEG_EXPAND_BATCH; // record loads in flight per lane in the expansion stage
-#ifndef KPEG_EXPAND_PREFETCH_AHEAD
-#define KPEG_EXPAND_PREFETCH_AHEAD 1024
-#endif
-constexpr uint32_t EXPAND_PREFETCH_AHEAD = KPEG_EXPAND_PREFETCH_AHEAD; // strips ahead whose record lines are pulled into L2
-constexpr int EXPAND_PREFETCH_LINES = 112;                            // record indices per group of 32 subsequences
+constexpr uint32_t IDCT_PREFETCH_AHEAD = KPEG_IDCT_PREFETCH_AHEAD; // strips: 148 SMs x 8 CTAs, the strip that runs in this CTA's slot next
 
 constexpr int TIE_LIST_CAP = 160; // (block, sample) entries per strip; a strip with more walks its blocks' masks instead
 
@@ -97,14 +79,11 @@ struct IdctSmem {
     uint4 coef[NB * 8];           // [block][chunk ^ (block & 7)]: eight biased 16-bit coefficients per chunk, zig-zag order
     uint2 samp[NC * 8 * 2 * NM];  // [comp][row][half][mcu] -> four rounded, unshifted samples, biased 16-bit
     float2 qpair[NC][32];         // prescaled quantisers in the pair order of the transform (pair_nat)
-    float2 qdc[NC][32];           // the same with every AC entry zero: what a block that loses its AC terms (F1) multiplies by
     uint16_t ties[TIE_LIST_CAP];  // block in strip | sample << 7
     uint8_t flag[NB];             // per block: BLK_*
-    int32_t carry[4];             // DC: predictor values entering the strip
-    uint32_t reset_slot;          // DC: slot of the last predictor restart at or before the strip's first MCU
     uint32_t ntie, any_huge;
     uint32_t img0, by0, bx0, mi0; // image / block row / block column / MCU-in-image of the strip's first MCU
-    unsigned long long mbar;      // completion barrier of the stage-A bulk copies
+    unsigned long long mbar;      // completion barrier of the stage-0 bulk copies
 };
 // eight strips per SM: 228 KB of shared memory, 1 KB of each CTA's share taken by the driver
 static_assert(sizeof(IdctSmem<3>) <= (233472 / 8 - 1024), "idct_kernel<3> no longer fits eight CTAs per SM");
@@ -478,16 +457,12 @@ __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v)
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
 }
 
-// byte offset inside the tile of coefficient slot `off` (block * 64 + zig-zag index): chunk (zz >> 3) ^ (block & 7)
-__device__ __forceinline__ uint32_t tile_byte(uint32_t off) { return (off * 2u) ^ ((off >> 2) & 0x70u); }
-
 template <int NC>
 __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MIN_CTAS : 16) idct_kernel(IdctArgs a)
 {
     constexpr int NM = IDCT_MCUS_PER_CTA;
     constexpr int NB = NM * NC;
-    constexpr uint32_t TILE_SLOTS = NB * 64u;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     IdctSmem<NC> &sm = *reinterpret_cast<IdctSmem<NC> *>(smem_raw);
 
     const int t = threadIdx.x;
@@ -498,17 +473,20 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
     const uint32_t strip = blockIdx.x;
     const uint32_t mcu0 = strip * NM;
     const uint32_t m = mcu0 + ml;
-    const uint32_t blk0 = mcu0 * NC;
     const bool active = m < total_mcus;
 
-    // ---- stage A: quantisers by the copy engine, strip origin, empty tile -------------------------------
+    // ---- stage 0: tile and quantisers by the copy engine, strip origin ------------------------------------------
     const uint32_t bar = smem_u32(&sm.mbar);
     if (t == 0) {
-        constexpr uint32_t table_bytes = NC * 64u * 4u;
+        constexpr uint32_t table_bytes = NC * 64u * 4u, tile_bytes = NB * 128u;
+        const char *tile = reinterpret_cast<const char *>(a.tiles) + (size_t)strip * tile_bytes;
         mbar_init(bar, 1);
-        mbar_expect_tx(bar, 2u * table_bytes);
+        mbar_expect_tx(bar, table_bytes + tile_bytes);
+        bulk_load(smem_u32(sm.coef), tile, tile_bytes, bar);
         bulk_load(smem_u32(sm.qpair), a.tables->qpair, table_bytes, bar);
-        bulk_load(smem_u32(sm.qdc), a.tables->qdc, table_bytes, bar);
+        // the tile of the strip that will run in this CTA's slot next: DRAM -> L2 now
+        if (strip + IDCT_PREFETCH_AHEAD < a.nstrips)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(tile + (size_t)IDCT_PREFETCH_AHEAD * tile_bytes), "r"(tile_bytes) : "memory");
         sm.ntie = 0;
         sm.any_huge = 0;
         const uint32_t img = mcu0 / a.g.mcus_per_image, mi = mcu0 - img * a.g.mcus_per_image;
@@ -516,166 +494,9 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
         sm.mi0 = mi;
         sm.by0 = mi / a.g.mcus_x;
         sm.bx0 = mi - sm.by0 * a.g.mcus_x;
-        // predictors restart at every restart interval and image (T.81 F.2.1.3.1)
-        const uint32_t mreset = a.g.restart_interval ? mi - mi % a.g.restart_interval : 0u;
-        sm.reset_slot = (img * a.g.mcus_per_image + mreset) * (uint32_t)NC * 64u;
-        sm.carry[0] = sm.carry[1] = sm.carry[2] = 0;
+        mbar_wait(bar, 0); // the barrier below hands the data on
     }
-    const uint32_t tile_addr = smem_u32(sm.coef);
-    if (a.coef_in == nullptr) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            sm.coef[i * NB + t] = make_uint4(BIAS2, BIAS2, BIAS2, BIAS2);
-        __syncthreads();
-
-        // ---- stage B: expansion of the records that fall into the strip ---------------------------------
-        const uint32_t nsub = a.meta->nsub;
-        const uint32_t s0 = blk0 * 64u; // first slot of the strip; slots are < 2^32 (host_tables.h)
-        const uint32_t lane = (uint32_t)ml;
-        const uint32_t first0 = min(__ldg(a.strip_sub + strip), nsub - 1u);
-        {
-            // the record lines a strip that starts about one CTA lifetime from now will read: DRAM -> L2 now, so its
-            // batches below wait for L2, not for DRAM.  (Which strip that is need not be exact.)
-            const uint32_t ahead = strip + EXPAND_PREFETCH_AHEAD;
-            if (ahead < a.nstrips) {
-                const uint32_t fs = min(__ldg(a.strip_sub + ahead), nsub - 1u);
-                const char *g0 = reinterpret_cast<const char *>(a.rec + ((size_t)(fs >> 5) * a.rec_kmax) * 32u);
-                const uint32_t lines = min(a.rec_kmax, (uint32_t)EXPAND_PREFETCH_LINES);
-                for (uint32_t k = (uint32_t)t; k < 2u * lines; k += (uint32_t)NB) {
-                    const uint32_t grp = k >= lines ? 1u : 0u; // the strip's subsequences usually straddle two groups of 32
-                    const char *ptr = g0 + ((size_t)grp * a.rec_kmax + (k - grp * lines)) * 128u;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-                }
-            }
-        }
-        uint32_t first = first0;
-        for (int chunk = 0; chunk < 128; ++chunk, first += 32u) { // a strip meets at most ~3 100 subsequences
-            const uint32_t sub = first + lane;
-            bool act = sub < nsub;
-            const uint32_t ss = act ? __ldg(a.start_slot + sub) : 0xFFFFFFFFu;
-            // the first subsequence begins at or before the strip's first slot, the others inside the strip -- or beyond it
-            act = act && (ss <= s0 || ss - s0 < TILE_SLOTS);
-            uint32_t n = 0, stride = 128u;
-            const uint32_t *base = a.rec;
-            if (act) {
-                const uint32_t nr = __ldg(a.nrec + sub);
-                n = min(nr & 1023u, a.rec_kmax);
-                if (nr >> 10) { // redone in a sparse relay round: private contiguous area
-                    base = a.rec_alt + (size_t)((nr >> 10) - 1u) * a.rec_kmax;
-                    stride = 4u;
-                } else {
-                    base = a.rec + ((size_t)(sub >> 5) * a.rec_kmax) * 32u + (sub & 31u);
-                }
-            }
-            // slot of record position 0 relative to the tile (may be "negative"); lanes without a subsequence get an
-            // offset that keeps the out-of-range marker of the batched loads below out of range
-            const uint32_t off0 = act ? (ss & ~63u) - s0 : TILE_SLOTS;
-            const uint32_t nmax = __reduce_max_sync(0xffffffffu, n);
-            // The loads of a batch are all issued before the first value is used: the expansion is a chain of DRAM
-            // round trips otherwise (one per record index; measured: 60 % of the kernel's stall samples).  A record index
-            // beyond the lane's count reads as position 0xFFFF, which falls outside every tile.
-            const char *bp = reinterpret_cast<const char *>(base) + (size_t)((uint32_t)comp * EXPAND_BATCH) * stride;
-            const size_t step = (size_t)(NC * EXPAND_BATCH) * stride;
-            for (uint32_t k0 = (uint32_t)comp * EXPAND_BATCH; k0 < nmax; k0 += NC * EXPAND_BATCH, bp += step) {
-                uint32_t r[EXPAND_BATCH];
-#pragma unroll
-                for (int u = 0; u < EXPAND_BATCH; ++u)
-                    r[u] = k0 + (uint32_t)u < n ? __ldg(reinterpret_cast<const uint32_t *>(bp + (size_t)u * stride)) : 0xFFFFFFFFu;
-#pragma unroll
-                for (int u = 0; u < EXPAND_BATCH; ++u) {
-                    const uint32_t off = off0 + record_pos(r[u]);
-                    if (off < TILE_SLOTS)
-                        st_shared_u16(tile_addr + tile_byte(off), r[u]);
-                }
-            }
-            // the next 32 subsequences matter only if the last one of these still begins inside the strip
-            if (!__shfl_sync(0xffffffffu, act && sub + 1u < nsub ? 1 : 0, 31))
-                break;
-        }
-        // ---- DC predictors entering the strip (K2) -----------------------------------------------------
-        // = the predictors at the entry of the subsequence the strip's first slot lies in (from the offset scan, unless
-        // they restart between that entry and the strip) + the DC differences that subsequence decoded before the strip
-        // (its records at slot 0 of a block, between the last restart and the strip's first slot).  Warp 0, lanes over
-        // the records of that one subsequence; the lines were just read by the loop above.
-        if (comp == 0) {
-            const uint32_t ss = __ldg(a.start_slot + first0);
-            const uint32_t reset_slot = sm.reset_slot;
-            int part[3] = {0, 0, 0};
-            if (ss < s0 && reset_slot < s0) {
-                const uint32_t nr = __ldg(a.nrec + first0);
-                const uint32_t n = min(nr & 1023u, a.rec_kmax);
-                const uint32_t *base = (nr >> 10) ? a.rec_alt + (size_t)((nr >> 10) - 1u) * a.rec_kmax
-                                                  : a.rec + ((size_t)(first0 >> 5) * a.rec_kmax) * 32u + (first0 & 31u);
-                const uint32_t stride = (nr >> 10) ? 1u : 32u; // in records
-                const uint32_t entry = ss & ~63u;
-                for (uint32_t k = lane; k < n; k += 32u) {
-                    const uint32_t r = __ldg(base + (size_t)k * stride);
-                    const uint32_t at = entry + record_pos(r);
-                    if ((at & 63u) == 0u && at < s0 && at >= reset_slot) {
-                        const uint32_t c = NC == 3 ? (at >> 6) % 3u : 0u;
-                        const int v = record_value(r);
-                        part[0] += c == 0u ? v : 0;
-                        part[1] += c == 1u ? v : 0;
-                        part[2] += c == 2u ? v : 0;
-                    }
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                part[c] = __reduce_add_sync(0xffffffffu, part[c]);
-            if (lane == 0) {
-                int pre[3] = {0, 0, 0};
-                if (ss >= reset_slot && reset_slot < s0) // no restart between the subsequence's entry and the strip
-                    dcs_unpack(a.dcpre[first0], pre);
-                sm.carry[0] = pre[0] + part[0];
-                sm.carry[1] = pre[1] + part[1];
-                sm.carry[2] = pre[2] + part[2];
-            }
-        }
-    } else {
-        // fallback: the Huffman final pass (entropy_write) left a coefficient matrix in global memory
-        for (uint32_t g = (uint32_t)t; g < (uint32_t)NB * 8u; g += (uint32_t)NB) {
-            const uint32_t b = g >> 3, k = g & 7u;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (blk0 + b < a.g.total_blocks)
-                v = __ldg(reinterpret_cast<const uint4 *>(a.coef_in) + (size_t)blk0 * 8u + g);
-            sm.coef[b * 8u + (k ^ (b & 7u))] = make_uint4(v.x ^ BIAS2, v.y ^ BIAS2, v.z ^ BIAS2, v.w ^ BIAS2);
-        }
-    }
-    if (t == 0)
-        mbar_wait(bar, 0); // the quantiser tables: the barrier below hands them on
     __syncthreads();
-
-    // ---- stage C: DC prediction -----------------------------------------------------------------------
-    // the block's DC difference is in slot 0; MCU.cpp:97-104: a block whose DC DIFFERENCE is 0 loses its AC terms
-    const uint32_t dcw = sm.coef[bl * 8 + (bl & 7)].x; // chunk 0 of the block
-    const int dcdiff = active ? (int)(dcw & 0xFFFFu) - (int)COEF_BIAS : 0;
-    const bool drop_ac = (a.g.flags & 1u) && dcdiff == 0;
-    int dcv;
-    if (a.dc_in) {
-        // fallback: the predicted DC values come from dc_integrate_kernel (kernels.cu)
-        dcv = active ? (int)__ldg(a.dc_in + blk0 + (uint32_t)bl) : 0;
-    } else {
-        bool reset = false;
-        if (active) { // mcu_is_reset: predictors restart at every restart interval and image (T.81 F.2.1.3.1)
-            uint32_t mi = sm.mi0 + (uint32_t)ml;
-            if (mi >= a.g.mcus_per_image)
-                mi %= a.g.mcus_per_image;
-            reset = a.g.restart_interval ? (mi % a.g.restart_interval) == 0u : mi == 0u;
-        }
-        int v = dcdiff;
-        uint32_t f = reset ? 1u : 0u;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int ov = __shfl_up_sync(0xffffffffu, v, d);
-            const uint32_t of = __shfl_up_sync(0xffffffffu, f, d);
-            if (ml >= d) {
-                v = f ? v : v + ov;
-                f |= of;
-            }
-        }
-        dcv = (int)(short)(v + (f ? 0 : sm.carry[comp]));
-    }
 
     // ---- stage 1: one thread = one 8x8 block ------------------------------------------------------
     uint4 ch[8];
@@ -684,32 +505,9 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
         ch[k] = sm.coef[bl * 8 + (k ^ (bl & 7))];
     uint32_t tie_lo = 0, tie_hi = 0; // this block's tie mask (bit layout: tie_bit)
     if (active) {
-        // slot 0 gets the integrated DC value, here and in the tile (stage 3 and the coefficient dump read the tile)
-        ch[0].x = (ch[0].x & 0xFFFF0000u) | (((uint32_t)dcv + COEF_BIAS) & 0xFFFFu);
-        st_shared_u16(tile_addr + (uint32_t)bl * 128u + (((uint32_t)bl & 7u) << 4), (uint32_t)dcv + COEF_BIAS);
-        if (drop_ac) {
-            sm.coef[bl * 8 + (bl & 7)] = make_uint4((ch[0].x & 0xFFFFu) | (COEF_BIAS << 16), BIAS2, BIAS2, BIAS2);
-#pragma unroll
-            for (int k = 1; k < 8; ++k)
-                sm.coef[bl * 8 + (k ^ (bl & 7))] = make_uint4(BIAS2, BIAS2, BIAS2, BIAS2);
-        }
-    }
-    if (a.coef_out) { // parity hook: the strip's coefficients as the reference holds them inside constructMCU
-        __syncthreads();
-        for (uint32_t g = (uint32_t)t; g < (uint32_t)NB * 8u; g += (uint32_t)NB) {
-            const uint32_t b = g >> 3, k = g & 7u;
-            if (blk0 + b < a.g.total_blocks) {
-                const uint4 v = sm.coef[b * 8u + (k ^ (b & 7u))];
-                reinterpret_cast<uint4 *>(a.coef_out)[(size_t)blk0 * 8u + g] = make_uint4(v.x ^ BIAS2, v.y ^ BIAS2, v.z ^ BIAS2, v.w ^ BIAS2);
-            }
-        }
-        if (a.pixels == nullptr)
-            return; // coefficients only
-    }
-    if (active) {
         F2 P[32];
         float a_ac, a_dc;
-        dequant_dezigzag(ch, drop_ac ? sm.qdc[comp] : sm.qpair[comp], P, a_ac, a_dc, std::make_integer_sequence<int, 32>{});
+        dequant_dezigzag(ch, sm.qpair[comp], P, a_ac, a_dc, std::make_integer_sequence<int, 32>{});
         const float A = a_ac + a_dc;
         uint32_t flag = (A != 0.0f ? BLK_NONZERO : 0u) | (A > COLOUR_SAFE_A ? BLK_WIDE : 0u);
         if (A > SAMPLE_SAFE_A) {
@@ -719,6 +517,7 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
         } else if (a_ac == 0.0f) {
             // DC only (flat blocks are common, and for suitable DC values EVERY sample is an exact tie): the reference's
             // sum has one non-zero term, float(C0 * C0 * F), whatever the sample (cos 0 = 1): MCU.cpp:190-198, :228
+            const int dcv = (int)(ch[0].x & 0xFFFFu) - (int)COEF_BIAS;
             const int F = dcv * __ldg(&a.tables->qint[comp][0]);
             const float tt = mul_f32(__ldg(&a.tables->cc[0][0]), (float)F);
             const uint32_t b = ((uint32_t)round_half_away(0.25f * tt) + COEF_BIAS) & 0xFFFFu;

@@ -77,26 +77,41 @@ struct EntropyArgs {
 
 constexpr int ENTROPY_THREADS = 128;
 
-// K2 + K3 (k3_fused.cu).  The strip's coefficients come from the records (rec != nullptr: expansion inside the kernel)
-// or, in the fallback, from the coefficient matrix the Huffman final pass wrote (coef_in).
-struct IdctArgs {
+// ---- coefficient tiles: what K2 hands to K3 ------------------------------------------------------------------
+// The quantised coefficients of a strip of IDCT_MCUS_PER_CTA consecutive MCUs (MCU-interleaved blocks: Y,Cb,Cr per
+// MCU), DC prediction and the reference's DC-difference rule already applied, stored as the IMAGE OF K3's SHARED-MEMORY
+// TILE: 16-bit values biased by COEF_BIAS (an empty slot is 0x8000), zig-zag order, one 128-byte line per block, and
+// inside the line the 16-byte chunk k of block b at chunk position k ^ (b & 7).  Strips are whole multiples of eight
+// blocks, so the swizzle is the same whether b counts from the strip or from the job.  K2 writes a tile with one bulk
+// copy out of its shared memory, K3 reads it with one bulk copy into its own.
+constexpr int IDCT_MCUS_PER_CTA = 32;
+KPEG_HD uint32_t coef_tile_chunk(uint32_t block, uint32_t k) { return block * 8u + (k ^ (block & 7u)); } // in 16-byte chunks
+KPEG_HD uint32_t coef_tile_byte(uint32_t slot) { return (slot * 2u) ^ ((slot >> 2) & 0x70u); }           // slot = block * 64 + zig-zag index
+
+// K2 (k2_expand.cu): record expansion + DC prediction -> coefficient tiles
+struct ExpandArgs {
     const uint32_t *rec;      // [group of 32 subsequences][rec_kmax][32]
     const uint32_t *nrec;     // [nsub]
     const uint32_t *rec_alt;  // private record areas (subsequences redone in sparse relay rounds)
     uint32_t rec_kmax;
     const uint32_t *start_slot; // [nsub]
     const uint32_t *strip_sub;  // [nstrips]
-    const int16_t *coef_in;   // fallback input: [total_blocks][64], slot 0 = DC difference
-    int16_t *coef_out;        // optional: the strip's coefficients as the reference holds them (DC integrated, F1 applied)
     const long long *dcpre;   // [nsub] packed DC predictor values at the entry of every subsequence (offset scan)
-    const int16_t *dc_in;     // fallback input: [total_blocks] predicted DC values (dc_integrate_kernel)
-    uint32_t nstrips;
-    const DeviceTables *tables;
-    uint8_t *pixels;          // [nimages][height][width][ncomp]; nullptr with coef_out = coefficients only
+    void *tiles;              // [nstrips] tile images
     DevMeta *meta;
     JobGeom g;
 };
-constexpr int IDCT_MCUS_PER_CTA = 32;
+
+// K3 (k3_fused.cu): dequantise + de-zigzag + IDCT + level shift + colour + store, from the coefficient tiles
+struct IdctArgs {
+    const void *tiles;        // [nstrips] tile images (K2, or tiles_from_matrix after the Huffman final pass)
+    uint32_t nstrips;
+    const DeviceTables *tables;
+    uint8_t *pixels;          // [nimages][height][width][ncomp]
+    DevMeta *meta;
+    JobGeom g;
+};
+
 
 void kernels_context_created();   // contexts of this process share the device: the cooperative relay loops of
 void kernels_context_destroyed(); // all of them together must stay co-resident
@@ -115,6 +130,10 @@ void launch_entropy_scan(const EntropyArgs &a, cudaStream_t s, uint32_t *launche
 void launch_entropy_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launches);  // Huffman final pass
 // fallback only: DC prediction over the DC differences the Huffman final pass left (dcdiff -> dc), one CTA per restart segment
 void launch_dc_integrate(const JobGeom &g, const int16_t *dcdiff, int16_t *dc, cudaStream_t s, uint32_t *launches);
+void launch_expand(const ExpandArgs &a, cudaStream_t s, uint32_t *launches); // K2
+// fallback (after the Huffman final pass + dc_integrate): plain coefficient matrix -> tile images
+void launch_tiles_from_matrix(const JobGeom &g, const int16_t *coef, const int16_t *dc, void *tiles, cudaStream_t s, uint32_t *launches);
+void launch_matrix_from_tiles(const void *tiles, int16_t *coef, uint32_t total_blocks, cudaStream_t s); // parity hook
 cudaError_t launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches);
 void k3_configure();                      // function attributes of the K3 kernels (called by kernels_configure)
 uint32_t k3_strip_slots(uint32_t ncomp);  // coefficient slots one K3 strip covers

@@ -60,6 +60,7 @@ struct Job {
     bool active = false;
     JobGeom g = {};
     EntropyArgs ea = {};
+    ExpandArgs xa = {};
     IdctArgs ia = {};
     int rounds = 0;
     uint32_t launches = 0;
@@ -73,7 +74,7 @@ struct Job {
 struct Lane {
     cudaStream_t stream = nullptr;
     DevBuf scan, words, seg_bit, tile_kept, tile_rst, cls, state, work, seg_hint, start_slot, scan_tiles;
-    DevBuf coef, dcdiff, dc, pixels, meta, rec, nrec, rec_alt, strip_sub, dcs, dcpre, scan_tiles_dcs;
+    DevBuf coef, dcdiff, dc, tiles, pixels, meta, rec, nrec, rec_alt, strip_sub, dcs, dcpre, scan_tiles_dcs;
     PinBuf h_meta;
     // host-buffer batches: pinned staging of the small scans + the separator positions, and their device copy
     PinBuf h_stage, h_ends;
@@ -292,21 +293,22 @@ int enqueue_downstream(kpeg_ctx *ctx, Lane &L)
     cudaStream_t s = L.stream;
     launch_entropy_scan(J.ea, s, &J.launches);
     mark(ctx, L, KPEG_T_ENTROPY_SCAN);
-    if (!J.use_records) {
-        // fallback: the Huffman final pass writes a coefficient matrix (every slot of every block: no zero-fill) and
-        // K3 takes its tiles from there
+    if (J.use_records) {
+        launch_expand(J.xa, s, &J.launches); // K2
+        mark(ctx, L, KPEG_T_ENTROPY_WRITE);
+    } else {
+        // fallback: the Huffman final pass writes a plain coefficient matrix (every slot of every block: no zero-fill)
+        // and the DC differences; DC prediction and the conversion into K3's tiles are separate small kernels
         const size_t coef_bytes = (size_t)J.g.total_blocks * 128u;
         TRY(ensure(ctx, s, L.coef, coef_bytes + 256));
         TRY(ensure(ctx, s, L.dcdiff, (size_t)J.g.total_blocks * 2u + 16));
         TRY(ensure(ctx, s, L.dc, (size_t)J.g.total_blocks * 2u + 16));
         J.ea.coef = (int16_t *)L.coef.p;
         J.ea.dcdiff = (int16_t *)L.dcdiff.p;
-        J.ia.rec = nullptr;
-        J.ia.coef_in = (const int16_t *)L.coef.p;
-        J.ia.dc_in = (const int16_t *)L.dc.p;
         launch_entropy_write(J.ea, s, &J.launches);
         mark(ctx, L, KPEG_T_ENTROPY_WRITE);
         launch_dc_integrate(J.g, (const int16_t *)L.dcdiff.p, (int16_t *)L.dc.p, s, &J.launches);
+        launch_tiles_from_matrix(J.g, (const int16_t *)L.coef.p, (const int16_t *)L.dc.p, L.tiles.p, s, &J.launches);
         mark(ctx, L, KPEG_T_DC_SCAN);
     }
     CK(launch_idct(J.ia, s, &J.launches));
@@ -380,6 +382,7 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     TRY(ensure(ctx, s, L.dcs, (size_t)nsub_max * sizeof(long long)));
     TRY(ensure(ctx, s, L.dcpre, (size_t)nsub_max * sizeof(long long)));
     TRY(ensure(ctx, s, L.scan_tiles_dcs, ((size_t)nsub_max / 1024u + 2u) * sizeof(long long)));
+    TRY(ensure(ctx, s, L.tiles, (size_t)nstrips * IDCT_MCUS_PER_CTA * g.ncomp * 128u + 256u));
     TRY(ensure(ctx, s, L.meta, sizeof(DevMeta)));
     TRY(ensure_pinned(ctx, s, L.h_meta, sizeof(DevMeta)));
     // records: one per value-carrying symbol.  3/8 of the subsequence's bits covers every table whose value-carrying
@@ -445,17 +448,20 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     ea.nsub_max = nsub_max;
     ea.g = g;
 
+    ExpandArgs &xa = J.xa;
+    xa.rec = ea.rec;
+    xa.nrec = ea.nrec;
+    xa.rec_alt = ea.rec_alt;
+    xa.rec_kmax = rec_kmax;
+    xa.start_slot = ea.start_slot;
+    xa.strip_sub = ea.strip_sub;
+    xa.dcpre = ea.dcpre;
+    xa.tiles = L.tiles.p;
+    xa.meta = d_meta;
+    xa.g = g;
+
     IdctArgs &ia = J.ia;
-    ia.rec = ea.rec;
-    ia.nrec = ea.nrec;
-    ia.rec_alt = ea.rec_alt;
-    ia.rec_kmax = rec_kmax;
-    ia.start_slot = ea.start_slot;
-    ia.strip_sub = ea.strip_sub;
-    ia.coef_in = nullptr;
-    ia.coef_out = nullptr;
-    ia.dcpre = ea.dcpre;
-    ia.dc_in = nullptr;
+    ia.tiles = L.tiles.p;
     ia.nstrips = nstrips;
     ia.tables = (const DeviceTables *)ctx->tables.p;
     ia.pixels = d_pixels;
@@ -493,7 +499,7 @@ int check_guards(kpeg_ctx *ctx, Lane &L)
     NamedBuf bufs[] = {{"cls", &L.cls},           {"scan", &L.scan},         {"words", &L.words},       {"seg_bit", &L.seg_bit},
                        {"tile_kept", &L.tile_kept}, {"tile_rst", &L.tile_rst}, {"state", &L.state},       {"work", &L.work},
                        {"seg_hint", &L.seg_hint}, {"start_slot", &L.start_slot}, {"scan_tiles", &L.scan_tiles},
-                       {"coef", &L.coef},         {"dcdiff", &L.dcdiff},     {"strip_sub", &L.strip_sub}, {"dc", &L.dc}, {"dcs", &L.dcs}, {"dcpre", &L.dcpre}, {"scan_tiles_dcs", &L.scan_tiles_dcs}, {"d_ends", &L.d_ends},
+                       {"coef", &L.coef},         {"dcdiff", &L.dcdiff},     {"tiles", &L.tiles},     {"strip_sub", &L.strip_sub}, {"dc", &L.dc}, {"dcs", &L.dcs}, {"dcpre", &L.dcpre}, {"scan_tiles_dcs", &L.scan_tiles_dcs}, {"d_ends", &L.d_ends},
                        {"pixels", &L.pixels},     {"meta", &L.meta},
                        {"rec", &L.rec},           {"nrec", &L.nrec},         {"rec_alt", &L.rec_alt},   {"tables", &ctx->tables}};
     uint8_t host[2 * GUARD_BYTES];
@@ -697,7 +703,7 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
         if (L.stream)
             cudaStreamSynchronize(L.stream);
         DevBuf *bufs[] = {&L.cls,  &L.scan, &L.words,    &L.seg_bit,    &L.tile_kept,  &L.tile_rst, &L.state,
-                          &L.work, &L.seg_hint, &L.start_slot, &L.scan_tiles, &L.coef,     &L.dcdiff,
+                          &L.work, &L.seg_hint, &L.start_slot, &L.scan_tiles, &L.coef,     &L.dcdiff, &L.tiles,
                           &L.strip_sub, &L.dc, &L.dcs, &L.dcpre, &L.scan_tiles_dcs, &L.pixels, &L.meta,
                           &L.rec,  &L.nrec,       &L.rec_alt};
         for (DevBuf *b : bufs)
@@ -1263,14 +1269,8 @@ extern "C" int kpeg_cuda_read_coefficients(kpeg_ctx *ctx, int16_t *out, size_t c
     if (cap < n)
         return fail(ctx, KPEG_ERR_ARG, "coefficient buffer too small");
     TRY(ensure(ctx, L.stream, ctx->merged, n * 2u));
-    // The coefficients of a decode exist only strip by strip in K3's shared memory.  The records (or, after the
-    // Huffman final pass, the coefficient matrix) of the lane's last job are still resident, so K3 runs once more in
-    // its coefficients-only form: expansion + DC prediction + F1 rule, tiles written out, no pixels.
-    IdctArgs ia = L.job.ia;
-    ia.coef_out = (int16_t *)ctx->merged.p;
-    ia.pixels = nullptr;
-    uint32_t launches = 0;
-    CK(launch_idct(ia, L.stream, &launches));
+    // the coefficient tiles of the lane's last job are still resident: un-bias and un-swizzle them
+    launch_matrix_from_tiles(L.tiles.p, (int16_t *)ctx->merged.p, ctx->last_g.total_blocks, L.stream);
     CK(cudaMemcpyAsync(out, ctx->merged.p, n * 2u, cudaMemcpyDeviceToHost, L.stream));
     CK(cudaStreamSynchronize(L.stream));
     CK(cudaGetLastError());

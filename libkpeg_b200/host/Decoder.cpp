@@ -136,17 +136,33 @@ namespace kpeg
         }
         m_plan.flags = m_parity ? KPEG_FLAG_REF_PARITY : 0u;
 
-        kpeg_ctx* ctx = nullptr;
-        if ( kpeg_cuda_create( m_device, &ctx ) != KPEG_OK )
-        {
-            LOG(Logger::Level::ERROR) << "No usable CUDA device: this build has no CPU decode path";
-            return ResultCode::ERROR;
-        }
         m_pixels.assign( (std::size_t)m_plan.width * m_plan.height * m_plan.ncomp, 0 );
-        const int rc = kpeg_cuda_decode( ctx, &m_plan, m_file.data() + scanOff, scanLen, m_pixels.data(), &m_stats );
-        if ( rc != KPEG_OK )
-            LOG(Logger::Level::ERROR) << "Decode failed: " << kpeg_cuda_last_error( ctx );
-        kpeg_cuda_destroy( ctx );
+        int rc;
+        if ( m_devices.size() > 1 )
+        {
+            // restart-interval tiles over several GPUs, every band into its rows of m_pixels (Image.cpp:51-70 placement)
+            rc = kpeg_cuda_decode_tiled( m_devices.data(), (int)m_devices.size(), &m_plan, m_file.data() + scanOff, scanLen,
+                                         m_pixels.data(), &m_stats );
+            if ( rc == KPEG_ERR_CUDA )
+                LOG(Logger::Level::ERROR) << "No usable CUDA device: this build has no CPU decode path";
+            else if ( rc != KPEG_OK )
+                LOG(Logger::Level::ERROR) << "Decode failed: " << kpeg_tiled_last_error();
+        }
+        else
+        {
+            // a context borrowed from the process-wide pool: the reference constructs one decoder per file
+            // (main.cpp:54-79); streams, pinned bookkeeping and device scratch survive from one file to the next
+            kpeg_ctx* ctx = nullptr;
+            if ( kpeg_cuda_acquire( m_device, &ctx ) != KPEG_OK )
+            {
+                LOG(Logger::Level::ERROR) << "No usable CUDA device: this build has no CPU decode path";
+                return ResultCode::ERROR;
+            }
+            rc = kpeg_cuda_decode( ctx, &m_plan, m_file.data() + scanOff, scanLen, m_pixels.data(), &m_stats );
+            if ( rc != KPEG_OK )
+                LOG(Logger::Level::ERROR) << "Decode failed: " << kpeg_cuda_last_error( ctx );
+            kpeg_cuda_release( m_device, ctx );
+        }
         if ( rc == KPEG_ERR_STREAM )
             return ResultCode::DECODE_INCOMPLETE;
         if ( rc != KPEG_OK )

@@ -76,7 +76,10 @@ namespace kpeg
             // true (default): reproduce the reference bit for bit, including its DC-difference quirk
             // (src/MCU.cpp:97-104).  false: ITU-T T.81 behaviour.
             void setParity( bool on ) { m_parity = on; }
-            void setDevice( int device ) { m_device = device; }
+            void setDevice( int device ) { m_device = device; m_devices.clear(); }
+            // several devices: the restart-interval tiles of the image are spread over them (kpeg_cuda_decode_tiled);
+            // an image without usable restart markers is decoded whole by the first one
+            void setDevices( const std::vector<int>& devices ) { m_devices = devices; if ( !devices.empty() ) m_device = devices[0]; }
 
             const std::vector<std::uint8_t>& pixels() const { return m_pixels; }
             unsigned width() const { return m_plan.width; }
@@ -97,6 +100,7 @@ namespace kpeg
             bool m_decoded;
             bool m_parity;
             int m_device;
+            std::vector<int> m_devices;
     };
 }
 

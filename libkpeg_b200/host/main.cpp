@@ -8,6 +8,7 @@
 // none or too many (main.cpp:54-79).  Extra, non-reference switches come before the file name:
 //   --t81        ITU-T T.81 behaviour instead of bit-exact reference parity
 //   --device N   CUDA device index
+//   --devices L  several devices, e.g. 0-7 or 0,2,3: the restart-interval tiles of the image are spread over them
 //   --quiet      log only to kpeg.log
 #include <cstdlib>
 #include <iostream>
@@ -41,7 +42,29 @@ namespace
     {
         bool parity = true;
         int device = 0;
+        std::vector<int> devices;
     };
+
+    // "0-3", "0,2,5", "1": device list of --devices
+    std::vector<int> parseDevices( const std::string& s )
+    {
+        std::vector<int> out;
+        std::size_t i = 0;
+        while ( i < s.size() )
+        {
+            std::size_t j = s.find( ',', i );
+            if ( j == std::string::npos ) j = s.size();
+            const std::string part = s.substr( i, j - i );
+            const std::size_t dash = part.find( '-' );
+            if ( dash == std::string::npos )
+                out.push_back( std::atoi( part.c_str() ) );
+            else
+                for ( int d = std::atoi( part.substr( 0, dash ).c_str() ); d <= std::atoi( part.substr( dash + 1 ).c_str() ); ++d )
+                    out.push_back( d );
+            i = j + 1;
+        }
+        return out;
+    }
 
     void decodeJPEG( const std::string& filename, const Options& opt )
     {
@@ -53,6 +76,8 @@ namespace
         kpeg::JPEGDecoder decoder;
         decoder.setParity( opt.parity );
         decoder.setDevice( opt.device );
+        if ( !opt.devices.empty() )
+            decoder.setDevices( opt.devices );
         decoder.open( filename );
         if ( decoder.decodeImageFile() == kpeg::JPEGDecoder::ResultCode::DECODE_DONE )
             decoder.dumpRawData();
@@ -74,6 +99,7 @@ int main( int argc, char** argv )
             if ( a == "--t81" ) opt.parity = false;
             else if ( a == "--quiet" ) kpeg::Logger::get().setQuiet( true );
             else if ( a == "--device" && i + 1 < argc ) opt.device = std::atoi( argv[++i] );
+            else if ( a == "--devices" && i + 1 < argc ) opt.devices = parseDevices( argv[++i] );
             else args.push_back( a );
         }
 
