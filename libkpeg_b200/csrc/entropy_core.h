@@ -24,11 +24,12 @@ namespace kpeg {
 
 KPEG_HD uint32_t max_u32(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
-KPEG_HD uint32_t funnel_left(uint32_t hi, uint32_t lo, uint32_t s)
+KPEG_HD uint32_t funnel_left(uint32_t hi, uint32_t lo, uint32_t s) // the count is taken modulo 32
 {
 #if defined(__CUDA_ARCH__)
     return __funnelshift_l(lo, hi, s);
 #else
+    s &= 31u;
     return s ? (hi << s) | (lo >> (32u - s)) : hi;
 #endif
 }
@@ -263,7 +264,7 @@ template <bool EMIT, bool DCS = false, class Words, class Luts, class Rec>
 KPEG_HD void relay_run(DecState &d, const Words &W, const Luts &L, const StreamView &S, const JobGeom &g, uint32_t end_bit,
                        const Rec &rec)
 {
-    const uint32_t ring = g.ncomp * 2u * (uint32_t)LUT_SIZE;
+    const uint32_t ring_last = (g.ncomp * 2u - 1u) * (uint32_t)LUT_SIZE; // the last table of the ring: the last component's AC table
     long long dcs = d.dcs;
     uint32_t wc = dcs_weight(d.toff >> (LUT_BITS + 1));                    // weight of the current component
     uint32_t wd = (d.toff & (uint32_t)LUT_SIZE) ? 0u : wc;                 // ... if the next symbol is its DC difference
@@ -284,25 +285,20 @@ KPEG_HD void relay_run(DecState &d, const Words &W, const Luts &L, const StreamV
                 // store alone is predicated
                 worst = max_u32(worst, size ? zn : adv);
                 rec.emit(size != 0u, nrec, record_pack(q + adv - 1u, bv));
-                nrec += size ? 1u : 0u;
+                nrec += size < 1u ? size : 1u;
             }
             if (DCS)
                 dcs += (long long)(int32_t)(bv - COEF_BIAS) * (long long)(int32_t)wd;
         }
-        if (zn >= 64u) { // end of the block: next table of the ring
-            q = (q | 63u) + 1u;
-            toff += (uint32_t)LUT_SIZE;
-            const bool wrap = toff == ring;
-            toff = wrap ? 0u : toff;
-            if (DCS) {
-                wc = wrap ? 1u : wc << DCS_SHIFT;
-                wd = wc;
-            }
-        } else {
-            q += adv;
-            toff |= (uint32_t)LUT_SIZE;
-            if (DCS)
-                wd = 0u;
+        // end of the block: next table of the ring (a block ends in its AC table); selects, not a branch -- some lane of a
+        // warp ends a block in almost every iteration, so both sides of a branch would be issued anyway
+        const bool endb = zn >= 64u;
+        const bool wrap = toff == ring_last;
+        q = endb ? (q | 63u) + 1u : q + adv;
+        toff = endb ? (wrap ? 0u : toff + (uint32_t)LUT_SIZE) : (toff | (uint32_t)LUT_SIZE);
+        if (DCS) {
+            wc = endb ? (wrap ? 1u : wc << DCS_SHIFT) : wc;
+            wd = endb ? wc : 0u;
         }
     };
     auto cross_boundary = [&]() { // onto boundary k: state (segend, component 0, DC), position and DC sums restart
@@ -324,22 +320,24 @@ KPEG_HD void relay_run(DecState &d, const Words &W, const Luts &L, const StreamV
     // except next to an image end) no symbol of this call can straddle it, and with a word-aligned end_bit
     // "p < end_bit" is "j < end_bit / 32": the loop carries neither p nor a boundary test.
     if (p < end_bit && (end_bit & 31u) == 0u && segend >= end_bit + 32u) {
+        // the funnel shift takes its count modulo 32, so the bit position itself is the count: no separate
+        // "bits into the word" counter to keep in step
         const uint32_t jend = end_bit >> 5;
         while (j < jend) {
             const uint32_t nxt = W(j + 2u);
-            const uint32_t win = funnel_left(w0, w1, sh);
+            const uint32_t win = funnel_left(w0, w1, p);
             uint32_t e = L.fast(toff, win >> (32 - LUT_BITS));
             if ((e & 31u) == 0u)
                 e = L.slow(toff, win, e);
             symbol(win, e);
-            sh += e & 31u;
-            const bool cross = sh >= 32u;
-            sh = cross ? sh - 32u : sh;
-            j = cross ? j + 1u : j;
+            p += e & 31u;
+            const uint32_t jn = p >> 5;
+            const bool cross = jn != j;
             w0 = cross ? w1 : w0;
             w1 = cross ? nxt : w1;
+            j = jn;
         }
-        p = (j << 5) + sh;
+        sh = p & 31u;
     }
     while (p < end_bit) {
         const uint32_t nxt = W(j + 2u); // consumed at the bottom of the iteration, if at all

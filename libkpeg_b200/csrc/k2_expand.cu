@@ -38,13 +38,18 @@
 namespace kpeg {
 
 #ifndef KPEG_EXPAND_BATCH
-#define KPEG_EXPAND_BATCH 8
+#define KPEG_EXPAND_BATCH 16
 #endif
 constexpr int EXPAND_BATCH = KPEG_EXPAND_BATCH; // record loads in flight per lane
 #ifndef KPEG_EXPAND_MIN_CTAS
 #define KPEG_EXPAND_MIN_CTAS 12
 #endif
 constexpr int EXPAND_THREADS = 128;
+#ifndef KPEG_EXPAND_PREFETCH_AHEAD
+#define KPEG_EXPAND_PREFETCH_AHEAD 1776
+#endif
+constexpr uint32_t EXPAND_PREFETCH_AHEAD = KPEG_EXPAND_PREFETCH_AHEAD; // strips ahead whose record lines are pulled into L2 (0 = off)
+constexpr uint32_t EXPAND_PREFETCH_LINES = 112;                        // record indices per group of 32 subsequences
 constexpr uint32_t BIAS2 = COEF_BIAS | (COEF_BIAS << 16);
 
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v)
@@ -80,6 +85,17 @@ __global__ void __launch_bounds__(EXPAND_THREADS, KPEG_EXPAND_MIN_CTAS) expand_k
     // ---- stage A ---------------------------------------------------------------------------------------
     const uint32_t nsub = a.meta->nsub;
     const uint32_t first0 = min(__ldg(a.strip_sub + strip), nsub - 1u);
+    if (EXPAND_PREFETCH_AHEAD != 0u && strip + EXPAND_PREFETCH_AHEAD < a.nstrips) {
+        // the record lines a strip that starts about one CTA lifetime from now will read: DRAM -> L2 now, so that its
+        // batches wait for L2, not for DRAM.  (Which strip that is need not be exact.)
+        const uint32_t fs = min(__ldg(a.strip_sub + strip + EXPAND_PREFETCH_AHEAD), nsub - 1u);
+        const char *g0 = reinterpret_cast<const char *>(a.rec + ((size_t)(fs >> 5) * a.rec_kmax) * 32u);
+        const uint32_t lines = min(a.rec_kmax, EXPAND_PREFETCH_LINES);
+        for (uint32_t k = (uint32_t)t; k < 2u * lines; k += EXPAND_THREADS) {
+            const uint32_t grp = k >= lines ? 1u : 0u; // the strip's subsequences usually straddle two groups of 32
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(g0 + ((size_t)grp * a.rec_kmax + (k - grp * lines)) * 128u));
+        }
+    }
     for (int i = t; i < NB * 8; i += EXPAND_THREADS)
         sm.coef[i] = make_uint4(BIAS2, BIAS2, BIAS2, BIAS2);
     if (t == 0) {
@@ -99,12 +115,12 @@ __global__ void __launch_bounds__(EXPAND_THREADS, KPEG_EXPAND_MIN_CTAS) expand_k
         const uint32_t sub = first + lane;
         bool act = sub < nsub;
         const uint32_t ss = act ? __ldg(a.start_slot + sub) : 0xFFFFFFFFu;
+        const uint32_t nr = act ? __ldg(a.nrec + sub) : 0u; // together with start_slot: one round trip, not two
         // the first subsequence begins at or before the strip's first slot, the others inside the strip -- or beyond it
         act = act && (ss <= s0 || ss - s0 < TILE_SLOTS);
         uint32_t n = 0, stride = 128u;
         const uint32_t *base = a.rec;
         if (act) {
-            const uint32_t nr = __ldg(a.nrec + sub);
             n = min(nr & 1023u, a.rec_kmax);
             if (nr >> 10) { // redone in a sparse relay round: private contiguous area
                 base = a.rec_alt + (size_t)((nr >> 10) - 1u) * a.rec_kmax;

@@ -98,6 +98,7 @@ struct ExpandArgs {
     const uint32_t *strip_sub;  // [nstrips]
     const long long *dcpre;   // [nsub] packed DC predictor values at the entry of every subsequence (offset scan)
     void *tiles;              // [nstrips] tile images
+    uint32_t nstrips;
     DevMeta *meta;
     JobGeom g;
 };

@@ -457,6 +457,7 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     xa.strip_sub = ea.strip_sub;
     xa.dcpre = ea.dcpre;
     xa.tiles = L.tiles.p;
+    xa.nstrips = nstrips;
     xa.meta = d_meta;
     xa.g = g;
 

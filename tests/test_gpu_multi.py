@@ -87,6 +87,7 @@ def test_tiled_decode_into_device_frame_peer_gather(decoder):
 
 def test_context_pool_reuses_contexts():
     lib = api.load_cuda_library()
+    lib.kpeg_cuda_pool_clear()  # contexts the tiled decodes of other tests left idle
     a, b = C.c_void_p(), C.c_void_p()
     assert lib.kpeg_cuda_acquire(0, C.byref(a)) == 0
     lib.kpeg_cuda_release(0, a)

@@ -17,5 +17,5 @@ B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --skip-pixel-check"
 $B > gpurun_out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${tag}_launches.csv $B > gpurun_out/${tag}_ncu1.log 2>&1
 $B > gpurun_out/${tag}_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'idct_kernel|entropy_relay_full|entropy_cold|unstuff_write|unstuff_count' -s 100 -c 5 -o gpurun_out/${tag}_prof -f $B > gpurun_out/${tag}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'idct_kernel|expand_kernel|entropy_relay_full|entropy_cold' -s 88 -c 4 -o gpurun_out/${tag}_prof -f $B > gpurun_out/${tag}_ncu2.log 2>&1
 tail -3 gpurun_out/${tag}_ncu2.log
