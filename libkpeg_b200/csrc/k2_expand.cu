@@ -46,7 +46,7 @@ constexpr int EXPAND_BATCH = KPEG_EXPAND_BATCH; // record loads in flight per la
 #endif
 constexpr int EXPAND_THREADS = 128;
 #ifndef KPEG_EXPAND_PREFETCH_AHEAD
-#define KPEG_EXPAND_PREFETCH_AHEAD 1776
+#define KPEG_EXPAND_PREFETCH_AHEAD 0
 #endif
 constexpr uint32_t EXPAND_PREFETCH_AHEAD = KPEG_EXPAND_PREFETCH_AHEAD; // strips ahead whose record lines are pulled into L2 (0 = off)
 constexpr uint32_t EXPAND_PREFETCH_LINES = 112;                        // record indices per group of 32 subsequences

@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256) rgb_to_planar_kernel(const uint8_t *rgb, 
     if (i + 4u <= n && (n & 3u) == 0 && ((reinterpret_cast<uintptr_t>(rgb) | reinterpret_cast<uintptr_t>(planes)) & 3u) == 0) {
         const uint32_t *in = reinterpret_cast<const uint32_t *>(rgb) + q * 3u;
         const uint32_t w0 = __ldg(in), w1 = __ldg(in + 1), w2 = __ldg(in + 2); // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
-        reinterpret_cast<uint32_t *>(pr)[q] = __byte_perm(w0, w1, 0x6230) & 0x00FFFFFFu | ((w2 >> 8) & 0xFFu) << 24;
+        reinterpret_cast<uint32_t *>(pr)[q] = (__byte_perm(w0, w1, 0x0630) & 0x00FFFFFFu) | ((w2 >> 8) & 0xFFu) << 24;
         reinterpret_cast<uint32_t *>(pg)[q] = ((w0 >> 8) & 0xFFu) | (w1 & 0xFFu) << 8 | (w1 >> 24) << 16 | ((w2 >> 16) & 0xFFu) << 24;
         reinterpret_cast<uint32_t *>(pb)[q] = ((w0 >> 16) & 0xFFu) | ((w1 >> 8) & 0xFFu) << 8 | (w2 & 0xFFu) << 16 | (w2 >> 24) << 24;
     } else {
@@ -460,9 +460,22 @@ __device__ __forceinline__ void k1_stage_stream(K1Smem &sm, const EntropyArgs &a
     const uint32_t gw0 = (tile * TILE) << wlog;
     const uint32_t nwords = ((uint32_t)TILE << wlog) + K1_TAIL_WORDS;
     const uint32_t total_words = ((total_bits + 31u) >> 5) + 4u; // the stream buffer has zeroed slack beyond this
-    for (uint32_t l = threadIdx.x; l < nwords; l += blockDim.x) {
-        const uint32_t gw = gw0 + l;
-        sm.words[k1_pad(l)] = gw < total_words ? __ldg(a.words + gw) : 0u;
+    // eight loads in flight per thread: issued one by one (load, wait, store) the staging was a chain of sixteen memory
+    // round trips per tile and a quarter of the stall samples of the cold and relay kernels
+    constexpr int STAGE_BATCH = 8;
+    for (uint32_t l0 = threadIdx.x; l0 < nwords; l0 += STAGE_BATCH * blockDim.x) {
+        uint32_t v[STAGE_BATCH];
+#pragma unroll
+        for (int i = 0; i < STAGE_BATCH; ++i) {
+            const uint32_t l = l0 + (uint32_t)i * blockDim.x, gw = gw0 + l;
+            v[i] = (l < nwords && gw < total_words) ? __ldg(a.words + gw) : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < STAGE_BATCH; ++i) {
+            const uint32_t l = l0 + (uint32_t)i * blockDim.x;
+            if (l < nwords)
+                sm.words[k1_pad(l)] = v[i];
+        }
     }
     __syncthreads();
 }
@@ -663,6 +676,21 @@ struct PrivateWords {
     }
 };
 
+// the words of one subsequence into its thread's private slice, eight loads in flight
+__device__ __forceinline__ void stage_private_words(uint32_t *mine, const uint32_t *words, uint32_t j0, uint32_t n, uint32_t total_words)
+{
+    for (uint32_t k0 = 0; k0 < n; k0 += 8u) {
+        uint32_t v[8];
+#pragma unroll
+        for (uint32_t i = 0; i < 8u; ++i)
+            v[i] = (k0 + i < n && j0 + k0 + i < total_words) ? __ldg(words + j0 + k0 + i) : 0u;
+#pragma unroll
+        for (uint32_t i = 0; i < 8u; ++i)
+            if (k0 + i < n)
+                mine[k0 + i] = v[i];
+    }
+}
+
 __host__ __device__ inline size_t k1_sparse_smem_bytes(uint32_t sub_bits)
 {
     return sizeof(K1Smem) + (size_t)ENTROPY_THREADS * (sub_bits / 32u + 5u) * sizeof(uint32_t);
@@ -688,8 +716,7 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_relay_sparse_kernel(E
         inraw = __ldcg(reinterpret_cast<const uint4 *>(&a.state[sub - 1]));
         const uint32_t j0 = inraw.x >> 5;
         const uint32_t total_words = ((total_bits + 31u) >> 5) + 4u;
-        for (uint32_t k = 0; k < stride - 1u; ++k)
-            mine[k] = j0 + k < total_words ? __ldg(a.words + j0 + k) : 0u;
+        stage_private_words(mine, a.words, j0, stride - 1u, total_words);
     }
     __syncthreads(); // tables staged
     if (!active)
@@ -788,8 +815,7 @@ __global__ void __launch_bounds__(ENTROPY_THREADS, 8) entropy_relay_loop_kernel(
                 continue;
             const uint4 inraw = __ldcg(reinterpret_cast<const uint4 *>(&a.state[sub - 1]));
             const uint32_t j0 = inraw.x >> 5;
-            for (uint32_t k = 0; k < stride - 1u; ++k)
-                mine[k] = j0 + k < total_words ? __ldg(a.words + j0 + k) : 0u;
+            stage_private_words(mine, a.words, j0, stride - 1u, total_words);
             W.gw0 = j0;
             const uint32_t end = min((sub + 1u) << (wlog + 5u), total_bits);
             const SubState out = relay_decode(a, W, L, S, sub, end, inraw.x, inraw.z & CZ_STATE_MASK, true);
