@@ -15,14 +15,19 @@
 //            folded into the quantiser), de-zigzag by register renaming, separable fp32 IDCT, rounding, tie-band test;
 //            blocks without AC coefficients take the reference's one-term evaluation directly
 //   stage 2  per pixel row: YCbCr -> RGB on pixel pairs (fp32 with proven margin, double otherwise), pack, store
-//   stage 3  the samples inside the tie band (0.1 % .. 0.7 %) are re-evaluated in the reference's own operation order
-//            from the tile, which is still in shared memory, and their pixels rewritten -- by one warp, lanes = samples
+//   stage 3  the samples inside the tie band (0.1 % .. 0.7 %) need the reference's own operation order: the strip lists
+//            their pixels (one record per pixel: where it is, which components are tied, the three fast samples) and
+//            idct_patch_kernel re-evaluates them afterwards from the coefficient tiles with full warps.  (Resolved inside
+//            this kernel -- one warp, six lanes busy on average, the CTA's slot held for a 64-term serial chain, and the
+//            unrolled chain in this kernel's instruction stream -- it cost 21 % of the stall samples and a third of the
+//            instruction-cache misses.)  Only a strip with more ties than its list holds resolves them itself.
 //
 // All file:line citations are relative to /root/reference.
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <utility>
 
 #include "entropy_core.h"
@@ -70,7 +75,8 @@ __device__ __forceinline__ int tie_sample(int w, int b)
 #endif
 constexpr uint32_t IDCT_PREFETCH_AHEAD = KPEG_IDCT_PREFETCH_AHEAD; // strips: 148 SMs x 8 CTAs, the strip that runs in this CTA's slot next
 
-constexpr int TIE_LIST_CAP = 160; // (block, sample) entries per strip; a strip with more walks its blocks' masks instead
+constexpr int TIE_LIST_CAP = IDCT_TIE_LIST_CAP; // (block, sample) entries per strip; a strip with more walks its blocks' masks instead
+constexpr uint32_t TIE_EMPTY = 0xFFFFFFFFu;     // tie record without a pixel
 
 template <int NC>
 struct IdctSmem {
@@ -690,9 +696,11 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
     }
     __syncthreads();
 
-    // ---- stage 3: the samples inside the tie band, in the reference's own operation order ------------------
+    // ---- stage 3: the samples inside the tie band ------------------------------------------------------------
     const uint32_t ntie = sm.ntie;
     if (ntie == 0u && sm.any_huge == 0u) {
+        if (t == 0)
+            a.tie_cnt[strip] = 0u;
         if (colour_exact)
             atomicAdd(&a.meta->colour_exact, colour_exact);
         return;
@@ -730,17 +738,40 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
         }
     };
     if (ntie <= (uint32_t)TIE_LIST_CAP) {
-        // the common case: ONE warp, lanes = listed samples, so the long serial evaluation runs with as many lanes as there
-        // are ties; the other warps are done
-        if (t < 32) {
-            for (uint32_t i = (uint32_t)t; i < ntie; i += 32u)
-                resolve(sm.ties[i] & 127u, (int)(sm.ties[i] >> 7));
-            __syncwarp();
-            for (uint32_t i = (uint32_t)t; i < ntie; i += 32u)
-                repaint(sm.ties[i] & 127u, (int)(sm.ties[i] >> 7));
+        // the common case: one record per tied PIXEL for idct_patch_kernel.  A pixel may be tied in more than one
+        // component: the entry of the lowest tied component carries the flags of all of them, the others stay empty.
+        // Pixels of an MCU that is redone wholesale below (BLK_HUGE) and pixels outside the image are not listed.
+        for (uint32_t i = (uint32_t)t; i < ntie; i += (uint32_t)NB) {
+            const uint32_t e = sm.ties[i], b = e & 127u, mm_l = b / NC, c = b % NC;
+            const int sidx = (int)(e >> 7);
+            uint32_t flags = 0;
+            for (uint32_t j = 0; j < ntie; ++j) {
+                const uint32_t o = sm.ties[j];
+                if ((o >> 7) == (e >> 7) && (o & 127u) / NC == mm_l)
+                    flags |= 1u << ((o & 127u) % NC);
+            }
+            uint32_t huge = 0;
+            for (int cc = 0; cc < NC; ++cc)
+                huge |= sm.flag[mm_l * NC + cc];
+            uint4 r = make_uint4(TIE_EMPTY, 0, 0, 0);
+            uint32_t img, by, bx;
+            mcu_origin(mm_l, img, by, bx);
+            const uint32_t px = bx * 8u + (uint32_t)(sidx & 7), py = by * 8u + (uint32_t)(sidx >> 3);
+            if ((flags & (0u - flags)) == (1u << c) && !(huge & BLK_HUGE) && mcu0 + mm_l < total_mcus && px < W && py < H) {
+                r.x = img * W * H + py * W + px; // pixels of a job are < 2^32 (host_tables.h)
+                r.y = mcu0 + mm_l;
+                r.z = (uint32_t)sidx | (flags << 8) | ((uint32_t)sp16[samp_index(0, mm_l, sidx)] << 16);
+                r.w = NC == 3 ? (uint32_t)sp16[samp_index(1, mm_l, sidx)] | ((uint32_t)sp16[samp_index(2, mm_l, sidx)] << 16) : 0u;
+            }
+            a.tie_rec[(size_t)strip * TIE_LIST_CAP + i] = r;
         }
+        if (t == 0)
+            a.tie_cnt[strip] = ntie;
     } else {
-        // more ties than the list holds (flat or synthetic content): every thread walks the mask of its own block
+        // more ties than the list holds (flat or synthetic content): every thread walks the mask of its own block and
+        // resolves its ties here, from the tile, which is still in shared memory
+        if (t == 0)
+            a.tie_cnt[strip] = 0u;
         for (int pass = 0; pass < 2; ++pass) {
             uint32_t lo = tie_lo, hi = tie_hi;
             while (lo | hi) {
@@ -797,6 +828,82 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
         atomicAdd(&a.meta->colour_exact, colour_exact);
 }
 
+// ---- the tied pixels, re-evaluated in the reference's own operation order (MCU.cpp:184-198, :228) ---------------
+// Tie record (uint4): x = pixel index in the job (image-major, row-major) or TIE_EMPTY, y = MCU index in the job,
+// z = sample index | tied components << 8 | fast Y sample << 16, w = fast Cb sample | fast Cr sample << 16 (samples
+// biased by COEF_BIAS).  A warp takes the records of 32 strips at a time and hands them out 32 per pass, so the long
+// serial evaluation always runs with (nearly) full warps.
+template <int NC>
+__device__ __noinline__ int exact_sample_global(const uint4 *tiles, const DeviceTables *T, uint32_t gb, uint32_t comp, int s)
+{
+    uint4 ch[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        ch[k] = __ldg(tiles + coef_tile_chunk(gb, (uint32_t)k));
+    const int x = s >> 3, y = s & 7;
+    double cx[8], cy[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        cx[k] = __ldg(&T->cosd[x][k]);
+        cy[k] = __ldg(&T->cosd[y][k]);
+    }
+    const float sum = exact_terms(ch, T->qint[comp], cx, cy, __ldg(&T->cc[0][0]), __ldg(&T->cc[0][1]),
+                                  std::make_integer_sequence<int, 64>{});
+    const float out = (float)mul_f64(0.25, (double)sum);
+    return round_half_away(out);
+}
+
+template <int NC>
+__global__ void __launch_bounds__(128) idct_patch_kernel(IdctArgs a)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t nwarps = gridDim.x * 4u, w = blockIdx.x * 4u + (threadIdx.x >> 5);
+    const uint4 *tiles = reinterpret_cast<const uint4 *>(a.tiles);
+    for (uint32_t s0 = w * 32u; s0 < a.nstrips; s0 += nwarps * 32u) {
+        const uint32_t strip = s0 + lane;
+        const uint32_t cnt = strip < a.nstrips ? min(__ldg(a.tie_cnt + strip), (uint32_t)TIE_LIST_CAP) : 0u;
+        uint32_t incl = cnt; // inclusive scan of the 32 strips' counts
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d)
+                incl += o;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        for (uint32_t e0 = 0; e0 < total; e0 += 32u) {
+            const uint32_t e = e0 + lane;
+            // the strip record e belongs to: the first lane whose inclusive count exceeds e (five shuffle steps)
+            uint32_t lo = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(lo + (uint32_t)step - 1u));
+                if (v <= e)
+                    lo += (uint32_t)step;
+            }
+            const uint32_t before = __shfl_sync(0xffffffffu, incl - cnt, (int)min(lo, 31u));
+            if (e >= total)
+                continue;
+            const uint4 r = __ldg(a.tie_rec + (size_t)(s0 + lo) * TIE_LIST_CAP + (e - before));
+            if (r.x == TIE_EMPTY)
+                continue;
+            const int s = (int)(r.z & 63u);
+            const uint32_t flags = (r.z >> 8) & 7u;
+            int v[3] = {(int)(r.z >> 16) - (int)COEF_BIAS, (int)(r.w & 0xFFFFu) - (int)COEF_BIAS, (int)(r.w >> 16) - (int)COEF_BIAS};
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                if (flags & (1u << c))
+                    v[c] = exact_sample_global<NC>(tiles, a.tables, r.y * NC + (uint32_t)c, (uint32_t)c, s);
+            const uint32_t px = colour_px<NC>(v[0], v[1], v[2]);
+            uint8_t *dst = a.pixels + (size_t)r.x * NC;
+            dst[0] = (uint8_t)px;
+            if (NC == 3) {
+                dst[1] = (uint8_t)(px >> 8);
+                dst[2] = (uint8_t)(px >> 16);
+            }
+        }
+    }
+}
+
 void k3_configure()
 {
     cudaFuncSetAttribute(idct_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IdctSmem<3>));
@@ -814,6 +921,13 @@ cudaError_t launch_idct(const IdctArgs &a_in, cudaStream_t s, uint32_t *launches
         idct_kernel<3><<<grid, 3 * IDCT_MCUS_PER_CTA, sizeof(IdctSmem<3>), s>>>(a);
     else
         idct_kernel<1><<<grid, IDCT_MCUS_PER_CTA, sizeof(IdctSmem<1>), s>>>(a);
+    ++*launches;
+    // the pixels inside the tie band: a small grid (a few records per strip), full warps
+    const uint32_t pgrid = std::min<uint32_t>((grid + 127u) / 128u, 148u * 8u);
+    if (a.g.ncomp == 3)
+        idct_patch_kernel<3><<<pgrid, 128, 0, s>>>(a);
+    else
+        idct_patch_kernel<1><<<pgrid, 128, 0, s>>>(a);
     ++*launches;
     return cudaSuccess;
 }

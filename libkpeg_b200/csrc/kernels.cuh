@@ -109,9 +109,12 @@ struct IdctArgs {
     uint32_t nstrips;
     const DeviceTables *tables;
     uint8_t *pixels;          // [nimages][height][width][ncomp]
+    uint4 *tie_rec;           // [nstrips][IDCT_TIE_LIST_CAP] records of the pixels inside the tie band (k3_fused.cu)
+    uint32_t *tie_cnt;        // [nstrips] entries in use
     DevMeta *meta;
     JobGeom g;
 };
+constexpr int IDCT_TIE_LIST_CAP = 96; // a strip with more ties than this resolves them inside K3
 
 
 void kernels_context_created();   // contexts of this process share the device: the cooperative relay loops of

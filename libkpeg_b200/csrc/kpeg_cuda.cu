@@ -74,7 +74,7 @@ struct Job {
 struct Lane {
     cudaStream_t stream = nullptr;
     DevBuf scan, words, seg_bit, tile_kept, tile_rst, cls, state, work, seg_hint, start_slot, scan_tiles;
-    DevBuf coef, dcdiff, dc, tiles, pixels, meta, rec, nrec, rec_alt, strip_sub, dcs, dcpre, scan_tiles_dcs;
+    DevBuf coef, dcdiff, dc, tiles, tie_rec, tie_cnt, pixels, meta, rec, nrec, rec_alt, strip_sub, dcs, dcpre, scan_tiles_dcs;
     PinBuf h_meta;
     // host-buffer batches: pinned staging of the small scans + the separator positions, and their device copy
     PinBuf h_stage, h_ends;
@@ -383,6 +383,8 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     TRY(ensure(ctx, s, L.dcpre, (size_t)nsub_max * sizeof(long long)));
     TRY(ensure(ctx, s, L.scan_tiles_dcs, ((size_t)nsub_max / 1024u + 2u) * sizeof(long long)));
     TRY(ensure(ctx, s, L.tiles, (size_t)nstrips * IDCT_MCUS_PER_CTA * g.ncomp * 128u + 256u));
+    TRY(ensure(ctx, s, L.tie_rec, (size_t)nstrips * IDCT_TIE_LIST_CAP * sizeof(uint4)));
+    TRY(ensure(ctx, s, L.tie_cnt, (size_t)nstrips * sizeof(uint32_t)));
     TRY(ensure(ctx, s, L.meta, sizeof(DevMeta)));
     TRY(ensure_pinned(ctx, s, L.h_meta, sizeof(DevMeta)));
     // records: one per value-carrying symbol.  3/8 of the subsequence's bits covers every table whose value-carrying
@@ -466,6 +468,8 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     ia.nstrips = nstrips;
     ia.tables = (const DeviceTables *)ctx->tables.p;
     ia.pixels = d_pixels;
+    ia.tie_rec = (uint4 *)L.tie_rec.p;
+    ia.tie_cnt = (uint32_t *)L.tie_cnt.p;
     ia.meta = d_meta;
     ia.g = g;
 
@@ -500,7 +504,7 @@ int check_guards(kpeg_ctx *ctx, Lane &L)
     NamedBuf bufs[] = {{"cls", &L.cls},           {"scan", &L.scan},         {"words", &L.words},       {"seg_bit", &L.seg_bit},
                        {"tile_kept", &L.tile_kept}, {"tile_rst", &L.tile_rst}, {"state", &L.state},       {"work", &L.work},
                        {"seg_hint", &L.seg_hint}, {"start_slot", &L.start_slot}, {"scan_tiles", &L.scan_tiles},
-                       {"coef", &L.coef},         {"dcdiff", &L.dcdiff},     {"tiles", &L.tiles},     {"strip_sub", &L.strip_sub}, {"dc", &L.dc}, {"dcs", &L.dcs}, {"dcpre", &L.dcpre}, {"scan_tiles_dcs", &L.scan_tiles_dcs}, {"d_ends", &L.d_ends},
+                       {"coef", &L.coef},         {"dcdiff", &L.dcdiff},     {"tiles", &L.tiles},       {"tie_rec", &L.tie_rec},   {"tie_cnt", &L.tie_cnt},     {"strip_sub", &L.strip_sub}, {"dc", &L.dc}, {"dcs", &L.dcs}, {"dcpre", &L.dcpre}, {"scan_tiles_dcs", &L.scan_tiles_dcs}, {"d_ends", &L.d_ends},
                        {"pixels", &L.pixels},     {"meta", &L.meta},
                        {"rec", &L.rec},           {"nrec", &L.nrec},         {"rec_alt", &L.rec_alt},   {"tables", &ctx->tables}};
     uint8_t host[2 * GUARD_BYTES];
@@ -704,7 +708,7 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
         if (L.stream)
             cudaStreamSynchronize(L.stream);
         DevBuf *bufs[] = {&L.cls,  &L.scan, &L.words,    &L.seg_bit,    &L.tile_kept,  &L.tile_rst, &L.state,
-                          &L.work, &L.seg_hint, &L.start_slot, &L.scan_tiles, &L.coef,     &L.dcdiff, &L.tiles,
+                          &L.work, &L.seg_hint, &L.start_slot, &L.scan_tiles, &L.coef,     &L.dcdiff, &L.tiles, &L.tie_rec, &L.tie_cnt,
                           &L.strip_sub, &L.dc, &L.dcs, &L.dcpre, &L.scan_tiles_dcs, &L.pixels, &L.meta,
                           &L.rec,  &L.nrec,       &L.rec_alt};
         for (DevBuf *b : bufs)

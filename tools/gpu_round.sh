@@ -4,7 +4,7 @@ tag=$1
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_tests.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_tests.txt
 tail -5 gpurun_out/${tag}_tests.txt
-python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err || tail -20 gpurun_out/${tag}_bench.err
+python bench.py --steps 20 --warmup 3 ${BENCH_FLAGS:---no-extras --no-cpu-baseline} > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err || tail -20 gpurun_out/${tag}_bench.err
 python - "$tag" <<'PY'
 import json,sys
 try:
@@ -13,9 +13,9 @@ try:
 except Exception as e:
     print("bench ERR", e)
 PY
-B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --skip-pixel-check"
+B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --skip-pixel-check --no-extras --quick"
 $B > gpurun_out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${tag}_launches.csv $B > gpurun_out/${tag}_ncu1.log 2>&1
 $B > gpurun_out/${tag}_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'idct_kernel|expand_kernel|entropy_relay_full|entropy_cold' -s 88 -c 4 -o gpurun_out/${tag}_prof -f $B > gpurun_out/${tag}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'idct_kernel|idct_patch|expand_kernel|entropy_relay_full|entropy_cold' -s 50 -c 5 -o gpurun_out/${tag}_prof -f $B > gpurun_out/${tag}_ncu2.log 2>&1
 tail -3 gpurun_out/${tag}_ncu2.log
