@@ -26,6 +26,10 @@ def build_product(targets=("all",)) -> None:
 def build_oracle() -> None:
     """oracle/_ref: the CPU restatement, and the unmodified reference when /root/reference exists."""
     _run(["make", "all"], cwd=ROOT / "oracle")
+    # the reference's own executable with its hot path replaced by the C ABI (INTEGRATION.md section 2), when
+    # /root/reference is present; needs libkpeg_cuda.so, so build_product() first
+    import sys
+    _run([sys.executable, str(ROOT / "oracle" / "hybrid" / "build.py")], cwd=ROOT)
 
 
 def build_emu() -> None:

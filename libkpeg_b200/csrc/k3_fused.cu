@@ -853,13 +853,16 @@ __device__ __noinline__ int exact_sample_global(const uint4 *tiles, const Device
     return round_half_away(out);
 }
 
+constexpr int PATCH_WARPS = 8;
+
 template <int NC>
-__global__ void __launch_bounds__(128) idct_patch_kernel(IdctArgs a)
+__global__ void __launch_bounds__(PATCH_WARPS * 32) idct_patch_kernel(IdctArgs a)
 {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t nwarps = gridDim.x * 4u, w = blockIdx.x * 4u + (threadIdx.x >> 5);
+    // one CTA per 32 strips; its warps share the passes over the group's records (a pass = 32 records, one per lane):
+    // every pass is a long serial chain, so it is the number of warps in flight that hides it
+    const uint32_t lane = threadIdx.x & 31u, wl = threadIdx.x >> 5;
     const uint4 *tiles = reinterpret_cast<const uint4 *>(a.tiles);
-    for (uint32_t s0 = w * 32u; s0 < a.nstrips; s0 += nwarps * 32u) {
+    for (uint32_t s0 = blockIdx.x * 32u; s0 < a.nstrips; s0 += gridDim.x * 32u) {
         const uint32_t strip = s0 + lane;
         const uint32_t cnt = strip < a.nstrips ? min(__ldg(a.tie_cnt + strip), (uint32_t)TIE_LIST_CAP) : 0u;
         uint32_t incl = cnt; // inclusive scan of the 32 strips' counts
@@ -870,7 +873,7 @@ __global__ void __launch_bounds__(128) idct_patch_kernel(IdctArgs a)
                 incl += o;
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        for (uint32_t e0 = 0; e0 < total; e0 += 32u) {
+        for (uint32_t e0 = wl * 32u; e0 < total; e0 += PATCH_WARPS * 32u) {
             const uint32_t e = e0 + lane;
             // the strip record e belongs to: the first lane whose inclusive count exceeds e (five shuffle steps)
             uint32_t lo = 0;
@@ -923,11 +926,11 @@ cudaError_t launch_idct(const IdctArgs &a_in, cudaStream_t s, uint32_t *launches
         idct_kernel<1><<<grid, IDCT_MCUS_PER_CTA, sizeof(IdctSmem<1>), s>>>(a);
     ++*launches;
     // the pixels inside the tie band: a small grid (a few records per strip), full warps
-    const uint32_t pgrid = std::min<uint32_t>((grid + 127u) / 128u, 148u * 8u);
+    const uint32_t pgrid = std::min<uint32_t>((grid + 31u) / 32u, 148u * 16u);
     if (a.g.ncomp == 3)
-        idct_patch_kernel<3><<<pgrid, 128, 0, s>>>(a);
+        idct_patch_kernel<3><<<pgrid, PATCH_WARPS * 32, 0, s>>>(a);
     else
-        idct_patch_kernel<1><<<pgrid, 128, 0, s>>>(a);
+        idct_patch_kernel<1><<<pgrid, PATCH_WARPS * 32, 0, s>>>(a);
     ++*launches;
     return cudaSuccess;
 }

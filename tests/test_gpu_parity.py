@@ -190,6 +190,27 @@ def test_cli_drop_in(tmp_path, lena_jpg):
     assert not (tmp_path / "lena.ppm.x").exists()
 
 
+@pytest.mark.skipif(not (ROOT / "oracle" / "_ref" / "kpeg_ref_cuda").exists(), reason="hybrid binary did not travel to this box")
+def test_reference_with_cuda_hot_path(tmp_path, lena_jpg):
+    """INTEGRATION.md section 2, compiled: the REFERENCE's executable -- its parser, Image class and PPM writer, built from
+    /root/reference by oracle/hybrid/build.py -- with decodeScanData() + createImageFromMCUs() replaced by the C ABI.  The
+    PPM it writes for lena.jpg is byte-identical to the unmodified reference's (golden hash)."""
+    exe = ROOT / "oracle" / "_ref" / "kpeg_ref_cuda"
+    p = tmp_path / "lena.jpg"
+    p.write_bytes(lena_jpg)
+    r = subprocess.run([str(exe), str(p)], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    g = np.load(ROOT / "tests" / "golden" / "lena_ref.npz")
+    assert hashlib.sha256((tmp_path / "lena.ppm").read_bytes()).hexdigest() == str(g["ppm_sha256"])
+    # and a synthetic stream against the CUDA path's own CLI
+    jpg = synth_encode(SynthParams(136, 72, quality=85, seed=77)).tobytes()
+    (tmp_path / "a.jpg").write_bytes(jpg)
+    (tmp_path / "b.jpg").write_bytes(jpg)
+    subprocess.run([str(exe), "a.jpg"], cwd=tmp_path, capture_output=True, timeout=300, check=True)
+    subprocess.run([str(ROOT / "libkpeg_b200" / "lib" / "kpeg"), "--quiet", "b.jpg"], cwd=tmp_path, capture_output=True, timeout=300, check=True)
+    assert (tmp_path / "a.ppm").read_bytes() == (tmp_path / "b.ppm").read_bytes()
+
+
 @pytest.mark.skipif(not H.have_reference_binary(), reason="compiled reference did not travel to this box")
 def test_against_compiled_reference_live(decoder, tmp_path):
     """Run the unmodified reference here, on this box's libm, against the CUDA path."""
