@@ -329,6 +329,21 @@ class Decoder:
         rc = self._lib.kpeg_cuda_submit_batch(self._h, C.byref(plan), n, sp, sl, op)
         self._check(rc, "kpeg_cuda_submit_batch")
 
+    def prepare_batch(self, scans: list[np.ndarray], outs: list[np.ndarray]):
+        """The pointer / length arrays kpeg_cuda_submit_batch takes, built once for buffers that are reused step after
+        step (the marshalling of thousands of numpy arrays costs more than the call).  -> handle for submit_prepared."""
+        n = len(scans)
+        for a in list(scans) + list(outs):
+            if not (a.flags["C_CONTIGUOUS"] and a.dtype == np.uint8):
+                raise ValueError("prepare_batch needs contiguous uint8 arrays (they are used in place)")
+        return (n, (_vp * n)(*[_ptr(s) for s in scans]), (C.c_size_t * n)(*[s.size for s in scans]),
+                (_vp * n)(*[_ptr(o) for o in outs]), scans, outs)
+
+    def submit_prepared(self, plan: Plan, handle):
+        n, sp, sl, op, scans, outs = handle
+        self._pending.append((scans, outs))
+        self._check(self._lib.kpeg_cuda_submit_batch(self._h, C.byref(plan), n, sp, sl, op), "kpeg_cuda_submit_batch")
+
     def wait(self):
         rc = self._lib.kpeg_cuda_wait(self._h, C.byref(self.last_stats))
         self._pending.clear()
@@ -366,6 +381,19 @@ def decode_file_tiled(devices: list[int], data, flags: int = KPEG_FLAG_REF_PARIT
     if rc != KPEG_OK:
         raise KpegError(rc, f"kpeg_cuda_decode_file_tiled: {lib.kpeg_tiled_last_error().decode(errors='replace')}")
     return out.reshape(shape), st
+
+
+def decode_tiled(devices: list[int], plan: Plan, scan: np.ndarray, out: np.ndarray) -> Stats:
+    """kpeg_cuda_decode_tiled on an already parsed image: restart-interval bands of `scan`, one per listed device (a
+    device may be listed several times: its bands then overlap their copies and kernels), into the rows of `out`."""
+    lib = load_cuda_library()
+    assert out.nbytes == plan.height * plan.width * plan.ncomp and out.flags.c_contiguous and scan.flags.c_contiguous
+    dv = (C.c_int * len(devices))(*devices)
+    st = Stats()
+    rc = lib.kpeg_cuda_decode_tiled(dv, len(devices), C.byref(plan), _ptr(scan), scan.size, _ptr(out), C.byref(st))
+    if rc != KPEG_OK:
+        raise KpegError(rc, f"kpeg_cuda_decode_tiled: {lib.kpeg_tiled_last_error().decode(errors='replace')}")
+    return st
 
 
 def packed_offsets(scans: list[np.ndarray]) -> np.ndarray:

@@ -185,7 +185,11 @@ __global__ void __launch_bounds__(EXPAND_THREADS, KPEG_EXPAND_MIN_CTAS) expand_k
             part[c] = __reduce_add_sync(0xffffffffu, part[c]);
         if (lane == 0) {
             int pre[3] = {0, 0, 0};
-            if (ss >= reset_slot && reset_slot < s0) // no restart between the subsequence's entry and the strip
+            // no restart between the subsequence's entry and the strip.  An entry ON the restart slot (ss == reset_slot)
+            // starts from zero: either the boundary was crossed at the very end of the subsequence before (its sums
+            // are zero anyway) or the subsequence is entered in the padding bits BEFORE the boundary, and the prefix
+            // it was handed still belongs to the interval that is ending
+            if (ss > reset_slot && reset_slot < s0)
                 dcs_unpack(a.dcpre[first0], pre);
             sm.carry[0] = pre[0] + part[0];
             sm.carry[1] = pre[1] + part[1];

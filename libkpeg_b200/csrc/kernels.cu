@@ -303,6 +303,45 @@ __global__ void __launch_bounds__(256) write_separators_kernel(uint8_t *scan, co
     }
 }
 
+// Host-buffer batches whose scans lie back to back in host memory travel as ONE copy into a staging buffer; this kernel
+// moves scan i from there to its place in the lane's stream buffer (two bytes further on per scan: the separators) and
+// writes the RSTn after it.  ends[i] = offset just past scan i in the DESTINATION (as for write_separators_kernel), so
+// scan i starts at ends[i-1] + 2 there and at ends[i-1] + 2 - 2 i in the staging buffer.  One CTA per scan and
+// round; destination words are written whole (two source words and a funnel shift), the ragged ends byte by byte.
+__global__ void __launch_bounds__(256) repack_scans_kernel(const uint8_t *stage, uint8_t *scan, const uint64_t *ends, uint32_t n)
+{
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint64_t d0 = i ? ends[i - 1] + 2u : 0u, d1 = ends[i]; // destination byte range of the scan
+        const uint8_t *src = stage + (d0 - 2ull * i);
+        uint8_t *dst = scan + d0;
+        const uint64_t len = d1 - d0;
+        const uint64_t to_word = (4u - (reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u;
+        const uint64_t head = len < to_word ? len : to_word;
+        const uint64_t nwords = (len - head) >> 2;
+        const uint8_t *sw = src + head; // source of the first whole destination word
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(sw) & 3u);
+        const uint32_t *sa = reinterpret_cast<const uint32_t *>(sw - mis);
+        uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+        for (uint64_t w = threadIdx.x; w < nwords; w += 256u) {
+            const uint32_t lo = __ldg(sa + w);
+            dw[w] = mis ? __funnelshift_r(lo, __ldg(sa + w + 1u), 8u * mis) : lo;
+        }
+        for (uint64_t b = threadIdx.x; b < head; b += 256u)
+            dst[b] = src[b];
+        for (uint64_t b = head + (nwords << 2) + threadIdx.x; b < len; b += 256u)
+            dst[b] = src[b];
+        if (threadIdx.x == 0) {
+            scan[d1] = 0xFFu;
+            scan[d1 + 1u] = (uint8_t)(0xD0u + (i & 7u));
+        }
+    }
+}
+
+void launch_repack_scans(const uint8_t *stage, uint8_t *scan, const uint64_t *ends, uint32_t n, cudaStream_t s)
+{
+    repack_scans_kernel<<<n < 148u * 8u ? n : 148u * 8u, 256, 0, s>>>(stage, scan, ends, n);
+}
+
 void launch_write_separators(uint8_t *scan, const uint64_t *ends, uint32_t n, cudaStream_t s)
 {
     write_separators_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(scan, ends, n);

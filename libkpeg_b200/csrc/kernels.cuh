@@ -120,6 +120,7 @@ constexpr int IDCT_TIE_LIST_CAP = 96; // a strip with more ties than this resolv
 void kernels_context_created();   // contexts of this process share the device: the cooperative relay loops of
 void kernels_context_destroyed(); // all of them together must stay co-resident
 void kernels_configure(int max_concurrent_jobs); // jobs (lanes) that may be on the device at the same time // per-device function attributes (call once after cudaSetDevice)
+void launch_repack_scans(const uint8_t *stage, uint8_t *scan, const uint64_t *ends, uint32_t n, cudaStream_t s); // contiguous host scans -> packed batch
 void launch_write_separators(uint8_t *scan, const uint64_t *ends, uint32_t n, cudaStream_t s); // RSTn after every scan of a packed batch
 void launch_gray_to_rgb(const uint8_t *gray, uint8_t *rgb, size_t npixels, cudaStream_t s);     // PPM payload of a one-component image
 void launch_rgb_to_planar(const uint8_t *rgb, uint8_t *planes, size_t npixels, cudaStream_t s); // [3][H][W] planes

@@ -78,7 +78,7 @@ struct Lane {
     PinBuf h_meta;
     // host-buffer batches: pinned staging of the small scans + the separator positions, and their device copy
     PinBuf h_stage, h_ends;
-    DevBuf d_ends;
+    DevBuf d_ends, d_stage;
     cudaEvent_t ev[MAX_EVENTS] = {};
     int ev_stage[MAX_EVENTS] = {};
     int nev = 0;
@@ -720,6 +720,7 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
         if (L.h_ends.p)
             cudaFreeHost(L.h_ends.p);
         dev_free(L.d_ends);
+        dev_free(L.d_stage);
         for (int i = 0; i < MAX_EVENTS; ++i)
             if (L.ev[i])
                 cudaEventDestroy(L.ev[i]);
@@ -1074,32 +1075,52 @@ extern "C" int kpeg_cuda_submit_batch(kpeg_ctx *ctx, const kpeg_plan *plan, int 
             TRY(ensure_pinned(ctx, L.stream, L.h_stage, small_bytes));
         mark(ctx, L, -1);
         uint64_t *ends = (uint64_t *)L.h_ends.p;
-        uint8_t *stage = (uint8_t *)L.h_stage.p;
-        size_t o = 0, so = 0, run_o = 0, run_so = 0; // device offset, staging offset, start of the open staged run
-        auto flush_run = [&]() -> cudaError_t {
-            if (so == run_so)
-                return cudaSuccess;
-            const cudaError_t e = cudaMemcpyAsync((uint8_t *)L.scan.p + run_o, stage + run_so, so - run_so, cudaMemcpyHostToDevice, L.stream);
-            run_so = so;
-            return e;
-        };
-        for (int i = i0; i < i1; ++i) {
-            if (scan_lens[i] < SMALL_SCAN) {
-                if (so == run_so)
-                    run_o = o;
-                memcpy(stage + so, scans[i], scan_lens[i]);
-                so += scan_lens[i] + 2; // the separator's two bytes travel with the run; the kernel below fills them in
-            } else {
-                CK(flush_run());
-                CK(cudaMemcpyAsync((uint8_t *)L.scan.p + o, scans[i], scan_lens[i], cudaMemcpyHostToDevice, L.stream));
+        // (0) scans that lie back to back in host memory (a caller that keeps its files in one arena): ONE copy of the
+        // whole run into a device staging buffer, and a kernel that moves every scan to its place (the separators need
+        // two bytes between scans, so the run cannot be copied to its final place directly)
+        bool contiguous = m >= 2;
+        for (int i = i0; contiguous && i + 1 < i1; ++i)
+            contiguous = scans[i] + scan_lens[i] == scans[i + 1];
+        if (contiguous) {
+            const size_t run = total - 2u * (size_t)m;
+            TRY(ensure(ctx, L.stream, L.d_stage, run + 64));
+            size_t o = 0;
+            for (int i = i0; i < i1; ++i) {
+                o += scan_lens[i];
+                ends[i - i0] = o;
+                o += 2;
             }
-            o += scan_lens[i];
-            ends[i - i0] = o;
-            o += 2;
+            CK(cudaMemcpyAsync(L.d_stage.p, scans[i0], run, cudaMemcpyHostToDevice, L.stream));
+            CK(cudaMemcpyAsync(L.d_ends.p, ends, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, L.stream));
+            launch_repack_scans((const uint8_t *)L.d_stage.p, (uint8_t *)L.scan.p, (const uint64_t *)L.d_ends.p, (uint32_t)m, L.stream);
+        } else {
+            uint8_t *stage = (uint8_t *)L.h_stage.p;
+            size_t o = 0, so = 0, run_o = 0, run_so = 0; // device offset, staging offset, start of the open staged run
+            auto flush_run = [&]() -> cudaError_t {
+                if (so == run_so)
+                    return cudaSuccess;
+                const cudaError_t e = cudaMemcpyAsync((uint8_t *)L.scan.p + run_o, stage + run_so, so - run_so, cudaMemcpyHostToDevice, L.stream);
+                run_so = so;
+                return e;
+            };
+            for (int i = i0; i < i1; ++i) {
+                if (scan_lens[i] < SMALL_SCAN) {
+                    if (so == run_so)
+                        run_o = o;
+                    memcpy(stage + so, scans[i], scan_lens[i]);
+                    so += scan_lens[i] + 2; // the separator's two bytes travel with the run; the kernel below fills them in
+                } else {
+                    CK(flush_run());
+                    CK(cudaMemcpyAsync((uint8_t *)L.scan.p + o, scans[i], scan_lens[i], cudaMemcpyHostToDevice, L.stream));
+                }
+                o += scan_lens[i];
+                ends[i - i0] = o;
+                o += 2;
+            }
+            CK(flush_run());
+            CK(cudaMemcpyAsync(L.d_ends.p, ends, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, L.stream));
+            launch_write_separators((uint8_t *)L.scan.p, (const uint64_t *)L.d_ends.p, (uint32_t)m, L.stream);
         }
-        CK(flush_run());
-        CK(cudaMemcpyAsync(L.d_ends.p, ends, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, L.stream));
-        launch_write_separators((uint8_t *)L.scan.p, (const uint64_t *)L.d_ends.p, (uint32_t)m, L.stream);
         mark(ctx, L, KPEG_T_H2D);
         // Copies out: one per run of images whose host buffers follow each other (a caller that decodes into one
         // frame buffer gets ONE copy per chunk)

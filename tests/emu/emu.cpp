@@ -255,7 +255,7 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
                 const uint32_t reset_slot = (img * g.mcus_per_image + mreset) * nc * 64u;
                 const uint32_t ss = start[first0];
                 int carry[3] = {0, 0, 0};
-                if (ss >= reset_slot && reset_slot < s0)
+                if (ss > reset_slot && reset_slot < s0) // an entry ON the restart slot may still lie before the boundary (padding bits)
                     dcs_unpack(dcpre[first0], carry);
                 if (ss < s0 && reset_slot < s0)
                     for (uint32_t r : all_recs[first0]) {

@@ -5,7 +5,7 @@ import ctypes as C
 
 import numpy as np
 import pytest
-from hypothesis import given, settings
+from hypothesis import example, given, settings
 from hypothesis import strategies as st
 
 import helpers as H
@@ -89,6 +89,8 @@ def test_corrupt_stream_flags_an_error(lena_jpg):
 @settings(max_examples=25, deadline=None)
 @given(w=st.integers(1, 96), h=st.integers(1, 64), q=st.integers(5, 100), ri=st.integers(0, 9),
        nc=st.sampled_from([1, 3]), seed=st.integers(0, 2 ** 31), sb=st.sampled_from([64, 128, 512]))
+# a subsequence entered in the padding bits BEFORE a restart boundary whose slot is also where a strip's predictors restart
+@example(w=57, h=33, q=5, ri=7, nc=1, seed=5, sb=64)
 def test_property_random_streams(w, h, q, ri, nc, seed, sb):
     flags = QUIRK_FREE | (EMIT_RESTART if ri else 0) | (GRAY_CONTENT if nc == 1 else 0)
     jpg = synth_encode(SynthParams(w, h, file_components=nc, quality=q, restart_interval=ri, flags=flags, seed=seed,

@@ -153,6 +153,20 @@ def test_host_batch_small_and_large_scans_contiguous_outputs(decoder):
     decoder.decode_batch(plan, scans, outs)
     for i, (a, b) in enumerate(zip(outs, want)):
         assert np.array_equal(a, b), f"image {i} (contiguous outputs)"
+    # scans back to back in ONE host arena: a single copy in, repacked on the device
+    arena = api.PinnedArray(sum(sc.size for sc in scans))
+    views, o = [], 0
+    for sc in scans:
+        arena.array[o:o + sc.size] = sc
+        views.append(arena.array[o:o + sc.size])
+        o += sc.size
+    frame.array[:] = 0
+    handle = decoder.prepare_batch(views, outs)
+    decoder.submit_prepared(plan, handle)
+    decoder.wait()
+    for i, (a, b) in enumerate(zip(outs, want)):
+        assert np.array_equal(a, b), f"image {i} (contiguous inputs)"
+    arena.free()
     outs2 = [np.empty((h, w, 3), dtype=np.uint8) for _ in jpgs]  # separate buffers: one copy per image
     decoder.decode_batch(plan, scans, outs2)
     for i, (a, b) in enumerate(zip(outs2, want)):

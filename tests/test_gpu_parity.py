@@ -434,6 +434,21 @@ def test_random_streams_on_the_gpu(decoder):
         decoder.set_tuning(sub_bits=512)
 
 
+def test_strip_entered_in_the_padding_before_a_restart(decoder):
+    """Regression (found by tests/test_emu_logic.py::test_property_random_streams): several restart intervals inside one
+    64-bit subsequence, and a strip of 32 MCUs whose first subsequence is entered in the padding bits before the restart
+    boundary that is also the strip's predictor restart -- the DC prefix handed to that subsequence belongs to the
+    interval that is ending and must not be used."""
+    decoder.set_tuning(sub_bits=64)
+    try:
+        for seed in range(5, 25):
+            jpg = synth_encode(SynthParams(57, 33, file_components=1, quality=5, restart_interval=7,
+                                           flags=QUIRK_FREE | EMIT_RESTART | GRAY_CONTENT, seed=seed, noise_amp=seed % 60 + 1)).tobytes()
+            check_against_oracle(decoder, jpg)
+    finally:
+        decoder.set_tuning(sub_bits=512)
+
+
 def test_pil_encoded_files_with_optimised_tables(decoder):
     """Files from another encoder (libjpeg via PIL, 4:4:4): standard and per-image OPTIMISED Huffman tables (code
     lengths up to 16, symbols in another order, tables shared between components or not), comment segments, natural
