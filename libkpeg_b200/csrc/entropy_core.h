@@ -20,6 +20,10 @@
 
 #include "kpeg_common.h"
 
+#ifndef KPEG_BLOCK_END_BRANCH
+#define KPEG_BLOCK_END_BRANCH 0 // 1: the end of a block as a branch of the symbol loop (relay_run); 0: selects
+#endif
+
 namespace kpeg {
 
 KPEG_HD uint32_t max_u32(uint32_t a, uint32_t b) { return a > b ? a : b; }
@@ -61,6 +65,12 @@ struct PlainWords { // word `gw` of the big-endian stream from a plain array
 #else
         return words[gw];
 #endif
+    }
+    // words j and j + 1: the 64 bits a symbol that begins in word j can touch
+    KPEG_HD void pair(uint32_t j, uint32_t &w0, uint32_t &w1) const
+    {
+        w0 = (*this)(j);
+        w1 = (*this)(j + 1u);
     }
 };
 
@@ -137,14 +147,15 @@ constexpr uint32_t COEF_BIAS = 0x8000u; // coefficients travel as value + COEF_B
 KPEG_HD uint32_t biased_extend(uint32_t win, uint32_t T, uint32_t size)
 {
     const uint32_t x = win << (T - size);            // magnitude bits left-aligned
-    const uint32_t m = (uint32_t)((int32_t)x >> 31); // all ones: leading 1, the value itself; zero: leading 0, value - (2^size - 1)
+    const uint32_t s = (uint32_t)((int32_t)x >> 31); // all ones: leading 1, the value itself; zero: leading 0, value - (2^size - 1)
+    const uint32_t t = x ^ ~s;                       // leading 0: complemented, so that the field below is (2^size - 1) - raw
 #if defined(__CUDA_ARCH__)
-    const uint32_t raw = __funnelshift_rc(x, 0u, 32u - size); // one clamped shift (size == 0: 32 bits)
+    const uint32_t u = __funnelshift_rc(t, 0u, 32u - size); // one clamped shift (size == 0: 32 bits, i.e. 0)
 #else
-    const uint32_t raw = (x >> 16) >> (16u - size);
+    const uint32_t u = (t >> 16) >> (16u - size);
 #endif
-    // raw - (2^size - 1 where the leading bit is 0) == raw + ((-1 << size) | m) + 1
-    return raw + ((0xFFFFFFFFu << size) | m) + (COEF_BIAS + 1u);
+    // raw, or -((2^size - 1) - raw): one multiply-add by +-1 with the bias as the addend
+    return u * (~s | 1u) + COEF_BIAS;
 }
 
 // SubState::cz = (component << 8) | zig-zag index in the low 10 bits -- the decoder STATE, the part the relay's
@@ -244,13 +255,19 @@ KPEG_HD SubState relay_exit_state(const DecState &d)
 // Decode from the state in `d` until the first symbol boundary at or after `end_bit`; produces the exit state, the
 // slot count and -- EMIT -- one record per value-carrying symbol.
 //
-// Loop state: bit position p with the words j, j+1 of the stream in registers, sh = p & 31 (a symbol is at most 27
-// bits, so two words always cover it); word j+2 is fetched unconditionally at the top of every iteration and rotated
-// in, branch-free, when sh crosses 32 -- lanes of a warp cross word boundaries at different symbols, a conditional
-// refill would be executed (mostly masked) by every warp on almost every iteration.  Table offset
-// toff = (2*component + (z != 0)) * LUT_SIZE: a DC symbol switches to the component's AC table (toff |= LUT_SIZE),
-// the end of a block to the next table in the ring.  q is the running record position (block * 64 + zig-zag index,
-// counted from the first slot of the entry block); the zig-zag index is q & 63.
+// Loop state: the bit position p alone.  Every iteration loads the two stream words that cover the symbol (W.pair:
+// words p / 32 and p / 32 + 1 from the thread's own shared-memory region, one multiply-add for the address) and takes
+// the 32-bit window with one funnel shift whose count is p itself (taken modulo 32).  A symbol is at most 27 bits.
+// (Keeping the words in registers and rotating a look-ahead word in cost ten instructions per symbol; the two loads
+// cost two, and the kernels are bound by instruction issue, not by the latency of the chain.)
+//
+// Table offset toff = (2*component + (z != 0)) * LUT_SIZE: a DC symbol switches to the component's AC table
+// (toff |= LUT_SIZE), the end of a block to the next table in the ring.  q is the running record position
+// (block * 64 + zig-zag index, counted from the first slot of the entry block); the zig-zag index is q & 63.
+//
+// The end of a block (next table of the ring, position rounded up to the next block) is a chain of selects by default;
+// KPEG_BLOCK_END_BRANCH=1 builds it as a branch (measured at 4K q95: two dozen symbols per block, so 70 % of a warp's
+// iterations have a lane that ends a block and run the branch body for that one lane -- no gain).
 //
 // Errors of the decode are annotations of the exit state (CZ_*), not device status bits: a speculative decode from a
 // wrong entry state meets "errors" that mean nothing; only the annotations of the LAST decode of a subsequence -- the
@@ -258,90 +275,119 @@ KPEG_HD SubState relay_exit_state(const DecState &d)
 //
 // DCS: also add up the DC differences per component (dcs_weight / dcs_unpack above).  wd is the weight the NEXT
 // symbol's value is added with: 2^(15 component) when that symbol is a DC difference, 0 otherwise -- so the sum costs
-// one multiply-add per symbol and two selects, no test of what kind of symbol it was.  (biased_extend gives exactly
-// COEF_BIAS for a symbol without magnitude bits, i.e. the value 0.)
+// one multiply-add per symbol, no test of what kind of symbol it was.  (biased_extend gives exactly COEF_BIAS for a
+// symbol without magnitude bits, i.e. the value 0.)
 template <bool EMIT, bool DCS = false, class Words, class Luts, class Rec>
 KPEG_HD void relay_run(DecState &d, const Words &W, const Luts &L, const StreamView &S, const JobGeom &g, uint32_t end_bit,
                        const Rec &rec)
 {
     const uint32_t ring_last = (g.ncomp * 2u - 1u) * (uint32_t)LUT_SIZE; // the last table of the ring: the last component's AC table
-    long long dcs = d.dcs;
     uint32_t wc = dcs_weight(d.toff >> (LUT_BITS + 1));                    // weight of the current component
     uint32_t wd = (d.toff & (uint32_t)LUT_SIZE) ? 0u : wc;                 // ... if the next symbol is its DC difference
-    uint32_t p = d.p, j = d.j, sh = d.sh, w0 = d.w0, w1 = d.w1, toff = d.toff, q = d.q, qj = d.qj;
+    unsigned long long dcs = (unsigned long long)d.dcs, wsum = wd;         // biased sum; the weights that go with it
+    uint32_t p = d.p, toff = d.toff, q = d.q, qj = d.qj;
     uint32_t k = d.k, segend = d.segend, nrec = d.nrec, flags = d.flags;
     int32_t seg = d.seg;
     // one running maximum finds both kinds of bad symbol: a value-carrying symbol must end inside its block
     // (zig-zag index + advance <= 64), a symbol without a value must have a real advance (1, 16 or 64; "no code
-    // matches" is the entry with the impossible advance 127)
+    // matches" is the entry with the impossible advance 127).  Only a symbol that reaches the end of its block can be
+    // either, so the maximum is taken there.
     uint32_t worst = 0;
+    uint32_t blk_end = (q | 63u) + 1u; // position of the next block's slot 0
     auto symbol = [&](uint32_t win, uint32_t e) { // everything a symbol does except moving the bit position
         const uint32_t T = e & 31u, adv = e >> 9, size = (e >> 5) & 15u;
-        const uint32_t zn = (q & 63u) + adv;
+        const uint32_t qn = q + adv;
         if (EMIT || DCS) {
             const uint32_t bv = biased_extend(win, T, size);
             if (EMIT) {
                 // no branch: the record word is computed for every symbol (nearly all of them carry a value) and the
                 // store alone is predicated
-                worst = max_u32(worst, size ? zn : adv);
-                rec.emit(size != 0u, nrec, record_pack(q + adv - 1u, bv));
-                nrec += size < 1u ? size : 1u;
+                rec.emit(size != 0u, nrec, record_pack(qn - 1u, bv));
+                nrec += size != 0u ? 1u : 0u;
             }
+#if KPEG_BLOCK_END_BRANCH
+            if (DCS) { // the biased value; COEF_BIAS times the weights used comes off at the end
+                dcs += (unsigned long long)bv * wd;
+                wd = 0u;
+            }
+#else
             if (DCS)
-                dcs += (long long)(int32_t)(bv - COEF_BIAS) * (long long)(int32_t)wd;
+                dcs += (unsigned long long)((long long)(int32_t)(bv - COEF_BIAS) * (long long)(int32_t)wd);
+#endif
         }
-        // end of the block: next table of the ring (a block ends in its AC table); selects, not a branch -- some lane of a
-        // warp ends a block in almost every iteration, so both sides of a branch would be issued anyway
-        const bool endb = zn >= 64u;
+#if KPEG_BLOCK_END_BRANCH
+        uint32_t tn = toff | (uint32_t)LUT_SIZE;
+        q = qn;
+        if (qn >= blk_end) { // end of the block (EOB, or a coefficient in slot 63 -- or beyond: garbage)
+            if (EMIT)
+                worst = max_u32(worst, size ? qn - (blk_end - 64u) : adv);
+            const bool wrap = toff == ring_last;
+            tn = wrap ? 0u : toff + (uint32_t)LUT_SIZE; // next table of the ring (a block ends in its AC table)
+            q = blk_end;
+            blk_end += 64u;
+            if (DCS) {
+                wc = wrap ? 1u : wc << DCS_SHIFT;
+                wd = wc;
+                wsum += wc;
+            }
+        }
+        toff = tn;
+#else
+        // end of the block (EOB, or a coefficient in slot 63 -- or beyond: garbage): selects, not a branch -- with two
+        // dozen symbols per block some lane of a warp ends a block in most iterations, and a divergent branch then runs
+        // its body for that one lane (measured: 70 % of the iterations at 4K q95)
+        const bool endb = qn >= blk_end;
         const bool wrap = toff == ring_last;
-        q = endb ? (q | 63u) + 1u : q + adv;
-        toff = endb ? (wrap ? 0u : toff + (uint32_t)LUT_SIZE) : (toff | (uint32_t)LUT_SIZE);
+        if (EMIT)
+            worst = max_u32(worst, size ? qn + 64u - blk_end : adv);
+        q = endb ? blk_end : qn;
+        blk_end += endb ? 64u : 0u;
+        toff = endb ? (wrap ? 0u : toff + (uint32_t)LUT_SIZE) : (toff | (uint32_t)LUT_SIZE); // next table of the ring / the AC table
         if (DCS) {
             wc = endb ? (wrap ? 1u : wc << DCS_SHIFT) : wc;
             wd = endb ? wc : 0u;
         }
+#endif
     };
     auto cross_boundary = [&]() { // onto boundary k: state (segend, component 0, DC), position and DC sums restart
         q = (q + 63u) & ~63u;
         if (seg >= 0 && q - qj != seg_slot_base(g, k) - seg_slot_base(g, (uint32_t)seg))
             flags |= CZ_SEG_MISMATCH; // the interval between the last boundary and this one
         qj = q;
+        blk_end = q + 64u;
         seg = (int32_t)k;
         p = segend;
         toff = 0;
         if (DCS) { // predictors restart with the interval (T.81 F.2.1.3.1)
             dcs = 0;
             wc = wd = 1u;
+            wsum = 1u;
         }
         ++k;
         segend = S.seg_bit[k];
     };
     // Fast lane.  When the next boundary lies at least a symbol beyond end_bit (always, without restart markers,
     // except next to an image end) no symbol of this call can straddle it, and with a word-aligned end_bit
-    // "p < end_bit" is "j < end_bit / 32": the loop carries neither p nor a boundary test.
+    // "p < end_bit" is "p / 32 < end_bit / 32": the loop carries no boundary test.
     if (p < end_bit && (end_bit & 31u) == 0u && segend >= end_bit + 32u) {
-        // the funnel shift takes its count modulo 32, so the bit position itself is the count: no separate
-        // "bits into the word" counter to keep in step
         const uint32_t jend = end_bit >> 5;
-        while (j < jend) {
-            const uint32_t nxt = W(j + 2u);
-            const uint32_t win = funnel_left(w0, w1, p);
+        uint32_t j = p >> 5;
+        do {
+            uint32_t w0, w1;
+            W.pair(j, w0, w1);
+            const uint32_t win = funnel_left(w0, w1, p); // the count is taken modulo 32
             uint32_t e = L.fast(toff, win >> (32 - LUT_BITS));
             if ((e & 31u) == 0u)
                 e = L.slow(toff, win, e);
             symbol(win, e);
             p += e & 31u;
-            const uint32_t jn = p >> 5;
-            const bool cross = jn != j;
-            w0 = cross ? w1 : w0;
-            w1 = cross ? nxt : w1;
-            j = jn;
-        }
-        sh = p & 31u;
+            j = p >> 5;
+        } while (j < jend);
     }
     while (p < end_bit) {
-        const uint32_t nxt = W(j + 2u); // consumed at the bottom of the iteration, if at all
-        const uint32_t win = funnel_left(w0, w1, sh);
+        uint32_t w0, w1;
+        W.pair(p >> 5, w0, w1);
+        const uint32_t win = funnel_left(w0, w1, p);
         uint32_t e = L.fast(toff, win >> (32 - LUT_BITS));
         if ((e & 31u) == 0u) // code longer than LUT_BITS (or no code at all)
             e = L.slow(toff, win, e);
@@ -352,38 +398,21 @@ KPEG_HD void relay_run(DecState &d, const Words &W, const Luts &L, const StreamV
             cross_boundary();
             if (p >= S.total_bits)
                 break;
-            j = p >> 5;
-            sh = p & 31u;
-            w0 = W(j);
-            w1 = W(j + 1u);
             continue;
         }
         symbol(win, e);
         p += T;
-        sh += T;
-        const bool cross = sh >= 32u; // selects, not a branch
-        sh = cross ? sh - 32u : sh;
-        j = cross ? j + 1u : j;
-        w0 = cross ? w1 : w0;
-        w1 = cross ? nxt : w1;
     }
     // An interval without padding bits can end exactly where the subsequence stops: the boundary is crossed here, not
     // skipped by the next subsequence's dec_init -- every restart of the predictors is then visible to the scans as a
     // boundary some subsequence crossed.
-    if (p == segend && p < S.total_bits) {
+    if (p == segend && p < S.total_bits)
         cross_boundary();
-        j = p >> 5;
-        sh = p & 31u;
-        w0 = W(j);
-        w1 = W(j + 1u);
-    }
     if (EMIT)
         flags |= worst == ENTRY_ADV_INVALID ? CZ_BAD_CODE : (worst > 64u ? CZ_SLOT_OVERFLOW : 0u);
     d.p = p;
-    d.j = j;
-    d.sh = sh;
-    d.w0 = w0;
-    d.w1 = w1;
+    d.j = p >> 5;
+    d.sh = p & 31u;
     d.toff = toff;
     d.z = q & 63u;
     d.q = q;
@@ -394,7 +423,13 @@ KPEG_HD void relay_run(DecState &d, const Words &W, const Luts &L, const StreamV
     d.seg = seg;
     d.nrec = nrec;
     d.flags = flags;
-    d.dcs = dcs;
+#if KPEG_BLOCK_END_BRANCH
+    // the weights actually used: a DC difference that is still to come (wd pending) has not been added
+    d.dcs = (long long)(dcs - (unsigned long long)COEF_BIAS * (wsum - wd));
+#else
+    (void)wsum;
+    d.dcs = (long long)dcs;
+#endif
 }
 
 // ---- Huffman final pass (fallback when records cannot be used) ---------------------------------------

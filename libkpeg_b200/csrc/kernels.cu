@@ -519,6 +519,72 @@ __device__ __forceinline__ void k1_stage_stream(K1Smem &sm, const EntropyArgs &a
     __syncthreads();
 }
 
+// ---- per-thread stream regions (cold pass, relay round 1) -----------------------------------------------------------
+// The relay passes load the two words that cover a symbol in every iteration (entropy_core.h relay_run), so the address
+// of word j must cost one multiply-add: every thread gets a REGION of its own -- the words of its subsequence followed
+// by the first word of the next one (a symbol that begins in the last word runs into it) -- at stride
+// words_per_subsequence + 1, which is odd: lanes reading word k of their regions hit 32 different banks.  In terms of
+// the linear slice, word l sits at l + l / words_per_subsequence, and the slot before a region's first word holds a
+// second copy of that word (it is the look-ahead word of the region before).
+struct RegionWords {
+    uint32_t pbase; // shared byte address of the region's first word - 4 * (global index of that word)
+    __device__ __forceinline__ uint32_t operator()(uint32_t gw) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(pbase + 4u * gw));
+        return v;
+    }
+    __device__ __forceinline__ void pair(uint32_t j, uint32_t &w0, uint32_t &w1) const
+    {
+        const uint32_t at = pbase + 4u * j;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(at));
+        asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(at));
+    }
+};
+
+__host__ __device__ inline size_t k1_region_smem_bytes(uint32_t sub_bits)
+{
+    return sizeof(K1Smem) + (size_t)(ENTROPY_THREADS * (sub_bits / 32u + 1u) + 1u) * sizeof(uint32_t);
+}
+
+// The tile's stream slice into the threads' regions (coalesced loads).  Ends with a __syncthreads().
+__device__ __forceinline__ void k1_stage_regions(K1Smem &sm, const EntropyArgs &a, uint32_t tile, uint32_t total_bits, uint32_t wlog)
+{
+    const uint32_t gw0 = (tile * ENTROPY_THREADS) << wlog;
+    const uint32_t nwords = ((uint32_t)ENTROPY_THREADS << wlog) + 1u;
+    const uint32_t total_words = ((total_bits + 31u) >> 5) + 4u; // the stream buffer has zeroed slack beyond this
+    const uint32_t in_sub = (1u << wlog) - 1u;
+    constexpr int STAGE_BATCH = 8; // loads in flight per thread
+    for (uint32_t l0 = threadIdx.x; l0 < nwords; l0 += STAGE_BATCH * blockDim.x) {
+        uint32_t v[STAGE_BATCH];
+#pragma unroll
+        for (int i = 0; i < STAGE_BATCH; ++i) {
+            const uint32_t l = l0 + (uint32_t)i * blockDim.x, gw = gw0 + l;
+            v[i] = (l < nwords && gw < total_words) ? __ldg(a.words + gw) : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < STAGE_BATCH; ++i) {
+            const uint32_t l = l0 + (uint32_t)i * blockDim.x;
+            if (l < nwords) {
+                const uint32_t at = l + (l >> wlog);
+                sm.words[at] = v[i];
+                if ((l & in_sub) == 0u && l != 0u)
+                    sm.words[at - 1u] = v[i]; // look-ahead word of the region before
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ RegionWords k1_region_words(const K1Smem &sm, uint32_t tile, uint32_t wlog)
+{
+    // thread t: region at word t * (words per subsequence + 1), first global word (tile * THREADS + t) * words per subsequence
+    const uint32_t t = threadIdx.x, wps = 1u << wlog;
+    RegionWords W;
+    W.pbase = (uint32_t)__cvta_generic_to_shared(sm.words) + 4u * (t * (wps + 1u)) - 4u * (((tile * ENTROPY_THREADS + t) << wlog));
+    return W;
+}
+
 // first segment index whose start bit is >= bit  (seg_bit[0..nseg] ascending, seg_bit[nseg] = total_bits)
 __device__ __forceinline__ uint32_t first_seg_at_or_after(const uint32_t *seg_bit, uint32_t nseg, uint32_t bit)
 {
@@ -565,10 +631,10 @@ __global__ void __launch_bounds__(ENTROPY_THREADS) entropy_cold_kernel(EntropyAr
     const SmemLuts L = k1_luts(sm, a);
     StreamView S{a.seg_bit, total_bits};
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        k1_stage_stream(sm, a, tile, total_bits, wlog);
+        k1_stage_regions(sm, a, tile, total_bits, wlog);
         const uint32_t sub = tile * ENTROPY_THREADS + threadIdx.x;
         if (sub < nsub) {
-            const SmemWords W = k1_words(sm, tile, wlog);
+            const RegionWords W = k1_region_words(sm, tile, wlog);
             const uint32_t p0 = sub << (wlog + 5u);
             const uint32_t end = min(p0 + a.g.sub_bits, total_bits);
             const uint32_t hint = a.g.nseg > 1u ? first_seg_at_or_after(a.seg_bit, a.g.nseg, p0) : (sub ? 1u : 0u);
@@ -678,7 +744,7 @@ __global__ void __launch_bounds__(ENTROPY_THREADS, 10) entropy_relay_full_kernel
     const SmemLuts L = k1_luts(sm, a);
     StreamView S{a.seg_bit, total_bits};
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        k1_stage_stream(sm, a, tile, total_bits, wlog);
+        k1_stage_regions(sm, a, tile, total_bits, wlog);
         const uint32_t sub = tile * ENTROPY_THREADS + threadIdx.x;
         if (sub < nsub) {
             // cold value or already relayed: either is a valid iterate; subsequence 0 starts from the true state
@@ -690,7 +756,7 @@ __global__ void __launch_bounds__(ENTROPY_THREADS, 10) entropy_relay_full_kernel
             const uint32_t start = sub << (wlog + 5u);
             // without records, a subsequence whose cold decode already started from this state is done
             if (a.rec || (sub != 0u && !(in.p == start && (in.cz & CZ_STATE_MASK) == 0u))) {
-                const SmemWords W = k1_words(sm, tile, wlog);
+                const RegionWords W = k1_region_words(sm, tile, wlog);
                 const uint32_t end = min((sub + 1u) << (wlog + 5u), total_bits);
                 const SubState out = relay_decode(a, W, L, S, sub, end, in.p, in.cz & CZ_STATE_MASK, false);
                 if (sub)
@@ -712,6 +778,12 @@ struct PrivateWords {
         uint32_t v;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr + 4u * (gw - gw0)));
         return v;
+    }
+    __device__ __forceinline__ void pair(uint32_t j, uint32_t &w0, uint32_t &w1) const
+    {
+        const uint32_t at = addr + 4u * (j - gw0);
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(at));
+        asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(at));
     }
 };
 
@@ -1318,7 +1390,7 @@ static uint32_t k1_grid(const EntropyArgs &a)
 void launch_entropy_cold(const EntropyArgs &a, cudaStream_t s, uint32_t *launches)
 {
     const uint32_t wlog = ilog2(a.g.sub_bits / 32u);
-    entropy_cold_kernel<<<k1_grid(a), ENTROPY_THREADS, k1_smem_bytes(a.g.sub_bits), s>>>(a, wlog);
+    entropy_cold_kernel<<<k1_grid(a), ENTROPY_THREADS, k1_region_smem_bytes(a.g.sub_bits), s>>>(a, wlog);
     ++*launches;
 }
 
@@ -1326,7 +1398,7 @@ void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint3
 {
     if (round == 1) {
         const uint32_t wlog = ilog2(a.g.sub_bits / 32u);
-        entropy_relay_full_kernel<<<k1_grid(a), ENTROPY_THREADS, k1_smem_bytes(a.g.sub_bits), s>>>(a, wlog);
+        entropy_relay_full_kernel<<<k1_grid(a), ENTROPY_THREADS, k1_region_smem_bytes(a.g.sub_bits), s>>>(a, wlog);
     } else {
         const uint32_t grid = (a.nsub_max + ENTROPY_THREADS - 1) / ENTROPY_THREADS;
         const uint32_t wlog = ilog2(a.g.sub_bits / 32u);
@@ -1401,7 +1473,7 @@ void launch_entropy_write(const EntropyArgs &a, cudaStream_t s, uint32_t *launch
 void kernels_configure(int max_concurrent_jobs)
 {
     g_max_concurrent_loops = (uint32_t)(max_concurrent_jobs > 0 ? max_concurrent_jobs : 1);
-    const int k1max = (int)k1_smem_bytes(1024);
+    const int k1max = (int)k1_region_smem_bytes(1024);
     cudaFuncSetAttribute(entropy_cold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k1max);
     cudaFuncSetAttribute(entropy_relay_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k1max);
     cudaFuncSetAttribute(entropy_relay_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1413,7 +1485,7 @@ void kernels_configure(int max_concurrent_jobs)
         cudaFuncSetAttribute(entropy_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)k1_write_smem_bytes(1024));
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entropy_cold_kernel, ENTROPY_THREADS,
-                                                          k1_smem_bytes(512)) != cudaSuccess || per_sm < 1)
+                                                          k1_region_smem_bytes(512)) != cudaSuccess || per_sm < 1)
             per_sm = 4;
         g_k1_grid_cap = (uint32_t)(sms * per_sm);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entropy_write_kernel, WRITE_THREADS,
