@@ -50,15 +50,14 @@ struct NatZz {
 // block is bounded by A / 4: the 64 basis functions are bounded by 1/4):
 //   BLK_NONZERO  some coefficient is non-zero (otherwise all 64 samples are 0)
 //   BLK_WIDE     A > COLOUR_SAFE_A: samples may leave the range the fp32 colour path is proven for
-//   BLK_HUGE     samples may not fit the 16-bit sample tile: the MCU is reconstructed wholesale on the exact path
+//   BLK_HUGE     samples may not fit the 16-bit fields of a tie record: the MCU is reconstructed wholesale on the exact path
 constexpr uint32_t BLK_NONZERO = 1u, BLK_WIDE = 2u, BLK_HUGE = 4u;
 constexpr float COLOUR_SAFE_A = 4.0f * (COLOUR_FAST_RANGE - 8.0f);
 constexpr float SAMPLE_SAFE_A = 4.0f * 32000.0f;
 
-// rint() by magic-number add with the 16-bit bias folded in: the low 16 bits of the bit pattern of x + SAMPLE_MAGIC are
-// rint(x) + COEF_BIAS, and SAMPLE_MAGIC stays inside [2^23, 2^24) for every |x| < 32768.
+// A biased 16-bit coefficient c + COEF_BIAS placed in the low mantissa bits of RINT_MAGIC's pattern is the float
+// RINT_MAGIC + COEF_BIAS + c: subtracting SAMPLE_MAGIC gives c (exactly).
 constexpr float SAMPLE_MAGIC = RINT_MAGIC + 32768.0f;
-constexpr uint32_t BIAS2 = COEF_BIAS | (COEF_BIAS << 16);
 
 // Bit layout of a block's 64-bit tie mask (x = rows 0..3, y = rows 4..7): the bit of sample (row, col) in its word.
 // The upper 16 bits hold columns 0..3, the lower 16 columns 4..7; inside, earlier samples sit higher.
@@ -82,9 +81,15 @@ template <int NC>
 struct IdctSmem {
     static constexpr int NM = IDCT_MCUS_PER_CTA;
     static constexpr int NB = NM * NC;
-    uint4 coef[NB * 8];           // [block][chunk ^ (block & 7)]: eight biased 16-bit coefficients per chunk, zig-zag order
-    uint2 samp[NC * 8 * 2 * NM];  // [comp][row][half][mcu] -> four rounded, unshifted samples, biased 16-bit
+    // The coefficient tile and the sample tile share their memory: every thread pulls its block into registers, a CTA
+    // barrier, and the samples go where the coefficients were.  (The rare paths that need coefficients again -- the exact
+    // evaluation of a strip with more ties than its list holds -- fetch them from the tile in global memory.)
+    union {
+        uint4 coef[NB * 8];           // [block][chunk ^ (block & 7)]: eight biased 16-bit coefficients per chunk, zig-zag order
+        float4 samp[NC * 8 * 2 * NM]; // [comp][row][half][mcu] -> four rounded, unshifted samples (integer-valued floats)
+    };
     float2 qpair[NC][32];         // prescaled quantisers in the pair order of the transform (pair_nat)
+    uint2 tiemask[NB];            // per block: its tie mask (bit layout: tie_bit), for the flags of a tied pixel's other components
     uint16_t ties[TIE_LIST_CAP];  // block in strip | sample << 7
     uint8_t flag[NB];             // per block: BLK_*
     uint32_t ntie, any_huge;
@@ -318,14 +323,13 @@ __device__ __noinline__ uint32_t colour_px_general(float y, float cb, float cr)
     return (uint32_t)clamp_u8(R) | ((uint32_t)clamp_u8(G) << 8) | ((uint32_t)clamp_u8(B) << 16);
 }
 
-// eight biased samples (two uint2 halves) -> four pairs of floats (exact: the values are integers)
-__device__ __forceinline__ void unbias_row(const uint2 &h0, const uint2 &h1, F2 (&v)[4])
+// eight samples of a row (two float4 halves) -> four pairs: register naming only
+__device__ __forceinline__ void row_pairs(const float4 &h0, const float4 &h1, F2 (&v)[4])
 {
-    const F2 unbias = splat2(SAMPLE_MAGIC);
-    v[0] = lane_sub(pack2(biased16_as_magic(h0.x, 0), biased16_as_magic(h0.x, 1)), unbias);
-    v[1] = lane_sub(pack2(biased16_as_magic(h0.y, 0), biased16_as_magic(h0.y, 1)), unbias);
-    v[2] = lane_sub(pack2(biased16_as_magic(h1.x, 0), biased16_as_magic(h1.x, 1)), unbias);
-    v[3] = lane_sub(pack2(biased16_as_magic(h1.y, 0), biased16_as_magic(h1.y, 1)), unbias);
+    v[0] = pack2(h0.x, h0.y);
+    v[1] = pack2(h0.z, h0.w);
+    v[2] = pack2(h1.x, h1.y);
+    v[3] = pack2(h1.z, h1.w);
 }
 
 // -> the row's 24 bytes as six words; returns the number of pixels that took the double expression.
@@ -436,27 +440,10 @@ __device__ __forceinline__ float exact_terms(const uint4 (&ch)[8], const int32_t
     return sum;
 }
 
-// The reference's evaluation of sample s of block bl (component comp) of the strip's tile (DC value already in slot 0,
-// AC coefficients already dropped where the F1 rule says so).
+// The reference's evaluation of sample s of block gb (index in the job, component comp) from the coefficient tiles in global
+// memory (DC value already in slot 0, AC coefficients already dropped where the F1 rule says so); defined below.
 template <int NC>
-__device__ __noinline__ int exact_sample_tile(const IdctSmem<NC> *sm, const DeviceTables *T, uint32_t bl, uint32_t comp, int s)
-{
-    uint4 ch[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-        ch[k] = sm->coef[bl * 8u + ((uint32_t)k ^ (bl & 7u))];
-    const int x = s >> 3, y = s & 7;
-    double cx[8], cy[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        cx[k] = __ldg(&T->cosd[x][k]);
-        cy[k] = __ldg(&T->cosd[y][k]);
-    }
-    const float sum = exact_terms(ch, T->qint[comp], cx, cy, __ldg(&T->cc[0][0]), __ldg(&T->cc[0][1]),
-                                  std::make_integer_sequence<int, 64>{});
-    const float out = (float)mul_f64(0.25, (double)sum);
-    return round_half_away(out);
-}
+__device__ __noinline__ int exact_sample_global(const uint4 *tiles, const DeviceTables *T, uint32_t gb, uint32_t comp, int s);
 
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v)
 {
@@ -509,6 +496,7 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
 #pragma unroll
     for (int k = 0; k < 8; ++k)
         ch[k] = sm.coef[bl * 8 + (k ^ (bl & 7))];
+    __syncthreads(); // every block is in registers: the samples may overwrite the tile
     uint32_t tie_lo = 0, tie_hi = 0; // this block's tie mask (bit layout: tie_bit)
     if (active) {
         F2 P[32];
@@ -526,8 +514,8 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
             const int dcv = (int)(ch[0].x & 0xFFFFu) - (int)COEF_BIAS;
             const int F = dcv * __ldg(&a.tables->qint[comp][0]);
             const float tt = mul_f32(__ldg(&a.tables->cc[0][0]), (float)F);
-            const uint32_t b = ((uint32_t)round_half_away(0.25f * tt) + COEF_BIAS) & 0xFFFFu;
-            const uint2 row = make_uint2(b | (b << 16), b | (b << 16));
+            const float b = (float)round_half_away(0.25f * tt);
+            const float4 row = make_float4(b, b, b, b);
 #pragma unroll
             for (int i = 0; i < 16; ++i)
                 sm.samp[(comp * 16 + i) * NM + ml] = row;
@@ -538,10 +526,10 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
             // rounded value exceeds thresh, i.e. when d*d - thresh^2 >= 0: one FFMA2 per sample pair, and the
             // complement of the sign bit is shifted into the block's mask with one funnel shift per sample (no
             // compares, no predicates).  thresh^2 is taken a hair low, so the packed test can only flag more than
-            // |d| > thresh does.  The low 16 bits of x + M are the biased sample the tile keeps.
+            // |d| > thresh does.  (x + M) - M, an integer-valued float, is the sample the tile keeps.
             const float t2 = thresh > 0.0f ? thresh * thresh * (1.0f - 1.0f / 2097152.0f) : 0.0f;
             const F2 neg_t2 = splat2(-t2);
-            const F2 magic = splat2(SAMPLE_MAGIC);
+            const F2 magic = splat2(RINT_MAGIC);
             uint32_t keep[2][2]; // [half][word]: sign bits = "outside the band", 16 per half and word
             auto half_block = [&](auto HALF) { // columns 4 half .. 4 half + 3 of all eight rows
                 constexpr int half = decltype(HALF)::value;
@@ -552,14 +540,13 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
                 uint32_t kl = 0, kh = 0;
 #pragma unroll
                 for (int row = 0; row < 8; ++row) {
-                    uint32_t w[2];
+                    F2 w[2];
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         const F2 x = pack2(v[2 * k][row], v[2 * k + 1][row]);
-                        const F2 mm = lane_add(x, magic);
-                        const F2 d = lane_sub(x, lane_sub(mm, magic));
+                        w[k] = lane_sub(lane_add(x, magic), magic);
+                        const F2 d = lane_sub(x, w[k]);
                         const F2 e = lane_fma(d, d, neg_t2);
-                        w[k] = __byte_perm((uint32_t)float_bits(lo2(mm)), (uint32_t)float_bits(hi2(mm)), 0x5410u);
                         if (row < 4) {
                             kl = __funnelshift_l((uint32_t)float_bits(lo2(e)), kl, 1);
                             kl = __funnelshift_l((uint32_t)float_bits(hi2(e)), kl, 1);
@@ -568,7 +555,7 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
                             kh = __funnelshift_l((uint32_t)float_bits(hi2(e)), kh, 1);
                         }
                     }
-                    sm.samp[((comp * 8 + row) * 2 + half) * NM + ml] = make_uint2(w[0], w[1]);
+                    sm.samp[((comp * 8 + row) * 2 + half) * NM + ml] = make_float4(lo2(w[0]), hi2(w[0]), lo2(w[1]), hi2(w[1]));
                 }
                 keep[half][0] = kl;
                 keep[half][1] = kh;
@@ -598,6 +585,7 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
         }
         sm.flag[bl] = (uint8_t)flag;
     }
+    sm.tiemask[bl] = make_uint2(tie_lo, tie_hi);
     __syncthreads();
 
     // ---- stage 2: colour conversion + interleaved store -------------------------------------------
@@ -637,14 +625,14 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
             const uint32_t y = by * 8u + row;
             if (y >= H)
                 continue;
-            const uint2 y0 = sm.samp[((0 * 8 + row) * 2 + 0) * NM + ml], y1 = sm.samp[((0 * 8 + row) * 2 + 1) * NM + ml];
+            const float4 y0 = sm.samp[((0 * 8 + row) * 2 + 0) * NM + ml], y1 = sm.samp[((0 * 8 + row) * 2 + 1) * NM + ml];
             uint32_t out[2 * NC];
             uint32_t redo = 0;
             if constexpr (NC == 3) {
                 F2 yy[4], bb[4], cc[4];
-                unbias_row(y0, y1, yy);
-                unbias_row(sm.samp[((1 * 8 + row) * 2 + 0) * NM + ml], sm.samp[((1 * 8 + row) * 2 + 1) * NM + ml], bb);
-                unbias_row(sm.samp[((2 * 8 + row) * 2 + 0) * NM + ml], sm.samp[((2 * 8 + row) * 2 + 1) * NM + ml], cc);
+                row_pairs(y0, y1, yy);
+                row_pairs(sm.samp[((1 * 8 + row) * 2 + 0) * NM + ml], sm.samp[((1 * 8 + row) * 2 + 1) * NM + ml], bb);
+                row_pairs(sm.samp[((2 * 8 + row) * 2 + 0) * NM + ml], sm.samp[((2 * 8 + row) * 2 + 1) * NM + ml], cc);
                 uint32_t o6[6];
                 if (mode == COLOUR_PLAIN)
                     colour_exact += colour_row8<COLOUR_PLAIN>(yy, bb, cc, o6, redo);
@@ -657,11 +645,11 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
                     out[k] = o6[k];
             } else {
                 // gray: the reference's colour path with Cb = Cr = 128 gives R = G = B = clamp(Y)
-                const uint32_t w4[4] = {y0.x, y0.y, y1.x, y1.y};
+                const float f8[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
                 int v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    v[j] = (int)((j & 1) ? (w4[j >> 1] >> 16) : (w4[j >> 1] & 0xFFFFu)) - (int)COEF_BIAS + 128;
+                for (int j = 0; j < 8; ++j) // integer-valued floats: the magic add is exact
+                    v[j] = float_bits(f8[j] + (RINT_MAGIC + 128.0f)) - RINT_MAGIC_BITS;
                 out[0] = pack4_sat(v[0], v[1], v[2], v[3]);
                 out[1] = pack4_sat(v[4], v[5], v[6], v[7]);
             }
@@ -682,10 +670,10 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
                 redo &= redo - 1u;
                 if (bx * 8u + (uint32_t)j >= W)
                     continue;
-                const uint16_t *sp = reinterpret_cast<const uint16_t *>(sm.samp);
-                const int sy = (int)sp[(((0 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)] - (int)COEF_BIAS;
-                const int sb = (int)sp[(((1 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)] - (int)COEF_BIAS;
-                const int sr = (int)sp[((((NC - 1) * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)] - (int)COEF_BIAS;
+                const float *sp = reinterpret_cast<const float *>(sm.samp);
+                const int sy = (int)sp[(((0 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
+                const int sb = (int)sp[(((1 * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
+                const int sr = (int)sp[((((NC - 1) * 8 + row) * 2 + (j >> 2)) * NM + ml) * 4 + (j & 3)];
                 const uint32_t e = colour_exact_int(sy, sb, sr);
                 dst[3 * j] = (uint8_t)e;
                 dst[3 * j + 1] = (uint8_t)(e >> 8);
@@ -705,14 +693,16 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
             atomicAdd(&a.meta->colour_exact, colour_exact);
         return;
     }
-    uint16_t *sp16 = reinterpret_cast<uint16_t *>(sm.samp);
-    auto samp_index = [&](uint32_t c, uint32_t mm_l, int s) { // 16-bit index of sample s of component c of MCU mm_l
+    float *spf = reinterpret_cast<float *>(sm.samp);
+    const uint4 *gtiles = reinterpret_cast<const uint4 *>(a.tiles);
+    const uint32_t blk0 = mcu0 * (uint32_t)NC; // first block of the strip in the job
+    auto samp_index = [&](uint32_t c, uint32_t mm_l, int s) { // index of sample s of component c of MCU mm_l in the sample tile
         return ((((c * 8u + (uint32_t)(s >> 3)) * 2u + (uint32_t)((s & 7) >> 2)) * NM + mm_l) * 4u) + (uint32_t)(s & 3);
     };
     auto resolve = [&](uint32_t b, int s) { // exact sample -> sample tile
         const uint32_t c = b % NC, mm_l = b / NC;
-        const int e = exact_sample_tile<NC>(&sm, a.tables, b, c, s);
-        sp16[samp_index(c, mm_l, s)] = (uint16_t)((uint32_t)e + COEF_BIAS);
+        const int e = exact_sample_global<NC>(gtiles, a.tables, blk0 + b, c, s);
+        spf[samp_index(c, mm_l, s)] = (float)e;
     };
     auto repaint = [&](uint32_t b, int s) { // pixel of sample s of block b's MCU from the (now exact) sample tile
         const uint32_t mm_l = b / NC;
@@ -723,11 +713,11 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
         const uint32_t px = bx * 8u + (uint32_t)(s & 7), py = by * 8u + (uint32_t)(s >> 3);
         if (px >= W || py >= H)
             return;
-        const int y = (int)sp16[samp_index(0, mm_l, s)] - (int)COEF_BIAS;
+        const int y = (int)spf[samp_index(0, mm_l, s)];
         int cb = 0, cr = 0;
         if (NC == 3) {
-            cb = (int)sp16[samp_index(1, mm_l, s)] - (int)COEF_BIAS;
-            cr = (int)sp16[samp_index(NC - 1, mm_l, s)] - (int)COEF_BIAS;
+            cb = (int)spf[samp_index(1, mm_l, s)];
+            cr = (int)spf[samp_index(NC - 1, mm_l, s)];
         }
         const uint32_t v = colour_px<NC>(y, cb, cr);
         uint8_t *dst = a.pixels + ((size_t)img * W * H + (size_t)py * W + px) * NC;
@@ -744,15 +734,15 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
         for (uint32_t i = (uint32_t)t; i < ntie; i += (uint32_t)NB) {
             const uint32_t e = sm.ties[i], b = e & 127u, mm_l = b / NC, c = b % NC;
             const int sidx = (int)(e >> 7);
-            uint32_t flags = 0;
-            for (uint32_t j = 0; j < ntie; ++j) {
-                const uint32_t o = sm.ties[j];
-                if ((o >> 7) == (e >> 7) && (o & 127u) / NC == mm_l)
-                    flags |= 1u << ((o & 127u) % NC);
-            }
-            uint32_t huge = 0;
-            for (int cc = 0; cc < NC; ++cc)
+            // which components of this pixel are tied: one bit of each block's mask
+            const int tbit = tie_bit(sidx >> 3, sidx & 7);
+            uint32_t flags = 0, huge = 0;
+#pragma unroll
+            for (int cc = 0; cc < NC; ++cc) {
+                const uint2 tm = sm.tiemask[mm_l * NC + cc];
+                flags |= ((((sidx >> 3) & 4) ? tm.y : tm.x) >> tbit & 1u) << cc;
                 huge |= sm.flag[mm_l * NC + cc];
+            }
             uint4 r = make_uint4(TIE_EMPTY, 0, 0, 0);
             uint32_t img, by, bx;
             mcu_origin(mm_l, img, by, bx);
@@ -760,8 +750,9 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
             if ((flags & (0u - flags)) == (1u << c) && !(huge & BLK_HUGE) && mcu0 + mm_l < total_mcus && px < W && py < H) {
                 r.x = img * W * H + py * W + px; // pixels of a job are < 2^32 (host_tables.h)
                 r.y = mcu0 + mm_l;
-                r.z = (uint32_t)sidx | (flags << 8) | ((uint32_t)sp16[samp_index(0, mm_l, sidx)] << 16);
-                r.w = NC == 3 ? (uint32_t)sp16[samp_index(1, mm_l, sidx)] | ((uint32_t)sp16[samp_index(2, mm_l, sidx)] << 16) : 0u;
+                auto biased = [&](uint32_t c) { return ((uint32_t)(int)spf[samp_index(c, mm_l, sidx)] + COEF_BIAS) & 0xFFFFu; };
+                r.z = (uint32_t)sidx | (flags << 8) | (biased(0) << 16);
+                r.w = NC == 3 ? biased(1) | (biased(2) << 16) : 0u;
             }
             a.tie_rec[(size_t)strip * TIE_LIST_CAP + i] = r;
         }
@@ -812,7 +803,7 @@ __global__ void __launch_bounds__(NC * IDCT_MCUS_PER_CTA, NC == 3 ? KPEG_IDCT_MI
                 continue;
             int e[3] = {0, 0, 0};
             for (int c = 0; c < NC; ++c)
-                e[c] = exact_sample_tile<NC>(&sm, a.tables, mm_l * NC + (uint32_t)c, (uint32_t)c, s);
+                e[c] = exact_sample_global<NC>(gtiles, a.tables, blk0 + mm_l * NC + (uint32_t)c, (uint32_t)c, s);
             const uint32_t v = NC == 3 ? colour_exact_int(e[0], e[1], e[2]) : (uint32_t)clamp_u8(e[0] + 128);
             uint8_t *dst = a.pixels + ((size_t)img * W * H + (size_t)py * W + px) * NC;
             dst[0] = (uint8_t)v;

@@ -665,7 +665,11 @@ struct GlobalRecorder {
     uint32_t stride_bytes; // 128 in the warp-interleaved layout, 4 in a private area: one IMAD.WIDE per address
     __device__ __forceinline__ void emit(bool on, uint32_t k, uint32_t w) const
     {
+#ifdef KPEG_WHATIF_NO_STORE // timing experiment only (results are wrong): how much of the relay is the record stores
+        if (on && k < kmax && w == 0x12345u)
+#else
         if (on && k < kmax)
+#endif
             asm volatile("st.global.u32 [%0], %1;" ::"l"(base + (size_t)k * stride_bytes), "r"(w) : "memory");
     }
 };
@@ -697,7 +701,11 @@ __device__ __forceinline__ SubState relay_decode(const EntropyArgs &a, const Wor
         // registers, not values the compiler recomputes from the kernel parameters for every symbol (it did: seven
         // instructions of address arithmetic per record)
         asm volatile("" : "+l"(R.base), "+r"(R.kmax), "+r"(R.stride_bytes));
+#ifdef KPEG_WHATIF_NO_DCS // timing experiment only (results are wrong)
+        relay_run<true, false>(d, W, L, S, a.g, end, R);
+#else
         relay_run<true, true>(d, W, L, S, a.g, end, R);
+#endif
         a.nrec[sub] = min(d.nrec, NREC_MASK) | (area << 10);
         a.dcs[sub] = d.dcs;
         if (d.nrec > a.rec_kmax)
@@ -732,7 +740,7 @@ __device__ __forceinline__ void relay_publish(const EntropyArgs &a, uint32_t sub
     }
 }
 
-__global__ void __launch_bounds__(ENTROPY_THREADS, 10) entropy_relay_full_kernel(EntropyArgs a, uint32_t wlog)
+__global__ void __launch_bounds__(ENTROPY_THREADS, 8) entropy_relay_full_kernel(EntropyArgs a, uint32_t wlog)
 {
     extern __shared__ __align__(16) unsigned char k1_raw[];
     K1Smem &sm = *reinterpret_cast<K1Smem *>(k1_raw);
