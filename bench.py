@@ -437,15 +437,13 @@ def leg_tiles(dec, K, rank, world, dist, device, torch, quick):
     pinned = nbytes_band > 0 and lib.kpeg_cuda_host_register(mine.ctypes.data, nbytes_band) == 0
     h_in = PinnedArray(band.scan.size)
     h_in.array[:] = band.scan
-    # the rank's band through the product's tiled entry point, its own GPU listed four times: four sub-bands whose copies
-    # in, kernels and copies out overlap (kpeg_cuda_decode_tiled: one host thread and one pooled context per entry)
-    from libkpeg_b200.api import decode_tiled
-    sub_bands = [device] * 4
-    decode_tiled(sub_bands, band.plan, h_in.array, mine)
+    # kpeg_cuda_decode on the rank's band: a large restart-marked image from host memory goes through the context's
+    # lanes as sub-bands, so its copies in, kernels and copies out overlap (kpeg_cuda.cu decode_banded)
+    dec.decode_scan(band.plan, h_in.array, out=mine)
     sync()
     t0 = time.perf_counter()
     for _ in range(steps):
-        decode_tiled(sub_bands, band.plan, h_in.array, mine)
+        dec.decode_scan(band.plan, h_in.array, out=mine)
     e2e_s = _max_over_ranks(torch, dist, device, time.perf_counter() - t0)
     sync()
     # parity, on rank 0, from the SHARED frame: narrow bands out of the regions different ranks wrote against the oracle's
@@ -470,7 +468,7 @@ def leg_tiles(dec, K, rank, world, dist, device, torch, quick):
     res = {"workload": f"{side}x{side} RGB 4:4:4 q=90, restart interval = one MCU row (BASELINE.json configs[4]), {world} band(s) of whole MCU rows, one per GPU",
            "device_resident_mpixel_per_s": side * side * steps / dev_s / 1e6, "e2e_mpixel_per_s": side * side * steps / e2e_s / 1e6,
            "band_rows_rank0": int(band.rows), "band_scan_bytes_rank0": int(band.scan.size), "steps": steps,
-           "e2e_call": "kpeg_cuda_decode_tiled per rank on its band, the rank's GPU listed four times (four sub-bands in flight)",
+           "e2e_call": "kpeg_cuda_decode per rank on its band (host buffers; the band goes through the context's lanes as four sub-bands whose copies and kernels overlap)",
            "e2e_frame": "one host frame shared by the rank processes (/dev/shm), each rank's rows pinned with kpeg_cuda_host_register" if pinned
                         else "one host frame shared by the rank processes (/dev/shm), NOT pinned (registration refused)",
            "pixels_match_oracle": ok, "checked": "three 64-row bands of the shared frame (first, middle, last) against the oracle, on rank 0",

@@ -97,6 +97,16 @@ struct kpeg_ctx {
     int split_parts = 4;     // concurrent jobs a device-resident batch is cut into (KPEG_SPLIT)
     int host_chunks = 8;     // pipeline depth of a host-pointer batch (KPEG_HOST_CHUNKS)
     int submit_parts = 1;    // jobs one deferred submission is cut into (KPEG_SUBMIT_SPLIT)
+    // restart-interval bands a large image from host memory is cut into (KPEG_BANDS).  Off (1) by default: finding the cut
+    // points is a walk over the scan's markers on the host, ~0.15 ms per MB, which costs more than overlapping the copy in
+    // and the kernels with the copy out gains (16384x16384: 19 ms whole, 23 ms in 4 or 8 bands; profiles/README.md)
+    int band_parts = 1;
+    // result copies of the lanes leave one after another (each waits for the one enqueued before it): copies to the
+    // host that run at the same time share the link AND slow each other down (measured: four concurrent 200 MB copies
+    // take twice as long as the same four back to back); KPEG_D2H_CHAIN=0 turns the ordering off
+    bool d2h_chain = true;
+    bool d2h_chain_armed = false;
+    cudaEvent_t d2h_done = nullptr;
     Lane lane[NLANES];
 
     DevBuf tables, merged;
@@ -201,9 +211,21 @@ int ensure_pinned(kpeg_ctx *ctx, cudaStream_t stream, PinBuf &b, size_t bytes)
 }
 
 // ---- plan -> device tables (shared by all lanes) ---------------------------------------------------
+// The device tables (Huffman LUTs, quantisers) depend on the components' table selectors and the tables themselves,
+// not on the image's dimensions, restart interval or flags: jobs that differ only in those -- the restart-interval
+// bands of one image, say -- share the tables and can be in flight together.
+bool same_tables(const kpeg_plan *a, const kpeg_plan *b)
+{
+    kpeg_plan x = *a, y = *b;
+    x.width = y.width = x.height = y.height = 0;
+    x.restart_interval = y.restart_interval = 0;
+    x.flags = y.flags = 0;
+    return memcmp(&x, &y, sizeof x) == 0;
+}
+
 int upload_plan(kpeg_ctx *ctx, const kpeg_plan *pl)
 {
-    if (ctx->have_plan && memcmp(&ctx->plan_cached, pl, sizeof *pl) == 0)
+    if (ctx->have_plan && same_tables(&ctx->plan_cached, pl))
         return KPEG_OK;
     // a new plan: nothing may still be reading the old tables
     for (Lane &L : ctx->lane)
@@ -258,6 +280,17 @@ void add_times(kpeg_ctx *ctx, Lane &L, kpeg_stats *stats)
 {
     if (!stats || !ctx->profiling || L.nev < 2)
         return;
+    static const bool timeline = getenv("KPEG_TIMELINE") != nullptr; // development: when every stage of every lane ended, relative to lane 0's window
+    if (timeline && ctx->lane[0].ev[0]) {
+        fprintf(stderr, "[kpeg timeline] lane %d:", (int)(&L - ctx->lane));
+        for (int i = 0; i < L.nev; ++i) {
+            float at = 0.0f;
+            if (cudaEventElapsedTime(&at, ctx->lane[0].ev[0], L.ev[i]) != cudaSuccess)
+                cudaGetLastError();
+            fprintf(stderr, " %d@%.2f", L.ev_stage[i], at);
+        }
+        fprintf(stderr, "\n");
+    }
     for (int i = 1; i < L.nev; ++i) {
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, L.ev[i - 1], L.ev[i]) != cudaSuccess) {
@@ -313,11 +346,18 @@ int enqueue_downstream(kpeg_ctx *ctx, Lane &L)
     }
     CK(launch_idct(J.ia, s, &J.launches));
     mark(ctx, L, KPEG_T_IDCT);
+    const bool chain = ctx->d2h_chain && ctx->d2h_done && !J.d2h.empty();
+    if (chain && ctx->d2h_chain_armed)
+        CK(cudaStreamWaitEvent(s, ctx->d2h_done, 0));
     for (const Copy &c : J.d2h) {
         if (c.peer >= 0)
             CK(cudaMemcpyPeerAsync(c.dst, c.peer, c.src, ctx->device, c.bytes, s));
         else
             CK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, s));
+    }
+    if (chain) {
+        CK(cudaEventRecord(ctx->d2h_done, s));
+        ctx->d2h_chain_armed = true;
     }
     if (!J.d2h.empty())
         mark(ctx, L, KPEG_T_D2H);
@@ -348,7 +388,7 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     cudaStream_t s = L.stream;
     if (J.active) // a deferred job still owns this lane's scratch: complete it first
         finish_deferred(ctx, li);
-    if (ctx->have_plan && memcmp(&ctx->plan_cached, pl, sizeof *pl) != 0)
+    if (ctx->have_plan && !same_tables(&ctx->plan_cached, pl))
         for (int i = 0; i < NLANES; ++i) // the tables are shared: nothing deferred may outlive them
             if (ctx->lane[i].job.active)
                 finish_deferred(ctx, i);
@@ -616,6 +656,88 @@ void zero_stats(kpeg_stats *stats)
         memset(stats, 0, sizeof *stats);
 }
 
+// One large restart-marked image from host memory: its restart-interval bands (whole MCU rows, each a complete image
+// of the same width and tables) go through the lanes one band per lane, so the copy in of one band, the kernels of
+// another and the copy out of a third overlap.  The cut points are found by walking the restart markers of the scan
+// (as kpeg_split_restart_bands does) -- about 0.1 ms per MB on the host -- so the walk is interleaved with the
+// submissions: a band is enqueued as soon as the marker that ends it has been found, and the GPU works on it while
+// the walk goes on.  Synchronous.  KPEG_ERR_UNSUPPORTED when the restart interval does not line up with MCU rows
+// (nothing has been enqueued then).
+int decode_banded(kpeg_ctx *ctx, const kpeg_plan *plan, const uint8_t *scan, size_t scan_len, uint8_t *pixels_out, kpeg_stats *stats)
+{
+    const uint32_t mx = (plan->width + 7u) / 8u, my = (plan->height + 7u) / 8u, ri = plan->restart_interval;
+    if (ri == 0 || !((ri % mx) == 0 || (mx % ri) == 0))
+        return KPEG_ERR_UNSUPPORTED; // bands must begin on a restart marker
+    const uint32_t row_step = (ri % mx) == 0 ? ri / mx : 1u; // MCU rows between candidate cut points
+    const uint32_t units = (my + row_step - 1) / row_step;
+    const uint32_t parts = std::min<uint32_t>((uint32_t)std::min(ctx->band_parts, NLANES), units);
+    if (parts < 2)
+        return KPEG_ERR_UNSUPPORTED;
+    uint32_t row[NLANES + 1]; // first MCU row of every band, balanced in cut units (kpeg_split_restart_bands)
+    for (uint32_t k = 0; k <= parts; ++k)
+        row[k] = std::min<uint32_t>(my, (uint32_t)((uint64_t)units * k / parts) * row_step);
+    for (int i = 0; i < NLANES; ++i)
+        if (ctx->lane[i].job.active)
+            finish_deferred(ctx, i);
+    const size_t row_bytes = (size_t)plan->width * plan->ncomp;
+    int rc = KPEG_OK, used[NLANES], nused = 0;
+    auto submit = [&](uint32_t k, size_t begin, size_t end) -> int { // band k = scan[begin, end)
+        const uint32_t r0 = std::min<uint32_t>(row[k] * 8u, plan->height), r1 = std::min<uint32_t>(row[k + 1] * 8u, plan->height);
+        Lane &L = ctx->lane[k];
+        kpeg_plan bp = *plan;
+        bp.height = (uint16_t)(r1 - r0);
+        const size_t blen = end - begin, bpix = row_bytes * (r1 - r0);
+        TRY(ensure(ctx, L.stream, L.scan, blen + 64));
+        TRY(ensure(ctx, L.stream, L.pixels, bpix + 64));
+        mark(ctx, L, -1);
+        CK(cudaMemcpyAsync(L.scan.p, scan + begin, blen, cudaMemcpyHostToDevice, L.stream));
+        mark(ctx, L, KPEG_T_H2D);
+        TRY(job_enqueue(ctx, (int)k, &bp, (const uint8_t *)L.scan.p, blen, 1, (uint8_t *)L.pixels.p,
+                        {Copy{pixels_out + (size_t)r0 * row_bytes, L.pixels.p, bpix}}));
+        used[nused++] = (int)k;
+        return KPEG_OK;
+    };
+    // walk the markers: marker number j (1-based) precedes restart interval j; band b begins after marker row[b] * mx / ri
+    uint32_t b = 1;
+    uint64_t markers = 0;
+    size_t begin = 0;
+    const uint8_t *p = scan, *end = scan + scan_len;
+    while (b < parts && p + 1 < end && rc == KPEG_OK) {
+        const uint8_t *q = (const uint8_t *)memchr(p, 0xFF, (size_t)(end - 1 - p));
+        if (!q)
+            break;
+        const uint8_t m = q[1];
+        if (m >= 0xD0 && m <= 0xD7) {
+            ++markers;
+            if (((uint64_t)row[b] * mx) / ri == markers) {
+                rc = submit(b - 1, begin, (size_t)(q - scan));
+                begin = (size_t)(q + 2 - scan);
+                ++b;
+            }
+            p = q + 2;
+        } else {
+            p = q + (m == 0xFF ? 1 : 2);
+        }
+    }
+    if (rc == KPEG_OK && b < parts)
+        rc = fail(ctx, KPEG_ERR_STREAM, "fewer restart markers than the restart interval promises");
+    if (rc == KPEG_OK)
+        rc = submit(parts - 1, begin, scan_len);
+    const std::string first_err = ctx->err;
+    for (int i = 0; i < nused; ++i) { // every enqueued band is completed, whatever happened to the others
+        const int frc = job_finish(ctx, used[i], stats);
+        if (rc == KPEG_OK && frc != KPEG_OK)
+            rc = frc;
+        else if (frc != KPEG_OK)
+            ctx->err = first_err;
+    }
+    if (stats) {
+        stats->width = plan->width;
+        stats->height = plan->height;
+    }
+    return rc;
+}
+
 } // namespace
 
 // ==================================================================================================
@@ -674,6 +796,11 @@ extern "C" int kpeg_cuda_create(int device, kpeg_ctx **out)
         ctx->submit_parts = std::max(1, std::min(NLANES, atoi(e)));
     if (const char *e = getenv("KPEG_HOST_CHUNKS"))
         ctx->host_chunks = std::max(1, std::min(64, atoi(e)));
+    if (const char *e = getenv("KPEG_BANDS"))
+        ctx->band_parts = std::max(1, std::min(NLANES, atoi(e)));
+    if (const char *e = getenv("KPEG_D2H_CHAIN"))
+        ctx->d2h_chain = e[0] != '0';
+    cudaEventCreateWithFlags(&ctx->d2h_done, cudaEventDisableTiming);
     if (const char *rr = getenv("KPEG_RELAY_ROUNDS")) {
         const long v = strtol(rr, nullptr, 10);
         if (v >= 2 && v < MAX_RELAY_ROUNDS)
@@ -735,6 +862,8 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
         cudaFreeHost(ctx->h_sep.p);
     if (ctx->tables_ready)
         cudaEventDestroy(ctx->tables_ready);
+    if (ctx->d2h_done)
+        cudaEventDestroy(ctx->d2h_done);
     delete ctx;
 }
 
@@ -866,6 +995,11 @@ extern "C" int kpeg_cuda_decode(kpeg_ctx *ctx, const kpeg_plan *plan, const uint
     if (L.job.active) // a deferred job still reads this lane's scan / pixel buffers: complete it before they can move
         finish_deferred(ctx, 0);
     const size_t npix = (size_t)plan->width * plan->height * plan->ncomp;
+    if (ctx->band_parts > 1 && plan->restart_interval != 0 && npix >= ((size_t)64 << 20)) {
+        const int brc = decode_banded(ctx, plan, scan, scan_len, pixels_out, stats);
+        if (brc != KPEG_ERR_UNSUPPORTED) // UNSUPPORTED: the restart interval does not line up with MCU rows -- whole image below
+            return brc;
+    }
     TRY(ensure(ctx, L.stream, L.scan, scan_len + 64));
     TRY(ensure(ctx, L.stream, L.pixels, npix + 64));
     mark(ctx, L, -1);

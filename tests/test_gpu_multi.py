@@ -172,3 +172,38 @@ def test_host_batch_small_and_large_scans_contiguous_outputs(decoder):
     for i, (a, b) in enumerate(zip(outs2, want)):
         assert np.array_equal(a, b), f"image {i} (separate outputs)"
     frame.free()
+
+
+def test_large_restart_image_goes_through_the_lanes_in_bands(monkeypatch):
+    """With KPEG_BANDS=4, kpeg_cuda_decode on a large (>= 64 MB of pixels) restart-marked image from host memory cuts it
+    into four restart-interval bands that run on the context's lanes with their copies overlapping (decode_banded; off
+    by default, the host-side marker walk costs more than the overlap gains); the frame must equal the one a context
+    without it (whole image, one lane) produces, a corrupt band must surface as an
+    error, and an image whose restart interval does not line up with MCU rows must still decode (whole)."""
+    w, h = 8192, 2744  # 67 MB of pixels; 343 MCU rows: bands of unequal height
+    jpg = _banded_jpg(w=w, h=h, ri_rows=1, q=60, seed=21)
+    monkeypatch.setenv("KPEG_BANDS", "4")
+    banded = K.Decoder(device=0)
+    monkeypatch.delenv("KPEG_BANDS")
+    whole = K.Decoder(device=0)
+    try:
+        a = banded.decode_file(jpg)
+        launches_banded = banded.last_stats.kernel_launches
+        b = whole.decode_file(jpg)
+        assert np.array_equal(a, b)
+        assert launches_banded >= 3 * whole.last_stats.kernel_launches  # four kernel sequences, not one
+        assert banded.last_stats.height == h and banded.last_stats.segments >= 343
+        # (content against the oracle: test_config4_full_size_restart_bands and the small-image tests; the oracle on an
+        # image of this size takes minutes)
+        bad = bytearray(jpg)
+        _, off, n = K.parse_jfif(bytes(bad))
+        bad[off + n // 2: off + n // 2 + 64] = bytes(64)  # a run of zero bytes inside the third band
+        with pytest.raises(K.KpegError):
+            banded.decode_file(bytes(bad))
+        assert np.array_equal(banded.decode_file(jpg), b)  # the context is usable afterwards
+        # restart interval of 5 MCUs: neither a whole number of rows nor a divisor of one -> decoded whole
+        odd = synth_encode(SynthParams(width=w, height=h, quality=30, restart_interval=5, flags=QUIRK_FREE | EMIT_RESTART, seed=4)).tobytes()
+        assert np.array_equal(banded.decode_file(odd), whole.decode_file(odd))
+    finally:
+        banded.close()
+        whole.close()
