@@ -103,6 +103,22 @@ typedef struct kpeg_ctx kpeg_ctx;
  * Decoder.cpp:532-577, would read: everything after the SOS header up to the EOI marker). */
 int kpeg_parse_jfif(const uint8_t *file, size_t len, kpeg_plan *plan, size_t *scan_off, size_t *scan_len);
 
+/* A frame with one scan PER component (T.81 A.2.3; the reference reads such SOS headers, Decoder.cpp:461-530, and then
+ * decodes the first scan as if it were interleaved).  One kpeg_scan per SOS: `plan` is everything needed to decode THAT
+ * scan on its own -- ncomp = its number of components (1 for a non-interleaved scan, with that component's selectors in
+ * slot 0), the tables and restart interval in force at its SOS (they may be redefined between scans, T.81 B.2.3) --
+ * comp[] the frame component behind each slot, [off, off + len) its entropy-coded segment inside the file.
+ * kpeg_parse_jfif_scans accepts what kpeg_parse_jfif accepts (then *nscans == 1 and scans[0].plan == *frame) plus
+ * three-component frames coded as three single-component scans in any order; *frame then holds the dimensions and,
+ * in slots 0..2, the quantisers of components 0..2 (frame->restart_interval is 0: it is a per-scan property). */
+typedef struct kpeg_scan {
+    kpeg_plan plan;
+    uint8_t comp[3];
+    size_t off, len;
+} kpeg_scan;
+#define KPEG_MAX_SCANS 3
+int kpeg_parse_jfif_scans(const uint8_t *file, size_t len, kpeg_plan *frame, kpeg_scan *scans, int max_scans, int *nscans);
+
 /* ---- context ------------------------------------------------------------------------------ */
 /* One context per (thread, device): owns eight lanes (a CUDA stream with its own device scratch and pinned
  * bookkeeping each), all grown on demand and reused across decodes.  Not thread-safe; use one context per thread. */
@@ -196,8 +212,16 @@ int kpeg_cuda_wait(kpeg_ctx *ctx, kpeg_stats *stats);
 int kpeg_cuda_submit_batch(kpeg_ctx *ctx, const kpeg_plan *plan, int n, const uint8_t *const *scans,
                            const size_t *scan_lens, uint8_t *const *pixels_out);
 
-/* Whole-file convenience used by the JPEGDecoder drop-in: parse + decode.  pixels_out must hold
- * width*height*ncomp bytes (query with kpeg_parse_jfif first) -- cap is checked. */
+/* The scans kpeg_parse_jfif_scans found, decoded to one frame (HOST buffers in and out, synchronous).  One interleaved
+ * scan is kpeg_cuda_decode; three single-component scans are entropy-decoded one after another, each with its own
+ * tables, into per-component coefficient tiles, which one small kernel interleaves into the MCU order K3 consumes --
+ * from there on (dequantisation, IDCT, colour, store: MCU.cpp:110-279, Image.cpp:51-70) the path is the same.
+ * frame->flags selects the parity mode for every scan. */
+int kpeg_cuda_decode_scans(kpeg_ctx *ctx, const kpeg_plan *frame, const kpeg_scan *scans, int nscans, const uint8_t *file,
+                           size_t file_len, uint8_t *pixels_out, kpeg_stats *stats);
+
+/* Whole-file convenience used by the JPEGDecoder drop-in: parse (kpeg_parse_jfif_scans) + decode (kpeg_cuda_decode_scans).
+ * pixels_out must hold width*height*ncomp bytes (query with kpeg_parse_jfif_scans first) -- cap is checked. */
 int kpeg_cuda_decode_file(kpeg_ctx *ctx, const uint8_t *file, size_t len, uint32_t flags, uint8_t *pixels_out,
                           size_t cap, kpeg_plan *plan_out, kpeg_stats *stats);
 

@@ -31,6 +31,7 @@ extern "C" {
 #define KPEG_SYNTH_EMIT_RESTART 1u /* write DRI + RSTn (otherwise restart_interval only shapes the nudge) */
 #define KPEG_SYNTH_GRAY_CONTENT 2u /* luminance-only content; chroma blocks (if any) are all zero */
 #define KPEG_SYNTH_QUIRK_FREE 4u   /* see above */
+#define KPEG_SYNTH_NON_INTERLEAVED 8u /* three-component files: one scan per component (T.81 A.2.3) instead of one interleaved scan */
 
 typedef struct kpeg_synth_params {
     int32_t width, height;       /* pixels; any size >= 1 (edges are replicated to whole blocks) */

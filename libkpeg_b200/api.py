@@ -46,6 +46,14 @@ class Plan(C.Structure):
     ]
 
 
+class Scan(C.Structure):
+    """struct kpeg_scan: one SOS of a frame (kpeg_parse_jfif_scans)"""
+    _fields_ = [("plan", Plan), ("comp", C.c_uint8 * 3), ("off", C.c_size_t), ("len", C.c_size_t)]
+
+
+KPEG_MAX_SCANS = 3
+
+
 class Stats(C.Structure):
     """struct kpeg_stats"""
     _fields_ = [
@@ -74,6 +82,8 @@ _u8p = C.POINTER(C.c_uint8)
 _vp = C.c_void_p
 SYMBOLS = {
     "kpeg_parse_jfif": (C.c_int, [_vp, C.c_size_t, C.POINTER(Plan), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "kpeg_parse_jfif_scans": (C.c_int, [_vp, C.c_size_t, C.POINTER(Plan), C.POINTER(Scan), C.c_int, C.POINTER(C.c_int)]),
+    "kpeg_cuda_decode_scans": (C.c_int, [_vp, C.POINTER(Plan), C.POINTER(Scan), C.c_int, _vp, C.c_size_t, _vp, C.POINTER(Stats)]),
     "kpeg_cuda_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "kpeg_cuda_destroy": (None, [_vp]),
     "kpeg_cuda_last_error": (C.c_char_p, [_vp]),
@@ -164,6 +174,19 @@ def parse_jfif(data: bytes | np.ndarray):
     return plan, off.value, ln.value
 
 
+def parse_jfif_scans(data: bytes | np.ndarray):
+    """Container parse that also accepts frames coded one scan per component -> (frame Plan, [Scan, ...])."""
+    lib = load_cuda_library()
+    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    frame = Plan()
+    scans = (Scan * KPEG_MAX_SCANS)()
+    n = C.c_int(0)
+    rc = lib.kpeg_parse_jfif_scans(_ptr(buf), buf.size, C.byref(frame), scans, KPEG_MAX_SCANS, C.byref(n))
+    if rc != KPEG_OK:
+        raise KpegError(rc, "kpeg_parse_jfif_scans")
+    return frame, [scans[i] for i in range(n.value)]
+
+
 def ppm_header(width: int, height: int) -> bytes:
     lib = load_cuda_library()
     buf = C.create_string_buffer(256)
@@ -248,9 +271,23 @@ class Decoder:
     # -- decode -------------------------------------------------------------------------------
     def decode_file(self, data, flags: int = KPEG_FLAG_REF_PARITY, out: np.ndarray | None = None) -> np.ndarray:
         buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
-        plan, off, ln = parse_jfif(buf)
-        plan.flags = flags
-        return self.decode_scan(plan, buf[off:off + ln], out=out)
+        frame, scans = parse_jfif_scans(buf)
+        if len(scans) == 1:
+            plan = scans[0].plan
+            plan.flags = flags
+            return self.decode_scan(plan, buf[scans[0].off:scans[0].off + scans[0].len], out=out)
+        # one scan per component: kpeg_cuda_decode_scans
+        frame.flags = flags
+        buf = np.ascontiguousarray(buf)
+        shape = (frame.height, frame.width, frame.ncomp)
+        if out is None:
+            out = np.empty(shape, dtype=np.uint8)
+        assert out.nbytes == frame.height * frame.width * frame.ncomp and out.flags.c_contiguous
+        arr = (Scan * len(scans))(*scans)
+        rc = self._lib.kpeg_cuda_decode_scans(self._h, C.byref(frame), arr, len(scans), _ptr(buf), buf.size, _ptr(out),
+                                              C.byref(self.last_stats))
+        self._check(rc, "kpeg_cuda_decode_scans")
+        return out.reshape(shape)
 
     def decode_scan(self, plan: Plan, scan: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         scan = np.ascontiguousarray(scan, dtype=np.uint8)

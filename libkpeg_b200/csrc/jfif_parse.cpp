@@ -47,16 +47,23 @@ size_t find_scan_end(const uint8_t *f, size_t n, size_t s)
 
 } // namespace
 
-extern "C" int kpeg_parse_jfif(const uint8_t *f, size_t n, kpeg_plan *pl, size_t *scan_off, size_t *scan_len)
+// The marker walk.  `pl` accumulates the frame and the tables in force; every SOS adds one kpeg_scan: a plan of its own
+// (the scan's components in slots 0.., the tables and restart interval in force at that point -- T.81 B.2.3 allows DHT /
+// DQT / DRI between scans) and its entropy-coded segment.  Accepted: ONE interleaved scan of all components in frame
+// order (what the reference decodes, Decoder.cpp:461-530), or one scan PER component in any order (T.81 A.2.3: the MCU
+// of a non-interleaved scan is one block; the reference reads such SOS headers and then mis-decodes).  Stops as soon as
+// every component has its scan.
+static int parse_impl(const uint8_t *f, size_t n, kpeg_plan *pl, kpeg_scan *scans, int max_scans, int *nscans)
 {
-    if (!f || !pl || !scan_off || !scan_len)
-        return KPEG_ERR_ARG;
     memset(pl, 0, sizeof *pl);
+    *nscans = 0;
     if (n < 4 || f[0] != 0xFF || f[1] != 0xD8)
         return KPEG_ERR_FORMAT; // no SOI
     size_t i = 2;
     bool have_frame = false;
     uint8_t comp_id[3] = {0, 0, 0};
+    bool comp_done[3] = {false, false, false};
+    unsigned covered = 0;
     for (;;) {
         if (i + 2 > n)
             return KPEG_ERR_FORMAT;
@@ -71,7 +78,7 @@ extern "C" int kpeg_parse_jfif(const uint8_t *f, size_t n, kpeg_plan *pl, size_t
         if (marker == 0xD8 || marker == 0x01 || (marker >= 0xD0 && marker <= 0xD7))
             continue; // stand-alone markers
         if (marker == 0xD9)
-            return KPEG_ERR_FORMAT; // EOI before any scan
+            return KPEG_ERR_FORMAT; // EOI before every component had its scan
         if (i + 2 > n)
             return KPEG_ERR_FORMAT;
         const unsigned L = be16(f + i);
@@ -81,7 +88,7 @@ extern "C" int kpeg_parse_jfif(const uint8_t *f, size_t n, kpeg_plan *pl, size_t
         const unsigned plen = L - 2;
         switch (marker) {
         case 0xC0: { // SOF0 -- parseSOF0Segment, Decoder.cpp:301-364
-            if (plen < 6)
+            if (plen < 6 || have_frame)
                 return KPEG_ERR_FORMAT;
             if (p[0] != 8)
                 return KPEG_ERR_UNSUPPORTED;
@@ -160,35 +167,96 @@ extern "C" int kpeg_parse_jfif(const uint8_t *f, size_t n, kpeg_plan *pl, size_t
             if (!have_frame || plen < 1)
                 return KPEG_ERR_FORMAT;
             const unsigned ns = p[0];
-            if (ns != pl->ncomp)
-                return KPEG_ERR_UNSUPPORTED; // non-interleaved multi-scan files
+            if (ns != pl->ncomp && ns != 1)
+                return KPEG_ERR_UNSUPPORTED; // two-component scans
             if (plen < 1 + 2 * ns + 3)
                 return KPEG_ERR_FORMAT;
+            if (*nscans >= max_scans)
+                return KPEG_ERR_UNSUPPORTED; // a multi-scan file handed to the single-scan entry point
+            kpeg_scan *sc = &scans[*nscans];
+            memset(sc, 0, sizeof *sc);
+            sc->plan = *pl; // dimensions, tables and restart interval as they stand
+            sc->plan.ncomp = (uint8_t)ns;
             for (unsigned s = 0; s < ns; ++s) {
-                if (p[1 + 2 * s] != comp_id[s])
-                    return KPEG_ERR_UNSUPPORTED; // scan order must be frame order
+                unsigned c = 0;
+                while (c < pl->ncomp && comp_id[c] != p[1 + 2 * s])
+                    ++c;
+                if (c == pl->ncomp)
+                    return KPEG_ERR_FORMAT; // no such component in the frame
+                if (ns > 1 && c != s)
+                    return KPEG_ERR_UNSUPPORTED; // an interleaved scan must list the components in frame order
+                if (comp_done[c])
+                    return KPEG_ERR_UNSUPPORTED; // a component coded twice: not sequential baseline
                 const unsigned td = p[2 + 2 * s] >> 4, ta = p[2 + 2 * s] & 15u;
                 if (td > 3 || ta > 3)
                     return KPEG_ERR_FORMAT;
-                pl->comp_td[s] = (uint8_t)td;
-                pl->comp_ta[s] = (uint8_t)ta;
-            }
-            for (unsigned c = 0; c < pl->ncomp; ++c) {
-                if (!pl->qt_present[pl->comp_tq[c]] || !pl->ht_present[0][pl->comp_td[c]] ||
-                    !pl->ht_present[1][pl->comp_ta[c]])
+                if (!pl->qt_present[pl->comp_tq[c]] || !pl->ht_present[0][td] || !pl->ht_present[1][ta])
                     return KPEG_ERR_FORMAT;
+                comp_done[c] = true;
+                sc->comp[s] = (uint8_t)c;
+                sc->plan.comp_tq[s] = pl->comp_tq[c];
+                sc->plan.comp_td[s] = (uint8_t)td;
+                sc->plan.comp_ta[s] = (uint8_t)ta;
+                pl->comp_td[c] = (uint8_t)td;
+                pl->comp_ta[c] = (uint8_t)ta;
             }
+            for (unsigned s = ns; s < 3; ++s)
+                sc->plan.comp_tq[s] = sc->plan.comp_td[s] = sc->plan.comp_ta[s] = 0;
             const size_t s0 = i + L;
             const size_t e = find_scan_end(f, n, s0);
-            *scan_off = s0;
-            *scan_len = e - s0;
-            return KPEG_OK;
+            sc->off = s0;
+            sc->len = e - s0;
+            ++*nscans;
+            covered += ns;
+            if (covered == pl->ncomp)
+                return KPEG_OK;
+            if (e + 1 >= n)
+                return KPEG_ERR_FORMAT; // the file ends before the other components' scans
+            i = e; // on the marker that ended the segment
+            continue;
         }
         default: // APPn, COM, DNL, ...: skipped by length
             break;
         }
         i += L;
     }
+}
+
+extern "C" int kpeg_parse_jfif(const uint8_t *f, size_t n, kpeg_plan *pl, size_t *scan_off, size_t *scan_len)
+{
+    if (!f || !pl || !scan_off || !scan_len)
+        return KPEG_ERR_ARG;
+    kpeg_scan sc;
+    int ns = 0;
+    const int rc = parse_impl(f, n, pl, &sc, 1, &ns);
+    if (rc != KPEG_OK)
+        return rc;
+    *pl = sc.plan; // one interleaved scan: its plan is the frame's
+    *scan_off = sc.off;
+    *scan_len = sc.len;
+    return KPEG_OK;
+}
+
+extern "C" int kpeg_parse_jfif_scans(const uint8_t *f, size_t n, kpeg_plan *frame, kpeg_scan *scans, int max_scans, int *nscans)
+{
+    if (!f || !frame || !scans || max_scans < 1 || !nscans)
+        return KPEG_ERR_ARG;
+    const int rc = parse_impl(f, n, frame, scans, max_scans, nscans);
+    if (rc != KPEG_OK || *nscans == 1)
+        return rc;
+    // one scan per component.  The quantiser of a component is the table in force when ITS scan began (T.81 B.2.3): the
+    // frame plan gets them in slots 0..2, component c using slot c, whatever ids the file used.
+    kpeg_plan out = *frame;
+    memset(out.qt_present, 0, sizeof out.qt_present);
+    for (int k = 0; k < *nscans; ++k) {
+        const unsigned c = scans[k].comp[0];
+        memcpy(out.qt[c], scans[k].plan.qt[scans[k].plan.comp_tq[0]], sizeof out.qt[c]);
+        out.qt_present[c] = 1;
+        out.comp_tq[c] = (uint8_t)c;
+    }
+    out.restart_interval = 0; // per scan (kpeg_scan::plan)
+    *frame = out;
+    return KPEG_OK;
 }
 
 // Cuts one restart-marked entropy-coded segment into `parts` bands of whole MCU rows, so that each

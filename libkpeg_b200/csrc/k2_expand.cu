@@ -282,6 +282,30 @@ __global__ void __launch_bounds__(256) matrix_from_tiles_kernel(const uint4 *til
     coef[i] = make_uint4(v.x ^ BIAS2, v.y ^ BIAS2, v.z ^ BIAS2, v.w ^ BIAS2);
 }
 
+// ---- one scan per component (T.81 A.2.3) --------------------------------------------------------------------
+// Every component was entropy-decoded as a one-component image of its own: its tiles hold block m of the component at
+// block position m.  K3 wants the blocks of an MCU side by side (block m * 3 + c): one thread per 16-byte chunk.
+__global__ void __launch_bounds__(256) interleave_tiles_kernel(const uint4 *t0, const uint4 *t1, const uint4 *t2, uint4 *out,
+                                                               uint32_t nmcu_padded)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x; // chunk index in the interleaved tiles
+    const uint32_t gb = i >> 3, k = i & 7u;
+    const uint32_t m = gb / 3u, c = gb - m * 3u;
+    if (m >= nmcu_padded)
+        return;
+    const uint4 *src = c == 0u ? t0 : (c == 1u ? t1 : t2);
+    out[coef_tile_chunk(gb, k)] = __ldg(src + coef_tile_chunk(m, k));
+}
+
+void launch_interleave_tiles(const void *t0, const void *t1, const void *t2, void *out, uint32_t nmcu_padded, cudaStream_t s,
+                             uint32_t *launches)
+{
+    const uint32_t chunks = nmcu_padded * 3u * 8u;
+    interleave_tiles_kernel<<<(chunks + 255u) / 256u, 256, 0, s>>>(reinterpret_cast<const uint4 *>(t0), reinterpret_cast<const uint4 *>(t1),
+                                                                   reinterpret_cast<const uint4 *>(t2), reinterpret_cast<uint4 *>(out), nmcu_padded);
+    ++*launches;
+}
+
 void launch_expand(const ExpandArgs &a, cudaStream_t s, uint32_t *launches)
 {
     const uint32_t total_mcus = a.g.nimages * a.g.mcus_per_image;

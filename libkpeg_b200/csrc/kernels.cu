@@ -1135,8 +1135,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) entropy_scan_apply_kernel(Entrop
         status |= (st.cz & CZ_SLOT_OVERFLOW) ? ST_SLOT_OVERFLOW : 0u;
         status |= (st.cz & CZ_SEG_MISMATCH) ? ST_SEG_MISMATCH : 0u;
         const uint32_t total_slots = a.g.total_blocks * 64u;
-        // surplus symbols after the last MCU of the stream are not an error (as in the Huffman final pass)
-        if (st.seg >= 0 && (begin & ~63u) + (st.cz >> CZ_POS_SHIFT) != end && !((uint32_t)st.seg >= a.g.nseg && end >= total_slots))
+        // surplus symbols after the last MCU of the stream are not an error (as in the Huffman final pass); a stream that
+        // ENDS before its last MCU is: its last symbol straddles the end like padding would, but too early
+        const uint32_t reached = (begin & ~63u) + (st.cz >> CZ_POS_SHIFT);
+        if (st.seg >= 0 && reached != end && !((uint32_t)st.seg >= a.g.nseg && end >= total_slots && reached >= total_slots))
             status |= ST_SEG_MISMATCH;
         if ((end & 63u) != (st.cz & 63u) || ((end >> 6) % a.g.ncomp) != ((st.cz >> 8) & 3u))
             status |= ST_EXIT_MISMATCH;

@@ -139,6 +139,9 @@ void launch_expand(const ExpandArgs &a, cudaStream_t s, uint32_t *launches); // 
 // fallback (after the Huffman final pass + dc_integrate): plain coefficient matrix -> tile images
 void launch_tiles_from_matrix(const JobGeom &g, const int16_t *coef, const int16_t *dc, void *tiles, cudaStream_t s, uint32_t *launches);
 void launch_matrix_from_tiles(const void *tiles, int16_t *coef, uint32_t total_blocks, cudaStream_t s); // parity hook
+// three one-component tile sets (one scan per component) -> the MCU-interleaved tiles K3 consumes
+void launch_interleave_tiles(const void *t0, const void *t1, const void *t2, void *out, uint32_t nmcu_padded, cudaStream_t s,
+                             uint32_t *launches);
 cudaError_t launch_idct(const IdctArgs &a, cudaStream_t s, uint32_t *launches);
 void k3_configure();                      // function attributes of the K3 kernels (called by kernels_configure)
 uint32_t k3_strip_slots(uint32_t ncomp);  // coefficient slots one K3 strip covers

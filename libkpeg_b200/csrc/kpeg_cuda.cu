@@ -69,6 +69,7 @@ struct Job {
     bool loop_used = true; // relay rounds 2.. ran as the cooperative device-side loop (DevMeta::relay_rounds is meaningful)
     size_t scan_len = 0;
     std::vector<Copy> d2h; // result copies to (re)issue after the downstream stages
+    bool entropy_only = false; // stop after K2: the tiles are the result (one scan of a frame coded one scan per component)
 };
 
 struct Lane {
@@ -110,6 +111,7 @@ struct kpeg_ctx {
     Lane lane[NLANES];
 
     DevBuf tables, merged;
+    DevBuf scan_tiles[3]; // frames coded one scan per component: the components' tiles before they are interleaved
     PinBuf h_tables, h_sep;
     cudaEvent_t tables_ready = nullptr;
     kpeg_plan plan_cached;
@@ -341,11 +343,13 @@ int enqueue_downstream(kpeg_ctx *ctx, Lane &L)
         launch_entropy_write(J.ea, s, &J.launches);
         mark(ctx, L, KPEG_T_ENTROPY_WRITE);
         launch_dc_integrate(J.g, (const int16_t *)L.dcdiff.p, (int16_t *)L.dc.p, s, &J.launches);
-        launch_tiles_from_matrix(J.g, (const int16_t *)L.coef.p, (const int16_t *)L.dc.p, L.tiles.p, s, &J.launches);
+        launch_tiles_from_matrix(J.g, (const int16_t *)L.coef.p, (const int16_t *)L.dc.p, J.xa.tiles, s, &J.launches);
         mark(ctx, L, KPEG_T_DC_SCAN);
     }
-    CK(launch_idct(J.ia, s, &J.launches));
-    mark(ctx, L, KPEG_T_IDCT);
+    if (!J.entropy_only) {
+        CK(launch_idct(J.ia, s, &J.launches));
+        mark(ctx, L, KPEG_T_IDCT);
+    }
     const bool chain = ctx->d2h_chain && ctx->d2h_done && !J.d2h.empty();
     if (chain && ctx->d2h_chain_armed)
         CK(cudaStreamWaitEvent(s, ctx->d2h_done, 0));
@@ -381,7 +385,7 @@ void finish_deferred(kpeg_ctx *ctx, int li)
 // order) at d_scan.  Optimistic: the stages downstream of the relay are issued before it is known
 // whether the pre-issued relay rounds reached the fixed point; job_finish repairs that if not.
 int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_scan, size_t scan_len, uint32_t nimages,
-                uint8_t *d_pixels, std::vector<Copy> d2h)
+                uint8_t *d_pixels, std::vector<Copy> d2h, void *tiles_only = nullptr)
 {
     Lane &L = ctx->lane[li];
     Job &J = L.job;
@@ -444,6 +448,8 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     J.g = g;
     J.scan_len = scan_len;
     J.d2h = std::move(d2h);
+    J.entropy_only = tiles_only != nullptr;
+    void *const tiles = tiles_only ? tiles_only : L.tiles.p;
     DevMeta *d_meta = (DevMeta *)L.meta.p;
 
     CK(cudaMemsetAsync(d_meta, 0, sizeof(DevMeta), s));
@@ -498,13 +504,13 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     xa.start_slot = ea.start_slot;
     xa.strip_sub = ea.strip_sub;
     xa.dcpre = ea.dcpre;
-    xa.tiles = L.tiles.p;
+    xa.tiles = tiles;
     xa.nstrips = nstrips;
     xa.meta = d_meta;
     xa.g = g;
 
     IdctArgs &ia = J.ia;
-    ia.tiles = L.tiles.p;
+    ia.tiles = tiles;
     ia.nstrips = nstrips;
     ia.tables = (const DeviceTables *)ctx->tables.p;
     ia.pixels = d_pixels;
@@ -864,6 +870,8 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
         cudaEventDestroy(ctx->tables_ready);
     if (ctx->d2h_done)
         cudaEventDestroy(ctx->d2h_done);
+    for (DevBuf &b : ctx->scan_tiles)
+        dev_free(b);
     delete ctx;
 }
 
@@ -1397,22 +1405,138 @@ extern "C" int kpeg_cuda_interleaved_to_planar(kpeg_ctx *ctx, const uint8_t *d_r
     return KPEG_OK;
 }
 
+// A frame coded one scan per component (T.81 A.2.3).  Every scan is a one-component image with tables of its own: K0,
+// K1 and K2 run on it unchanged and leave the component's coefficient tiles (DC prediction and the reference's
+// DC-difference rule included: both are per component); one kernel interleaves the three tile sets into MCU order and
+// K3 runs as for an interleaved file.  Synchronous, on lane 0; not a throughput path.
+extern "C" int kpeg_cuda_decode_scans(kpeg_ctx *ctx, const kpeg_plan *frame, const kpeg_scan *scans, int nscans, const uint8_t *file,
+                                      size_t file_len, uint8_t *pixels_out, kpeg_stats *stats)
+{
+    if (!ctx || !frame || !scans || nscans < 1 || !file || !pixels_out)
+        return KPEG_ERR_ARG;
+    for (int k = 0; k < nscans; ++k)
+        if (scans[k].off > file_len || scans[k].len > file_len - scans[k].off)
+            return fail(ctx, KPEG_ERR_ARG, "scan outside the file");
+    if (nscans == 1 && scans[0].plan.ncomp == frame->ncomp) {
+        kpeg_plan pl = scans[0].plan;
+        pl.flags = frame->flags;
+        return kpeg_cuda_decode(ctx, &pl, file + scans[0].off, scans[0].len, pixels_out, stats);
+    }
+    if (frame->ncomp != 3 || nscans != 3)
+        return fail(ctx, KPEG_ERR_UNSUPPORTED, "a frame is one interleaved scan or one scan per component");
+    bool seen[3] = {false, false, false};
+    for (int k = 0; k < 3; ++k) {
+        if (scans[k].plan.ncomp != 1 || scans[k].comp[0] > 2 || seen[scans[k].comp[0]] || scans[k].plan.width != frame->width ||
+            scans[k].plan.height != frame->height)
+            return fail(ctx, KPEG_ERR_ARG, "scans do not cover the frame's components once each");
+        seen[scans[k].comp[0]] = true;
+    }
+    CK(cudaSetDevice(ctx->device));
+    zero_stats(stats);
+    for (int i = 0; i < NLANES; ++i)
+        if (ctx->lane[i].job.active)
+            finish_deferred(ctx, i);
+    Lane &L = ctx->lane[0];
+    cudaStream_t s = L.stream;
+    JobGeom g3;
+    const char *why = nullptr;
+    const int grc = make_job_geom(frame, 1, ctx->sub_bits, &g3, &why);
+    if (grc != KPEG_OK)
+        return fail(ctx, grc, why);
+    const uint32_t nstrips = (g3.mcus_per_image + IDCT_MCUS_PER_CTA - 1) / IDCT_MCUS_PER_CTA;
+    const uint32_t nmcu_padded = nstrips * IDCT_MCUS_PER_CTA;
+    for (int c = 0; c < 3; ++c)
+        TRY(ensure(ctx, s, ctx->scan_tiles[c], (size_t)nmcu_padded * 128u + 256u));
+    kpeg_stats part;
+    uint32_t launches = 0;
+    for (int k = 0; k < 3; ++k) {
+        kpeg_plan pl = scans[k].plan;
+        pl.flags = frame->flags;
+        TRY(ensure(ctx, s, L.scan, scans[k].len + 64));
+        mark(ctx, L, -1);
+        CK(cudaMemcpyAsync(L.scan.p, file + scans[k].off, scans[k].len, cudaMemcpyHostToDevice, s));
+        mark(ctx, L, KPEG_T_H2D);
+        TRY(job_enqueue(ctx, 0, &pl, (const uint8_t *)L.scan.p, scans[k].len, 1, nullptr, {}, ctx->scan_tiles[scans[k].comp[0]].p));
+        memset(&part, 0, sizeof part);
+        TRY(job_finish(ctx, 0, stats ? &part : nullptr));
+        if (stats) {
+            stats->scan_bytes += part.scan_bytes;
+            stats->unstuffed_bytes += part.unstuffed_bytes;
+            stats->segments += part.segments;
+            stats->subsequences += part.subsequences;
+            stats->sync_rounds = std::max(stats->sync_rounds, part.sync_rounds);
+            stats->kernel_launches += part.kernel_launches;
+            for (int t = 0; t < KPEG_T_COUNT; ++t)
+                stats->ms[t] += part.ms[t];
+            stats->ms_total += part.ms_total;
+        }
+    }
+    // the frame's tables (quantisers of the three components) for K3
+    kpeg_plan fp = *frame;
+    for (int c = 0; c < 3; ++c) { // K3 needs no Huffman tables, but the device tables are built from a whole plan
+        fp.comp_td[c] = scans[0].plan.comp_td[0];
+        fp.comp_ta[c] = scans[0].plan.comp_ta[0];
+    }
+    memcpy(fp.ht, scans[0].plan.ht, sizeof fp.ht);
+    memcpy(fp.ht_present, scans[0].plan.ht_present, sizeof fp.ht_present);
+    TRY(upload_plan(ctx, &fp));
+    const size_t npix = (size_t)frame->width * frame->height * 3u;
+    TRY(ensure(ctx, s, L.tiles, (size_t)nmcu_padded * 3u * 128u + 256u));
+    TRY(ensure(ctx, s, L.pixels, npix + 64));
+    TRY(ensure(ctx, s, L.tie_rec, (size_t)nstrips * IDCT_TIE_LIST_CAP * sizeof(uint4)));
+    TRY(ensure(ctx, s, L.tie_cnt, (size_t)nstrips * sizeof(uint32_t)));
+    DevMeta *d_meta = (DevMeta *)L.meta.p, *h_meta = (DevMeta *)L.h_meta.p;
+    CK(cudaMemsetAsync(d_meta, 0, sizeof(DevMeta), s));
+    mark(ctx, L, -1);
+    launch_interleave_tiles(ctx->scan_tiles[0].p, ctx->scan_tiles[1].p, ctx->scan_tiles[2].p, L.tiles.p, nmcu_padded, s, &launches);
+    IdctArgs ia;
+    ia.tiles = L.tiles.p;
+    ia.nstrips = nstrips;
+    ia.tables = (const DeviceTables *)ctx->tables.p;
+    ia.pixels = (uint8_t *)L.pixels.p;
+    ia.tie_rec = (uint4 *)L.tie_rec.p;
+    ia.tie_cnt = (uint32_t *)L.tie_cnt.p;
+    ia.meta = d_meta;
+    ia.g = g3;
+    CK(launch_idct(ia, s, &launches));
+    mark(ctx, L, KPEG_T_IDCT);
+    CK(cudaMemcpyAsync(pixels_out, L.pixels.p, npix, cudaMemcpyDeviceToHost, s));
+    mark(ctx, L, KPEG_T_D2H);
+    CK(cudaMemcpyAsync(h_meta, d_meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (ctx->guard)
+        TRY(check_guards(ctx, L));
+    ctx->last_lane = 0;
+    ctx->last_g = g3; // kpeg_cuda_read_coefficients: the interleaved tiles
+    if (stats) {
+        stats->width = frame->width;
+        stats->height = frame->height;
+        stats->ncomp = 3;
+        stats->exact_samples += h_meta->exact_samples;
+        stats->kernel_launches += launches;
+        add_times(ctx, L, stats);
+    }
+    return KPEG_OK;
+}
+
 extern "C" int kpeg_cuda_decode_file(kpeg_ctx *ctx, const uint8_t *file, size_t len, uint32_t flags, uint8_t *pixels_out,
                                      size_t cap, kpeg_plan *plan_out, kpeg_stats *stats)
 {
     if (!ctx || !file || !pixels_out)
         return KPEG_ERR_ARG;
-    kpeg_plan plan;
-    size_t off = 0, slen = 0;
-    const int prc = kpeg_parse_jfif(file, len, &plan, &off, &slen);
+    kpeg_plan frame;
+    kpeg_scan scans[KPEG_MAX_SCANS];
+    int nscans = 0;
+    const int prc = kpeg_parse_jfif_scans(file, len, &frame, scans, KPEG_MAX_SCANS, &nscans);
     if (prc != KPEG_OK)
         return fail(ctx, prc, prc == KPEG_ERR_UNSUPPORTED ? "unsupported JPEG coding" : "malformed JFIF container");
-    plan.flags = flags;
+    frame.flags = flags;
     if (plan_out)
-        *plan_out = plan;
-    if ((size_t)plan.width * plan.height * plan.ncomp > cap)
+        *plan_out = frame;
+    if ((size_t)frame.width * frame.height * frame.ncomp > cap)
         return fail(ctx, KPEG_ERR_ARG, "pixel buffer too small");
-    return kpeg_cuda_decode(ctx, &plan, file + off, slen, pixels_out, stats);
+    return kpeg_cuda_decode_scans(ctx, &frame, scans, nscans, file, len, pixels_out, stats);
 }
 
 extern "C" int kpeg_cuda_read_coefficients(kpeg_ctx *ctx, int16_t *out, size_t cap)

@@ -122,8 +122,11 @@ namespace kpeg
         LOG(Logger::Level::INFO) << "Started decoding process...";
         printDetectedSegmentNames();
 
-        std::size_t scanOff = 0, scanLen = 0;
-        const int prc = kpeg_parse_jfif( m_file.data(), m_file.size(), &m_plan, &scanOff, &scanLen );
+        // one interleaved scan (all the reference decodes, Decoder.cpp:461-530) or one scan per component (T.81 A.2.3)
+        kpeg_scan scans[KPEG_MAX_SCANS];
+        int nscans = 0;
+        const int prc = kpeg_parse_jfif_scans( m_file.data(), m_file.size(), &m_plan, scans, KPEG_MAX_SCANS, &nscans );
+        const std::size_t scanOff = nscans ? scans[0].off : 0, scanLen = nscans ? scans[0].len : 0;
         if ( prc == KPEG_ERR_UNSUPPORTED )
         {
             LOG(Logger::Level::INFO) << "Terminated decoding process [NOT-OK].";
@@ -138,7 +141,7 @@ namespace kpeg
 
         m_pixels.assign( (std::size_t)m_plan.width * m_plan.height * m_plan.ncomp, 0 );
         int rc;
-        if ( m_devices.size() > 1 )
+        if ( m_devices.size() > 1 && nscans == 1 )
         {
             // restart-interval tiles over several GPUs, every band into its rows of m_pixels (Image.cpp:51-70 placement)
             rc = kpeg_cuda_decode_tiled( m_devices.data(), (int)m_devices.size(), &m_plan, m_file.data() + scanOff, scanLen,
@@ -158,7 +161,7 @@ namespace kpeg
                 LOG(Logger::Level::ERROR) << "No usable CUDA device: this build has no CPU decode path";
                 return ResultCode::ERROR;
             }
-            rc = kpeg_cuda_decode( ctx, &m_plan, m_file.data() + scanOff, scanLen, m_pixels.data(), &m_stats );
+            rc = kpeg_cuda_decode_scans( ctx, &m_plan, scans, nscans, m_file.data(), m_file.size(), m_pixels.data(), &m_stats );
             if ( rc != KPEG_OK )
                 LOG(Logger::Level::ERROR) << "Decode failed: " << kpeg_cuda_last_error( ctx );
             kpeg_cuda_release( m_device, ctx );

@@ -387,56 +387,63 @@ extern "C" int kpeg_synth_encode(const kpeg_synth_params *p, uint8_t **out, size
         put16(o, 4);
         put16(o, ri);
     }
-    o.push_back(0xFF);
-    o.push_back(0xDA);
-    put16(o, 6 + 2 * nc);
-    o.push_back((uint8_t)nc);
-    for (int c = 0; c < nc; ++c) {
-        o.push_back((uint8_t)(c + 1));
-        o.push_back((uint8_t)(c ? 0x11 : 0x00));
-    }
-    o.push_back(0x00);
-    o.push_back(0x3F);
-    o.push_back(0x00);
-
     const HuffEnc dcL(kDcLumaBits, kDcVals), dcC(kDcChromaBits, kDcVals);
     const HuffEnc acL(kAcLumaBits, kAcLumaVals), acC(kAcChromaBits, kAcChromaVals);
     BitWriter bw(o);
-    int pred[3] = {0, 0, 0};
-    for (long m = 0; m < g.nmcu; ++m) {
-        if (emit_rst && m && (m % ri) == 0) {
-            bw.flush_ones();
-            o.push_back(0xFF);
-            o.push_back((uint8_t)(0xD0 + ((m / ri - 1) & 7)));
-            pred[0] = pred[1] = pred[2] = 0;
+    // one interleaved scan of all components, or -- KPEG_SYNTH_NON_INTERLEAVED -- one scan per component (T.81 A.2.3:
+    // the MCU of a non-interleaved scan is one block, blocks in raster order; the restart interval counts those)
+    const bool split = nc == 3 && (p->flags & KPEG_SYNTH_NON_INTERLEAVED);
+    for (int scan = 0; scan < (split ? nc : 1); ++scan) {
+        const int c0 = split ? scan : 0, c1 = split ? scan + 1 : nc;
+        o.push_back(0xFF);
+        o.push_back(0xDA);
+        put16(o, 6 + 2 * (c1 - c0));
+        o.push_back((uint8_t)(c1 - c0));
+        for (int c = c0; c < c1; ++c) {
+            o.push_back((uint8_t)(c + 1));
+            o.push_back((uint8_t)(c ? 0x11 : 0x00));
         }
-        for (int c = 0; c < nc; ++c) {
-            const int16_t *zz = &coef[((size_t)m * nc + c) * 64];
-            const HuffEnc &hd = c ? dcC : dcL, &ha = c ? acC : acL;
-            int diff = zz[0] - pred[c];
-            pred[c] = zz[0];
-            int cat = category(diff);
-            bw.put(hd.code[cat], hd.len[cat]);
-            put_value(bw, diff, cat);
-            int run = 0;
-            for (int i = 1; i < 64; ++i) {
-                if (zz[i] == 0) {
-                    ++run;
-                    continue;
-                }
-                while (run > 15) {
-                    bw.put(ha.code[0xF0], ha.len[0xF0]);
-                    run -= 16;
-                }
-                cat = category(zz[i]);
-                int sym = (run << 4) | cat;
-                bw.put(ha.code[sym], ha.len[sym]);
-                put_value(bw, zz[i], cat);
-                run = 0;
+        o.push_back(0x00);
+        o.push_back(0x3F);
+        o.push_back(0x00);
+        int pred[3] = {0, 0, 0};
+        for (long m = 0; m < g.nmcu; ++m) {
+            if (emit_rst && m && (m % ri) == 0) {
+                bw.flush_ones();
+                o.push_back(0xFF);
+                o.push_back((uint8_t)(0xD0 + ((m / ri - 1) & 7)));
+                pred[0] = pred[1] = pred[2] = 0;
             }
-            if (run)
-                bw.put(ha.code[0x00], ha.len[0x00]);
+            for (int c = c0; c < c1; ++c) {
+                const int16_t *zz = &coef[((size_t)m * nc + c) * 64];
+                const HuffEnc &hd = c ? dcC : dcL, &ha = c ? acC : acL;
+                int diff = zz[0] - pred[c];
+                pred[c] = zz[0];
+                int cat = category(diff);
+                bw.put(hd.code[cat], hd.len[cat]);
+                put_value(bw, diff, cat);
+                int run = 0;
+                for (int i = 1; i < 64; ++i) {
+                    if (zz[i] == 0) {
+                        ++run;
+                        continue;
+                    }
+                    while (run > 15) {
+                        bw.put(ha.code[0xF0], ha.len[0xF0]);
+                        run -= 16;
+                    }
+                    cat = category(zz[i]);
+                    int sym = (run << 4) | cat;
+                    bw.put(ha.code[sym], ha.len[sym]);
+                    put_value(bw, zz[i], cat);
+                    run = 0;
+                }
+                if (run)
+                    bw.put(ha.code[0x00], ha.len[0x00]);
+            }
         }
+        if (scan + 1 < (split ? nc : 1))
+            bw.flush_ones(); // the next SOS marker starts on a byte boundary
     }
     bw.flush_ones();
     o.push_back(0xFF);

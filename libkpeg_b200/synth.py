@@ -14,6 +14,7 @@ PKG = Path(__file__).resolve().parent
 EMIT_RESTART = 1
 GRAY_CONTENT = 2
 QUIRK_FREE = 4
+NON_INTERLEAVED = 8  # three-component files: one scan per component
 
 
 class _Params(C.Structure):

@@ -147,7 +147,18 @@ typedef struct {
     uint16_t qt[4][64];
     int qt_present[4];
     huff_t ht[2][4];
-    size_t scan_off, scan_len;
+    size_t scan_off, scan_len; /* the first scan (all of it for the single interleaved scan the reference decodes) */
+    /* Every scan of the frame, each with the tables and restart interval in force at its SOS (T.81 B.2.3: tables may
+     * be redefined between scans).  The reference reads Ns = 1..4 (Decoder.cpp:461-530) but then decodes the first scan
+     * as if it were interleaved; here a frame is either ONE interleaved scan of all components or one scan PER
+     * component (T.81 A.2.3: the MCU of a non-interleaved scan is one block, blocks in raster order). */
+    int nscans;
+    struct scan_t {
+        int ns, comp[3], td[3], ta[3];
+        int restart_interval;
+        huff_t ht[2][4];
+        size_t off, len;
+    } scans[3];
 } plan_t;
 
 static int rd16(const uint8_t *p) { return (p[0] << 8) | p[1]; }
@@ -255,20 +266,37 @@ static int parse_container(const uint8_t *f, size_t n, plan_t *pl)
             if (!have_sof || plen < 1)
                 return KPO_ERR_FORMAT;
             int ns = p[0];
-            if (ns != pl->ncomp || plen < 1 + 2 * ns + 3)
-                return KPO_ERR_UNSUPPORTED;
+            if ((ns != pl->ncomp && ns != 1) || plen < 1 + 2 * ns + 3 || pl->nscans >= 3)
+                return KPO_ERR_UNSUPPORTED; /* two-component scans, more scans than components */
+            struct scan_t *sc = &pl->scans[pl->nscans];
+            sc->ns = ns;
             for (int s = 0; s < ns; ++s) {
                 int cid = p[1 + 2 * s], c;
                 for (c = 0; c < pl->ncomp; ++c)
                     if (pl->comp_id[c] == cid)
                         break;
-                if (c != s)
-                    return KPO_ERR_UNSUPPORTED; /* scan order must equal frame order */
-                pl->comp_td[c] = p[2 + 2 * s] >> 4;
-                pl->comp_ta[c] = p[2 + 2 * s] & 15;
-                if (pl->comp_td[c] > 3 || pl->comp_ta[c] > 3)
+                if (c == pl->ncomp)
                     return KPO_ERR_FORMAT;
+                if (ns > 1 && c != s)
+                    return KPO_ERR_UNSUPPORTED; /* interleaved: scan order must equal frame order */
+                for (int k = 0; k < pl->nscans; ++k)
+                    for (int j = 0; j < pl->scans[k].ns; ++j)
+                        if (pl->scans[k].comp[j] == c)
+                            return KPO_ERR_UNSUPPORTED; /* a component coded twice (not baseline sequential) */
+                sc->comp[s] = c;
+                sc->td[s] = p[2 + 2 * s] >> 4;
+                sc->ta[s] = p[2 + 2 * s] & 15;
+                if (sc->td[s] > 3 || sc->ta[s] > 3)
+                    return KPO_ERR_FORMAT;
+                if (!pl->qt_present[pl->comp_tq[c]])
+                    return KPO_ERR_FORMAT;
+                if (!pl->ht[0][sc->td[s]].present || !pl->ht[1][sc->ta[s]].present)
+                    return KPO_ERR_FORMAT;
+                pl->comp_td[c] = sc->td[s];
+                pl->comp_ta[c] = sc->ta[s];
             }
+            sc->restart_interval = pl->restart_interval;
+            memcpy(sc->ht, pl->ht, sizeof sc->ht);
             /* entropy-coded segment: everything up to the first marker that is neither a
              * stuffed FF00, an RSTn nor an FF fill byte.  scanImageData (Decoder.cpp:532-577)
              * stops only at FFD9; identical on well-formed single-scan files. */
@@ -286,15 +314,22 @@ static int parse_container(const uint8_t *f, size_t n, plan_t *pl)
             }
             if (e + 1 >= n)
                 e = n; /* truncated file: take what is there */
-            pl->scan_off = s0;
-            pl->scan_len = e - s0;
-            for (int c = 0; c < pl->ncomp; ++c) {
-                if (!pl->qt_present[pl->comp_tq[c]])
-                    return KPO_ERR_FORMAT;
-                if (!pl->ht[0][pl->comp_td[c]].present || !pl->ht[1][pl->comp_ta[c]].present)
-                    return KPO_ERR_FORMAT;
+            sc->off = s0;
+            sc->len = e - s0;
+            if (pl->nscans == 0) {
+                pl->scan_off = s0;
+                pl->scan_len = e - s0;
             }
-            return KPO_OK;
+            ++pl->nscans;
+            int covered = 0;
+            for (int k = 0; k < pl->nscans; ++k)
+                covered += pl->scans[k].ns;
+            if (covered == pl->ncomp)
+                return KPO_OK; /* every component has its scan: whatever follows (EOI, trailing bytes) is not looked at */
+            if (e >= n)
+                return KPO_ERR_FORMAT; /* the file ends before the remaining components' scans */
+            i = e; /* on the marker that ended the segment */
+            continue;
         }
         default: /* APPn, COM, DNL...: skipped by length (the reference FATALs on most, F7) */
             break;
@@ -355,15 +390,15 @@ static int huff_decode(bitrd_t *b, const huff_t *h)
     return -1; /* the reference would keep appending bits forever (Decoder.cpp:706-748) */
 }
 
-static int decode_coefficients(const plan_t *pl, const uint8_t *scan, size_t slen, uint32_t flags,
+static int decode_coefficients(const plan_t *pl, const struct scan_t *sc, const uint8_t *scan, size_t slen, uint32_t flags,
                                int16_t *coef)
 {
     const int nc = pl->ncomp;
     const int mx = (pl->width + 7) / 8, my = (pl->height + 7) / 8;
-    const long nmcu = (long)mx * my;
+    const long nmcu = (long)mx * my; /* 1x1 sampling: a non-interleaved scan has as many MCUs (blocks) as an interleaved one */
     bitrd_t br = {scan, slen, 0, 0, 0, 0};
     int pred[3] = {0, 0, 0}; /* MCU.cpp:53 DCDiff[]; per-image here */
-    const int ri = pl->restart_interval;
+    const int ri = sc->restart_interval;
 
     for (long m = 0; m < nmcu; ++m) {
         if (ri && m && (m % ri) == 0) {
@@ -377,8 +412,9 @@ static int decode_coefficients(const plan_t *pl, const uint8_t *scan, size_t sle
             br.pos += 2;
             pred[0] = pred[1] = pred[2] = 0;
         }
-        for (int c = 0; c < nc; ++c) {
-            const huff_t *hd = &pl->ht[0][pl->comp_td[c]], *ha = &pl->ht[1][pl->comp_ta[c]];
+        for (int si = 0; si < sc->ns; ++si) {
+            const int c = sc->comp[si];
+            const huff_t *hd = &sc->ht[0][sc->td[si]], *ha = &sc->ht[1][sc->ta[si]];
             int16_t *zz = coef + ((size_t)m * nc + c) * 64;
             memset(zz, 0, 64 * sizeof(int16_t));
 
@@ -586,7 +622,11 @@ int kpo_decode(const uint8_t *file, size_t len, uint32_t flags, int want_pixels,
         free(pl);
         return KPO_ERR_NOMEM;
     }
-    rc = decode_coefficients(pl, file + pl->scan_off, pl->scan_len, flags, img->coef);
+    img->scan_bytes = 0;
+    for (int k = 0; k < pl->nscans && rc == KPO_OK; ++k) {
+        img->scan_bytes += (int64_t)pl->scans[k].len;
+        rc = decode_coefficients(pl, &pl->scans[k], file + pl->scans[k].off, pl->scans[k].len, flags, img->coef);
+    }
     if (rc == KPO_OK && want_pixels) {
         img->pixels = (uint8_t *)malloc((size_t)pl->width * pl->height * pl->ncomp);
         if (!img->pixels)

@@ -214,7 +214,8 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
             st2 |= (out.cz & CZ_BAD_CODE) ? ST_BAD_CODE : 0u;
             st2 |= (out.cz & CZ_SLOT_OVERFLOW) ? ST_SLOT_OVERFLOW : 0u;
             st2 |= (out.cz & CZ_SEG_MISMATCH) ? ST_SEG_MISMATCH : 0u;
-            if (out.seg >= 0 && (begin & ~63u) + (out.cz >> CZ_POS_SHIFT) != fin && !((uint32_t)out.seg >= g.nseg && fin >= total_slots))
+            const uint32_t reached = (begin & ~63u) + (out.cz >> CZ_POS_SHIFT);
+            if (out.seg >= 0 && reached != fin && !((uint32_t)out.seg >= g.nseg && fin >= total_slots && reached >= total_slots))
                 st2 |= ST_SEG_MISMATCH;
             if ((fin & 63u) != (out.cz & 63u) || ((fin >> 6) % g.ncomp) != ((out.cz >> 8) & 3u))
                 st2 |= ST_EXIT_MISMATCH;

@@ -98,9 +98,12 @@ def _seg(marker, payload):
 
 
 def write_jpeg(coef, width, height, ncomp, qts, tq, dc_tables, ac_tables, td, ta, comp_ids=(1, 2, 3),
-               interleaved=True, extra_segments=b""):
+               interleaved=True, extra_segments=b"", scan_order=None, redefine=None):
     """coef [blocks][64] (MCU-interleaved, zig-zag, DC integrated).  qts: {id: 64 values (zig-zag)};
-    dc_tables / ac_tables: {id: (counts[16], symbols)}; tq / td / ta: table id per component."""
+    dc_tables / ac_tables: {id: (counts[16], symbols)}; tq / td / ta: table id per component.
+    Non-interleaved files only: scan_order = the components in the order their scans are written (default 0, 1, 2);
+    redefine = {component: (dc_tables, ac_tables, td, ta)}: DHT segments written right before that component's scan
+    (they REPLACE tables of the same id, T.81 B.2.4.2) and the selectors that scan uses."""
     coef = np.asarray(coef, dtype=np.int16).reshape(-1, 64)
     mx, my = (width + 7) // 8, (height + 7) // 8
     assert coef.shape[0] == mx * my * ncomp
@@ -119,8 +122,18 @@ def write_jpeg(coef, width, height, ncomp, qts, tq, dc_tables, ac_tables, td, ta
             out += _seg(0xC4, bytes([(cls << 4) | tid]) + bytes(int(x) for x in counts) + bytes(int(s) for s in symbols[:n]))
     dc_codes = [canonical_codes(*dc_tables[td[c]]) for c in range(ncomp)]
     ac_codes = [canonical_codes(*ac_tables[ta[c]]) for c in range(ncomp)]
-    scans = [list(range(ncomp))] if interleaved else [[c] for c in range(ncomp)]
+    scans = [list(range(ncomp))] if interleaved else [[c] for c in (scan_order or range(ncomp))]
+    td, ta = list(td), list(ta)
     for comps in scans:
+        if redefine and not interleaved and comps[0] in redefine:
+            c = comps[0]
+            new_dc, new_ac, td[c], ta[c] = redefine[c]
+            for cls, tabs in ((0, new_dc), (1, new_ac)):
+                for tid, (counts, symbols) in tabs.items():
+                    n = int(sum(counts))
+                    out += _seg(0xC4, bytes([(cls << 4) | tid]) + bytes(int(x) for x in counts) + bytes(int(s) for s in symbols[:n]))
+            dc_codes[c] = canonical_codes(*new_dc[td[c]]) if td[c] in new_dc else canonical_codes(*dc_tables[td[c]])
+            ac_codes[c] = canonical_codes(*new_ac[ta[c]]) if ta[c] in new_ac else canonical_codes(*ac_tables[ta[c]])
         sos = bytes([len(comps)])
         for c in comps:
             sos += bytes([comp_ids[c], (td[c] << 4) | ta[c]])

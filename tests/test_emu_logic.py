@@ -79,6 +79,7 @@ def test_corrupt_stream_flags_an_error(lena_jpg):
     plan, off, n = K.parse_jfif(buf)
     e = H.emu_decode(buf[: off + n // 2].tobytes() + b"\xff\xd9", want_pixels=False)
     assert e["status"] != 0  # truncated: the stream ends before the last MCU
+    assert e["records_ok"], "the record flavour (what the product runs) must reject a truncated stream as well"
     rng = np.random.default_rng(3)
     bad = buf.copy()
     idx = rng.integers(off + 100, off + n - 100, size=200)

@@ -13,6 +13,7 @@ import pytest
 
 import helpers as H
 import libkpeg_b200 as K
+from libkpeg_b200 import api
 from libkpeg_b200.synth import EMIT_RESTART, GRAY_CONTENT, QUIRK_FREE, SynthParams, synth_encode
 
 pytestmark = pytest.mark.gpu
@@ -537,3 +538,81 @@ def test_relay_barrier_timeout_falls_back_to_host_rounds(monkeypatch, lena_jpg):
             assert np.array_equal(o, H.oracle_decode(j.tobytes())["pixels"])
     finally:
         dec.close()
+
+
+# ---- frames coded one scan per component (T.81 A.2.3) ------------------------------------------------
+def _scan_twins(w, h, ri=0, q=80, seed=5, quirk_free=True):
+    from libkpeg_b200.synth import NON_INTERLEAVED
+    fl = (QUIRK_FREE if quirk_free else 0) | (EMIT_RESTART if ri else 0)
+    base = dict(width=w, height=h, quality=q, restart_interval=ri, seed=seed)
+    return (synth_encode(SynthParams(**base, flags=fl)).tobytes(), synth_encode(SynthParams(**base, flags=fl | NON_INTERLEAVED)).tobytes())
+
+
+@pytest.mark.parametrize("w,h,ri,q", [(64, 48, 0, 90), (57, 33, 0, 50), (120, 80, 5, 75), (33, 17, 3, 20), (640, 424, 80, 95), (1, 1, 0, 50)])
+def test_one_scan_per_component_files(decoder, w, h, ri, q):
+    """The reference reads the SOS header of a non-interleaved scan (Decoder.cpp:461-530) and then decodes it as if it
+    were interleaved; the T.81-correct decode (A.2.3) is pinned through twin streams: the same quantised coefficients
+    written as ONE interleaved scan -- which the reference decodes and the oracle is pinned on -- and as three scans must
+    give the same coefficients and the same pixels, in both parity modes."""
+    inter, split = _scan_twins(w, h, ri, q)
+    for parity in (True, False):
+        got, ref = check_against_oracle(decoder, split, parity=parity)
+        assert decoder.last_stats.kernel_launches >= 3 * 9  # three entropy-decode sequences
+        twin = decoder.decode_file(inter, flags=K.KPEG_FLAG_REF_PARITY if parity else 0)
+        assert np.array_equal(got, twin)
+
+
+def test_one_scan_per_component_with_the_dc_difference_quirk(decoder):
+    """Streams that are NOT quirk-free: blocks whose DC difference is 0 lose their AC terms in parity mode (MCU.cpp:97-104).
+    The DC difference of a block is the same in both scan orders, so the twins still agree."""
+    inter, split = _scan_twins(200, 120, ri=0, q=30, seed=9, quirk_free=False)
+    a, _ = check_against_oracle(decoder, split, parity=True)
+    b, _ = check_against_oracle(decoder, split, parity=False)
+    assert not np.array_equal(a, b)  # the quirk does bite on this stream
+    assert np.array_equal(a, decoder.decode_file(inter))
+
+
+def test_scans_in_any_order_with_tables_redefined_between_them(decoder):
+    """Scans in the order Cr, Y, Cb; each component with a quantiser and Huffman tables of its own; before the Cb scan two
+    DHT segments REPLACE the tables Y used (same ids) and the Cb scan selects those ids -- a decoder that keeps only the
+    last definition of a table id, or decodes the scans in frame order with the final tables, gets Y or Cb wrong."""
+    import jpeg_writer as JW
+    base = synth_encode(SynthParams(88, 56, quality=70, seed=31)).tobytes()
+    plan, _, _ = K.parse_jfif(base)
+    ref0 = H.oracle_decode(base, parity=False, want_pixels=False)
+    t = JW.tables_of(plan)
+    dc_l, ac_l, dc_c, ac_c = t[(0, 0)], t[(1, 0)], t[(0, 1)], t[(1, 1)]
+    qy, qc = [int(x) for x in plan.qt[0]], [int(x) for x in plan.qt[1]]
+    qts = {0: qy, 1: qc, 2: [min(255, x + 2) for x in qc]}
+    jpg = JW.write_jpeg(ref0["coef"], plan.width, plan.height, 3, qts, tq=(0, 1, 2),
+                        dc_tables={0: dc_l, 1: dc_c}, ac_tables={0: ac_l, 1: ac_c}, td=(0, 1, 1), ta=(0, 1, 1),
+                        comp_ids=(1, 2, 3), interleaved=False, scan_order=(2, 0, 1),
+                        redefine={1: ({0: JW.permuted_table(*dc_c, seed=4)}, {0: JW.permuted_table(*ac_c, seed=5)}, 0, 0)})
+    frame, scans = api.parse_jfif_scans(jpg)
+    assert [sc.comp[0] for sc in scans] == [2, 0, 1]
+    for parity in (True, False):
+        check_against_oracle(decoder, jpg, parity=parity)
+
+
+def test_corrupt_scan_of_a_multi_scan_file_is_an_error(decoder):
+    _, split = _scan_twins(256, 256, ri=0, q=85)
+    frame, scans = api.parse_jfif_scans(split)
+    mid = scans[1].off + scans[1].len // 2
+    bad = split[:mid] + split[scans[1].off + scans[1].len:]  # the second half of the Cb scan is missing
+    with pytest.raises(RuntimeError):
+        H.oracle_decode(bad)
+    with pytest.raises(K.KpegError) as e:
+        decoder.decode_file(bad)
+    assert e.value.code == api.KPEG_ERR_STREAM
+    check_against_oracle(decoder, split)  # the context is fine afterwards
+
+
+def test_cli_decodes_one_scan_per_component(tmp_path):
+    inter, split = _scan_twins(136, 72, q=85, seed=77)
+    (tmp_path / "a.jpg").write_bytes(inter)
+    (tmp_path / "b.jpg").write_bytes(split)
+    exe = str(ROOT / "libkpeg_b200" / "lib" / "kpeg")
+    for name in ("a.jpg", "b.jpg"):
+        r = subprocess.run([exe, "--quiet", name], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert (tmp_path / "a.ppm").read_bytes() == (tmp_path / "b.ppm").read_bytes()

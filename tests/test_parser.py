@@ -125,3 +125,66 @@ def test_distinct_tables_per_component_cpu():
         e = H.emu_decode(jpg, sub_bits=sb)
         assert e["status"] == 0 and e["records_ok"]
         assert np.array_equal(o["coef"], e["coef"]) and np.array_equal(o["pixels"], e["pixels"])
+
+
+# ---- frames coded one scan per component (T.81 A.2.3) ------------------------------------------------
+def _noninterleaved(w=72, h=40, ri=0, q=80, seed=5, flags=0):
+    from libkpeg_b200.synth import EMIT_RESTART, NON_INTERLEAVED, QUIRK_FREE, SynthParams, synth_encode
+    fl = QUIRK_FREE | flags | (EMIT_RESTART if ri else 0)
+    base = dict(width=w, height=h, quality=q, restart_interval=ri, seed=seed)
+    return (synth_encode(SynthParams(**base, flags=fl)).tobytes(),
+            synth_encode(SynthParams(**base, flags=fl | NON_INTERLEAVED)).tobytes())
+
+
+def test_one_scan_per_component_is_parsed_scan_by_scan():
+    inter, split = _noninterleaved(ri=4)
+    with pytest.raises(K.KpegError) as e:
+        K.parse_jfif(split)  # the single-scan entry point does not take it
+    assert e.value.code == api.KPEG_ERR_UNSUPPORTED
+    frame, scans = api.parse_jfif_scans(split)
+    assert (frame.width, frame.height, frame.ncomp, len(scans)) == (72, 40, 3, 3)
+    fi, si = api.parse_jfif_scans(inter)
+    assert len(si) == 1 and si[0].plan.ncomp == 3 and bytes(si[0].plan) == bytes(fi)
+    for k, sc in enumerate(scans):
+        assert sc.plan.ncomp == 1 and sc.comp[0] == k and sc.plan.restart_interval == 4
+        assert (sc.plan.width, sc.plan.height) == (72, 40)
+        assert sc.plan.comp_td[0] == sc.plan.comp_ta[0] == (0 if k == 0 else 1)
+        assert split[sc.off - 10:sc.off - 8] == b"\xff\xda" and sc.len > 0
+        # the quantiser of component k sits in slot k of the frame plan
+        src = fi.qt[0 if k == 0 else 1]
+        assert list(frame.qt[k]) == list(src) and frame.comp_tq[k] == k
+
+
+def test_one_scan_per_component_equals_the_interleaved_twin_in_the_oracle():
+    """Twin streams: the same quantised coefficients as one interleaved scan (which the reference decodes and the oracle
+    is pinned on) and as three scans -- the oracle must give the same coefficients and pixels for both."""
+    for kw in (dict(), dict(w=57, h=33, q=40), dict(w=120, h=80, ri=5, q=75), dict(w=33, h=17, ri=3, q=20)):
+        inter, split = _noninterleaved(**kw)
+        a, b = H.oracle_decode(inter, parity=True), H.oracle_decode(split, parity=True)
+        assert np.array_equal(a["coef"], b["coef"]) and np.array_equal(a["pixels"], b["pixels"])
+    pil = np.asarray(PIL.open(io.BytesIO(split)).convert("RGB")).astype(int)  # an independent decoder accepts the file
+    assert np.abs(pil - b["pixels"].astype(int)).max() <= 4
+
+
+def test_multi_scan_files_the_path_does_not_take():
+    _, split = _noninterleaved()
+    frame, scans = api.parse_jfif_scans(split)
+    # the file ends after the second scan
+    cut = split[:scans[2].off - 10] + b"\xff\xd9"
+    with pytest.raises(K.KpegError) as e:
+        api.parse_jfif_scans(cut)
+    assert e.value.code == api.KPEG_ERR_FORMAT
+    # the second scan codes component 1 again ... (component id lives 5 bytes into the SOS payload)
+    twice = bytearray(split)
+    twice[scans[2].off - 5] = 2
+    with pytest.raises(K.KpegError) as e:
+        api.parse_jfif_scans(bytes(twice))
+    assert e.value.code == api.KPEG_ERR_UNSUPPORTED
+    # a two-component scan
+    import jpeg_writer as JW
+    two = bytearray(split)
+    sos = scans[0].off - 10
+    two[sos:scans[0].off] = JW._seg(0xDA, bytes([2, 1, 0x00, 2, 0x11, 0, 63, 0]))
+    with pytest.raises(K.KpegError) as e:
+        api.parse_jfif_scans(bytes(two))
+    assert e.value.code == api.KPEG_ERR_UNSUPPORTED
