@@ -225,6 +225,16 @@ int kpeg_cuda_decode_scans(kpeg_ctx *ctx, const kpeg_plan *frame, const kpeg_sca
 int kpeg_cuda_decode_file(kpeg_ctx *ctx, const uint8_t *file, size_t len, uint32_t flags, uint8_t *pixels_out,
                           size_t cap, kpeg_plan *plan_out, kpeg_stats *stats);
 
+/* n whole files of ANY mix of dimensions, tables and codings (what "decode this directory" needs; the reference
+ * constructs one JPEGDecoder per file, main.cpp:54-79).  Parsed on the host; files whose plans are identical are decoded
+ * together as one batch (kpeg_cuda_submit_batch: one kernel sequence per group), files coded one scan per component go
+ * through kpeg_cuda_decode_scans.  pixels_out[i] must hold caps[i] >= width*height*ncomp bytes of file i (query with
+ * kpeg_parse_jfif_scans).  results[i] (may be NULL) receives file i's own return code, plans_out[i] (may be NULL) its
+ * frame plan; a bad file does not stop the others.  Returns KPEG_OK when every file decoded, else the first failure
+ * (text: kpeg_cuda_last_error).  Host buffers (ideally pinned) in and out; synchronous. */
+int kpeg_cuda_decode_files(kpeg_ctx *ctx, int n, const uint8_t *const *files, const size_t *lens, uint32_t flags,
+                           uint8_t *const *pixels_out, const size_t *caps, kpeg_plan *plans_out, int *results, kpeg_stats *stats);
+
 /* Parity hook: the quantised coefficients of the LAST decode on this context, as the reference
  * holds them transiently inside MCU::constructMCU (MCU.cpp:93-108): [block][64] int16, blocks
  * MCU-interleaved (Y,Cb,Cr per MCU), zig-zag order, DC prediction already integrated.

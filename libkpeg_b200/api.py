@@ -84,6 +84,8 @@ SYMBOLS = {
     "kpeg_parse_jfif": (C.c_int, [_vp, C.c_size_t, C.POINTER(Plan), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "kpeg_parse_jfif_scans": (C.c_int, [_vp, C.c_size_t, C.POINTER(Plan), C.POINTER(Scan), C.c_int, C.POINTER(C.c_int)]),
     "kpeg_cuda_decode_scans": (C.c_int, [_vp, C.POINTER(Plan), C.POINTER(Scan), C.c_int, _vp, C.c_size_t, _vp, C.POINTER(Stats)]),
+    "kpeg_cuda_decode_files": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_size_t), C.c_uint32, C.POINTER(_vp), C.POINTER(C.c_size_t),
+                                         C.POINTER(Plan), C.POINTER(C.c_int), C.POINTER(Stats)]),
     "kpeg_cuda_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "kpeg_cuda_destroy": (None, [_vp]),
     "kpeg_cuda_last_error": (C.c_char_p, [_vp]),
@@ -288,6 +290,29 @@ class Decoder:
                                               C.byref(self.last_stats))
         self._check(rc, "kpeg_cuda_decode_scans")
         return out.reshape(shape)
+
+    def decode_files(self, files: list, flags: int = KPEG_FLAG_REF_PARITY):
+        """kpeg_cuda_decode_files: any mix of files in one call -> (list of images, or None where a file failed; list of
+        per-file return codes).  Files with identical plans are decoded as one batch."""
+        bufs = [np.ascontiguousarray(np.frombuffer(f, dtype=np.uint8) if not isinstance(f, np.ndarray) else f) for f in files]
+        n = len(bufs)
+        outs, shapes = [], []
+        for b in bufs:
+            try:
+                frame, _ = parse_jfif_scans(b)
+                shapes.append((frame.height, frame.width, 3) if frame.ncomp == 3 else (frame.height, frame.width))
+                outs.append(np.empty(int(frame.height) * frame.width * frame.ncomp, dtype=np.uint8))
+            except KpegError:
+                shapes.append(None)
+                outs.append(np.empty(1, dtype=np.uint8))
+        fp = (_vp * n)(*[_ptr(b) for b in bufs])
+        fl = (C.c_size_t * n)(*[b.size for b in bufs])
+        op = (_vp * n)(*[_ptr(o) for o in outs])
+        oc = (C.c_size_t * n)(*[o.size for o in outs])
+        res = (C.c_int * n)()
+        self._lib.kpeg_cuda_decode_files(self._h, n, fp, fl, flags, op, oc, None, res, C.byref(self.last_stats))
+        codes = [int(r) for r in res]
+        return [o.reshape(sh) if (c == KPEG_OK and sh is not None) else None for o, sh, c in zip(outs, shapes, codes)], codes
 
     def decode_scan(self, plan: Plan, scan: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         scan = np.ascontiguousarray(scan, dtype=np.uint8)

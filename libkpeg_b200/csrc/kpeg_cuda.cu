@@ -1539,6 +1539,156 @@ extern "C" int kpeg_cuda_decode_file(kpeg_ctx *ctx, const uint8_t *file, size_t 
     return kpeg_cuda_decode_scans(ctx, &frame, scans, nscans, file, len, pixels_out, stats);
 }
 
+// Any mix of files.  Files with identical plans (dimensions, tables, restart interval) travel together as ONE batch --
+// one kernel sequence for the group -- and the groups overlap on the lanes; only when a group fails are its files
+// decoded one by one, to find out which of them it was.
+extern "C" int kpeg_cuda_decode_files(kpeg_ctx *ctx, int n, const uint8_t *const *files, const size_t *lens, uint32_t flags,
+                                      uint8_t *const *pixels_out, const size_t *caps, kpeg_plan *plans_out, int *results,
+                                      kpeg_stats *stats)
+{
+    if (!ctx || n <= 0 || !files || !lens || !pixels_out || !caps)
+        return KPEG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    zero_stats(stats);
+    struct File {
+        kpeg_plan frame;
+        kpeg_scan scans[KPEG_MAX_SCANS];
+        int nscans = 0, rc = KPEG_OK, group = -1;
+    };
+    struct Group {
+        kpeg_plan plan;
+        std::vector<int> members;
+        std::vector<const uint8_t *> scans;
+        std::vector<size_t> lens;
+        std::vector<uint8_t *> outs;
+    };
+    std::vector<File> fl((size_t)n);
+    std::vector<Group> groups;
+    std::string first_err;
+    int first_rc = KPEG_OK;
+    auto note = [&](int i, int rc, const char *what) {
+        fl[(size_t)i].rc = rc;
+        if (rc != KPEG_OK && first_rc == KPEG_OK) {
+            first_rc = rc;
+            first_err = std::string("file ") + std::to_string(i) + ": " + what;
+        }
+    };
+    for (int i = 0; i < n; ++i) {
+        File &f = fl[(size_t)i];
+        if (!files[i] || !pixels_out[i]) {
+            note(i, KPEG_ERR_ARG, "null pointer");
+            continue;
+        }
+        const int prc = kpeg_parse_jfif_scans(files[i], lens[i], &f.frame, f.scans, KPEG_MAX_SCANS, &f.nscans);
+        if (prc != KPEG_OK) {
+            note(i, prc, prc == KPEG_ERR_UNSUPPORTED ? "unsupported JPEG coding" : "malformed JFIF container");
+            continue;
+        }
+        f.frame.flags = flags;
+        if (plans_out)
+            plans_out[i] = f.frame;
+        if ((size_t)f.frame.width * f.frame.height * f.frame.ncomp > caps[i]) {
+            note(i, KPEG_ERR_ARG, "pixel buffer too small");
+            continue;
+        }
+        if (f.nscans != 1)
+            continue; // one scan per component: decoded on its own below
+        kpeg_plan pl = f.scans[0].plan;
+        pl.flags = flags;
+        size_t g = 0;
+        while (g < groups.size() && memcmp(&groups[g].plan, &pl, sizeof pl) != 0)
+            ++g;
+        if (g == groups.size()) {
+            groups.emplace_back();
+            groups.back().plan = pl;
+        }
+        f.group = (int)g;
+        groups[g].members.push_back(i);
+        groups[g].scans.push_back(files[i] + f.scans[0].off);
+        groups[g].lens.push_back(f.scans[0].len);
+        groups[g].outs.push_back(pixels_out[i]);
+    }
+    // earlier deferred submissions keep their own outcome for the caller's kpeg_cuda_wait
+    for (int i = 0; i < NLANES; ++i)
+        if (ctx->lane[i].job.active)
+            finish_deferred(ctx, i);
+    const int saved_rc = ctx->deferred_rc;
+    const std::string saved_err = ctx->deferred_err;
+    const kpeg_stats saved_stats = ctx->deferred_stats;
+    auto reset_deferred = [&]() {
+        ctx->deferred_rc = KPEG_OK;
+        ctx->deferred_err.clear();
+        memset(&ctx->deferred_stats, 0, sizeof ctx->deferred_stats);
+    };
+    auto add_stats = [&](const kpeg_stats &p) {
+        if (!stats)
+            return;
+        stats->scan_bytes += p.scan_bytes;
+        stats->unstuffed_bytes += p.unstuffed_bytes;
+        stats->segments += p.segments;
+        stats->subsequences += p.subsequences;
+        stats->sync_rounds = std::max(stats->sync_rounds, p.sync_rounds);
+        stats->exact_samples += p.exact_samples;
+        stats->kernel_launches += p.kernel_launches;
+    };
+    // every group is submitted, then ONE wait: the groups overlap on the lanes like consecutive batches do
+    reset_deferred();
+    int all_rc = KPEG_OK;
+    for (Group &g : groups) {
+        const int rc = kpeg_cuda_submit_batch(ctx, &g.plan, (int)g.members.size(), g.scans.data(), g.lens.data(), g.outs.data());
+        if (all_rc == KPEG_OK)
+            all_rc = rc;
+    }
+    {
+        kpeg_stats part;
+        const int wrc = kpeg_cuda_wait(ctx, &part);
+        if (all_rc == KPEG_OK)
+            all_rc = wrc;
+        add_stats(part);
+    }
+    if (all_rc != KPEG_OK) {
+        // something failed, and a deferred failure does not say where: group by group, then file by file
+        for (Group &g : groups) {
+            reset_deferred();
+            int rc = kpeg_cuda_submit_batch(ctx, &g.plan, (int)g.members.size(), g.scans.data(), g.lens.data(), g.outs.data());
+            kpeg_stats part;
+            const int wrc = kpeg_cuda_wait(ctx, &part);
+            if (rc == KPEG_OK)
+                rc = wrc;
+            if (rc == KPEG_OK)
+                continue;
+            if (g.members.size() == 1) {
+                note(g.members[0], rc, ctx->err.c_str());
+                continue;
+            }
+            for (size_t k = 0; k < g.members.size(); ++k) {
+                const int one = kpeg_cuda_decode(ctx, &g.plan, g.scans[k], g.lens[k], g.outs[k], &part);
+                if (one != KPEG_OK)
+                    note(g.members[k], one, ctx->err.c_str());
+            }
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        File &f = fl[(size_t)i];
+        if (f.rc != KPEG_OK || f.nscans == 1)
+            continue;
+        kpeg_stats part;
+        const int rc = kpeg_cuda_decode_scans(ctx, &f.frame, f.scans, f.nscans, files[i], lens[i], pixels_out[i], &part);
+        add_stats(part);
+        if (rc != KPEG_OK)
+            note(i, rc, ctx->err.c_str());
+    }
+    ctx->deferred_rc = saved_rc;
+    ctx->deferred_err = saved_err;
+    ctx->deferred_stats = saved_stats;
+    if (results)
+        for (int i = 0; i < n; ++i)
+            results[i] = fl[(size_t)i].rc;
+    if (first_rc != KPEG_OK)
+        ctx->err = first_err;
+    return first_rc;
+}
+
 extern "C" int kpeg_cuda_read_coefficients(kpeg_ctx *ctx, int16_t *out, size_t cap)
 {
     if (!ctx || !out)

@@ -207,3 +207,33 @@ def test_large_restart_image_goes_through_the_lanes_in_bands(monkeypatch):
     finally:
         banded.close()
         whole.close()
+
+
+def test_decode_files_takes_any_mix_of_files(decoder):
+    """kpeg_cuda_decode_files: files of different sizes, qualities (tables), component counts and codings in ONE call;
+    files with identical plans share a batch; a truncated file and a non-JPEG get their own error codes and do not stop
+    the others.  Every decoded image equals the oracle's."""
+    from libkpeg_b200.synth import NON_INTERLEAVED
+    lena = (H.ROOT / "tests" / "golden" / "lena.jpg").read_bytes() if hasattr(H, "ROOT") else None
+    files = []
+    for seed in (1, 2, 3):  # one plan, three files
+        files.append(synth_encode(SynthParams(64, 48, quality=80, seed=seed)).tobytes())
+    files.append(synth_encode(SynthParams(120, 80, quality=50, seed=4)).tobytes())
+    files.append(synth_encode(SynthParams(120, 80, quality=95, restart_interval=7, flags=QUIRK_FREE | EMIT_RESTART, seed=5)).tobytes())
+    files.append(synth_encode(SynthParams(97, 33, file_components=1, quality=70, flags=QUIRK_FREE | GRAY_CONTENT, seed=6)).tobytes())
+    files.append(synth_encode(SynthParams(88, 56, quality=70, seed=7, flags=QUIRK_FREE | NON_INTERLEAVED)).tobytes())
+    if lena:
+        files.append(lena)
+    good = len(files)
+    _, off, n = K.parse_jfif(files[0])
+    files.append(files[0][:off + n // 2] + b"\xff\xd9")  # same plan as the first three, truncated
+    files.append(b"not a jpeg at all")
+    imgs, codes = decoder.decode_files(files)
+    assert codes[:good] == [0] * good and codes[good] == api.KPEG_ERR_STREAM and codes[good + 1] == api.KPEG_ERR_FORMAT
+    assert imgs[good] is None and imgs[good + 1] is None
+    for i in range(good):
+        ref = H.oracle_decode(files[i], parity=True)["pixels"]
+        assert np.array_equal(imgs[i], ref), f"file {i}"
+    # all good: one kernel sequence per distinct plan (5 plans + lena), not one per file
+    imgs2, codes2 = decoder.decode_files(files[:good])
+    assert codes2 == [0] * good and all(np.array_equal(a, b) for a, b in zip(imgs2, imgs[:good]))
