@@ -105,6 +105,10 @@ struct kpeg_ctx {
     // result copies of the lanes leave one after another (each waits for the one enqueued before it): copies to the
     // host that run at the same time share the link AND slow each other down (measured: four concurrent 200 MB copies
     // take twice as long as the same four back to back); KPEG_D2H_CHAIN=0 turns the ordering off
+    // relay round 2 as a launch of its own, rounds 3.. in the cooperative loop (KPEG_RELAY_ROUND2_WIDE=1).  Off: measured, the
+    // loop takes as long without round 2 (every round costs the latency of one serial subsequence decode, ~35 us, whatever
+    // the length of its list) and the extra launch costs 2 % of the throughput
+    bool relay_round2_wide = false;
     bool d2h_chain = true;
     bool d2h_chain_armed = false;
     cudaEvent_t d2h_done = nullptr;
@@ -524,15 +528,19 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     J.rounds = ctx->relay_rounds < 2 ? 2 : (ctx->relay_rounds > MAX_RELAY_ROUNDS - 1 ? MAX_RELAY_ROUNDS - 1 : ctx->relay_rounds);
     launch_entropy_relay(ea, 1, s, &J.launches);
     mark(ctx, L, KPEG_T_ENTROPY_RELAY);
-    // rounds 2.. in one cooperative launch (device-side loop, stops at the fixed point); the cap only
-    // bounds the loop -- a stream that needs more is finished by job_finish
+    // (experiment knob, off: round 2 -- 6 % of the subsequences at 4K q95 -- as a wide launch of its own)
+    if (ctx->relay_round2_wide)
+        launch_entropy_relay(ea, 2, s, &J.launches);
+    const int loop_first = ctx->relay_round2_wide ? 3 : 2;
+    // the later rounds (0.5 %, 0.04 %, ...) in one cooperative launch (device-side loop, stops at the fixed point); the
+    // cap only bounds the loop -- a stream that needs more is finished by job_finish
     J.rounds = MAX_RELAY_ROUNDS - 2;
-    if (launch_entropy_relay_loop(ea, 2, J.rounds, s, &J.launches) != cudaSuccess) {
+    if (launch_entropy_relay_loop(ea, loop_first, J.rounds, s, &J.launches) != cudaSuccess) {
         // the driver refused the cooperative launch (MPS / a partitioned device): the same rounds as separate
         // launches; job_finish adds more if these do not reach the fixed point
         J.loop_used = false;
-        J.rounds = std::max(2, std::min(ctx->relay_rounds, MAX_RELAY_ROUNDS - 1));
-        for (int r = 2; r <= J.rounds; ++r)
+        J.rounds = std::max(loop_first, std::min(ctx->relay_rounds, MAX_RELAY_ROUNDS - 1));
+        for (int r = loop_first; r <= J.rounds; ++r)
             launch_entropy_relay(ea, r, s, &J.launches);
     }
     mark(ctx, L, KPEG_T_RELAY_SPARSE);
@@ -804,6 +812,8 @@ extern "C" int kpeg_cuda_create(int device, kpeg_ctx **out)
         ctx->host_chunks = std::max(1, std::min(64, atoi(e)));
     if (const char *e = getenv("KPEG_BANDS"))
         ctx->band_parts = std::max(1, std::min(NLANES, atoi(e)));
+    if (const char *e = getenv("KPEG_RELAY_ROUND2_WIDE"))
+        ctx->relay_round2_wide = e[0] != '0';
     if (const char *e = getenv("KPEG_D2H_CHAIN"))
         ctx->d2h_chain = e[0] != '0';
     cudaEventCreateWithFlags(&ctx->d2h_done, cudaEventDisableTiming);
