@@ -68,13 +68,13 @@ enum {
     KPEG_T_UNSTUFF,        /* K0: unstuff_count + unstuff_scan + unstuff_write                            */
     KPEG_T_ENTROPY_COLD,   /* K1: speculative cold decode of every subsequence                            */
     KPEG_T_ENTROPY_RELAY,  /* K1: first relay round (every subsequence, emits symbol records)             */
-    KPEG_T_ENTROPY_SCAN,   /* K1: segmented offset scan                                                   */
-    KPEG_T_ENTROPY_WRITE,  /* K1: final pass (record expansion, or Huffman decode) writing coefficients   */
-    KPEG_T_DC_SCAN,        /* K2                                                                          */
-    KPEG_T_IDCT,           /* K3: fused dequant + IDCT + colour + store                                   */
+    KPEG_T_ENTROPY_SCAN,   /* K1: segmented scan of slot counts and DC sums over the subsequences          */
+    KPEG_T_ENTROPY_WRITE,  /* K2: record expansion + DC prediction -> coefficient tiles (or the Huffman final pass) */
+    KPEG_T_DC_SCAN,        /* fallback only: DC prediction + tile conversion behind the Huffman final pass  */
+    KPEG_T_IDCT,           /* K3: fused dequant + IDCT + colour + store, and the exact re-evaluation pass  */
     KPEG_T_D2H,            /* device -> host copy of the pixels (host-pointer entry points only)          */
     KPEG_T_RELAY_SPARSE,   /* K1: later relay rounds (work list only) up to the fixed point               */
-    KPEG_T_IDCT_PATCH,     /* K3: exact (reference-order) re-evaluation of the pixels inside the tie band  */
+    KPEG_T_IDCT_PATCH,     /* (not used: the exact pass is timed with KPEG_T_IDCT)                         */
     KPEG_T_COUNT
 };
 
