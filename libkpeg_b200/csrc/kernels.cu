@@ -342,6 +342,34 @@ void launch_repack_scans(const uint8_t *stage, uint8_t *scan, const uint64_t *en
     repack_scans_kernel<<<n < 148u * 8u ? n : 148u * 8u, 256, 0, s>>>(stage, scan, ends, n);
 }
 
+// Number of RSTn markers (FF D0 .. FF D7) in scan[0, len): what tells how many restart intervals -- hence MCU rows -- a
+// band that was cut at a byte position holds (kpeg_cuda.cu decode_banded).  Inside entropy-coded data an FF is always
+// followed by 00 (stuffing), another FF (fill) or a marker, so the two-byte test is exact.  16 bytes per thread, the byte
+// after the chunk fetched separately; one atomic per warp.
+__global__ void __launch_bounds__(256) count_restart_markers_kernel(const uint8_t *scan, uint32_t len, uint32_t *count)
+{
+    const uint32_t stride = gridDim.x * 256u * 16u;
+    uint32_t n = 0;
+    for (uint32_t at = (blockIdx.x * 256u + threadIdx.x) * 16u; at < len; at += stride) {
+        const uint32_t m = min(16u, len - at);
+        uint32_t prev = __ldg(scan + at);
+        for (uint32_t i = 1; i <= m; ++i) {
+            const uint32_t cur = at + i < len ? (uint32_t)__ldg(scan + at + i) : 0u;
+            n += (prev == 0xFFu && (cur & 0xF8u) == 0xD0u) ? 1u : 0u;
+            prev = cur;
+        }
+    }
+    n = __reduce_add_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31u) == 0u && n)
+        atomicAdd(count, n);
+}
+
+void launch_count_restart_markers(const uint8_t *scan, uint32_t len, uint32_t *count, cudaStream_t s)
+{
+    const uint32_t blocks = (len + 4095u) / 4096u;
+    count_restart_markers_kernel<<<blocks < 148u * 8u ? (blocks ? blocks : 1u) : 148u * 8u, 256, 0, s>>>(scan, len, count);
+}
+
 void launch_write_separators(uint8_t *scan, const uint64_t *ends, uint32_t n, cudaStream_t s)
 {
     write_separators_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(scan, ends, n);

@@ -122,6 +122,7 @@ void kernels_context_destroyed(); // all of them together must stay co-resident
 void kernels_configure(int max_concurrent_jobs); // jobs (lanes) that may be on the device at the same time // per-device function attributes (call once after cudaSetDevice)
 void launch_repack_scans(const uint8_t *stage, uint8_t *scan, const uint64_t *ends, uint32_t n, cudaStream_t s); // contiguous host scans -> packed batch
 void launch_write_separators(uint8_t *scan, const uint64_t *ends, uint32_t n, cudaStream_t s); // RSTn after every scan of a packed batch
+void launch_count_restart_markers(const uint8_t *scan, uint32_t len, uint32_t *count, cudaStream_t s); // *count += RSTn markers in scan[0, len)
 void launch_gray_to_rgb(const uint8_t *gray, uint8_t *rgb, size_t npixels, cudaStream_t s);     // PPM payload of a one-component image
 void launch_rgb_to_planar(const uint8_t *rgb, uint8_t *planes, size_t npixels, cudaStream_t s); // [3][H][W] planes
 void launch_unstuff(const UnstuffArgs &a, uint32_t sub_bits, cudaStream_t s, uint32_t *launches);

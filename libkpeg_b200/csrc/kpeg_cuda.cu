@@ -98,10 +98,10 @@ struct kpeg_ctx {
     int split_parts = 4;     // concurrent jobs a device-resident batch is cut into (KPEG_SPLIT)
     int host_chunks = 8;     // pipeline depth of a host-pointer batch (KPEG_HOST_CHUNKS)
     int submit_parts = 1;    // jobs one deferred submission is cut into (KPEG_SUBMIT_SPLIT)
-    // restart-interval bands a large image from host memory is cut into (KPEG_BANDS).  Off (1) by default: finding the cut
-    // points is a walk over the scan's markers on the host, ~0.15 ms per MB, which costs more than overlapping the copy in
-    // and the kernels with the copy out gains (16384x16384: 19 ms whole, 23 ms in 4 or 8 bands; profiles/README.md)
-    int band_parts = 1;
+    // bands a large restart-marked image from host memory is cut into, one per lane (KPEG_BANDS; 1 = off)
+    int band_parts = 4;
+    DevBuf band_counts;     // RSTn markers counted per band (decode_banded)
+    PinBuf h_band_counts;
     // result copies of the lanes leave one after another (each waits for the one enqueued before it): copies to the
     // host that run at the same time share the link AND slow each other down (measured: four concurrent 200 MB copies
     // take twice as long as the same four back to back); KPEG_D2H_CHAIN=0 turns the ordering off
@@ -670,73 +670,93 @@ void zero_stats(kpeg_stats *stats)
         memset(stats, 0, sizeof *stats);
 }
 
-// One large restart-marked image from host memory: its restart-interval bands (whole MCU rows, each a complete image
-// of the same width and tables) go through the lanes one band per lane, so the copy in of one band, the kernels of
-// another and the copy out of a third overlap.  The cut points are found by walking the restart markers of the scan
-// (as kpeg_split_restart_bands does) -- about 0.1 ms per MB on the host -- so the walk is interleaved with the
-// submissions: a band is enqueued as soon as the marker that ends it has been found, and the GPU works on it while
-// the walk goes on.  Synchronous.  KPEG_ERR_UNSUPPORTED when the restart interval does not line up with MCU rows
-// (nothing has been enqueued then).
+// One large restart-marked image from host memory: bands of whole MCU rows, each a complete image of the same width
+// and tables, go through the lanes one band per lane, so the copy in of one band, the kernels of another and the copy
+// out of a third overlap.  The scan is cut at BYTE positions (the first RSTn marker at or after k/parts of its length: a
+// memchr over a few hundred bytes); how many restart intervals -- hence MCU rows -- each band holds is counted on the GPU
+// from the band's own bytes once they are there (count_restart_markers_kernel: 10 us for 24 MB), so the host never walks
+// the scan.  (Finding cut points at given ROWS instead is a marker walk over the whole scan, 12 ms for 96 MB, more
+// than the overlap gains: profiles/README.md.)  Needs a restart interval of whole MCU rows.  Synchronous.
+// KPEG_ERR_UNSUPPORTED when the image does not qualify (nothing has been enqueued then).
 int decode_banded(kpeg_ctx *ctx, const kpeg_plan *plan, const uint8_t *scan, size_t scan_len, uint8_t *pixels_out, kpeg_stats *stats)
 {
     const uint32_t mx = (plan->width + 7u) / 8u, my = (plan->height + 7u) / 8u, ri = plan->restart_interval;
-    if (ri == 0 || !((ri % mx) == 0 || (mx % ri) == 0))
-        return KPEG_ERR_UNSUPPORTED; // bands must begin on a restart marker
-    const uint32_t row_step = (ri % mx) == 0 ? ri / mx : 1u; // MCU rows between candidate cut points
-    const uint32_t units = (my + row_step - 1) / row_step;
-    const uint32_t parts = std::min<uint32_t>((uint32_t)std::min(ctx->band_parts, NLANES), units);
-    if (parts < 2)
+    if (ri == 0 || ri % mx != 0 || scan_len < (1u << 20))
         return KPEG_ERR_UNSUPPORTED;
-    uint32_t row[NLANES + 1]; // first MCU row of every band, balanced in cut units (kpeg_split_restart_bands)
-    for (uint32_t k = 0; k <= parts; ++k)
-        row[k] = std::min<uint32_t>(my, (uint32_t)((uint64_t)units * k / parts) * row_step);
+    const uint32_t rows_per_interval = ri / mx;
+    const uint32_t parts = (uint32_t)std::min(ctx->band_parts, NLANES);
+    if (parts < 2 || my < parts * rows_per_interval * 2u)
+        return KPEG_ERR_UNSUPPORTED;
+    // cut points: the first RSTn marker at or after k / parts of the scan
+    size_t begin[NLANES + 1], end[NLANES];
+    begin[0] = 0;
+    for (uint32_t k = 1; k < parts; ++k) {
+        const uint8_t *p = scan + std::max(scan_len * k / parts, begin[k - 1] + 1), *stop = scan + scan_len;
+        const uint8_t *cut = nullptr;
+        while (p + 1 < stop) {
+            const uint8_t *q = (const uint8_t *)memchr(p, 0xFF, (size_t)(stop - 1 - p));
+            if (!q)
+                break;
+            if ((q[1] & 0xF8u) == 0xD0u) {
+                cut = q;
+                break;
+            }
+            p = q + 1;
+        }
+        if (!cut)
+            return KPEG_ERR_UNSUPPORTED; // no marker in the rest of the scan: not the stream the plan describes; decoded whole
+        end[k - 1] = (size_t)(cut - scan);
+        begin[k] = end[k - 1] + 2u;
+    }
+    end[parts - 1] = scan_len;
     for (int i = 0; i < NLANES; ++i)
         if (ctx->lane[i].job.active)
             finish_deferred(ctx, i);
+    // copies in + marker counts, every band on its own lane
+    TRY(ensure(ctx, ctx->lane[0].stream, ctx->band_counts, NLANES * sizeof(uint32_t)));
+    TRY(ensure_pinned(ctx, ctx->lane[0].stream, ctx->h_band_counts, NLANES * sizeof(uint32_t)));
+    uint32_t *d_counts = (uint32_t *)ctx->band_counts.p, *h_counts = (uint32_t *)ctx->h_band_counts.p;
+    for (uint32_t k = 0; k < parts; ++k) {
+        Lane &L = ctx->lane[k];
+        const size_t blen = end[k] - begin[k];
+        TRY(ensure(ctx, L.stream, L.scan, blen + 64));
+        mark(ctx, L, -1);
+        CK(cudaMemcpyAsync(L.scan.p, scan + begin[k], blen, cudaMemcpyHostToDevice, L.stream));
+        if (k + 1 < parts) { // the last band holds whatever rows are left
+            CK(cudaMemsetAsync(d_counts + k, 0, sizeof(uint32_t), L.stream));
+            launch_count_restart_markers((const uint8_t *)L.scan.p, (uint32_t)blen, d_counts + k, L.stream);
+            CK(cudaMemcpyAsync(h_counts + k, d_counts + k, sizeof(uint32_t), cudaMemcpyDeviceToHost, L.stream));
+        }
+        mark(ctx, L, KPEG_T_H2D);
+    }
     const size_t row_bytes = (size_t)plan->width * plan->ncomp;
     int rc = KPEG_OK, used[NLANES], nused = 0;
-    auto submit = [&](uint32_t k, size_t begin, size_t end) -> int { // band k = scan[begin, end)
-        const uint32_t r0 = std::min<uint32_t>(row[k] * 8u, plan->height), r1 = std::min<uint32_t>(row[k + 1] * 8u, plan->height);
+    uint32_t row0 = 0; // first MCU row of the band
+    for (uint32_t k = 0; k < parts && rc == KPEG_OK; ++k) {
         Lane &L = ctx->lane[k];
-        kpeg_plan bp = *plan;
-        bp.height = (uint16_t)(r1 - r0);
-        const size_t blen = end - begin, bpix = row_bytes * (r1 - r0);
-        TRY(ensure(ctx, L.stream, L.scan, blen + 64));
-        TRY(ensure(ctx, L.stream, L.pixels, bpix + 64));
-        mark(ctx, L, -1);
-        CK(cudaMemcpyAsync(L.scan.p, scan + begin, blen, cudaMemcpyHostToDevice, L.stream));
-        mark(ctx, L, KPEG_T_H2D);
-        TRY(job_enqueue(ctx, (int)k, &bp, (const uint8_t *)L.scan.p, blen, 1, (uint8_t *)L.pixels.p,
-                        {Copy{pixels_out + (size_t)r0 * row_bytes, L.pixels.p, bpix}}));
-        used[nused++] = (int)k;
-        return KPEG_OK;
-    };
-    // walk the markers: marker number j (1-based) precedes restart interval j; band b begins after marker row[b] * mx / ri
-    uint32_t b = 1;
-    uint64_t markers = 0;
-    size_t begin = 0;
-    const uint8_t *p = scan, *end = scan + scan_len;
-    while (b < parts && p + 1 < end && rc == KPEG_OK) {
-        const uint8_t *q = (const uint8_t *)memchr(p, 0xFF, (size_t)(end - 1 - p));
-        if (!q)
-            break;
-        const uint8_t m = q[1];
-        if (m >= 0xD0 && m <= 0xD7) {
-            ++markers;
-            if (((uint64_t)row[b] * mx) / ri == markers) {
-                rc = submit(b - 1, begin, (size_t)(q - scan));
-                begin = (size_t)(q + 2 - scan);
-                ++b;
+        uint32_t rows = my - row0;
+        if (k + 1 < parts) {
+            CK(cudaStreamSynchronize(L.stream)); // the band is on the device and its markers are counted
+            const uint64_t r = ((uint64_t)h_counts[k] + 1u) * rows_per_interval;
+            if (r >= rows) { // more intervals than the frame has rows for: corrupt stream
+                rc = fail(ctx, KPEG_ERR_STREAM, "restart markers do not match the restart interval");
+                break;
             }
-            p = q + 2;
-        } else {
-            p = q + (m == 0xFF ? 1 : 2);
+            rows = (uint32_t)r;
         }
+        const uint32_t y0 = row0 * 8u, y1 = std::min<uint32_t>((row0 + rows) * 8u, plan->height);
+        kpeg_plan bp = *plan;
+        bp.height = (uint16_t)(y1 - y0);
+        const size_t bpix = row_bytes * (y1 - y0);
+        rc = ensure(ctx, L.stream, L.pixels, bpix + 64);
+        if (rc != KPEG_OK)
+            break;
+        rc = job_enqueue(ctx, (int)k, &bp, (const uint8_t *)L.scan.p, end[k] - begin[k], 1, (uint8_t *)L.pixels.p,
+                         {Copy{pixels_out + (size_t)y0 * row_bytes, L.pixels.p, bpix}});
+        if (rc == KPEG_OK)
+            used[nused++] = (int)k;
+        row0 += rows;
     }
-    if (rc == KPEG_OK && b < parts)
-        rc = fail(ctx, KPEG_ERR_STREAM, "fewer restart markers than the restart interval promises");
-    if (rc == KPEG_OK)
-        rc = submit(parts - 1, begin, scan_len);
     const std::string first_err = ctx->err;
     for (int i = 0; i < nused; ++i) { // every enqueued band is completed, whatever happened to the others
         const int frc = job_finish(ctx, used[i], stats);
@@ -745,6 +765,8 @@ int decode_banded(kpeg_ctx *ctx, const kpeg_plan *plan, const uint8_t *scan, siz
         else if (frc != KPEG_OK)
             ctx->err = first_err;
     }
+    for (uint32_t k = 0; k < parts; ++k) // lanes whose copies were issued but whose band was never enqueued
+        cudaStreamSynchronize(ctx->lane[k].stream);
     if (stats) {
         stats->width = plan->width;
         stats->height = plan->height;
@@ -882,6 +904,9 @@ extern "C" void kpeg_cuda_destroy(kpeg_ctx *ctx)
         cudaEventDestroy(ctx->d2h_done);
     for (DevBuf &b : ctx->scan_tiles)
         dev_free(b);
+    dev_free(ctx->band_counts);
+    if (ctx->h_band_counts.p)
+        cudaFreeHost(ctx->h_band_counts.p);
     delete ctx;
 }
 

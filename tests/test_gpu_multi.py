@@ -175,17 +175,17 @@ def test_host_batch_small_and_large_scans_contiguous_outputs(decoder):
 
 
 def test_large_restart_image_goes_through_the_lanes_in_bands(monkeypatch):
-    """With KPEG_BANDS=4, kpeg_cuda_decode on a large (>= 64 MB of pixels) restart-marked image from host memory cuts it
-    into four restart-interval bands that run on the context's lanes with their copies overlapping (decode_banded; off
-    by default, the host-side marker walk costs more than the overlap gains); the frame must equal the one a context
-    without it (whole image, one lane) produces, a corrupt band must surface as an
-    error, and an image whose restart interval does not line up with MCU rows must still decode (whole)."""
+    """kpeg_cuda_decode on a large (>= 64 MB of pixels) restart-marked image from host memory cuts it into four bands that
+    run on the context's lanes with their copies overlapping (decode_banded: cut at byte positions, the restart markers
+    of every band counted on the GPU to learn its rows); the frame must equal the one a context with KPEG_BANDS=1 (whole
+    image, one lane) produces, a corrupt band must surface as an error, and an image whose restart interval is not a whole
+    number of MCU rows must still decode (whole)."""
     w, h = 8192, 2744  # 67 MB of pixels; 343 MCU rows: bands of unequal height
     jpg = _banded_jpg(w=w, h=h, ri_rows=1, q=60, seed=21)
-    monkeypatch.setenv("KPEG_BANDS", "4")
     banded = K.Decoder(device=0)
-    monkeypatch.delenv("KPEG_BANDS")
+    monkeypatch.setenv("KPEG_BANDS", "1")
     whole = K.Decoder(device=0)
+    monkeypatch.delenv("KPEG_BANDS")
     try:
         a = banded.decode_file(jpg)
         launches_banded = banded.last_stats.kernel_launches
@@ -201,7 +201,10 @@ def test_large_restart_image_goes_through_the_lanes_in_bands(monkeypatch):
         with pytest.raises(K.KpegError):
             banded.decode_file(bytes(bad))
         assert np.array_equal(banded.decode_file(jpg), b)  # the context is usable afterwards
-        # restart interval of 5 MCUs: neither a whole number of rows nor a divisor of one -> decoded whole
+        # two restart intervals per MCU row, and rows of unequal band sizes with a two-row interval
+        two = _banded_jpg(w=w, h=h, ri_rows=2, q=40, seed=8)
+        assert np.array_equal(banded.decode_file(two), whole.decode_file(two))
+        # restart interval of 5 MCUs: not a whole number of rows -> decoded whole
         odd = synth_encode(SynthParams(width=w, height=h, quality=30, restart_interval=5, flags=QUIRK_FREE | EMIT_RESTART, seed=4)).tobytes()
         assert np.array_equal(banded.decode_file(odd), whole.decode_file(odd))
     finally:

@@ -20,7 +20,7 @@ with open(path, "wb") as f:
     f.truncate(nb)
 shm = np.memmap(path, dtype=np.uint8, mode="r+", shape=(nb,))
 print("register rc", lib.kpeg_cuda_host_register(shm.ctypes.data, nb))
-for bands, chain in (("1", "1"), ("4", "1"), ("8", "1")):
+for bands, chain in (("1", "1"), ("2", "1"), ("4", "1"), ("8", "1")):
     os.environ["KPEG_BANDS"] = bands
     os.environ["KPEG_D2H_CHAIN"] = chain
     dec = K.Decoder(device=0)
