@@ -79,9 +79,83 @@ struct BandJob {
     kpeg_stats stats;
 };
 
-// cut `scan` into one band per device; images without usable restart markers become one band on devices[0]
+// RSTn markers (FF D0 .. FF D7) in [p, end): inside entropy-coded data an FF is followed by 00, FF or a marker
+uint64_t count_restart_markers(const uint8_t *p, const uint8_t *end)
+{
+    uint64_t n = 0;
+    while (p + 1 < end) {
+        const uint8_t *q = (const uint8_t *)memchr(p, 0xFF, (size_t)(end - 1 - p));
+        if (!q)
+            break;
+        n += (q[1] & 0xF8u) == 0xD0u ? 1u : 0u;
+        p = q + ((q[1] & 0xF8u) == 0xD0u ? 2 : 1);
+    }
+    return n;
+}
+
+// Cut `scan` into one band per device; images without usable restart markers become one band on devices[0].
+// With a restart interval of whole MCU rows the scan is cut at BYTE positions (the first RSTn at or after k / ndev of its
+// length) and the restart intervals of every band are counted by ndev host threads at once, one band each: the rows of a
+// band follow from its marker count.  (kpeg_split_restart_bands finds cut points at given rows by ONE walk over all
+// markers of the scan -- 12 ms for the 96 MB of a 16384x16384 image, several times what a band then takes on its GPU.)
 int make_bands(const int *devices, int ndev, const kpeg_plan *plan, const uint8_t *scan, size_t len, std::vector<BandJob> &jobs)
 {
+    const uint32_t mx = ((uint32_t)plan->width + 7u) / 8u, my = ((uint32_t)plan->height + 7u) / 8u, ri = plan->restart_interval;
+    if (ndev > 1 && ri != 0 && ri % mx == 0 && len >= ((size_t)1 << 20) && my >= (uint32_t)ndev * (ri / mx) * 2u) {
+        const uint32_t rpi = ri / mx;
+        std::vector<size_t> begin((size_t)ndev), end((size_t)ndev);
+        bool ok = true;
+        begin[0] = 0;
+        for (int k = 1; k < ndev && ok; ++k) {
+            const uint8_t *p = scan + std::max(len * (size_t)k / (size_t)ndev, begin[(size_t)k - 1] + 1), *stop = scan + len, *cut = nullptr;
+            while (p + 1 < stop) {
+                const uint8_t *q = (const uint8_t *)memchr(p, 0xFF, (size_t)(stop - 1 - p));
+                if (!q)
+                    break;
+                if ((q[1] & 0xF8u) == 0xD0u) {
+                    cut = q;
+                    break;
+                }
+                p = q + 1;
+            }
+            ok = cut != nullptr;
+            if (ok) {
+                end[(size_t)k - 1] = (size_t)(cut - scan);
+                begin[(size_t)k] = end[(size_t)k - 1] + 2u;
+            }
+        }
+        if (ok) {
+            end[(size_t)ndev - 1] = len;
+            std::vector<uint64_t> markers((size_t)ndev, 0);
+            std::vector<std::thread> th;
+            for (int k = 0; k + 1 < ndev; ++k) // the last band holds whatever rows are left
+                th.emplace_back([&, k] { markers[(size_t)k] = count_restart_markers(scan + begin[(size_t)k], scan + end[(size_t)k]); });
+            for (auto &t : th)
+                t.join();
+            uint32_t row0 = 0;
+            for (int k = 0; k < ndev; ++k) {
+                uint64_t rows = my - row0;
+                if (k + 1 < ndev) {
+                    rows = (markers[(size_t)k] + 1u) * rpi;
+                    if (rows >= my - row0)
+                        return KPEG_ERR_STREAM; // more restart intervals than the frame has rows for
+                }
+                const uint32_t y0 = row0 * 8u, y1 = std::min<uint32_t>((row0 + (uint32_t)rows) * 8u, plan->height);
+                BandJob j;
+                j.device = devices[k];
+                j.plan = *plan;
+                j.plan.height = (uint16_t)(y1 - y0);
+                j.scan = scan + begin[(size_t)k];
+                j.len = end[(size_t)k] - begin[(size_t)k];
+                j.row0 = y0;
+                j.rows = y1 - y0;
+                memset(&j.stats, 0, sizeof j.stats);
+                jobs.push_back(j);
+                row0 += (uint32_t)rows;
+            }
+            return KPEG_OK;
+        }
+    }
     std::vector<uint64_t> b0((size_t)ndev), b1((size_t)ndev);
     std::vector<uint32_t> row((size_t)ndev + 1);
     int parts = ndev;

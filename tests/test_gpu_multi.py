@@ -240,3 +240,22 @@ def test_decode_files_takes_any_mix_of_files(decoder):
     # all good: one kernel sequence per distinct plan (5 plans + lena), not one per file
     imgs2, codes2 = decoder.decode_files(files[:good])
     assert codes2 == [0] * good and all(np.array_equal(a, b) for a, b in zip(imgs2, imgs[:good]))
+
+
+@pytest.mark.parametrize("ndev,ri_rows", [(2, 1), (3, 1), (5, 2)])
+def test_tiled_decode_of_a_large_scan_cuts_at_byte_positions(decoder, ndev, ri_rows):
+    """Scans of 1 MB and more with a restart interval of whole MCU rows are cut at byte positions and the rows of every band
+    follow from its marker count (counted by one host thread per band): bands of unequal, data-dependent height."""
+    jpg = _banded_jpg(w=2048, h=1400, ri_rows=ri_rows, q=92, seed=12)
+    _, off, n = K.parse_jfif(jpg)
+    assert n >= 1 << 20
+    whole = decoder.decode_file(jpg)
+    got, st = api.decode_file_tiled([0] * ndev, jpg)
+    assert np.array_equal(got, whole)
+    assert st.kernel_launches >= 10 * ndev
+    # a band that lost a restart marker: the rows no longer add up -> an error, not a shifted image
+    bad = bytearray(jpg)
+    k = jpg.index(b"\xff\xd3", off + n // 3)
+    bad[k:k + 2] = b"\x00\x00"
+    with pytest.raises(K.KpegError):
+        api.decode_file_tiled([0] * ndev, bytes(bad))
