@@ -164,7 +164,9 @@ int kpeg_cuda_memcpy_d2h(kpeg_ctx *ctx, void *dst, const void *src, size_t bytes
  *  pixels_out     : HOST buffer of width*height*ncomp bytes; interleaved R,G,B rows top-down for
  *                   ncomp==3 (the payload Image::dumpRawData writes, Image.cpp:129-135), one gray
  *                   byte per pixel for ncomp==1.
- * Synchronous: returns after the pixels are in pixels_out.
+ * Synchronous: returns after the pixels are in pixels_out.  An image of 64 MB of pixels or more whose restart interval is
+ * a whole number of MCU rows is cut into bands that run on the context's lanes with their copies overlapping
+ * ($KPEG_BANDS, default 4; 1 = one job).
  */
 int kpeg_cuda_decode(kpeg_ctx *ctx, const kpeg_plan *plan, const uint8_t *scan, size_t scan_len,
                      uint8_t *pixels_out, kpeg_stats *stats);
@@ -238,7 +240,8 @@ int kpeg_cuda_decode_files(kpeg_ctx *ctx, int n, const uint8_t *const *files, co
 /* Parity hook: the quantised coefficients of the LAST decode on this context, as the reference
  * holds them transiently inside MCU::constructMCU (MCU.cpp:93-108): [block][64] int16, blocks
  * MCU-interleaved (Y,Cb,Cr per MCU), zig-zag order, DC prediction already integrated.
- * `cap` is in int16 elements. */
+ * `cap` is in int16 elements.  (After a decode that ran as several jobs -- a large restart-marked image cut into bands,
+ * a batch cut into chunks -- these are the coefficients of the job that finished last.) */
 int kpeg_cuda_read_coefficients(kpeg_ctx *ctx, int16_t *out, size_t cap);
 
 /* Host-only: cut one restart-marked scan into `parts` bands of whole MCU rows; band b is the byte
