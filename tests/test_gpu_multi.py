@@ -259,3 +259,20 @@ def test_tiled_decode_of_a_large_scan_cuts_at_byte_positions(decoder, ndev, ri_r
     bad[k:k + 2] = b"\x00\x00"
     with pytest.raises(K.KpegError):
         api.decode_file_tiled([0] * ndev, bytes(bad))
+
+
+def test_decode_files_many_files_few_plans(decoder):
+    """120 files in six plans (sizes x qualities), shuffled: six batches, every image equal to its single-file decode."""
+    rng = np.random.default_rng(77)
+    specs = [(64, 48, 80), (64, 48, 60), (96, 64, 80), (40, 40, 90), (128, 24, 70), (57, 33, 50)]
+    files = []
+    for i in range(120):
+        w, h, q = specs[int(rng.integers(0, len(specs)))]
+        files.append(synth_encode(SynthParams(w, h, quality=q, seed=1000 + i)).tobytes())
+    imgs, codes = decoder.decode_files(files)
+    assert codes == [0] * len(files)
+    assert decoder.last_stats.kernel_launches <= 12 * len(specs) + 12  # one kernel sequence per plan, not per file
+    for i in (0, 17, 63, 119):
+        assert np.array_equal(imgs[i], decoder.decode_file(files[i])), f"file {i}"
+    ref = H.oracle_decode(files[5], parity=True)["pixels"]
+    assert np.array_equal(imgs[5], ref)

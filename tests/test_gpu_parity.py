@@ -424,6 +424,8 @@ def test_random_streams_on_the_gpu(decoder):
             nc = int(rng.choice([1, 3]))
             sb = int(rng.choice([64, 128, 256, 512, 1024]))
             flags = (QUIRK_FREE if trial % 4 else 0) | (EMIT_RESTART if ri else 0) | (GRAY_CONTENT if nc == 1 else 0)
+            if nc == 3 and trial % 5 == 0:
+                flags |= 8  # NON_INTERLEAVED: one scan per component (kpeg_cuda_decode_scans)
             jpg = synth_encode(SynthParams(w, h, file_components=nc, quality=q, restart_interval=ri, flags=flags,
                                            seed=int(rng.integers(0, 2 ** 31)), noise_amp=int(rng.integers(1, 61)))).tobytes()
             decoder.set_tuning(sub_bits=sb)
