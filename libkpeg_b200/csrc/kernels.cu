@@ -438,6 +438,10 @@ void launch_unstuff(const UnstuffArgs &a, uint32_t sub_bits, cudaStream_t s, uin
 // K1: entropy decode
 // =================================================================================================
 
+#ifndef KPEG_LONGLUT_GLOBAL
+#define KPEG_LONGLUT_GLOBAL 0 // 1: second-level Huffman tables read from global memory instead of shared memory
+#endif
+
 // Shared-memory image of what one CTA needs: the lookup tables (staged once per CTA) and the slice of
 // the bit stream that belongs to the tile of ENTROPY_THREADS subsequences being decoded.  The slice is
 // stored linearly with one padding word after every 32 (position l + (l >> 5)): lanes reading word k
@@ -446,7 +450,9 @@ void launch_unstuff(const UnstuffArgs &a, uint32_t sub_bits, cudaStream_t s, uin
 // the bit window looks two words ahead.
 struct K1Smem {
     uint16_t fast[MAX_LUTS * LUT_SIZE];
+#if !KPEG_LONGLUT_GLOBAL
     uint16_t longlut[MAX_LUTS * LONG_CAP];
+#endif
     uint32_t long_n[8];
     uint32_t words[1]; // padded(ENTROPY_THREADS * words_per_subsequence + 4), sized at launch
 };
@@ -475,6 +481,7 @@ struct SmemWords {
 struct SmemLuts {
     uint32_t fast_addr; // shared byte address of fast[0]
     uint32_t long_addr; // shared byte address of longlut[0]
+    const uint16_t *glong; // the second-level tables in global memory (KPEG_LONGLUT_GLOBAL)
     const K1Smem *sm;
     const HuffCanon *canon; // global
     __device__ __forceinline__ uint32_t fast(uint32_t toff, uint32_t idx) const
@@ -489,7 +496,11 @@ struct SmemLuts {
         if (e) { // pointer to a 64-entry sub-table indexed by stream bits 10..15
             uint16_t v;
             const uint32_t idx = ti * (uint32_t)LONG_CAP + ((e >> 5) - 1u) * (uint32_t)SUB_SIZE + ((win >> 16) & (uint32_t)(SUB_SIZE - 1));
+#if KPEG_LONGLUT_GLOBAL
+            v = __ldg(glong + idx); // second level from global memory (L1-resident: 6 KB): the shared memory it took is worth two more CTAs per SM
+#else
             asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(long_addr + 2u * idx));
+#endif
             return v;
         }
         return huff_slow_lookup(canon[ti], win);
@@ -510,6 +521,7 @@ __device__ __forceinline__ void k1_stage_tables(K1Smem &sm, const EntropyArgs &a
     }
     if (threadIdx.x < MAX_LUTS)
         sm.long_n[threadIdx.x] = t->luts.long_n[threadIdx.x];
+#if !KPEG_LONGLUT_GLOBAL
     for (uint32_t ti = 0; ti < nt; ++ti) {
         const uint32_t n = (t->luts.long_n[ti] * (uint32_t)sizeof(uint16_t) + 15u) / 16u;
         const uint4 *src = reinterpret_cast<const uint4 *>(&t->luts.longlut[ti][0]);
@@ -517,6 +529,7 @@ __device__ __forceinline__ void k1_stage_tables(K1Smem &sm, const EntropyArgs &a
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
             dst[i] = __ldg(src + i);
     }
+#endif
 }
 
 // The tile's stream slice (coalesced loads).  Ends with a __syncthreads().
@@ -631,7 +644,12 @@ __device__ __forceinline__ SmemLuts k1_luts(const K1Smem &sm, const EntropyArgs 
 {
     SmemLuts L;
     L.fast_addr = (uint32_t)__cvta_generic_to_shared(sm.fast);
+#if KPEG_LONGLUT_GLOBAL
+    L.long_addr = 0;
+#else
     L.long_addr = (uint32_t)__cvta_generic_to_shared(sm.longlut);
+#endif
+    L.glong = &a.tables->luts.longlut[0][0];
     L.sm = &sm;
     L.canon = a.tables->canon;
     return L;
