@@ -11,6 +11,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
+#include <thread>
+#include <vector>
+
 #include "kpeg_cuda.h"
 
 namespace {
@@ -20,16 +24,16 @@ inline unsigned be16(const uint8_t *p) { return (unsigned)((p[0] << 8) | p[1]); 
 // End of the entropy-coded segment that starts at `s`: the first marker that is neither a stuffed
 // FF00, an RSTn nor a fill byte.  scanImageData (Decoder.cpp:532-577) stops at the first FF D9 only; both
 // agree on well-formed single-scan files, including ones with bytes (or whole images) after the first EOI.
-size_t find_scan_end(const uint8_t *f, size_t n, size_t s)
+size_t find_scan_end_range(const uint8_t *f, size_t n, size_t s, size_t stop)
 {
-    // Always walk the markers (a memchr per FF byte: cheap next to the PCIe copy of the same bytes).  Trusting a
-    // trailing FF D9 instead would send files that carry data after the first EOI (MPO, concatenated JPEGs, appended
-    // previews) to the GPU whole; the reference stops at the first FF D9 (Decoder.cpp:546-557), and so does this.
+    // the first position e in [s, stop) with f[e] == FF and f[e + 1] not in {00, D0..D7, FF}; `stop` if there is none.
+    // Evaluating positions one by one is the same as the sequential walk that skips two bytes after FF 00 / FF Dx:
+    // the byte skipped is never an FF itself.
     size_t e = s;
-    while (e + 1 < n) {
-        const uint8_t *q = (const uint8_t *)memchr(f + e, 0xFF, n - 1 - e);
+    while (e < stop && e + 1 < n) {
+        const uint8_t *q = (const uint8_t *)memchr(f + e, 0xFF, std::min(stop, n - 1) - e);
         if (!q)
-            return n;
+            return stop;
         e = (size_t)(q - f);
         const uint8_t b = f[e + 1];
         if (b == 0x00 || (b >= 0xD0 && b <= 0xD7)) {
@@ -42,6 +46,40 @@ size_t find_scan_end(const uint8_t *f, size_t n, size_t s)
         }
         return e;
     }
+    return stop;
+}
+
+size_t find_scan_end(const uint8_t *f, size_t n, size_t s)
+{
+    // Always walk the markers.  Trusting a trailing FF D9 instead would send files that carry data after the first EOI
+    // (MPO, concatenated JPEGs, appended previews) to the GPU whole; the reference stops at the first FF D9
+    // (Decoder.cpp:546-557), and so does this.  The walk costs ~0.13 ms per MB -- 12 ms for the scan of a 16384x16384
+    // image, as long as its decode -- so large scans are walked by several threads, each over its own stretch; the
+    // first hit in file order wins.
+    constexpr size_t PAR_MIN = (size_t)4 << 20;
+    if (n - s < PAR_MIN) {
+        const size_t e = find_scan_end_range(f, n, s, n);
+        return e;
+    }
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt < 2 ? 2 : (nt > 8 ? 8 : nt);
+    std::vector<size_t> hit(nt, n);
+    std::vector<std::thread> th;
+    const size_t span = (n - s + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+        const size_t a = s + t * span, b = std::min(n, a + span);
+        if (a >= b)
+            break;
+        th.emplace_back([&, t, a, b] {
+            const size_t e = find_scan_end_range(f, n, a, b);
+            hit[t] = e < b ? e : n;
+        });
+    }
+    for (auto &x : th)
+        x.join();
+    for (unsigned t = 0; t < nt; ++t)
+        if (hit[t] < n)
+            return hit[t];
     return n;
 }
 

@@ -188,3 +188,38 @@ def test_multi_scan_files_the_path_does_not_take():
     with pytest.raises(K.KpegError) as e:
         api.parse_jfif_scans(bytes(two))
     assert e.value.code == api.KPEG_ERR_UNSUPPORTED
+
+
+def test_end_of_a_large_scan_is_found_by_the_parallel_walk():
+    """Scans of 4 MB and more are walked by several host threads, each over its own stretch: the end must be where the
+    sequential walk puts it -- the first FF that is not followed by 00, D0..D7 or FF -- wherever it falls (stretch
+    boundaries included), with stuffed FFs, restart markers and fill bytes on both sides of every boundary."""
+    from libkpeg_b200.synth import QUIRK_FREE, SynthParams, synth_encode
+    small = synth_encode(SynthParams(16, 16, quality=50, seed=1, flags=QUIRK_FREE)).tobytes()
+    _, off, n = K.parse_jfif(small)
+    head = small[:off]
+    rng = np.random.default_rng(5)
+    size = 6 * 1024 * 1024 + 123
+    body = rng.integers(0, 255, size=size, dtype=np.uint8)  # no FF at all
+    pos = rng.choice(size - 4, size=40000, replace=False)
+    pos.sort()
+    pos = pos[np.diff(pos, prepend=-10) > 3]
+    kind = rng.integers(0, 3, size=pos.size)
+    for p, k in zip(pos, kind):
+        body[p] = 0xFF
+        body[p + 1] = (0x00, 0xD0 + (int(p) & 7), 0xFF)[int(k)]
+        if k == 2:
+            body[p + 2] = 0x00  # FF FF 00: a fill byte, then a stuffed FF
+    nthreads = 8
+    span = (size + nthreads - 1) // nthreads
+    ends = [size - 2, size // 2 + 17, 5] + [t * span + d for t in range(1, nthreads) for d in (-2, -1, 0, 1)]
+    for e in ends:
+        buf = body.copy()
+        buf[e] = 0xFF
+        buf[e + 1] = 0xD9
+        if buf[e - 1] == 0xFF:  # do not turn the byte before into the first half of another pair
+            buf[e - 1] = 0x01
+        file = head + buf.tobytes()
+        _, o2, n2 = K.parse_jfif(file)
+        # the sequential definition, restricted to the bytes before e (nothing there may terminate the scan)
+        assert o2 == off and n2 == e, f"end at {e}: found {n2}"
