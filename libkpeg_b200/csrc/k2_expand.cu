@@ -110,9 +110,14 @@ __global__ void __launch_bounds__(EXPAND_THREADS, KPEG_EXPAND_MIN_CTAS) expand_k
     const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(sm.coef);
 
     // ---- stage B: expansion of the records that fall into the strip ---------------------------------------
+    // 32 subsequences at a time, one per lane -- or, with subsequences of 1024 bits (a strip then meets only ~14 of
+    // them: more than half of the lanes would idle), 16 at a time with TWO lanes per subsequence, one taking its even
+    // records, the other the odd ones.
+    const bool pair = a.g.sub_bits >= 1024u;
+    const uint32_t per_chunk = pair ? 16u : 32u, half = pair ? lane >> 4 : 0u, kstep = pair ? 2u : 1u;
     uint32_t first = first0;
-    for (int chunk = 0; chunk < 128; ++chunk, first += 32u) { // a strip meets at most ~3 100 subsequences
-        const uint32_t sub = first + lane;
+    for (int chunk = 0; chunk < 256; ++chunk, first += per_chunk) { // a strip meets at most ~3 100 subsequences
+        const uint32_t sub = first + (pair ? lane & 15u : lane);
         bool act = sub < nsub;
         const uint32_t ss = act ? __ldg(a.start_slot + sub) : 0xFFFFFFFFu;
         const uint32_t nr = act ? __ldg(a.nrec + sub) : 0u; // together with start_slot: one round trip, not two
@@ -132,15 +137,18 @@ __global__ void __launch_bounds__(EXPAND_THREADS, KPEG_EXPAND_MIN_CTAS) expand_k
         // slot of record position 0 relative to the tile (may be "negative"); lanes without a subsequence get an
         // offset that keeps the out-of-range marker of the batched loads below out of range
         const uint32_t off0 = act ? (ss & ~63u) - s0 : TILE_SLOTS;
-        const uint32_t nmax = __reduce_max_sync(0xffffffffu, n);
+        // records this lane takes: all of them, or every other one starting at `half`
+        const uint32_t mine = pair ? (n + 1u - half) >> 1 : n;
+        const uint32_t nmax = __reduce_max_sync(0xffffffffu, mine);
         // A record index beyond the lane's count reads as position 0xFFFF, which falls outside every tile.
-        const char *bp = reinterpret_cast<const char *>(base) + (size_t)(warp * EXPAND_BATCH) * stride;
-        const size_t step = (size_t)(NW * EXPAND_BATCH) * stride;
+        const size_t rstride = (size_t)stride * kstep; // bytes between two records of this lane
+        const char *bp = reinterpret_cast<const char *>(base) + (size_t)half * stride + (size_t)(warp * EXPAND_BATCH) * rstride;
+        const size_t step = (size_t)(NW * EXPAND_BATCH) * rstride;
         for (uint32_t k0 = warp * EXPAND_BATCH; k0 < nmax; k0 += NW * EXPAND_BATCH, bp += step) {
             uint32_t r[EXPAND_BATCH];
 #pragma unroll
             for (int u = 0; u < EXPAND_BATCH; ++u)
-                r[u] = k0 + (uint32_t)u < n ? __ldg(reinterpret_cast<const uint32_t *>(bp + (size_t)u * stride)) : 0xFFFFFFFFu;
+                r[u] = k0 + (uint32_t)u < mine ? __ldg(reinterpret_cast<const uint32_t *>(bp + (size_t)u * rstride)) : 0xFFFFFFFFu;
 #pragma unroll
             for (int u = 0; u < EXPAND_BATCH; ++u) {
                 const uint32_t off = off0 + record_pos(r[u]);
@@ -148,7 +156,7 @@ __global__ void __launch_bounds__(EXPAND_THREADS, KPEG_EXPAND_MIN_CTAS) expand_k
                     st_shared_u16(tile_addr + coef_tile_byte(off), r[u]);
             }
         }
-        // the next 32 subsequences matter only if the last one of these still begins inside the strip
+        // the next subsequences matter only if the last one of these still begins inside the strip
         if (!__shfl_sync(0xffffffffu, act && sub + 1u < nsub ? 1 : 0, 31))
             break;
     }
