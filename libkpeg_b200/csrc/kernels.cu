@@ -1434,13 +1434,26 @@ static uint32_t ilog2(uint32_t v)
     return l;
 }
 
+static uint32_t g_sm_count = 148;
 static uint32_t g_k1_grid_cap = 148 * 8;
 static uint32_t g_k1_write_grid_cap = 148 * 4;
 
+// CTAs of the persistent cold / relay kernels: what is resident at this subsequence size (the stream regions grow with
+// it: 8 CTAs per SM at 512 bits, 6 at 1024), so that the grid is one wave
 static uint32_t k1_grid(const EntropyArgs &a)
 {
+    static uint32_t cap_for[16] = {};
+    const uint32_t wlog = ilog2(a.g.sub_bits / 32u) & 15u;
+    if (cap_for[wlog] == 0u) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entropy_relay_full_kernel, ENTROPY_THREADS,
+                                                          k1_region_smem_bytes(a.g.sub_bits)) != cudaSuccess || per_sm < 1)
+            per_sm = 4;
+        cap_for[wlog] = g_sm_count * (uint32_t)per_sm;
+    }
     const uint32_t tiles = (a.nsub_max + ENTROPY_THREADS - 1) / ENTROPY_THREADS;
-    return tiles < g_k1_grid_cap ? tiles : g_k1_grid_cap;
+    const uint32_t cap = cap_for[wlog] < g_k1_grid_cap ? cap_for[wlog] : g_k1_grid_cap;
+    return tiles < cap ? tiles : cap;
 }
 
 void launch_entropy_cold(const EntropyArgs &a, cudaStream_t s, uint32_t *launches)
@@ -1464,7 +1477,6 @@ void launch_entropy_relay(const EntropyArgs &a, int round, cudaStream_t s, uint3
     ++*launches;
 }
 
-static uint32_t g_sm_count = 148;
 static uint32_t g_max_concurrent_loops = 8;
 static std::atomic<int> g_live_contexts{0};
 
