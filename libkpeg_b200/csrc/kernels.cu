@@ -1449,11 +1449,17 @@ static uint32_t k1_grid(const EntropyArgs &a)
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entropy_relay_full_kernel, ENTROPY_THREADS,
                                                           k1_region_smem_bytes(a.g.sub_bits)) != cudaSuccess || per_sm < 1)
             per_sm = 4;
+        if (const char *e = getenv("KPEG_K1_PER_SM")) // experiments: fewer CTAs per SM leave room for the other lanes' kernels
+            per_sm = std::max(1, std::min(per_sm, atoi(e)));
         cap_for[wlog] = g_sm_count * (uint32_t)per_sm;
     }
     const uint32_t tiles = (a.nsub_max + ENTROPY_THREADS - 1) / ENTROPY_THREADS;
     const uint32_t cap = cap_for[wlog] < g_k1_grid_cap ? cap_for[wlog] : g_k1_grid_cap;
-    return tiles < cap ? tiles : cap;
+    if (tiles <= cap)
+        return tiles ? tiles : 1u;
+    // every CTA the same number of tiles: with 3.5 tiles per CTA the last of four rounds would run half empty
+    const uint32_t rounds = (tiles + cap - 1u) / cap;
+    return (tiles + rounds - 1u) / rounds;
 }
 
 void launch_entropy_cold(const EntropyArgs &a, cudaStream_t s, uint32_t *launches)
