@@ -571,7 +571,9 @@ int check_guards(kpeg_ctx *ctx, Lane &L)
                        {"seg_hint", &L.seg_hint}, {"start_slot", &L.start_slot}, {"scan_tiles", &L.scan_tiles},
                        {"coef", &L.coef},         {"dcdiff", &L.dcdiff},     {"tiles", &L.tiles},       {"tie_rec", &L.tie_rec},   {"tie_cnt", &L.tie_cnt},     {"strip_sub", &L.strip_sub}, {"dc", &L.dc}, {"dcs", &L.dcs}, {"dcpre", &L.dcpre}, {"scan_tiles_dcs", &L.scan_tiles_dcs}, {"d_ends", &L.d_ends},
                        {"pixels", &L.pixels},     {"meta", &L.meta},
-                       {"rec", &L.rec},           {"nrec", &L.nrec},         {"rec_alt", &L.rec_alt},   {"tables", &ctx->tables}};
+                       {"rec", &L.rec},           {"nrec", &L.nrec},         {"rec_alt", &L.rec_alt},   {"tables", &ctx->tables},
+                       {"d_stage", &L.d_stage},   {"scan_tiles[0]", &ctx->scan_tiles[0]}, {"scan_tiles[1]", &ctx->scan_tiles[1]},
+                       {"scan_tiles[2]", &ctx->scan_tiles[2]}, {"band_counts", &ctx->band_counts}, {"merged", &ctx->merged}};
     uint8_t host[2 * GUARD_BYTES];
     for (const NamedBuf &nb : bufs) {
         const DevBuf &b = *nb.buf;
