@@ -305,6 +305,7 @@ def leg_gray_batch(dec, K, rank, world, dist, device, torch, quick):
     from libkpeg_b200.shard import shard_range
     from libkpeg_b200.synth import GRAY_CONTENT, QUIRK_FREE, SynthParams, synth_encode
     total, side = (4096 if not quick else 256), 512
+    total = int(os.environ.get("KPEG_BENCH_GRAY_TOTAL", total))  # development: a rank's share at N > 1, on one GPU
     idx = list(shard_range(total, rank, world))
     n = len(idx)
     threads = max(1, (os.cpu_count() or 1) // max(world, 1))
@@ -350,7 +351,9 @@ def leg_gray_batch(dec, K, rank, world, dist, device, torch, quick):
     # the device-resident pass is short (a few ms per rep at N = 8): the same number of images per rank at every N, so that
     # neither filling the lanes nor a moment of host jitter on one rank (the time is the max over ranks) dominates
     dev_reps = 4 * reps * max(1, total // max(n, 1))
-    run_device(3)
+    # warm-up: every one of the context's eight lanes must have sized its scratch (a lane allocates at its first job)
+    subs_per_rep = max(1, -(-n // per_sub))
+    run_device(max(3, -(-16 // subs_per_rep)))
     sync()
     t0 = time.perf_counter()
     run_device(dev_reps)
@@ -364,7 +367,7 @@ def leg_gray_batch(dec, K, rank, world, dist, device, torch, quick):
             dec.submit_prepared(plan, prepared)
         dec.wait()
 
-    run_e2e(2)
+    run_e2e(max(2, -(-16 // max(1, min(8, n // max(1, per_sub // 8))))))  # the chunks of a submission rotate through the lanes
     sync()
     e2e_reps = reps * max(1, min(4, total // max(n, 1)))  # more repetitions where a rank's share is small (see dev_reps)
     t0 = time.perf_counter()
