@@ -254,6 +254,14 @@ int kpeg_cuda_read_coefficients(kpeg_ctx *ctx, int16_t *out, size_t cap);
 int kpeg_split_restart_bands(const uint8_t *scan, size_t len, const kpeg_plan *plan, int parts, uint64_t *out_begin,
                              uint64_t *out_end, uint32_t *out_row);
 
+/* Host-only: the same kind of bands, cut at BYTE positions instead of given rows: band b begins at the first RSTn marker
+ * at or after b/parts of the scan, and its rows follow from the number of restart markers it holds (counted by one host
+ * thread per band) -- no single walk over all markers of a large scan; the bands' heights depend on the data.  Needs a
+ * restart interval of whole MCU rows and at least two intervals per band (else KPEG_ERR_UNSUPPORTED: use
+ * kpeg_split_restart_bands).  Same outputs as kpeg_split_restart_bands. */
+int kpeg_split_restart_bands_by_bytes(const uint8_t *scan, size_t len, const kpeg_plan *plan, int parts, uint64_t *out_begin,
+                                      uint64_t *out_end, uint32_t *out_row);
+
 /* ---- one image over several GPUs (kpeg_tiled.cpp) ---------------------------------------------------------
  * The restart-interval tiles of one very large image, one band of whole MCU rows per listed device (a device may be
  * listed more than once), each band decoded by its own GPU straight into its rows of the caller's frame

@@ -120,6 +120,8 @@ SYMBOLS = {
     "kpeg_cuda_read_coefficients": (C.c_int, [_vp, _vp, C.c_size_t]),
     "kpeg_split_restart_bands": (C.c_int, [_vp, C.c_size_t, C.POINTER(Plan), C.c_int, C.POINTER(C.c_uint64),
                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    "kpeg_split_restart_bands_by_bytes": (C.c_int, [_vp, C.c_size_t, C.POINTER(Plan), C.c_int, C.POINTER(C.c_uint64),
+                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "kpeg_ppm_header": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
     "kpeg_cuda_acquire": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "kpeg_cuda_release": (None, [C.c_int, _vp]),

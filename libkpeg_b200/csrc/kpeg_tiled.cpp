@@ -93,73 +93,74 @@ uint64_t count_restart_markers(const uint8_t *p, const uint8_t *end)
     return n;
 }
 
-// Cut `scan` into one band per device; images without usable restart markers become one band on devices[0].
-// With a restart interval of whole MCU rows the scan is cut at BYTE positions (the first RSTn at or after k / ndev of its
-// length) and the restart intervals of every band are counted by ndev host threads at once, one band each: the rows of a
-// band follow from its marker count.  (kpeg_split_restart_bands finds cut points at given rows by ONE walk over all
-// markers of the scan -- 12 ms for the 96 MB of a 16384x16384 image, several times what a band then takes on its GPU.)
-int make_bands(const int *devices, int ndev, const kpeg_plan *plan, const uint8_t *scan, size_t len, std::vector<BandJob> &jobs)
+} // namespace
+
+// Host-only (include/kpeg_cuda.h): bands of whole MCU rows cut at BYTE positions.
+extern "C" int kpeg_split_restart_bands_by_bytes(const uint8_t *scan, size_t len, const kpeg_plan *plan, int parts,
+                                                 uint64_t *out_begin, uint64_t *out_end, uint32_t *out_row)
 {
+    if (!scan || !plan || parts < 1 || !out_begin || !out_end || !out_row)
+        return KPEG_ERR_ARG;
     const uint32_t mx = ((uint32_t)plan->width + 7u) / 8u, my = ((uint32_t)plan->height + 7u) / 8u, ri = plan->restart_interval;
-    if (ndev > 1 && ri != 0 && ri % mx == 0 && len >= ((size_t)1 << 20) && my >= (uint32_t)ndev * (ri / mx) * 2u) {
-        const uint32_t rpi = ri / mx;
-        std::vector<size_t> begin((size_t)ndev), end((size_t)ndev);
-        bool ok = true;
-        begin[0] = 0;
-        for (int k = 1; k < ndev && ok; ++k) {
-            const uint8_t *p = scan + std::max(len * (size_t)k / (size_t)ndev, begin[(size_t)k - 1] + 1), *stop = scan + len, *cut = nullptr;
-            while (p + 1 < stop) {
-                const uint8_t *q = (const uint8_t *)memchr(p, 0xFF, (size_t)(stop - 1 - p));
-                if (!q)
-                    break;
-                if ((q[1] & 0xF8u) == 0xD0u) {
-                    cut = q;
-                    break;
-                }
-                p = q + 1;
+    if (parts < 2 || ri == 0 || ri % mx != 0 || my < (uint32_t)parts * (ri / mx) * 2u)
+        return KPEG_ERR_UNSUPPORTED;
+    const uint32_t rpi = ri / mx;
+    out_begin[0] = 0;
+    for (int k = 1; k < parts; ++k) {
+        const uint8_t *p = scan + std::max<size_t>(len * (size_t)k / (size_t)parts, (size_t)out_begin[k - 1] + 1), *stop = scan + len, *cut = nullptr;
+        while (p + 1 < stop) {
+            const uint8_t *q = (const uint8_t *)memchr(p, 0xFF, (size_t)(stop - 1 - p));
+            if (!q)
+                break;
+            if ((q[1] & 0xF8u) == 0xD0u) {
+                cut = q;
+                break;
             }
-            ok = cut != nullptr;
-            if (ok) {
-                end[(size_t)k - 1] = (size_t)(cut - scan);
-                begin[(size_t)k] = end[(size_t)k - 1] + 2u;
-            }
+            p = q + 1;
         }
-        if (ok) {
-            end[(size_t)ndev - 1] = len;
-            std::vector<uint64_t> markers((size_t)ndev, 0);
-            std::vector<std::thread> th;
-            for (int k = 0; k + 1 < ndev; ++k) // the last band holds whatever rows are left
-                th.emplace_back([&, k] { markers[(size_t)k] = count_restart_markers(scan + begin[(size_t)k], scan + end[(size_t)k]); });
-            for (auto &t : th)
-                t.join();
-            uint32_t row0 = 0;
-            for (int k = 0; k < ndev; ++k) {
-                uint64_t rows = my - row0;
-                if (k + 1 < ndev) {
-                    rows = (markers[(size_t)k] + 1u) * rpi;
-                    if (rows >= my - row0)
-                        return KPEG_ERR_STREAM; // more restart intervals than the frame has rows for
-                }
-                const uint32_t y0 = row0 * 8u, y1 = std::min<uint32_t>((row0 + (uint32_t)rows) * 8u, plan->height);
-                BandJob j;
-                j.device = devices[k];
-                j.plan = *plan;
-                j.plan.height = (uint16_t)(y1 - y0);
-                j.scan = scan + begin[(size_t)k];
-                j.len = end[(size_t)k] - begin[(size_t)k];
-                j.row0 = y0;
-                j.rows = y1 - y0;
-                memset(&j.stats, 0, sizeof j.stats);
-                jobs.push_back(j);
-                row0 += (uint32_t)rows;
-            }
-            return KPEG_OK;
+        if (!cut)
+            return KPEG_ERR_UNSUPPORTED; // no marker left: fewer intervals than bands
+        out_end[k - 1] = (uint64_t)(cut - scan);
+        out_begin[k] = out_end[k - 1] + 2u;
+    }
+    out_end[parts - 1] = len;
+    std::vector<uint64_t> markers((size_t)parts, 0);
+    std::vector<std::thread> th;
+    for (int k = 0; k + 1 < parts; ++k) // the last band holds whatever rows are left
+        th.emplace_back([&, k] { markers[(size_t)k] = count_restart_markers(scan + out_begin[k], scan + out_end[k]); });
+    for (auto &t : th)
+        t.join();
+    uint32_t row0 = 0;
+    for (int k = 0; k < parts; ++k) {
+        out_row[k] = row0;
+        if (k + 1 < parts) {
+            const uint64_t rows = (markers[(size_t)k] + 1u) * rpi;
+            if (rows >= my - row0)
+                return KPEG_ERR_STREAM; // more restart intervals than the frame has rows for
+            row0 += (uint32_t)rows;
         }
     }
+    out_row[parts] = my;
+    return KPEG_OK;
+}
+
+namespace {
+
+// Cut `scan` into one band per device; images without usable restart markers become one band on devices[0].
+// Scans of 1 MB and more with a restart interval of whole MCU rows are cut at BYTE positions and the restart intervals
+// of every band are counted by one host thread per band (kpeg_split_restart_bands_by_bytes); otherwise the cut points
+// are found at given rows by ONE walk over all markers (kpeg_split_restart_bands: 12 ms for the 96 MB of a 16384x16384
+// image, several times what a band then takes on its GPU).
+int make_bands(const int *devices, int ndev, const kpeg_plan *plan, const uint8_t *scan, size_t len, std::vector<BandJob> &jobs)
+{
     std::vector<uint64_t> b0((size_t)ndev), b1((size_t)ndev);
     std::vector<uint32_t> row((size_t)ndev + 1);
     int parts = ndev;
-    int rc = ndev > 1 ? kpeg_split_restart_bands(scan, len, plan, ndev, b0.data(), b1.data(), row.data()) : KPEG_ERR_UNSUPPORTED;
+    int rc = KPEG_ERR_UNSUPPORTED;
+    if (ndev > 1 && len >= ((size_t)1 << 20))
+        rc = kpeg_split_restart_bands_by_bytes(scan, len, plan, ndev, b0.data(), b1.data(), row.data());
+    if (rc == KPEG_ERR_UNSUPPORTED && ndev > 1)
+        rc = kpeg_split_restart_bands(scan, len, plan, ndev, b0.data(), b1.data(), row.data());
     if (rc == KPEG_ERR_STREAM)
         return rc;
     if (rc != KPEG_OK) { // no restart interval that lines up with MCU rows: the image does not shard ("replicas only")

@@ -31,15 +31,18 @@ class Band:
     rows: int           # pixel rows in the band
 
 
-def split_restart_bands(plan: Plan, scan: np.ndarray, parts: int) -> list[Band]:
+def split_restart_bands(plan: Plan, scan: np.ndarray, parts: int, by_bytes: bool = False) -> list[Band]:
+    """by_bytes: cut at byte positions (kpeg_split_restart_bands_by_bytes: the bands' heights follow from their restart
+    marker counts) instead of at balanced rows (kpeg_split_restart_bands: one walk over all markers of the scan)."""
     lib = load_cuda_library()
     scan = np.ascontiguousarray(scan, dtype=np.uint8)
     ob = (C.c_uint64 * parts)()
     oe = (C.c_uint64 * parts)()
     orow = (C.c_uint32 * (parts + 1))()
-    rc = lib.kpeg_split_restart_bands(scan.ctypes.data, scan.size, C.byref(plan), parts, ob, oe, orow)
+    fn = lib.kpeg_split_restart_bands_by_bytes if by_bytes else lib.kpeg_split_restart_bands
+    rc = fn(scan.ctypes.data, scan.size, C.byref(plan), parts, ob, oe, orow)
     if rc != KPEG_OK:
-        raise KpegError(rc, "kpeg_split_restart_bands")
+        raise KpegError(rc, "kpeg_split_restart_bands_by_bytes" if by_bytes else "kpeg_split_restart_bands")
     bands = []
     for b in range(parts):
         r0, r1 = min(orow[b] * 8, plan.height), min(orow[b + 1] * 8, plan.height)

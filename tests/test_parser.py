@@ -223,3 +223,37 @@ def test_end_of_a_large_scan_is_found_by_the_parallel_walk():
         _, o2, n2 = K.parse_jfif(file)
         # the sequential definition, restricted to the bytes before e (nothing there may terminate the scan)
         assert o2 == off and n2 == e, f"end at {e}: found {n2}"
+
+
+def test_bands_cut_at_byte_positions_decode_to_the_same_frame():
+    """kpeg_split_restart_bands_by_bytes: every band begins right after a restart marker, its rows are (markers inside
+    it + 1) x rows per interval, the bands tile the frame -- and, decoded one by one (by the CPU single-stepper here, by
+    the GPUs in tests/test_gpu_multi.py), they give the rows of the whole image."""
+    from libkpeg_b200.shard import split_restart_bands
+    from libkpeg_b200.synth import EMIT_RESTART, QUIRK_FREE, SynthParams, synth_encode
+    for (w, h, ri_rows, parts) in [(256, 200, 1, 3), (128, 320, 2, 4), (64, 64, 1, 2)]:
+        jpg = synth_encode(SynthParams(w, h, quality=85, restart_interval=(w // 8) * ri_rows, flags=QUIRK_FREE | EMIT_RESTART, seed=w + h)).tobytes()
+        plan, off, n = K.parse_jfif(jpg)
+        scan = np.frombuffer(jpg, dtype=np.uint8)[off:off + n]
+        bands = split_restart_bands(plan, scan, parts, by_bytes=True)
+        assert len(bands) == parts and bands[0].row0 == 0 and sum(b.rows for b in bands) == h
+        whole = H.oracle_decode(jpg, parity=True)["pixels"]
+        at = off
+        for k, b in enumerate(bands):
+            start = b.scan.ctypes.data - scan.ctypes.data
+            if k:
+                assert scan[start - 2] == 0xFF and 0xD0 <= scan[start - 1] <= 0xD7  # begins right after a marker
+                assert start >= n * k // parts                                          # ... at or after k / parts of the scan
+            body = bytes(b.scan)
+            markers = sum(1 for i in range(len(body) - 1) if body[i] == 0xFF and 0xD0 <= body[i + 1] <= 0xD7)
+            assert b.row0 % 8 == 0 and (b.rows == (markers + 1) * 8 * ri_rows or k == parts - 1)
+            plan_b = b.plan
+            plan_b.flags = 1
+            e = H.emu_decode(None, scans=[np.frombuffer(body, dtype=np.uint8)], plan=plan_b)
+            assert e["status"] == 0 and np.array_equal(e["pixels"][0], whole[b.row0:b.row0 + b.rows]), f"band {k}"
+    # a restart interval that is not a whole number of MCU rows, or fewer than two intervals per band: not this splitter's case
+    odd = synth_encode(SynthParams(128, 128, quality=70, restart_interval=5, flags=QUIRK_FREE | EMIT_RESTART, seed=3)).tobytes()
+    plan, off, n = K.parse_jfif(odd)
+    with pytest.raises(K.KpegError) as ex:
+        split_restart_bands(plan, np.frombuffer(odd, dtype=np.uint8)[off:off + n], 2, by_bytes=True)
+    assert ex.value.code == api.KPEG_ERR_UNSUPPORTED
