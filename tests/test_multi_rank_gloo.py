@@ -56,7 +56,8 @@ def _worker(rank, world, port, mode, ret):
             w, h = 96, 136  # 12 x 17 MCUs; one restart interval per MCU row
             jpg = synth_encode(SynthParams(w, h, quality=92, restart_interval=12, flags=QUIRK_FREE | EMIT_RESTART, seed=77))
             plan, off, ln = K.parse_jfif(jpg)
-            bands = split_restart_bands(plan, jpg[off:off + ln], world)
+            # "bands": cut at balanced rows; "bands_by_bytes": cut at byte positions, rows from each band's marker count
+            bands = split_restart_bands(plan, jpg[off:off + ln], world, by_bytes=(mode == "bands_by_bytes"))
             assert sum(b.rows for b in bands) == h and [b.row0 for b in bands] == sorted(b.row0 for b in bands)
             b = bands[rank]
             out = np.zeros((h, w, 3), dtype=np.uint8)
@@ -80,7 +81,7 @@ def _worker(rank, world, port, mode, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,world", [("batch", 2), ("bands", 2), ("bands", 3)])
+@pytest.mark.parametrize("mode,world", [("batch", 2), ("bands", 2), ("bands", 3), ("bands_by_bytes", 2), ("bands_by_bytes", 3)])
 def test_sharded_decode_over_gloo(mode, world):
     port = _free_port()
     mgr = mp.Manager()
