@@ -128,8 +128,8 @@ const char *kpeg_cuda_last_error(const kpeg_ctx *ctx); /* never NULL */
 int kpeg_cuda_device_count(void);
 int kpeg_cuda_set_profiling(kpeg_ctx *ctx, int on);
 /* Tuning knobs of the speculative entropy decode (0 = leave unchanged): bits per subsequence (a power of two, 64..1024,
- * or $KPEG_SUB_BITS; -1 = back to the default: chosen per job, 1024 for streams with long restart segments -- large images
- * without restart markers -- and 512 otherwise) and the number of relay rounds issued up front when the cooperative
+ * or $KPEG_SUB_BITS; -1 = back to the default: chosen per job, 1024 for streams with long restart segments AND long blocks --
+ * large high-quality images without restart markers -- and 512 otherwise) and the number of relay rounds issued up front when the cooperative
  * loop is unavailable (>= 2; default 8 or $KPEG_RELAY_ROUNDS; more are added automatically when needed). */
 int kpeg_cuda_set_tuning(kpeg_ctx *ctx, int sub_bits, int relay_rounds);
 /* The CUDA stream (cudaStream_t) all of this context's work is issued on. */

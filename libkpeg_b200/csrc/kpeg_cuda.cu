@@ -94,7 +94,7 @@ struct kpeg_ctx {
     bool profiling = false;
     uint32_t sub_bits = 512;
     // no size asked for (set_tuning / KPEG_SUB_BITS): 1024 bits for streams whose restart segments are long (>= 4 Mbit on
-    // average: large images without restart markers -- the relay then converges in two rounds instead of five and the
+    // average: large images without restart markers) and whose blocks are long (>= 96 bits on average: high quality) -- the relay then converges in two rounds instead of five and the
     // cooperative loop, which holds SM slots while it waits out one serial subsequence decode per round, is a third as
     // long: +3 % on the 4K workload), 512 otherwise (segment boundaries are synchronisation points: 512 is 10-17 % faster
     // on the 512x512 batch and on the image with a restart interval per MCU row)
@@ -411,7 +411,12 @@ int job_enqueue(kpeg_ctx *ctx, int li, const kpeg_plan *pl, const uint8_t *d_sca
     uint32_t sub_bits = ctx->sub_bits;
     if (ctx->sub_bits_auto) {
         const uint64_t segs = (uint64_t)nimages * (pl->restart_interval ? ((uint64_t)((pl->width + 7u) / 8u) * ((pl->height + 7u) / 8u) + pl->restart_interval - 1u) / pl->restart_interval : 1u);
-        sub_bits = (uint64_t)scan_len * 8u >= segs * ((uint64_t)4 << 20) ? 1024u : 512u;
+        // ... and whose blocks are long (>= 96 bits on average, i.e. high quality settings): streams of short blocks
+        // re-synchronise within a few hundred bits, their relay needs one or two rounds at 512 bits already (4K q50:
+        // 145 Gpixel/s at 512 bits, 139 at 1024; 1080p q90: equal; 4K q95: 80 vs 87)
+        const uint64_t blocks = (uint64_t)nimages * ((pl->width + 7u) / 8u) * ((pl->height + 7u) / 8u) * pl->ncomp;
+        const uint64_t bits = (uint64_t)scan_len * 8u;
+        sub_bits = (bits >= segs * ((uint64_t)4 << 20) && bits >= blocks * 96u) ? 1024u : 512u;
     }
     int rc = make_job_geom(pl, nimages, sub_bits, &g, &why);
     if (rc != KPEG_OK)
