@@ -269,6 +269,26 @@ KPEG_HD int32_t float_bits(float x)
 #endif
 }
 
+// (double)f for f zero or normal, by integer arithmetic: sign | (exponent + 896) << 20 | mantissa >> 3 in the high
+// word, the low three mantissa bits on top of the low word.  The hardware conversion (F2F.F64.F32) runs on the
+// quarter-rate XU pipe, and the exact re-evaluation of a sample (idct_patch_kernel, k3_fused.cu) does two of them per
+// term of its 64-term chain: 128 of its 193 conversions per sample.  Denormal inputs cannot occur there: a term is
+// cc * F with F an integer (|t| >= 0.49 or 0), and the float accumulator holds 0 or a residue of such terms (>= 2^-53
+// times their size), never a value below 2^-126.  Checked against the cast in tests/test_emu_logic.py.
+KPEG_HD double widen_f32(float f)
+{
+    const uint32_t b = (uint32_t)float_bits(f), a = b & 0x7FFFFFFFu;
+    const uint32_t hi = (b & 0x80000000u) | (a ? (a >> 3) + 0x38000000u : 0u), lo = b << 29;
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double((int)hi, (int)lo);
+#else
+    const uint64_t u = ((uint64_t)hi << 32) | lo;
+    double d;
+    memcpy(&d, &u, 8);
+    return d;
+#endif
+}
+
 KPEG_HD bool ycc_to_rgb_fast(float y, float cb, float cr, int &R, int &G, int &B)
 {
     const float yr = y + 127.501f; // +128 level shift, +0.001 bias, -0.5 (floor by rint)

@@ -42,6 +42,10 @@ struct NatZz {
     static constexpr int value = make_zigzag_tables().nat2zz[NAT];
 };
 
+#ifndef KPEG_EXACT_WIDEN_INT
+#define KPEG_EXACT_WIDEN_INT 0 // 1: the exact evaluation widens float -> double by integer arithmetic (idct_core.h widen_f32) instead of F2F
+#endif
+
 #ifndef KPEG_IDCT_MIN_CTAS
 #define KPEG_IDCT_MIN_CTAS 8
 #endif
@@ -433,8 +437,13 @@ __device__ __forceinline__ float exact_terms(const uint4 (&ch)[8], const int32_t
         const int F = chunk_coef_int<zi>(ch) * __ldg(q + zi);                           // MCU.cpp:110-112, :115-120
         const float cc = (u == 0 && v == 0) ? c00 : ((u == 0 || v == 0) ? c01 : 1.0f); // Cu * Cv
         const float t = mul_f32(cc, (float)F);
+#if KPEG_EXACT_WIDEN_INT
+        const double d = mul_f64(mul_f64(widen_f32(t), cx[u]), cy[v]);
+        sum = (float)add_f64(widen_f32(sum), d); // float accumulator, rounded every term
+#else
         const double d = mul_f64(mul_f64((double)t, cx[u]), cy[v]);
         sum = (float)add_f64((double)sum, d); // float accumulator, rounded every term
+#endif
     };
     (term(std::integral_constant<int, Ns>{}), ...);
     return sum;

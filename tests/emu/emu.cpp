@@ -383,6 +383,13 @@ int emu_decode(const uint8_t *scan, size_t scan_len, const kpeg_plan *plan, uint
     return KPEG_OK;
 }
 
+// idct_core.h widen_f32 on an array (tests: must equal the cast for zero and normal floats)
+void emu_widen_f32(const float *in, double *out, size_t n)
+{
+    for (size_t i = 0; i < n; ++i)
+        out[i] = widen_f32(in[i]);
+}
+
 // Two-tier colour conversion of one pixel (unshifted samples).  Returns 1 if the exact path ran.
 int emu_colour(int y, int cb, int cr, int rgb[3])
 {

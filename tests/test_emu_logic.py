@@ -207,3 +207,26 @@ def test_pair_order_quantiser_tables(lena_jpg):
         for j in range(64):
             assert qpair[c, j] == qscale[c, nat2zz[int(pn[j])]]
             assert qdc[c, j] == (qpair[c, j] if pn[j] == 0 else 0.0)
+
+
+def test_float_to_double_by_integer_arithmetic():
+    """widen_f32 (idct_core.h), which the exact sample evaluation can use instead of the hardware conversion
+    (-DKPEG_EXACT_WIDEN_INT=1): equal to the cast for +-0 and every normal float -- random bit patterns, the extremes,
+    integers times the reference's float scale factors (the only operands it ever sees)."""
+    import ctypes as C
+    lib = H.emu()
+    lib.emu_widen_f32.restype = None
+    lib.emu_widen_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    rng = np.random.default_rng(9)
+    bits = rng.integers(0, 2 ** 32, size=2_000_000, dtype=np.uint64).astype(np.uint32)
+    exp = (bits >> 23) & 0xFF
+    bits = bits[(exp != 0) & (exp != 255)]  # normal floats
+    f = np.concatenate([bits.view(np.float32),
+                        np.array([0.0, -0.0, np.finfo(np.float32).tiny, -np.finfo(np.float32).tiny, np.finfo(np.float32).max,
+                                  -np.finfo(np.float32).max, 1.0, -1.0, 0.49999997, 0.70710677], dtype=np.float32),
+                        (np.arange(-70000, 70000, dtype=np.float32) * np.float32(0.70710677)),
+                        (np.arange(-70000, 70000, dtype=np.float32) * np.float32(0.49999997))])
+    f = np.ascontiguousarray(f, dtype=np.float32)
+    out = np.empty(f.size, dtype=np.float64)
+    lib.emu_widen_f32(f.ctypes.data, out.ctypes.data, f.size)
+    assert np.array_equal(out.view(np.uint64), f.astype(np.float64).view(np.uint64))
