@@ -42,6 +42,10 @@ struct NatZz {
     static constexpr int value = make_zigzag_tables().nat2zz[NAT];
 };
 
+#ifndef KPEG_EXACT_SKIP_ZERO
+#define KPEG_EXACT_SKIP_ZERO 1 // the exact evaluation skips the accumulation of zero terms (same bits, shorter dependent chain)
+#endif
+
 #ifndef KPEG_EXACT_WIDEN_INT
 #define KPEG_EXACT_WIDEN_INT 0 // 1: the exact evaluation widens float -> double by integer arithmetic (idct_core.h widen_f32) instead of F2F
 #endif
@@ -442,7 +446,15 @@ __device__ __forceinline__ float exact_terms(const uint4 (&ch)[8], const int32_t
         sum = (float)add_f64(widen_f32(sum), d); // float accumulator, rounded every term
 #else
         const double d = mul_f64(mul_f64((double)t, cx[u]), cy[v]);
+#if KPEG_EXACT_SKIP_ZERO
+        // a zero coefficient contributes +-0, which leaves the float accumulator unchanged: the add is predicated off,
+        // so the lane's dependent chain is as long as its block has non-zero coefficients, not 64 terms (the kernel is
+        // bound by the latency of that chain; at low quality settings the tied samples sit in blocks with a handful)
+        if (F != 0)
+            sum = (float)add_f64((double)sum, d);
+#else
         sum = (float)add_f64((double)sum, d); // float accumulator, rounded every term
+#endif
 #endif
     };
     (term(std::integral_constant<int, Ns>{}), ...);
